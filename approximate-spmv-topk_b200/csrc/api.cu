@@ -1,0 +1,547 @@
+// api.cu -- C ABI of libtopkspmv.so (see include/topkspmv.h), float CSR path and dispatch.
+#include <chrono>
+#include <cstring>
+
+#include "csr_build.cuh"
+#include "csr_topk.cuh"
+#include "handle.hpp"
+
+using namespace tks;
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+constexpr uint32_t kKMax = 1024;
+const int kCaps[4] = {256, 512, 1024, 2048};
+const int kCapThreads[4] = {512, 512, 512, 256};
+
+int cap_variant_for_k(uint32_t k) {
+    if (k <= 128) return 0;
+    if (k <= 384) return 1;
+    if (k <= 896) return 2;
+    return 3;
+}
+
+size_t main_smem_bytes(uint32_t cols, int variant) {
+    return ((cols * 4u + 15u) & ~15u) + (size_t)(kCapThreads[variant] / 32) * kCaps[variant] * 8u;
+}
+
+template <int CAP>
+cudaError_t prep_main(Handle *h, int variant) {
+    size_t smem = main_smem_bytes(h->cfg.max_cols, variant);
+    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP>, kCapThreads[variant],
+                                                      smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    h->main_grid[variant] = per_sm * h->num_sms;
+    return cudaSuccess;
+}
+
+template <int CAP>
+void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, RunState *st, uint32_t k,
+                 cudaStream_t s) {
+    size_t smem = main_smem_bytes(m.cols, variant);
+    csr_topk_main_kernel<CAP><<<h->main_grid[variant], kCapThreads[variant], smem, s>>>(
+        m, x, st, h->d_pool, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX);
+}
+
+__global__ void widen_u32_to_u64_kernel(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+uint64_t max_pool_keys(const Handle *h) {
+    uint64_t best = 0;
+    for (int v = 0; v < 4; v++) {
+        uint64_t n = (uint64_t)h->main_grid[v] * (kCapThreads[v] / 32) * kCaps[v];
+        if (n > best) best = n;
+    }
+    return best;
+}
+
+int alloc_query_side(Handle *h) {
+    const uint32_t mb = (uint32_t)h->cfg.max_batch;
+    h->kmax = kKMax;
+    TKS_CUDA(h, cudaMalloc(&h->d_x, (size_t)mb * h->cfg.max_cols * sizeof(float)));
+    TKS_CUDA(h, cudaMalloc(&h->d_state, mb * sizeof(RunState)));
+    TKS_CUDA(h, cudaMemset(h->d_state, 0, mb * sizeof(RunState)));
+    h->pool_cap = max_pool_keys(h);
+    TKS_CUDA(h, cudaMalloc(&h->d_pool, h->pool_cap * sizeof(uint64_t)));
+    h->n_sample_cap = 2048;
+    TKS_CUDA(h, cudaMalloc(&h->d_sample_keys, h->n_sample_cap * sizeof(uint32_t)));
+    TKS_CUDA(h, cudaMalloc(&h->d_res_keys, (size_t)mb * h->kmax * sizeof(uint64_t)));
+    TKS_CUDA(h, cudaMalloc(&h->d_res_idx, (size_t)mb * h->kmax * sizeof(uint32_t)));
+    TKS_CUDA(h, cudaMalloc(&h->d_res_val, (size_t)mb * h->kmax * sizeof(float)));
+    TKS_CUDA(h, cudaMalloc(&h->d_res_count, mb * sizeof(uint32_t)));
+    TKS_CUDA(h, cudaMemset(h->d_res_count, 0, mb * sizeof(uint32_t)));
+    TKS_CUDA(h, cudaMallocHost(&h->h_res_idx, (size_t)mb * h->kmax * sizeof(uint32_t)));
+    TKS_CUDA(h, cudaMallocHost(&h->h_res_val, (size_t)mb * h->kmax * sizeof(float)));
+    TKS_CUDA(h, cudaMallocHost(&h->h_res_count, mb * sizeof(uint32_t)));
+    TKS_CUDA(h, cudaMallocHost(&h->h_x, (size_t)mb * h->cfg.max_cols * sizeof(float)));
+    return TKS_OK;
+}
+
+void free_matrix(Handle *h) {
+    cudaFree(h->d_val); h->d_val = nullptr;
+    cudaFree(h->d_colf); h->d_colf = nullptr;
+    cudaFree(h->d_ptr64); h->d_ptr64 = nullptr;
+    cudaFree(h->d_chunk_start); h->d_chunk_start = nullptr;
+    cudaFree(h->d_chunk_rb); h->d_chunk_rb = nullptr;
+    h->have_matrix = false;
+}
+
+// Build colf + chunk table from a device CSR.  d_val_src may alias nothing we own; it is copied.
+template <typename P>
+int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, const P *d_ptr,
+                          const uint32_t *d_idx, const float *d_val_src, float *d_val_adopt) {
+    cudaStream_t s = h->stream;
+    const size_t pad = 1024;   // over-read slack of the 128-bit streaming loads (zero filled)
+    h->chunk_nnz = h->cfg.chunk_nnz > 0 ? (uint32_t)h->cfg.chunk_nnz : 2048u;
+    h->chunk_nnz = (h->chunk_nnz + kElemsPerIter - 1) / kElemsPerIter * kElemsPerIter;
+    uint64_t nch = (nnz + h->chunk_nnz - 1) / h->chunk_nnz;
+    if (nch == 0) nch = 1;
+    if (nch > 0xFFFFFFF0ull) return h->fail(TKS_EINVAL, "too many chunks (%llu)", (unsigned long long)nch);
+    h->n_chunks = (uint32_t)nch;
+
+    if (d_val_adopt) {
+        h->d_val = d_val_adopt;
+    } else {
+        TKS_CUDA(h, cudaMalloc(&h->d_val, nnz * sizeof(float) + pad));
+        TKS_CUDA(h, cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_val) + nnz * sizeof(float), 0, pad, s));
+        TKS_CUDA(h, cudaMemcpyAsync(h->d_val, d_val_src, nnz * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    TKS_CUDA(h, cudaMalloc(&h->d_colf, nnz * sizeof(uint32_t) + pad));
+    TKS_CUDA(h, cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_colf) + nnz * sizeof(uint32_t), 0, pad, s));
+    TKS_CUDA(h, cudaMalloc(&h->d_chunk_start, (nch + 1) * sizeof(uint64_t)));
+    TKS_CUDA(h, cudaMalloc(&h->d_chunk_rb, nch * sizeof(uint32_t)));
+    uint32_t *d_err = nullptr;
+    TKS_CUDA(h, cudaMalloc(&d_err, sizeof(uint32_t)));
+    TKS_CUDA(h, cudaMemsetAsync(d_err, 0, sizeof(uint32_t), s));
+
+    if (nnz > 0) {
+        csr_copy_cols_kernel<P><<<h->num_sms * 8, 256, 0, s>>>(d_idx, nnz, cols, h->d_colf, d_err);
+        const uint32_t rb = (uint32_t)((rows + 255) / 256);
+        csr_mark_rows_kernel<P><<<rb, 256, 0, s>>>(d_ptr, rows, nnz, h->d_colf, d_err);
+    }
+    csr_chunk_table_kernel<P><<<(uint32_t)((nch + 1 + 127) / 128), 128, 0, s>>>(
+        d_ptr, rows, nnz, h->chunk_nnz, h->n_chunks, h->d_chunk_start, h->d_chunk_rb);
+    uint32_t herr = 0;
+    TKS_CUDA(h, cudaMemcpyAsync(&herr, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    TKS_CUDA(h, cudaStreamSynchronize(s));
+    TKS_CUDA(h, cudaGetLastError());
+    cudaFree(d_err);
+    if (herr) {
+        free_matrix(h);
+        return h->fail(TKS_EINVAL, "invalid CSR:%s%s%s", (herr & kErrColRange) ? " column index >= cols;" : "",
+                       (herr & kErrDelta) ? " too many consecutive empty rows;" : "",
+                       (herr & kErrPtrOrder) ? " row_ptr not monotone / out of range;" : "");
+    }
+    h->rows = rows; h->cols = cols; h->nnz = nnz;
+    h->device_bytes = nnz * 8ull + (nch + 1) * 8ull + nch * 4ull;
+    h->have_matrix = true;
+    h->have_result = false;
+    // bytes = nnz*(4+4) + (N+1)*sizeof(rowptr) + C*4 + k*8 ; k added at run time
+    h->stats.rows = rows; h->stats.cols = cols; h->stats.nnz = nnz; h->stats.packets = 0;
+    h->stats.device_bytes = h->device_bytes;
+    return TKS_OK;
+}
+
+int check_float_upload(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, uint64_t row_offset) {
+    if (h->cfg.mode != TKS_MODE_FLOAT_CSR) return h->fail(TKS_ESTATE, "handle is not in FLOAT_CSR mode");
+    if (cols == 0 || cols > (uint32_t)h->cfg.max_cols)
+        return h->fail(TKS_EINVAL, "cols=%u outside 1..max_cols=%d", cols, h->cfg.max_cols);
+    if (rows + row_offset > 0xFFFFFFFFull) return h->fail(TKS_EINVAL, "row ids exceed 32 bits");
+    (void)nnz;
+    return TKS_OK;
+}
+
+int launch_float(Handle *h, uint32_t k, cudaStream_t s) {
+    if (!h->have_matrix) return h->fail(TKS_ESTATE, "no matrix uploaded");
+    if (!h->have_query) return h->fail(TKS_ESTATE, "no query set");
+    if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k=%u outside 1..%u", k, h->kmax);
+    const int variant = cap_variant_for_k(k);
+    const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
+    CsrDevice m{h->d_val, h->d_colf, h->d_chunk_start, h->d_chunk_rb, h->n_chunks, h->cols,
+                (uint32_t)h->row_offset};
+    uint32_t n_sample = h->n_chunks < (uint32_t)h->num_sms * 8u ? h->n_chunks : (uint32_t)h->num_sms * 8u;
+    if (n_sample > h->n_sample_cap) n_sample = h->n_sample_cap;
+    const uint32_t stride = h->n_chunks / n_sample;
+    uint32_t n2 = 1;
+    while (n2 < n_sample) n2 <<= 1;
+    size_t sample_smem = (size_t)h->cols * 4u;
+    if (sample_smem < (size_t)n2 * 8u) sample_smem = (size_t)n2 * 8u;
+    for (uint32_t q = 0; q < h->batch; q++) {
+        const float *x = h->d_x + (size_t)q * h->cols;
+        RunState *st = h->d_state + q;
+        const uint32_t sgrid = (n_sample * kWarp + kSampleThreads - 1) / kSampleThreads;
+        csr_sample_kernel<<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride,
+                                                                     k);
+        switch (variant) {
+            case 0: launch_main<256>(h, 0, m, x, st, k, s); break;
+            case 1: launch_main<512>(h, 1, m, x, st, k, s); break;
+            case 2: launch_main<1024>(h, 2, m, x, st, k, s); break;
+            default: launch_main<2048>(h, 3, m, x, st, k, s); break;
+        }
+        select_topk_kernel<<<1, kSelectThreads, kSelectSortCap * 8u, s>>>(
+            h->d_pool, &st->pool_count, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
+            h->d_res_idx + (size_t)q * h->kmax, h->d_res_val + (size_t)q * h->kmax, h->d_res_count + q, st);
+    }
+    TKS_CUDA(h, cudaGetLastError());
+    h->last_k = k;
+    h->stats.launches_per_run = 3 * h->batch;
+    h->stats.algorithmic_bytes =
+        h->nnz * 8ull + (h->rows + 1) * (h->nnz > 0xFFFFFFFFull ? 8ull : 4ull) + (uint64_t)h->cols * 4ull + k * 8ull;
+    return TKS_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+
+extern "C" {
+
+int tks_version(void) { return TKS_VERSION; }
+
+int tks_default_config(tks_config *cfg) {
+    if (!cfg) return TKS_EINVAL;
+    std::memset(cfg, 0, sizeof *cfg);
+    cfg->mode = TKS_MODE_FLOAT_CSR;
+    cfg->fixed_width = 20;            // the paper's headline design (BASELINE config 3); types.hpp:20 ships 32
+    cfg->partitions = 32;             // types.hpp:36
+    cfg->local_k = 8;                 // types.hpp:51
+    cfg->limited_finished_rows = 4;   // types.hpp:77
+    cfg->max_cols = 1024;             // types.hpp:55
+    cfg->tie_break = TKS_TIE_LOWER_INDEX;
+    cfg->device = 0;
+    cfg->max_batch = 1;
+    cfg->chunk_nnz = 0;
+    return TKS_OK;
+}
+
+const char *tks_last_error(const tks_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int tks_create(const tks_config *cfg, tks_handle **out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return TKS_EINVAL; }
+    *out = nullptr;
+    if (cfg->mode != TKS_MODE_FLOAT_CSR && cfg->mode != TKS_MODE_FIXED_BSCSR) {
+        g_create_error = "unknown mode"; return TKS_EINVAL;
+    }
+    if (cfg->max_cols < 1 || cfg->max_cols > (int)(kColMask + 1)) {
+        g_create_error = "max_cols outside 1..16384"; return TKS_EINVAL;
+    }
+    if (cfg->mode == TKS_MODE_FIXED_BSCSR) {
+        if (cfg->fixed_width < 17 || cfg->fixed_width > 32) { g_create_error = "fixed_width outside 17..32"; return TKS_EINVAL; }
+        if (cfg->max_cols > 1024) { g_create_error = "BS-CSR column field is 10 bits: max_cols <= 1024"; return TKS_EINVAL; }
+        const int B = tks_bscsr_packet_size(cfg->fixed_width);
+        if (cfg->limited_finished_rows < 1 || cfg->limited_finished_rows > B || cfg->limited_finished_rows > 16) {
+            g_create_error = "limited_finished_rows outside 1..min(B,16)"; return TKS_EINVAL;
+        }
+        if (cfg->local_k < 1 || cfg->local_k > 64) { g_create_error = "local_k outside 1..64"; return TKS_EINVAL; }
+        if (cfg->partitions < 1 || cfg->partitions > 4096) { g_create_error = "partitions outside 1..4096"; return TKS_EINVAL; }
+    }
+    if (cfg->max_batch < 1 || cfg->max_batch > 1024) { g_create_error = "max_batch outside 1..1024"; return TKS_EINVAL; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return TKS_ECUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return TKS_EINVAL; }
+    tks_handle *h = new (std::nothrow) tks_handle();
+    if (!h) { g_create_error = "out of memory"; return TKS_ENOMEM; }
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    auto bail = [&](const char *what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        tks_destroy(h);
+        return TKS_ECUDA;
+    };
+    if ((e = cudaSetDevice(h->device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (prop.major < 10) {
+        g_create_error = "device is not sm_100-class (this library is built for sm_100a only)";
+        tks_destroy(h);
+        return TKS_ECUDA;
+    }
+    h->num_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if (cfg->mode == TKS_MODE_FLOAT_CSR) {
+        if ((e = prep_main<256>(h, 0)) != cudaSuccess) return bail("prep_main<256>", e);
+        if ((e = prep_main<512>(h, 1)) != cudaSuccess) return bail("prep_main<512>", e);
+        if ((e = prep_main<1024>(h, 2)) != cudaSuccess) return bail("prep_main<1024>", e);
+        if ((e = prep_main<2048>(h, 3)) != cudaSuccess) return bail("prep_main<2048>", e);
+        if ((e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kSelectSortCap * 8u))) != cudaSuccess)
+            return bail("select smem attr", e);
+        int rc = alloc_query_side(h);
+        if (rc != TKS_OK) { g_create_error = h->err; tks_destroy(h); return rc; }
+    }
+    *out = h;
+    return TKS_OK;
+}
+
+void tks_destroy(tks_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    free_matrix(h);
+    bscsr_destroy(h);
+    cudaFree(h->d_x); cudaFree(h->d_state); cudaFree(h->d_pool); cudaFree(h->d_sample_keys);
+    cudaFree(h->d_res_keys); cudaFree(h->d_res_idx); cudaFree(h->d_res_val); cudaFree(h->d_res_count);
+    cudaFreeHost(h->h_res_idx); cudaFreeHost(h->h_res_val); cudaFreeHost(h->h_res_count); cudaFreeHost(h->h_x);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int tks_upload_csr_device(tks_handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, const void *d_ptr,
+                          int ptr_bits, const uint32_t *d_idx, const float *d_val, uint64_t row_offset) {
+    if (!h) return TKS_EINVAL;
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    int rc = check_float_upload(h, rows, cols, nnz, row_offset);
+    if (rc) return rc;
+    if (ptr_bits != 32 && ptr_bits != 64) return h->fail(TKS_EINVAL, "ptr_bits must be 32 or 64");
+    if (!d_ptr || (nnz && (!d_idx || !d_val))) return h->fail(TKS_EINVAL, "null array");
+    free_matrix(h);
+    h->row_offset = row_offset;
+    // keep a 64-bit copy of row_ptr for tks_download_csr
+    TKS_CUDA(h, cudaMalloc(&h->d_ptr64, (rows + 1) * sizeof(uint64_t)));
+    if (ptr_bits == 64) {
+        TKS_CUDA(h, cudaMemcpyAsync(h->d_ptr64, d_ptr, (rows + 1) * 8, cudaMemcpyDeviceToDevice, h->stream));
+        return build_from_device_csr<uint64_t>(h, rows, cols, nnz, (const uint64_t *)d_ptr, d_idx, d_val, nullptr);
+    }
+    int rc2 = build_from_device_csr<uint32_t>(h, rows, cols, nnz, (const uint32_t *)d_ptr, d_idx, d_val, nullptr);
+    if (rc2) return rc2;
+    widen_u32_to_u64_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>((const uint32_t *)d_ptr, rows + 1, h->d_ptr64);
+    TKS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return TKS_OK;
+}
+
+int tks_upload_csr(tks_handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, const void *ptr, int ptr_bits,
+                   const uint32_t *idx, const float *val, uint64_t row_offset) {
+    if (!h) return TKS_EINVAL;
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    int rc = check_float_upload(h, rows, cols, nnz, row_offset);
+    if (rc) return rc;
+    if (ptr_bits != 32 && ptr_bits != 64) return h->fail(TKS_EINVAL, "ptr_bits must be 32 or 64");
+    if (!ptr || (nnz && (!idx || !val))) return h->fail(TKS_EINVAL, "null array");
+    void *d_ptr = nullptr;
+    uint32_t *d_idx = nullptr;
+    float *d_val = nullptr;
+    const size_t pb = (size_t)(ptr_bits / 8);
+    TKS_CUDA(h, cudaMalloc(&d_ptr, (rows + 1) * pb));
+    TKS_CUDA(h, cudaMalloc(&d_idx, (nnz ? nnz : 1) * sizeof(uint32_t)));
+    TKS_CUDA(h, cudaMalloc(&d_val, (nnz ? nnz : 1) * sizeof(float)));
+    TKS_CUDA(h, cudaMemcpy(d_ptr, ptr, (rows + 1) * pb, cudaMemcpyHostToDevice));
+    if (nnz) {
+        TKS_CUDA(h, cudaMemcpy(d_idx, idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        TKS_CUDA(h, cudaMemcpy(d_val, val, nnz * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    rc = tks_upload_csr_device(h, rows, cols, nnz, d_ptr, ptr_bits, d_idx, d_val, row_offset);
+    cudaFree(d_ptr); cudaFree(d_idx); cudaFree(d_val);
+    return rc;
+}
+
+int tks_generate_synthetic(tks_handle *h, uint64_t rows, uint32_t cols, uint32_t avg_degree, int dist,
+                           uint64_t seed, uint64_t row_offset) {
+    if (!h) return TKS_EINVAL;
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    int rc = check_float_upload(h, rows, cols, 0, row_offset);
+    if (rc) return rc;
+    if (rows == 0 || avg_degree < 2 || avg_degree > 128) return h->fail(TKS_EINVAL, "rows>0, 2<=avg_degree<=128");
+    if (dist != 0 && dist != 1) return h->fail(TKS_EINVAL, "dist: 0 uniform, 1 gamma");
+    free_matrix(h);
+    h->row_offset = row_offset;
+    cudaStream_t s = h->stream;
+    uint32_t *d_deg = nullptr;
+    uint64_t *d_bs = nullptr;
+    const uint32_t nb = (uint32_t)((rows + kScanBlock - 1) / kScanBlock);
+    TKS_CUDA(h, cudaMalloc(&d_deg, rows * sizeof(uint32_t)));
+    TKS_CUDA(h, cudaMalloc(&d_bs, ((size_t)nb + 1) * sizeof(uint64_t)));
+    TKS_CUDA(h, cudaMalloc(&h->d_ptr64, (rows + 1) * sizeof(uint64_t)));
+    synth_degree_kernel<<<(uint32_t)((rows + 255) / 256), 256, 0, s>>>(rows, row_offset, seed, avg_degree, dist, d_deg);
+    scan_block_sums_kernel<<<nb, kScanBlock, 0, s>>>(d_deg, rows, d_bs);
+    scan_block_offsets_kernel<<<1, 32, 0, s>>>(d_bs, nb);
+    scan_finish_kernel<<<nb, kScanBlock, 0, s>>>(d_deg, rows, d_bs, h->d_ptr64);
+    uint64_t nnz = 0;
+    TKS_CUDA(h, cudaMemcpyAsync(&nnz, h->d_ptr64 + rows, 8, cudaMemcpyDeviceToHost, s));
+    TKS_CUDA(h, cudaStreamSynchronize(s));
+    cudaFree(d_deg); cudaFree(d_bs);
+    uint32_t *d_idx = nullptr;
+    float *d_val = nullptr;
+    const size_t pad = 1024;
+    TKS_CUDA(h, cudaMalloc(&d_idx, nnz * sizeof(uint32_t)));
+    TKS_CUDA(h, cudaMalloc(&d_val, nnz * sizeof(float) + pad));
+    TKS_CUDA(h, cudaMemsetAsync(reinterpret_cast<uint8_t *>(d_val) + nnz * sizeof(float), 0, pad, s));
+    synth_fill_kernel<<<(uint32_t)((rows + 127) / 128), 128, 0, s>>>(rows, row_offset, seed, cols, h->d_ptr64, d_idx, d_val);
+    TKS_CUDA(h, cudaGetLastError());
+    rc = build_from_device_csr<uint64_t>(h, rows, cols, nnz, h->d_ptr64, d_idx, nullptr, d_val);
+    cudaFree(d_idx);
+    return rc;
+}
+
+int tks_download_csr(tks_handle *h, uint64_t *ptr64, uint32_t *idx, float *val) {
+    if (!h) return TKS_EINVAL;
+    if (!h->have_matrix || !h->d_ptr64) return h->fail(TKS_ESTATE, "no CSR matrix resident");
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    if (ptr64) TKS_CUDA(h, cudaMemcpy(ptr64, h->d_ptr64, (h->rows + 1) * 8, cudaMemcpyDeviceToHost));
+    if (val) TKS_CUDA(h, cudaMemcpy(val, h->d_val, h->nnz * 4, cudaMemcpyDeviceToHost));
+    if (idx) {
+        TKS_CUDA(h, cudaMemcpy(idx, h->d_colf, h->nnz * 4, cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < h->nnz; i++) idx[i] &= kColMask;
+    }
+    return TKS_OK;
+}
+
+int tks_set_query_device(tks_handle *h, const void *d_vec, uint32_t batch, void *cuda_stream) {
+    if (!h || !d_vec) return TKS_EINVAL;
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) {
+        if (batch != 1) return h->fail(TKS_EINVAL, "BS-CSR mode takes one query at a time");
+        return bscsr_set_query(h, nullptr, (const uint32_t *)d_vec, s);
+    }
+    if (!h->have_matrix) return h->fail(TKS_ESTATE, "no matrix uploaded");
+    if (batch < 1 || batch > (uint32_t)h->cfg.max_batch) return h->fail(TKS_EINVAL, "batch outside 1..max_batch");
+    TKS_CUDA(h, cudaMemcpyAsync(h->d_x, d_vec, (size_t)batch * h->cols * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    h->batch = batch;
+    h->have_query = true;
+    return TKS_OK;
+}
+
+int tks_set_query(tks_handle *h, const void *vec, uint32_t batch) {
+    if (!h || !vec) return TKS_EINVAL;
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) {
+        if (batch != 1) return h->fail(TKS_EINVAL, "BS-CSR mode takes one query at a time");
+        return bscsr_set_query(h, (const uint32_t *)vec, nullptr, h->stream);
+    }
+    if (!h->have_matrix) return h->fail(TKS_ESTATE, "no matrix uploaded");
+    if (batch < 1 || batch > (uint32_t)h->cfg.max_batch) return h->fail(TKS_EINVAL, "batch outside 1..max_batch");
+    const size_t bytes = (size_t)batch * h->cols * sizeof(float);
+    std::memcpy(h->h_x, vec, bytes);
+    TKS_CUDA(h, cudaMemcpyAsync(h->d_x, h->h_x, bytes, cudaMemcpyHostToDevice, h->stream));
+    h->batch = batch;
+    h->have_query = true;
+    return TKS_OK;
+}
+
+int tks_run_async(tks_handle *h, uint32_t k, void *cuda_stream) {
+    if (!h) return TKS_EINVAL;
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) { h->last_k = k; return bscsr_launch(h, s); }
+    return launch_float(h, k, s);
+}
+
+int tks_run(tks_handle *h, uint32_t k, float *kernel_ms, float *total_ms) {
+    if (!h) return TKS_EINVAL;
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    auto t0 = std::chrono::high_resolution_clock::now();
+    TKS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    int rc;
+    if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) { h->last_k = k; rc = bscsr_launch(h, h->stream); }
+    else rc = launch_float(h, k, h->stream);
+    if (rc) return rc;
+    TKS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) {
+        rc = bscsr_fetch(h);
+        if (rc) return rc;
+    } else {
+        const size_t n = (size_t)h->batch * h->kmax;
+        TKS_CUDA(h, cudaMemcpyAsync(h->h_res_idx, h->d_res_idx, n * 4, cudaMemcpyDeviceToHost, h->stream));
+        TKS_CUDA(h, cudaMemcpyAsync(h->h_res_val, h->d_res_val, n * 4, cudaMemcpyDeviceToHost, h->stream));
+        TKS_CUDA(h, cudaMemcpyAsync(h->h_res_count, h->d_res_count, h->batch * 4, cudaMemcpyDeviceToHost, h->stream));
+        TKS_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    float ms = 0.f;
+    TKS_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    auto t1 = std::chrono::high_resolution_clock::now();
+    h->stats.last_kernel_ms = ms;
+    h->stats.last_total_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
+    if (kernel_ms) *kernel_ms = ms;
+    if (total_ms) *total_ms = h->stats.last_total_ms;
+    h->have_result = true;
+    return TKS_OK;
+}
+
+int tks_read_result(tks_handle *h, uint32_t query, uint32_t *idx_out, void *val_out, uint32_t *count) {
+    if (!h || !idx_out || !val_out) return TKS_EINVAL;
+    if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) {
+        if (query != 0) return h->fail(TKS_EINVAL, "BS-CSR mode has a single query");
+        return bscsr_read_result(h, idx_out, (uint32_t *)val_out, h->last_k, count);
+    }
+    if (!h->have_result) {
+        // results of an async run: fetch now
+        if (h->last_k == 0) return h->fail(TKS_ESTATE, "no run yet");
+        TKS_CUDA(h, cudaSetDevice(h->device));
+        const size_t n = (size_t)h->batch * h->kmax;
+        TKS_CUDA(h, cudaDeviceSynchronize());
+        TKS_CUDA(h, cudaMemcpy(h->h_res_idx, h->d_res_idx, n * 4, cudaMemcpyDeviceToHost));
+        TKS_CUDA(h, cudaMemcpy(h->h_res_val, h->d_res_val, n * 4, cudaMemcpyDeviceToHost));
+        TKS_CUDA(h, cudaMemcpy(h->h_res_count, h->d_res_count, h->batch * 4, cudaMemcpyDeviceToHost));
+        h->have_result = true;
+    }
+    if (query >= h->batch) return h->fail(TKS_EINVAL, "query index out of range");
+    const uint32_t k = h->last_k;
+    std::memcpy(idx_out, h->h_res_idx + (size_t)query * h->kmax, k * 4);
+    std::memcpy(val_out, h->h_res_val + (size_t)query * h->kmax, k * 4);
+    if (count) *count = h->h_res_count[query];
+    return TKS_OK;
+}
+
+int tks_read_partition_results(tks_handle *h, uint32_t *idx_words, uint32_t *val_words) {
+    if (!h) return TKS_EINVAL;
+    if (h->cfg.mode != TKS_MODE_FIXED_BSCSR) return h->fail(TKS_ESTATE, "BS-CSR mode only");
+    return bscsr_read_partition_results(h, idx_words, val_words);
+}
+
+int tks_result_keys_device(tks_handle *h, uint32_t query, const uint64_t **d_keys, uint32_t *count) {
+    if (!h || !d_keys) return TKS_EINVAL;
+    if (h->cfg.mode != TKS_MODE_FLOAT_CSR) return h->fail(TKS_ESTATE, "float mode only");
+    if (query >= (uint32_t)h->cfg.max_batch) return h->fail(TKS_EINVAL, "query index out of range");
+    *d_keys = h->d_res_keys + (size_t)query * h->kmax;
+    if (count) *count = h->last_k;
+    return TKS_OK;
+}
+
+int tks_merge_keys_device(tks_handle *h, uint32_t query, const uint64_t *d_keys, uint32_t n_keys, uint32_t k,
+                          void *cuda_stream) {
+    if (!h || !d_keys) return TKS_EINVAL;
+    if (h->cfg.mode != TKS_MODE_FLOAT_CSR) return h->fail(TKS_ESTATE, "float mode only");
+    if (query >= (uint32_t)h->cfg.max_batch) return h->fail(TKS_EINVAL, "query index out of range");
+    if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k out of range");
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    select_topk_kernel<<<1, kSelectThreads, kSelectSortCap * 8u, s>>>(
+        d_keys, nullptr, n_keys, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX, h->d_res_keys + (size_t)query * h->kmax,
+        h->d_res_idx + (size_t)query * h->kmax, h->d_res_val + (size_t)query * h->kmax, h->d_res_count + query,
+        nullptr);
+    TKS_CUDA(h, cudaGetLastError());
+    h->last_k = k;
+    if (h->batch < query + 1) h->batch = query + 1;
+    h->have_result = false;   // tks_read_result will fetch
+    return TKS_OK;
+}
+
+int tks_get_stats(tks_handle *h, tks_stats *out) {
+    if (!h || !out) return TKS_EINVAL;
+    if (h->cfg.mode == TKS_MODE_FLOAT_CSR && h->d_state) {
+        cudaSetDevice(h->device);
+        RunState st{};
+        if (cudaMemcpy(&st, h->d_state, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess)
+            h->stats.last_candidates = st.result_count;
+    }
+    *out = h->stats;
+    return TKS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// handle.hpp -- the object behind tks_handle (one matrix shard on one device).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/topkspmv.h"
+#include "common.cuh"
+
+namespace tks {
+
+struct BscsrState;   // bscsr_api.cu
+struct RunState;     // csr_topk.cuh
+
+struct Handle {
+    tks_config cfg{};
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    // matrix (float CSR mode)
+    bool have_matrix = false;
+    uint64_t rows = 0, nnz = 0, row_offset = 0;
+    uint32_t cols = 0;
+    float *d_val = nullptr;
+    uint32_t *d_colf = nullptr;
+    uint64_t *d_ptr64 = nullptr;        // kept for tks_download_csr (exact copy of row_ptr as u64)
+    uint64_t *d_chunk_start = nullptr;
+    uint32_t *d_chunk_rb = nullptr;
+    uint32_t n_chunks = 0, chunk_nnz = 0;
+    uint64_t device_bytes = 0;
+
+    // query + scratch + results (float mode), sized by max_batch
+    uint32_t batch = 0;                 // queries set by the last tks_set_query
+    bool have_query = false;
+    float *d_x = nullptr;
+    RunState *d_state = nullptr;        // one per query slot
+    uint64_t *d_pool = nullptr;
+    uint64_t pool_cap = 0;
+    uint32_t *d_sample_keys = nullptr;
+    uint32_t n_sample_cap = 0;
+    uint32_t kmax = 0;
+    uint64_t *d_res_keys = nullptr;
+    uint32_t *d_res_idx = nullptr;
+    float *d_res_val = nullptr;
+    uint32_t *d_res_count = nullptr;
+    uint32_t *h_res_idx = nullptr;      // pinned
+    float *h_res_val = nullptr;         // pinned
+    uint32_t *h_res_count = nullptr;    // pinned
+    float *h_x = nullptr;               // pinned staging for tks_set_query
+    uint32_t last_k = 0;
+    bool have_result = false;
+
+    // launch geometry of the main kernel, per CAP variant
+    int main_grid[4] = {0, 0, 0, 0};
+
+    BscsrState *bs = nullptr;
+
+    tks_stats stats{};
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define TKS_CUDA(h, call)                                                                              \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return (h)->fail(TKS_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),       \
+                             __FILE__, __LINE__);                                                      \
+    } while (0)
+
+// bscsr_api.cu
+int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *packets_per_part,
+                 const void *const *packets, const uint32_t *first_row, const uint64_t *nnz_per_part);
+int bscsr_set_query(Handle *h, const uint32_t *vec32_host, const uint32_t *vec32_dev, cudaStream_t s);
+int bscsr_launch(Handle *h, cudaStream_t s);
+int bscsr_fetch(Handle *h);   // D2H of partition result words + host merge
+int bscsr_read_result(Handle *h, uint32_t *idx_out, uint32_t *val_out, uint32_t k, uint32_t *count);
+int bscsr_read_partition_results(Handle *h, uint32_t *idx_words, uint32_t *val_words);
+void bscsr_destroy(Handle *h);
+
+}  // namespace tks
+
+struct tks_handle : tks::Handle {};

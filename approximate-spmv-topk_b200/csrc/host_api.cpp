@@ -1,0 +1,96 @@
+// host_api.cpp -- the CPU-only entry points of include/topkspmv.h: the reference's host surface
+// around the accelerator (MTX loader, COO->CSR, value quantisation, BS-CSR packet builder), exported
+// through the same C ABI so that non-C++ callers (ctypes tests, bench.py) use the very code the
+// host executable uses.  No CUDA here and no top-k computation: nothing in this file is a fallback.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/topkspmv.h"
+#include "../host/bscsr_packer.hpp"
+#include "../host/fixed_point.hpp"
+#include "../host/mtx_reader.hpp"
+
+static thread_local std::string g_host_error;
+
+extern "C" {
+
+const char *tks_host_last_error(void) { return g_host_error.c_str(); }
+
+int tks_bscsr_packet_size(int fixed_width) {
+    if (fixed_width < 1 || fixed_width > 64) return TKS_EINVAL;
+    return tkshost::bscsr_packet_size(fixed_width);
+}
+
+uint32_t tks_fixed32_from_double(double v) { return ufixed32::from_double(v); }
+
+uint32_t tks_fixedW_from_fixed32(uint32_t raw32, int fixed_width) {
+    return tkshost::fixedW_from_fixed32(raw32, fixed_width);
+}
+
+int tks_pack_bscsr(const uint32_t *row, const uint32_t *col, const uint32_t *val32, uint64_t nnz, uint32_t num_rows,
+                   int partitions, int fixed_width, uint64_t *packets_per_part, uint32_t *first_row,
+                   uint64_t *nnz_per_part, void *packets) {
+    if (!row || !col || !val32 || !packets_per_part || !first_row || !nnz_per_part) { g_host_error = "null argument"; return TKS_EINVAL; }
+    if (fixed_width < 17 || fixed_width > 32 || partitions < 1) { g_host_error = "fixed_width outside 17..32 or partitions < 1"; return TKS_EINVAL; }
+    tkshost::BscsrPartitioning part;
+    std::string err;
+    int rc = tkshost::bscsr_partition(row, nnz, num_rows, partitions, fixed_width, part, &err);
+    if (rc != 0) { g_host_error = err; return TKS_EINVAL; }
+    for (int p = 0; p < partitions; p++) {
+        packets_per_part[p] = part.num_packets[p];
+        first_row[p] = part.first_row[p];
+        nnz_per_part[p] = part.nnz_start[p + 1] - part.nnz_start[p];
+    }
+    if (!packets) return TKS_OK;
+    auto *out = static_cast<tkshost::Packet512 *>(packets);
+    uint64_t off = 0;
+    for (int p = 0; p < partitions; p++) {
+        const uint64_t s = part.nnz_start[p];
+        tkshost::bscsr_pack_partition(row + s, col + s, val32 + s, part.nnz_start[p + 1] - s,
+                                      p == 0 ? 0u : part.last_row[p - 1], fixed_width, out + off);
+        off += part.num_packets[p];
+    }
+    return TKS_OK;
+}
+
+int tks_read_mtx(const char *path, int zero_indexed, int sort_tuples, int ignore_values, uint32_t *rows, uint32_t *cols,
+                 uint64_t *nnz, uint64_t nnz_capacity, uint32_t *x, uint32_t *y, double *val) {
+    if (!path || !rows || !cols || !nnz) { g_host_error = "null argument"; return TKS_EINVAL; }
+    static thread_local std::string cached_path;
+    static thread_local std::vector<uint32_t> cx, cy;
+    static thread_local std::vector<double> cv;
+    static thread_local uint32_t crows, ccols;
+    static thread_local int cflags = -1;
+    const int flags = (zero_indexed ? 1 : 0) | (sort_tuples ? 2 : 0) | (ignore_values ? 4 : 0);
+    if (cached_path != path || cflags != flags) {
+        uint32_t r = 0, c = 0, n = 0;
+        std::string err;
+        int rc = tkshost::readMtx<uint32_t, double>(path, &cx, &cy, &cv, &r, &c, &n, 0, !ignore_values, false,
+                                                    zero_indexed != 0, sort_tuples != 0, &err);
+        if (rc != 0) { g_host_error = err; cached_path.clear(); return TKS_EIO; }
+        cached_path = path; cflags = flags; crows = r; ccols = c;
+    }
+    *rows = crows; *cols = ccols; *nnz = cx.size();
+    if (nnz_capacity == 0) return TKS_OK;
+    if (nnz_capacity < cx.size() || !x || !y || !val) { g_host_error = "output buffers too small"; return TKS_EINVAL; }
+    std::memcpy(x, cx.data(), cx.size() * 4);
+    std::memcpy(y, cy.data(), cy.size() * 4);
+    std::memcpy(val, cv.data(), cv.size() * 8);
+    cached_path.clear(); cx.clear(); cx.shrink_to_fit(); cy.clear(); cy.shrink_to_fit(); cv.clear(); cv.shrink_to_fit();
+    return TKS_OK;
+}
+
+int tks_coo2csr(const uint32_t *x, const uint32_t *y, const float *val, uint64_t nnz, uint32_t rows, uint32_t cols,
+                uint32_t *ptr, uint32_t *idx, float *out_val) {
+    if (!x || !y || !val || !ptr || !idx || !out_val) { g_host_error = "null argument"; return TKS_EINVAL; }
+    std::vector<uint32_t> xs(x, x + nnz), ys(y, y + nnz);
+    std::vector<float> vs(val, val + nnz);
+    if (tkshost::coo2csr<uint32_t, float>(ptr, idx, out_val, xs, ys, vs, rows, cols) != 0) {
+        g_host_error = "Error: Index out of bounds!";
+        return TKS_EINVAL;
+    }
+    return TKS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// spmv.hpp -- `struct SpMV`, the accelerator functor every reference main() drives, re-seated on the
+// C ABI of libtopkspmv.so (include/topkspmv.h).  Same four verbs, same argument meaning:
+//   ctor          upload the matrix (and the first query)      host_spmv_bscsr.cpp:104, host_spmv_topk_csr_gpu.cu:95
+//   operator()    run, return elapsed nanoseconds of the kernel host_spmv_bscsr.cpp:323, host_spmv_topk_csr_gpu.cu:171
+//   read_result   sorted (score desc) values and indices        host_spmv_bscsr.cpp:399, host_spmv_topk_csr_gpu.cu:233
+//   reset         upload a new query, return elapsed ns         host_spmv_bscsr.cpp:450, host_spmv_topk_csr_gpu.cu:241
+// Errors: the reference exits; so does this wrapper (message from tks_last_error).
+#pragma once
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../include/topkspmv.h"
+#include "bscsr_packer.hpp"
+#include "fixed_point.hpp"
+#include "types.hpp"
+
+#define TKS_OR_DIE(h, call)                                                             \
+    do {                                                                                \
+        int rc__ = (call);                                                              \
+        if (rc__ != 0) {                                                                \
+            fprintf(stderr, "%s failed (%d): %s\n", #call, rc__, tks_last_error(h));    \
+            exit(EXIT_FAILURE);                                                         \
+        }                                                                               \
+    } while (0)
+
+// Exact fp32 engine: constructor signature of the reference GPU host (CSR arrays + query + k).
+struct SpMV {
+    tks_handle *h = nullptr;
+    int_type num_rows, num_cols, num_nnz;
+    int k;
+    float last_full_ms = 0.f;
+
+    SpMV(int_type *ptr, int_type *idx, float *val, int_type num_rows_, int_type num_cols_, int_type num_nnz_,
+         float *vec, int k_, int device = 0, bool tie_higher = false, int debug = 0)
+        : num_rows(num_rows_), num_cols(num_cols_), num_nnz(num_nnz_), k(k_) {
+        tks_config cfg;
+        tks_default_config(&cfg);
+        cfg.mode = TKS_MODE_FLOAT_CSR;
+        cfg.device = device;
+        cfg.max_cols = num_cols_ > MAX_COLS ? (int)num_cols_ : MAX_COLS;
+        cfg.tie_break = tie_higher ? TKS_TIE_HIGHER_INDEX : TKS_TIE_LOWER_INDEX;
+        TKS_OR_DIE(nullptr, tks_create(&cfg, &h));
+        if (debug) printf("Write inputs into device memory\n");
+        TKS_OR_DIE(h, tks_upload_csr(h, num_rows, num_cols, num_nnz, ptr, 32, idx, val, 0));
+        TKS_OR_DIE(h, tks_set_query(h, vec, 1));
+    }
+    ~SpMV() { tks_destroy(h); }
+    SpMV(const SpMV &) = delete;
+
+    float operator()(int debug) {
+        float kernel_ms = 0.f;
+        TKS_OR_DIE(h, tks_run(h, (uint32_t)k, &kernel_ms, &last_full_ms));
+        if (debug) printf("Kernel terminated\nComputation took %f ms (%f ms with read-back)\n", kernel_ms, last_full_ms);
+        return kernel_ms * 1e6f;
+    }
+    void read_result(std::vector<float> &res, std::vector<int_type> &res_idx, int debug = 0) {
+        (void)debug;
+        res.resize(k); res_idx.resize(k);
+        uint32_t count = 0;
+        TKS_OR_DIE(h, tks_read_result(h, 0, res_idx.data(), res.data(), &count));
+    }
+    long reset(float *vec, int debug) {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        TKS_OR_DIE(h, tks_set_query(h, vec, 1));
+        long ns = (long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::high_resolution_clock::now() - t0).count();
+        if (debug) printf("Reset took %f ms\n", ns / 1e6);
+        return ns;
+    }
+};
+
+// FPGA-semantics engine: constructor signature of the reference FPGA host (COO + fixed-point values).
+struct SpMVFixed {
+    tks_handle *h = nullptr;
+    int_type num_rows, num_cols, num_nnz;
+    int k;
+    int fixed_width, partitions;
+    float last_full_ms = 0.f;
+
+    SpMVFixed(int_type *x, int_type *y, ufixed32 *val, int_type num_rows_, int_type num_cols_, int_type num_nnz_,
+              ufixed32 *vec, int k_, int fixed_width_ = FIXED_WIDTH, int partitions_ = SPMV_PARTITIONS,
+              int local_k = K, int lfr = LIMITED_FINISHED_ROWS, int device = 0, int debug = 0)
+        : num_rows(num_rows_), num_cols(num_cols_), num_nnz(num_nnz_), k(k_), fixed_width(fixed_width_), partitions(partitions_) {
+        tks_config cfg;
+        tks_default_config(&cfg);
+        cfg.mode = TKS_MODE_FIXED_BSCSR;
+        cfg.fixed_width = fixed_width;
+        cfg.partitions = partitions;
+        cfg.local_k = local_k;
+        cfg.limited_finished_rows = lfr;
+        cfg.device = device;
+        cfg.tie_break = TKS_TIE_HIGHER_INDEX;   // sort_tuples order of the reference merge (host:447)
+        TKS_OR_DIE(nullptr, tks_create(&cfg, &h));
+        // packet_coo (host:133-187)
+        static_assert(sizeof(ufixed32) == 4, "ufixed32 must be a bare 32-bit word");
+        std::vector<uint64_t> ppp(partitions), npp(partitions);
+        std::vector<uint32_t> first_row(partitions);
+        TKS_OR_DIE(h, tks_pack_bscsr(x, y, reinterpret_cast<uint32_t *>(val), num_nnz, num_rows, partitions, fixed_width,
+                                     ppp.data(), first_row.data(), npp.data(), nullptr));
+        uint64_t total = 0;
+        for (auto n : ppp) total += n;
+        std::vector<tkshost::Packet512> packets(total);
+        TKS_OR_DIE(h, tks_pack_bscsr(x, y, reinterpret_cast<uint32_t *>(val), num_nnz, num_rows, partitions, fixed_width,
+                                     ppp.data(), first_row.data(), npp.data(), packets.data()));
+        std::vector<const void *> pp(partitions);
+        uint64_t off = 0;
+        for (int p = 0; p < partitions; p++) { pp[p] = packets.data() + off; off += ppp[p]; }
+        if (debug) printf("Write inputs into device memory (%llu packets)\n", (unsigned long long)total);
+        TKS_OR_DIE(h, tks_upload_bscsr(h, num_cols, (uint32_t)partitions, ppp.data(), pp.data(), first_row.data(), npp.data()));
+        TKS_OR_DIE(h, tks_set_query(h, vec, 1));
+    }
+    ~SpMVFixed() { tks_destroy(h); }
+    SpMVFixed(const SpMVFixed &) = delete;
+
+    long operator()(int debug) {
+        float kernel_ms = 0.f;
+        TKS_OR_DIE(h, tks_run(h, (uint32_t)k, &kernel_ms, &last_full_ms));
+        if (debug) printf("Kernel terminated\nComputation took %f ms\n", kernel_ms);
+        return (long)(kernel_ms * 1e6f);
+    }
+    // appends, and may return fewer than k entries, like host_spmv_bscsr.cpp:399-448
+    void read_result(std::vector<ufixed32> &res, std::vector<int_type> &res_idx, int debug = 0) {
+        (void)debug;
+        std::vector<uint32_t> idx(k), val(k);
+        uint32_t count = 0;
+        TKS_OR_DIE(h, tks_read_result(h, 0, idx.data(), val.data(), &count));
+        for (uint32_t i = 0; i < count; i++) { res_idx.push_back(idx[i]); res.push_back(ufixed32::from_raw(val[i])); }
+    }
+    long reset(ufixed32 *vec, int debug) {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        TKS_OR_DIE(h, tks_set_query(h, vec, 1));
+        long ns = (long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::high_resolution_clock::now() - t0).count();
+        if (debug) printf("Reset took %f ms\n", ns / 1e6);
+        return ns;
+    }
+};

@@ -1,0 +1,193 @@
+"""Python mirror of the reference's `struct SpMV` functor over the C ABI.
+
+Same four verbs as src/fpga/src/host_spmv_bscsr.cpp:79-485 and src/gpu/host_spmv_topk_csr_gpu.cu:44-263:
+constructor (upload), __call__ (run, returns kernel nanoseconds), read_result, reset.  All arrays are
+HOST numpy arrays; every call goes through libtopkspmv.so -- there is no NumPy compute path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import _ptr, check
+
+
+class _Base:
+    handle = None
+
+    def _create(self, cfg):
+        L = capi.lib()
+        h = C.c_void_p()
+        rc = L.tks_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise capi.TksError(rc, (L.tks_last_error(None) or b"").decode())
+        self.handle = h
+        self.cfg = cfg
+
+    def close(self):
+        if self.handle is not None:
+            capi.lib().tks_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def stats(self) -> capi.TksStats:
+        st = capi.TksStats()
+        check(capi.lib().tks_get_stats(self.handle, C.byref(st)), self.handle)
+        return st
+
+    def run_timed(self, k=None):
+        """operator() with both timings: (kernel_ms, total_ms)."""
+        k = self.k if k is None else k
+        km, tm = C.c_float(), C.c_float()
+        check(capi.lib().tks_run(self.handle, k, C.byref(km), C.byref(tm)), self.handle)
+        self.k = k
+        return km.value, tm.value
+
+    def __call__(self, debug=0):
+        km, _ = self.run_timed()
+        return km * 1e6
+
+    def run_async(self, k=None, stream=0):
+        k = self.k if k is None else k
+        check(capi.lib().tks_run_async(self.handle, k, C.c_void_p(stream)), self.handle)
+        self.k = k
+
+
+class SpMV(_Base):
+    """Exact fp32 CSR engine (host_spmv_topk_csr_gpu.cu:95 signature: ptr, idx, val, rows, cols, nnz, vec, k)."""
+
+    def __init__(self, ptr=None, idx=None, val=None, num_rows=0, num_cols=0, num_nnz=None, vec=None, k=100,
+                 device=0, tie_higher=False, max_batch=1, max_cols=None, chunk_nnz=0, row_offset=0):
+        cfg = capi.default_config(mode=capi.MODE_FLOAT_CSR, device=device, max_batch=max_batch,
+                                  tie_break=capi.TIE_HIGHER_INDEX if tie_higher else capi.TIE_LOWER_INDEX,
+                                  max_cols=max(1024, int(max_cols or num_cols or 1024)), chunk_nnz=chunk_nnz)
+        self._create(cfg)
+        self.k = k
+        self.num_rows, self.num_cols = int(num_rows), int(num_cols)
+        if ptr is not None:
+            self.upload(ptr, idx, val, num_rows, num_cols, row_offset)
+            if vec is not None:
+                self.reset(vec)
+
+    def upload(self, ptr, idx, val, num_rows, num_cols, row_offset=0):
+        ptr = np.ascontiguousarray(ptr)
+        if ptr.dtype not in (np.uint32, np.uint64):
+            ptr = ptr.astype(np.uint64)
+        idx = np.ascontiguousarray(idx, np.uint32)
+        val = np.ascontiguousarray(val, np.float32)
+        bits = 32 if ptr.dtype == np.uint32 else 64
+        check(capi.lib().tks_upload_csr(self.handle, int(num_rows), int(num_cols), idx.size, _ptr(ptr), bits,
+                                        _ptr(idx), _ptr(val), int(row_offset)), self.handle)
+        self.num_rows, self.num_cols = int(num_rows), int(num_cols)
+
+    def generate_synthetic(self, rows, cols, avg_degree, dist="gamma", seed=0, row_offset=0):
+        d = {"uniform": 0, "gamma": 1}[dist]
+        check(capi.lib().tks_generate_synthetic(self.handle, int(rows), int(cols), int(avg_degree), d, int(seed),
+                                                int(row_offset)), self.handle)
+        self.num_rows, self.num_cols = int(rows), int(cols)
+
+    def download_csr(self):
+        st = self.stats()
+        ptr = np.zeros(st.rows + 1, np.uint64)
+        idx = np.zeros(st.nnz, np.uint32)
+        val = np.zeros(st.nnz, np.float32)
+        check(capi.lib().tks_download_csr(self.handle, _ptr(ptr), _ptr(idx), _ptr(val)), self.handle)
+        return ptr, idx, val
+
+    def reset(self, vec, debug=0):
+        vec = np.ascontiguousarray(vec, np.float32)
+        batch = 1 if vec.ndim == 1 else vec.shape[0]
+        assert vec.shape[-1] == self.num_cols, "query length must equal num_cols"
+        check(capi.lib().tks_set_query(self.handle, _ptr(vec), batch), self.handle)
+        self.batch = batch
+        return 0
+
+    def reset_device(self, dptr, batch=1, stream=0):
+        check(capi.lib().tks_set_query_device(self.handle, C.c_void_p(dptr), batch, C.c_void_p(stream)), self.handle)
+        self.batch = batch
+
+    def read_result(self, query=0):
+        """Returns (values float32[k], indices uint32[k], count)."""
+        idx = np.zeros(self.k, np.uint32)
+        val = np.zeros(self.k, np.float32)
+        cnt = C.c_uint32()
+        check(capi.lib().tks_read_result(self.handle, query, _ptr(idx), _ptr(val), C.byref(cnt)), self.handle)
+        return val, idx, cnt.value
+
+    def result_keys_device(self, query=0):
+        p, n = C.c_void_p(), C.c_uint32()
+        check(capi.lib().tks_result_keys_device(self.handle, query, C.byref(p), C.byref(n)), self.handle)
+        return p.value, n.value
+
+    def merge_keys_device(self, dptr, n_keys, k=None, query=0, stream=0):
+        k = self.k if k is None else k
+        check(capi.lib().tks_merge_keys_device(self.handle, query, C.c_void_p(dptr), n_keys, k, C.c_void_p(stream)),
+              self.handle)
+
+
+class SpMVFixed(_Base):
+    """FPGA-semantics engine (host_spmv_bscsr.cpp:104 signature: x, y, val, rows, cols, nnz, vec).
+
+    x, y: row-sorted COO; val32 / vec32: raw ap_ufixed<32,1> words (real_type_inout)."""
+
+    def __init__(self, x, y, val32, num_rows, num_cols, vec32=None, k=100, fixed_width=20, partitions=32, local_k=8,
+                 limited_finished_rows=4, device=0):
+        cfg = capi.default_config(mode=capi.MODE_FIXED_BSCSR, device=device, fixed_width=fixed_width,
+                                  partitions=partitions, local_k=local_k,
+                                  limited_finished_rows=limited_finished_rows, tie_break=capi.TIE_HIGHER_INDEX)
+        self._create(cfg)
+        self.k = k
+        self.num_rows, self.num_cols = int(num_rows), int(num_cols)
+        self.B = capi.bscsr_packet_size(fixed_width)
+        packets, ppp, first, npp = capi.pack_bscsr(x, y, val32, num_rows, partitions, fixed_width)
+        self.upload_packets(packets, ppp, first, npp)
+        if vec32 is not None:
+            self.reset(vec32)
+
+    def upload_packets(self, packets, ppp, first_row, npp):
+        P = len(ppp)
+        self._packets = packets   # keep alive during the call
+        offs = np.concatenate([[0], np.cumsum(ppp)]).astype(np.uint64)
+        base = packets.ctypes.data
+        ptrs = (C.c_void_p * P)(*[C.c_void_p(base + int(offs[p]) * 64) for p in range(P)])
+        ppp = np.ascontiguousarray(ppp, np.uint64)
+        first_row = np.ascontiguousarray(first_row, np.uint32)
+        npp = np.ascontiguousarray(npp, np.uint64)
+        check(capi.lib().tks_upload_bscsr(self.handle, self.num_cols, P, _ptr(ppp), C.cast(ptrs, C.c_void_p),
+                                          _ptr(first_row), _ptr(npp)), self.handle)
+        self.first_row = first_row
+        self.partitions = P
+
+    def reset(self, vec32, debug=0):
+        vec32 = np.ascontiguousarray(vec32, np.uint32)
+        assert vec32.size == self.num_cols
+        check(capi.lib().tks_set_query(self.handle, _ptr(vec32), 1), self.handle)
+        return 0
+
+    def read_result(self):
+        """Returns (raw values uint32[count], indices uint32[count]) -- may be shorter than k."""
+        idx = np.zeros(self.k, np.uint32)
+        val = np.zeros(self.k, np.uint32)
+        cnt = C.c_uint32()
+        check(capi.lib().tks_read_result(self.handle, 0, _ptr(idx), _ptr(val), C.byref(cnt)), self.handle)
+        return val[:cnt.value], idx[:cnt.value]
+
+    def read_partition_results(self):
+        Kp = self.cfg.local_k
+        idx_w = np.zeros((self.partitions, Kp, 16), np.uint32)
+        val_w = np.zeros((self.partitions, Kp, 16), np.uint32)
+        check(capi.lib().tks_read_partition_results(self.handle, _ptr(idx_w), _ptr(val_w)), self.handle)
+        return idx_w, val_w

@@ -1,0 +1,182 @@
+/*
+ * topkspmv.h -- C ABI of libtopkspmv.so, the B200-native fused Top-K SpMV engine.
+ *
+ * The reference (AlbertoParravicini/approximate-spmv-topk) has no FFI layer; its
+ * accelerator seam is the per-backend `struct SpMV` functor that every host main()
+ * drives through four verbs (citations relative to the reference checkout):
+ *
+ *   construct      src/fpga/src/host_spmv_bscsr.cpp:104   src/gpu/host_spmv_topk_csr_gpu.cu:95
+ *   operator()     src/fpga/src/host_spmv_bscsr.cpp:323   src/gpu/host_spmv_topk_csr_gpu.cu:171
+ *   read_result    src/fpga/src/host_spmv_bscsr.cpp:399   src/gpu/host_spmv_topk_csr_gpu.cu:233
+ *   reset          src/fpga/src/host_spmv_bscsr.cpp:450   src/gpu/host_spmv_topk_csr_gpu.cu:241
+ *
+ * Each entry point below names the reference interface it replaces.  Plain C,
+ * pointers and sizes only; no C++/torch types cross this boundary.  All calls
+ * return 0 on success, a negative TKS_E* code otherwise; tks_last_error() gives
+ * the message.  One handle = one matrix shard resident on one CUDA device.
+ * A handle is thread-compatible (one caller at a time), like the reference's SpMV.
+ * There is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef TOPKSPMV_H
+#define TOPKSPMV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TKS_VERSION 1
+
+/* error codes */
+#define TKS_OK 0
+#define TKS_EINVAL (-1)   /* bad argument / unsupported knob value          */
+#define TKS_ECUDA (-2)    /* CUDA runtime error (message has the details)   */
+#define TKS_ESTATE (-3)   /* call out of order (e.g. run before upload)     */
+#define TKS_ENOMEM (-4)
+#define TKS_EIO (-5)      /* file errors in the host-side loaders           */
+
+/* mode: which reference back-end's semantics the handle reproduces */
+#define TKS_MODE_FLOAT_CSR 0   /* exact fp32 CSR  (src/gpu/host_spmv_topk_csr_gpu.cu)                */
+#define TKS_MODE_FIXED_BSCSR 1 /* FPGA semantics: W-bit fixed point, BS-CSR packets, P partitions x  */
+                               /* LFR lanes x local K (src/fpga/src/ip/spmv/spmv_bscsr_top_k_*.{hpp,cpp}) */
+
+/* tie-break of equal scores in the final list */
+#define TKS_TIE_LOWER_INDEX 0  /* north-star contract                                          */
+#define TKS_TIE_HIGHER_INDEX 1 /* reference sort_tuples, src/common/utils/evaluation_utils.hpp:52-56 */
+
+/* Runtime form of the reference's compile-time knobs (src/common/types.hpp). */
+typedef struct tks_config {
+    int32_t mode;                  /* TKS_MODE_*                                              */
+    int32_t fixed_width;           /* FIXED_WIDTH  types.hpp:20   (17..32; BS-CSR mode only)  */
+    int32_t partitions;            /* SPMV_PARTITIONS types.hpp:36 (BS-CSR mode only)         */
+    int32_t local_k;               /* K  types.hpp:51  per-lane local top-K (BS-CSR mode)     */
+    int32_t limited_finished_rows; /* LIMITED_FINISHED_ROWS types.hpp:77 (BS-CSR mode)        */
+    int32_t max_cols;              /* MAX_COLS types.hpp:55 (1024; float mode accepts <=16384) */
+    int32_t tie_break;             /* TKS_TIE_*                                               */
+    int32_t device;                /* CUDA device ordinal                                     */
+    int32_t max_batch;             /* max queries per run (float mode), >= 1                  */
+    int32_t chunk_nnz;             /* float mode work-unit size in nnz (0 = default)          */
+    int32_t reserved[6];
+} tks_config;
+
+typedef struct tks_handle tks_handle;
+
+/* What the last run moved and how long it took (algorithmic bytes). */
+typedef struct tks_stats {
+    uint64_t rows, cols, nnz;
+    uint64_t packets;             /* BS-CSR mode: total 64-byte packets                 */
+    uint64_t algorithmic_bytes;   /* per query, formula of DESIGN.md "Roofline"         */
+    uint64_t device_bytes;        /* bytes actually resident for the matrix              */
+    float last_kernel_ms;         /* device time of the last tks_run (CUDA events)       */
+    float last_total_ms;          /* host wall time of the last tks_run                  */
+    uint32_t last_candidates;     /* candidates that survived the threshold filter       */
+    uint32_t launches_per_run;    /* kernels launched by one tks_run                     */
+    uint32_t reserved[8];
+} tks_stats;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+
+int tks_default_config(tks_config *cfg);                       /* types.hpp defaults          */
+int tks_create(const tks_config *cfg, tks_handle **out);       /* SpMV ctor, first half       */
+void tks_destroy(tks_handle *h);
+const char *tks_last_error(const tks_handle *h);               /* h may be NULL (create errors) */
+int tks_version(void);
+
+/* ---- matrix upload (SpMV ctor, second half: host:133,250-321; gpu:105-168) */
+
+/* CSR as built by coo2csr (src/common/utils/utils.hpp:522-580).  ptr has rows+1
+ * entries of 32 or 64 bits; idx/val have nnz entries.  row_offset is added to
+ * every reported index (global row id of local row 0, for row-sharded use).  */
+int tks_upload_csr(tks_handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, const void *ptr,
+                   int ptr_bits, const uint32_t *idx, const float *val, uint64_t row_offset);
+/* Same, with DEVICE pointers (data already in HBM, e.g. generated there). */
+int tks_upload_csr_device(tks_handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
+                          const void *d_ptr, int ptr_bits, const uint32_t *d_idx,
+                          const float *d_val, uint64_t row_offset);
+
+/* Caller-built BS-CSR packets (host_spmv_bscsr.cpp:189-248 output): for each of
+ * `partitions` partitions a host array of packets_per_part[p] 64-byte words,
+ * the partition's first row (host:145) and its number of COO entries.         */
+int tks_upload_bscsr(tks_handle *h, uint32_t cols, uint32_t partitions,
+                     const uint64_t *packets_per_part, const void *const *packets,
+                     const uint32_t *first_row, const uint64_t *nnz_per_part);
+
+/* Synthetic matrix generated in HBM with the law of
+ * src/resources/python/create_matrices.py:84-104 (dist 0 = uniform, 1 = gamma).
+ * Float mode only.  row_offset/global_rows let N ranks generate disjoint shards. */
+int tks_generate_synthetic(tks_handle *h, uint64_t rows, uint32_t cols, uint32_t avg_degree,
+                           int dist, uint64_t seed, uint64_t row_offset);
+
+/* Copy the resident CSR back to the host (ptr64: rows+1, idx/val: nnz; any may be NULL).
+ * Lets a checker see exactly the matrix tks_generate_synthetic made.           */
+int tks_download_csr(tks_handle *h, uint64_t *ptr64, uint32_t *idx, float *val);
+
+/* ---- per query ---------------------------------------------------------- */
+
+/* reset(vec): float mode: batch x cols fp32 values, row-major.  BS-CSR mode:
+ * cols raw 32-bit ap_ufixed<32,1> words (what write_block_vec stores,
+ * src/fpga/src/ip/fpga_utils.hpp:346-355), batch must be 1.                   */
+int tks_set_query(tks_handle *h, const void *vec, uint32_t batch);
+int tks_set_query_device(tks_handle *h, const void *d_vec, uint32_t batch, void *cuda_stream);
+
+/* operator(): launch and wait.  k = CLI -k (options.hpp:103).  Timings optional. */
+int tks_run(tks_handle *h, uint32_t k, float *kernel_ms, float *total_ms);
+/* Enqueue only (no sync) on the caller's stream; result stays on the device.   */
+int tks_run_async(tks_handle *h, uint32_t k, void *cuda_stream);
+
+/* read_result(): sorted (score desc, tie-break).  Float mode: val_out is
+ * float[k].  BS-CSR mode: val_out is uint32_t[] raw ap_ufixed<32,1> scores and
+ * *count may be < k (host_spmv_bscsr.cpp:399-448).  Buffers must hold k entries. */
+int tks_read_result(tks_handle *h, uint32_t query, uint32_t *idx_out, void *val_out, uint32_t *count);
+
+/* BS-CSR mode: the kernel's raw output in the reference layout
+ * (spmv_bscsr_top_k_multicore.cpp:151-185): partitions x local_k words of
+ * 16 x u32 (row index local to the partition) and 16 x u32 (ap_ufixed<32,1>). */
+int tks_read_partition_results(tks_handle *h, uint32_t *idx_words, uint32_t *val_words);
+
+/* ---- multi-GPU plumbing: K candidates per rank, merged after an all-gather */
+
+/* Device pointer to the last run's sorted candidates of query q as 64-bit keys
+ * (score bits << 32 | tie-ordered index) and their count (<= k).               */
+int tks_result_keys_device(tks_handle *h, uint32_t query, const uint64_t **d_keys, uint32_t *count);
+/* Merge n_keys gathered keys (device) into this handle's result for query q.   */
+int tks_merge_keys_device(tks_handle *h, uint32_t query, const uint64_t *d_keys, uint32_t n_keys,
+                          uint32_t k, void *cuda_stream);
+
+int tks_get_stats(tks_handle *h, tks_stats *out);
+
+/* ---- host-side surface the reference hosts use around the accelerator ---- */
+
+/* BSCSR_PACKET_SIZE (types.hpp:71-72) for a given FIXED_WIDTH.                 */
+int tks_bscsr_packet_size(int fixed_width);
+/* Value quantisation chain double -> ap_ufixed<32,1> -> float -> ap_ufixed<W,1>
+ * (utils.hpp:401; fpga_utils.hpp:336-338).                                     */
+uint32_t tks_fixed32_from_double(double v);
+uint32_t tks_fixedW_from_fixed32(uint32_t raw32, int fixed_width);
+
+/* Row partitioning + packet builder (host_spmv_bscsr.cpp:133-248) for row-sorted
+ * COO with raw ap_ufixed<32,1> values.  Call once with packets == NULL to get
+ * packets_per_part/first_row/nnz_per_part, then with `packets` pointing at
+ * sum(packets_per_part) * 64 bytes, partitions laid out back to back.          */
+int tks_pack_bscsr(const uint32_t *row, const uint32_t *col, const uint32_t *val32, uint64_t nnz,
+                   uint32_t num_rows, int partitions, int fixed_width, uint64_t *packets_per_part,
+                   uint32_t *first_row, uint64_t *nnz_per_part, void *packets);
+
+/* readMtx (utils.hpp:474-520 + mmio.hpp): coordinate real/integer/pattern general.
+ * zero_indexed: the file's indices are 0-based (the reference hosts hard-code
+ * true, host_spmv_bscsr.cpp:539; the MTX standard and its generator are 1-based).
+ * Two-call protocol: nnz_capacity == 0 only fills rows/cols/nnz.              */
+int tks_read_mtx(const char *path, int zero_indexed, int sort_tuples, int ignore_values,
+                 uint32_t *rows, uint32_t *cols, uint64_t *nnz, uint64_t nnz_capacity,
+                 uint32_t *x, uint32_t *y, double *val);
+
+/* coo2csr (utils.hpp:522-580), stable counting sort by row.                    */
+int tks_coo2csr(const uint32_t *x, const uint32_t *y, const float *val, uint64_t nnz, uint32_t rows,
+                uint32_t cols, uint32_t *ptr, uint32_t *idx, float *out_val);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOPKSPMV_H */

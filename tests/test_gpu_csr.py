@@ -1,0 +1,221 @@
+"""GPU parity tests of the fused fp32 CSR Top-K SpMV engine, through the C ABI (ctypes).
+
+Bar (BASELINE.json north_star): scores within 1e-5 relative of the CPU reference, index sets identical
+except where scores tie within that tolerance; with exactly-representable data the result must be
+bit-exact including the tie-break order."""
+import numpy as np
+import pytest
+
+from conftest import make_query
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def check_against_scores(idx, val, cnt, y, k, tie="lower", exact=False):
+    """y: reference score of every row (fp32, sequential order = the reference gold's arithmetic)."""
+    n = y.size
+    want = min(k, n)
+    assert cnt == want
+    idx, val = idx[:cnt], val[:cnt]
+    assert len(set(idx.tolist())) == cnt, "duplicate rows in the result"
+    assert np.all(idx < n)
+    assert np.all(np.diff(val) <= 0), "scores not sorted descending"
+    if exact:
+        order = np.lexsort((np.arange(n) if tie == "lower" else -np.arange(n), -y.astype(np.float64)))[:want]
+        assert np.array_equal(idx, order.astype(np.uint32))
+        assert np.array_equal(val.view(np.uint32), y[order].view(np.uint32))
+        return
+    np.testing.assert_allclose(val, y[idx], rtol=RTOL, atol=1e-7)
+    ys = np.sort(y)[::-1]
+    kth = ys[want - 1]
+    must = np.nonzero(y > kth * (1 + RTOL) + 1e-7)[0]
+    assert set(must.tolist()) <= set(idx.tolist()), "a row clearly above the k-th score is missing"
+    assert np.all(y[idx] >= kth * (1 - RTOL) - 1e-7), "a row clearly below the k-th score was returned"
+
+
+def run_engine(tks, ptr, col, val, rows, cols, vec, k, **kw):
+    with tks.SpMV(ptr, col, val, rows, cols, vec=vec, k=k, **kw) as s:
+        s()
+        v, i, c = s.read_result()
+    return i, v, c
+
+
+@pytest.fixture(scope="module")
+def cfg1(gen):
+    """BASELINE config 1: matrix_10000_1024_20_gamma, k=100."""
+    x, y, v = gen.create_sparse_matrix(10000, 1024, 20, "gamma", seed=0)
+    return x, y, v.astype(np.float32), gen.csr_from_coo(x, 10000)
+
+
+def test_cfg1_matches_gold_and_float64(cuda_required, tks, orc, cfg1):
+    x, y, v, ptr = cfg1
+    with tks.SpMV(ptr, y, v, 10000, 1024, k=100) as s:
+        for qs in range(1, 6):
+            vec = make_query(1024, qs)
+            s.reset(vec)
+            s()
+            val, idx, cnt = s.read_result()
+            yref = orc.spmv_f32(x, y, v, vec, 10000)
+            check_against_scores(idx, val, cnt, yref, 100)
+            gi, gv = orc.gold_topk_f32(x, y, v, vec, 100)          # the reference's own algorithm
+            np.testing.assert_allclose(val, gv, rtol=RTOL)
+            fi, fv = orc.f64_topk(ptr, y, v, vec, 100)             # sparse_dot_topn stand-in
+            np.testing.assert_allclose(val, fv, rtol=RTOL)
+            assert len(set(idx.tolist()) ^ set(fi.tolist())) <= 2   # only boundary near-ties may differ
+
+
+@pytest.mark.parametrize("k", [1, 8, 20, 100, 128, 129, 384, 500, 1024])
+def test_k_sweep(cuda_required, tks, orc, cfg1, k):
+    x, y, v, ptr = cfg1
+    vec = make_query(1024, 77)
+    idx, val, cnt = run_engine(tks, ptr, y, v, 10000, 1024, vec, k)
+    check_against_scores(idx, val, cnt, orc.spmv_f32(x, y, v, vec, 10000), k)
+
+
+@pytest.mark.parametrize("chunk_nnz", [128, 256, 1024, 4096, 65536])
+def test_chunk_sizes(cuda_required, tks, orc, cfg1, chunk_nnz):
+    x, y, v, ptr = cfg1
+    vec = make_query(1024, 5)
+    idx, val, cnt = run_engine(tks, ptr, y, v, 10000, 1024, vec, 100, chunk_nnz=chunk_nnz)
+    check_against_scores(idx, val, cnt, orc.spmv_f32(x, y, v, vec, 10000), 100)
+
+
+def exact_matrix(rows, cols, rng, max_deg=12, empty_frac=0.0):
+    """Values and query are small powers of two: every summation order gives the same fp32 result."""
+    deg = rng.integers(1, max_deg + 1, rows)
+    if empty_frac > 0:
+        deg[rng.random(rows) < empty_frac] = 0
+    ptr = np.zeros(rows + 1, np.uint64)
+    np.cumsum(deg, out=ptr[1:])
+    nnz = int(ptr[-1])
+    x = np.repeat(np.arange(rows, dtype=np.uint32), deg)
+    col = rng.integers(0, cols, nnz).astype(np.uint32)
+    val = (2.0 ** rng.integers(-3, 1, nnz)).astype(np.float32)
+    vec = (2.0 ** rng.integers(-4, 1, cols)).astype(np.float32)
+    return ptr, x, col, val, vec
+
+
+@pytest.mark.parametrize("tie_higher", [False, True])
+@pytest.mark.parametrize("rows,k,max_deg,empty", [(5000, 100, 12, 0.0), (5000, 100, 3, 0.0), (3000, 64, 8, 0.2),
+                                                   (50, 100, 5, 0.0), (1, 8, 4, 0.0), (300, 7, 300, 0.0)])
+def test_exact_ties_and_edge_shapes(cuda_required, tks, orc, rows, k, max_deg, empty, tie_higher):
+    """Massive ties (few distinct scores), rows of length 1..3 inside one lane, empty rows, fewer rows
+    than k, a single row, rows longer than a warp iteration: bit-exact incl. tie order."""
+    rng = np.random.default_rng(rows * 31 + k)
+    ptr, x, col, val, vec = exact_matrix(rows, 256, rng, max_deg, empty)
+    yref = orc.spmv_f32(x, col, val, vec, rows)
+    nonempty = np.diff(ptr.astype(np.int64)) > 0
+    with tks.SpMV(ptr, col, val, rows, 256, vec=vec, k=k, tie_higher=tie_higher, chunk_nnz=256) as s:
+        s()
+        v, i, c = s.read_result()
+    # empty rows are never candidates (the reference's COO gold never sees them either)
+    cand = np.nonzero(nonempty)[0]
+    want = min(k, cand.size)
+    assert c == want
+    sec = cand if not tie_higher else -cand
+    order = cand[np.lexsort((sec, -yref[cand].astype(np.float64)))[:want]]
+    assert np.array_equal(i[:c], order.astype(np.uint32))
+    assert np.array_equal(v[:c].view(np.uint32), yref[order].view(np.uint32))
+    assert np.all(i[c:] == 0) and np.all(v[c:] == 0)
+
+
+def test_negative_and_zero_scores_exact(cuda_required, tks, orc):
+    rng = np.random.default_rng(3)
+    ptr, x, col, val, vec = exact_matrix(4000, 128, rng, 6)
+    val = val * rng.choice(np.array([-1.0, 1.0], np.float32), val.size)
+    yref = orc.spmv_f32(x, col, val, vec, 4000)
+    idx, v, cnt = run_engine(tks, ptr, col, val, 4000, 128, vec, 1000)
+    check_against_scores(idx, v, cnt, yref, 1000, exact=True)
+
+
+def test_long_rows_and_wide_matrix(cuda_required, tks, orc):
+    """Rows far longer than a chunk, cols up to the 14-bit limit."""
+    rng = np.random.default_rng(8)
+    rows, cols = 64, 16384
+    deg = rng.integers(1, 9000, rows)
+    ptr = np.zeros(rows + 1, np.uint64)
+    np.cumsum(deg, out=ptr[1:])
+    nnz = int(ptr[-1])
+    x = np.repeat(np.arange(rows, dtype=np.uint32), deg)
+    col = rng.integers(0, cols, nnz).astype(np.uint32)
+    val = rng.random(nnz).astype(np.float32)
+    vec = make_query(cols, 1)
+    idx, v, cnt = run_engine(tks, ptr, col, val, rows, cols, vec, 10, max_cols=cols)
+    y64 = np.zeros(rows)
+    np.add.at(y64, x, val.astype(np.float64) * vec[col].astype(np.float64))
+    order = np.argsort(-y64)[:10]
+    assert np.array_equal(np.sort(idx[:cnt]), np.sort(order.astype(np.uint32)))
+    np.testing.assert_allclose(v[:cnt], y64[idx[:cnt]], rtol=2e-5)
+
+
+def test_row_offset_and_repeatability(cuda_required, tks, orc, cfg1):
+    x, y, v, ptr = cfg1
+    vec = make_query(1024, 21)
+    with tks.SpMV(ptr, y, v, 10000, 1024, vec=vec, k=50, row_offset=123456) as s:
+        s()
+        v1, i1, _ = s.read_result()
+        for _ in range(5):
+            s()
+            v2, i2, _ = s.read_result()
+            assert np.array_equal(i1, i2) and np.array_equal(v1.view(np.uint32), v2.view(np.uint32))
+    idx0, val0, _ = run_engine(tks, ptr, y, v, 10000, 1024, vec, 50)
+    assert np.array_equal(i1, idx0 + 123456)
+    assert np.array_equal(v1.view(np.uint32), val0.view(np.uint32))
+
+
+def test_errors(cuda_required, tks):
+    ptr = np.array([0, 2, 4], np.uint64)
+    col = np.array([0, 1, 2, 5000], np.uint32)
+    val = np.ones(4, np.float32)
+    with pytest.raises(tks.capi.TksError, match="column index"):
+        tks.SpMV(ptr, col, val, 2, 1024)
+    with tks.SpMV(ptr, np.array([0, 1, 2, 3], np.uint32), val, 2, 1024, k=100) as s:
+        with pytest.raises(tks.capi.TksError, match="no query"):
+            s()
+        s.reset(np.ones(1024, np.float32))
+        with pytest.raises(tks.capi.TksError):
+            s.run_timed(k=5000)
+
+
+def test_synthetic_device_generator_matches_law_and_oracle(cuda_required, tks, orc):
+    """tks_generate_synthetic: download the matrix it made, check the generator law (create_matrices.py)
+    and run the oracle on exactly that matrix."""
+    rows, cols = 200_000, 1024
+    with tks.SpMV(num_cols=cols, k=100) as s:
+        for dist, avg in (("gamma", 20), ("uniform", 40)):
+            s.generate_synthetic(rows, cols, avg, dist, seed=7)
+            ptr, idx, val = s.download_csr()
+            deg = np.diff(ptr.astype(np.int64))
+            assert deg.min() >= 1
+            if dist == "uniform":
+                assert deg.min() == avg // 2 and deg.max() == int(avg * 1.5)
+                assert abs(deg.mean() - avg) < 0.2
+            else:
+                assert abs(deg.mean() - 19.5) < 0.2          # E[int(Gamma(3, 20/3))]
+            x = np.repeat(np.arange(rows, dtype=np.uint32), deg)
+            key = x.astype(np.int64) * cols + idx
+            assert np.all(np.diff(key) >= 0), "columns must be sorted inside a row"
+            nrm = np.sqrt(np.add.reduceat(val.astype(np.float64) ** 2, ptr[:-1].astype(np.int64)))
+            np.testing.assert_allclose(nrm, 1.0, rtol=1e-5)
+            vec = make_query(cols, 3)
+            s.reset(vec)
+            s()
+            v, i, c = s.read_result()
+            check_against_scores(i, v, c, orc.spmv_f32(x, idx, val, vec, rows), 100)
+
+
+def test_two_million_rows_vs_float64(cuda_required, tks, orc):
+    """Larger than L2: 2M x 1024 gamma-20 generated in HBM, checked against float64 on the host."""
+    rows, cols = 2_000_000, 1024
+    with tks.SpMV(num_cols=cols, k=100) as s:
+        s.generate_synthetic(rows, cols, 20, "gamma", seed=11)
+        ptr, idx, val = s.download_csr()
+        for qs in (1, 2):
+            vec = make_query(cols, qs)
+            s.reset(vec)
+            s()
+            v, i, c = s.read_result()
+            fi, fv = orc.f64_topk(ptr, idx, val, vec, 100)
+            np.testing.assert_allclose(v, fv, rtol=RTOL)
+            assert len(set(i.tolist()) ^ set(fi.tolist())) <= 2
