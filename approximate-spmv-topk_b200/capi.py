@@ -23,7 +23,7 @@ class TksConfig(C.Structure):
     _fields_ = [("mode", C.c_int32), ("fixed_width", C.c_int32), ("partitions", C.c_int32),
                 ("local_k", C.c_int32), ("limited_finished_rows", C.c_int32), ("max_cols", C.c_int32),
                 ("tie_break", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_int32),
-                ("chunk_nnz", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("chunk_nnz", C.c_int32), ("profile_kernels", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class TksStats(C.Structure):
@@ -31,7 +31,7 @@ class TksStats(C.Structure):
                 ("algorithmic_bytes", C.c_uint64), ("device_bytes", C.c_uint64),
                 ("last_kernel_ms", C.c_float), ("last_total_ms", C.c_float),
                 ("last_candidates", C.c_uint32), ("launches_per_run", C.c_uint32),
-                ("reserved", C.c_uint32 * 8)]
+                ("last_main_kernel_ms", C.c_float), ("reserved", C.c_uint32 * 7)]
 
 
 class TksError(RuntimeError):

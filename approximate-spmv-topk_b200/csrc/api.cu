@@ -160,7 +160,7 @@ int check_float_upload(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, ui
     return TKS_OK;
 }
 
-int launch_float(Handle *h, uint32_t k, cudaStream_t s) {
+int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false) {
     if (!h->have_matrix) return h->fail(TKS_ESTATE, "no matrix uploaded");
     if (!h->have_query) return h->fail(TKS_ESTATE, "no query set");
     if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k=%u outside 1..%u", k, h->kmax);
@@ -181,12 +181,14 @@ int launch_float(Handle *h, uint32_t k, cudaStream_t s) {
         const uint32_t sgrid = (n_sample * kWarp + kSampleThreads - 1) / kSampleThreads;
         csr_sample_kernel<<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride,
                                                                      k);
+        if (profile && q == 0) cudaEventRecord(h->evm0, s);
         switch (variant) {
             case 0: launch_main<256>(h, 0, m, x, st, k, s); break;
             case 1: launch_main<512>(h, 1, m, x, st, k, s); break;
             case 2: launch_main<1024>(h, 2, m, x, st, k, s); break;
             default: launch_main<2048>(h, 3, m, x, st, k, s); break;
         }
+        if (profile && q == 0) cudaEventRecord(h->evm1, s);
         select_topk_kernel<<<1, kSelectThreads, kSelectSortCap * 8u, s>>>(
             h->d_pool, &st->pool_count, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
             h->d_res_idx + (size_t)q * h->kmax, h->d_res_val + (size_t)q * h->kmax, h->d_res_count + q, st);
@@ -273,11 +275,19 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&h->evm0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&h->evm1)) != cudaSuccess) return bail("cudaEventCreate", e);
     if (cfg->mode == TKS_MODE_FLOAT_CSR) {
         if ((e = prep_main<256>(h, 0)) != cudaSuccess) return bail("prep_main<256>", e);
         if ((e = prep_main<512>(h, 1)) != cudaSuccess) return bail("prep_main<512>", e);
         if ((e = prep_main<1024>(h, 2)) != cudaSuccess) return bail("prep_main<1024>", e);
         if ((e = prep_main<2048>(h, 3)) != cudaSuccess) return bail("prep_main<2048>", e);
+        {
+            size_t ss = (size_t)cfg->max_cols * 4u;
+            if (ss < 2048u * 8u) ss = 2048u * 8u;
+            if ((e = cudaFuncSetAttribute(csr_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess)
+                return bail("sample smem attr", e);
+        }
         if ((e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(kSelectSortCap * 8u))) != cudaSuccess)
             return bail("select smem attr", e);
@@ -298,6 +308,8 @@ void tks_destroy(tks_handle *h) {
     cudaFreeHost(h->h_res_idx); cudaFreeHost(h->h_res_val); cudaFreeHost(h->h_res_count); cudaFreeHost(h->h_x);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evm0) cudaEventDestroy(h->evm0);
+    if (h->evm1) cudaEventDestroy(h->evm1);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -449,7 +461,7 @@ int tks_run(tks_handle *h, uint32_t k, float *kernel_ms, float *total_ms) {
     TKS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     int rc;
     if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) { h->last_k = k; rc = bscsr_launch(h, h->stream); }
-    else rc = launch_float(h, k, h->stream);
+    else rc = launch_float(h, k, h->stream, h->cfg.profile_kernels != 0);
     if (rc) return rc;
     TKS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) {
@@ -466,6 +478,11 @@ int tks_run(tks_handle *h, uint32_t k, float *kernel_ms, float *total_ms) {
     TKS_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     auto t1 = std::chrono::high_resolution_clock::now();
     h->stats.last_kernel_ms = ms;
+    if (h->cfg.profile_kernels && h->cfg.mode == TKS_MODE_FLOAT_CSR) {
+        float mm = 0.f;
+        TKS_CUDA(h, cudaEventElapsedTime(&mm, h->evm0, h->evm1));
+        h->stats.last_main_kernel_ms = mm;
+    }
     h->stats.last_total_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
     if (kernel_ms) *kernel_ms = ms;
     if (total_ms) *total_ms = h->stats.last_total_ms;

@@ -70,10 +70,12 @@ class SpMV(_Base):
     """Exact fp32 CSR engine (host_spmv_topk_csr_gpu.cu:95 signature: ptr, idx, val, rows, cols, nnz, vec, k)."""
 
     def __init__(self, ptr=None, idx=None, val=None, num_rows=0, num_cols=0, num_nnz=None, vec=None, k=100,
-                 device=0, tie_higher=False, max_batch=1, max_cols=None, chunk_nnz=0, row_offset=0):
+                 device=0, tie_higher=False, max_batch=1, max_cols=None, chunk_nnz=0, row_offset=0,
+                 profile_kernels=False):
         cfg = capi.default_config(mode=capi.MODE_FLOAT_CSR, device=device, max_batch=max_batch,
                                   tie_break=capi.TIE_HIGHER_INDEX if tie_higher else capi.TIE_LOWER_INDEX,
-                                  max_cols=max(1024, int(max_cols or num_cols or 1024)), chunk_nnz=chunk_nnz)
+                                  max_cols=max(1024, int(max_cols or num_cols or 1024)), chunk_nnz=chunk_nnz,
+                                  profile_kernels=int(profile_kernels))
         self._create(cfg)
         self.k = k
         self.num_rows, self.num_cols = int(num_rows), int(num_cols)

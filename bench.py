@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- fused Top-K SpMV throughput on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+A "step" = one Top-K SpMV query over the resident matrix:
+  N = 1   workload cfg2: synthetic 10M x 1024, gamma ~20 nnz/row, fp32 CSR, single query, k = 100
+  N > 1   workload cfg4: synthetic 200M x 1024, uniform ~40 nnz/row, fp32, k = 100, rows sharded evenly
+          over the N ranks, K candidates per rank all-gathered (NCCL) and merged on every rank
+  --workload cfg3: the cfg2 matrix as 20-bit BS-CSR packets, 32 partitions x local K=8 (FPGA semantics)
+`value` = non-zeros processed per second by the whole job with the matrix and the queries resident in HBM;
+`e2e`   = the same through the reference-facing calls reset(vec) / operator() / read_result with HOST
+          buffers (query H2D and result D2H inside the timed region).
+The matrix is generated in HBM (tks_generate_synthetic: the law of the reference's create_matrices.py);
+it is far larger than the 126 MB L2, so no flush is needed between steps.
+
+--impl reference times the reference's CPU path on the box's host cores (see cpu_reference()).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    "cfg2": dict(rows=10_000_000, cols=1024, deg=20, dist="gamma", mode="float",
+                 name="cfg2: synthetic 10M x 1024, gamma ~20 nnz/row, fp32 CSR, single query, k=100"),
+    "cfg3": dict(rows=10_000_000, cols=1024, deg=20, dist="gamma", mode="fixed",
+                 name="cfg3: cfg2 matrix in 20-bit BS-CSR packets, 32 partitions x local K=8 (FPGA semantics)"),
+    "cfg4": dict(rows=200_000_000, cols=1024, deg=40, dist="uniform", mode="float",
+                 name="cfg4: synthetic 200M x 1024, uniform ~40 nnz/row, fp32, k=100, row-sharded + K-candidate allgather"),
+}
+K = 100
+SEED = 0
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            j = json.loads(p.read_text())
+            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_queries(cols, n, seed0=1):
+    """test_cpu.py:99-100: U[0,1)^C / L2 norm; seeds 1..n (the reference is unseeded)."""
+    out = np.zeros((n, cols), np.float32)
+    for i in range(n):
+        rng = np.random.default_rng(seed0 + i)
+        v = rng.random(cols)
+        out[i] = (v / np.linalg.norm(v)).astype(np.float32)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU implementation on the host cores
+# ---------------------------------------------------------------------------------------------
+
+def cpu_reference(ptr, idx, val, queries, k, max_seconds=25.0, min_steps=1):
+    """Times the reference's own CPU Top-K SpMV on this box.
+
+    The reference's CPU path is sparse_dot_topn.awesome_cossim_topn(..., use_threads=True, n_jobs=40)
+    (test_cpu.py:104); that dependency is absent and un-pinned, so the arm runs the reference's other CPU
+    implementation of the same path, spmv_coo_gold_top_k + sort_tuples (gold_algorithms.hpp:188-246,
+    evaluation_utils.hpp:40-62): the reference's OWN code from oracle/_ref/libref_gold.so when it was
+    built (kind "reference"), else the oracle's restatement of it (kind "port").  Like the threaded
+    sparse_dot_topn, rows are split into one contiguous block per host thread, each block is reduced
+    with the reference routine, and the per-block top-k lists are merged.
+    Returns (seconds_per_query_list, kind, cores, results)."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    rows = ptr.size - 1
+    cores = os.cpu_count() or 1
+    use_ref = oracle.ref_gold() is not None
+    kind = "reference" if use_ref else "port"
+    fn = oracle.ref_gold_topk_f32 if use_ref else oracle.gold_topk_f32
+    deg = np.diff(ptr.astype(np.int64))
+    x = np.repeat(np.arange(rows, dtype=np.uint32), deg)
+    cuts = [int(ptr[rows * t // cores]) for t in range(cores + 1)]
+    blocks = [(cuts[t], cuts[t + 1]) for t in range(cores) if cuts[t + 1] > cuts[t]]
+    times, results = [], []
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        t_start = time.perf_counter()
+        for q in queries:
+            t0 = time.perf_counter()
+            parts = list(ex.map(lambda b: fn(x[b[0]:b[1]], idx[b[0]:b[1]], val[b[0]:b[1]], q, k), blocks))
+            ai = np.concatenate([p[0] for p in parts]); av = np.concatenate([p[1] for p in parts])
+            order = np.lexsort((-ai.astype(np.int64), -av.astype(np.float64)))[:k]
+            results.append((ai[order], av[order]))
+            times.append(time.perf_counter() - t0)
+            if len(times) >= min_steps and time.perf_counter() - t_start > max_seconds:
+                break
+    return times, kind, cores, results
+
+
+def reference_arm(args):
+    """`--impl reference`: rank 0 only; bounded sample of the same workload on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from _pkg import pkg
+    tks = pkg()
+    wl = WORKLOADS[args.workload or ("cfg2" if args.gpus == 1 else "cfg4")]
+    sample_rows = min(wl["rows"], args.ref_rows)
+    x, y, v = tks.create_matrices.create_sparse_matrix(sample_rows, wl["cols"], wl["deg"], wl["dist"], seed=SEED)
+    ptr = tks.create_matrices.csr_from_coo(x, sample_rows)
+    val = v.astype(np.float32)
+    nnz = int(ptr[-1])
+    queries = make_queries(wl["cols"], args.warmup + args.steps)
+    cpu_reference(ptr, y, val, queries[:args.warmup], K, max_seconds=1e9)
+    times, kind, cores, _ = cpu_reference(ptr, y, val, queries[args.warmup:], K, max_seconds=240.0, min_steps=args.steps)
+    sec = sum(times) / len(times)
+    value = nnz / sec
+    sample = (f"{sample_rows} of {wl['rows']} rows of the same synthetic law ({nnz} nnz), {len(times)} queries, "
+              f"reference spmv_coo_gold_top_k over {cores} row blocks in {cores} host threads "
+              f"(sparse_dot_topn is absent from the image)")
+    line = {"impl": "reference", "metric": "topk_spmv_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": args.gpus,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "k": K},
+            "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+
+class _DevArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from _pkg import pkg
+    tks = pkg()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl_key = args.workload or ("cfg2" if world == 1 else "cfg4")
+    wl = WORKLOADS[wl_key]
+    rows_total = args.rows or wl["rows"]
+    cols = wl["cols"]
+    shards = tks.sharding.plan_row_shards_even(rows_total, world)
+    r0, r1 = shards[rank]
+    peak_gbs, peak_src = measured_peaks()
+    stream = torch.cuda.current_stream().cuda_stream
+    nsteps = args.warmup + args.steps
+    queries = make_queries(cols, nsteps)
+
+    if wl["mode"] == "fixed":
+        return ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src)
+
+    # profile_kernels: tks_run (the e2e path) also brackets the dominant kernel with two events; the
+    # resident path (tks_run_async) never does
+    eng = tks.SpMV(num_cols=cols, k=K, device=local, profile_kernels=True)
+    t0 = time.perf_counter()
+    eng.generate_synthetic(r1 - r0, cols, wl["deg"], wl["dist"], seed=SEED, row_offset=r0)
+    gen_s = time.perf_counter() - t0
+    st = eng.stats()
+    nnz_local = int(st.nnz)
+    nnz_t = torch.tensor([nnz_local], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(nnz_t)
+    nnz_total = int(nnz_t.item())
+
+    dq = torch.from_numpy(queries).cuda()            # queries resident in HBM for `value`
+    if world > 1:
+        gathered = torch.empty(world * K, dtype=torch.int64, device="cuda")
+
+    def step(i):
+        eng.reset_device(dq[i].data_ptr(), 1, stream)
+        eng.run_async(K, stream)
+        if world > 1:
+            kp, n = eng.result_keys_device(0)
+            mine = torch.as_tensor(_DevArray(kp, K, "<i8"), device="cuda")
+            dist.all_gather_into_tensor(gathered, mine)
+            eng.merge_keys_device(gathered.data_ptr(), world * K, K, 0, stream)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = nnz_total / (ms_step * 1e-3)
+    val_last, idx_last, cnt_last = eng.read_result()
+
+    # e2e: reference-facing calls with HOST buffers (reset -> operator() -> read_result), every step
+    hq = [np.ascontiguousarray(q) for q in queries]
+    e2e_ms = []
+    for i in range(nsteps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        eng.reset(hq[i])
+        if world == 1:
+            eng.run_timed(K)
+            v_e, i_e, _ = eng.read_result()
+        else:
+            eng.run_async(K, stream)
+            kp, n = eng.result_keys_device(0)
+            mine = torch.as_tensor(_DevArray(kp, K, "<i8"), device="cuda")
+            dist.all_gather_into_tensor(gathered, mine)
+            eng.merge_keys_device(gathered.data_ptr(), world * K, K, 0, stream)
+            torch.cuda.synchronize()
+            v_e, i_e, _ = eng.read_result()
+        dt = (time.perf_counter() - t0) * 1e3
+        if i >= args.warmup:
+            e2e_ms.append(dt)
+    e2e_t = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms_step = float(e2e_t.item())
+    # the device-resident and the host-buffer paths must agree on the last query
+    assert np.array_equal(i_e, idx_last) and np.array_equal(v_e, val_last), "e2e and resident results differ"
+
+    # roofline of the dominant kernel (csr_topk_main_kernel), timed alone with CUDA events on its stream
+    stats = eng.stats()
+    alg_bytes_local = int(stats.algorithmic_bytes)
+    main_ms = measure_main_kernel(tks, eng, hq, args, K)
+    achieved = alg_bytes_local / (main_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "csr_topk_main_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+            "frac": achieved / peak_gbs, "traffic": load_traffic(wl_key), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes_local, "main_kernel_ms": main_ms,
+            "step_frac": alg_bytes_local / (ms_step * 1e-3) / 1e9 / peak_gbs}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_leg(tks, eng, hq[args.warmup:], idx_last, val_last, args)
+
+    if rank == 0:
+        line = {"metric": "topk_spmv_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "rows": rows_total, "cols": cols, "nnz": nnz_total, "k": K,
+                           "sharding": f"rows/{world}" if world > 1 else "none",
+                           "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * 8 / 1e9),
+                           "generator_s": round(gen_s, 2)},
+                "roofline": roof,
+                "cpu_baseline": cpu,
+                "e2e": {"value": nnz_total / (e2e_ms_step * 1e-3), "unit": "nnz/s", "ms_per_step": e2e_ms_step,
+                        "h2d_bytes_per_step": cols * 4, "d2h_bytes_per_step": K * 8 + 4,
+                        "api": "SpMV.reset(host vec) -> operator() -> read_result(host)"},
+                "gpu_launches": args.steps * (3 if world == 1 else 4),
+                "hbm_gbs_effective": alg_bytes_local * world / (ms_step * 1e-3) / 1e9,
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_main_kernel(tks, eng, hq, args, k):
+    """Average duration of the dominant kernel alone (CUDA events recorded by tks_run on its own stream
+    right before and after csr_topk_main_kernel; cfg.profile_kernels)."""
+    ms = []
+    for i in range(args.warmup + args.steps):
+        eng.reset(hq[i % len(hq)])
+        km, _ = eng.run_timed(k)
+        st = eng.stats()
+        v = st.last_main_kernel_ms if st.last_main_kernel_ms > 0 else km
+        if i >= args.warmup:
+            ms.append(v)
+    return sum(ms) / len(ms)
+
+
+def load_traffic(wl_key):
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(wl_key)
+        except Exception:
+            return None
+    return None
+
+
+def cpu_baseline_leg(tks, eng, queries, idx_gpu, val_gpu, args):
+    """cpu_baseline on a bounded sample of the SAME matrix (first rows of the resident CSR)."""
+    ptr, idx, val = eng.download_csr()
+    sample_rows = min(ptr.size - 1, args.ref_rows)
+    e = int(ptr[sample_rows])
+    times, kind, cores, _ = cpu_reference(ptr[:sample_rows + 1], idx[:e], val[:e], queries, K, max_seconds=20.0)
+    sec = sum(times) / len(times)
+    return {"value": e / sec, "unit": "nnz/s", "cores": cores, "kind": kind,
+            "sample": f"first {sample_rows} rows ({e} nnz) of the benchmark matrix, {len(times)} queries, "
+                      f"reference spmv_coo_gold_top_k over {cores} row blocks in {cores} threads",
+            "ms_per_query_on_sample": sec * 1e3}
+
+
+def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
+    raise SystemExit("cfg3 bench leg: use after the BS-CSR engine is built")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)      # NITER of test_spmv_topk.py:21
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS.keys()])
+    ap.add_argument("--rows", type=int, default=0, help="override the workload's total rows (debug)")
+    ap.add_argument("--ref-rows", type=int, default=2_000_000, help="rows of the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

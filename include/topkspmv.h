@@ -58,7 +58,8 @@ typedef struct tks_config {
     int32_t device;                /* CUDA device ordinal                                     */
     int32_t max_batch;             /* max queries per run (float mode), >= 1                  */
     int32_t chunk_nnz;             /* float mode work-unit size in nnz (0 = default)          */
-    int32_t reserved[6];
+    int32_t profile_kernels;       /* 1: tks_run also times the dominant kernel alone (stats)  */
+    int32_t reserved[5];
 } tks_config;
 
 typedef struct tks_handle tks_handle;
@@ -73,7 +74,8 @@ typedef struct tks_stats {
     float last_total_ms;          /* host wall time of the last tks_run                  */
     uint32_t last_candidates;     /* candidates that survived the threshold filter       */
     uint32_t launches_per_run;    /* kernels launched by one tks_run                     */
-    uint32_t reserved[8];
+    float last_main_kernel_ms;    /* dominant kernel alone (only with cfg.profile_kernels) */
+    uint32_t reserved[7];
 } tks_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */
