@@ -24,7 +24,7 @@ int cap_variant_for_k(uint32_t k) {
 }
 
 size_t main_smem_bytes(uint32_t cols, int variant) {
-    return ((cols * 4u + 15u) & ~15u) + (size_t)(kCapThreads[variant] / 32) * kCaps[variant] * 8u;
+    return (((cols + 1u) * 4u + 15u) & ~15u) + (size_t)(kCapThreads[variant] / 32) * kCaps[variant] * 8u;
 }
 
 template <int CAP>
@@ -72,7 +72,7 @@ int alloc_query_side(Handle *h) {
     TKS_CUDA(h, cudaMemset(h->d_state, 0, mb * sizeof(RunState)));
     h->pool_cap = max_pool_keys(h);
     TKS_CUDA(h, cudaMalloc(&h->d_pool, h->pool_cap * sizeof(uint64_t)));
-    h->n_sample_cap = 2048;
+    h->n_sample_cap = 8192;
     TKS_CUDA(h, cudaMalloc(&h->d_sample_keys, h->n_sample_cap * sizeof(uint32_t)));
     TKS_CUDA(h, cudaMalloc(&h->d_res_keys, (size_t)mb * h->kmax * sizeof(uint64_t)));
     TKS_CUDA(h, cudaMalloc(&h->d_res_idx, (size_t)mb * h->kmax * sizeof(uint32_t)));
@@ -91,17 +91,32 @@ void free_matrix(Handle *h) {
     cudaFree(h->d_colf); h->d_colf = nullptr;
     cudaFree(h->d_ptr64); h->d_ptr64 = nullptr;
     cudaFree(h->d_chunk_start); h->d_chunk_start = nullptr;
-    cudaFree(h->d_chunk_rb); h->d_chunk_rb = nullptr;
+    cudaFree(h->d_chunk_ord); h->d_chunk_ord = nullptr;
+    cudaFree(h->d_row_map); h->d_row_map = nullptr;
     h->have_matrix = false;
 }
 
-// Build colf + chunk table from a device CSR.  d_val_src may alias nothing we own; it is copied.
+// Exclusive scan of n u32 values into n+1 u64 values (setup only).
+int device_scan_u32(Handle *h, const uint32_t *d_in, uint64_t n, uint64_t *d_out) {
+    cudaStream_t s = h->stream;
+    const uint32_t nb = (uint32_t)((n + kScanBlock - 1) / kScanBlock);
+    uint64_t *d_bs = nullptr;
+    TKS_CUDA(h, cudaMalloc(&d_bs, ((size_t)nb + 1) * sizeof(uint64_t)));
+    scan_block_sums_kernel<<<nb, kScanBlock, 0, s>>>(d_in, n, d_bs);
+    scan_block_offsets_kernel<<<1, 32, 0, s>>>(d_bs, nb);
+    scan_finish_kernel<<<nb, kScanBlock, 0, s>>>(d_in, n, d_bs, d_out);
+    TKS_CUDA(h, cudaStreamSynchronize(s));
+    cudaFree(d_bs);
+    return TKS_OK;
+}
+
+// Build colf + chunk table (+ row map when rows are empty) from a device CSR.  val is copied unless adopted.
 template <typename P>
 int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, const P *d_ptr,
                           const uint32_t *d_idx, const float *d_val_src, float *d_val_adopt) {
     cudaStream_t s = h->stream;
-    const size_t pad = 1024;   // over-read slack of the 128-bit streaming loads (zero filled)
-    h->chunk_nnz = h->cfg.chunk_nnz > 0 ? (uint32_t)h->cfg.chunk_nnz : 2048u;
+    const size_t pad = 2048;   // over-read slack of the 256-bit streaming loads (zero filled)
+    h->chunk_nnz = h->cfg.chunk_nnz > 0 ? (uint32_t)h->cfg.chunk_nnz : 4096u;
     h->chunk_nnz = (h->chunk_nnz + kElemsPerIter - 1) / kElemsPerIter * kElemsPerIter;
     uint64_t nch = (nnz + h->chunk_nnz - 1) / h->chunk_nnz;
     if (nch == 0) nch = 1;
@@ -118,34 +133,46 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
     TKS_CUDA(h, cudaMalloc(&h->d_colf, nnz * sizeof(uint32_t) + pad));
     TKS_CUDA(h, cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_colf) + nnz * sizeof(uint32_t), 0, pad, s));
     TKS_CUDA(h, cudaMalloc(&h->d_chunk_start, (nch + 1) * sizeof(uint64_t)));
-    TKS_CUDA(h, cudaMalloc(&h->d_chunk_rb, nch * sizeof(uint32_t)));
-    uint32_t *d_err = nullptr;
+    TKS_CUDA(h, cudaMalloc(&h->d_chunk_ord, nch * sizeof(uint32_t)));
+    uint32_t *d_err = nullptr, *d_flag = nullptr;
+    uint64_t *d_ord = nullptr;
     TKS_CUDA(h, cudaMalloc(&d_err, sizeof(uint32_t)));
     TKS_CUDA(h, cudaMemsetAsync(d_err, 0, sizeof(uint32_t), s));
+    TKS_CUDA(h, cudaMalloc(&d_flag, (rows ? rows : 1) * sizeof(uint32_t)));
+    TKS_CUDA(h, cudaMalloc(&d_ord, (rows + 1) * sizeof(uint64_t)));
 
-    if (nnz > 0) {
-        csr_copy_cols_kernel<P><<<h->num_sms * 8, 256, 0, s>>>(d_idx, nnz, cols, h->d_colf, d_err);
-        const uint32_t rb = (uint32_t)((rows + 255) / 256);
-        csr_mark_rows_kernel<P><<<rb, 256, 0, s>>>(d_ptr, rows, nnz, h->d_colf, d_err);
+    if (nnz > 0) csr_copy_cols_kernel<P><<<h->num_sms * 8, 256, 0, s>>>(d_idx, nnz, cols, h->d_colf, d_err);
+    if (rows > 0) {
+        csr_mark_rows_kernel<P><<<(uint32_t)((rows + 255) / 256), 256, 0, s>>>(d_ptr, rows, nnz, h->d_colf, d_flag, d_err);
+        int rc = device_scan_u32(h, d_flag, rows, d_ord);
+        if (rc) return rc;
+    } else {
+        TKS_CUDA(h, cudaMemsetAsync(d_ord, 0, sizeof(uint64_t), s));
+    }
+    uint64_t n_nonempty = 0;
+    TKS_CUDA(h, cudaMemcpyAsync(&n_nonempty, d_ord + rows, 8, cudaMemcpyDeviceToHost, s));
+    TKS_CUDA(h, cudaStreamSynchronize(s));
+    const bool has_empty = n_nonempty != rows;
+    if (has_empty) {
+        TKS_CUDA(h, cudaMalloc(&h->d_row_map, (n_nonempty ? n_nonempty : 1) * sizeof(uint32_t)));
+        csr_row_map_kernel<<<(uint32_t)((rows + 255) / 256), 256, 0, s>>>(d_flag, d_ord, rows, h->d_row_map);
     }
     csr_chunk_table_kernel<P><<<(uint32_t)((nch + 1 + 127) / 128), 128, 0, s>>>(
-        d_ptr, rows, nnz, h->chunk_nnz, h->n_chunks, h->d_chunk_start, h->d_chunk_rb);
+        d_ptr, rows, nnz, h->chunk_nnz, h->n_chunks, has_empty ? d_ord : nullptr, h->d_chunk_start, h->d_chunk_ord);
     uint32_t herr = 0;
     TKS_CUDA(h, cudaMemcpyAsync(&herr, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     TKS_CUDA(h, cudaStreamSynchronize(s));
     TKS_CUDA(h, cudaGetLastError());
-    cudaFree(d_err);
+    cudaFree(d_err); cudaFree(d_flag); cudaFree(d_ord);
     if (herr) {
         free_matrix(h);
-        return h->fail(TKS_EINVAL, "invalid CSR:%s%s%s", (herr & kErrColRange) ? " column index >= cols;" : "",
-                       (herr & kErrDelta) ? " too many consecutive empty rows;" : "",
+        return h->fail(TKS_EINVAL, "invalid CSR:%s%s", (herr & kErrColRange) ? " column index >= cols;" : "",
                        (herr & kErrPtrOrder) ? " row_ptr not monotone / out of range;" : "");
     }
     h->rows = rows; h->cols = cols; h->nnz = nnz;
-    h->device_bytes = nnz * 8ull + (nch + 1) * 8ull + nch * 4ull;
+    h->device_bytes = nnz * 8ull + (nch + 1) * 8ull + nch * 4ull + (has_empty ? n_nonempty * 4ull : 0ull);
     h->have_matrix = true;
     h->have_result = false;
-    // bytes = nnz*(4+4) + (N+1)*sizeof(rowptr) + C*4 + k*8 ; k added at run time
     h->stats.rows = rows; h->stats.cols = cols; h->stats.nnz = nnz; h->stats.packets = 0;
     h->stats.device_bytes = h->device_bytes;
     return TKS_OK;
@@ -166,15 +193,12 @@ int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false) {
     if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k=%u outside 1..%u", k, h->kmax);
     const int variant = cap_variant_for_k(k);
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
-    CsrDevice m{h->d_val, h->d_colf, h->d_chunk_start, h->d_chunk_rb, h->n_chunks, h->cols,
+    CsrDevice m{h->d_val, h->d_colf, h->d_chunk_start, h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols,
                 (uint32_t)h->row_offset};
-    uint32_t n_sample = h->n_chunks < (uint32_t)h->num_sms * 8u ? h->n_chunks : (uint32_t)h->num_sms * 8u;
+    uint32_t n_sample = h->n_chunks < (uint32_t)h->num_sms * 32u ? h->n_chunks : (uint32_t)h->num_sms * 32u;
     if (n_sample > h->n_sample_cap) n_sample = h->n_sample_cap;
     const uint32_t stride = h->n_chunks / n_sample;
-    uint32_t n2 = 1;
-    while (n2 < n_sample) n2 <<= 1;
-    size_t sample_smem = (size_t)h->cols * 4u;
-    if (sample_smem < (size_t)n2 * 8u) sample_smem = (size_t)n2 * 8u;
+    const size_t sample_smem = ((size_t)h->cols + 1u) * 4u;
     for (uint32_t q = 0; q < h->batch; q++) {
         const float *x = h->d_x + (size_t)q * h->cols;
         RunState *st = h->d_state + q;
@@ -189,7 +213,7 @@ int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false) {
             default: launch_main<2048>(h, 3, m, x, st, k, s); break;
         }
         if (profile && q == 0) cudaEventRecord(h->evm1, s);
-        select_topk_kernel<<<1, kSelectThreads, kSelectSortCap * 8u, s>>>(
+        select_topk_kernel<<<1, kSelectThreads, 0, s>>>(
             h->d_pool, &st->pool_count, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
             h->d_res_idx + (size_t)q * h->kmax, h->d_res_val + (size_t)q * h->kmax, h->d_res_count + q, st);
     }
@@ -233,8 +257,8 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
     if (cfg->mode != TKS_MODE_FLOAT_CSR && cfg->mode != TKS_MODE_FIXED_BSCSR) {
         g_create_error = "unknown mode"; return TKS_EINVAL;
     }
-    if (cfg->max_cols < 1 || cfg->max_cols > (int)(kColMask + 1)) {
-        g_create_error = "max_cols outside 1..16384"; return TKS_EINVAL;
+    if (cfg->max_cols < 1 || cfg->max_cols >= (int)kMaxCols) {
+        g_create_error = "max_cols outside 1..16383"; return TKS_EINVAL;
     }
     if (cfg->mode == TKS_MODE_FIXED_BSCSR) {
         if (cfg->fixed_width < 17 || cfg->fixed_width > 32) { g_create_error = "fixed_width outside 17..32"; return TKS_EINVAL; }
@@ -282,15 +306,9 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
         if ((e = prep_main<512>(h, 1)) != cudaSuccess) return bail("prep_main<512>", e);
         if ((e = prep_main<1024>(h, 2)) != cudaSuccess) return bail("prep_main<1024>", e);
         if ((e = prep_main<2048>(h, 3)) != cudaSuccess) return bail("prep_main<2048>", e);
-        {
-            size_t ss = (size_t)cfg->max_cols * 4u;
-            if (ss < 2048u * 8u) ss = 2048u * 8u;
-            if ((e = cudaFuncSetAttribute(csr_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess)
-                return bail("sample smem attr", e);
-        }
-        if ((e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(kSelectSortCap * 8u))) != cudaSuccess)
-            return bail("select smem attr", e);
+        if ((e = cudaFuncSetAttribute(csr_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(((size_t)cfg->max_cols + 1u) * 4u))) != cudaSuccess)
+            return bail("sample smem attr", e);
         int rc = alloc_query_side(h);
         if (rc != TKS_OK) { g_create_error = h->err; tks_destroy(h); return rc; }
     }
@@ -374,22 +392,18 @@ int tks_generate_synthetic(tks_handle *h, uint64_t rows, uint32_t cols, uint32_t
     h->row_offset = row_offset;
     cudaStream_t s = h->stream;
     uint32_t *d_deg = nullptr;
-    uint64_t *d_bs = nullptr;
-    const uint32_t nb = (uint32_t)((rows + kScanBlock - 1) / kScanBlock);
     TKS_CUDA(h, cudaMalloc(&d_deg, rows * sizeof(uint32_t)));
-    TKS_CUDA(h, cudaMalloc(&d_bs, ((size_t)nb + 1) * sizeof(uint64_t)));
     TKS_CUDA(h, cudaMalloc(&h->d_ptr64, (rows + 1) * sizeof(uint64_t)));
     synth_degree_kernel<<<(uint32_t)((rows + 255) / 256), 256, 0, s>>>(rows, row_offset, seed, avg_degree, dist, d_deg);
-    scan_block_sums_kernel<<<nb, kScanBlock, 0, s>>>(d_deg, rows, d_bs);
-    scan_block_offsets_kernel<<<1, 32, 0, s>>>(d_bs, nb);
-    scan_finish_kernel<<<nb, kScanBlock, 0, s>>>(d_deg, rows, d_bs, h->d_ptr64);
+    rc = device_scan_u32(h, d_deg, rows, h->d_ptr64);
+    if (rc) return rc;
     uint64_t nnz = 0;
     TKS_CUDA(h, cudaMemcpyAsync(&nnz, h->d_ptr64 + rows, 8, cudaMemcpyDeviceToHost, s));
     TKS_CUDA(h, cudaStreamSynchronize(s));
-    cudaFree(d_deg); cudaFree(d_bs);
+    cudaFree(d_deg);
     uint32_t *d_idx = nullptr;
     float *d_val = nullptr;
-    const size_t pad = 1024;
+    const size_t pad = 2048;
     TKS_CUDA(h, cudaMalloc(&d_idx, nnz * sizeof(uint32_t)));
     TKS_CUDA(h, cudaMalloc(&d_val, nnz * sizeof(float) + pad));
     TKS_CUDA(h, cudaMemsetAsync(reinterpret_cast<uint8_t *>(d_val) + nnz * sizeof(float), 0, pad, s));
@@ -408,7 +422,7 @@ int tks_download_csr(tks_handle *h, uint64_t *ptr64, uint32_t *idx, float *val) 
     if (val) TKS_CUDA(h, cudaMemcpy(val, h->d_val, h->nnz * 4, cudaMemcpyDeviceToHost));
     if (idx) {
         TKS_CUDA(h, cudaMemcpy(idx, h->d_colf, h->nnz * 4, cudaMemcpyDeviceToHost));
-        for (uint64_t i = 0; i < h->nnz; i++) idx[i] &= kColMask;
+        for (uint64_t i = 0; i < h->nnz; i++) idx[i] = (idx[i] & kColOffMask) >> 2;
     }
     return TKS_OK;
 }
@@ -538,7 +552,7 @@ int tks_merge_keys_device(tks_handle *h, uint32_t query, const uint64_t *d_keys,
     if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k out of range");
     TKS_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
-    select_topk_kernel<<<1, kSelectThreads, kSelectSortCap * 8u, s>>>(
+    select_topk_kernel<<<1, kSelectThreads, 0, s>>>(
         d_keys, nullptr, n_keys, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX, h->d_res_keys + (size_t)query * h->kmax,
         h->d_res_idx + (size_t)query * h->kmax, h->d_res_val + (size_t)query * h->kmax, h->d_res_count + query,
         nullptr);

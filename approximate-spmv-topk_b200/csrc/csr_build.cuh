@@ -12,7 +12,6 @@ namespace tks {
 
 // error bits written by the build kernels
 constexpr uint32_t kErrColRange = 1u;     // column index >= cols
-constexpr uint32_t kErrDelta = 2u;        // more than kMaxDelta-1 consecutive empty rows
 constexpr uint32_t kErrPtrOrder = 4u;     // row_ptr not non-decreasing / out of range
 
 template <typename P>
@@ -24,50 +23,48 @@ __global__ void csr_copy_cols_kernel(const uint32_t *__restrict__ idx, uint64_t 
     for (; i < nnz; i += stride) {
         uint32_t c = idx[i];
         bad |= (c >= cols);
-        colf[i] = c & kColMask;
+        colf[i] = (c << 2) & kColOffMask;
     }
     if (bad) atomicOr(err, kErrColRange);
 }
 
-// One thread per row: tag the row's first non-zero with (row - previous non-empty row).
+// One thread per row: tag the row's first non-zero; count non-empty rows.
 template <typename P>
 __global__ void csr_mark_rows_kernel(const P *__restrict__ ptr, uint64_t rows, uint64_t nnz,
-                                     uint32_t *__restrict__ colf, uint32_t *err) {
+                                     uint32_t *__restrict__ colf, uint32_t *nonempty_flag, uint32_t *err) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const uint64_t b = ptr[r], e = ptr[r + 1];
-    if (e < b || e > nnz) { atomicOr(err, kErrPtrOrder); return; }
-    if (b == e) return;
-    // previous non-empty row (rows are almost never empty: the loop is O(1) in practice)
-    int64_t q = (int64_t)r - 1;
-    while (q >= 0 && ptr[q] == ptr[q + 1]) q--;
-    const uint64_t delta = (uint64_t)((int64_t)r - q);
-    if (delta > kMaxDelta) { atomicOr(err, kErrDelta); return; }
-    colf[b] |= (uint32_t)delta << kColBits;
+    if (e < b || e > nnz) { atomicOr(err, kErrPtrOrder); nonempty_flag[r] = 0; return; }
+    nonempty_flag[r] = (b != e) ? 1u : 0u;
+    if (b != e) colf[b] |= kRowStartBit;
 }
 
-// One thread per chunk: first row starting at or after c*chunk_nnz.
+// row_map[ordinal] = row for non-empty rows, given ord = exclusive scan of the non-empty flags (as u64).
+__global__ void csr_row_map_kernel(const uint32_t *__restrict__ nonempty_flag, const uint64_t *__restrict__ ord,
+                                   uint64_t rows, uint32_t *__restrict__ row_map) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows && nonempty_flag[r]) row_map[ord[r]] = (uint32_t)r;
+}
+
+// One thread per chunk: first row starting at or after c*chunk_nnz, and its ordinal among non-empty rows.
 template <typename P>
 __global__ void csr_chunk_table_kernel(const P *__restrict__ ptr, uint64_t rows, uint64_t nnz, uint32_t chunk_nnz,
-                                       uint32_t n_chunks, uint64_t *__restrict__ chunk_start,
-                                       uint32_t *__restrict__ chunk_rb) {
+                                       uint32_t n_chunks, const uint64_t *__restrict__ ord,
+                                       uint64_t *__restrict__ chunk_start, uint32_t *__restrict__ chunk_ord) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > n_chunks) return;
     if (c == n_chunks) { chunk_start[c] = nnz; return; }
     const uint64_t target = (uint64_t)c * chunk_nnz;
-    // lower_bound over ptr[0..rows]
-    uint64_t lo = 0, hi = rows;
+    uint64_t lo = 0, hi = rows;   // lower_bound over ptr[0..rows)
     while (lo < hi) {
         uint64_t mid = (lo + hi) >> 1;
         if ((uint64_t)ptr[mid] < target) lo = mid + 1; else hi = mid;
     }
-    // lo = first row with ptr[row] >= target (or rows)
-    uint64_t r1 = lo;
-    while (r1 < rows && ptr[r1] == ptr[r1 + 1]) r1++;          // first non-empty row
+    // lo = first row with ptr[row] >= target (or rows); empty rows at lo share its offset
     chunk_start[c] = (lo < rows) ? (uint64_t)ptr[lo] : nnz;
-    int64_t q = (int64_t)r1 - 1;
-    while (q >= 0 && ptr[q] == ptr[q + 1]) q--;                // last non-empty row before it
-    chunk_rb[c] = (uint32_t)q;                                 // -1 wraps; the kernel only adds deltas to it
+    // ordinal of the first non-empty row >= lo: ord[] is an exclusive count of non-empty rows (nullptr: none empty)
+    chunk_ord[c] = ord ? (uint32_t)((lo < rows) ? ord[lo] : ord[rows]) : (uint32_t)lo;
 }
 
 // ---------------------------------------------------------------------------

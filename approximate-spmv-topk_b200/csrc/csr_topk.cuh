@@ -9,15 +9,16 @@
 //
 // Device layout (built once by tks_upload_csr, see csr_build.cuh):
 //   val  [nnz]  fp32, as uploaded
-//   colf [nnz]  u32 : bits 0..13 column, bits 14..31 "row delta" = how many rows
-//                     the row counter advances AT this element (0 = same row as
-//                     the previous non-zero; >= 1 on the first non-zero of a row;
-//                     > 1 skips empty rows).  Same 4 bytes as a CSR column index,
-//                     so the kernel never reads row_ptr.
-//   chunk_start[c], chunk_rb[c] : work units of ~chunk_nnz non-zeros, aligned to
-//                     row starts; rb = last non-empty row before the chunk.
+//   colf [nnz]  u32 : bits 0..15 = column * 4 (the byte offset of x[col] in shared
+//                     memory), bit 31 = "this non-zero starts a row".  Same 4 bytes
+//                     as a CSR column index, so the kernel never reads row_ptr.
+//   chunk_start[c], chunk_ord[c] : work units of ~chunk_nnz non-zeros aligned to row
+//                     starts; ord = ordinal of the chunk's first row among the
+//                     non-empty rows.  row_map[ord] -> row id exists only when the
+//                     matrix has empty rows (they can never be candidates: the
+//                     reference's COO gold never sees them either).
 //
-// Kernels per query:  csr_sample_kernel (threshold from a 0.3 % sample)
+// Kernels per query:  csr_sample_kernel (threshold from a ~1 % sample)
 //                  -> csr_topk_main_kernel (the HBM stream, > 95 % of the time)
 //                  -> select_topk_kernel   (k best of the surviving candidates)
 #pragma once
@@ -26,12 +27,12 @@
 
 namespace tks {
 
-constexpr uint32_t kColBits = 14;
-constexpr uint32_t kColMask = (1u << kColBits) - 1u;
-constexpr uint32_t kMaxDelta = (1u << (32 - kColBits)) - 1u;
-constexpr uint32_t kElemsPerLane = 4;                       // one 128-bit load per array
-constexpr uint32_t kElemsPerIter = kWarp * kElemsPerLane;   // 128 non-zeros per warp iteration
-constexpr uint32_t kSampleIters = 4;                        // sample = first 512 nnz of a chunk
+constexpr uint32_t kColOffMask = 0xFFFCu;                   // column * 4
+constexpr uint32_t kRowStartBit = 0x80000000u;
+constexpr uint32_t kMaxCols = 16384;                       // exclusive: cols <= 16383 (slot `cols` holds 0.0)
+constexpr uint32_t kEpl = 8;                                // elements per lane: one 256-bit load per array
+constexpr uint32_t kElemsPerIter = kWarp * kEpl;            // 256 non-zeros per warp iteration
+constexpr uint32_t kSampleIters = 2;                        // sample = first 512 nnz of a chunk
 constexpr uint32_t kMainThreads = 512;
 constexpr uint32_t kSampleThreads = 256;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
@@ -40,7 +41,8 @@ struct CsrDevice {
     const float *val;
     const uint32_t *colf;
     const uint64_t *chunk_start;   // n_chunks + 1 entries
-    const uint32_t *chunk_rb;      // n_chunks entries
+    const uint32_t *chunk_ord;     // n_chunks entries
+    const uint32_t *row_map;       // ordinal -> row id, or nullptr when every row is non-empty
     uint32_t n_chunks;
     uint32_t cols;
     uint32_t row_offset;           // added to every reported row id
@@ -52,63 +54,91 @@ struct RunState {
     uint32_t pool_count;      // candidates appended to the global pool
     uint32_t tau_key;         // ordered-float lower bound on the k-th best score (0 = none)
     uint32_t sample_ticket;   // last-block election of the sample kernel
-    uint32_t result_count;
+    uint32_t result_count;    // pool size of the last run (statistics)
     uint32_t pad[3];
 };
 
+struct U32x8 { uint32_t w[8]; };
+
+// 256-bit streaming load (LDG.E.256 on sm_100): read-only path, no L1 allocation --
+// every matrix byte is touched exactly once per query.
+__device__ __forceinline__ U32x8 ldg_stream_256(const void *p) {
+    U32x8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]),
+                   "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
+__device__ __forceinline__ float tau_from_key(uint32_t key) { return key == 0 ? neg_inf() : ordered_to_f32(key); }
+
 // --------------------------------------------------------------------------
-// One warp iteration: 128 consecutive non-zeros, 4 per lane.
-// Produces, for the lane's FIRST row boundary, the total of the row that ends
-// there (T), plus the lane-local pieces needed for rows that start and end
-// inside the lane.  All additions are explicit __fadd_rn/__fmul_rn so that the
-// sample kernel and the main kernel produce bit-identical row sums.
+// One warp iteration: 256 consecutive non-zeros, 8 per lane.
+//   seg[j]  inclusive segmented sum inside the lane (restarts at row starts)
+//   fb      bit j set <=> element j starts a row
+//   T       total of the row that ends at the lane's first row start
+//   cm      max of seg[j-1] over row starts j >= 1: a superset filter for rows that
+//           start and end inside this lane
+// All float ops are explicit __fmul_rn/__fadd_rn so that the sample kernel and the
+// main kernel produce bit-identical row sums (no FMA contraction either way).
 // --------------------------------------------------------------------------
 struct IterState {
-    float seg[4];      // inclusive segmented sums inside the lane
-    uint32_t d[4];     // row deltas
-    float T;           // completed-row total at the lane's first boundary
-    uint32_t nf;       // boundaries in this lane
-    uint32_t dsum;     // sum of deltas in this lane
-    unsigned fm;       // ballot: lanes with >= 1 boundary
+    float seg[8];
+    float T, cm;
+    uint32_t fb, nf;
+    unsigned fm;   // ballot: lanes with >= 1 row start
 };
 
 template <bool MASKED>
-__device__ __forceinline__ void csr_iter(const uint4 vraw, const uint4 craw, const float *__restrict__ xs,
-                                         uint64_t ebase, uint64_t s, uint64_t e, float carry_in,
+__device__ __forceinline__ void csr_iter(const U32x8 &vraw, const U32x8 &craw, const uint8_t *__restrict__ xs_bytes,
+                                         uint32_t zero_off, uint32_t lo, uint32_t hi, float carry_in,
                                          float &carry_out, IterState &o) {
     const unsigned lane = lane_id();
-    float v[4] = {__uint_as_float(vraw.x), __uint_as_float(vraw.y), __uint_as_float(vraw.z),
-                  __uint_as_float(vraw.w)};
-    uint32_t c[4] = {craw.x, craw.y, craw.z, craw.w};
-    float p[4];
+    uint32_t frev = 0;
+    float cm = neg_inf();
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        o.d[j] = c[j] >> kColBits;
-        p[j] = __fmul_rn(v[j], xs[c[j] & kColMask]);
+    for (int j = 0; j < 8; j++) {
+        uint32_t c = craw.w[j];
+        uint32_t vbits = vraw.w[j];
         if (MASKED) {
-            bool in = (ebase + j >= s) && (ebase + j < e);
-            p[j] = in ? p[j] : 0.0f;
-            o.d[j] = in ? o.d[j] : 0u;
+            const bool in = ((uint32_t)j >= lo) && ((uint32_t)j < hi);
+            c = in ? c : zero_off;      // column -> the zero slot behind x, no row start
+            vbits = in ? vbits : 0u;
+        }
+        const float x = *reinterpret_cast<const float *>(xs_bytes + (c & kColOffMask));
+        const float p = __fmul_rn(__uint_as_float(vbits), x);
+        const bool f = (int32_t)c < 0;
+        frev = __funnelshift_l(c, frev, 1);   // collects bit 31 of every element
+        if (j == 0) {
+            o.seg[0] = p;
+        } else {
+            if (f) cm = fmaxf(cm, o.seg[j - 1]);
+            o.seg[j] = f ? p : __fadd_rn(o.seg[j - 1], p);
         }
     }
-    const bool f0 = o.d[0] != 0, f1 = o.d[1] != 0, f2 = o.d[2] != 0, f3 = o.d[3] != 0;
-    o.seg[0] = p[0];
-    o.seg[1] = f1 ? p[1] : __fadd_rn(o.seg[0], p[1]);
-    o.seg[2] = f2 ? p[2] : __fadd_rn(o.seg[1], p[2]);
-    o.seg[3] = f3 ? p[3] : __fadd_rn(o.seg[2], p[3]);
-    const float head = f0 ? 0.0f : (f1 ? o.seg[0] : (f2 ? o.seg[1] : (f3 ? o.seg[2] : o.seg[3])));
-    o.nf = (uint32_t)f0 + (uint32_t)f1 + (uint32_t)f2 + (uint32_t)f3;
-    o.dsum = o.d[0] + o.d[1] + o.d[2] + o.d[3];
-    o.fm = __ballot_sync(kFull, o.nf != 0);
+    o.cm = cm;
+    o.fb = __brev(frev) >> 24;   // bit j <=> element j starts a row
+    o.nf = __popc(o.fb);
+    o.fm = __ballot_sync(kFull, o.fb != 0);
 
-    // inclusive segmented scan of the lane tails; segments restart at lanes with a boundary
+    // head = sum of the elements before the lane's first row start (whole lane if none)
+    const uint32_t t = (uint32_t)__ffs((int)o.fb) - 1u;   // first row start (undefined when fb == 0)
+    const bool b0 = t & 1u, b1 = t & 2u, b2 = t & 4u;
+    const float a0 = b0 ? o.seg[0] : 0.0f, a1 = b0 ? o.seg[2] : o.seg[1];
+    const float a2 = b0 ? o.seg[4] : o.seg[3], a3 = b0 ? o.seg[6] : o.seg[5];
+    const float c0 = b1 ? a1 : a0, c1 = b1 ? a3 : a2;
+    const float head = (o.fb == 0) ? o.seg[7] : (b2 ? c1 : c0);
+
+    // inclusive segmented scan of the lane tails; segments restart at lanes with a row start
     const unsigned le = o.fm & lanemask_le();
-    const int seg_start = le ? (31 - __clz(le)) : 0;
-    float I = o.seg[3];
+    const int dist = (int)lane - (le ? (31 - __clz(le)) : 0);
+    float I = o.seg[7];
 #pragma unroll
     for (int dlt = 1; dlt < 32; dlt <<= 1) {
-        float t = __shfl_up_sync(kFull, I, dlt);
-        if ((int)lane - dlt >= seg_start) I = __fadd_rn(I, t);
+        const float up = __shfl_up_sync(kFull, I, dlt);
+        if (dist >= dlt) I = __fadd_rn(I, up);
     }
     float E = __shfl_up_sync(kFull, I, 1);
     if (lane == 0) E = 0.0f;
@@ -130,11 +160,12 @@ struct MaxSink {
 
 template <int CAP>
 struct PoolSink {
-    uint64_t *buf;        // this warp's CAP keys in shared memory
-    uint32_t cnt;         // warp-uniform
+    uint64_t *buf;            // this warp's CAP keys in shared memory
+    uint32_t cnt;             // warp-uniform
     uint32_t k;
-    float tau;            // current lower bound used by the filter
-    uint32_t *tau_key_g;  // global lower bound (atomicMax)
+    float tau;                // current lower bound used by the filter
+    uint32_t *tau_key_g;      // global lower bound (atomicMax)
+    const uint32_t *row_map;
     uint32_t row_offset;
     int tie_higher;
 
@@ -148,16 +179,18 @@ struct PoolSink {
             uint32_t old = 0;
             if (lane == 0) old = atomicMax(tau_key_g, tk);
             old = __shfl_sync(kFull, old, 0);
-            const uint32_t best = old > tk ? old : tk;
-            tau = ordered_to_f32(best);
+            tau = ordered_to_f32(old > tk ? old : tk);
         }
     }
-    __device__ __forceinline__ void emit(bool pred, float score, uint32_t row) {
+    __device__ __forceinline__ void emit(bool pred, float score, uint32_t ord) {
         const unsigned m = __ballot_sync(kFull, pred);
         if (m == 0) return;
         const uint32_t n = __popc(m);
         if (cnt + n > CAP) compact();
-        if (pred) buf[cnt + __popc(m & lanemask_lt())] = make_key(f32_to_ordered(score), row + row_offset, tie_higher);
+        if (pred) {
+            const uint32_t row = (row_map ? row_map[ord] : ord) + row_offset;
+            buf[cnt + __popc(m & lanemask_lt())] = make_key(f32_to_ordered(score), row, tie_higher);
+        }
         cnt += n;
         __syncwarp();
     }
@@ -165,82 +198,135 @@ struct PoolSink {
 
 // Stream one chunk (or its first max_iters iterations) through `sink`.
 template <typename Sink>
-__device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const float *__restrict__ xs, uint32_t c,
-                                                  uint32_t max_iters, bool flush_tail, Sink &sink) {
+__device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint32_t c,
+                                                  uint32_t max_iters, Sink &sink) {
     const unsigned lane = lane_id();
     const uint64_t s = m.chunk_start[c], e = m.chunk_start[c + 1];
     if (s >= e) return;
-    const uint64_t a0 = s & ~3ull;
-    uint64_t n_iter64 = (e - a0 + kElemsPerIter - 1) / kElemsPerIter;
+    const uint64_t a0 = s & ~7ull;                       // 32-byte aligned start of the first 256-bit load
+    const uint64_t n_iter64 = (e - a0 + kElemsPerIter - 1) / kElemsPerIter;
     const bool truncated = n_iter64 > max_iters;
     const uint32_t n_iter = truncated ? max_iters : (uint32_t)n_iter64;
-    const uint4 *vp = reinterpret_cast<const uint4 *>(m.val + a0) + lane;
-    const uint4 *cp = reinterpret_cast<const uint4 *>(m.colf + a0) + lane;
+    const uint32_t last_iter = (uint32_t)n_iter64 - 1;   // chunks are far smaller than 2^32 * 256 non-zeros
+    const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val + a0) + lane * 32u;
+    const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.colf + a0) + lane * 32u;
+    const uint32_t zero_off = m.cols * 4u;
 
-    uint32_t R = m.chunk_rb[c];   // row in progress (the bogus one before the chunk at first)
+    uint32_t R = m.chunk_ord[c] - 1u;   // ordinal of the row "in progress" (a bogus one before the chunk at first)
     bool first_pending = true;
     float carry = 0.0f;
 
-    // two-deep software prefetch: loads of iterations it+1 and it+2 are in flight while it is reduced
-    uint4 v1 = ldg_stream_u4(vp), c1 = ldg_stream_u4(cp);
-    uint4 v2 = v1, c2 = c1;
-    if (n_iter > 1) { v2 = ldg_stream_u4(vp + kWarp); c2 = ldg_stream_u4(cp + kWarp); }
-
+    U32x8 nv = ldg_stream_256(vp), nc = ldg_stream_256(cp);
+#pragma unroll 2
     for (uint32_t it = 0; it < n_iter; it++) {
-        const uint4 cv = v1, cc = c1;
-        v1 = v2; c1 = c2;
-        if (it + 2 < n_iter) {
-            v2 = ldg_stream_u4(vp + (size_t)(it + 2) * kWarp);
-            c2 = ldg_stream_u4(cp + (size_t)(it + 2) * kWarp);
-        }
-        const uint64_t ebase = a0 + (uint64_t)it * kElemsPerIter + lane * kElemsPerLane;
+        const U32x8 cv = nv, cc = nc;
+        vp += kElemsPerIter * 4u;
+        cp += kElemsPerIter * 4u;
+        if (it + 1 < n_iter) { nv = ldg_stream_256(vp); nc = ldg_stream_256(cp); }
         IterState o;
         float carry_out;
-        if (it == 0 || it + 1 == (uint32_t)n_iter64)
-            csr_iter<true>(cv, cc, xs, ebase, s, e, carry, carry_out, o);
-        else
-            csr_iter<false>(cv, cc, xs, ebase, s, e, carry, carry_out, o);
+        if (it == 0 || it == last_iter) {
+            // lanes' elements outside [s, e) are neutralised
+            const int64_t ebase = (int64_t)(a0 + (uint64_t)it * kElemsPerIter + lane * kEpl);
+            const int64_t l64 = (int64_t)s - ebase, h64 = (int64_t)e - ebase;
+            const uint32_t lo = l64 < 0 ? 0u : (l64 > 8 ? 8u : (uint32_t)l64);
+            const uint32_t hi = h64 < 0 ? 0u : (h64 > 8 ? 8u : (uint32_t)h64);
+            csr_iter<true>(cv, cc, xs_bytes, zero_off, lo, hi, carry, carry_out, o);
+        } else {
+            csr_iter<false>(cv, cc, xs_bytes, zero_off, 0u, 8u, carry, carry_out, o);
+        }
         carry = carry_out;
 
-        const bool pass = (o.nf != 0) && (o.T >= sink.tau);
-        const unsigned pm = __ballot_sync(kFull, pass);
-        const unsigned im = __ballot_sync(kFull, o.nf >= 2);
-        const uint32_t Rtot = __reduce_add_sync(kFull, o.dsum);
-        if (pm | im) {
-            // row id in progress when entering this lane = R + exclusive prefix of deltas
-            uint32_t pre = o.dsum;
+        const bool passT = (o.fb != 0) && (o.T >= sink.tau);
+        const unsigned pm = __ballot_sync(kFull, passT || (o.cm >= sink.tau));
+        const uint32_t Rtot = __reduce_add_sync(kFull, o.nf);
+        if (pm) {
+            // ordinal of the row in progress when entering this lane = R + rows started in lower lanes
+            uint32_t pre = o.nf;
 #pragma unroll
             for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                uint32_t t = __shfl_up_sync(kFull, pre, dlt);
-                if ((int)lane >= dlt) pre += t;
+                const uint32_t up = __shfl_up_sync(kFull, pre, dlt);
+                if ((int)lane >= dlt) pre += up;
             }
-            const uint32_t Rl = R + (pre - o.dsum);
+            const uint32_t ord_l = R + (pre - o.nf);
             const bool bogus = first_pending && (lane == (unsigned)(__ffs(o.fm) - 1));
-            sink.emit(pass && !bogus, o.T, Rl);
-            if (im) {
-                // rows that start AND end inside one lane (length <= 3)
-                uint32_t Rj = Rl;
-                bool seen = false;
+            sink.emit(passT && !bogus, o.T, ord_l);
+            if (__any_sync(kFull, o.nf >= 2)) {
+                // rows that start AND end inside one lane (length <= 7)
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const bool fj = o.d[j] != 0;
-                    const float sv = o.seg[j > 0 ? j - 1 : 0];
-                    sink.emit(fj && seen && (sv >= sink.tau), sv, Rj);
-                    if (fj) { seen = true; Rj += o.d[j]; }
+                for (int j = 1; j < 8; j++) {
+                    const uint32_t below = o.fb & ((1u << j) - 1u);
+                    const bool ends_here = ((o.fb >> j) & 1u) && below != 0;
+                    sink.emit(ends_here && (o.seg[j - 1] >= sink.tau), o.seg[j - 1], ord_l + __popc(below));
                 }
             }
         }
         if (o.fm) first_pending = false;
         R += Rtot;
     }
-    if (flush_tail && !truncated) {
+    if (!truncated) {
         // the row in progress at the end of the chunk is complete (chunks end on row boundaries)
         sink.emit(lane == 0 && !first_pending && (carry >= sink.tau), carry, R);
     }
 }
 
-__device__ __forceinline__ float tau_from_key(uint32_t key) {
-    return key == 0 ? -__int_as_float(0x7f800000) : ordered_to_f32(key);
+// --------------------------------------------------------------------------
+// Exact k-th largest of n 32-bit keys held in shared memory, by a whole CTA:
+// MSB radix select, 8 bits per pass, warp-aggregated histogram updates (the
+// keys of one pass mostly share their digit, plain atomics would serialise).
+// Returns 0 when n < k.  hist: 256 words of shared memory.
+// --------------------------------------------------------------------------
+template <typename KeyT, typename LoadF>
+__device__ __forceinline__ KeyT block_radix_select(LoadF load, uint32_t n, uint32_t k, uint32_t *hist,
+                                                   uint32_t *s_bin, uint32_t *s_above) {
+    if (n < k) return (KeyT)0;
+    KeyT prefix = 0, pmask = 0;
+    uint32_t need = k;
+    for (int shift = (int)sizeof(KeyT) * 8 - 8; shift >= 0; shift -= 8) {
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const uint32_t n_round = (n + blockDim.x - 1) / blockDim.x * blockDim.x;
+        for (uint32_t i = threadIdx.x; i < n_round; i += blockDim.x) {
+            const bool in = i < n;
+            const KeyT key = in ? load(i) : (KeyT)0;
+            const bool act = in && ((key & pmask) == prefix);
+            const uint32_t digit = (uint32_t)(key >> shift) & 0xFFu;
+            const unsigned am = __ballot_sync(kFull, act);
+            if (act) {
+                const unsigned peers = __match_any_sync(am, digit);
+                if ((unsigned)(__ffs(peers) - 1) == lane_id()) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // suffix sums over 256 bins by one warp: lane l owns bins 8l..8l+7
+            uint32_t loc[8], tot = 0;
+#pragma unroll
+            for (int b = 0; b < 8; b++) { loc[b] = hist[threadIdx.x * 8 + b]; tot += loc[b]; }
+            uint32_t suf = tot;   // inclusive suffix over lanes
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                const uint32_t dn = __shfl_down_sync(kFull, suf, dlt);
+                if (threadIdx.x + dlt < 32) suf += dn;
+            }
+            uint32_t above = suf - tot;   // keys in bins of higher lanes
+            // the wanted bin is the highest b with (count of bins > b) < need <= (count of bins >= b)
+            int found = -1;
+            uint32_t found_above = 0;
+#pragma unroll
+            for (int b = 7; b >= 0; b--) {
+                if (found < 0 && above < need && above + loc[b] >= need) { found = (int)threadIdx.x * 8 + b; found_above = above; }
+                above += loc[b];
+            }
+            if (found >= 0) { *s_bin = (uint32_t)found; *s_above = found_above; }
+        }
+        __syncthreads();
+        prefix |= (KeyT)(*s_bin) << shift;
+        pmask |= (KeyT)0xFF << shift;
+        need -= *s_above;
+        __syncthreads();
+    }
+    return prefix;
 }
 
 // --------------------------------------------------------------------------
@@ -255,35 +341,30 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
                                                                      uint32_t k) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float *xs = reinterpret_cast<float *>(smem_raw);
-    for (uint32_t i = threadIdx.x; i < m.cols; i += blockDim.x) xs[i] = x[i];
+    for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? x[i] : 0.0f;
     __syncthreads();
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
     if (gw < n_sample) {
-        MaxSink sink{0.0f, false, tau_from_key(0)};
+        MaxSink sink{0.0f, false, neg_inf()};
         const uint32_t c = gw * stride;
-        if (c < m.n_chunks) csr_process_chunk(m, xs, c, kSampleIters, true, sink);
-        // warp max
+        if (c < m.n_chunks) csr_process_chunk(m, smem_raw, c, kSampleIters, sink);
         uint32_t key = sink.any ? f32_to_ordered(sink.best) : 0u;
         key = __reduce_max_sync(kFull, key);
         if (lane_id() == 0) sample_keys[gw] = key;
     }
     // last block picks the k-th largest
-    __shared__ uint32_t s_ticket;
+    __shared__ uint32_t s_ticket, s_bin, s_above;
+    __shared__ uint32_t hist[256];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_ticket = atomicAdd(&st->sample_ticket, 1u);
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
     __threadfence();
-    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);   // reuse (x no longer needed)
-    uint32_t n2 = 1;
-    while (n2 < n_sample) n2 <<= 1;
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x)
-        keys[i] = (i < n_sample) ? (uint64_t)ld_relaxed_u32(sample_keys + i) : 0ull;
-    bitonic_sort_desc(keys, n2, threadIdx.x, blockDim.x, [] { __syncthreads(); });
+    const uint32_t kth = block_radix_select<uint32_t>([&](uint32_t i) { return ld_relaxed_u32(sample_keys + i); },
+                                                      n_sample, k, hist, &s_bin, &s_above);
     if (threadIdx.x == 0) {
-        if (k <= n_sample && keys[k - 1] != 0ull) atomicMax(&st->tau_key, (uint32_t)keys[k - 1]);
+        if (kth != 0) atomicMax(&st->tau_key, kth);
         st->sample_ticket = 0;
     }
 }
@@ -299,17 +380,18 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
                      int tie_higher) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float *xs = reinterpret_cast<float *>(smem_raw);
-    uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + ((m.cols * 4u + 15u) & ~15u));
-    for (uint32_t i = threadIdx.x; i < m.cols; i += blockDim.x) xs[i] = x[i];
+    uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (((m.cols + 1u) * 4u + 15u) & ~15u));
+    for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? x[i] : 0.0f;
     __syncthreads();
 
     const unsigned lane = lane_id();
     PoolSink<CAP> sink;
     sink.buf = bufs + (threadIdx.x / kWarp) * CAP;
     sink.cnt = 0;
-    sink.tau = tau_from_key(0);
+    sink.tau = neg_inf();
     sink.k = k;
     sink.tau_key_g = &st->tau_key;
+    sink.row_map = m.row_map;
     sink.row_offset = m.row_offset;
     sink.tie_higher = tie_higher;
 
@@ -319,7 +401,7 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
         c = __shfl_sync(kFull, c, 0);
         if (c >= m.n_chunks) break;
         sink.tau = fmaxf(sink.tau, tau_from_key(ld_relaxed_u32(&st->tau_key)));
-        csr_process_chunk(m, xs, c, 0xFFFFFFFFu, true, sink);
+        csr_process_chunk(m, smem_raw, c, 0xFFFFFFFFu, sink);
     }
 
     // hand the survivors to the global pool (filtered by the freshest bound)
@@ -327,7 +409,7 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
     __syncwarp();
     for (uint32_t base = 0; base < sink.cnt; base += kWarp) {
         const uint32_t i = base + lane;
-        uint64_t key = (i < sink.cnt) ? sink.buf[i] : 0ull;
+        const uint64_t key = (i < sink.cnt) ? sink.buf[i] : 0ull;
         const bool keep = (i < sink.cnt) && (key_score(key) >= tk);
         const unsigned mk = __ballot_sync(kFull, keep);
         if (mk) {
@@ -340,21 +422,21 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
 }
 
 // --------------------------------------------------------------------------
-// Kernel 3: k best keys of a pool, one CTA.  Pools that fit the shared-memory
-// sorter are sorted directly; larger ones go through an exact MSB radix select
-// first.  Also resets the per-query scratch for the next run.
+// Kernel 3: k best keys of a pool, one CTA.  Small pools are sorted directly in
+// shared memory; larger ones go through the exact radix select first (keys are
+// unique, so exactly k keys are >= the k-th largest).  Also resets the per-query
+// scratch for the next run.
 // --------------------------------------------------------------------------
 constexpr uint32_t kSelectThreads = 1024;
-constexpr uint32_t kSelectSortCap = 8192;   // 64 KB of keys
+constexpr uint32_t kSelectSortCap = 2048;   // keys sorted directly (16 KB)
 
 __global__ void __launch_bounds__(kSelectThreads)
 select_topk_kernel(const uint64_t *__restrict__ pool, const uint32_t *pool_count_ptr, uint32_t pool_count_imm,
                    uint32_t k, int tie_higher, uint64_t *out_keys, uint32_t *out_idx, float *out_val,
                    uint32_t *out_count, RunState *st_reset) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);
+    __shared__ uint64_t keys[kSelectSortCap];
     __shared__ uint32_t hist[256];
-    __shared__ uint32_t s_sel_bin, s_above, s_cnt;
+    __shared__ uint32_t s_bin, s_above, s_cnt;
     const uint32_t tid = threadIdx.x;
     const uint32_t n = pool_count_ptr ? *pool_count_ptr : pool_count_imm;
 
@@ -363,40 +445,13 @@ select_topk_kernel(const uint64_t *__restrict__ pool, const uint32_t *pool_count
         for (uint32_t i = tid; i < n; i += blockDim.x) keys[i] = pool[i];
         m = n;
     } else {
-        // exact radix select of the k-th largest key, 8 bits at a time from the top
-        uint64_t prefix = 0, pmask = 0;
-        uint32_t need = k < n ? k : n;   // rank still wanted inside the current prefix bucket
-        for (int shift = 56; shift >= 0; shift -= 8) {
-            for (uint32_t i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-            __syncthreads();
-            for (uint32_t i = tid; i < n; i += blockDim.x) {
-                uint64_t key = pool[i];
-                if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1u);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                uint32_t acc = 0;
-                int b = 255;
-                for (; b > 0; b--) {
-                    if (acc + hist[b] >= need) break;
-                    acc += hist[b];
-                }
-                s_sel_bin = (uint32_t)b;
-                s_above = acc;
-            }
-            __syncthreads();
-            prefix |= (uint64_t)s_sel_bin << shift;
-            pmask |= 0xFFull << shift;
-            need -= s_above;
-            __syncthreads();
-        }
-        // prefix is now the k-th largest key; keys are unique, so exactly min(k,n) keys are >= it
+        const uint64_t kth = block_radix_select<uint64_t>([&](uint32_t i) { return pool[i]; }, n, k, hist, &s_bin, &s_above);
         if (tid == 0) s_cnt = 0;
         __syncthreads();
         for (uint32_t i = tid; i < n; i += blockDim.x) {
-            uint64_t key = pool[i];
-            if (key >= prefix) {
-                uint32_t pos = atomicAdd(&s_cnt, 1u);
+            const uint64_t key = pool[i];
+            if (key >= kth && key != 0ull) {
+                const uint32_t pos = atomicAdd(&s_cnt, 1u);
                 if (pos < kSelectSortCap) keys[pos] = key;
             }
         }

@@ -32,7 +32,8 @@ struct Handle {
     uint32_t *d_colf = nullptr;
     uint64_t *d_ptr64 = nullptr;        // kept for tks_download_csr (exact copy of row_ptr as u64)
     uint64_t *d_chunk_start = nullptr;
-    uint32_t *d_chunk_rb = nullptr;
+    uint32_t *d_chunk_ord = nullptr;
+    uint32_t *d_row_map = nullptr;      // ordinal -> row, only when the matrix has empty rows
     uint32_t n_chunks = 0, chunk_nnz = 0;
     uint64_t device_bytes = 0;
 

@@ -216,7 +216,11 @@ def ours(args):
     shards = tks.sharding.plan_row_shards_even(rows_total, world)
     r0, r1 = shards[rank]
     peak_gbs, peak_src = measured_peaks()
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default torch stream: everything of a step (query copy, our kernels, NCCL, merge) is enqueued on it
+    # and the CUDA events that time the region are recorded on it (a NULL stream would mean "the handle's own")
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
     nsteps = args.warmup + args.steps
     queries = make_queries(cols, nsteps)
 
@@ -334,6 +338,7 @@ def ours(args):
                         "h2d_bytes_per_step": cols * 4, "d2h_bytes_per_step": K * 8 + 4,
                         "api": "SpMV.reset(host vec) -> operator() -> read_result(host)"},
                 "gpu_launches": args.steps * (3 if world == 1 else 4),
+                "candidates_last_step": int(stats.last_candidates),
                 "hbm_gbs_effective": alg_bytes_local * world / (ms_step * 1e-3) / 1e9,
                 "clocks": clocks}
         print(json.dumps(line), flush=True)

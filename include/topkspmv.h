@@ -53,7 +53,7 @@ typedef struct tks_config {
     int32_t partitions;            /* SPMV_PARTITIONS types.hpp:36 (BS-CSR mode only)         */
     int32_t local_k;               /* K  types.hpp:51  per-lane local top-K (BS-CSR mode)     */
     int32_t limited_finished_rows; /* LIMITED_FINISHED_ROWS types.hpp:77 (BS-CSR mode)        */
-    int32_t max_cols;              /* MAX_COLS types.hpp:55 (1024; float mode accepts <=16384) */
+    int32_t max_cols;              /* MAX_COLS types.hpp:55 (1024; float mode accepts <=16383) */
     int32_t tie_break;             /* TKS_TIE_*                                               */
     int32_t device;                /* CUDA device ordinal                                     */
     int32_t max_batch;             /* max queries per run (float mode), >= 1                  */

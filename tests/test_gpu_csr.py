@@ -132,7 +132,7 @@ def test_negative_and_zero_scores_exact(cuda_required, tks, orc):
 def test_long_rows_and_wide_matrix(cuda_required, tks, orc):
     """Rows far longer than a chunk, cols up to the 14-bit limit."""
     rng = np.random.default_rng(8)
-    rows, cols = 64, 16384
+    rows, cols = 64, 16383
     deg = rng.integers(1, 9000, rows)
     ptr = np.zeros(rows + 1, np.uint64)
     np.cumsum(deg, out=ptr[1:])
