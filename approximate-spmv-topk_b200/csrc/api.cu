@@ -198,7 +198,8 @@ int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false) {
     uint32_t n_sample = h->n_chunks < (uint32_t)h->num_sms * 32u ? h->n_chunks : (uint32_t)h->num_sms * 32u;
     if (n_sample > h->n_sample_cap) n_sample = h->n_sample_cap;
     const uint32_t stride = h->n_chunks / n_sample;
-    const size_t sample_smem = ((size_t)h->cols + 1u) * 4u;
+    size_t sample_smem = ((size_t)h->cols + 1u) * 4u;
+    if (sample_smem < (size_t)n_sample * 4u) sample_smem = (size_t)n_sample * 4u;
     for (uint32_t q = 0; q < h->batch; q++) {
         const float *x = h->d_x + (size_t)q * h->cols;
         RunState *st = h->d_state + q;
@@ -213,7 +214,7 @@ int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false) {
             default: launch_main<2048>(h, 3, m, x, st, k, s); break;
         }
         if (profile && q == 0) cudaEventRecord(h->evm1, s);
-        select_topk_kernel<<<1, kSelectThreads, 0, s>>>(
+        select_topk_kernel<<<1, kSelectThreads, kSelectSmemKeys * 8u, s>>>(
             h->d_pool, &st->pool_count, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
             h->d_res_idx + (size_t)q * h->kmax, h->d_res_val + (size_t)q * h->kmax, h->d_res_count + q, st);
     }
@@ -306,9 +307,15 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
         if ((e = prep_main<512>(h, 1)) != cudaSuccess) return bail("prep_main<512>", e);
         if ((e = prep_main<1024>(h, 2)) != cudaSuccess) return bail("prep_main<1024>", e);
         if ((e = prep_main<2048>(h, 3)) != cudaSuccess) return bail("prep_main<2048>", e);
-        if ((e = cudaFuncSetAttribute(csr_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(((size_t)cfg->max_cols + 1u) * 4u))) != cudaSuccess)
-            return bail("sample smem attr", e);
+        {
+            size_t ss = ((size_t)cfg->max_cols + 1u) * 4u;
+            if (ss < 8192u * 4u) ss = 8192u * 4u;
+            if ((e = cudaFuncSetAttribute(csr_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess)
+                return bail("sample smem attr", e);
+            if ((e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(kSelectSmemKeys * 8u))) != cudaSuccess)
+                return bail("select smem attr", e);
+        }
         int rc = alloc_query_side(h);
         if (rc != TKS_OK) { g_create_error = h->err; tks_destroy(h); return rc; }
     }
@@ -552,7 +559,7 @@ int tks_merge_keys_device(tks_handle *h, uint32_t query, const uint64_t *d_keys,
     if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k out of range");
     TKS_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
-    select_topk_kernel<<<1, kSelectThreads, 0, s>>>(
+    select_topk_kernel<<<1, kSelectThreads, kSelectSmemKeys * 8u, s>>>(
         d_keys, nullptr, n_keys, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX, h->d_res_keys + (size_t)query * h->kmax,
         h->d_res_idx + (size_t)query * h->kmax, h->d_res_val + (size_t)query * h->kmax, h->d_res_count + query,
         nullptr);

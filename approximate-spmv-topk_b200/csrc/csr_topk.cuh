@@ -271,12 +271,15 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
 }
 
 // --------------------------------------------------------------------------
-// Exact k-th largest of n 32-bit keys held in shared memory, by a whole CTA:
-// MSB radix select, 8 bits per pass, warp-aggregated histogram updates (the
-// keys of one pass mostly share their digit, plain atomics would serialise).
-// Returns 0 when n < k.  hist: 256 words of shared memory.
+// Exact top-k threshold of n keys (load(i), normally shared memory) by a whole
+// CTA: MSB radix select, 8 bits per pass, warp-aggregated histogram updates (the
+// keys of one pass mostly share their digit; plain atomics would serialise).
+// Returns a threshold `thr` such that exactly-or-at-least k keys are >= thr and
+// every key >= thr is among the k largest when keys are unique; stops as soon
+// as a whole bucket is needed (usually after 3-4 passes).  Returns 0 when n < k.
+// hist: 256 words of shared memory; s_bin/s_above: 2 words.
 // --------------------------------------------------------------------------
-template <typename KeyT, typename LoadF>
+template <typename KeyT, bool EARLY_EXIT, typename LoadF>
 __device__ __forceinline__ KeyT block_radix_select(LoadF load, uint32_t n, uint32_t k, uint32_t *hist,
                                                    uint32_t *s_bin, uint32_t *s_above) {
     if (n < k) return (KeyT)0;
@@ -310,21 +313,24 @@ __device__ __forceinline__ KeyT block_radix_select(LoadF load, uint32_t n, uint3
                 if (threadIdx.x + dlt < 32) suf += dn;
             }
             uint32_t above = suf - tot;   // keys in bins of higher lanes
-            // the wanted bin is the highest b with (count of bins > b) < need <= (count of bins >= b)
-            int found = -1;
-            uint32_t found_above = 0;
+            // the wanted bin is the highest b with (keys in bins > b) < need <= (keys in bins >= b)
 #pragma unroll
             for (int b = 7; b >= 0; b--) {
-                if (found < 0 && above < need && above + loc[b] >= need) { found = (int)threadIdx.x * 8 + b; found_above = above; }
+                if (above < need && above + loc[b] >= need) {
+                    s_bin[0] = threadIdx.x * 8 + b;
+                    s_above[0] = above;
+                    s_above[1] = loc[b];
+                }
                 above += loc[b];
             }
-            if (found >= 0) { *s_bin = (uint32_t)found; *s_above = found_above; }
         }
         __syncthreads();
-        prefix |= (KeyT)(*s_bin) << shift;
+        prefix |= (KeyT)s_bin[0] << shift;
         pmask |= (KeyT)0xFF << shift;
-        need -= *s_above;
+        need -= s_above[0];
+        const bool whole_bucket = (need == s_above[1]);
         __syncthreads();
+        if (EARLY_EXIT && whole_bucket) break;   // every key of this bucket is wanted: prefix (low bits 0) is the threshold
     }
     return prefix;
 }
@@ -334,6 +340,7 @@ __device__ __forceinline__ KeyT block_radix_select(LoadF load, uint32_t n, uint3
 // iterations of chunk w*stride exactly as the main kernel will and keeps the
 // best completed row.  The k-th largest of these warp maxima is the score of k
 // distinct real rows, hence a valid lower bound on the k-th best score.
+// Dynamic shared memory: max((cols+1)*4, n_sample*4) bytes.
 // --------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m, const float *__restrict__ x,
                                                                      RunState *st, uint32_t *sample_keys,
@@ -353,7 +360,7 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
         if (lane_id() == 0) sample_keys[gw] = key;
     }
     // last block picks the k-th largest
-    __shared__ uint32_t s_ticket, s_bin, s_above;
+    __shared__ uint32_t s_ticket, s_bin, s_above[2];
     __shared__ uint32_t hist[256];
     __threadfence();
     __syncthreads();
@@ -361,10 +368,12 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
     __threadfence();
-    const uint32_t kth = block_radix_select<uint32_t>([&](uint32_t i) { return ld_relaxed_u32(sample_keys + i); },
-                                                      n_sample, k, hist, &s_bin, &s_above);
+    uint32_t *skeys = reinterpret_cast<uint32_t *>(smem_raw);   // x is no longer needed by this block
+    for (uint32_t i = threadIdx.x; i < n_sample; i += blockDim.x) skeys[i] = __ldcg(sample_keys + i);
+    __syncthreads();
+    const uint32_t thr = block_radix_select<uint32_t, false>([&](uint32_t i) { return skeys[i]; }, n_sample, k, hist, &s_bin, s_above);
     if (threadIdx.x == 0) {
-        if (kth != 0) atomicMax(&st->tau_key, kth);
+        if (thr != 0) atomicMax(&st->tau_key, thr);
         st->sample_ticket = 0;
     }
 }
@@ -422,35 +431,45 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
 }
 
 // --------------------------------------------------------------------------
-// Kernel 3: k best keys of a pool, one CTA.  Small pools are sorted directly in
-// shared memory; larger ones go through the exact radix select first (keys are
-// unique, so exactly k keys are >= the k-th largest).  Also resets the per-query
-// scratch for the next run.
+// Kernel 3: k best keys of a pool, one CTA.  The pool is staged in shared memory
+// (up to kSelectSmemKeys keys; larger pools are read from L2 on every pass),
+// reduced with the radix select to the <= kSelectSortCap keys above the
+// threshold, and those are sorted.  Also resets the per-query scratch.
+// Dynamic shared memory: kSelectSmemKeys * 8 bytes.
 // --------------------------------------------------------------------------
 constexpr uint32_t kSelectThreads = 1024;
-constexpr uint32_t kSelectSortCap = 2048;   // keys sorted directly (16 KB)
+constexpr uint32_t kSelectSortCap = 2048;     // keys sorted directly (16 KB static)
+constexpr uint32_t kSelectSmemKeys = 20480;   // pool keys staged in dynamic shared memory (160 KB)
 
 __global__ void __launch_bounds__(kSelectThreads)
 select_topk_kernel(const uint64_t *__restrict__ pool, const uint32_t *pool_count_ptr, uint32_t pool_count_imm,
                    uint32_t k, int tie_higher, uint64_t *out_keys, uint32_t *out_idx, float *out_val,
                    uint32_t *out_count, RunState *st_reset) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint64_t *staged = reinterpret_cast<uint64_t *>(smem_raw);
     __shared__ uint64_t keys[kSelectSortCap];
     __shared__ uint32_t hist[256];
-    __shared__ uint32_t s_bin, s_above, s_cnt;
+    __shared__ uint32_t s_bin, s_above[2], s_cnt;
     const uint32_t tid = threadIdx.x;
     const uint32_t n = pool_count_ptr ? *pool_count_ptr : pool_count_imm;
 
-    uint32_t m = 0;   // number of keys staged in shared memory
+    uint32_t m = 0;   // number of keys in keys[]
     if (n <= kSelectSortCap) {
         for (uint32_t i = tid; i < n; i += blockDim.x) keys[i] = pool[i];
         m = n;
     } else {
-        const uint64_t kth = block_radix_select<uint64_t>([&](uint32_t i) { return pool[i]; }, n, k, hist, &s_bin, &s_above);
+        const bool in_smem = n <= kSelectSmemKeys;
+        if (in_smem) {
+            for (uint32_t i = tid; i < n; i += blockDim.x) staged[i] = pool[i];
+            __syncthreads();
+        }
+        auto load = [&](uint32_t i) { return in_smem ? staged[i] : pool[i]; };
+        const uint64_t thr = block_radix_select<uint64_t, true>(load, n, k, hist, &s_bin, s_above);
         if (tid == 0) s_cnt = 0;
         __syncthreads();
         for (uint32_t i = tid; i < n; i += blockDim.x) {
-            const uint64_t key = pool[i];
-            if (key >= kth && key != 0ull) {
+            const uint64_t key = load(i);
+            if (key >= thr && key != 0ull) {
                 const uint32_t pos = atomicAdd(&s_cnt, 1u);
                 if (pos < kSelectSortCap) keys[pos] = key;
             }
