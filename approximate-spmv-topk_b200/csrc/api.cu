@@ -214,7 +214,7 @@ int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false) {
             default: launch_main<2048>(h, 3, m, x, st, k, s); break;
         }
         if (profile && q == 0) cudaEventRecord(h->evm1, s);
-        select_topk_kernel<<<1, kSelectThreads, kSelectSmemKeys * 8u, s>>>(
+        select_topk_kernel<<<1, kSelectThreads, kSelectDynSmem, s>>>(
             h->d_pool, &st->pool_count, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
             h->d_res_idx + (size_t)q * h->kmax, h->d_res_val + (size_t)q * h->kmax, h->d_res_count + q, st);
     }
@@ -313,7 +313,7 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
             if ((e = cudaFuncSetAttribute(csr_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess)
                 return bail("sample smem attr", e);
             if ((e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(kSelectSmemKeys * 8u))) != cudaSuccess)
+                                          (int)(kSelectDynSmem))) != cudaSuccess)
                 return bail("select smem attr", e);
         }
         int rc = alloc_query_side(h);
@@ -559,7 +559,7 @@ int tks_merge_keys_device(tks_handle *h, uint32_t query, const uint64_t *d_keys,
     if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k out of range");
     TKS_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
-    select_topk_kernel<<<1, kSelectThreads, kSelectSmemKeys * 8u, s>>>(
+    select_topk_kernel<<<1, kSelectThreads, kSelectDynSmem, s>>>(
         d_keys, nullptr, n_keys, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX, h->d_res_keys + (size_t)query * h->kmax,
         h->d_res_idx + (size_t)query * h->kmax, h->d_res_val + (size_t)query * h->kmax, h->d_res_count + query,
         nullptr);

@@ -282,23 +282,25 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
 template <typename KeyT, bool EARLY_EXIT, typename LoadF>
 __device__ __forceinline__ KeyT block_radix_select(LoadF load, uint32_t n, uint32_t k, uint32_t *hist,
                                                    uint32_t *s_bin, uint32_t *s_above) {
+    // hist: one private 256-bin histogram per warp (blockDim/32 * 256 words): same-digit updates only
+    // contend inside a warp, where shared-memory atomics are cheap; bins are summed across warps after.
     if (n < k) return (KeyT)0;
+    const uint32_t nwarps = blockDim.x / kWarp;
+    uint32_t *my = hist + (threadIdx.x / kWarp) * 256u;
     KeyT prefix = 0, pmask = 0;
     uint32_t need = k;
     for (int shift = (int)sizeof(KeyT) * 8 - 8; shift >= 0; shift -= 8) {
-        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        for (uint32_t i = threadIdx.x; i < nwarps * 256u; i += blockDim.x) hist[i] = 0;
         __syncthreads();
-        const uint32_t n_round = (n + blockDim.x - 1) / blockDim.x * blockDim.x;
-        for (uint32_t i = threadIdx.x; i < n_round; i += blockDim.x) {
-            const bool in = i < n;
-            const KeyT key = in ? load(i) : (KeyT)0;
-            const bool act = in && ((key & pmask) == prefix);
-            const uint32_t digit = (uint32_t)(key >> shift) & 0xFFu;
-            const unsigned am = __ballot_sync(kFull, act);
-            if (act) {
-                const unsigned peers = __match_any_sync(am, digit);
-                if ((unsigned)(__ffs(peers) - 1) == lane_id()) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
-            }
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const KeyT key = load(i);
+            if ((key & pmask) == prefix) atomicAdd(&my[(uint32_t)(key >> shift) & 0xFFu], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            uint32_t tot = 0;
+            for (uint32_t w = 0; w < nwarps; w++) tot += hist[w * 256u + threadIdx.x];
+            hist[threadIdx.x] = tot;   // thread t only ever touches bin t of every slice: no race
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
     }
     // last block picks the k-th largest
     __shared__ uint32_t s_ticket, s_bin, s_above[2];
-    __shared__ uint32_t hist[256];
+    __shared__ uint32_t hist[(kSampleThreads / kWarp) * 256];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_ticket = atomicAdd(&st->sample_ticket, 1u);
@@ -435,20 +437,21 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
 // (up to kSelectSmemKeys keys; larger pools are read from L2 on every pass),
 // reduced with the radix select to the <= kSelectSortCap keys above the
 // threshold, and those are sorted.  Also resets the per-query scratch.
-// Dynamic shared memory: kSelectSmemKeys * 8 bytes.
+// Dynamic shared memory: kSelectDynSmem bytes (per-warp histograms + staged keys).
 // --------------------------------------------------------------------------
 constexpr uint32_t kSelectThreads = 1024;
 constexpr uint32_t kSelectSortCap = 2048;     // keys sorted directly (16 KB static)
-constexpr uint32_t kSelectSmemKeys = 20480;   // pool keys staged in dynamic shared memory (160 KB)
+constexpr uint32_t kSelectSmemKeys = 16384;   // pool keys staged in dynamic shared memory (128 KB)
+constexpr uint32_t kSelectDynSmem = (kSelectThreads / kWarp) * 1024u + kSelectSmemKeys * 8u;
 
 __global__ void __launch_bounds__(kSelectThreads)
 select_topk_kernel(const uint64_t *__restrict__ pool, const uint32_t *pool_count_ptr, uint32_t pool_count_imm,
                    uint32_t k, int tie_higher, uint64_t *out_keys, uint32_t *out_idx, float *out_val,
                    uint32_t *out_count, RunState *st_reset) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint64_t *staged = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);                                  // 32 KB
+    uint64_t *staged = reinterpret_cast<uint64_t *>(smem_raw + (kSelectThreads / kWarp) * 1024u);
     __shared__ uint64_t keys[kSelectSortCap];
-    __shared__ uint32_t hist[256];
     __shared__ uint32_t s_bin, s_above[2], s_cnt;
     const uint32_t tid = threadIdx.x;
     const uint32_t n = pool_count_ptr ? *pool_count_ptr : pool_count_imm;
