@@ -300,6 +300,7 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_query, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&h->evm0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&h->evm1)) != cudaSuccess) return bail("cudaEventCreate", e);
     if (cfg->mode == TKS_MODE_FLOAT_CSR) {
@@ -333,6 +334,7 @@ void tks_destroy(tks_handle *h) {
     cudaFreeHost(h->h_res_idx); cudaFreeHost(h->h_res_val); cudaFreeHost(h->h_res_count); cudaFreeHost(h->h_x);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_query) cudaEventDestroy(h->ev_query);
     if (h->evm0) cudaEventDestroy(h->evm0);
     if (h->evm1) cudaEventDestroy(h->evm1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -460,8 +462,10 @@ int tks_set_query(tks_handle *h, const void *vec, uint32_t batch) {
     if (!h->have_matrix) return h->fail(TKS_ESTATE, "no matrix uploaded");
     if (batch < 1 || batch > (uint32_t)h->cfg.max_batch) return h->fail(TKS_EINVAL, "batch outside 1..max_batch");
     const size_t bytes = (size_t)batch * h->cols * sizeof(float);
+    TKS_CUDA(h, cudaEventSynchronize(h->ev_query));   // the pinned staging buffer may still feed the previous copy
     std::memcpy(h->h_x, vec, bytes);
     TKS_CUDA(h, cudaMemcpyAsync(h->d_x, h->h_x, bytes, cudaMemcpyHostToDevice, h->stream));
+    TKS_CUDA(h, cudaEventRecord(h->ev_query, h->stream));
     h->batch = batch;
     h->have_query = true;
     return TKS_OK;

@@ -1,15 +1,303 @@
-// bscsr_api.cu -- placeholder, replaced by the real fixed-point engine.
+// bscsr_api.cu -- host side of the FPGA-semantics engine: packet upload + chunk tables, query
+// transform, kernel dispatch on (FIXED_WIDTH, LIMITED_FINISHED_ROWS), result words, host merge.
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+#include "bscsr_topk.cuh"
 #include "handle.hpp"
+
 namespace tks {
-int bscsr_upload(Handle *h, uint32_t, uint32_t, const uint64_t *, const void *const *, const uint32_t *, const uint64_t *) { return h->fail(TKS_ESTATE, "BS-CSR engine not built"); }
-int bscsr_set_query(Handle *h, const uint32_t *, const uint32_t *, cudaStream_t) { return h->fail(TKS_ESTATE, "BS-CSR engine not built"); }
-int bscsr_launch(Handle *h, cudaStream_t) { return h->fail(TKS_ESTATE, "BS-CSR engine not built"); }
-int bscsr_fetch(Handle *h) { return h->fail(TKS_ESTATE, "BS-CSR engine not built"); }
-int bscsr_read_result(Handle *h, uint32_t *, uint32_t *, uint32_t, uint32_t *) { return h->fail(TKS_ESTATE, "BS-CSR engine not built"); }
-int bscsr_read_partition_results(Handle *h, uint32_t *, uint32_t *) { return h->fail(TKS_ESTATE, "BS-CSR engine not built"); }
-void bscsr_destroy(Handle *) {}
+
+struct BscsrState {
+    uint32_t P = 0, cols = 0, B = 0;
+    uint64_t total_packets = 0, total_nnz = 0;
+    std::vector<uint32_t> first_row;
+    uint8_t *d_packets = nullptr;
+    uint32_t *d_chunk_first = nullptr, *d_chunk_count = nullptr, *d_chunk_local0 = nullptr, *d_chunk_row_in = nullptr,
+             *d_chunk_lookback = nullptr, *d_part_chunk_begin = nullptr;
+    uint32_t n_chunks = 0, chunk_cap = 0;
+    BscsrLogs logs{};
+    uint32_t *d_xq = nullptr;        // 1024 pre-shifted query words
+    uint32_t *h_xq = nullptr;        // pinned
+    uint32_t *d_counter = nullptr;   // dynamic chunk scheduler
+    uint32_t *d_res_idx = nullptr, *d_res_val = nullptr;   // P x Kp x 16 words each
+    uint32_t *h_res_idx = nullptr, *h_res_val = nullptr;   // pinned
+    bool have_query = false, have_words = false;
+    int grid = 0;
+    std::vector<uint32_t> merged_idx, merged_val;          // read_result() output of the last run
+};
+
+namespace {
+
+template <int W, int LFR>
+void launch_stream(Handle *h, BscsrState *b, const BscsrDevice &m, cudaStream_t s) {
+    bscsr_stream_kernel<W, LFR><<<b->grid, kBsThreads, 0, s>>>(m, b->d_xq, (uint32_t)h->cfg.local_k, b->logs, b->d_counter);
 }
-extern "C" int tks_upload_bscsr(tks_handle *h, uint32_t cols, uint32_t partitions, const uint64_t *ppp, const void *const *packets, const uint32_t *first_row, const uint64_t *npp) {
+
+template <int W>
+int dispatch_lfr(Handle *h, BscsrState *b, const BscsrDevice &m, cudaStream_t s) {
+    switch (h->cfg.limited_finished_rows) {
+        case 1: launch_stream<W, 1>(h, b, m, s); break;
+        case 2: launch_stream<W, 2>(h, b, m, s); break;
+        case 3: launch_stream<W, 3>(h, b, m, s); break;
+        case 4: launch_stream<W, 4>(h, b, m, s); break;
+        default: return h->fail(TKS_EINVAL, "limited_finished_rows=%d is not instantiated (1..4)", h->cfg.limited_finished_rows);
+    }
+    bscsr_replay_kernel<W><<<b->P * (uint32_t)h->cfg.limited_finished_rows, kReplayThreads, 0, s>>>(
+        b->logs, b->d_part_chunk_begin, (uint32_t)h->cfg.limited_finished_rows, (uint32_t)h->cfg.local_k, b->chunk_cap,
+        b->d_res_idx, b->d_res_val, b->d_counter);
+    return TKS_OK;
+}
+
+bool width_supported(int W) { return W == 20 || W == 21 || W == 25 || W == 26 || W == 32; }
+
+}  // namespace
+
+int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *packets_per_part,
+                 const void *const *packets, const uint32_t *first_row, const uint64_t *nnz_per_part) {
+    if (h->cfg.mode != TKS_MODE_FIXED_BSCSR) return h->fail(TKS_ESTATE, "handle is not in FIXED_BSCSR mode");
+    if (!packets_per_part || !packets || !first_row) return h->fail(TKS_EINVAL, "null argument");
+    if (partitions != (uint32_t)h->cfg.partitions) return h->fail(TKS_EINVAL, "partitions != cfg.partitions");
+    if (cols == 0 || cols > 1024) return h->fail(TKS_EINVAL, "cols outside 1..1024 (10-bit column field)");
+    const int W = h->cfg.fixed_width, LFR = h->cfg.limited_finished_rows, Kp = h->cfg.local_k;
+    if (!width_supported(W)) return h->fail(TKS_EINVAL, "fixed_width=%d is not instantiated (20, 21, 25, 26, 32)", W);
+    if (Kp < 1 || Kp > (int)kBsMaxKp) return h->fail(TKS_EINVAL, "local_k outside 1..32");
+    if (LFR < 1 || LFR > (int)kBsMaxLfr) return h->fail(TKS_EINVAL, "limited_finished_rows outside 1..4");
+    const int B = tks_bscsr_packet_size(W);
+    bscsr_destroy(h);
+    BscsrState *b = new BscsrState();
+    h->bs = b;
+    b->P = partitions; b->cols = cols; b->B = (uint32_t)B;
+    b->first_row.assign(first_row, first_row + partitions);
+    uint64_t total = 0;
+    for (uint32_t p = 0; p < partitions; p++) {
+        if (packets_per_part[p] == 0 || !packets[p]) return h->fail(TKS_EINVAL, "partition %u has no packets", p);
+        total += packets_per_part[p];
+        if (nnz_per_part) b->total_nnz += nnz_per_part[p];
+    }
+    if (total > 0xFFFFFFF0ull) return h->fail(TKS_EINVAL, "more than 2^32 packets on one device");
+    b->total_packets = total;
+    b->chunk_cap = 2048;
+
+    // ---- chunk tables (host, once per matrix): row counter and carry look-back at every chunk start ----
+    std::vector<uint32_t> c_first, c_count, c_local0, c_row_in, c_look, part_begin(partitions + 1, 0);
+    uint64_t goff = 0;
+    for (uint32_t p = 0; p < partitions; p++) {
+        part_begin[p] = (uint32_t)c_first.size();
+        const uint8_t *pk = static_cast<const uint8_t *>(packets[p]);
+        const uint64_t np = packets_per_part[p];
+        uint32_t last_row = 0;
+        std::vector<uint8_t> keepflag(np);   // packet passes the carried partial sum through (n == 1 && !new)
+        for (uint64_t i = 0; i < np; i++) {
+            uint64_t w0;
+            std::memcpy(&w0, pk + i * 64, 8);
+            const uint32_t xf = pk[i * 64 + 63] >> 7;
+            // validation: cumulative ends are non-decreasing, start >= 1, end <= B
+            uint32_t prev = 0;
+            for (int s = 0; s < B; s++) {
+                uint32_t xs = (uint32_t)((w0 >> (4 * s)) & 0xF);
+                if (s >= 16) break;   // B <= 15 for W >= 20; (4-bit fields of packets with B == 16 spill into word 1)
+                if (xs < prev || xs > (uint32_t)B || (s == 0 && xs == 0))
+                    return h->fail(TKS_EINVAL, "malformed packet %llu of partition %u (segment ends not in 1..B / decreasing)",
+                                   (unsigned long long)i, p);
+                prev = xs;
+            }
+            uint32_t n = 0, pe = 0;
+            for (int s = 0; s < LFR; s++) { uint32_t xs = (uint32_t)((w0 >> (4 * s)) & 0xF); n += (xs != pe); pe = xs; }
+            const uint32_t nw = (i != 0) ? xf : 0u;
+            if (i % b->chunk_cap == 0) {
+                c_first.push_back((uint32_t)(goff + i));
+                c_count.push_back((uint32_t)std::min<uint64_t>(b->chunk_cap, np - i));
+                c_local0.push_back((uint32_t)i);
+                c_row_in.push_back(last_row);
+                uint32_t L = 0;
+                if (i > 0) { L = 1; while (i - L > 0 && keepflag[i - L]) L++; }
+                c_look.push_back(L);
+            }
+            last_row += n + nw - 1u;
+            keepflag[i] = (n == 1 && nw == 0) || (n == 0 && nw != 0);
+        }
+        goff += np;
+    }
+    part_begin[partitions] = (uint32_t)c_first.size();
+    b->n_chunks = (uint32_t)c_first.size();
+
+    // ---- device memory ----
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    TKS_CUDA(h, cudaMalloc(&b->d_packets, total * 64));
+    goff = 0;
+    for (uint32_t p = 0; p < partitions; p++) {
+        TKS_CUDA(h, cudaMemcpy(b->d_packets + goff * 64, packets[p], packets_per_part[p] * 64, cudaMemcpyHostToDevice));
+        goff += packets_per_part[p];
+    }
+    auto up = [&](uint32_t **d, const std::vector<uint32_t> &v) -> cudaError_t {
+        cudaError_t e = cudaMalloc(d, std::max<size_t>(1, v.size()) * 4);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*d, v.data(), v.size() * 4, cudaMemcpyHostToDevice);
+    };
+    TKS_CUDA(h, up(&b->d_chunk_first, c_first));
+    TKS_CUDA(h, up(&b->d_chunk_count, c_count));
+    TKS_CUDA(h, up(&b->d_chunk_local0, c_local0));
+    TKS_CUDA(h, up(&b->d_chunk_row_in, c_row_in));
+    TKS_CUDA(h, up(&b->d_chunk_lookback, c_look));
+    TKS_CUDA(h, up(&b->d_part_chunk_begin, part_begin));
+    const size_t nlog = (size_t)b->n_chunks * LFR;
+    TKS_CUDA(h, cudaMalloc(&b->logs.val, nlog * b->chunk_cap * 4));
+    TKS_CUDA(h, cudaMalloc(&b->logs.row, nlog * b->chunk_cap * 4));
+    TKS_CUDA(h, cudaMalloc(&b->logs.cnt, nlog * 4));
+    TKS_CUDA(h, cudaMalloc(&b->logs.top, nlog * 32 * 4));
+    TKS_CUDA(h, cudaMalloc(&b->d_xq, 1024 * 4));
+    TKS_CUDA(h, cudaMallocHost(&b->h_xq, 1024 * 4));
+    TKS_CUDA(h, cudaMalloc(&b->d_counter, 4));
+    TKS_CUDA(h, cudaMemset(b->d_counter, 0, 4));
+    const size_t nres = (size_t)partitions * Kp * 16;
+    TKS_CUDA(h, cudaMalloc(&b->d_res_idx, nres * 4));
+    TKS_CUDA(h, cudaMalloc(&b->d_res_val, nres * 4));
+    TKS_CUDA(h, cudaMemset(b->d_res_idx, 0, nres * 4));   // positions >= LFR stay 0 (.cpp:100-110)
+    TKS_CUDA(h, cudaMemset(b->d_res_val, 0, nres * 4));
+    TKS_CUDA(h, cudaMallocHost(&b->h_res_idx, nres * 4));
+    TKS_CUDA(h, cudaMallocHost(&b->h_res_val, nres * 4));
+    b->grid = h->num_sms * 4;   // 4 CTAs of 8 warps per SM
+    if ((uint32_t)b->grid * (kBsThreads / 32) > b->n_chunks) b->grid = (int)((b->n_chunks + kBsThreads / 32 - 1) / (kBsThreads / 32));
+
+    h->rows = 0; h->cols = cols; h->nnz = b->total_nnz;
+    h->have_matrix = true;
+    h->stats.rows = 0; h->stats.cols = cols; h->stats.nnz = b->total_nnz; h->stats.packets = total;
+    h->stats.device_bytes = total * 64;
+    // 64 * sum ceil(nnz_p / B) + 64 * ceil(C / B) + P * Kp * 128
+    h->stats.algorithmic_bytes = 64ull * total + 64ull * ((cols + B - 1) / B) + (uint64_t)partitions * Kp * 128ull;
+    h->stats.launches_per_run = 2;
+    return TKS_OK;
+}
+
+int bscsr_set_query(Handle *h, const uint32_t *vec32_host, const uint32_t *vec32_dev, cudaStream_t s) {
+    BscsrState *b = h->bs;
+    if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");
+    const int W = h->cfg.fixed_width;
+    std::vector<uint32_t> tmp;
+    if (!vec32_host) {
+        tmp.resize(b->cols);
+        TKS_CUDA(h, cudaMemcpyAsync(tmp.data(), vec32_dev, b->cols * 4, cudaMemcpyDeviceToHost, s));
+        TKS_CUDA(h, cudaStreamSynchronize(s));
+        vec32_host = tmp.data();
+    }
+    // kernel vec load (.cpp:127-137): W-bit truncation of the 32-bit word; pre-shifted by one for the
+    // umulhi product (see bscsr_stream_kernel); columns >= cols read 0 like the zero-initialised URAM
+    for (uint32_t c = 0; c < 1024; c++) {
+        uint32_t xq = (c < b->cols) ? (vec32_host[c] >> (32 - W)) : 0u;
+        b->h_xq[c] = (W == 32) ? xq : (xq << 1);
+    }
+    TKS_CUDA(h, cudaMemcpyAsync(b->d_xq, b->h_xq, 1024 * 4, cudaMemcpyHostToDevice, s));
+    TKS_CUDA(h, cudaStreamSynchronize(s));   // h_xq (pinned staging) is reused by the next call
+    b->have_query = true;
+    return TKS_OK;
+}
+
+int bscsr_launch(Handle *h, cudaStream_t s) {
+    BscsrState *b = h->bs;
+    if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");
+    if (!b->have_query) return h->fail(TKS_ESTATE, "no query set");
+    BscsrDevice m{b->d_packets, b->d_chunk_first, b->d_chunk_count, b->d_chunk_local0, b->d_chunk_row_in,
+                  b->d_chunk_lookback, b->n_chunks, b->chunk_cap};
+    int rc;
+    switch (h->cfg.fixed_width) {
+        case 20: rc = dispatch_lfr<20>(h, b, m, s); break;
+        case 21: rc = dispatch_lfr<21>(h, b, m, s); break;
+        case 25: rc = dispatch_lfr<25>(h, b, m, s); break;
+        case 26: rc = dispatch_lfr<26>(h, b, m, s); break;
+        case 32: rc = dispatch_lfr<32>(h, b, m, s); break;
+        default: return h->fail(TKS_EINVAL, "fixed_width not instantiated");
+    }
+    if (rc) return rc;
+    TKS_CUDA(h, cudaGetLastError());
+    b->have_words = false;
+    return TKS_OK;
+}
+
+int bscsr_fetch(Handle *h) {
+    BscsrState *b = h->bs;
+    if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");
+    const size_t nres = (size_t)b->P * h->cfg.local_k * 16;
+    TKS_CUDA(h, cudaMemcpyAsync(b->h_res_idx, b->d_res_idx, nres * 4, cudaMemcpyDeviceToHost, h->stream));
+    TKS_CUDA(h, cudaMemcpyAsync(b->h_res_val, b->d_res_val, nres * 4, cudaMemcpyDeviceToHost, h->stream));
+    TKS_CUDA(h, cudaStreamSynchronize(h->stream));
+    b->have_words = true;
+    // read_result (host_spmv_bscsr.cpp:399-448): all P x Kp x B slots, idx += first_row[p], keep val > 0,
+    // first insertion of an index wins, then sort_tuples (evaluation_utils.hpp:40-62)
+    std::unordered_map<uint32_t, uint32_t> seen;
+    std::vector<std::pair<uint32_t, uint32_t>> out;   // (idx, val)
+    const int Kp = h->cfg.local_k;
+    for (uint32_t p = 0; p < b->P; p++)
+        for (int t = 0; t < Kp; t++)
+            for (uint32_t q = 0; q < b->B; q++) {
+                const size_t o = ((size_t)p * Kp + t) * 16 + q;
+                const uint32_t v = b->h_res_val[o];
+                if (v == 0) continue;
+                const uint32_t id = b->h_res_idx[o] + b->first_row[p];
+                if (seen.emplace(id, v).second) out.emplace_back(id, v);
+            }
+    const bool higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
+    std::sort(out.begin(), out.end(), [&](const std::pair<uint32_t, uint32_t> &l, const std::pair<uint32_t, uint32_t> &r) {
+        if (l.second != r.second) return l.second > r.second;
+        return higher ? (l.first > r.first) : (l.first < r.first);
+    });
+    b->merged_idx.resize(out.size());
+    b->merged_val.resize(out.size());
+    for (size_t i = 0; i < out.size(); i++) { b->merged_idx[i] = out[i].first; b->merged_val[i] = out[i].second; }
+    h->stats.last_candidates = (uint32_t)out.size();
+    return TKS_OK;
+}
+
+int bscsr_read_result(Handle *h, uint32_t *idx_out, uint32_t *val_out, uint32_t k, uint32_t *count) {
+    BscsrState *b = h->bs;
+    if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");
+    if (!b->have_words) {
+        TKS_CUDA(h, cudaSetDevice(h->device));
+        TKS_CUDA(h, cudaDeviceSynchronize());
+        int rc = bscsr_fetch(h);
+        if (rc) return rc;
+    }
+    const uint32_t n = (uint32_t)std::min<size_t>(k, b->merged_idx.size());
+    std::memcpy(idx_out, b->merged_idx.data(), n * 4);
+    std::memcpy(val_out, b->merged_val.data(), n * 4);
+    for (uint32_t i = n; i < k; i++) { idx_out[i] = 0; val_out[i] = 0; }
+    if (count) *count = n;
+    return TKS_OK;
+}
+
+int bscsr_read_partition_results(Handle *h, uint32_t *idx_words, uint32_t *val_words) {
+    BscsrState *b = h->bs;
+    if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");
+    if (!b->have_words) {
+        TKS_CUDA(h, cudaSetDevice(h->device));
+        TKS_CUDA(h, cudaDeviceSynchronize());
+        int rc = bscsr_fetch(h);
+        if (rc) return rc;
+    }
+    const size_t nres = (size_t)b->P * h->cfg.local_k * 16;
+    if (idx_words) std::memcpy(idx_words, b->h_res_idx, nres * 4);
+    if (val_words) std::memcpy(val_words, b->h_res_val, nres * 4);
+    return TKS_OK;
+}
+
+void bscsr_destroy(Handle *h) {
+    BscsrState *b = h->bs;
+    if (!b) return;
+    cudaFree(b->d_packets); cudaFree(b->d_chunk_first); cudaFree(b->d_chunk_count); cudaFree(b->d_chunk_local0);
+    cudaFree(b->d_chunk_row_in); cudaFree(b->d_chunk_lookback); cudaFree(b->d_part_chunk_begin);
+    cudaFree(b->logs.val); cudaFree(b->logs.row); cudaFree(b->logs.cnt); cudaFree(b->logs.top);
+    cudaFree(b->d_xq); cudaFreeHost(b->h_xq); cudaFree(b->d_counter);
+    cudaFree(b->d_res_idx); cudaFree(b->d_res_val); cudaFreeHost(b->h_res_idx); cudaFreeHost(b->h_res_val);
+    delete b;
+    h->bs = nullptr;
+}
+
+}  // namespace tks
+
+extern "C" int tks_upload_bscsr(tks_handle *h, uint32_t cols, uint32_t partitions, const uint64_t *packets_per_part,
+                                const void *const *packets, const uint32_t *first_row, const uint64_t *nnz_per_part) {
     if (!h) return TKS_EINVAL;
-    return tks::bscsr_upload(h, cols, partitions, ppp, packets, first_row, npp);
+    return tks::bscsr_upload(h, cols, partitions, packets_per_part, packets, first_row, nnz_per_part);
 }

@@ -21,7 +21,7 @@ struct Handle {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr, ev_query = nullptr;
     std::string err;
 
     // matrix (float CSR mode)

@@ -1,0 +1,123 @@
+"""GPU parity tests of the FPGA-semantics engine (W-bit fixed point, BS-CSR packets, P partitions x LFR
+lanes x local K) through the C ABI.  Bar: BIT-EXACT against the oracle's literal sequential transcription
+of the HLS kernel, both the raw per-partition result words (slot positions included) and the merged list."""
+import numpy as np
+import pytest
+
+from conftest import make_query
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(tks, orc, x, y, v, rows, cols, vec, k=100, W=20, P=32, Kp=8, LFR=4):
+    o = orc.bscsr_topk(x, y, v, rows, vec, P=P, W=W, Kp=Kp, LFR=LFR)
+    with tks.SpMVFixed(x, y, o["val32"], rows, cols, vec32=o["vec32"], k=k, fixed_width=W, partitions=P,
+                       local_k=Kp, limited_finished_rows=LFR) as f:
+        f()
+        gv, gi = f.read_result()
+        iw, vw = f.read_partition_results()
+        # a second query on the same handle (reset path)
+        vec2 = make_query(cols, 4242)
+        o2 = orc.bscsr_topk(x, y, v, rows, vec2, P=P, W=W, Kp=Kp, LFR=LFR)
+        f.reset(o2["vec32"])
+        f()
+        gv2, gi2 = f.read_result()
+    assert np.array_equal(iw, o["idx_words"]), "partition index words differ"
+    assert np.array_equal(vw, o["val_words"]), "partition value words differ"
+    n = min(k, o["idx"].size)
+    assert np.array_equal(gi, o["idx"][:n]) and np.array_equal(gv, o["val"][:n])
+    n2 = min(k, o2["idx"].size)
+    assert np.array_equal(gi2, o2["idx"][:n2]) and np.array_equal(gv2, o2["val"][:n2])
+    return o
+
+
+@pytest.mark.parametrize("W", [20, 21, 25, 26, 32])
+def test_cfg1_all_widths(cuda_required, tks, orc, gen, W):
+    """BASELINE config 1 matrix through the designs of test_spmv_topk.py:41-47 (20/21/25/26/32 bit)."""
+    x, y, v = gen.create_sparse_matrix(10000, 1024, 20, "gamma", seed=0)
+    o = run_both(tks, orc, x, y, v, 10000, 1024, make_query(1024, 1), W=W)
+    assert o["idx"].size >= 100
+
+
+@pytest.mark.parametrize("deg,dist", [(2, "gamma"), (4, "gamma"), (6, "uniform"), (40, "uniform")])
+def test_row_lengths_incl_lfr_overflow_drift(cuda_required, tks, orc, gen, deg, dist):
+    """Short rows put more than LFR segments into a packet: the reference's row counter drifts and partial
+    sums are mis-carried; the engine must reproduce exactly that."""
+    x, y, v = gen.create_sparse_matrix(20000, 1024, deg, dist, seed=deg)
+    run_both(tks, orc, x, y, v, 20000, 1024, make_query(1024, 2))
+
+
+@pytest.mark.parametrize("Kp", [1, 2, 4, 8, 16, 32])
+def test_local_k_variants_incl_argmin4_typo(cuda_required, tks, orc, gen, Kp):
+    x, y, v = gen.create_sparse_matrix(8000, 512, 20, "gamma", seed=Kp)
+    run_both(tks, orc, x, y, v, 8000, 512, make_query(512, 3), Kp=Kp, k=50)
+
+
+@pytest.mark.parametrize("LFR", [1, 2, 3, 4])
+def test_limited_finished_rows_variants(cuda_required, tks, orc, gen, LFR):
+    x, y, v = gen.create_sparse_matrix(8000, 1024, 12, "gamma", seed=10 + LFR)
+    run_both(tks, orc, x, y, v, 8000, 1024, make_query(1024, 5), LFR=LFR)
+
+
+@pytest.mark.parametrize("P", [1, 2, 7, 32, 64])
+def test_partition_counts_and_many_chunks(cuda_required, tks, orc, gen, P):
+    """Few partitions => many chunks per partition: exercises the chunk carry look-back, the tabulated row
+    counter and the replay filter across chunks."""
+    x, y, v = gen.create_sparse_matrix(120000, 1024, 20, "gamma", seed=P)
+    run_both(tks, orc, x, y, v, 120000, 1024, make_query(1024, 6), P=P)
+
+
+def test_massive_ties(cuda_required, tks, orc):
+    """Identical rows: every candidate value ties, so the surviving indices depend on the exact slot
+    dynamics of the replace-min lists (`>=` replacement, argmin -> highest slot among equal minima)."""
+    rows, per = 6000, 5
+    x = np.repeat(np.arange(rows, dtype=np.uint32), per)
+    y = np.tile(np.array([3, 99, 400, 401, 1000], np.uint32), rows)
+    v = np.tile(np.array([0.5, 0.25, 0.125, 0.5, 0.3]), rows)
+    # a few distinct rows sprinkled in
+    rng = np.random.default_rng(0)
+    hot = rng.choice(rows, 40, replace=False)
+    for r in hot:
+        v[r * per:(r + 1) * per] = rng.random(per)
+    for Kp in (4, 8):
+        run_both(tks, orc, x, y, v, rows, 1024, make_query(1024, 8), Kp=Kp, P=8)
+
+
+def test_long_rows_span_many_packets(cuda_required, tks, orc):
+    rng = np.random.default_rng(5)
+    rows = 640
+    deg = rng.integers(1, 400, rows)
+    x = np.repeat(np.arange(rows, dtype=np.uint32), deg)
+    y = np.sort(rng.integers(0, 1024, x.size)).astype(np.uint32)
+    y = rng.integers(0, 1024, x.size).astype(np.uint32)
+    v = rng.random(x.size) / 20.0
+    run_both(tks, orc, x, y, v, rows, 1024, make_query(1024, 9), P=4, k=30)
+
+
+def test_tiny_partitions(cuda_required, tks, orc):
+    """One row per partition (a single packet each): nothing is ever finished -> empty result."""
+    rows = 32
+    x = np.arange(rows, dtype=np.uint32)
+    y = np.arange(rows, dtype=np.uint32)
+    v = np.full(rows, 0.5)
+    o = run_both(tks, orc, x, y, v, rows, 64, make_query(64, 1), k=10)
+    assert o["idx"].size == 0
+
+
+def test_errors(cuda_required, tks, orc, gen):
+    x, y, v = gen.create_sparse_matrix(2000, 1024, 20, "gamma", seed=0)
+    val32 = orc.fx32_from_double(v)
+    with pytest.raises(tks.capi.TksError, match="not instantiated|outside"):
+        tks.SpMVFixed(x, y, val32, 2000, 1024, fixed_width=23)
+    packets, ppp, first, npp = tks.capi.pack_bscsr(x, y, val32, 2000, 32, 20)
+    bad = packets.copy()
+    bad[5, 0] = (bad[5, 0] & ~np.uint64(0xFF)) | np.uint64(0x12)     # x[0]=2, x[1]=1: decreasing ends
+    f = tks.SpMVFixed.__new__(tks.SpMVFixed)
+    cfg = tks.capi.default_config(mode=tks.capi.MODE_FIXED_BSCSR, fixed_width=20)
+    f._create(cfg); f.num_cols = 1024; f.k = 10
+    with pytest.raises(tks.capi.TksError, match="malformed packet"):
+        f.upload_packets(bad, ppp, first, npp)
+    f.upload_packets(packets, ppp, first, npp)
+    with pytest.raises(tks.capi.TksError, match="no query"):
+        f()
+    f.close()
