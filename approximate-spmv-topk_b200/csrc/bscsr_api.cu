@@ -148,6 +148,8 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     TKS_CUDA(h, cudaMalloc(&b->logs.row, nlog * b->chunk_cap * 4));
     TKS_CUDA(h, cudaMalloc(&b->logs.cnt, nlog * 4));
     TKS_CUDA(h, cudaMalloc(&b->logs.top, nlog * 32 * 4));
+    TKS_CUDA(h, cudaMalloc(&b->logs.p0, nlog * 4));
+    TKS_CUDA(h, cudaMemset(b->logs.p0, 0, nlog * 4));
     TKS_CUDA(h, cudaMalloc(&b->d_xq, 1024 * 4));
     TKS_CUDA(h, cudaMallocHost(&b->h_xq, 1024 * 4));
     TKS_CUDA(h, cudaMalloc(&b->d_counter, 4));
@@ -287,7 +289,7 @@ void bscsr_destroy(Handle *h) {
     if (!b) return;
     cudaFree(b->d_packets); cudaFree(b->d_chunk_first); cudaFree(b->d_chunk_count); cudaFree(b->d_chunk_local0);
     cudaFree(b->d_chunk_row_in); cudaFree(b->d_chunk_lookback); cudaFree(b->d_part_chunk_begin);
-    cudaFree(b->logs.val); cudaFree(b->logs.row); cudaFree(b->logs.cnt); cudaFree(b->logs.top);
+    cudaFree(b->logs.val); cudaFree(b->logs.row); cudaFree(b->logs.cnt); cudaFree(b->logs.top); cudaFree(b->logs.p0);
     cudaFree(b->d_xq); cudaFreeHost(b->h_xq); cudaFree(b->d_counter);
     cudaFree(b->d_res_idx); cudaFree(b->d_res_val); cudaFreeHost(b->h_res_idx); cudaFreeHost(b->h_res_val);
     delete b;

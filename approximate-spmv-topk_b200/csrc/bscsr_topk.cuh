@@ -53,6 +53,7 @@ struct BscsrLogs {
     uint32_t *row;     // [n_chunks][LFR][chunk_cap]
     uint32_t *cnt;     // [n_chunks][LFR]
     uint32_t *top;     // [n_chunks][LFR][32]  chunk-local K largest values, descending
+    uint32_t *p0;      // [n_chunks][LFR]  1 when packet 0 of the PARTITION offered a candidate to lane j
 };
 
 template <int W>
@@ -235,6 +236,7 @@ bscsr_stream_kernel(BscsrDevice m, const uint32_t *__restrict__ xq, uint32_t Kp,
                     fin = (x[j - 1] != (j > 1 ? x[j - 2] : 0u)) && (n != (uint32_t)j);
                 }
                 const uint32_t row = start_row + (uint32_t)j - 1u;
+                if (active && local_idx == 0) logs.p0[(size_t)c * LFR + j] = fin ? 1u : 0u;
                 const bool pass = emitting && fin && (val >= theta[j]);
                 const unsigned pm = __ballot_sync(0xFFFFFFFFu, pass);
                 if (pm) {
@@ -294,6 +296,7 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
     if (tid == 0) { s_worst_idx = 0; s_worst_val = 0; s_started = 0; s_n = 0; }
     if (blockIdx.x == 0 && tid == 0 && chunk_counter_reset) *chunk_counter_reset = 0;
     uint32_t rtop = 0;   // warp 0: running K largest values of all chunks seen so far (lanes 0..Kp-1)
+    const bool first_from_packet0 = logs.p0[(size_t)cb * LFR + j] != 0;
     __syncthreads();
 
     auto replay = [&]() {
@@ -304,9 +307,9 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
             for (uint32_t i = 0; i < n; i++) {
                 const uint32_t v = s_sv[i], r = s_sr[i];
                 if (!started) {
-                    // the argmin is recomputed after EVERY packet: unless this candidate comes from packet 0 of
-                    // the partition (row == j-1), the all-zero list has already moved the worst slot
-                    if (r != j - 1u) { wi = bs_argmin(Lval, Kp); wv = Lval[wi]; }
+                    // the argmin is recomputed after EVERY packet (hpp:376-388): unless the first candidate comes
+                    // from packet 0 of the partition, the all-zero list has already moved the worst slot
+                    if (!first_from_packet0) { wi = bs_argmin(Lval, Kp); wv = Lval[wi]; }
                     started = 1;
                 }
                 if (v >= wv) {
