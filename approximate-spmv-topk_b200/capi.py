@@ -131,6 +131,14 @@ def fixed32_from_double(a) -> np.ndarray:
     return np.fromiter((f(float(v)) for v in a.ravel()), np.uint32, a.size).reshape(a.shape)
 
 
+def fixed32_from_double_np(a) -> np.ndarray:
+    """Vectorised (T) value cast of utils.hpp:401 for arrays: double -> raw ap_ufixed<32,1,AP_TRN_ZERO>.
+    Same rule as tks_fixed32_from_double (tests compare them); host-side data preparation only."""
+    a = np.asarray(a, np.float64)
+    s = np.floor(np.where(a > 0, a, 0.0) * 2147483648.0)
+    return np.mod(s, 4294967296.0).astype(np.uint64).astype(np.uint32)
+
+
 def pack_bscsr(row, col, val32, num_rows, partitions=32, fixed_width=20):
     """tks_pack_bscsr: returns (packets uint64[total,8], packets_per_part, first_row, nnz_per_part)."""
     row = np.ascontiguousarray(row, np.uint32)

@@ -503,7 +503,7 @@ int tks_run(tks_handle *h, uint32_t k, float *kernel_ms, float *total_ms) {
     TKS_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     auto t1 = std::chrono::high_resolution_clock::now();
     h->stats.last_kernel_ms = ms;
-    if (h->cfg.profile_kernels && h->cfg.mode == TKS_MODE_FLOAT_CSR) {
+    if (h->cfg.profile_kernels) {
         float mm = 0.f;
         TKS_CUDA(h, cudaEventElapsedTime(&mm, h->evm0, h->evm1));
         h->stats.last_main_kernel_ms = mm;

@@ -33,7 +33,10 @@ namespace {
 
 template <int W, int LFR>
 void launch_stream(Handle *h, BscsrState *b, const BscsrDevice &m, cudaStream_t s) {
+    const bool prof = h->cfg.profile_kernels != 0 && s == h->stream;
+    if (prof) cudaEventRecord(h->evm0, s);
     bscsr_stream_kernel<W, LFR><<<b->grid, kBsThreads, 0, s>>>(m, b->d_xq, (uint32_t)h->cfg.local_k, b->logs, b->d_counter);
+    if (prof) cudaEventRecord(h->evm1, s);
 }
 
 template <int W>
@@ -178,12 +181,17 @@ int bscsr_set_query(Handle *h, const uint32_t *vec32_host, const uint32_t *vec32
     BscsrState *b = h->bs;
     if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");
     const int W = h->cfg.fixed_width;
-    std::vector<uint32_t> tmp;
     if (!vec32_host) {
-        tmp.resize(b->cols);
-        TKS_CUDA(h, cudaMemcpyAsync(tmp.data(), vec32_dev, b->cols * 4, cudaMemcpyDeviceToHost, s));
-        TKS_CUDA(h, cudaStreamSynchronize(s));
-        vec32_host = tmp.data();
+        switch (W) {
+            case 20: bscsr_query_kernel<20><<<4, 256, 0, s>>>(vec32_dev, b->cols, b->d_xq); break;
+            case 21: bscsr_query_kernel<21><<<4, 256, 0, s>>>(vec32_dev, b->cols, b->d_xq); break;
+            case 25: bscsr_query_kernel<25><<<4, 256, 0, s>>>(vec32_dev, b->cols, b->d_xq); break;
+            case 26: bscsr_query_kernel<26><<<4, 256, 0, s>>>(vec32_dev, b->cols, b->d_xq); break;
+            default: bscsr_query_kernel<32><<<4, 256, 0, s>>>(vec32_dev, b->cols, b->d_xq); break;
+        }
+        TKS_CUDA(h, cudaGetLastError());
+        b->have_query = true;
+        return TKS_OK;
     }
     // kernel vec load (.cpp:127-137): W-bit truncation of the 32-bit word; pre-shifted by one for the
     // umulhi product (see bscsr_stream_kernel); columns >= cols read 0 like the zero-initialised URAM

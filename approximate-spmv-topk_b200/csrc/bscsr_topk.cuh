@@ -266,6 +266,16 @@ bscsr_stream_kernel(BscsrDevice m, const uint32_t *__restrict__ xq, uint32_t Kp,
     }
 }
 
+// kernel vec load (.cpp:127-137) for a query already in HBM: W-bit truncation of the raw 32-bit words,
+// pre-shifted for the umulhi product; columns >= cols read 0 like the zero-initialised URAM copies.
+template <int W>
+__global__ void bscsr_query_kernel(const uint32_t *__restrict__ vec32, uint32_t cols, uint32_t *__restrict__ xq) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= 1024) return;
+    const uint32_t q = (c < cols) ? (vec32[c] >> (32 - W)) : 0u;
+    xq[c] = (W == 32) ? q : (q << 1);
+}
+
 // argmin with MIN(res,a,b) = res[a] < res[b] ? a : b (hpp:28): highest slot among equal minima;
 // K == 4 reproduces `MIN(res, 2, 2)` (hpp:45): slot 3 is never the minimum.
 __device__ __forceinline__ uint32_t bs_argmin(const uint32_t *v, uint32_t Kp) {

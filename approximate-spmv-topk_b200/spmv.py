@@ -146,10 +146,11 @@ class SpMVFixed(_Base):
     x, y: row-sorted COO; val32 / vec32: raw ap_ufixed<32,1> words (real_type_inout)."""
 
     def __init__(self, x, y, val32, num_rows, num_cols, vec32=None, k=100, fixed_width=20, partitions=32, local_k=8,
-                 limited_finished_rows=4, device=0):
+                 limited_finished_rows=4, device=0, profile_kernels=False):
         cfg = capi.default_config(mode=capi.MODE_FIXED_BSCSR, device=device, fixed_width=fixed_width,
                                   partitions=partitions, local_k=local_k,
-                                  limited_finished_rows=limited_finished_rows, tie_break=capi.TIE_HIGHER_INDEX)
+                                  limited_finished_rows=limited_finished_rows, tie_break=capi.TIE_HIGHER_INDEX,
+                                  profile_kernels=int(profile_kernels))
         self._create(cfg)
         self.k = k
         self.num_rows, self.num_cols = int(num_rows), int(num_cols)
@@ -178,6 +179,9 @@ class SpMVFixed(_Base):
         assert vec32.size == self.num_cols
         check(capi.lib().tks_set_query(self.handle, _ptr(vec32), 1), self.handle)
         return 0
+
+    def reset_device(self, dptr, stream=0):
+        check(capi.lib().tks_set_query_device(self.handle, C.c_void_p(dptr), 1, C.c_void_p(stream)), self.handle)
 
     def read_result(self):
         """Returns (raw values uint32[count], indices uint32[count]) -- may be shorter than k."""
