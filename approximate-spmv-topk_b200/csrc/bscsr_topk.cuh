@@ -91,7 +91,9 @@ bscsr_stream_kernel(BscsrDevice m, const uint32_t *__restrict__ xq, uint32_t Kp,
     constexpr int B = F::B;
     constexpr uint32_t M = F::M;
     __shared__ uint32_t xs[1024];   // query, pre-shifted (see bscsr_api.cu); columns >= cols hold 0
+    __shared__ uint32_t ptab[16 * kBsThreads];   // [prefix length 0..15][thread]: running sums of the products
     for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) xs[i] = xq[i];
+    ptab[threadIdx.x] = 0;
     __syncthreads();
     const unsigned lane = lane_id();
     const uint8_t *xsb = reinterpret_cast<const uint8_t *>(xs);
@@ -135,9 +137,9 @@ bscsr_stream_kernel(BscsrDevice m, const uint32_t *__restrict__ xq, uint32_t Kp,
 #pragma unroll
                 for (int s = 0; s < LFR; s++) x[s] = (x01 >> (4 * s)) & 0xFu;   // LFR <= 8 fits the first word
             }
-            uint32_t Lsum[LFR];
-#pragma unroll
-            for (int s = 0; s < LFR; s++) Lsum[s] = 0;
+            // prefix sums of the products go to a per-thread column of shared memory, so that the LFR
+            // "sum of the first x[s] products" are 4 conflict-free loads instead of 4 x B predicated adds
+            uint32_t acc = 0;
 #pragma unroll
             for (int j = 0; j < B; j++) {
                 uint32_t pw;
@@ -163,10 +165,12 @@ bscsr_stream_kernel(BscsrDevice m, const uint32_t *__restrict__ xq, uint32_t Kp,
                     // xs holds xq << 1 and v is top-aligned: umulhi gives (v * xq) >> (W-1) exactly
                     pw = __umulhi(v << (32 - W), xv);
                 }
-#pragma unroll
-                for (int s = 0; s < LFR; s++)
-                    if ((uint32_t)j < x[s]) Lsum[s] += pw;   // x is non-decreasing (checked at upload)
+                acc += pw;
+                ptab[(j + 1) * kBsThreads + threadIdx.x] = acc;
             }
+            uint32_t Lsum[LFR];
+#pragma unroll
+            for (int s = 0; s < LFR; s++) Lsum[s] = ptab[x[s] * kBsThreads + threadIdx.x];   // x is non-decreasing (checked at upload)
             uint32_t agg[LFR];
             uint32_t n = 0;
 #pragma unroll
