@@ -16,9 +16,13 @@ struct BscsrState {
     std::vector<uint32_t> first_row;
     uint8_t *d_packets = nullptr;
     uint32_t *d_chunk_first = nullptr, *d_chunk_count = nullptr, *d_chunk_local0 = nullptr, *d_chunk_row_in = nullptr,
-             *d_chunk_lookback = nullptr, *d_part_chunk_begin = nullptr;
+             *d_chunk_lookback = nullptr, *d_chunk_part = nullptr, *d_part_chunk_begin = nullptr;
     uint32_t n_chunks = 0, chunk_cap = 0;
     BscsrLogs logs{};
+    // sample pieces (first kBsSamplePackets packets of every partition, kBsSamplePiece each)
+    uint32_t *d_s_first = nullptr, *d_s_count = nullptr, *d_s_local0 = nullptr, *d_s_lookback = nullptr, *d_s_part = nullptr,
+             *d_s_part_begin = nullptr, *d_piece_top = nullptr, *d_ticket = nullptr, *d_theta_seed = nullptr;
+    uint32_t n_pieces = 0;
     uint32_t *d_xq = nullptr;        // 1024 pre-shifted query words
     uint32_t *h_xq = nullptr;        // pinned
     uint32_t *d_counter = nullptr;   // dynamic chunk scheduler
@@ -32,15 +36,20 @@ struct BscsrState {
 namespace {
 
 template <int W, int LFR>
-void launch_stream(Handle *h, BscsrState *b, const BscsrDevice &m, cudaStream_t s) {
+void launch_stream(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s) {
     const bool prof = h->cfg.profile_kernels != 0 && s == h->stream;
+    BscsrSample sm{b->d_s_first, b->d_s_count, b->d_s_local0, b->d_s_lookback, b->d_s_part, b->n_pieces,
+                   b->d_s_part_begin, b->d_piece_top, b->d_ticket, b->d_theta_seed};
+    const uint32_t sgrid = (b->n_pieces * 32u + kBsThreads - 1) / kBsThreads;
+    bscsr_sample_kernel<W, LFR><<<sgrid, kBsThreads, 0, s>>>(b->d_packets, sm, b->d_xq, (uint32_t)h->cfg.local_k);
     if (prof) cudaEventRecord(h->evm0, s);
-    bscsr_stream_kernel<W, LFR><<<b->grid, kBsThreads, 0, s>>>(m, b->d_xq, (uint32_t)h->cfg.local_k, b->logs, b->d_counter);
+    bscsr_stream_kernel<W, LFR><<<b->grid, kBsThreads, 0, s>>>(b->d_packets, m, b->d_xq, (uint32_t)h->cfg.local_k, b->logs,
+                                                             b->d_theta_seed, b->d_counter);
     if (prof) cudaEventRecord(h->evm1, s);
 }
 
 template <int W>
-int dispatch_lfr(Handle *h, BscsrState *b, const BscsrDevice &m, cudaStream_t s) {
+int dispatch_lfr(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s) {
     switch (h->cfg.limited_finished_rows) {
         case 1: launch_stream<W, 1>(h, b, m, s); break;
         case 2: launch_stream<W, 2>(h, b, m, s); break;
@@ -82,13 +91,15 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     }
     if (total > 0xFFFFFFF0ull) return h->fail(TKS_EINVAL, "more than 2^32 packets on one device");
     b->total_packets = total;
-    b->chunk_cap = 2048;
+    b->chunk_cap = 512;
 
     // ---- chunk tables (host, once per matrix): row counter and carry look-back at every chunk start ----
-    std::vector<uint32_t> c_first, c_count, c_local0, c_row_in, c_look, part_begin(partitions + 1, 0);
+    std::vector<uint32_t> c_first, c_count, c_local0, c_row_in, c_look, c_part, part_begin(partitions + 1, 0);
+    std::vector<uint32_t> s_first, s_count, s_local0, s_look, s_part, s_part_begin(partitions + 1, 0);
     uint64_t goff = 0;
     for (uint32_t p = 0; p < partitions; p++) {
         part_begin[p] = (uint32_t)c_first.size();
+        s_part_begin[p] = (uint32_t)s_first.size();
         const uint8_t *pk = static_cast<const uint8_t *>(packets[p]);
         const uint64_t np = packets_per_part[p];
         uint32_t last_row = 0;
@@ -118,6 +129,16 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
                 uint32_t L = 0;
                 if (i > 0) { L = 1; while (i - L > 0 && keepflag[i - L]) L++; }
                 c_look.push_back(L);
+                c_part.push_back(p);
+            }
+            if (i < kBsSamplePackets && i % kBsSamplePiece == 0) {
+                s_first.push_back((uint32_t)(goff + i));
+                s_count.push_back((uint32_t)std::min<uint64_t>(kBsSamplePiece, std::min<uint64_t>(np, kBsSamplePackets) - i));
+                s_local0.push_back((uint32_t)i);
+                uint32_t L = 0;
+                if (i > 0) { L = 1; while (i - L > 0 && keepflag[i - L]) L++; }
+                s_look.push_back(L);
+                s_part.push_back(p);
             }
             last_row += n + nw - 1u;
             keepflag[i] = (n == 1 && nw == 0) || (n == 0 && nw != 0);
@@ -125,7 +146,9 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
         goff += np;
     }
     part_begin[partitions] = (uint32_t)c_first.size();
+    s_part_begin[partitions] = (uint32_t)s_first.size();
     b->n_chunks = (uint32_t)c_first.size();
+    b->n_pieces = (uint32_t)s_first.size();
 
     // ---- device memory ----
     TKS_CUDA(h, cudaSetDevice(h->device));
@@ -146,11 +169,22 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     TKS_CUDA(h, up(&b->d_chunk_row_in, c_row_in));
     TKS_CUDA(h, up(&b->d_chunk_lookback, c_look));
     TKS_CUDA(h, up(&b->d_part_chunk_begin, part_begin));
+    TKS_CUDA(h, up(&b->d_chunk_part, c_part));
+    TKS_CUDA(h, up(&b->d_s_first, s_first));
+    TKS_CUDA(h, up(&b->d_s_count, s_count));
+    TKS_CUDA(h, up(&b->d_s_local0, s_local0));
+    TKS_CUDA(h, up(&b->d_s_lookback, s_look));
+    TKS_CUDA(h, up(&b->d_s_part, s_part));
+    TKS_CUDA(h, up(&b->d_s_part_begin, s_part_begin));
+    TKS_CUDA(h, cudaMalloc(&b->d_piece_top, (size_t)b->n_pieces * LFR * 32 * 4));
+    TKS_CUDA(h, cudaMalloc(&b->d_ticket, partitions * 4));
+    TKS_CUDA(h, cudaMemset(b->d_ticket, 0, partitions * 4));
+    TKS_CUDA(h, cudaMalloc(&b->d_theta_seed, (size_t)partitions * LFR * 4));
+    TKS_CUDA(h, cudaMemset(b->d_theta_seed, 0, (size_t)partitions * LFR * 4));
     const size_t nlog = (size_t)b->n_chunks * LFR;
     TKS_CUDA(h, cudaMalloc(&b->logs.val, nlog * b->chunk_cap * 4));
     TKS_CUDA(h, cudaMalloc(&b->logs.row, nlog * b->chunk_cap * 4));
     TKS_CUDA(h, cudaMalloc(&b->logs.cnt, nlog * 4));
-    TKS_CUDA(h, cudaMalloc(&b->logs.top, nlog * 32 * 4));
     TKS_CUDA(h, cudaMalloc(&b->logs.p0, nlog * 4));
     TKS_CUDA(h, cudaMemset(b->logs.p0, 0, nlog * 4));
     TKS_CUDA(h, cudaMalloc(&b->d_xq, 1024 * 4));
@@ -173,7 +207,7 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     h->stats.device_bytes = total * 64;
     // 64 * sum ceil(nnz_p / B) + 64 * ceil(C / B) + P * Kp * 128
     h->stats.algorithmic_bytes = 64ull * total + 64ull * ((cols + B - 1) / B) + (uint64_t)partitions * Kp * 128ull;
-    h->stats.launches_per_run = 2;
+    h->stats.launches_per_run = 3;
     return TKS_OK;
 }
 
@@ -209,8 +243,8 @@ int bscsr_launch(Handle *h, cudaStream_t s) {
     BscsrState *b = h->bs;
     if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");
     if (!b->have_query) return h->fail(TKS_ESTATE, "no query set");
-    BscsrDevice m{b->d_packets, b->d_chunk_first, b->d_chunk_count, b->d_chunk_local0, b->d_chunk_row_in,
-                  b->d_chunk_lookback, b->n_chunks, b->chunk_cap};
+    BscsrChunks m{b->d_chunk_first, b->d_chunk_count, b->d_chunk_local0, b->d_chunk_row_in, b->d_chunk_lookback,
+                  b->d_chunk_part, b->n_chunks, b->chunk_cap};
     int rc;
     switch (h->cfg.fixed_width) {
         case 20: rc = dispatch_lfr<20>(h, b, m, s); break;
@@ -297,7 +331,9 @@ void bscsr_destroy(Handle *h) {
     if (!b) return;
     cudaFree(b->d_packets); cudaFree(b->d_chunk_first); cudaFree(b->d_chunk_count); cudaFree(b->d_chunk_local0);
     cudaFree(b->d_chunk_row_in); cudaFree(b->d_chunk_lookback); cudaFree(b->d_part_chunk_begin);
-    cudaFree(b->logs.val); cudaFree(b->logs.row); cudaFree(b->logs.cnt); cudaFree(b->logs.top); cudaFree(b->logs.p0);
+    cudaFree(b->logs.val); cudaFree(b->logs.row); cudaFree(b->logs.cnt); cudaFree(b->logs.p0);
+    cudaFree(b->d_chunk_part); cudaFree(b->d_s_first); cudaFree(b->d_s_count); cudaFree(b->d_s_local0); cudaFree(b->d_s_lookback);
+    cudaFree(b->d_s_part); cudaFree(b->d_s_part_begin); cudaFree(b->d_piece_top); cudaFree(b->d_ticket); cudaFree(b->d_theta_seed);
     cudaFree(b->d_xq); cudaFreeHost(b->h_xq); cudaFree(b->d_counter);
     cudaFree(b->d_res_idx); cudaFree(b->d_res_val); cudaFreeHost(b->h_res_idx); cudaFreeHost(b->h_res_val);
     delete b;

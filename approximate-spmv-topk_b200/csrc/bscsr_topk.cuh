@@ -11,19 +11,22 @@
 // The reference streams each partition strictly in order (II=1 pipeline); 32 sequential streams
 // cannot fill 148 SMs, so the stream is cut into chunks that are processed concurrently:
 //
+//   bscsr_sample_kernel   reduces the first packets of every partition (in 64-packet pieces, one per
+//        warp) and leaves, per (partition, lane), the K-th largest candidate seen there.  Those are
+//        real candidates that precede every later chunk of the partition in stream order, so the
+//        value is a lower bound on the sequential kernel's threshold for all those chunks.
 //   bscsr_stream_kernel   one warp per chunk, one thread per 64-byte packet per iteration:
 //        decode, fixed-point products against the query in shared memory, <= LFR segment sums,
 //        then two warp scans rebuild what the sequential kernel carries from packet to packet
 //        (row counter; partial sum of the row that straddles packets).  The carry entering a
 //        chunk is recomputed from the few packets before it (look-back precomputed at upload);
 //        the row counter entering a chunk depends only on the matrix and is tabulated at upload.
-//        Every candidate (value, row) that is >= the chunk's own running K-th largest is LOGGED in
-//        stream order.  Any candidate the sequential kernel would have accepted is in the log,
-//        because the sequential threshold (K-th largest of ALL earlier candidates) can only be
-//        higher than the chunk-local one; rejected candidates never change the lists.
-//   bscsr_replay_kernel   one CTA per (partition, lane): drops log entries below the K-th largest
-//        of all EARLIER chunks (same argument), then replays the few hundred survivors through the
-//        literal replace-min state machine.  Output: the reference's result words.
+//        Every candidate (value, row) that is >= max(seed, the chunk's own running K-th largest)
+//        is LOGGED in stream order.  Any candidate the sequential kernel would have accepted is in
+//        the log, because the sequential threshold (K-th largest of ALL earlier candidates) can only
+//        be higher; rejected candidates never change the lists.
+//   bscsr_replay_kernel   one CTA per (partition, lane): gathers the chunk logs in order and replays
+//        them through the literal replace-min state machine.  Output: the reference's result words.
 #pragma once
 
 #include "common.cuh"
@@ -33,47 +36,35 @@ namespace tks {
 constexpr uint32_t kBsThreads = 256;          // 8 warps per CTA in the stream kernel
 constexpr uint32_t kBsMaxKp = 32;             // local K (types.hpp K) supported: 1..32
 constexpr uint32_t kBsMaxLfr = 4;             // LFR values instantiated: 1..4 (see bscsr_api.cu)
+constexpr uint32_t kBsSamplePackets = 2048;   // prefix of every partition reduced by the sample kernel
+constexpr uint32_t kBsSamplePiece = 64;       // packets per sample warp
 constexpr uint32_t kReplayThreads = 256;
-constexpr uint32_t kReplayTile = 512;         // chunks handled per tile in the replay kernel
-constexpr uint32_t kReplaySurvivors = 2048;   // survivors buffered between sequential replays
+constexpr uint32_t kReplaySurvivors = 4096;   // log entries buffered between sequential replays
 
-struct BscsrDevice {
-    const uint8_t *packets;          // all partitions back to back, 64 bytes per packet
-    const uint32_t *chunk_first;     // global index of the chunk's first packet
-    const uint32_t *chunk_count;     // packets in the chunk (<= chunk_cap)
-    const uint32_t *chunk_local0;    // index of that packet inside its partition
-    const uint32_t *chunk_row_in;    // the kernel's row counter before the chunk (upload-time table)
-    const uint32_t *chunk_lookback;  // packets before the chunk needed to rebuild the carried partial sum
-    uint32_t n_chunks;
-    uint32_t chunk_cap;
+struct BscsrChunks {
+    const uint32_t *first;      // global index of the chunk's first packet
+    const uint32_t *count;      // packets in the chunk
+    const uint32_t *local0;     // index of that packet inside its partition
+    const uint32_t *row_in;     // the kernel's row counter before the chunk (upload-time table)
+    const uint32_t *lookback;   // packets before the chunk needed to rebuild the carried partial sum
+    const uint32_t *part;       // partition of the chunk
+    uint32_t n;
+    uint32_t cap;               // max packets per chunk = log capacity per (chunk, lane)
 };
 
 struct BscsrLogs {
-    uint32_t *val;     // [n_chunks][LFR][chunk_cap]
-    uint32_t *row;     // [n_chunks][LFR][chunk_cap]
+    uint32_t *val;     // [n_chunks][LFR][cap]
+    uint32_t *row;     // [n_chunks][LFR][cap]
     uint32_t *cnt;     // [n_chunks][LFR]
-    uint32_t *top;     // [n_chunks][LFR][32]  chunk-local K largest values, descending
     uint32_t *p0;      // [n_chunks][LFR]  1 when packet 0 of the PARTITION offered a candidate to lane j
 };
 
 template <int W>
 struct BsFmt {
     static constexpr int B = 511 / (W + 14);          // types.hpp:71-72
-    static constexpr int XOFF = 0, YOFF = 4 * B, VOFF = 14 * B;
+    static constexpr int YOFF = 4 * B, VOFF = 14 * B;
     static constexpr uint32_t M = (W == 32) ? 0xFFFFFFFFu : ((1u << (W & 31)) - 1u);
 };
-
-// bits [lo, lo+width) of a 512-bit little-endian word held in 16 registers (compile-time position)
-template <int LO, int WIDTH>
-__device__ __forceinline__ uint32_t bs_field(const uint32_t (&w)[16]) {
-    constexpr int q = LO / 32, s = LO % 32;
-    constexpr uint32_t mask = (WIDTH == 32) ? 0xFFFFFFFFu : ((1u << (WIDTH & 31)) - 1u);
-    if constexpr (s + WIDTH <= 32) {
-        return (w[q] >> s) & mask;
-    } else {
-        return __funnelshift_r(w[q], w[q + 1], s) & mask;
-    }
-}
 
 // sorted-descending insert of v into a K-entry list spread over lanes 0..Kp-1
 __device__ __forceinline__ uint32_t lane_list_insert(uint32_t top, uint32_t v, uint32_t Kp) {
@@ -83,189 +74,291 @@ __device__ __forceinline__ uint32_t lane_list_insert(uint32_t top, uint32_t v, u
     return top;
 }
 
-template <int W, int LFR>
-__global__ void __launch_bounds__(kBsThreads)
-bscsr_stream_kernel(BscsrDevice m, const uint32_t *__restrict__ xq, uint32_t Kp, BscsrLogs logs,
-                    uint32_t *chunk_counter) {
+__device__ __forceinline__ void bs_load_packet(const uint8_t *p, uint32_t (&w)[16]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                 : "l"(p + 32));
+}
+
+// Sinks of the packet loop.  LogSink keeps the stream-ordered log of one chunk; TopSink (sample) only
+// keeps the K largest values per lane.
+template <int LFR>
+struct BsLogSink {
+    uint32_t *val, *row;   // this chunk's log, [LFR][cap]
+    uint32_t cap;
+    uint32_t lcnt[LFR];
+    __device__ __forceinline__ void put(int j, bool pass, unsigned pm, uint32_t v, uint32_t r) {
+        if (pass) {
+            const uint32_t pos = lcnt[j] + __popc(pm & lanemask_lt());
+            val[(size_t)j * cap + pos] = v;
+            row[(size_t)j * cap + pos] = r;
+        }
+        lcnt[j] += __popc(pm);
+    }
+};
+template <int LFR>
+struct BsTopSink {
+    __device__ __forceinline__ void put(int, bool, unsigned, uint32_t, uint32_t) {}
+};
+
+// Packets [begin, end) of one partition, 32 per iteration; packets before `first` only rebuild the carry.
+// theta/top: per lane-list running K-th largest and the K largest values (lanes 0..Kp-1), updated in place.
+template <int W, int LFR, typename Sink>
+__device__ __forceinline__ void bs_process(const uint8_t *__restrict__ packets, uint32_t begin, uint32_t first,
+                                           uint32_t end, uint32_t local0, uint32_t row_base, uint32_t Kp,
+                                           const uint8_t *xsb, uint32_t *ptab, uint32_t (&theta)[LFR],
+                                           uint32_t (&top)[LFR], Sink &sink, uint32_t *p0flags) {
     using F = BsFmt<W>;
     constexpr int B = F::B;
     constexpr uint32_t M = F::M;
-    __shared__ uint32_t xs[1024];   // query, pre-shifted (see bscsr_api.cu); columns >= cols hold 0
-    __shared__ uint32_t ptab[16 * kBsThreads];   // [prefix length 0..15][thread]: running sums of the products
-    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) xs[i] = xq[i];
-    ptab[threadIdx.x] = 0;
-    __syncthreads();
     const unsigned lane = lane_id();
-    const uint8_t *xsb = reinterpret_cast<const uint8_t *>(xs);
-
-    for (;;) {
-        uint32_t c = 0;
-        if (lane == 0) c = atomicAdd(chunk_counter, 1u);
-        c = __shfl_sync(0xFFFFFFFFu, c, 0);
-        if (c >= m.n_chunks) break;
-        const uint32_t first = m.chunk_first[c], count = m.chunk_count[c], local0 = m.chunk_local0[c];
-        const uint32_t look = m.chunk_lookback[c];
-        uint32_t row_base = m.chunk_row_in[c];   // last_row_of_packet before the next packet (hpp:260)
-        uint32_t carry = 0;                      // last_row_of_packet_output (hpp:261)
-        uint32_t theta[LFR], top[LFR], lcnt[LFR];
+    uint32_t carry = 0;   // last_row_of_packet_output (hpp:261)
+    uint32_t w[16], wn[16];
+    {
+        const uint32_t g0 = begin + lane;
+        if (g0 < end) bs_load_packet(packets + (size_t)g0 * 64u, wn);
+        else {
 #pragma unroll
-        for (int j = 0; j < LFR; j++) { theta[j] = 0; top[j] = 0; lcnt[j] = 0; }
-
-        const uint32_t begin = first - look, end = first + count;
-        for (uint32_t base = begin; base < end; base += 32) {
-            const uint32_t g = base + lane;
-            const bool active = g < end;
-            const bool emitting = active && g >= first;
-            uint32_t w[16];
-            if (active) {
-                const uint8_t *p = m.packets + (size_t)g * 64u;
-                asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-                             : "l"(p));
-                asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                             : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
-                             : "l"(p + 32));
+            for (int i = 0; i < 16; i++) wn[i] = 0;
+        }
+    }
+    for (uint32_t base = begin; base < end; base += 32) {
+        const uint32_t g = base + lane;
+        const bool active = g < end;
+        const bool emitting = active && g >= first;
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = wn[i];
+        {
+            const uint32_t gn = g + 32;   // software prefetch of the next iteration's packet
+            if (gn < end) bs_load_packet(packets + (size_t)gn * 64u, wn);
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) wn[i] = 0;
+            }
+        }
+        // ---- loop 1 + loop 2 (hpp:168-220, 104-149): decode, products, segment sums ----
+        uint32_t x[LFR];
+#pragma unroll
+        for (int s = 0; s < LFR; s++) x[s] = (w[0] >> (4 * s)) & 0xFu;   // cumulative segment ends (LFR <= 8)
+        // prefix sums of the products go to a per-thread column of shared memory, so that the LFR
+        // "sum of the first x[s] products" are LFR conflict-free loads instead of LFR x B predicated adds
+        uint32_t acc = 0;
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            // column * 4 (byte offset into the query table) and the value: one shift + one mask each
+            const int yp = F::YOFF + 10 * j, yq = yp / 32, ysh = yp % 32;
+            uint32_t yraw;
+            if (ysh + 10 <= 32) yraw = (ysh >= 2) ? (w[yq] >> (ysh - 2)) : (w[yq] << (2 - ysh));
+            else yraw = __funnelshift_r(w[yq], w[yq + 1], ysh - 2);
+            const uint32_t xv = *reinterpret_cast<const uint32_t *>(xsb + (yraw & 0xFFCu));
+            const int vp = F::VOFF + W * j, vq = vp / 32, vsh = vp % 32;
+            uint32_t pw;
+            if constexpr (W == 32) {
+                // ufixed<32,1> * ufixed<32,1> -> drop 31 fraction bits, wrap to 32 (hpp:121-126)
+                const uint32_t v = (vsh == 0) ? w[vq] : __funnelshift_r(w[vq], w[vq + 1], vsh);
+                pw = (uint32_t)(((uint64_t)v * (uint64_t)xv) >> 31);
             } else {
-#pragma unroll
-                for (int i = 0; i < 16; i++) w[i] = 0;
+                // the query table holds xq << 1 and v is moved to the top of the word:
+                // umulhi gives (v * xq) >> (W-1) exactly
+                constexpr uint32_t topmask = ~((1u << (32 - W)) - 1u);
+                uint32_t vraw;
+                if (vsh + W <= 32) vraw = w[vq] << (32 - W - vsh);
+                else vraw = __funnelshift_r(w[vq], w[vq + 1], vsh - (32 - W));
+                pw = __umulhi(vraw & topmask, xv);
             }
-            // ---- loop 1 + loop 2 (hpp:168-220, 104-149): decode, products, segment sums ----
-            uint32_t x[LFR];
-            {
-                // cumulative segment ends x[0..LFR-1]: 4-bit fields at bit 4*s
-                const uint32_t x01 = w[0];
-#pragma unroll
-                for (int s = 0; s < LFR; s++) x[s] = (x01 >> (4 * s)) & 0xFu;   // LFR <= 8 fits the first word
-            }
-            // prefix sums of the products go to a per-thread column of shared memory, so that the LFR
-            // "sum of the first x[s] products" are 4 conflict-free loads instead of 4 x B predicated adds
-            uint32_t acc = 0;
-#pragma unroll
-            for (int j = 0; j < B; j++) {
-                uint32_t pw;
-                const uint32_t yoff = [&]() {
-                    // column * 4 = byte offset into the query table
-                    constexpr int lo = F::YOFF;
-                    const int pos = lo + 10 * j;
-                    const int q = pos / 32, s = pos % 32;
-                    uint32_t f = (s + 10 <= 32) ? (w[q] >> s) : __funnelshift_r(w[q], w[q + 1], s);
-                    return (f & 0x3FFu) << 2;
-                }();
-                const uint32_t xv = *reinterpret_cast<const uint32_t *>(xsb + yoff);
-                const uint32_t v = [&]() {
-                    const int pos = F::VOFF + W * j;
-                    const int q = pos / 32, s = pos % 32;
-                    uint32_t f = (s + W <= 32) ? (w[q] >> s) : __funnelshift_r(w[q], w[q + 1], s);
-                    return f & M;
-                }();
-                if constexpr (W == 32) {
-                    // ufixed<32,1> * ufixed<32,1> -> drop 31 fraction bits, wrap to 32 (hpp:121-126)
-                    pw = (uint32_t)(((uint64_t)v * (uint64_t)xv) >> 31);
-                } else {
-                    // xs holds xq << 1 and v is top-aligned: umulhi gives (v * xq) >> (W-1) exactly
-                    pw = __umulhi(v << (32 - W), xv);
-                }
-                acc += pw;
-                ptab[(j + 1) * kBsThreads + threadIdx.x] = acc;
-            }
-            uint32_t Lsum[LFR];
-#pragma unroll
-            for (int s = 0; s < LFR; s++) Lsum[s] = ptab[x[s] * kBsThreads + threadIdx.x];   // x is non-decreasing (checked at upload)
-            uint32_t agg[LFR];
-            uint32_t n = 0;
+            acc += pw;
+            ptab[(j + 1) * kBsThreads + threadIdx.x] = acc;
+        }
+        uint32_t agg[LFR];
+        uint32_t n = 0;
+        {
+            uint32_t prevL = 0, prev_end = 0;
 #pragma unroll
             for (int s = 0; s < LFR; s++) {
-                const uint32_t prev_end = s ? x[s - 1] : 0u;
-                agg[s] = (Lsum[s] - (s ? Lsum[s - 1] : 0u)) & M;
+                const uint32_t L = ptab[x[s] * kBsThreads + threadIdx.x];   // x is non-decreasing (checked at upload)
+                agg[s] = (L - prevL) & M;
                 n += (x[s] != prev_end);
+                prevL = L;
+                prev_end = x[s];
             }
-            // ---- loop 3 (hpp:246-326): what is carried from packet to packet ----
-            const uint32_t local_idx = local0 + (g - first);   // wraps correctly for look-back packets
-            const uint32_t nw = (active && local_idx != 0) ? (w[15] >> 31) : 0u;
-            // last_out recurrence  last_out_i = a_i + (k_i ? last_out_{i-1} : 0):
-            //   n == 0: al[0]            -> (0, new)
-            //   n == 1: al[1]            -> (agg0, !new)
-            //   n >= 2: al[n] = agg[n-1] -> (agg[n-1], false)
-            uint32_t a = 0;
-            bool keep = true;   // identity for inactive lanes
-            if (active) {
-                if (n == 0) { a = 0; keep = nw != 0; }
-                else if (n == 1) { a = agg[0]; keep = nw == 0; }
-                else {
-                    a = agg[LFR - 1];
+        }
+        // ---- loop 3 (hpp:246-326): what is carried from packet to packet ----
+        const uint32_t local_idx = local0 + (g - first);   // wraps correctly for look-back packets
+        const uint32_t nw = (active && local_idx != 0) ? (w[15] >> 31) : 0u;
+        // last_out recurrence  last_out_i = a_i + (keep_i ? last_out_{i-1} : 0):
+        //   n == 0: al[0]            -> (0, new)
+        //   n == 1: al[1]            -> (agg0, !new)
+        //   n >= 2: al[n] = agg[n-1] -> (agg[n-1], false)
+        uint32_t a = 0;
+        uint32_t keep = 1;   // identity for inactive lanes
+        if (active) {
+            if (n == 0) { a = 0; keep = nw; }
+            else if (n == 1) { a = agg[0]; keep = nw ^ 1u; }
+            else {
+                a = agg[LFR - 1];
 #pragma unroll
-                    for (int s = LFR - 2; s >= 1; s--) if (n == (uint32_t)(s + 1)) a = agg[s];
-                    keep = false;
-                }
+                for (int s = LFR - 2; s >= 1; s--) if (n == (uint32_t)(s + 1)) a = agg[s];
+                keep = 0;
             }
-            uint32_t delta = emitting ? (n + nw - 1u) : 0u;    // finished_rows_num (hpp:281), u32 wrap
-            // inclusive scans over the 32 packets of this iteration
-            uint32_t sa = a;
-            bool sk = keep;
-            uint32_t sd = delta;
+        }
+        const uint32_t delta = emitting ? (n + nw - 1u) : 0u;    // finished_rows_num (hpp:281)
+        // inclusive scans over the 32 packets of this iteration; the row-counter increments (< 2^16 per
+        // iteration) and the keep flag share one register: bits 0..15 sum of delta, bit 16 keep
+        uint32_t sa = a;
+        uint32_t sdk = (delta & 0xFFFFu) | (keep << 16);
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t ua = __shfl_up_sync(0xFFFFFFFFu, sa, d);
-                const int uk = __shfl_up_sync(0xFFFFFFFFu, (int)sk, d);
-                const uint32_t ud = __shfl_up_sync(0xFFFFFFFFu, sd, d);
-                if ((int)lane >= d) {
-                    if (sk) sa += ua;
-                    sk = sk && (uk != 0);
-                    sd += ud;
-                }
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t ua = __shfl_up_sync(0xFFFFFFFFu, sa, d);
+            const uint32_t udk = __shfl_up_sync(0xFFFFFFFFu, sdk, d);
+            if ((int)lane >= d) {
+                if (sdk & 0x10000u) sa += ua;
+                sdk = ((sdk + udk) & 0xFFFFu) | (sdk & udk & 0x10000u);
             }
-            // exclusive carry for this packet = inclusive value of the previous lane, chained to the warp carry
-            uint32_t pa = __shfl_up_sync(0xFFFFFFFFu, sa, 1);
-            int pk = __shfl_up_sync(0xFFFFFFFFu, (int)sk, 1);
-            if (lane == 0) { pa = 0; pk = 1; }
-            const uint32_t prev = (pa + (pk ? carry : 0u)) & M;          // last_row_of_packet_output seen by this packet
-            const uint32_t start_row = row_base + (sd - delta) + nw;      // hpp:282
-            // warp carries for the next iteration
-            const uint32_t la = __shfl_sync(0xFFFFFFFFu, sa, 31);
-            const int lk = __shfl_sync(0xFFFFFFFFu, (int)sk, 31);
-            carry = (la + (lk ? carry : 0u)) & M;
-            row_base += __shfl_sync(0xFFFFFFFFu, sd, 31);
+        }
+        // exclusive carry for this packet = inclusive value of the previous lane, chained to the warp carry
+        uint32_t pa = __shfl_up_sync(0xFFFFFFFFu, sa, 1);
+        uint32_t pdk = __shfl_up_sync(0xFFFFFFFFu, sdk, 1);
+        if (lane == 0) { pa = 0; pdk = 0x10000u; }
+        const uint32_t prev = (pa + ((pdk & 0x10000u) ? carry : 0u)) & M;   // last_row_of_packet_output seen by this packet
+        const uint32_t start_row = row_base + (pdk & 0xFFFFu) + nw;          // hpp:282
+        // warp carries for the next iteration
+        const uint32_t la = __shfl_sync(0xFFFFFFFFu, sa, 31);
+        const uint32_t ldk = __shfl_sync(0xFFFFFFFFu, sdk, 31);
+        carry = (la + ((ldk & 0x10000u) ? carry : 0u)) & M;
+        row_base += ldk & 0xFFFFu;
 
-            // ---- loop 4 (hpp:331-389): candidates of the LFR lanes ----
+        // ---- loop 4 (hpp:331-389): candidates of the LFR lanes ----
+        uint32_t val[LFR];
+        bool pass[LFR];
+        bool anyp = false;
+#pragma unroll
+        for (int j = 0; j < LFR; j++) {
+            bool fin;
+            if (j == 0) {
+                val[0] = prev;            // al[0] = last_out when the packet starts a new row
+                fin = nw != 0;
+            } else {
+                val[j] = agg[j - 1];
+                if (j == 1 && nw == 0) val[j] = (val[j] + prev) & M;
+                fin = (x[j - 1] != (j > 1 ? x[j - 2] : 0u)) && (n != (uint32_t)j);
+            }
+            if (p0flags && active && local_idx == 0) p0flags[j] = fin ? 1u : 0u;
+            pass[j] = emitting && fin && (val[j] >= theta[j]);
+            anyp |= pass[j];
+        }
+        if (__any_sync(0xFFFFFFFFu, anyp)) {
 #pragma unroll
             for (int j = 0; j < LFR; j++) {
-                uint32_t val;
-                bool fin;
-                if (j == 0) {
-                    val = prev;            // al[0] = last_out when the packet starts a new row
-                    fin = nw != 0;
-                } else {
-                    val = agg[j - 1];
-                    if (j == 1 && nw == 0) val = (val + prev) & M;
-                    fin = (x[j - 1] != (j > 1 ? x[j - 2] : 0u)) && (n != (uint32_t)j);
-                }
-                const uint32_t row = start_row + (uint32_t)j - 1u;
-                if (active && local_idx == 0) logs.p0[(size_t)c * LFR + j] = fin ? 1u : 0u;
-                const bool pass = emitting && fin && (val >= theta[j]);
-                const unsigned pm = __ballot_sync(0xFFFFFFFFu, pass);
+                const unsigned pm = __ballot_sync(0xFFFFFFFFu, pass[j]);
                 if (pm) {
-                    const size_t lbase = ((size_t)c * LFR + j) * m.chunk_cap;
-                    if (pass) {
-                        const uint32_t pos = lcnt[j] + __popc(pm & lanemask_lt());
-                        logs.val[lbase + pos] = val;
-                        logs.row[lbase + pos] = row;
-                    }
-                    lcnt[j] += __popc(pm);
+                    sink.put(j, pass[j], pm, val[j], start_row + (uint32_t)j - 1u);
                     unsigned rest = pm;
                     while (rest) {
                         const int src = __ffs(rest) - 1;
                         rest &= rest - 1;
-                        const uint32_t v = __shfl_sync(0xFFFFFFFFu, val, src);
-                        top[j] = lane_list_insert(top[j], v, Kp);
+                        top[j] = lane_list_insert(top[j], __shfl_sync(0xFFFFFFFFu, val[j], src), Kp);
                     }
                     theta[j] = __shfl_sync(0xFFFFFFFFu, top[j], (int)Kp - 1);
                 }
             }
         }
+    }
+}
+
+struct BscsrSample {
+    const uint32_t *first, *count, *local0, *lookback, *part;   // sample pieces (64 packets each)
+    uint32_t n;
+    const uint32_t *part_piece_begin;   // [P+1]
+    uint32_t *piece_top;                // [n][LFR][32]
+    uint32_t *ticket;                   // [P] pieces finished
+    uint32_t *theta_seed;               // [P][LFR]
+};
+
+template <int W, int LFR>
+__global__ void __launch_bounds__(kBsThreads)
+bscsr_sample_kernel(const uint8_t *__restrict__ packets, BscsrSample sm, const uint32_t *__restrict__ xq, uint32_t Kp) {
+    __shared__ uint32_t xs[1024];
+    __shared__ uint32_t ptab[16 * kBsThreads];
+    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) xs[i] = xq[i];
+    ptab[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned lane = lane_id();
+    const uint32_t piece = (blockIdx.x * blockDim.x + threadIdx.x) / 32u;
+    if (piece >= sm.n) return;
+    uint32_t theta[LFR], top[LFR];
+#pragma unroll
+    for (int j = 0; j < LFR; j++) { theta[j] = 0; top[j] = 0; }
+    BsTopSink<LFR> sink;
+    const uint32_t first = sm.first[piece];
+    bs_process<W, LFR>(packets, first - sm.lookback[piece], first, first + sm.count[piece], sm.local0[piece], 0u, Kp,
+                       reinterpret_cast<const uint8_t *>(xs), ptab, theta, top, sink, nullptr);
+#pragma unroll
+    for (int j = 0; j < LFR; j++) sm.piece_top[((size_t)piece * LFR + j) * 32u + lane] = (lane < Kp) ? top[j] : 0u;
+    // the last piece of the partition to finish merges the pieces' tops: K-th largest of the sampled prefix
+    const uint32_t p = sm.part[piece];
+    const uint32_t pb = sm.part_piece_begin[p], pe = sm.part_piece_begin[p + 1];
+    __threadfence();
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(&sm.ticket[p], 1u);
+    t = __shfl_sync(0xFFFFFFFFu, t, 0);
+    if (t != pe - pb - 1) return;
+    __threadfence();
+#pragma unroll
+    for (int j = 0; j < LFR; j++) {
+        uint32_t rtop = 0;
+        for (uint32_t q = pb; q < pe; q++) {
+            const uint32_t v = __ldcg(&sm.piece_top[((size_t)q * LFR + j) * 32u + lane]);
+            const uint32_t thr = __shfl_sync(0xFFFFFFFFu, rtop, (int)Kp - 1);
+            unsigned rest = __ballot_sync(0xFFFFFFFFu, lane < Kp && v > thr);
+            while (rest) {
+                const int src = __ffs(rest) - 1;
+                rest &= rest - 1;
+                rtop = lane_list_insert(rtop, __shfl_sync(0xFFFFFFFFu, v, src), Kp);
+            }
+        }
+        const uint32_t seed = __shfl_sync(0xFFFFFFFFu, rtop, (int)Kp - 1);
+        if (lane == 0) sm.theta_seed[p * LFR + j] = seed;
+    }
+    if (lane == 0) sm.ticket[p] = 0;
+}
+
+template <int W, int LFR>
+__global__ void __launch_bounds__(kBsThreads)
+bscsr_stream_kernel(const uint8_t *__restrict__ packets, BscsrChunks m, const uint32_t *__restrict__ xq, uint32_t Kp,
+                    BscsrLogs logs, const uint32_t *__restrict__ theta_seed, uint32_t *chunk_counter) {
+    __shared__ uint32_t xs[1024];                // query, pre-shifted (see bscsr_api.cu); columns >= cols hold 0
+    __shared__ uint32_t ptab[16 * kBsThreads];   // [prefix length 0..15][thread]: running sums of the products
+    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) xs[i] = xq[i];
+    ptab[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned lane = lane_id();
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(chunk_counter, 1u);
+        c = __shfl_sync(0xFFFFFFFFu, c, 0);
+        if (c >= m.n) break;
+        const uint32_t first = m.first[c], count = m.count[c], local0 = m.local0[c];
+        // chunks behind the sampled prefix of their partition start from the sample's K-th largest value
+        const bool seeded = local0 >= kBsSamplePackets;
+        uint32_t theta[LFR], top[LFR];
+        BsLogSink<LFR> sink;
+        sink.val = logs.val + (size_t)c * LFR * m.cap;
+        sink.row = logs.row + (size_t)c * LFR * m.cap;
+        sink.cap = m.cap;
 #pragma unroll
         for (int j = 0; j < LFR; j++) {
-            if (lane == 0) logs.cnt[(size_t)c * LFR + j] = lcnt[j];
-            logs.top[((size_t)c * LFR + j) * 32u + lane] = (lane < Kp) ? top[j] : 0u;
+            theta[j] = seeded ? theta_seed[m.part[c] * LFR + j] : 0u;
+            top[j] = theta[j];   // as if K candidates of that value had been seen: max(seed, own K-th largest)
+            sink.lcnt[j] = 0;
+        }
+        bs_process<W, LFR>(packets, first - m.lookback[c], first, first + count, local0, m.row_in[c], Kp,
+                           reinterpret_cast<const uint8_t *>(xs), ptab, theta, top, sink, logs.p0 + (size_t)c * LFR);
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < LFR; j++) logs.cnt[(size_t)c * LFR + j] = sink.lcnt[j];
         }
     }
 }
@@ -300,110 +393,93 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
     const uint32_t cb = part_chunk_begin[p], ce = part_chunk_begin[p + 1];
     const uint32_t tid = threadIdx.x;
     const unsigned lane = lane_id();
-    __shared__ uint32_t s_cnt[kReplayTile], s_off[kReplayTile + 1], s_thr[kReplayTile];
-    __shared__ uint32_t s_top[kReplayTile * 8];          // staged chunk tops, 8 at a time (see below)
     __shared__ uint32_t s_sv[kReplaySurvivors], s_sr[kReplaySurvivors];
-    __shared__ uint32_t s_n, s_wsum[kReplayThreads / 32];
+    __shared__ uint32_t s_wsum[kReplayThreads / 32];
     __shared__ uint32_t Lval[kBsMaxKp], Lidx[kBsMaxKp];
-    __shared__ uint32_t s_worst_idx, s_worst_val, s_started;
+    __shared__ uint32_t s_n, s_worst_idx, s_worst_val, s_started;
     if (tid < kBsMaxKp) { Lval[tid] = 0; Lidx[tid] = 0; }
     if (tid == 0) { s_worst_idx = 0; s_worst_val = 0; s_started = 0; s_n = 0; }
     if (blockIdx.x == 0 && tid == 0 && chunk_counter_reset) *chunk_counter_reset = 0;
-    uint32_t rtop = 0;   // warp 0: running K largest values of all chunks seen so far (lanes 0..Kp-1)
     const bool first_from_packet0 = logs.p0[(size_t)cb * LFR + j] != 0;
     __syncthreads();
 
+    // Literal replace-min (hpp:366-389) over the buffered entries, by warp 0: lanes screen 32 entries at a
+    // time against the CURRENT worst value (it only grows, so an entry below it can never be accepted);
+    // the rare accepted entries are applied one by one, in order, by lane 0.
     auto replay = [&]() {
-        // sequential, literal (hpp:366-389): only thread 0
-        if (tid == 0) {
+        if (tid < 32) {
             uint32_t wi = s_worst_idx, wv = s_worst_val, started = s_started;
             const uint32_t n = s_n;
-            for (uint32_t i = 0; i < n; i++) {
-                const uint32_t v = s_sv[i], r = s_sr[i];
-                if (!started) {
+            for (uint32_t b = 0; b < n; b += 32) {
+                const uint32_t i = b + lane;
+                const uint32_t v = (i < n) ? s_sv[i] : 0u, r = (i < n) ? s_sr[i] : 0u;
+                if (!started && n > 0) {
                     // the argmin is recomputed after EVERY packet (hpp:376-388): unless the first candidate comes
                     // from packet 0 of the partition, the all-zero list has already moved the worst slot
                     if (!first_from_packet0) { wi = bs_argmin(Lval, Kp); wv = Lval[wi]; }
                     started = 1;
                 }
-                if (v >= wv) {
-                    Lidx[wi] = r;
-                    Lval[wi] = v;
-                    wi = bs_argmin(Lval, Kp);
-                    wv = Lval[wi];
+                unsigned rest = __ballot_sync(0xFFFFFFFFu, i < n && v >= wv);
+                while (rest) {
+                    const int src = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    const uint32_t cv = __shfl_sync(0xFFFFFFFFu, v, src), cr = __shfl_sync(0xFFFFFFFFu, r, src);
+                    if (cv >= wv) {   // warp-uniform
+                        if (lane == 0) { Lidx[wi] = cr; Lval[wi] = cv; }
+                        __syncwarp();
+                        wi = bs_argmin(Lval, Kp);
+                        wv = Lval[wi];
+                    }
                 }
             }
-            s_worst_idx = wi; s_worst_val = wv; s_started = started; s_n = 0;
+            if (lane == 0) { s_worst_idx = wi; s_worst_val = wv; s_started = started; s_n = 0; }
         }
         __syncthreads();
     };
 
-    for (uint32_t t0 = cb; t0 < ce; t0 += kReplayTile) {
-        const uint32_t nt = (ce - t0 < kReplayTile) ? (ce - t0) : kReplayTile;
-        for (uint32_t i = tid; i < nt; i += blockDim.x) s_cnt[i] = logs.cnt[(size_t)(t0 + i) * LFR + j];
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t acc = 0;
-            for (uint32_t i = 0; i < nt; i++) { s_off[i] = acc; acc += s_cnt[i]; }
-            s_off[nt] = acc;
+    // chunks of the partition, kReplayThreads at a time: thread t copies the log of chunk t to its place
+    for (uint32_t t0 = cb; t0 < ce; t0 += blockDim.x) {
+        const uint32_t c = t0 + tid;
+        uint32_t cnt = (c < ce) ? logs.cnt[(size_t)c * LFR + j] : 0u;
+        // block-wide exclusive scan of cnt
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if ((int)lane >= d) inc += up;
         }
-        // thresholds: K-th largest value among the tops of all EARLIER chunks (warp 0, chunks in order)
-        for (uint32_t sub = 0; sub < nt; sub += 128) {   // tops staged 128 chunks at a time: 128 x 32 words = s_top? no: 8 words used
+        if (lane == 31) s_wsum[tid / 32] = inc;
+        __syncthreads();
+        uint32_t before = 0, all = 0;
+        for (uint32_t wv = 0; wv < blockDim.x / 32; wv++) { if (wv < tid / 32) before += s_wsum[wv]; all += s_wsum[wv]; }
+        if (s_n + all > kReplaySurvivors) {   // uniform: flush what is buffered first
             __syncthreads();
-            const uint32_t ns = (nt - sub < 128) ? (nt - sub) : 128;
-            // stage Kp (<= 32) tops of ns chunks; s_top holds ns * 32 words -> reuse as [128][32]
-            for (uint32_t i = tid; i < ns * 32u; i += blockDim.x)
-                s_top[i] = logs.top[((size_t)(t0 + sub + i / 32u) * LFR + j) * 32u + (i % 32u)];
-            __syncthreads();
-            if (tid < 32) {
-                for (uint32_t cidx = 0; cidx < ns; cidx++) {
-                    const uint32_t thr = __shfl_sync(0xFFFFFFFFu, rtop, (int)Kp - 1);
-                    if (lane == 0) s_thr[sub + cidx] = thr;
-                    const uint32_t v = s_top[cidx * 32u + lane];
-                    unsigned rest = __ballot_sync(0xFFFFFFFFu, lane < Kp && v > thr);
-                    while (rest) {
-                        const int src = __ffs(rest) - 1;
-                        rest &= rest - 1;
-                        rtop = lane_list_insert(rtop, __shfl_sync(0xFFFFFFFFu, v, src), Kp);
-                    }
+            replay();
+        }
+        if (all > kReplaySurvivors) {
+            // logs longer than the buffer (adversarial inputs): replay them straight from memory, in order
+            const uint32_t tend = (t0 + blockDim.x < ce) ? t0 + blockDim.x : ce;
+            for (uint32_t cc = t0; cc < tend; cc++) {
+                const uint32_t n_c = logs.cnt[(size_t)cc * LFR + j];
+                const size_t lbc = ((size_t)cc * LFR + j) * chunk_cap;
+                for (uint32_t e0 = 0; e0 < n_c; e0 += kReplaySurvivors) {
+                    const uint32_t ne = (n_c - e0 < kReplaySurvivors) ? (n_c - e0) : kReplaySurvivors;
+                    for (uint32_t e = tid; e < ne; e += blockDim.x) { s_sv[e] = logs.val[lbc + e0 + e]; s_sr[e] = logs.row[lbc + e0 + e]; }
+                    if (tid == 0) s_n = ne;
+                    __syncthreads();
+                    replay();
                 }
             }
+            continue;
         }
+        const uint32_t off = s_n + before + inc - cnt;
+        const size_t lb = ((size_t)c * LFR + j) * chunk_cap;
+        for (uint32_t e = 0; e < cnt; e++) { s_sv[off + e] = logs.val[lb + e]; s_sr[off + e] = logs.row[lb + e]; }
         __syncthreads();
-        // order-preserving filter of the tile's concatenated logs
-        const uint32_t total = s_off[nt];
-        for (uint32_t base = 0; base < total; base += blockDim.x) {
-            const uint32_t f = base + tid;
-            bool keep = false;
-            uint32_t v = 0, r = 0;
-            if (f < total) {
-                uint32_t lo = 0, hi = nt;   // chunk with s_off[chunk] <= f < s_off[chunk+1]
-                while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= f) lo = mid; else hi = mid; }
-                const size_t e = ((size_t)(t0 + lo) * LFR + j) * chunk_cap + (f - s_off[lo]);
-                v = logs.val[e];
-                r = logs.row[e];
-                keep = v >= s_thr[lo];
-            }
-            const unsigned km = __ballot_sync(0xFFFFFFFFu, keep);
-            if (lane == 0) s_wsum[tid / 32] = __popc(km);
-            __syncthreads();
-            uint32_t before = 0, all = 0;
-            for (uint32_t wv = 0; wv < blockDim.x / 32; wv++) { if (wv < tid / 32) before += s_wsum[wv]; all += s_wsum[wv]; }
-            if (s_n + all > kReplaySurvivors) {   // uniform: flush what is buffered first
-                __syncthreads();
-                replay();
-            }
-            if (keep) {
-                const uint32_t pos = s_n + before + __popc(km & lanemask_lt());
-                s_sv[pos] = v;
-                s_sr[pos] = r;
-            }
-            __syncthreads();
-            if (tid == 0) s_n += all;
-            __syncthreads();
-        }
-        replay();
+        if (tid == 0) s_n += all;
+        __syncthreads();
     }
+    replay();
     // write-back (.cpp:151-185): word t, position j = list j slot t; values widened to ufixed<32,1>
     if (tid < Kp) {
         const size_t o = ((size_t)p * Kp + tid) * 16u + j;
