@@ -306,17 +306,23 @@ bscsr_sample_kernel(const uint8_t *__restrict__ packets, BscsrSample sm, const u
     t = __shfl_sync(0xFFFFFFFFu, t, 0);
     if (t != pe - pb - 1) return;
     __threadfence();
-#pragma unroll
+    constexpr uint32_t kMaxPieces = kBsSamplePackets / kBsSamplePiece;
+#pragma unroll 1
     for (int j = 0; j < LFR; j++) {
+        // all loads first (independent), then the sequential merge from registers
+        uint32_t vq[kMaxPieces];
+#pragma unroll
+        for (uint32_t q = 0; q < kMaxPieces; q++)
+            vq[q] = (pb + q < pe) ? __ldcg(&sm.piece_top[((size_t)(pb + q) * LFR + j) * 32u + lane]) : 0u;
         uint32_t rtop = 0;
-        for (uint32_t q = pb; q < pe; q++) {
-            const uint32_t v = __ldcg(&sm.piece_top[((size_t)q * LFR + j) * 32u + lane]);
+#pragma unroll
+        for (uint32_t q = 0; q < kMaxPieces; q++) {
             const uint32_t thr = __shfl_sync(0xFFFFFFFFu, rtop, (int)Kp - 1);
-            unsigned rest = __ballot_sync(0xFFFFFFFFu, lane < Kp && v > thr);
+            unsigned rest = __ballot_sync(0xFFFFFFFFu, lane < Kp && vq[q] > thr);
             while (rest) {
                 const int src = __ffs(rest) - 1;
                 rest &= rest - 1;
-                rtop = lane_list_insert(rtop, __shfl_sync(0xFFFFFFFFu, v, src), Kp);
+                rtop = lane_list_insert(rtop, __shfl_sync(0xFFFFFFFFu, vq[q], src), Kp);
             }
         }
         const uint32_t seed = __shfl_sync(0xFFFFFFFFu, rtop, (int)Kp - 1);
@@ -394,7 +400,7 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
     const uint32_t tid = threadIdx.x;
     const unsigned lane = lane_id();
     __shared__ uint32_t s_sv[kReplaySurvivors], s_sr[kReplaySurvivors];
-    __shared__ uint32_t s_wsum[kReplayThreads / 32];
+    __shared__ uint32_t s_wsum[kReplayThreads / 32], s_off[kReplayThreads + 1];
     __shared__ uint32_t Lval[kBsMaxKp], Lidx[kBsMaxKp];
     __shared__ uint32_t s_n, s_worst_idx, s_worst_val, s_started;
     if (tid < kBsMaxKp) { Lval[tid] = 0; Lidx[tid] = 0; }
@@ -472,11 +478,21 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
             }
             continue;
         }
-        const uint32_t off = s_n + before + inc - cnt;
-        const size_t lb = ((size_t)c * LFR + j) * chunk_cap;
-        for (uint32_t e = 0; e < cnt; e++) { s_sv[off + e] = logs.val[lb + e]; s_sr[off + e] = logs.row[lb + e]; }
+        // order-preserving gather: entry f of the tile's concatenated logs belongs to the chunk whose
+        // exclusive offset is the last one <= f
+        s_off[tid] = before + inc - cnt;
+        if (tid == 0) s_off[blockDim.x] = all;
         __syncthreads();
-        if (tid == 0) s_n += all;
+        const uint32_t base_n = s_n;
+        for (uint32_t f = tid; f < all; f += blockDim.x) {
+            uint32_t lo = 0, hi = blockDim.x;
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= f) lo = mid; else hi = mid; }
+            const size_t e = ((size_t)(t0 + lo) * LFR + j) * chunk_cap + (f - s_off[lo]);
+            s_sv[base_n + f] = logs.val[e];
+            s_sr[base_n + f] = logs.row[e];
+        }
+        __syncthreads();
+        if (tid == 0) s_n = base_n + all;
         __syncthreads();
     }
     replay();
