@@ -379,18 +379,6 @@ __global__ void bscsr_query_kernel(const uint32_t *__restrict__ vec32, uint32_t 
     xq[c] = (W == 32) ? q : (q << 1);
 }
 
-// argmin with MIN(res,a,b) = res[a] < res[b] ? a : b (hpp:28): highest slot among equal minima;
-// K == 4 reproduces `MIN(res, 2, 2)` (hpp:45): slot 3 is never the minimum.
-__device__ __forceinline__ uint32_t bs_argmin(const uint32_t *v, uint32_t Kp) {
-    if (Kp == 4) {
-        const uint32_t m0 = (v[0] < v[1]) ? 0u : 1u;
-        return (v[m0] < v[2]) ? m0 : 2u;
-    }
-    uint32_t best = 0;
-    for (uint32_t i = 1; i < Kp; i++) best = (v[best] < v[i]) ? best : i;
-    return best;
-}
-
 template <int W>
 __global__ void __launch_bounds__(kReplayThreads)
 bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begin, uint32_t LFR, uint32_t Kp,
@@ -401,28 +389,37 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
     const unsigned lane = lane_id();
     __shared__ uint32_t s_sv[kReplaySurvivors], s_sr[kReplaySurvivors];
     __shared__ uint32_t s_wsum[kReplayThreads / 32], s_off[kReplayThreads + 1];
-    __shared__ uint32_t Lval[kBsMaxKp], Lidx[kBsMaxKp];
-    __shared__ uint32_t s_n, s_worst_idx, s_worst_val, s_started;
-    if (tid < kBsMaxKp) { Lval[tid] = 0; Lidx[tid] = 0; }
-    if (tid == 0) { s_worst_idx = 0; s_worst_val = 0; s_started = 0; s_n = 0; }
+    __shared__ uint32_t s_n;
+    if (tid == 0) s_n = 0;
     if (blockIdx.x == 0 && tid == 0 && chunk_counter_reset) *chunk_counter_reset = 0;
     const bool first_from_packet0 = logs.p0[(size_t)cb * LFR + j] != 0;
     __syncthreads();
 
-    // Literal replace-min (hpp:366-389) over the buffered entries, by warp 0: lanes screen 32 entries at a
-    // time against the CURRENT worst value (it only grows, so an entry below it can never be accepted);
-    // the rare accepted entries are applied one by one, in order, by lane 0.
+    // Literal replace-min (hpp:366-389) over the buffered entries, by warp 0.  The K slots live one per lane
+    // (lv/li of lanes 0..Kp-1), so the argmin is a warp reduction instead of a serial scan.  Lanes screen 32
+    // entries at a time against the CURRENT worst value (it only grows, so an entry below it can never be
+    // accepted); the rare accepted entries are applied one by one, in stream order.
+    uint32_t lv = 0, li = 0;   // warp 0 only: value / row index of slot `lane`
+    uint32_t wi = 0, wv = 0, started = 0;
+    auto warp_argmin = [&](uint32_t &idx, uint32_t &val) {
+        // MIN(res,a,b) = res[a] < res[b] ? a : b  -> the HIGHEST slot among equal minima (hpp:28);
+        // K == 4 reproduces `MIN(res, 2, 2)` (hpp:45): slot 3 is never the minimum
+        const bool in = lane < Kp && !(Kp == 4 && lane == 3);
+        const uint32_t mn = __reduce_min_sync(0xFFFFFFFFu, in ? lv : 0xFFFFFFFFu);
+        const unsigned who = __ballot_sync(0xFFFFFFFFu, in && lv == mn);
+        idx = 31u - (uint32_t)__clz((int)who);
+        val = mn;
+    };
     auto replay = [&]() {
         if (tid < 32) {
-            uint32_t wi = s_worst_idx, wv = s_worst_val, started = s_started;
             const uint32_t n = s_n;
             for (uint32_t b = 0; b < n; b += 32) {
                 const uint32_t i = b + lane;
                 const uint32_t v = (i < n) ? s_sv[i] : 0u, r = (i < n) ? s_sr[i] : 0u;
-                if (!started && n > 0) {
+                if (!started) {
                     // the argmin is recomputed after EVERY packet (hpp:376-388): unless the first candidate comes
                     // from packet 0 of the partition, the all-zero list has already moved the worst slot
-                    if (!first_from_packet0) { wi = bs_argmin(Lval, Kp); wv = Lval[wi]; }
+                    if (!first_from_packet0) warp_argmin(wi, wv);
                     started = 1;
                 }
                 unsigned rest = __ballot_sync(0xFFFFFFFFu, i < n && v >= wv);
@@ -431,14 +428,12 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
                     rest &= rest - 1;
                     const uint32_t cv = __shfl_sync(0xFFFFFFFFu, v, src), cr = __shfl_sync(0xFFFFFFFFu, r, src);
                     if (cv >= wv) {   // warp-uniform
-                        if (lane == 0) { Lidx[wi] = cr; Lval[wi] = cv; }
-                        __syncwarp();
-                        wi = bs_argmin(Lval, Kp);
-                        wv = Lval[wi];
+                        if (lane == wi) { li = cr; lv = cv; }
+                        warp_argmin(wi, wv);
                     }
                 }
             }
-            if (lane == 0) { s_worst_idx = wi; s_worst_val = wv; s_started = started; s_n = 0; }
+            if (lane == 0) s_n = 0;
         }
         __syncthreads();
     };
@@ -499,8 +494,8 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
     // write-back (.cpp:151-185): word t, position j = list j slot t; values widened to ufixed<32,1>
     if (tid < Kp) {
         const size_t o = ((size_t)p * Kp + tid) * 16u + j;
-        res_idx_words[o] = Lidx[tid];
-        res_val_words[o] = (W == 32) ? Lval[tid] : (Lval[tid] << (32 - W));
+        res_idx_words[o] = li;
+        res_val_words[o] = (W == 32) ? lv : (lv << (32 - W));
     }
 }
 
