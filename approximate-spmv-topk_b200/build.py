@@ -54,7 +54,7 @@ def build_host_exe(force: bool = False) -> Path:
         return EXE
     cxx = os.environ.get("CXX", "g++")
     cmd = [cxx, "-O3", "-std=c++17", "-o", str(EXE), str(src), f"-L{LIB_DIR}", "-ltopkspmv",
-           f"-Wl,-rpath,{LIB_DIR}", "-lpthread"]
+           "-Wl,-rpath,$ORIGIN/../approximate-spmv-topk_b200/lib", "-lpthread"]
     print("[build]", " ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)
     return EXE

@@ -219,3 +219,33 @@ def test_two_million_rows_vs_float64(cuda_required, tks, orc):
             fi, fv = orc.f64_topk(ptr, idx, val, vec, 100)
             np.testing.assert_allclose(v, fv, rtol=RTOL)
             assert len(set(i.tolist()) ^ set(fi.tolist())) <= 2
+
+
+def test_row_shards_merge_on_device_equals_unsharded(cuda_required, tks, orc, cfg1):
+    """The multi-GPU path on one device: 3 contiguous row shards (3 handles), their K candidate keys
+    concatenated (what the NCCL all-gather delivers) and merged by tks_merge_keys_device."""
+    import torch
+    x, y, v, ptr = cfg1
+    sh = tks.sharding
+    vec = make_query(1024, 31)
+    k = 100
+    idx0, val0, _ = run_engine(tks, ptr, y, v, 10000, 1024, vec, k)
+    shards = sh.plan_row_shards_by_nnz(ptr, 3)
+    engines, gathered = [], torch.empty(3 * k, dtype=torch.int64, device="cuda")
+    for r, (r0, r1) in enumerate(shards):
+        p, i, vv = sh.slice_csr(ptr, y, v, r0, r1)
+        e = tks.SpMV(p, i, vv, r1 - r0, 1024, vec=vec, k=k, row_offset=r0)
+        e()
+        kp, n = e.result_keys_device(0)
+
+        class _A:
+            __cuda_array_interface__ = {"shape": (k,), "typestr": "<i8", "data": (kp, False), "version": 2}
+        gathered[r * k:(r + 1) * k] = torch.as_tensor(_A(), device="cuda")
+        engines.append(e)
+    torch.cuda.synchronize()
+    engines[0].merge_keys_device(gathered.data_ptr(), 3 * k, k)
+    val, idx, cnt = engines[0].read_result()
+    assert cnt == k
+    assert np.array_equal(idx, idx0) and np.array_equal(val.view(np.uint32), val0.view(np.uint32))
+    for e in engines:
+        e.close()

@@ -1,0 +1,84 @@
+"""world_size-2 `gloo` test (CPU) of the multi-GPU plumbing: contiguous row shards, per-rank K
+candidates as 64-bit ordering keys, all-gather, merge on every rank.  The per-rank scores come from a plain
+float64 product here -- this test is about the exchange and the merge, not about the kernel."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, k, tie_higher, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from _pkg import pkg
+    tks = pkg()
+    gen, sh = tks.create_matrices, tks.sharding
+    rows, cols = 5000, 256
+    x, y, v = gen.create_sparse_matrix(rows, cols, 12, "gamma", seed=3)
+    ptr = gen.csr_from_coo(x, rows)
+    rng = np.random.default_rng(9)
+    vec = rng.random(cols)
+    shards = sh.plan_row_shards_by_nnz(ptr, world)
+    r0, r1 = shards[rank]
+    p, idx, val = sh.slice_csr(ptr, y, v, r0, r1)
+    # local scores of the shard (float32 like the engine's output), local row ids + row_offset
+    deg = np.diff(p.astype(np.int64))
+    lx = np.repeat(np.arange(r1 - r0), deg)
+    score = np.zeros(r1 - r0)
+    np.add.at(score, lx, val * vec[idx])
+    score = score.astype(np.float32)
+    order = np.lexsort((np.arange(score.size) if not tie_higher else -np.arange(score.size), -score.astype(np.float64)))[:k]
+    mine = sh.make_keys(score[order], (order + r0).astype(np.uint32), tie_higher)
+    mine = np.pad(mine, (0, k - mine.size))
+    t = torch.from_numpy(mine.view(np.int64).copy())
+    gathered = torch.empty(world * k, dtype=torch.int64)
+    dist.all_gather_into_tensor(gathered, t)
+    merged = sh.merge_topk_host([gathered.numpy().view(np.uint64)], k)
+    ms, mr = sh.split_keys(merged, tie_higher)
+    if rank == 0:
+        q.put((ms, mr, shards))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tie_higher", [False, True])
+def test_two_rank_allgather_merge_equals_global_topk(tie_higher):
+    world, k = 2, 50
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, k, tie_higher, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ms, mr, shards = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # global reference
+    sys.path.insert(0, str(ROOT))
+    from _pkg import pkg
+    gen = pkg().create_matrices
+    x, y, v = gen.create_sparse_matrix(5000, 256, 12, "gamma", seed=3)
+    vec = np.random.default_rng(9).random(256)
+    score = np.zeros(5000)
+    np.add.at(score, x, v * vec[y])
+    score = score.astype(np.float32)
+    order = np.lexsort((np.arange(5000) if not tie_higher else -np.arange(5000), -score.astype(np.float64)))[:k]
+    assert np.array_equal(mr, order.astype(np.uint32))
+    assert np.array_equal(ms, score[order])
+    assert shards[0][1] == shards[1][0] and shards[0][0] == 0 and shards[1][1] == 5000
