@@ -246,6 +246,9 @@ def test_row_shards_merge_on_device_equals_unsharded(cuda_required, tks, orc, cf
     engines[0].merge_keys_device(gathered.data_ptr(), 3 * k, k)
     val, idx, cnt = engines[0].read_result()
     assert cnt == k
-    assert np.array_equal(idx, idx0) and np.array_equal(val.view(np.uint32), val0.view(np.uint32))
+    # same rows; the scores may differ in the last bit because a shard changes which lanes a row's
+    # non-zeros fall into (a different fp32 summation order)
+    assert np.array_equal(np.sort(idx), np.sort(idx0))
+    np.testing.assert_allclose(val, val0, rtol=1e-6)
     for e in engines:
         e.close()
