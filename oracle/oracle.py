@@ -288,3 +288,116 @@ def ref_read_mtx(path, zero_indexed=False, sort=False):
     v = np.zeros(nnz.value, np.float32)
     R.ref_read_mtx_fetch(x, y, v)
     return rc, rows.value, cols.value, x, y, v
+
+
+# --------------------------------------------------------------------------
+# the reference's FPGA host + HLS kernel, compiled against oracle/shim and run in
+# software (oracle/ref_fpga.cpp) -- optional, one library per knob combination
+# --------------------------------------------------------------------------
+
+_ref_fpga = {}
+
+
+def ref_fpga_path(W=20, Kp=8, LFR=4, P=32):
+    return _HERE / "_ref" / f"libref_fpga_w{W}_k{Kp}_l{LFR}_p{P}.so"
+
+
+def ref_fpga(W=20, Kp=8, LFR=4, P=32):
+    """ctypes handle of oracle/_ref/libref_fpga_w<W>_k<Kp>_l<LFR>_p<P>.so, or None when never built."""
+    key = (W, Kp, LFR, P)
+    if key not in _ref_fpga:
+        path = ref_fpga_path(*key)
+        if not path.exists():
+            return None
+        R = C.CDLL(str(path))
+        ip = C.POINTER(C.c_int)
+        R.ref_fpga_params.argtypes = [ip, ip, ip, ip, ip]
+        R.ref_fx32_from_double.argtypes = [C.c_double]
+        R.ref_fx32_from_double.restype = C.c_uint32
+        R.ref_fxW_from_fx32.argtypes = [C.c_uint32]
+        R.ref_fxW_from_fx32.restype = C.c_uint32
+        R.ref_create_sample_vector_fx32.argtypes = [_u32p, C.c_int, C.c_int]
+        R.ref_fpga_create.argtypes = [_u32p, _u32p, _u32p, C.c_uint64, C.c_uint32, C.c_uint32, _u32p]
+        R.ref_fpga_create.restype = C.c_void_p
+        R.ref_fpga_destroy.argtypes = [C.c_void_p]
+        u32 = C.POINTER(C.c_uint32)
+        R.ref_fpga_partition_info.argtypes = [C.c_void_p, C.c_int, u32, u32, u32, u32]
+        R.ref_fpga_packets.argtypes = [C.c_void_p, C.c_int, _u64p]
+        R.ref_fpga_query_blocks.argtypes = [C.c_void_p, _u64p]
+        R.ref_fpga_run.argtypes = [C.c_void_p]
+        R.ref_fpga_reset.argtypes = [C.c_void_p, _u32p]
+        R.ref_fpga_result_words.argtypes = [C.c_void_p, C.c_int, _u32p, _u32p]
+        R.ref_fpga_read_result.argtypes = [C.c_void_p, _u32p, _u32p, C.c_uint32]
+        R.ref_fpga_read_result.restype = C.c_uint32
+        R.ref_gold_topk_fx32.argtypes = [_u32p, _u32p, _u32p, C.c_uint64, _u32p, C.c_uint32, C.c_int, _u32p, _u32p]
+        w, b, k, l, p = (C.c_int() for _ in range(5))
+        R.ref_fpga_params(C.byref(w), C.byref(b), C.byref(k), C.byref(l), C.byref(p))
+        assert (w.value, k.value, l.value, p.value) == key, "library knobs do not match its file name"
+        R.packet_size = b.value
+        _ref_fpga[key] = R
+    return _ref_fpga[key]
+
+
+class RefFpga:
+    """The reference's `struct SpMV` (host_spmv_bscsr.cpp:79-485) driving its own HLS kernel in software."""
+
+    def __init__(self, row, col, val32, num_rows, num_cols, vec32, W=20, Kp=8, LFR=4, P=32):
+        self.R = ref_fpga(W, Kp, LFR, P)
+        if self.R is None:
+            raise FileNotFoundError(ref_fpga_path(W, Kp, LFR, P))
+        self.W, self.Kp, self.LFR, self.P, self.B = W, Kp, LFR, P, self.R.packet_size
+        row, col, val32, vec32 = _c(row, np.uint32), _c(col, np.uint32), _c(val32, np.uint32), _c(vec32, np.uint32)
+        self.cols = int(num_cols)
+        self.h = self.R.ref_fpga_create(row, col, val32, row.size, int(num_rows), self.cols, vec32)
+
+    def close(self):
+        if self.h:
+            self.R.ref_fpga_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def partition_info(self):
+        out = np.zeros((self.P, 4), np.uint32)   # first_row, last_row, nnz, num_blocks
+        for p in range(self.P):
+            v = [C.c_uint32() for _ in range(4)]
+            self.R.ref_fpga_partition_info(self.h, p, *[C.byref(t) for t in v])
+            out[p] = [t.value for t in v]
+        return out
+
+    def packets(self):
+        info = self.partition_info()
+        res = []
+        for p in range(self.P):
+            o = np.zeros((int(info[p, 3]), 8), np.uint64)
+            self.R.ref_fpga_packets(self.h, p, o.reshape(-1))
+            res.append(o)
+        return res
+
+    def query_blocks(self):
+        o = np.zeros(((self.cols + self.B - 1) // self.B, 8), np.uint64)
+        self.R.ref_fpga_query_blocks(self.h, o.reshape(-1))
+        return o
+
+    def run(self):
+        self.R.ref_fpga_run(self.h)
+
+    def reset(self, vec32):
+        self.R.ref_fpga_reset(self.h, _c(vec32, np.uint32))
+
+    def result_words(self):
+        iw = np.zeros((self.P, self.Kp, 16), np.uint32)
+        vw = np.zeros((self.P, self.Kp, 16), np.uint32)
+        for p in range(self.P):
+            a = np.zeros(self.Kp * 16, np.uint32)
+            b = np.zeros(self.Kp * 16, np.uint32)
+            self.R.ref_fpga_result_words(self.h, p, a, b)
+            iw[p], vw[p] = a.reshape(self.Kp, 16), b.reshape(self.Kp, 16)
+        return iw, vw
+
+    def read_result(self):
+        cap = self.P * self.Kp * 16
+        ri, rv = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+        n = self.R.ref_fpga_read_result(self.h, ri, rv, cap)
+        return ri[:n].copy(), rv[:n].copy()
