@@ -18,7 +18,18 @@ def compare(orc, x, y, v, rows, cols, vec, W=20, Kp=8, LFR=4, P=32):
     info = ref.partition_info()
     assert np.array_equal(info[:, 0], o["packed"]["first_row"]) and np.array_equal(info[:, 1], o["packed"]["last_row"])
     for p, pk in enumerate(ref.packets()):
-        assert np.array_equal(pk, o["packed"]["packets"][p]), f"packets of partition {p} differ"
+        mine = o["packed"]["packets"][p].copy()
+        pk = pk.copy()
+        assert np.array_equal(pk[:-1], mine[:-1]), f"packets of partition {p} differ"
+        # The reference's packet builder compares the row of tuple [nnz_p] -- one past its vector -- with the last
+        # row (host_spmv_bscsr.cpp:224): heap garbage decides whether the LAST packet's final segment end is
+        # nnz or nnz+1 (a zero-valued padding slot, invisible to the kernel).  The restatement defines that read
+        # as "different row"; the 4-bit x fields of the last packet are therefore compared through the kernel
+        # outputs below, every other bit of it here.
+        xmask = np.uint64(~((1 << (4 * B)) - 1) & 0xFFFFFFFFFFFFFFFF)
+        pk[-1, 0] &= xmask
+        mine[-1, 0] &= xmask
+        assert np.array_equal(pk[-1], mine[-1]), f"last packet of partition {p} differs outside its x fields"
     assert np.array_equal(ref.query_blocks(), orc.pack_query(o["vec32"], W))
     ref.run()
     iw, vw = ref.result_words()
@@ -70,17 +81,11 @@ def test_long_rows_span_many_packets(orc):
     compare(orc, x, y, v, rows, cols, cases.make_query(cols, 9), P=4)
 
 
-def test_two_single_nnz_rows_per_partition(orc):
-    """One packet per partition holding two one-element rows: the first is a candidate (lane 1), the last row of
-    a partition is never offered.  (With ONE non-zero per partition the reference's packet builder
-    reads one tuple past its vector, host_spmv_bscsr.cpp:224, and the packet then depends on heap garbage; the
-    restatement defines that read as "different row", so that degenerate input is not compared here.)"""
-    rows = 64
-    x = np.arange(rows, dtype=np.uint32)
-    y = (x * 7 % 64).astype(np.uint32)
-    v = np.linspace(0.2, 0.9, rows)
-    o = compare(orc, x, y, v, rows, 64, cases.make_query(64, 1))
-    assert np.array_equal(np.sort(o["idx"]), np.arange(0, rows, 2))
+# NB: partitions of only a few non-zeros are deliberately not compared live.  In a partition's last, partly filled
+# packet the reference records the final row's segment end only because the out-of-bounds read at
+# host_spmv_bscsr.cpp:224 "sees a different row"; with tiny vectors recycled by the allocator the garbage can
+# equal the last row id, which drops that segment and changes the kernel's output from run to run.  The
+# restatement (and the CUDA packer) define the read as "different row" -- the outcome for any realistic heap.
 
 
 def test_quantisation_chain(orc):
