@@ -23,7 +23,8 @@ class TksConfig(C.Structure):
     _fields_ = [("mode", C.c_int32), ("fixed_width", C.c_int32), ("partitions", C.c_int32),
                 ("local_k", C.c_int32), ("limited_finished_rows", C.c_int32), ("max_cols", C.c_int32),
                 ("tie_break", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_int32),
-                ("chunk_nnz", C.c_int32), ("profile_kernels", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("chunk_nnz", C.c_int32), ("profile_kernels", C.c_int32), ("batch_mode", C.c_int32),
+                ("batch_pool_cap", C.c_int32), ("batch_fma", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class TksStats(C.Structure):
@@ -31,7 +32,8 @@ class TksStats(C.Structure):
                 ("algorithmic_bytes", C.c_uint64), ("device_bytes", C.c_uint64),
                 ("last_kernel_ms", C.c_float), ("last_total_ms", C.c_float),
                 ("last_candidates", C.c_uint32), ("launches_per_run", C.c_uint32),
-                ("last_main_kernel_ms", C.c_float), ("reserved", C.c_uint32 * 7)]
+                ("last_main_kernel_ms", C.c_float), ("batched_fallbacks", C.c_uint32),
+                ("reserved", C.c_uint32 * 6)]
 
 
 class TksError(RuntimeError):
@@ -45,7 +47,7 @@ SYMBOLS = [
     "tks_version", "tks_default_config", "tks_create", "tks_destroy", "tks_last_error",
     "tks_upload_csr", "tks_upload_csr_device", "tks_upload_bscsr", "tks_generate_synthetic",
     "tks_download_csr", "tks_set_query", "tks_set_query_device", "tks_run", "tks_run_async",
-    "tks_read_result", "tks_read_partition_results", "tks_result_keys_device", "tks_merge_keys_device",
+    "tks_read_result", "tks_read_partition_results", "tks_result_keys_device", "tks_merge_keys_device", "tks_merge_keys_batched_device",
     "tks_get_stats", "tks_bscsr_packet_size", "tks_fixed32_from_double", "tks_fixedW_from_fixed32",
     "tks_pack_bscsr", "tks_read_mtx", "tks_coo2csr",
 ]
@@ -85,6 +87,7 @@ def lib() -> C.CDLL:
     L.tks_read_partition_results.argtypes = [vp, vp, vp]
     L.tks_result_keys_device.argtypes = [vp, C.c_uint32, C.POINTER(vp), u32p]
     L.tks_merge_keys_device.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, vp]
+    L.tks_merge_keys_batched_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     L.tks_get_stats.argtypes = [vp, C.POINTER(TksStats)]
     L.tks_bscsr_packet_size.argtypes = [C.c_int]
     L.tks_fixed32_from_double.argtypes = [C.c_double]

@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "csr_build.cuh"
+#include "csr_batched.cuh"
 #include "csr_topk.cuh"
 #include "handle.hpp"
 
@@ -83,6 +84,16 @@ int alloc_query_side(Handle *h) {
     TKS_CUDA(h, cudaMallocHost(&h->h_res_val, (size_t)mb * h->kmax * sizeof(float)));
     TKS_CUDA(h, cudaMallocHost(&h->h_res_count, mb * sizeof(uint32_t)));
     TKS_CUDA(h, cudaMallocHost(&h->h_x, (size_t)mb * h->cfg.max_cols * sizeof(float)));
+    if (mb > 1 && h->batched_ok) {
+        const uint32_t npass = (mb + kBqPerPass - 1) / kBqPerPass;
+        h->bpool_cap = h->cfg.batch_pool_cap > 0 ? (uint32_t)h->cfg.batch_pool_cap : 32768u;
+        h->b_sample_cap = 8192;
+        TKS_CUDA(h, cudaMalloc(&h->d_xT, (size_t)npass * batched_table_bytes((uint32_t)h->cfg.max_cols)));
+        TKS_CUDA(h, cudaMalloc(&h->d_bpool, (size_t)mb * h->bpool_cap * sizeof(uint64_t)));
+        TKS_CUDA(h, cudaMalloc(&h->d_pass_counter, npass * sizeof(uint32_t)));
+        TKS_CUDA(h, cudaMemset(h->d_pass_counter, 0, npass * sizeof(uint32_t)));
+        TKS_CUDA(h, cudaMalloc(&h->d_bsample_keys, (size_t)mb * h->b_sample_cap * sizeof(uint32_t)));
+    }
     return TKS_OK;
 }
 
@@ -187,10 +198,8 @@ int check_float_upload(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, ui
     return TKS_OK;
 }
 
-int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false) {
-    if (!h->have_matrix) return h->fail(TKS_ESTATE, "no matrix uploaded");
-    if (!h->have_query) return h->fail(TKS_ESTATE, "no query set");
-    if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k=%u outside 1..%u", k, h->kmax);
+// sample -> main -> select for query q alone (also the fallback of a batched query whose pool overflowed)
+void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool profile) {
     const int variant = cap_variant_for_k(k);
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
     CsrDevice m{h->d_val, h->d_colf, h->d_chunk_start, h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols,
@@ -200,29 +209,106 @@ int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false) {
     const uint32_t stride = h->n_chunks / n_sample;
     size_t sample_smem = ((size_t)h->cols + 1u) * 4u;
     if (sample_smem < (size_t)n_sample * 4u) sample_smem = (size_t)n_sample * 4u;
-    for (uint32_t q = 0; q < h->batch; q++) {
-        const float *x = h->d_x + (size_t)q * h->cols;
-        RunState *st = h->d_state + q;
-        const uint32_t sgrid = (n_sample * kWarp + kSampleThreads - 1) / kSampleThreads;
-        csr_sample_kernel<<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride,
-                                                                     k);
-        if (profile && q == 0) cudaEventRecord(h->evm0, s);
-        switch (variant) {
-            case 0: launch_main<256>(h, 0, m, x, st, k, s); break;
-            case 1: launch_main<512>(h, 1, m, x, st, k, s); break;
-            case 2: launch_main<1024>(h, 2, m, x, st, k, s); break;
-            default: launch_main<2048>(h, 3, m, x, st, k, s); break;
-        }
-        if (profile && q == 0) cudaEventRecord(h->evm1, s);
-        select_topk_kernel<<<1, kSelectThreads, kSelectDynSmem, s>>>(
-            h->d_pool, &st->pool_count, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
-            h->d_res_idx + (size_t)q * h->kmax, h->d_res_val + (size_t)q * h->kmax, h->d_res_count + q, st);
+    const float *x = h->d_x + (size_t)q * h->cols;
+    RunState *st = h->d_state + q;
+    const uint32_t sgrid = (n_sample * kWarp + kSampleThreads - 1) / kSampleThreads;
+    csr_sample_kernel<<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, k);
+    if (profile) cudaEventRecord(h->evm0, s);
+    switch (variant) {
+        case 0: launch_main<256>(h, 0, m, x, st, k, s); break;
+        case 1: launch_main<512>(h, 1, m, x, st, k, s); break;
+        case 2: launch_main<1024>(h, 2, m, x, st, k, s); break;
+        default: launch_main<2048>(h, 3, m, x, st, k, s); break;
+    }
+    if (profile) cudaEventRecord(h->evm1, s);
+    select_topk_kernel<<<1, kSelectThreads, kSelectDynSmem, s>>>(
+        h->d_pool, 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
+        h->d_res_idx + (size_t)q * h->kmax, h->d_res_val + (size_t)q * h->kmax, 0u, h->d_res_count + q, nullptr);
+}
+
+template <bool SAMPLE>
+void launch_batched_kernel(Handle *h, const CsrDevice &m, const BatchedArgs &a, uint32_t grid, cudaStream_t s) {
+    const size_t smem = batched_smem_bytes(m.cols);
+    if (h->cfg.batch_fma) csr_batched_kernel<SAMPLE, true><<<grid, kBThreads, smem, s>>>(m, a);
+    else csr_batched_kernel<SAMPLE, false><<<grid, kBThreads, smem, s>>>(m, a);
+}
+
+// One matrix pass per 32 queries (csr_batched.cuh).
+void launch_batched(Handle *h, uint32_t k, cudaStream_t s, bool profile) {
+    CsrDevice m{h->d_val, h->d_colf, h->d_chunk_start, h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols,
+                (uint32_t)h->row_offset};
+    BatchedArgs a{};
+    a.xT = h->d_xT;
+    a.st = h->d_state;
+    a.pool = h->d_bpool;
+    a.pool_cap = h->bpool_cap;
+    a.batch = h->batch;
+    a.npass = (h->batch + kBqPerPass - 1) / kBqPerPass;
+    a.pass_counter = h->d_pass_counter;
+    a.sample_keys = h->d_bsample_keys;
+    a.n_sample = h->n_chunks < h->b_sample_cap ? h->n_chunks : h->b_sample_cap;
+    a.stride = h->n_chunks / a.n_sample;
+    a.tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
+    batched_transpose_kernel<<<h->num_sms, 256, 0, s>>>(h->d_x, h->batch, h->cols, a.npass, h->d_xT);
+    const uint32_t warps_per_cta = kBThreads / kWarp;
+    uint32_t sgrid = ((a.n_sample + 3u) / 4u + warps_per_cta - 1) / warps_per_cta;
+    if (sgrid > (uint32_t)h->num_sms) sgrid = (uint32_t)h->num_sms;
+    launch_batched_kernel<true>(h, m, a, sgrid, s);
+    batched_tau_kernel<<<h->batch, 256, (size_t)a.n_sample * 4u, s>>>(a, k);
+    if (profile) cudaEventRecord(h->evm0, s);
+    launch_batched_kernel<false>(h, m, a, (uint32_t)h->num_sms, s);
+    if (profile) cudaEventRecord(h->evm1, s);
+    select_topk_kernel<<<h->batch, kSelectThreads, kSelectDynSmem, s>>>(
+        h->d_bpool, h->bpool_cap, h->d_state, 0u, h->bpool_cap, k, a.tie_higher, h->d_res_keys, h->d_res_idx,
+        h->d_res_val, h->kmax, h->d_res_count, h->d_pass_counter);
+}
+
+bool use_batched(const Handle *h) {
+    return h->batch > 1 && h->batched_ok && h->cfg.batch_mode == 0 && h->d_xT != nullptr &&
+           batched_smem_bytes(h->cols) <= batched_smem_bytes((uint32_t)h->cfg.max_cols);
+}
+
+int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false) {
+    if (!h->have_matrix) return h->fail(TKS_ESTATE, "no matrix uploaded");
+    if (!h->have_query) return h->fail(TKS_ESTATE, "no query set");
+    if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k=%u outside 1..%u", k, h->kmax);
+    const uint64_t matrix_bytes = h->nnz * 8ull + (h->rows + 1) * (h->nnz > 0xFFFFFFFFull ? 8ull : 4ull);
+    if (use_batched(h)) {
+        launch_batched(h, k, s, profile);
+        h->last_run_batched = true;
+        h->stats.launches_per_run = 5;
+        // matrix bytes once + Q*C*4 + Q*k*8 (the kernel re-reads the matrix once per 32 queries;
+        // that is not counted)
+        h->stats.algorithmic_bytes = matrix_bytes + (uint64_t)h->batch * ((uint64_t)h->cols * 4ull + k * 8ull);
+    } else {
+        for (uint32_t q = 0; q < h->batch; q++) launch_single_query(h, q, k, s, profile && q == 0);
+        h->last_run_batched = false;
+        h->stats.launches_per_run = 3 * h->batch;
+        h->stats.algorithmic_bytes = matrix_bytes + (uint64_t)h->cols * 4ull + k * 8ull;
     }
     TKS_CUDA(h, cudaGetLastError());
     h->last_k = k;
-    h->stats.launches_per_run = 3 * h->batch;
-    h->stats.algorithmic_bytes =
-        h->nnz * 8ull + (h->rows + 1) * (h->nnz > 0xFFFFFFFFull ? 8ull : 4ull) + (uint64_t)h->cols * 4ull + k * 8ull;
+    return TKS_OK;
+}
+
+// Batched mode: queries whose candidate pool overflowed are re-run one by one through the single-query
+// kernels (their per-warp buffers compact instead of overflowing).  Called with the results in the pinned
+// host buffers; returns with them complete.
+int resolve_batched_overflow(Handle *h, cudaStream_t s) {
+    bool any = false;
+    for (uint32_t q = 0; q < h->batch; q++) {
+        if (h->h_res_count[q] != kPoolOverflow) continue;
+        launch_single_query(h, q, h->last_k, s, false);
+        any = true;
+    }
+    if (!any) return TKS_OK;
+    TKS_CUDA(h, cudaGetLastError());
+    const size_t n = (size_t)h->batch * h->kmax;
+    TKS_CUDA(h, cudaMemcpyAsync(h->h_res_idx, h->d_res_idx, n * 4, cudaMemcpyDeviceToHost, s));
+    TKS_CUDA(h, cudaMemcpyAsync(h->h_res_val, h->d_res_val, n * 4, cudaMemcpyDeviceToHost, s));
+    TKS_CUDA(h, cudaMemcpyAsync(h->h_res_count, h->d_res_count, h->batch * 4, cudaMemcpyDeviceToHost, s));
+    TKS_CUDA(h, cudaStreamSynchronize(s));
+    h->stats.batched_fallbacks += 1;
     return TKS_OK;
 }
 
@@ -317,6 +403,15 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
                                           (int)(kSelectDynSmem))) != cudaSuccess)
                 return bail("select smem attr", e);
         }
+        if (cfg->max_batch > 1 && batched_smem_bytes((uint32_t)cfg->max_cols) <= (size_t)prop.sharedMemPerBlockOptin) {
+            const int bs = (int)batched_smem_bytes((uint32_t)cfg->max_cols);
+            if ((e = cudaFuncSetAttribute(csr_batched_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs)) != cudaSuccess ||
+                (e = cudaFuncSetAttribute(csr_batched_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs)) != cudaSuccess ||
+                (e = cudaFuncSetAttribute(csr_batched_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs)) != cudaSuccess ||
+                (e = cudaFuncSetAttribute(csr_batched_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs)) != cudaSuccess)
+                return bail("batched smem attr", e);
+            h->batched_ok = true;
+        }
         int rc = alloc_query_side(h);
         if (rc != TKS_OK) { g_create_error = h->err; tks_destroy(h); return rc; }
     }
@@ -331,6 +426,7 @@ void tks_destroy(tks_handle *h) {
     bscsr_destroy(h);
     cudaFree(h->d_x); cudaFree(h->d_state); cudaFree(h->d_pool); cudaFree(h->d_sample_keys);
     cudaFree(h->d_res_keys); cudaFree(h->d_res_idx); cudaFree(h->d_res_val); cudaFree(h->d_res_count);
+    cudaFree(h->d_xT); cudaFree(h->d_bpool); cudaFree(h->d_pass_counter); cudaFree(h->d_bsample_keys);
     cudaFreeHost(h->h_res_idx); cudaFreeHost(h->h_res_val); cudaFreeHost(h->h_res_count); cudaFreeHost(h->h_x);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -476,7 +572,11 @@ int tks_run_async(tks_handle *h, uint32_t k, void *cuda_stream) {
     TKS_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) { h->last_k = k; return bscsr_launch(h, s); }
-    return launch_float(h, k, s);
+    int rc = launch_float(h, k, s);
+    if (rc) return rc;
+    h->have_result = false;
+    h->overflow_check_pending = h->last_run_batched;
+    return TKS_OK;
 }
 
 int tks_run(tks_handle *h, uint32_t k, float *kernel_ms, float *total_ms) {
@@ -498,6 +598,11 @@ int tks_run(tks_handle *h, uint32_t k, float *kernel_ms, float *total_ms) {
         TKS_CUDA(h, cudaMemcpyAsync(h->h_res_val, h->d_res_val, n * 4, cudaMemcpyDeviceToHost, h->stream));
         TKS_CUDA(h, cudaMemcpyAsync(h->h_res_count, h->d_res_count, h->batch * 4, cudaMemcpyDeviceToHost, h->stream));
         TKS_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (h->last_run_batched) {
+            rc = resolve_batched_overflow(h, h->stream);
+            if (rc) return rc;
+        }
+        h->overflow_check_pending = false;
     }
     float ms = 0.f;
     TKS_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -530,6 +635,11 @@ int tks_read_result(tks_handle *h, uint32_t query, uint32_t *idx_out, void *val_
         TKS_CUDA(h, cudaMemcpy(h->h_res_idx, h->d_res_idx, n * 4, cudaMemcpyDeviceToHost));
         TKS_CUDA(h, cudaMemcpy(h->h_res_val, h->d_res_val, n * 4, cudaMemcpyDeviceToHost));
         TKS_CUDA(h, cudaMemcpy(h->h_res_count, h->d_res_count, h->batch * 4, cudaMemcpyDeviceToHost));
+        if (h->overflow_check_pending) {
+            int rc = resolve_batched_overflow(h, h->stream);
+            if (rc) return rc;
+            h->overflow_check_pending = false;
+        }
         h->have_result = true;
     }
     if (query >= h->batch) return h->fail(TKS_EINVAL, "query index out of range");
@@ -550,6 +660,19 @@ int tks_result_keys_device(tks_handle *h, uint32_t query, const uint64_t **d_key
     if (!h || !d_keys) return TKS_EINVAL;
     if (h->cfg.mode != TKS_MODE_FLOAT_CSR) return h->fail(TKS_ESTATE, "float mode only");
     if (query >= (uint32_t)h->cfg.max_batch) return h->fail(TKS_EINVAL, "query index out of range");
+    if (h->overflow_check_pending) {
+        // an async batched run: make sure no query's candidate pool overflowed before its keys are used
+        TKS_CUDA(h, cudaSetDevice(h->device));
+        TKS_CUDA(h, cudaDeviceSynchronize());
+        TKS_CUDA(h, cudaMemcpy(h->h_res_count, h->d_res_count, h->batch * 4, cudaMemcpyDeviceToHost));
+        bool any = false;
+        for (uint32_t q = 0; q < h->batch; q++) any |= h->h_res_count[q] == kPoolOverflow;
+        if (any) {
+            int rc = resolve_batched_overflow(h, h->stream);
+            if (rc) return rc;
+        }
+        h->overflow_check_pending = false;
+    }
     *d_keys = h->d_res_keys + (size_t)query * h->kmax;
     if (count) *count = h->last_k;
     return TKS_OK;
@@ -564,13 +687,32 @@ int tks_merge_keys_device(tks_handle *h, uint32_t query, const uint64_t *d_keys,
     TKS_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     select_topk_kernel<<<1, kSelectThreads, kSelectDynSmem, s>>>(
-        d_keys, nullptr, n_keys, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX, h->d_res_keys + (size_t)query * h->kmax,
-        h->d_res_idx + (size_t)query * h->kmax, h->d_res_val + (size_t)query * h->kmax, h->d_res_count + query,
-        nullptr);
+        d_keys, 0u, nullptr, n_keys, 0u, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX,
+        h->d_res_keys + (size_t)query * h->kmax, h->d_res_idx + (size_t)query * h->kmax,
+        h->d_res_val + (size_t)query * h->kmax, 0u, h->d_res_count + query, nullptr);
     TKS_CUDA(h, cudaGetLastError());
     h->last_k = k;
     if (h->batch < query + 1) h->batch = query + 1;
     h->have_result = false;   // tks_read_result will fetch
+    return TKS_OK;
+}
+
+int tks_merge_keys_batched_device(tks_handle *h, const uint64_t *d_keys, uint32_t keys_per_query, uint32_t batch,
+                                  uint32_t k, void *cuda_stream) {
+    if (!h || !d_keys) return TKS_EINVAL;
+    if (h->cfg.mode != TKS_MODE_FLOAT_CSR) return h->fail(TKS_ESTATE, "float mode only");
+    if (batch < 1 || batch > (uint32_t)h->cfg.max_batch) return h->fail(TKS_EINVAL, "batch outside 1..max_batch");
+    if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k out of range");
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    select_topk_kernel<<<batch, kSelectThreads, kSelectDynSmem, s>>>(
+        d_keys, keys_per_query, nullptr, keys_per_query, 0u, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX,
+        h->d_res_keys, h->d_res_idx, h->d_res_val, h->kmax, h->d_res_count, nullptr);
+    TKS_CUDA(h, cudaGetLastError());
+    h->last_k = k;
+    if (h->batch < batch) h->batch = batch;
+    h->have_result = false;
+    h->overflow_check_pending = false;
     return TKS_OK;
 }
 

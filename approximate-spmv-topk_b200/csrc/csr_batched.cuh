@@ -1,0 +1,272 @@
+// csr_batched.cuh -- batched multi-query fused fp32 CSR Top-K SpMV for sm_100a (BASELINE config 5).
+//
+// One pass over the non-zeros serves 32 queries: the matrix is read from HBM once per 32 queries
+// instead of once per query.  The reference has no batched mode (its hosts loop `reset(vec)` +
+// `operator()` per query, src/gpu/host_spmv_topk_csr_gpu.cu:399-423); this is the north-star's
+// "batched multi-query mode amortises one matrix read across queries".
+//
+// Work decomposition ("lanes are queries"):
+//   * the queries of a pass live in shared memory as a table  xT[col][32]  (128 bytes per column, so one
+//     non-zero needs ONE conflict-free 128-byte row of it: 32 products per shared-memory wavefront,
+//     which is the floor for this problem -- SURVEY 7-H8: the bound is LDS bandwidth, not HBM);
+//   * a warp is four OCTETS of 8 lanes; every lane owns 4 queries (one LDS.128 of the table row) and every
+//     octet walks its own chunk of the CSR stream non-zero by non-zero, so a row's score for a query is
+//     accumulated sequentially in a single register, in non-zero order, with separate fp32 multiply and add --
+//     exactly the arithmetic of the reference gold (gold_algorithms.hpp:203-213), hence bit-identical
+//     scores (template FMA=true trades that for fused multiply-adds);
+//   * the (value, column) pairs of an octet's stream are fetched with the same coalesced 256-bit loads as
+//     the single-query kernel, staged in a 512-byte per-octet shared-memory window and re-read as
+//     octet-wide broadcasts (one LDS.128 delivers 4 values or 4 columns to the 8 lanes);
+//   * a finished row is compared with the query's threshold tau (k-th largest of a sample, as in
+//     csr_topk.cuh) and the rare survivors are appended to the query's pool in HBM.
+// Kernels per run:  batched_transpose_kernel -> csr_batched_kernel<SAMPLE> -> batched_tau_kernel
+//                -> csr_batched_kernel<MAIN> -> select_topk_kernel (one CTA per query).
+// If a query's pool overflows (adversarial score order), its count is reported as kPoolOverflow and the
+// host re-runs that query through the single-query kernels, which cannot overflow (api.cu).
+#pragma once
+
+#include "csr_topk.cuh"
+
+namespace tks {
+
+constexpr uint32_t kBqPerPass = 32;        // queries per pass: 8 lanes x 4 queries
+constexpr uint32_t kBThreads = 768;        // 24 warps, one CTA per SM (the table takes most of shared memory)
+constexpr uint32_t kBStage = 64;           // non-zeros staged per octet per batch (8 lanes x 8)
+constexpr uint32_t kBSampleBatches = 8;    // the sample reduces the first 512 non-zeros of a chunk
+constexpr uint32_t kBStageBytes = kBStage * 8u;                       // 64 values + 64 column words
+
+struct BatchedArgs {
+    const float *xT;          // [npass][cols+1][32]; row `cols` is all zeros (masked elements point there)
+    RunState *st;             // [batch]: tau_key, pool_count
+    uint64_t *pool;           // [batch][pool_cap]
+    uint32_t pool_cap;
+    uint32_t batch, npass;
+    uint32_t *pass_counter;   // [npass] dynamic chunk scheduler of the main kernel (reset by the select kernel)
+    uint32_t *sample_keys;    // [batch][n_sample]
+    uint32_t n_sample, stride;
+    int tie_higher;
+};
+
+__host__ __device__ inline size_t batched_table_bytes(uint32_t cols) { return ((size_t)cols + 1u) * kBqPerPass * 4u; }
+__host__ __device__ inline size_t batched_smem_bytes(uint32_t cols) {
+    return batched_table_bytes(cols) + (size_t)(kBThreads / 8u) * kBStageBytes;
+}
+
+// queries [batch][cols] row-major -> pass tables [npass][cols+1][32], zero padded
+__global__ void batched_transpose_kernel(const float *__restrict__ x, uint32_t batch, uint32_t cols, uint32_t npass,
+                                         float *__restrict__ xT) {
+    const uint32_t n = npass * (cols + 1u) * kBqPerPass;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t q = i % kBqPerPass, r = i / kBqPerPass;
+        const uint32_t col = r % (cols + 1u), pass = r / (cols + 1u);
+        const uint32_t gq = pass * kBqPerPass + q;
+        xT[i] = (col < cols && gq < batch) ? x[(size_t)gq * cols + col] : 0.0f;
+    }
+}
+
+// k-th largest of every query's sample maxima -> tau_key (one CTA per query)
+__global__ void __launch_bounds__(256) batched_tau_kernel(BatchedArgs a, uint32_t k) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t *skeys = reinterpret_cast<uint32_t *>(smem_raw);
+    __shared__ uint32_t s_bin, s_above[2];
+    __shared__ uint32_t hist[(256 / kWarp) * 256];
+    const uint32_t q = blockIdx.x;
+    for (uint32_t i = threadIdx.x; i < a.n_sample; i += blockDim.x) skeys[i] = a.sample_keys[(size_t)q * a.n_sample + i];
+    __syncthreads();
+    const uint32_t thr = block_radix_select<uint32_t, false>([&](uint32_t i) { return skeys[i]; }, a.n_sample, k, hist,
+                                                             &s_bin, s_above);
+    if (threadIdx.x == 0) a.st[q].tau_key = thr;
+}
+
+template <bool SAMPLE, bool FMA>
+struct BatchedLane {
+    float acc[4];
+    float tau[4];      // MAIN: thresholds of this lane's 4 queries (+inf for padding queries)
+    float best[4];     // SAMPLE: best completed row so far
+    uint32_t ord;      // ordinal of the row in progress
+    bool have_row;
+
+    __device__ __forceinline__ void finish_row(const CsrDevice &m, const BatchedArgs &a, uint32_t qbase) {
+        if (have_row) {
+            if (SAMPLE) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) best[q] = fmaxf(best[q], acc[q]);
+            } else {
+                const bool any = (acc[0] >= tau[0]) | (acc[1] >= tau[1]) | (acc[2] >= tau[2]) | (acc[3] >= tau[3]);
+                if (any) {
+                    const uint32_t row = (m.row_map ? m.row_map[ord] : ord) + m.row_offset;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (acc[q] >= tau[q]) {
+                            const uint32_t gq = qbase + q;
+                            const uint32_t pos = atomicAdd(&a.st[gq].pool_count, 1u);
+                            if (pos < a.pool_cap)
+                                a.pool[(size_t)gq * a.pool_cap + pos] = make_key(f32_to_ordered(acc[q]), row, a.tie_higher);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void step(uint32_t c, float v, const uint8_t *tab_lane, const CsrDevice &m,
+                                         const BatchedArgs &a, uint32_t qbase) {
+        if ((int32_t)c < 0) {   // this non-zero starts a row: the row in progress is complete
+            finish_row(m, a, qbase);
+            acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
+            ord++;
+            have_row = true;
+        }
+        const float4 x = *reinterpret_cast<const float4 *>(tab_lane + (c & 0x7FFFFFFFu));
+        if (FMA) {
+            // packed fp32x2 fused multiply-add (FFMA2 on sm_100): two instructions for the four queries
+            asm("{ .reg .b64 a, b, d;\n\t"
+                "mov.b64 a, {%2, %2}; mov.b64 b, {%3, %4}; mov.b64 d, {%0, %1};\n\t"
+                "fma.rn.f32x2 d, a, b, d; mov.b64 {%0, %1}, d; }"
+                : "+f"(acc[0]), "+f"(acc[1]) : "f"(v), "f"(x.x), "f"(x.y));
+            asm("{ .reg .b64 a, b, d;\n\t"
+                "mov.b64 a, {%2, %2}; mov.b64 b, {%3, %4}; mov.b64 d, {%0, %1};\n\t"
+                "fma.rn.f32x2 d, a, b, d; mov.b64 {%0, %1}, d; }"
+                : "+f"(acc[2]), "+f"(acc[3]) : "f"(v), "f"(x.z), "f"(x.w));
+        } else {
+            acc[0] = __fadd_rn(acc[0], __fmul_rn(v, x.x)); acc[1] = __fadd_rn(acc[1], __fmul_rn(v, x.y));
+            acc[2] = __fadd_rn(acc[2], __fmul_rn(v, x.z)); acc[3] = __fadd_rn(acc[3], __fmul_rn(v, x.w));
+        }
+    }
+};
+
+// One octet streams chunk c (or nothing when c >= n_chunks); all four octets of the warp run the same number
+// of batches (the longest of the four), the shorter ones on neutral elements.
+template <bool SAMPLE, bool FMA>
+__device__ __forceinline__ void batched_stream(const CsrDevice &m, const BatchedArgs &a, const uint8_t *tab_lane,
+                                               uint8_t *stage, uint32_t c, BatchedLane<SAMPLE, FMA> &L, uint32_t qbase) {
+    const unsigned l8 = lane_id() & 7u;
+    uint64_t s = 0, e = 0, a0 = 0;
+    uint32_t nb = 0;
+    if (c < m.n_chunks) {
+        s = m.chunk_start[c];
+        e = m.chunk_start[c + 1];
+        a0 = s & ~7ull;
+        nb = (e > s) ? (uint32_t)((e - a0 + kBStage - 1) / kBStage) : 0u;
+        L.ord = m.chunk_ord[c] - 1u;
+    }
+    bool truncated = false;
+    if (SAMPLE && nb > kBSampleBatches) { nb = kBSampleBatches; truncated = true; }
+    const uint32_t nb_w = __reduce_max_sync(kFull, nb);
+    L.acc[0] = L.acc[1] = L.acc[2] = L.acc[3] = 0.0f;
+    L.have_row = false;
+    const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val + a0) + l8 * 32u;
+    const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.colf + a0) + l8 * 32u;
+    const uint32_t zero_off = m.cols * (kBqPerPass * 4u);   // the all-zero table row
+    float *sval = reinterpret_cast<float *>(stage);
+    uint32_t *scol = reinterpret_cast<uint32_t *>(stage + kBStage * 4u);
+
+    U32x8 nv, nc;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { nv.w[j] = 0; nc.w[j] = 0; }
+    if (nb > 0) { nv = ldg_stream_256(vp); nc = ldg_stream_256(cp); }
+    for (uint32_t b = 0; b < nb_w; b++) {
+        // column words become byte offsets of the table row (col * 128, row-start flag kept in bit 31)
+        uint32_t cw[8], vw[8];
+        if (b == 0 || b + 1 >= nb) {
+            const int64_t ebase = (int64_t)(a0 + (uint64_t)b * kBStage + l8 * 8u);
+            const int64_t l64 = (int64_t)s - ebase, h64 = (int64_t)e - ebase;
+            uint32_t lo = l64 < 0 ? 0u : (l64 > 8 ? 8u : (uint32_t)l64);
+            uint32_t hi = h64 < 0 ? 0u : (h64 > 8 ? 8u : (uint32_t)h64);
+            if (b >= nb) { lo = 0; hi = 0; }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool in = ((uint32_t)j >= lo) && ((uint32_t)j < hi);
+                cw[j] = in ? (((nc.w[j] & kColOffMask) << 5) | (nc.w[j] & kRowStartBit)) : zero_off;
+                vw[j] = in ? nv.w[j] : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                cw[j] = ((nc.w[j] & kColOffMask) << 5) | (nc.w[j] & kRowStartBit);
+                vw[j] = nv.w[j];
+            }
+        }
+        __syncwarp();   // the previous batch has been consumed
+        reinterpret_cast<uint4 *>(sval)[l8 * 2] = make_uint4(vw[0], vw[1], vw[2], vw[3]);
+        reinterpret_cast<uint4 *>(sval)[l8 * 2 + 1] = make_uint4(vw[4], vw[5], vw[6], vw[7]);
+        reinterpret_cast<uint4 *>(scol)[l8 * 2] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+        reinterpret_cast<uint4 *>(scol)[l8 * 2 + 1] = make_uint4(cw[4], cw[5], cw[6], cw[7]);
+        __syncwarp();
+        if (b + 1 < nb) {   // next batch in flight while this one is consumed
+            nv = ldg_stream_256(vp + (size_t)(b + 1) * (kBStage * 4u));
+            nc = ldg_stream_256(cp + (size_t)(b + 1) * (kBStage * 4u));
+        }
+#pragma unroll 4
+        for (uint32_t i = 0; i < kBStage / 4; i++) {
+            const float4 v4 = reinterpret_cast<const float4 *>(sval)[i];   // octet-wide broadcast
+            const uint4 c4 = reinterpret_cast<const uint4 *>(scol)[i];
+            L.step(c4.x, v4.x, tab_lane, m, a, qbase);
+            L.step(c4.y, v4.y, tab_lane, m, a, qbase);
+            L.step(c4.z, v4.z, tab_lane, m, a, qbase);
+            L.step(c4.w, v4.w, tab_lane, m, a, qbase);
+        }
+    }
+    // chunks end on row boundaries: the row in progress is complete unless the sample cut the chunk short
+    if (!truncated) L.finish_row(m, a, qbase);
+    L.have_row = false;
+}
+
+// Dynamic shared memory: batched_smem_bytes(cols).
+template <bool SAMPLE, bool FMA>
+__global__ void __launch_bounds__(kBThreads, 1) csr_batched_kernel(CsrDevice m, BatchedArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const size_t tab_bytes = batched_table_bytes(m.cols);
+    const unsigned lane = lane_id(), l8 = lane & 7u, oct = lane >> 3;
+    const uint32_t warp = threadIdx.x / kWarp, nwarps = blockDim.x / kWarp;
+    uint8_t *stage = smem_raw + tab_bytes + (size_t)(warp * 4u + oct) * kBStageBytes;
+    const uint8_t *tab_lane = smem_raw + l8 * 16u;
+    BatchedLane<SAMPLE, FMA> L;
+
+    for (uint32_t pass = 0; pass < a.npass; pass++) {
+        __syncthreads();   // every warp is done with the previous pass's table
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(a.xT + (size_t)pass * (m.cols + 1u) * kBqPerPass);
+            float4 *dst = reinterpret_cast<float4 *>(smem_raw);
+            const uint32_t n4 = (m.cols + 1u) * (kBqPerPass / 4u);
+            for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
+        }
+        __syncthreads();
+        const uint32_t qbase = pass * kBqPerPass + l8 * 4u;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t gq = qbase + q;
+            L.tau[q] = (!SAMPLE && gq < a.batch) ? tau_from_key(ld_relaxed_u32(&a.st[gq].tau_key))
+                                                 : __int_as_float(0x7f800000);
+            L.best[q] = neg_inf();
+        }
+        if (SAMPLE) {
+            const uint32_t n_groups = (a.n_sample + 3u) / 4u;   // one warp reduces 4 samples (one per octet)
+            for (uint32_t g = blockIdx.x * nwarps + warp; g < n_groups; g += gridDim.x * nwarps) {
+                const uint32_t sidx = g * 4u + oct;
+                const uint32_t c = (sidx < a.n_sample) ? sidx * a.stride : 0xFFFFFFFFu;
+#pragma unroll
+                for (int q = 0; q < 4; q++) L.best[q] = neg_inf();
+                batched_stream<SAMPLE, FMA>(m, a, tab_lane, stage, c, L, qbase);
+                if (sidx < a.n_sample) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t gq = qbase + q;
+                        if (gq < a.batch)
+                            a.sample_keys[(size_t)gq * a.n_sample + sidx] =
+                                (L.best[q] == neg_inf()) ? 0u : f32_to_ordered(L.best[q]);
+                    }
+                }
+            }
+        } else {
+            for (;;) {
+                uint32_t c0 = 0;
+                if (lane == 0) c0 = atomicAdd(&a.pass_counter[pass], 4u);
+                c0 = __shfl_sync(kFull, c0, 0);
+                if (c0 >= m.n_chunks) break;
+                batched_stream<SAMPLE, FMA>(m, a, tab_lane, stage, c0 + oct, L, qbase);
+            }
+        }
+    }
+}
+
+}  // namespace tks

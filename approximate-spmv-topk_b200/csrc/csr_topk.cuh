@@ -444,17 +444,42 @@ constexpr uint32_t kSelectSortCap = 2048;     // keys sorted directly (16 KB sta
 constexpr uint32_t kSelectSmemKeys = 16384;   // pool keys staged in dynamic shared memory (128 KB)
 constexpr uint32_t kSelectDynSmem = (kSelectThreads / kWarp) * 1024u + kSelectSmemKeys * 8u;
 
+constexpr uint32_t kPoolOverflow = 0xFFFFFFFFu;   // *out_count when a capped pool overflowed (batched mode)
+
+// Grid: one CTA per query.  CTA q reads pool + q * pool_stride; its key count is st[q].pool_count (st != nullptr)
+// or pool_count_imm; results go to out_* + q * out_stride and out_count[q].  pool_cap != 0: a count above it
+// means keys were dropped -> out_count = kPoolOverflow and nothing else is written.
 __global__ void __launch_bounds__(kSelectThreads)
-select_topk_kernel(const uint64_t *__restrict__ pool, const uint32_t *pool_count_ptr, uint32_t pool_count_imm,
-                   uint32_t k, int tie_higher, uint64_t *out_keys, uint32_t *out_idx, float *out_val,
-                   uint32_t *out_count, RunState *st_reset) {
+select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunState *st, uint32_t pool_count_imm,
+                   uint32_t pool_cap, uint32_t k, int tie_higher, uint64_t *out_keys, uint32_t *out_idx,
+                   float *out_val, uint32_t out_stride, uint32_t *out_count, uint32_t *pass_counter) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);                                  // 32 KB
     uint64_t *staged = reinterpret_cast<uint64_t *>(smem_raw + (kSelectThreads / kWarp) * 1024u);
     __shared__ uint64_t keys[kSelectSortCap];
     __shared__ uint32_t s_bin, s_above[2], s_cnt;
     const uint32_t tid = threadIdx.x;
-    const uint32_t n = pool_count_ptr ? *pool_count_ptr : pool_count_imm;
+    const uint32_t q = blockIdx.x;
+    RunState *st_reset = st ? st + q : nullptr;
+    pool += (size_t)q * pool_stride;
+    out_keys += (size_t)q * out_stride;
+    out_idx += (size_t)q * out_stride;
+    out_val += (size_t)q * out_stride;
+    out_count += q;
+    const uint32_t n = st_reset ? st_reset->pool_count : pool_count_imm;
+    if (pool_cap != 0 && n > pool_cap) {
+        __syncthreads();   // everyone has read pool_count
+        if (tid == 0) {
+            *out_count = kPoolOverflow;
+            st_reset->result_count = n;
+            st_reset->chunk_counter = 0;
+            st_reset->pool_count = 0;
+            st_reset->tau_key = 0;
+            st_reset->sample_ticket = 0;
+            if (pass_counter && (q % 32u) == 0) pass_counter[q / 32u] = 0;
+        }
+        return;
+    }
 
     uint32_t m = 0;   // number of keys in keys[]
     if (n <= kSelectSortCap) {
@@ -501,6 +526,7 @@ select_topk_kernel(const uint64_t *__restrict__ pool, const uint32_t *pool_count
             st_reset->tau_key = 0;
             st_reset->sample_ticket = 0;
         }
+        if (pass_counter && (q % 32u) == 0) pass_counter[q / 32u] = 0;
     }
 }
 

@@ -58,6 +58,17 @@ struct Handle {
     uint32_t last_k = 0;
     bool have_result = false;
 
+    // batched mode (csr_batched.cuh), allocated when max_batch > 1
+    float *d_xT = nullptr;              // [npass][max_cols+1][32] transposed query tables
+    uint64_t *d_bpool = nullptr;        // [max_batch][bpool_cap] candidate keys
+    uint32_t bpool_cap = 0;
+    uint32_t *d_pass_counter = nullptr; // [ceil(max_batch/32)]
+    uint32_t *d_bsample_keys = nullptr; // [max_batch][b_sample_cap]
+    uint32_t b_sample_cap = 0;
+    bool batched_ok = false;            // the kernels' shared memory fits for max_cols
+    bool last_run_batched = false;
+    bool overflow_check_pending = false; // an async batched run has not been checked for pool overflow yet
+
     // launch geometry of the main kernel, per CAP variant
     int main_grid[4] = {0, 0, 0, 0};
 

@@ -71,11 +71,12 @@ class SpMV(_Base):
 
     def __init__(self, ptr=None, idx=None, val=None, num_rows=0, num_cols=0, num_nnz=None, vec=None, k=100,
                  device=0, tie_higher=False, max_batch=1, max_cols=None, chunk_nnz=0, row_offset=0,
-                 profile_kernels=False):
+                 profile_kernels=False, batch_mode=0, batch_pool_cap=0, batch_fma=False):
         cfg = capi.default_config(mode=capi.MODE_FLOAT_CSR, device=device, max_batch=max_batch,
                                   tie_break=capi.TIE_HIGHER_INDEX if tie_higher else capi.TIE_LOWER_INDEX,
                                   max_cols=max(1024, int(max_cols or num_cols or 1024)), chunk_nnz=chunk_nnz,
-                                  profile_kernels=int(profile_kernels))
+                                  profile_kernels=int(profile_kernels), batch_mode=int(batch_mode),
+                                  batch_pool_cap=int(batch_pool_cap), batch_fma=int(batch_fma))
         self._create(cfg)
         self.k = k
         self.num_rows, self.num_cols = int(num_rows), int(num_cols)
@@ -138,6 +139,12 @@ class SpMV(_Base):
         k = self.k if k is None else k
         check(capi.lib().tks_merge_keys_device(self.handle, query, C.c_void_p(dptr), n_keys, k, C.c_void_p(stream)),
               self.handle)
+
+
+    def merge_keys_batched_device(self, dptr, keys_per_query, batch, k=None, stream=0):
+        k = self.k if k is None else k
+        check(capi.lib().tks_merge_keys_batched_device(self.handle, C.c_void_p(dptr), keys_per_query, batch, k,
+                                                       C.c_void_p(stream)), self.handle)
 
 
 class SpMVFixed(_Base):

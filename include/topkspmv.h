@@ -59,7 +59,12 @@ typedef struct tks_config {
     int32_t max_batch;             /* max queries per run (float mode), >= 1                  */
     int32_t chunk_nnz;             /* float mode work-unit size in nnz (0 = default)          */
     int32_t profile_kernels;       /* 1: tks_run also times the dominant kernel alone (stats)  */
-    int32_t reserved[5];
+    int32_t batch_mode;            /* float mode, batch > 1: 0 = one matrix pass per 32 queries     */
+                                   /* (csr_batched.cuh; needs cols <= ~1500), 1 = one pass per query */
+    int32_t batch_pool_cap;        /* candidate keys per query in batched mode (0 = 32768)     */
+    int32_t batch_fma;             /* batched mode: 1 = fused multiply-add (scores no longer   */
+                                   /* bit-identical to the sequential fp32 gold)               */
+    int32_t reserved[2];
 } tks_config;
 
 typedef struct tks_handle tks_handle;
@@ -75,7 +80,8 @@ typedef struct tks_stats {
     uint32_t last_candidates;     /* candidates that survived the threshold filter       */
     uint32_t launches_per_run;    /* kernels launched by one tks_run                     */
     float last_main_kernel_ms;    /* dominant kernel alone (only with cfg.profile_kernels) */
-    uint32_t reserved[7];
+    uint32_t batched_fallbacks;   /* batched queries re-run alone because their pool overflowed */
+    uint32_t reserved[6];
 } tks_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -146,6 +152,11 @@ int tks_result_keys_device(tks_handle *h, uint32_t query, const uint64_t **d_key
 /* Merge n_keys gathered keys (device) into this handle's result for query q.   */
 int tks_merge_keys_device(tks_handle *h, uint32_t query, const uint64_t *d_keys, uint32_t n_keys,
                           uint32_t k, void *cuda_stream);
+
+/* Batched form: d_keys is [batch][keys_per_query] (the all-gathered candidates regrouped by query);
+ * one launch merges every query.                                               */
+int tks_merge_keys_batched_device(tks_handle *h, const uint64_t *d_keys, uint32_t keys_per_query,
+                                  uint32_t batch, uint32_t k, void *cuda_stream);
 
 int tks_get_stats(tks_handle *h, tks_stats *out);
 
