@@ -41,6 +41,8 @@ WORKLOADS = {
                  name="cfg3: cfg2 matrix in 20-bit BS-CSR packets, 32 partitions x local K=8 (FPGA semantics)"),
     "cfg4": dict(rows=200_000_000, cols=1024, deg=40, dist="uniform", mode="float",
                  name="cfg4: synthetic 200M x 1024, uniform ~40 nnz/row, fp32, k=100, row-sharded + K-candidate allgather"),
+    "cfg5": dict(rows=50_000_000, cols=1024, deg=20, dist="gamma", mode="batched", batch=64,
+                 name="cfg5: batched 64 queries x 50M x 1024 gamma ~20 nnz/row (one matrix read per 32 queries), fp32, k=100"),
 }
 K = 100
 SEED = 0
@@ -226,6 +228,8 @@ def ours(args):
 
     if wl["mode"] == "fixed":
         return ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src)
+    if wl["mode"] == "batched":
+        return ours_batched(args, tks, wl, rows_total, peak_gbs, peak_src, world, rank, local, stream)
 
     # profile_kernels: tks_run (the e2e path) also brackets the dominant kernel with two events; the
     # resident path (tks_run_async) never does
@@ -385,6 +389,156 @@ def cpu_baseline_leg(tks, eng, queries, idx_gpu, val_gpu, args):
             "ms_per_query_on_sample": sec * 1e3}
 
 
+def ours_batched(args, tks, wl, rows_total, peak_gbs, peak_src, world, rank, local, stream):
+    """cfg5: every step scores one batch of 64 queries against the resident matrix (rows sharded over the
+    ranks); `value` counts query x non-zero products per second (SURVEY 8d "amortised figure Q*nnz/s")."""
+    import torch
+    import torch.distributed as dist
+    cols, B = wl["cols"], wl["batch"]
+    shards = tks.sharding.plan_row_shards_even(rows_total, world)
+    r0, r1 = shards[rank]
+    eng = tks.SpMV(num_cols=cols, k=K, device=local, max_batch=B, profile_kernels=True, batch_fma=bool(args.batch_fma))
+    t0 = time.perf_counter()
+    eng.generate_synthetic(r1 - r0, cols, wl["deg"], wl["dist"], seed=SEED, row_offset=r0)
+    gen_s = time.perf_counter() - t0
+    nnz_local = int(eng.stats().nnz)
+    nnz_t = torch.tensor([nnz_local], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(nnz_t)
+    nnz_total = int(nnz_t.item())
+    nsteps = args.warmup + args.steps
+    nsets = min(nsteps, 4)                       # distinct query batches, cycled
+    hq = [make_queries(cols, B, seed0=1 + 1000 * i) for i in range(nsets)]
+    dq = [torch.from_numpy(q).cuda() for q in hq]
+    KMAX = 1024
+    if world > 1:
+        gathered = torch.empty((world, B, K), dtype=torch.int64, device="cuda")
+
+    def exchange():
+        kp, _ = eng.result_keys_device(0)
+        mine = torch.as_tensor(_DevArray2(kp, (B, KMAX), "<i8"), device="cuda")[:, :K].contiguous()
+        dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))
+        regrouped = gathered.permute(1, 0, 2).contiguous()          # [B][world][K]
+        eng.merge_keys_batched_device(regrouped.data_ptr(), world * K, B, K, stream)
+        return regrouped
+
+    def step(i):
+        eng.reset_device(dq[i % nsets].data_ptr(), B, stream)
+        eng.run_async(K, stream)
+        if world > 1:
+            return exchange()
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    keep = None
+    for i in range(args.steps):
+        keep = step(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    last_set = (nsteps - 1) % nsets
+    res_last = [eng.read_result(q) for q in (0, B - 1)]
+
+    # e2e: host queries in, host results out, every step
+    e2e_ms, main_ms = [], []
+    for i in range(nsteps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        eng.reset(hq[i % nsets])
+        if world == 1:
+            eng.run_timed(K)
+            main_ms.append(eng.stats().last_main_kernel_ms)
+        else:
+            eng.run_async(K, stream)
+            keep = exchange()
+            torch.cuda.synchronize()
+        out = [eng.read_result(q) for q in range(B)]
+        dt = (time.perf_counter() - t0) * 1e3
+        if i >= args.warmup:
+            e2e_ms.append(dt)
+    e2e_t = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms_step = float(e2e_t.item())
+    for (v0, i0, _), q in zip(res_last, (0, B - 1)):
+        assert np.array_equal(out[q][1], i0) and np.array_equal(out[q][0], v0), "e2e and resident results differ"
+    if world > 1:
+        # dominant kernel alone: one more profiled single-rank run (tks_run brackets it with events)
+        eng.reset(hq[0])
+        for _ in range(3):
+            eng.run_timed(K)
+            main_ms.append(eng.stats().last_main_kernel_ms)
+    sel = main_ms[args.warmup:] if world == 1 else main_ms
+    main = sum(sel) / len(sel)
+    st = eng.stats()
+    alg = int(st.algorithmic_bytes)
+    achieved = alg / (main * 1e-3) / 1e9
+    sm_clk = (clocks or {}).get("sm_mhz") or 1900.0
+    lds_peak_gbs = 148 * 128 * sm_clk * 1e6 / 1e9            # 128 B/clk/SM shared-memory bandwidth
+    lds_bytes = nnz_local * B * 4                             # one table word per (query, non-zero)
+    roof = {"bound": "hbm", "kernel": "csr_batched_kernel<MAIN>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+            "frac": achieved / peak_gbs, "traffic": load_traffic("cfg5"), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg, "main_kernel_ms": main,
+            "note": "SURVEY 7-H8: the binding resource is shared-memory bandwidth (one 4-byte table word per query x "
+                    "non-zero), not HBM; both fractions are reported",
+            "lds": {"achieved": lds_bytes / (main * 1e-3) / 1e9, "peak": lds_peak_gbs, "unit": "GB/s",
+                    "frac": lds_bytes / (main * 1e-3) / 1e9 / lds_peak_gbs,
+                    "peak_source": "148 SMs x 128 B/clk x sampled SM clock"}}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        ptr, idx, val = eng.download_csr()
+        sample_rows = min(ptr.size - 1, args.ref_rows // 4)
+        e = int(ptr[sample_rows])
+        times, kind, cores, _ = cpu_reference(ptr[:sample_rows + 1], idx[:e], val[:e], hq[0][:8], K, max_seconds=20.0)
+        sec = sum(times) / len(times)
+        cpu = {"value": e / sec, "unit": "nnz/s", "cores": cores, "kind": kind,
+               "sample": f"first {sample_rows} rows ({e} nnz), {len(times)} queries one after another (the reference has no "
+                         f"batched mode), spmv_coo_gold_top_k over {cores} row blocks in {cores} threads"}
+    if rank == 0:
+        line = {"metric": "topk_spmv_nnz_per_s", "value": B * nnz_total / (ms_step * 1e-3), "unit": "nnz/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "rows": rows_total, "cols": cols, "nnz": nnz_total, "k": K, "queries": B,
+                           "value_counts": "queries x non-zeros per second",
+                           "arithmetic": "fma" if args.batch_fma else "separate mul/add (bit-identical to the gold)",
+                           "sharding": f"rows/{world}" if world > 1 else "none",
+                           "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * 8 / 1e9),
+                           "generator_s": round(gen_s, 2)},
+                "roofline": roof, "cpu_baseline": cpu,
+                "e2e": {"value": B * nnz_total / (e2e_ms_step * 1e-3), "unit": "nnz/s", "ms_per_step": e2e_ms_step,
+                        "h2d_bytes_per_step": B * cols * 4, "d2h_bytes_per_step": B * (KMAX * 8 + 4),
+                        "api": "SpMV.reset(host [64, cols]) -> operator() -> read_result(q) for every query"},
+                "gpu_launches": args.steps * (5 if world == 1 else 6),
+                "batched_fallbacks": int(st.batched_fallbacks), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _DevArray2:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
 def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
     """cfg3: the cfg2 matrix quantised to 20-bit fixed point and packed into BS-CSR packets by the host
     packet builder (the reference does this on the host too), 32 partitions x LFR 4 x local K 8."""
@@ -495,6 +649,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override the workload's total rows (debug)")
     ap.add_argument("--ref-rows", type=int, default=2_000_000, help="rows of the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--batch-fma", action="store_true", help="cfg5: fused multiply-add arithmetic")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
