@@ -76,13 +76,19 @@ int alloc_query_side(Handle *h) {
     h->n_sample_cap = 8192;
     TKS_CUDA(h, cudaMalloc(&h->d_sample_keys, h->n_sample_cap * sizeof(uint32_t)));
     TKS_CUDA(h, cudaMalloc(&h->d_res_keys, (size_t)mb * h->kmax * sizeof(uint64_t)));
-    TKS_CUDA(h, cudaMalloc(&h->d_res_idx, (size_t)mb * h->kmax * sizeof(uint32_t)));
-    TKS_CUDA(h, cudaMalloc(&h->d_res_val, (size_t)mb * h->kmax * sizeof(float)));
-    TKS_CUDA(h, cudaMalloc(&h->d_res_count, mb * sizeof(uint32_t)));
-    TKS_CUDA(h, cudaMemset(h->d_res_count, 0, mb * sizeof(uint32_t)));
-    TKS_CUDA(h, cudaMallocHost(&h->h_res_idx, (size_t)mb * h->kmax * sizeof(uint32_t)));
-    TKS_CUDA(h, cudaMallocHost(&h->h_res_val, (size_t)mb * h->kmax * sizeof(float)));
-    TKS_CUDA(h, cudaMallocHost(&h->h_res_count, mb * sizeof(uint32_t)));
+    // results live in ONE block [count: mb (padded)] [idx: mb x kmax] [val: mb x kmax], mirrored in pinned host
+    // memory, so that a run's results come back with a single device-to-host copy
+    const size_t cnt_words = ((size_t)mb + 63u) & ~(size_t)63u;
+    h->res_block_bytes = (cnt_words + 2 * (size_t)mb * h->kmax) * 4u;
+    TKS_CUDA(h, cudaMalloc(&h->d_res_block, h->res_block_bytes));
+    TKS_CUDA(h, cudaMemset(h->d_res_block, 0, h->res_block_bytes));
+    TKS_CUDA(h, cudaMallocHost(&h->h_res_block, h->res_block_bytes));
+    h->d_res_count = h->d_res_block;
+    h->d_res_idx = h->d_res_block + cnt_words;
+    h->d_res_val = reinterpret_cast<float *>(h->d_res_idx + (size_t)mb * h->kmax);
+    h->h_res_count = h->h_res_block;
+    h->h_res_idx = h->h_res_block + cnt_words;
+    h->h_res_val = reinterpret_cast<float *>(h->h_res_idx + (size_t)mb * h->kmax);
     TKS_CUDA(h, cudaMallocHost(&h->h_x, (size_t)mb * h->cfg.max_cols * sizeof(float)));
     if (mb > 1 && h->batched_ok) {
         const uint32_t npass = (mb + kBqPerPass - 1) / kBqPerPass;
@@ -212,7 +218,12 @@ void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool
     const float *x = h->d_x + (size_t)q * h->cols;
     RunState *st = h->d_state + q;
     const uint32_t sgrid = (n_sample * kWarp + kSampleThreads - 1) / kSampleThreads;
-    csr_sample_kernel<<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, k);
+    // the sample grows with the matrix (~1 % of the non-zeros) so that the candidates stay a few thousand
+    uint64_t si = (h->nnz / 100u + (uint64_t)n_sample * kElemsPerIter - 1) / ((uint64_t)n_sample * kElemsPerIter);
+    const uint32_t max_si = h->chunk_nnz / kElemsPerIter;
+    const uint32_t sample_iters = (uint32_t)(si < 2 ? 2 : (si > max_si ? (max_si < 2 ? 2 : max_si) : si));
+    csr_sample_kernel<<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride,
+                                                                 sample_iters, k);
     if (profile) cudaEventRecord(h->evm0, s);
     switch (variant) {
         case 0: launch_main<256>(h, 0, m, x, st, k, s); break;
@@ -248,6 +259,10 @@ void launch_batched(Handle *h, uint32_t k, cudaStream_t s, bool profile) {
     a.sample_keys = h->d_bsample_keys;
     a.n_sample = h->n_chunks < h->b_sample_cap ? h->n_chunks : h->b_sample_cap;
     a.stride = h->n_chunks / a.n_sample;
+    {
+        uint64_t sb = (h->nnz / 50u + (uint64_t)a.n_sample * kBStage - 1) / ((uint64_t)a.n_sample * kBStage);
+        a.sample_batches = (uint32_t)(sb < 8 ? 8 : (sb > 64 ? 64 : sb));
+    }
     a.tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
     batched_transpose_kernel<<<h->num_sms, 256, 0, s>>>(h->d_x, h->batch, h->cols, a.npass, h->d_xT);
     const uint32_t warps_per_cta = kBThreads / kWarp;
@@ -291,6 +306,19 @@ int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false) {
     return TKS_OK;
 }
 
+// Results of the last run -> pinned host block (asynchronous on s).
+int fetch_results_async(Handle *h, cudaStream_t s) {
+    if (h->batch == (uint32_t)h->cfg.max_batch || h->res_block_bytes <= (64u << 10)) {
+        TKS_CUDA(h, cudaMemcpyAsync(h->h_res_block, h->d_res_block, h->res_block_bytes, cudaMemcpyDeviceToHost, s));
+    } else {
+        const size_t n = (size_t)h->batch * h->kmax;
+        TKS_CUDA(h, cudaMemcpyAsync(h->h_res_idx, h->d_res_idx, n * 4, cudaMemcpyDeviceToHost, s));
+        TKS_CUDA(h, cudaMemcpyAsync(h->h_res_val, h->d_res_val, n * 4, cudaMemcpyDeviceToHost, s));
+        TKS_CUDA(h, cudaMemcpyAsync(h->h_res_count, h->d_res_count, h->batch * 4, cudaMemcpyDeviceToHost, s));
+    }
+    return TKS_OK;
+}
+
 // Batched mode: queries whose candidate pool overflowed are re-run one by one through the single-query
 // kernels (their per-warp buffers compact instead of overflowing).  Called with the results in the pinned
 // host buffers; returns with them complete.
@@ -303,10 +331,8 @@ int resolve_batched_overflow(Handle *h, cudaStream_t s) {
     }
     if (!any) return TKS_OK;
     TKS_CUDA(h, cudaGetLastError());
-    const size_t n = (size_t)h->batch * h->kmax;
-    TKS_CUDA(h, cudaMemcpyAsync(h->h_res_idx, h->d_res_idx, n * 4, cudaMemcpyDeviceToHost, s));
-    TKS_CUDA(h, cudaMemcpyAsync(h->h_res_val, h->d_res_val, n * 4, cudaMemcpyDeviceToHost, s));
-    TKS_CUDA(h, cudaMemcpyAsync(h->h_res_count, h->d_res_count, h->batch * 4, cudaMemcpyDeviceToHost, s));
+    int rc = fetch_results_async(h, s);
+    if (rc) return rc;
     TKS_CUDA(h, cudaStreamSynchronize(s));
     h->stats.batched_fallbacks += 1;
     return TKS_OK;
@@ -425,9 +451,9 @@ void tks_destroy(tks_handle *h) {
     free_matrix(h);
     bscsr_destroy(h);
     cudaFree(h->d_x); cudaFree(h->d_state); cudaFree(h->d_pool); cudaFree(h->d_sample_keys);
-    cudaFree(h->d_res_keys); cudaFree(h->d_res_idx); cudaFree(h->d_res_val); cudaFree(h->d_res_count);
+    cudaFree(h->d_res_keys); cudaFree(h->d_res_block);
     cudaFree(h->d_xT); cudaFree(h->d_bpool); cudaFree(h->d_pass_counter); cudaFree(h->d_bsample_keys);
-    cudaFreeHost(h->h_res_idx); cudaFreeHost(h->h_res_val); cudaFreeHost(h->h_res_count); cudaFreeHost(h->h_x);
+    cudaFreeHost(h->h_res_block); cudaFreeHost(h->h_x);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_query) cudaEventDestroy(h->ev_query);
@@ -572,6 +598,8 @@ int tks_run_async(tks_handle *h, uint32_t k, void *cuda_stream) {
     TKS_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) { h->last_k = k; return bscsr_launch(h, s); }
+    // a query staged by tks_set_query (host) travels on the handle's own stream
+    if (s != h->stream) TKS_CUDA(h, cudaStreamWaitEvent(s, h->ev_query, 0));
     int rc = launch_float(h, k, s);
     if (rc) return rc;
     h->have_result = false;
@@ -593,10 +621,8 @@ int tks_run(tks_handle *h, uint32_t k, float *kernel_ms, float *total_ms) {
         rc = bscsr_fetch(h);
         if (rc) return rc;
     } else {
-        const size_t n = (size_t)h->batch * h->kmax;
-        TKS_CUDA(h, cudaMemcpyAsync(h->h_res_idx, h->d_res_idx, n * 4, cudaMemcpyDeviceToHost, h->stream));
-        TKS_CUDA(h, cudaMemcpyAsync(h->h_res_val, h->d_res_val, n * 4, cudaMemcpyDeviceToHost, h->stream));
-        TKS_CUDA(h, cudaMemcpyAsync(h->h_res_count, h->d_res_count, h->batch * 4, cudaMemcpyDeviceToHost, h->stream));
+        rc = fetch_results_async(h, h->stream);
+        if (rc) return rc;
         TKS_CUDA(h, cudaStreamSynchronize(h->stream));
         if (h->last_run_batched) {
             rc = resolve_batched_overflow(h, h->stream);
@@ -630,11 +656,10 @@ int tks_read_result(tks_handle *h, uint32_t query, uint32_t *idx_out, void *val_
         // results of an async run: fetch now
         if (h->last_k == 0) return h->fail(TKS_ESTATE, "no run yet");
         TKS_CUDA(h, cudaSetDevice(h->device));
-        const size_t n = (size_t)h->batch * h->kmax;
         TKS_CUDA(h, cudaDeviceSynchronize());
-        TKS_CUDA(h, cudaMemcpy(h->h_res_idx, h->d_res_idx, n * 4, cudaMemcpyDeviceToHost));
-        TKS_CUDA(h, cudaMemcpy(h->h_res_val, h->d_res_val, n * 4, cudaMemcpyDeviceToHost));
-        TKS_CUDA(h, cudaMemcpy(h->h_res_count, h->d_res_count, h->batch * 4, cudaMemcpyDeviceToHost));
+        int rcf = fetch_results_async(h, h->stream);
+        if (rcf) return rcf;
+        TKS_CUDA(h, cudaStreamSynchronize(h->stream));
         if (h->overflow_check_pending) {
             int rc = resolve_batched_overflow(h, h->stream);
             if (rc) return rc;

@@ -1,6 +1,7 @@
 // bscsr_api.cu -- host side of the FPGA-semantics engine: packet upload + chunk tables, query
 // transform, kernel dispatch on (FIXED_WIDTH, LIMITED_FINISHED_ROWS), result words, host merge.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 #include <vector>
@@ -30,10 +31,38 @@ struct BscsrState {
     uint32_t *h_res_idx = nullptr, *h_res_val = nullptr;   // pinned
     bool have_query = false, have_words = false;
     int grid = 0;
+    int variant = 0;             // TKS_BSCSR_VARIANT (experiments): 0 = default, 1 / 8 / 16 = query copies
+    bool variant_ready = false;  // launch geometry computed
+    bool replay_ready = false;
+    cudaEvent_t ev_query = nullptr;
     std::vector<uint32_t> merged_idx, merged_val;          // read_result() output of the last run
 };
 
 namespace {
+
+template <int W, int LFR, int XREP, int THREADS, bool PREFETCH>
+cudaError_t prep_stream_variant(int *ctas_per_sm) {
+    auto kern = bscsr_stream_kernel<W, LFR, XREP, THREADS, PREFETCH>;
+    const size_t smem = bscsr_stream_smem(XREP, THREADS);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kern, THREADS, smem);
+}
+
+template <int W, int LFR, int XREP, int THREADS, bool PREFETCH>
+void launch_stream_variant(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s) {
+    if (!b->variant_ready) {
+        int per_sm = 1;
+        cudaError_t e = prep_stream_variant<W, LFR, XREP, THREADS, PREFETCH>(&per_sm);
+        if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+        b->grid = h->num_sms * per_sm;
+        const uint32_t wpc = THREADS / 32;
+        if ((uint32_t)b->grid * wpc > b->n_chunks) b->grid = (int)((b->n_chunks + wpc - 1) / wpc);
+        b->variant_ready = true;
+    }
+    bscsr_stream_kernel<W, LFR, XREP, THREADS, PREFETCH><<<b->grid, THREADS, bscsr_stream_smem(XREP, THREADS), s>>>(
+        b->d_packets, m, b->d_xq, (uint32_t)h->cfg.local_k, b->logs, b->d_theta_seed, b->d_counter);
+}
 
 template <int W, int LFR>
 void launch_stream(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s) {
@@ -43,8 +72,12 @@ void launch_stream(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t 
     const uint32_t sgrid = (b->n_pieces * 32u + kBsThreads - 1) / kBsThreads;
     bscsr_sample_kernel<W, LFR><<<sgrid, kBsThreads, 0, s>>>(b->d_packets, sm, b->d_xq, (uint32_t)h->cfg.local_k);
     if (prof) cudaEventRecord(h->evm0, s);
-    bscsr_stream_kernel<W, LFR><<<b->grid, kBsThreads, 0, s>>>(b->d_packets, m, b->d_xq, (uint32_t)h->cfg.local_k, b->logs,
-                                                             b->d_theta_seed, b->d_counter);
+    // stream-kernel variants (query copies x CTA size); the alternatives exist for the headline format only
+    if (W == 20 && LFR == 4 && b->variant == 1) launch_stream_variant<20, 4, 1, 256, false>(h, b, m, s);
+    else if (W == 20 && LFR == 4 && b->variant == 16) launch_stream_variant<20, 4, 16, 1024, false>(h, b, m, s);
+    else if (W == 20 && LFR == 4 && b->variant == 8) launch_stream_variant<20, 4, 8, 1024, false>(h, b, m, s);
+    else if (W == 20 && LFR == 4 && b->variant == 33) launch_stream_variant<20, 4, 32, 768, false>(h, b, m, s);
+    else launch_stream_variant<W, LFR, kBsDefaultXrep, kBsDefaultThreads, true>(h, b, m, s);
     if (prof) cudaEventRecord(h->evm1, s);
 }
 
@@ -57,7 +90,11 @@ int dispatch_lfr(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s)
         case 4: launch_stream<W, 4>(h, b, m, s); break;
         default: return h->fail(TKS_EINVAL, "limited_finished_rows=%d is not instantiated (1..4)", h->cfg.limited_finished_rows);
     }
-    bscsr_replay_kernel<W><<<b->P * (uint32_t)h->cfg.limited_finished_rows, kReplayThreads, 0, s>>>(
+    if (!b->replay_ready) {
+        cudaFuncSetAttribute(bscsr_replay_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplayDynSmem);
+        b->replay_ready = true;
+    }
+    bscsr_replay_kernel<W><<<b->P * (uint32_t)h->cfg.limited_finished_rows, kReplayThreads, kReplayDynSmem, s>>>(
         b->logs, b->d_part_chunk_begin, (uint32_t)h->cfg.limited_finished_rows, (uint32_t)h->cfg.local_k, b->chunk_cap,
         b->d_res_idx, b->d_res_val, b->d_counter);
     return TKS_OK;
@@ -103,6 +140,7 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
         const uint8_t *pk = static_cast<const uint8_t *>(packets[p]);
         const uint64_t np = packets_per_part[p];
         uint32_t last_row = 0;
+        uint64_t next_chunk = 0;
         std::vector<uint8_t> keepflag(np);   // packet passes the carried partial sum through (n == 1 && !new)
         for (uint64_t i = 0; i < np; i++) {
             uint64_t w0;
@@ -121,15 +159,18 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
             uint32_t n = 0, pe = 0;
             for (int s = 0; s < LFR; s++) { uint32_t xs = (uint32_t)((w0 >> (4 * s)) & 0xF); n += (xs != pe); pe = xs; }
             const uint32_t nw = (i != 0) ? xf : 0u;
-            if (i % b->chunk_cap == 0) {
-                c_first.push_back((uint32_t)(goff + i));
-                c_count.push_back((uint32_t)std::min<uint64_t>(b->chunk_cap, np - i));
-                c_local0.push_back((uint32_t)i);
-                c_row_in.push_back(last_row);
+            if (i == next_chunk) {
                 uint32_t L = 0;
                 if (i > 0) { L = 1; while (i - L > 0 && keepflag[i - L]) L++; }
+                // look-back + chunk = a whole number of 32-packet warp iterations (no extra iteration for the look-back)
+                const uint64_t cnt = std::min<uint64_t>(b->chunk_cap - (L % 32u), np - i);
+                c_first.push_back((uint32_t)(goff + i));
+                c_count.push_back((uint32_t)cnt);
+                c_local0.push_back((uint32_t)i);
+                c_row_in.push_back(last_row);
                 c_look.push_back(L);
                 c_part.push_back(p);
+                next_chunk = i + cnt;
             }
             if (i < kBsSamplePackets && i % kBsSamplePiece == 0) {
                 s_first.push_back((uint32_t)(goff + i));
@@ -192,14 +233,13 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     TKS_CUDA(h, cudaMalloc(&b->d_counter, 4));
     TKS_CUDA(h, cudaMemset(b->d_counter, 0, 4));
     const size_t nres = (size_t)partitions * Kp * 16;
-    TKS_CUDA(h, cudaMalloc(&b->d_res_idx, nres * 4));
-    TKS_CUDA(h, cudaMalloc(&b->d_res_val, nres * 4));
-    TKS_CUDA(h, cudaMemset(b->d_res_idx, 0, nres * 4));   // positions >= LFR stay 0 (.cpp:100-110)
-    TKS_CUDA(h, cudaMemset(b->d_res_val, 0, nres * 4));
-    TKS_CUDA(h, cudaMallocHost(&b->h_res_idx, nres * 4));
-    TKS_CUDA(h, cudaMallocHost(&b->h_res_val, nres * 4));
-    b->grid = h->num_sms * 4;   // 4 CTAs of 8 warps per SM
-    if ((uint32_t)b->grid * (kBsThreads / 32) > b->n_chunks) b->grid = (int)((b->n_chunks + kBsThreads / 32 - 1) / (kBsThreads / 32));
+    // index words and value words in one block: one device-to-host copy per run
+    TKS_CUDA(h, cudaMalloc(&b->d_res_idx, 2 * nres * 4));
+    b->d_res_val = b->d_res_idx + nres;
+    TKS_CUDA(h, cudaMemset(b->d_res_idx, 0, 2 * nres * 4));   // positions >= LFR stay 0 (.cpp:100-110)
+    TKS_CUDA(h, cudaMallocHost(&b->h_res_idx, 2 * nres * 4));
+    b->h_res_val = b->h_res_idx + nres;
+    if (const char *v = std::getenv("TKS_BSCSR_VARIANT")) b->variant = std::atoi(v);
 
     h->rows = 0; h->cols = cols; h->nnz = b->total_nnz;
     h->have_matrix = true;
@@ -229,12 +269,14 @@ int bscsr_set_query(Handle *h, const uint32_t *vec32_host, const uint32_t *vec32
     }
     // kernel vec load (.cpp:127-137): W-bit truncation of the 32-bit word; pre-shifted by one for the
     // umulhi product (see bscsr_stream_kernel); columns >= cols read 0 like the zero-initialised URAM
+    if (!b->ev_query) TKS_CUDA(h, cudaEventCreateWithFlags(&b->ev_query, cudaEventDisableTiming));
+    TKS_CUDA(h, cudaEventSynchronize(b->ev_query));   // h_xq (pinned staging) may still feed the previous copy
     for (uint32_t c = 0; c < 1024; c++) {
         uint32_t xq = (c < b->cols) ? (vec32_host[c] >> (32 - W)) : 0u;
         b->h_xq[c] = (W == 32) ? xq : (xq << 1);
     }
     TKS_CUDA(h, cudaMemcpyAsync(b->d_xq, b->h_xq, 1024 * 4, cudaMemcpyHostToDevice, s));
-    TKS_CUDA(h, cudaStreamSynchronize(s));   // h_xq (pinned staging) is reused by the next call
+    TKS_CUDA(h, cudaEventRecord(b->ev_query, s));
     b->have_query = true;
     return TKS_OK;
 }
@@ -243,6 +285,7 @@ int bscsr_launch(Handle *h, cudaStream_t s) {
     BscsrState *b = h->bs;
     if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");
     if (!b->have_query) return h->fail(TKS_ESTATE, "no query set");
+    if (s != h->stream && b->ev_query) TKS_CUDA(h, cudaStreamWaitEvent(s, b->ev_query, 0));
     BscsrChunks m{b->d_chunk_first, b->d_chunk_count, b->d_chunk_local0, b->d_chunk_row_in, b->d_chunk_lookback,
                   b->d_chunk_part, b->n_chunks, b->chunk_cap};
     int rc;
@@ -264,24 +307,31 @@ int bscsr_fetch(Handle *h) {
     BscsrState *b = h->bs;
     if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");
     const size_t nres = (size_t)b->P * h->cfg.local_k * 16;
-    TKS_CUDA(h, cudaMemcpyAsync(b->h_res_idx, b->d_res_idx, nres * 4, cudaMemcpyDeviceToHost, h->stream));
-    TKS_CUDA(h, cudaMemcpyAsync(b->h_res_val, b->d_res_val, nres * 4, cudaMemcpyDeviceToHost, h->stream));
+    TKS_CUDA(h, cudaMemcpyAsync(b->h_res_idx, b->d_res_idx, 2 * nres * 4, cudaMemcpyDeviceToHost, h->stream));
     TKS_CUDA(h, cudaStreamSynchronize(h->stream));
     b->have_words = true;
     // read_result (host_spmv_bscsr.cpp:399-448): all P x Kp x B slots, idx += first_row[p], keep val > 0,
     // first insertion of an index wins, then sort_tuples (evaluation_utils.hpp:40-62)
-    std::unordered_map<uint32_t, uint32_t> seen;
-    std::vector<std::pair<uint32_t, uint32_t>> out;   // (idx, val)
+    // (<= P x Kp x LFR candidates: a sort instead of the reference's unordered_map; same outcome)
+    struct Cand { uint32_t idx, val, order; };
+    std::vector<Cand> cand;
     const int Kp = h->cfg.local_k;
+    cand.reserve((size_t)b->P * Kp * 4);
     for (uint32_t p = 0; p < b->P; p++)
         for (int t = 0; t < Kp; t++)
             for (uint32_t q = 0; q < b->B; q++) {
                 const size_t o = ((size_t)p * Kp + t) * 16 + q;
                 const uint32_t v = b->h_res_val[o];
                 if (v == 0) continue;
-                const uint32_t id = b->h_res_idx[o] + b->first_row[p];
-                if (seen.emplace(id, v).second) out.emplace_back(id, v);
+                cand.push_back({b->h_res_idx[o] + b->first_row[p], v, (uint32_t)cand.size()});
             }
+    std::sort(cand.begin(), cand.end(), [](const Cand &l, const Cand &r) {
+        return l.idx != r.idx ? l.idx < r.idx : l.order < r.order;
+    });
+    std::vector<std::pair<uint32_t, uint32_t>> out;   // (idx, val): the first insertion of an index wins
+    out.reserve(cand.size());
+    for (size_t i = 0; i < cand.size(); i++)
+        if (i == 0 || cand[i].idx != cand[i - 1].idx) out.emplace_back(cand[i].idx, cand[i].val);
     const bool higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
     std::sort(out.begin(), out.end(), [&](const std::pair<uint32_t, uint32_t> &l, const std::pair<uint32_t, uint32_t> &r) {
         if (l.second != r.second) return l.second > r.second;
@@ -335,7 +385,8 @@ void bscsr_destroy(Handle *h) {
     cudaFree(b->d_chunk_part); cudaFree(b->d_s_first); cudaFree(b->d_s_count); cudaFree(b->d_s_local0); cudaFree(b->d_s_lookback);
     cudaFree(b->d_s_part); cudaFree(b->d_s_part_begin); cudaFree(b->d_piece_top); cudaFree(b->d_ticket); cudaFree(b->d_theta_seed);
     cudaFree(b->d_xq); cudaFreeHost(b->h_xq); cudaFree(b->d_counter);
-    cudaFree(b->d_res_idx); cudaFree(b->d_res_val); cudaFreeHost(b->h_res_idx); cudaFreeHost(b->h_res_val);
+    cudaFree(b->d_res_idx); cudaFreeHost(b->h_res_idx);
+    if (b->ev_query) cudaEventDestroy(b->ev_query);
     delete b;
     h->bs = nullptr;
 }

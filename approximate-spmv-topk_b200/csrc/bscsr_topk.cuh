@@ -33,13 +33,16 @@
 
 namespace tks {
 
-constexpr uint32_t kBsThreads = 256;          // 8 warps per CTA in the stream kernel
+constexpr uint32_t kBsThreads = 256;          // 8 warps per CTA in the sample kernel
+constexpr int kBsDefaultXrep = 32;            // stream kernel: one query copy per shared-memory bank
+constexpr int kBsDefaultThreads = 768;        // stream kernel: one CTA of 24 warps per SM (128 KB query + 48 KB ptab)
 constexpr uint32_t kBsMaxKp = 32;             // local K (types.hpp K) supported: 1..32
 constexpr uint32_t kBsMaxLfr = 4;             // LFR values instantiated: 1..4 (see bscsr_api.cu)
 constexpr uint32_t kBsSamplePackets = 2048;   // prefix of every partition reduced by the sample kernel
 constexpr uint32_t kBsSamplePiece = 64;       // packets per sample warp
-constexpr uint32_t kReplayThreads = 256;
-constexpr uint32_t kReplaySurvivors = 4096;   // log entries buffered between sequential replays
+constexpr uint32_t kReplayThreads = 1024;      // one tile covers the ~800 chunks of a cfg3 partition
+constexpr uint32_t kReplaySurvivors = 8192;   // log entries buffered between sequential replays (dynamic smem)
+constexpr uint32_t kReplayDynSmem = kReplaySurvivors * 8u;
 
 struct BscsrChunks {
     const uint32_t *first;      // global index of the chunk's first packet
@@ -106,7 +109,11 @@ struct BsTopSink {
 
 // Packets [begin, end) of one partition, 32 per iteration; packets before `first` only rebuild the carry.
 // theta/top: per lane-list running K-th largest and the K largest values (lanes 0..Kp-1), updated in place.
-template <int W, int LFR, typename Sink>
+// XREP: copies of the query in shared memory (word col * XREP + (lane % XREP)): with 32 copies every lane
+// gathers from its own bank (no conflicts), with 16 two lanes share a bank pair, with 1 the gather is the
+// plain 1024-word table.  THREADS: CTA size = stride of the per-thread prefix-sum columns in ptab.
+// PREFETCH: keep the next iteration's packet in a second register set (16 more registers per thread).
+template <int W, int LFR, int XREP, int THREADS, bool PREFETCH, typename Sink>
 __device__ __forceinline__ void bs_process(const uint8_t *__restrict__ packets, uint32_t begin, uint32_t first,
                                            uint32_t end, uint32_t local0, uint32_t row_base, uint32_t Kp,
                                            const uint8_t *xsb, uint32_t *ptab, uint32_t (&theta)[LFR],
@@ -114,29 +121,39 @@ __device__ __forceinline__ void bs_process(const uint8_t *__restrict__ packets, 
     using F = BsFmt<W>;
     constexpr int B = F::B;
     constexpr uint32_t M = F::M;
+    constexpr int XS = (XREP == 32) ? 7 : (XREP == 16) ? 6 : (XREP == 8) ? 5 : (XREP == 4) ? 4 : (XREP == 2) ? 3 : 2;
+    static_assert((1 << XS) == 4 * XREP, "XREP must be a power of two <= 32");
+    constexpr uint32_t YMASK = 0x3FFu << XS;
     const unsigned lane = lane_id();
+    xsb += (lane & (uint32_t)(XREP - 1)) * 4u;   // this lane's copy
     uint32_t carry = 0;   // last_row_of_packet_output (hpp:261)
-    uint32_t w[16], wn[16];
-    {
+    uint32_t wa[16], wb[PREFETCH ? 16 : 1];
+    if (PREFETCH) {
         const uint32_t g0 = begin + lane;
-        if (g0 < end) bs_load_packet(packets + (size_t)g0 * 64u, wn);
+        if (g0 < end) bs_load_packet(packets + (size_t)g0 * 64u, wa);
         else {
 #pragma unroll
-            for (int i = 0; i < 16; i++) wn[i] = 0;
+            for (int i = 0; i < 16; i++) wa[i] = 0;
         }
     }
-    for (uint32_t base = begin; base < end; base += 32) {
+    // one iteration = 32 consecutive packets, one per lane; `w` holds this iteration's packet, `wn` receives the
+    // next one (software prefetch).  The caller alternates the two register sets instead of copying them.
+    auto iteration = [&](uint32_t base, uint32_t (&w)[16], uint32_t (&wn)[PREFETCH ? 16 : 1]) {
         const uint32_t g = base + lane;
         const bool active = g < end;
         const bool emitting = active && g >= first;
-#pragma unroll
-        for (int i = 0; i < 16; i++) w[i] = wn[i];
-        {
-            const uint32_t gn = g + 32;   // software prefetch of the next iteration's packet
+        if constexpr (PREFETCH) {
+            const uint32_t gn = g + 32;
             if (gn < end) bs_load_packet(packets + (size_t)gn * 64u, wn);
             else {
 #pragma unroll
                 for (int i = 0; i < 16; i++) wn[i] = 0;
+            }
+        } else {
+            if (active) bs_load_packet(packets + (size_t)g * 64u, w);
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) w[i] = 0;
             }
         }
         // ---- loop 1 + loop 2 (hpp:168-220, 104-149): decode, products, segment sums ----
@@ -151,9 +168,9 @@ __device__ __forceinline__ void bs_process(const uint8_t *__restrict__ packets, 
             // column * 4 (byte offset into the query table) and the value: one shift + one mask each
             const int yp = F::YOFF + 10 * j, yq = yp / 32, ysh = yp % 32;
             uint32_t yraw;
-            if (ysh + 10 <= 32) yraw = (ysh >= 2) ? (w[yq] >> (ysh - 2)) : (w[yq] << (2 - ysh));
-            else yraw = __funnelshift_r(w[yq], w[yq + 1], ysh - 2);
-            const uint32_t xv = *reinterpret_cast<const uint32_t *>(xsb + (yraw & 0xFFCu));
+            if (ysh + 10 <= 32) yraw = (ysh >= XS) ? (w[yq] >> (ysh - XS)) : (w[yq] << (XS - ysh));
+            else yraw = __funnelshift_r(w[yq], w[yq + 1], ysh - XS);
+            const uint32_t xv = *reinterpret_cast<const uint32_t *>(xsb + (yraw & YMASK));
             const int vp = F::VOFF + W * j, vq = vp / 32, vsh = vp % 32;
             uint32_t pw;
             if constexpr (W == 32) {
@@ -170,7 +187,7 @@ __device__ __forceinline__ void bs_process(const uint8_t *__restrict__ packets, 
                 pw = __umulhi(vraw & topmask, xv);
             }
             acc += pw;
-            ptab[(j + 1) * kBsThreads + threadIdx.x] = acc;
+            ptab[(j + 1) * THREADS + threadIdx.x] = acc;
         }
         uint32_t agg[LFR];
         uint32_t n = 0;
@@ -178,7 +195,7 @@ __device__ __forceinline__ void bs_process(const uint8_t *__restrict__ packets, 
             uint32_t prevL = 0, prev_end = 0;
 #pragma unroll
             for (int s = 0; s < LFR; s++) {
-                const uint32_t L = ptab[x[s] * kBsThreads + threadIdx.x];   // x is non-decreasing (checked at upload)
+                const uint32_t L = ptab[x[s] * THREADS + threadIdx.x];   // x is non-decreasing (checked at upload)
                 agg[s] = (L - prevL) & M;
                 n += (x[s] != prev_end);
                 prevL = L;
@@ -232,7 +249,7 @@ __device__ __forceinline__ void bs_process(const uint8_t *__restrict__ packets, 
 
         // ---- loop 4 (hpp:331-389): candidates of the LFR lanes ----
         uint32_t val[LFR];
-        bool pass[LFR];
+        bool pass[LFR], fin0[LFR];
         bool anyp = false;
 #pragma unroll
         for (int j = 0; j < LFR; j++) {
@@ -245,9 +262,15 @@ __device__ __forceinline__ void bs_process(const uint8_t *__restrict__ packets, 
                 if (j == 1 && nw == 0) val[j] = (val[j] + prev) & M;
                 fin = (x[j - 1] != (j > 1 ? x[j - 2] : 0u)) && (n != (uint32_t)j);
             }
-            if (p0flags && active && local_idx == 0) p0flags[j] = fin ? 1u : 0u;
+            fin0[j] = fin;
             pass[j] = emitting && fin && (val[j] >= theta[j]);
             anyp |= pass[j];
+        }
+        if (p0flags && base <= first && first < base + 32 && local0 == 0) {   // warp-uniform: packet 0 of the partition
+            if (active && local_idx == 0) {
+#pragma unroll
+                for (int j = 0; j < LFR; j++) p0flags[j] = fin0[j] ? 1u : 0u;
+            }
         }
         if (__any_sync(0xFFFFFFFFu, anyp)) {
 #pragma unroll
@@ -265,6 +288,14 @@ __device__ __forceinline__ void bs_process(const uint8_t *__restrict__ packets, 
                 }
             }
         }
+    };
+    if constexpr (PREFETCH) {
+        for (uint32_t base = begin; base < end; base += 64) {
+            iteration(base, wa, wb);
+            if (base + 32 < end) iteration(base + 32, wb, wa);
+        }
+    } else {
+        for (uint32_t base = begin; base < end; base += 32) iteration(base, wa, wb);
     }
 }
 
@@ -293,7 +324,7 @@ bscsr_sample_kernel(const uint8_t *__restrict__ packets, BscsrSample sm, const u
     for (int j = 0; j < LFR; j++) { theta[j] = 0; top[j] = 0; }
     BsTopSink<LFR> sink;
     const uint32_t first = sm.first[piece];
-    bs_process<W, LFR>(packets, first - sm.lookback[piece], first, first + sm.count[piece], sm.local0[piece], 0u, Kp,
+    bs_process<W, LFR, 1, kBsThreads, false>(packets, first - sm.lookback[piece], first, first + sm.count[piece], sm.local0[piece], 0u, Kp,
                        reinterpret_cast<const uint8_t *>(xs), ptab, theta, top, sink, nullptr);
 #pragma unroll
     for (int j = 0; j < LFR; j++) sm.piece_top[((size_t)piece * LFR + j) * 32u + lane] = (lane < Kp) ? top[j] : 0u;
@@ -331,13 +362,19 @@ bscsr_sample_kernel(const uint8_t *__restrict__ packets, BscsrSample sm, const u
     if (lane == 0) sm.ticket[p] = 0;
 }
 
-template <int W, int LFR>
-__global__ void __launch_bounds__(kBsThreads)
+// Dynamic shared memory: bscsr_stream_smem(XREP, THREADS) bytes = XREP copies of the query + the ptab columns.
+__host__ __device__ constexpr size_t bscsr_stream_smem(int xrep, int threads) {
+    return (size_t)1024 * xrep * 4 + (size_t)16 * threads * 4;
+}
+
+template <int W, int LFR, int XREP, int THREADS, bool PREFETCH>
+__global__ void __launch_bounds__(THREADS, (XREP <= 2 && THREADS <= 256) ? 4 : 1)
 bscsr_stream_kernel(const uint8_t *__restrict__ packets, BscsrChunks m, const uint32_t *__restrict__ xq, uint32_t Kp,
                     BscsrLogs logs, const uint32_t *__restrict__ theta_seed, uint32_t *chunk_counter) {
-    __shared__ uint32_t xs[1024];                // query, pre-shifted (see bscsr_api.cu); columns >= cols hold 0
-    __shared__ uint32_t ptab[16 * kBsThreads];   // [prefix length 0..15][thread]: running sums of the products
-    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) xs[i] = xq[i];
+    extern __shared__ __align__(16) uint8_t bs_smem[];
+    uint32_t *xs = reinterpret_cast<uint32_t *>(bs_smem);   // query, pre-shifted (bscsr_api.cu), XREP copies interleaved
+    uint32_t *ptab = xs + 1024 * XREP;                      // [prefix length 0..15][thread]: running sums of the products
+    for (uint32_t i = threadIdx.x; i < 1024u * XREP; i += THREADS) xs[i] = xq[i / XREP];
     ptab[threadIdx.x] = 0;
     __syncthreads();
     const unsigned lane = lane_id();
@@ -360,7 +397,7 @@ bscsr_stream_kernel(const uint8_t *__restrict__ packets, BscsrChunks m, const ui
             top[j] = theta[j];   // as if K candidates of that value had been seen: max(seed, own K-th largest)
             sink.lcnt[j] = 0;
         }
-        bs_process<W, LFR>(packets, first - m.lookback[c], first, first + count, local0, m.row_in[c], Kp,
+        bs_process<W, LFR, XREP, THREADS, PREFETCH>(packets, first - m.lookback[c], first, first + count, local0, m.row_in[c], Kp,
                            reinterpret_cast<const uint8_t *>(xs), ptab, theta, top, sink, logs.p0 + (size_t)c * LFR);
         if (lane == 0) {
 #pragma unroll
@@ -387,7 +424,8 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
     const uint32_t cb = part_chunk_begin[p], ce = part_chunk_begin[p + 1];
     const uint32_t tid = threadIdx.x;
     const unsigned lane = lane_id();
-    __shared__ uint32_t s_sv[kReplaySurvivors], s_sr[kReplaySurvivors];
+    extern __shared__ __align__(16) uint8_t replay_smem[];   // kReplayDynSmem bytes
+    uint32_t *s_sv = reinterpret_cast<uint32_t *>(replay_smem), *s_sr = s_sv + kReplaySurvivors;
     __shared__ uint32_t s_wsum[kReplayThreads / 32], s_off[kReplayThreads + 1];
     __shared__ uint32_t s_n;
     if (tid == 0) s_n = 0;

@@ -32,7 +32,6 @@ namespace tks {
 constexpr uint32_t kBqPerPass = 32;        // queries per pass: 8 lanes x 4 queries
 constexpr uint32_t kBThreads = 768;        // 24 warps, one CTA per SM (the table takes most of shared memory)
 constexpr uint32_t kBStage = 64;           // non-zeros staged per octet per batch (8 lanes x 8)
-constexpr uint32_t kBSampleBatches = 8;    // the sample reduces the first 512 non-zeros of a chunk
 constexpr uint32_t kBStageBytes = kBStage * 8u;                       // 64 values + 64 column words
 
 struct BatchedArgs {
@@ -44,6 +43,7 @@ struct BatchedArgs {
     uint32_t *pass_counter;   // [npass] dynamic chunk scheduler of the main kernel (reset by the select kernel)
     uint32_t *sample_keys;    // [batch][n_sample]
     uint32_t n_sample, stride;
+    uint32_t sample_batches;  // staging batches (64 non-zeros each) a sample octet reduces: ~2 % of the matrix in total
     int tie_higher;
 };
 
@@ -150,7 +150,7 @@ __device__ __forceinline__ void batched_stream(const CsrDevice &m, const Batched
         L.ord = m.chunk_ord[c] - 1u;
     }
     bool truncated = false;
-    if (SAMPLE && nb > kBSampleBatches) { nb = kBSampleBatches; truncated = true; }
+    if (SAMPLE && nb > a.sample_batches) { nb = a.sample_batches; truncated = true; }
     const uint32_t nb_w = __reduce_max_sync(kFull, nb);
     L.acc[0] = L.acc[1] = L.acc[2] = L.acc[3] = 0.0f;
     L.have_row = false;

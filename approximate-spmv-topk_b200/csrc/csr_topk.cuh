@@ -32,7 +32,6 @@ constexpr uint32_t kRowStartBit = 0x80000000u;
 constexpr uint32_t kMaxCols = 16384;                       // exclusive: cols <= 16383 (slot `cols` holds 0.0)
 constexpr uint32_t kEpl = 8;                                // elements per lane: one 256-bit load per array
 constexpr uint32_t kElemsPerIter = kWarp * kEpl;            // 256 non-zeros per warp iteration
-constexpr uint32_t kSampleIters = 2;                        // sample = first 512 nnz of a chunk
 constexpr uint32_t kMainThreads = 512;
 constexpr uint32_t kSampleThreads = 256;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
@@ -338,8 +337,8 @@ __device__ __forceinline__ KeyT block_radix_select(LoadF load, uint32_t n, uint3
 }
 
 // --------------------------------------------------------------------------
-// Kernel 1: threshold from a sample.  Warp w reduces the first kSampleIters
-// iterations of chunk w*stride exactly as the main kernel will and keeps the
+// Kernel 1: threshold from a sample.  Warp w reduces the first sample_iters
+// iterations (256 non-zeros each; ~1 % of the matrix in total) of chunk w*stride exactly as the main kernel will and keeps the
 // best completed row.  The k-th largest of these warp maxima is the score of k
 // distinct real rows, hence a valid lower bound on the k-th best score.
 // Dynamic shared memory: max((cols+1)*4, n_sample*4) bytes.
@@ -347,7 +346,7 @@ __device__ __forceinline__ KeyT block_radix_select(LoadF load, uint32_t n, uint3
 __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m, const float *__restrict__ x,
                                                                      RunState *st, uint32_t *sample_keys,
                                                                      uint32_t n_sample, uint32_t stride,
-                                                                     uint32_t k) {
+                                                                     uint32_t sample_iters, uint32_t k) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float *xs = reinterpret_cast<float *>(smem_raw);
     for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? x[i] : 0.0f;
@@ -356,7 +355,7 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
     if (gw < n_sample) {
         MaxSink sink{0.0f, false, neg_inf()};
         const uint32_t c = gw * stride;
-        if (c < m.n_chunks) csr_process_chunk(m, smem_raw, c, kSampleIters, sink);
+        if (c < m.n_chunks) csr_process_chunk(m, smem_raw, c, sample_iters, sink);
         uint32_t key = sink.any ? f32_to_ordered(sink.best) : 0u;
         key = __reduce_max_sync(kFull, key);
         if (lane_id() == 0) sample_keys[gw] = key;

@@ -48,6 +48,8 @@ struct Handle {
     uint32_t n_sample_cap = 0;
     uint32_t kmax = 0;
     uint64_t *d_res_keys = nullptr;
+    uint32_t *d_res_block = nullptr, *h_res_block = nullptr;   // [count][idx][val], device / pinned host
+    size_t res_block_bytes = 0;
     uint32_t *d_res_idx = nullptr;
     float *d_res_val = nullptr;
     uint32_t *d_res_count = nullptr;
