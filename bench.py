@@ -190,11 +190,6 @@ def reference_arm(args):
 # our arm
 # ---------------------------------------------------------------------------------------------
 
-class _DevArray:
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 def ours(args):
     import torch
     import torch.distributed as dist
@@ -245,17 +240,11 @@ def ours(args):
     nnz_total = int(nnz_t.item())
 
     dq = torch.from_numpy(queries).cuda()            # queries resident in HBM for `value`
-    if world > 1:
-        gathered = torch.empty(world * K, dtype=torch.int64, device="cuda")
+    sharded = tks.ShardedSpMV(eng, K, batch=1)       # run + all-gather of K candidates + merge (no-op exchange at N=1)
 
     def step(i):
         eng.reset_device(dq[i].data_ptr(), 1, stream)
-        eng.run_async(K, stream)
-        if world > 1:
-            kp, n = eng.result_keys_device(0)
-            mine = torch.as_tensor(_DevArray(kp, K, "<i8"), device="cuda")
-            dist.all_gather_into_tensor(gathered, mine)
-            eng.merge_keys_device(gathered.data_ptr(), world * K, K, 0, stream)
+        sharded.step(stream)
 
     for i in range(args.warmup):
         step(i)
@@ -297,11 +286,7 @@ def ours(args):
             eng.run_timed(K)
             v_e, i_e, _ = eng.read_result()
         else:
-            eng.run_async(K, stream)
-            kp, n = eng.result_keys_device(0)
-            mine = torch.as_tensor(_DevArray(kp, K, "<i8"), device="cuda")
-            dist.all_gather_into_tensor(gathered, mine)
-            eng.merge_keys_device(gathered.data_ptr(), world * K, K, 0, stream)
+            sharded.step(stream)
             torch.cuda.synchronize()
             v_e, i_e, _ = eng.read_result()
         dt = (time.perf_counter() - t0) * 1e3
@@ -411,22 +396,11 @@ def ours_batched(args, tks, wl, rows_total, peak_gbs, peak_src, world, rank, loc
     hq = [make_queries(cols, B, seed0=1 + 1000 * i) for i in range(nsets)]
     dq = [torch.from_numpy(q).cuda() for q in hq]
     KMAX = 1024
-    if world > 1:
-        gathered = torch.empty((world, B, K), dtype=torch.int64, device="cuda")
-
-    def exchange():
-        kp, _ = eng.result_keys_device(0)
-        mine = torch.as_tensor(_DevArray2(kp, (B, KMAX), "<i8"), device="cuda")[:, :K].contiguous()
-        dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))
-        regrouped = gathered.permute(1, 0, 2).contiguous()          # [B][world][K]
-        eng.merge_keys_batched_device(regrouped.data_ptr(), world * K, B, K, stream)
-        return regrouped
+    sharded = tks.ShardedSpMV(eng, K, batch=B)
 
     def step(i):
         eng.reset_device(dq[i % nsets].data_ptr(), B, stream)
-        eng.run_async(K, stream)
-        if world > 1:
-            return exchange()
+        sharded.step(stream)
 
     for i in range(args.warmup):
         step(i)
@@ -439,9 +413,8 @@ def ours_batched(args, tks, wl, rows_total, peak_gbs, peak_src, world, rank, loc
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    keep = None
     for i in range(args.steps):
-        keep = step(args.warmup + i)
+        step(args.warmup + i)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -466,8 +439,7 @@ def ours_batched(args, tks, wl, rows_total, peak_gbs, peak_src, world, rank, loc
             eng.run_timed(K)
             main_ms.append(eng.stats().last_main_kernel_ms)
         else:
-            eng.run_async(K, stream)
-            keep = exchange()
+            sharded.step(stream)
             torch.cuda.synchronize()
         out = [eng.read_result(q) for q in range(B)]
         dt = (time.perf_counter() - t0) * 1e3
@@ -532,11 +504,6 @@ def ours_batched(args, tks, wl, rows_total, peak_gbs, peak_src, world, rank, loc
     eng.close()
     if world > 1:
         dist.destroy_process_group()
-
-
-class _DevArray2:
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):

@@ -1,0 +1,85 @@
+"""One process per GPU over NCCL: contiguous row shards, all-gather of the K candidates, merge on
+every rank.  Uses 2 ranks when the box has >= 2 GPUs, else a single rank through the same code path."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, batch, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    from _pkg import pkg
+    from conftest import make_query
+    tks = pkg()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    gen, sh = tks.create_matrices, tks.sharding
+    rows, cols, k = 20000, 1024, 100
+    x, y, v = gen.create_sparse_matrix(rows, cols, 20, "gamma", seed=5)
+    v = v.astype(np.float32)
+    ptr = gen.csr_from_coo(x, rows)
+    r0, r1 = sh.plan_row_shards_by_nnz(ptr, world)[rank]
+    p, idx, val = sh.slice_csr(ptr, y, v, r0, r1)
+    Q = np.stack([make_query(cols, 300 + i) for i in range(batch)])
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        eng = tks.SpMV(p, idx, val, r1 - r0, cols, k=k, device=rank, row_offset=r0, max_batch=max(batch, 1))
+        sharded = tks.ShardedSpMV(eng, k, batch=batch)
+        out = []
+        for rep in range(2):                      # twice: the exchange buffers are reused
+            eng.reset(Q if batch > 1 else Q[0])
+            sharded.step(stream.cuda_stream)
+            torch.cuda.synchronize()
+            out = [eng.read_result(b) for b in range(batch)]
+    q.put((rank, [(a.copy(), b.copy(), c) for a, b, c in out]))
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [1, 33])
+def test_sharded_ranks_agree_with_global_topk(cuda_required, tks, orc, gen, batch):
+    import torch
+    import torch.multiprocessing as mp
+    from conftest import make_query
+    world = 2 if torch.cuda.device_count() >= 2 else 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, batch, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rows, cols, k = 20000, 1024, 100
+    x, y, v = gen.create_sparse_matrix(rows, cols, 20, "gamma", seed=5)
+    v = v.astype(np.float32)
+    for b in range(batch):
+        yref = orc.spmv_f32(x, y, v, make_query(cols, 300 + b), rows)
+        order = np.lexsort((np.arange(rows), -yref.astype(np.float64)))[:k]
+        for rank in range(world):
+            val, idx, cnt = results[rank][b]
+            assert cnt == k
+            assert set(idx.tolist()) == set(order.tolist())
+            np.testing.assert_allclose(val, yref[idx], rtol=1e-5)
+            if batch > 1:      # the batched kernel's sums are sequential fp32: exact, in the exact order
+                assert np.array_equal(idx, order.astype(np.uint32))
+                assert np.array_equal(val.view(np.uint32), yref[order].view(np.uint32))

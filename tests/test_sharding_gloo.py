@@ -82,3 +82,54 @@ def test_two_rank_allgather_merge_equals_global_topk(tie_higher):
     assert np.array_equal(mr, order.astype(np.uint32))
     assert np.array_equal(ms, score[order])
     assert shards[0][1] == shards[1][0] and shards[0][0] == 0 and shards[1][1] == 5000
+
+
+def _worker_batched(rank, world, port, k, batch, q):
+    """ShardedSpMV.exchange under gloo: [batch, k] keys per rank -> [batch, world*k] regrouped by query."""
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from _pkg import pkg
+    tks = pkg()
+    sh = tks.sharding
+    rows, cols = 4000, 128
+    rng = np.random.default_rng(1)
+    scores = rng.random((batch, rows)).astype(np.float32)          # stand-in for the engine's row scores
+    r0, r1 = sh.plan_row_shards_even(rows, world)[rank]
+    mine = np.zeros((batch, k), np.uint64)
+    for b in range(batch):
+        loc = scores[b, r0:r1]
+        order = np.lexsort((np.arange(loc.size), -loc.astype(np.float64)))[:k]
+        mine[b] = sh.make_keys(loc[order], (order + r0).astype(np.uint32))
+    s = tks.ShardedSpMV(engine=None, k=k, batch=batch)
+    regrouped = s.exchange(torch.from_numpy(mine.view(np.int64).copy()))
+    regrouped2 = s.exchange(torch.from_numpy(mine.view(np.int64).copy()))      # buffers are reused
+    assert torch.equal(regrouped, regrouped2) and tuple(regrouped.shape) == (batch, world * k)
+    merged = tks.distributed.merge_gathered_host(regrouped.numpy(), k)
+    if rank == 0:
+        q.put(merged)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [1, 5])
+def test_two_rank_batched_exchange_regroups_by_query(batch):
+    world, k = 2, 20
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_batched, args=(r, world, port, k, batch, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    merged = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sys.path.insert(0, str(ROOT))
+    from _pkg import pkg
+    sh = pkg().sharding
+    scores = np.random.default_rng(1).random((batch, 4000)).astype(np.float32)
+    for b in range(batch):
+        order = np.lexsort((np.arange(4000), -scores[b].astype(np.float64)))[:k]
+        ms, mr = sh.split_keys(merged[b])
+        assert np.array_equal(mr, order.astype(np.uint32)) and np.array_equal(ms, scores[b][order])
