@@ -35,50 +35,58 @@ struct BscsrState {
     bool variant_ready = false;  // launch geometry computed
     bool replay_ready = false;
     cudaEvent_t ev_query = nullptr;
+    bool bsx = false;            // packets re-encoded into the BSX device format (FIXED_WIDTH <= 22)
     std::vector<uint32_t> merged_idx, merged_val;          // read_result() output of the last run
 };
 
 namespace {
 
-template <int W, int LFR, int XREP, int THREADS, bool PREFETCH>
+template <int W, int LFR, int XREP, int THREADS, bool PREFETCH, bool BSX>
 cudaError_t prep_stream_variant(int *ctas_per_sm) {
-    auto kern = bscsr_stream_kernel<W, LFR, XREP, THREADS, PREFETCH>;
+    auto kern = bscsr_stream_kernel<W, LFR, XREP, THREADS, PREFETCH, BSX>;
     const size_t smem = bscsr_stream_smem(XREP, THREADS);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kern, THREADS, smem);
 }
 
-template <int W, int LFR, int XREP, int THREADS, bool PREFETCH>
+template <int W, int LFR, int XREP, int THREADS, bool PREFETCH, bool BSX>
 void launch_stream_variant(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s) {
     if (!b->variant_ready) {
         int per_sm = 1;
-        cudaError_t e = prep_stream_variant<W, LFR, XREP, THREADS, PREFETCH>(&per_sm);
+        cudaError_t e = prep_stream_variant<W, LFR, XREP, THREADS, PREFETCH, BSX>(&per_sm);
         if (e != cudaSuccess || per_sm < 1) per_sm = 1;
         b->grid = h->num_sms * per_sm;
         const uint32_t wpc = THREADS / 32;
         if ((uint32_t)b->grid * wpc > b->n_chunks) b->grid = (int)((b->n_chunks + wpc - 1) / wpc);
         b->variant_ready = true;
     }
-    bscsr_stream_kernel<W, LFR, XREP, THREADS, PREFETCH><<<b->grid, THREADS, bscsr_stream_smem(XREP, THREADS), s>>>(
+    bscsr_stream_kernel<W, LFR, XREP, THREADS, PREFETCH, BSX><<<b->grid, THREADS, bscsr_stream_smem(XREP, THREADS), s>>>(
         b->d_packets, m, b->d_xq, (uint32_t)h->cfg.local_k, b->logs, b->d_theta_seed, b->d_counter);
 }
 
-template <int W, int LFR>
-void launch_stream(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s) {
+template <int W, int LFR, bool BSX>
+void launch_stream_fmt(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s) {
     const bool prof = h->cfg.profile_kernels != 0 && s == h->stream;
     BscsrSample sm{b->d_s_first, b->d_s_count, b->d_s_local0, b->d_s_lookback, b->d_s_part, b->n_pieces,
                    b->d_s_part_begin, b->d_piece_top, b->d_ticket, b->d_theta_seed};
     const uint32_t sgrid = (b->n_pieces * 32u + kBsThreads - 1) / kBsThreads;
-    bscsr_sample_kernel<W, LFR><<<sgrid, kBsThreads, 0, s>>>(b->d_packets, sm, b->d_xq, (uint32_t)h->cfg.local_k);
+    bscsr_sample_kernel<W, LFR, BSX><<<sgrid, kBsThreads, 0, s>>>(b->d_packets, sm, b->d_xq, (uint32_t)h->cfg.local_k);
     if (prof) cudaEventRecord(h->evm0, s);
     // stream-kernel variants (query copies x CTA size); the alternatives exist for the headline format only
-    if (W == 20 && LFR == 4 && b->variant == 1) launch_stream_variant<20, 4, 1, 256, false>(h, b, m, s);
-    else if (W == 20 && LFR == 4 && b->variant == 16) launch_stream_variant<20, 4, 16, 1024, false>(h, b, m, s);
-    else if (W == 20 && LFR == 4 && b->variant == 8) launch_stream_variant<20, 4, 8, 1024, false>(h, b, m, s);
-    else if (W == 20 && LFR == 4 && b->variant == 33) launch_stream_variant<20, 4, 32, 768, false>(h, b, m, s);
-    else launch_stream_variant<W, LFR, kBsDefaultXrep, kBsDefaultThreads, true>(h, b, m, s);
+    if (W == 20 && LFR == 4 && BSX && b->variant == 1) launch_stream_variant<20, 4, 1, 256, false, BSX && W == 20>(h, b, m, s);
+    else if (W == 20 && LFR == 4 && BSX && b->variant == 16) launch_stream_variant<20, 4, 16, 1024, false, BSX && W == 20>(h, b, m, s);
+    else if (W == 20 && LFR == 4 && BSX && b->variant == 33) launch_stream_variant<20, 4, 32, 768, false, BSX && W == 20>(h, b, m, s);
+    else launch_stream_variant<W, LFR, kBsDefaultXrep, kBsDefaultThreads, true, BSX>(h, b, m, s);
     if (prof) cudaEventRecord(h->evm1, s);
+}
+
+template <int W, int LFR>
+void launch_stream(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s) {
+    if constexpr (W + 10 <= 32) {
+        if (b->bsx) { launch_stream_fmt<W, LFR, true>(h, b, m, s); return; }
+    }
+    launch_stream_fmt<W, LFR, false>(h, b, m, s);
 }
 
 template <int W>
@@ -129,6 +137,15 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     if (total > 0xFFFFFFF0ull) return h->fail(TKS_EINVAL, "more than 2^32 packets on one device");
     b->total_packets = total;
     b->chunk_cap = 512;
+    // FIXED_WIDTH <= 22: value + column fit one word -> re-encode into the BSX device format (bscsr_topk.cuh);
+    // TKS_BSCSR_VERBATIM=1 keeps the reference's words (the path the wider formats always take)
+    b->bsx = (W + 10 <= 32) && !(std::getenv("TKS_BSCSR_VERBATIM") && std::atoi(std::getenv("TKS_BSCSR_VERBATIM")) != 0);
+    std::vector<std::vector<uint32_t>> enc(b->bsx ? partitions : 0);
+    auto field = [](const uint8_t *pk72, int pos, int len) -> uint32_t {
+        uint64_t v;
+        std::memcpy(&v, pk72 + pos / 8, 8);
+        return (uint32_t)((v >> (pos % 8)) & ((1ull << len) - 1ull));
+    };
 
     // ---- chunk tables (host, once per matrix): row counter and carry look-back at every chunk start ----
     std::vector<uint32_t> c_first, c_count, c_local0, c_row_in, c_look, c_part, part_begin(partitions + 1, 0);
@@ -139,8 +156,9 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
         s_part_begin[p] = (uint32_t)s_first.size();
         const uint8_t *pk = static_cast<const uint8_t *>(packets[p]);
         const uint64_t np = packets_per_part[p];
-        uint32_t last_row = 0;
+        uint32_t last_row = 0, chunk_row_in = 0;
         uint64_t next_chunk = 0;
+        if (b->bsx) enc[p].assign((size_t)np * 16, 0u);
         std::vector<uint8_t> keepflag(np);   // packet passes the carried partial sum through (n == 1 && !new)
         for (uint64_t i = 0; i < np; i++) {
             uint64_t w0;
@@ -171,6 +189,17 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
                 c_look.push_back(L);
                 c_part.push_back(p);
                 next_chunk = i + cnt;
+                chunk_row_in = last_row;
+            }
+            if (b->bsx) {
+                uint8_t pk72[72] = {0};
+                std::memcpy(pk72, pk + i * 64, 64);
+                uint32_t *wout = enc[p].data() + (size_t)i * 16;
+                for (int j = 0; j < B; j++)
+                    wout[j] = (field(pk72, 14 * B + W * j, W) << (32 - W)) | field(pk72, 4 * B + 10 * j, 10);
+                const uint32_t rel = last_row - chunk_row_in + nw;
+                if (rel > 0xFFFu) return h->fail(TKS_EINVAL, "internal: row offset inside a chunk exceeds 12 bits");
+                wout[15] = (uint32_t)(w0 & 0xFFFFu) | ((nw | (n << 1) | (rel << 4)) << 16);
             }
             if (i < kBsSamplePackets && i % kBsSamplePiece == 0) {
                 s_first.push_back((uint32_t)(goff + i));
@@ -196,8 +225,10 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     TKS_CUDA(h, cudaMalloc(&b->d_packets, total * 64));
     goff = 0;
     for (uint32_t p = 0; p < partitions; p++) {
-        TKS_CUDA(h, cudaMemcpy(b->d_packets + goff * 64, packets[p], packets_per_part[p] * 64, cudaMemcpyHostToDevice));
+        const void *src = b->bsx ? static_cast<const void *>(enc[p].data()) : packets[p];
+        TKS_CUDA(h, cudaMemcpy(b->d_packets + goff * 64, src, packets_per_part[p] * 64, cudaMemcpyHostToDevice));
         goff += packets_per_part[p];
+        if (b->bsx) std::vector<uint32_t>().swap(enc[p]);
     }
     auto up = [&](uint32_t **d, const std::vector<uint32_t> &v) -> cudaError_t {
         cudaError_t e = cudaMalloc(d, std::max<size_t>(1, v.size()) * 4);

@@ -299,6 +299,188 @@ __device__ __forceinline__ void bs_process(const uint8_t *__restrict__ packets, 
     }
 }
 
+// --------------------------------------------------------------------------------------------------
+// BSX: the device-side packet format for FIXED_WIDTH <= 22 (one non-zero per 32-bit word).
+//
+// Everything about a packet that does not depend on the query -- where its fields sit, how many row
+// segments it closes, whether it starts a new row, the value of the kernel's row counter when it is
+// reached -- is decided by the matrix alone, so tks_upload_bscsr re-encodes the reference's 512-bit words
+// (fpga_utils.hpp:307-365) once, losslessly for what the kernel consumes, into 16 aligned words:
+//     word j < B :  val_j << (32 - W)  |  col_j                    (W-bit value on top, 10-bit column at the bottom)
+//     word 15    :  x[0..3] (4 bits each, cumulative segment ends)  |  meta << 16
+//     meta       :  bit 0      nw   = (packet index != 0) ? xf : 0          (hpp:278)
+//                   bits 1..3  n    = non-empty segments among the first LFR (hpp:131-142)
+//                   bits 4..15 rel  = row counter before the packet, relative to its chunk, + nw (hpp:280-282)
+// Per query this leaves: B x (mask, shift, gather, multiply-high, add, store), four prefix-sum look-ups, one
+// segmented warp scan for the partial sum carried from packet to packet, and the threshold tests.
+// Semantics are those of bs_process (same candidates, same order, same logs).
+// --------------------------------------------------------------------------------------------------
+template <int W>
+struct BsxFmt {
+    static_assert(W + 10 <= 32, "BSX needs value + column in one word");
+    static constexpr int B = 511 / (W + 14);
+    static constexpr uint32_t M = (1u << W) - 1u;
+    static constexpr uint32_t TOPMASK = ~((1u << (32 - W)) - 1u);
+    static constexpr int META = 15;
+};
+
+template <int W, int LFR, int XREP, int THREADS, bool PREFETCH, typename Sink>
+__device__ __forceinline__ void bsx_process(const uint8_t *__restrict__ packets, uint32_t begin, uint32_t first,
+                                            uint32_t end, uint32_t local0, uint32_t row_base, uint32_t Kp,
+                                            const uint8_t *xsb, uint32_t *ptab, uint32_t (&theta)[LFR],
+                                            uint32_t (&top)[LFR], Sink &sink, uint32_t *p0flags) {
+    using F = BsxFmt<W>;
+    constexpr int B = F::B;
+    constexpr uint32_t M = F::M;
+    constexpr int XS = (XREP == 32) ? 7 : (XREP == 16) ? 6 : (XREP == 8) ? 5 : (XREP == 4) ? 4 : (XREP == 2) ? 3 : 2;
+    static_assert((1 << XS) == 4 * XREP, "XREP must be a power of two <= 32");
+    static_assert(LFR <= 4, "word 15 carries x[0..3]");
+    const unsigned lane = lane_id();
+    // 32-bit shared-memory address of this lane's copy of the query: one multiply-add per gather address
+    const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xsb) + (lane & (uint32_t)(XREP - 1)) * 4u;
+    const unsigned lt = lanemask_lt();
+    uint32_t carry = 0;   // last_row_of_packet_output (hpp:261) entering the iteration
+    uint32_t wa[16], wb[PREFETCH ? 16 : 1];
+    if (PREFETCH) {
+        const uint32_t g0 = begin + lane;
+        if (g0 < end) bs_load_packet(packets + (size_t)g0 * 64u, wa);
+        else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) wa[i] = 0;
+        }
+    }
+    auto iteration = [&](uint32_t base, uint32_t (&w)[16], uint32_t (&wn)[PREFETCH ? 16 : 1]) {
+        const uint32_t g = base + lane;
+        const bool active = g < end;
+        const bool emitting = active && g >= first;
+        if constexpr (PREFETCH) {
+            const uint32_t gn = g + 32;
+            if (gn < end) bs_load_packet(packets + (size_t)gn * 64u, wn);
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) wn[i] = 0;
+            }
+        } else {
+            if (active) bs_load_packet(packets + (size_t)g * 64u, w);
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) w[i] = 0;
+            }
+        }
+        // ---- loops 1 + 2 (hpp:168-220, 104-149): products and their running sums ----
+        uint32_t acc = 0;
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            uint32_t xv;
+            asm("ld.shared.u32 %0, [%1];" : "=r"(xv) : "r"((w[j] & 0x3FFu) * (4u * XREP) + xs_addr));
+            acc += __umulhi(w[j] & F::TOPMASK, xv);   // the table holds xq << 1: exactly (val * xq) >> (W-1)
+            ptab[(j + 1) * THREADS + threadIdx.x] = acc;
+        }
+        const uint32_t mw = w[F::META];
+        uint32_t x[LFR], agg[LFR];
+        {
+            uint32_t prevL = 0;
+#pragma unroll
+            for (int s = 0; s < LFR; s++) {
+                x[s] = (mw >> (4 * s)) & 0xFu;
+                const uint32_t L = ptab[x[s] * THREADS + threadIdx.x];
+                agg[s] = (L - prevL) & M;
+                prevL = L;
+            }
+        }
+        const uint32_t nw = (mw >> 16) & 1u;
+        const uint32_t n = (mw >> 17) & 7u;
+        const uint32_t start_row = row_base + (mw >> 20);   // hpp:282, tabulated at upload
+        // ---- loop 3 (hpp:246-326): the partial sum carried from packet to packet ----
+        // last_out_i = a_i + (keep_i ? last_out_{i-1} : 0):  n == 0 -> (0, nw);  n == 1 -> (agg0, !nw);  n >= 2 -> (agg[n-1], 0)
+        uint32_t a = 0;
+#pragma unroll
+        for (int s = 0; s < LFR; s++) if (n == (uint32_t)(s + 1)) a = agg[s];
+        const bool keep = !active || (n < 2u && ((n ^ nw) & 1u));   // inactive lanes are the identity
+        const unsigned kb = __ballot_sync(0xFFFFFFFFu, keep);
+        // lanes below this one that belong to its run of `keep` packets (segmented inclusive scan by distance)
+        const unsigned brk = ~kb & (lt | (1u << lane));              // non-keep lanes at or below this one
+        const int dist = brk ? (int)lane - (31 - __clz((int)brk)) : (int)lane;
+        uint32_t sa = a;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t ua = __shfl_up_sync(0xFFFFFFFFu, sa, d);
+            if (dist >= d) sa += ua;
+        }
+        // what this packet sees as last_row_of_packet_output: the inclusive value of the previous lane, chained to
+        // the carry of the previous iteration when every lane below passes it through
+        uint32_t pa = __shfl_up_sync(0xFFFFFFFFu, sa, 1);
+        if (lane == 0) pa = 0;
+        const uint32_t prev = (pa + (((~kb & lt) == 0u) ? carry : 0u)) & M;
+        const uint32_t la = __shfl_sync(0xFFFFFFFFu, sa, 31);
+        carry = (la + ((kb == 0xFFFFFFFFu) ? carry : 0u)) & M;
+
+        // ---- loop 4 (hpp:331-389): candidates of the LFR lanes ----
+        uint32_t val[LFR];
+        bool pass[LFR], fin0[LFR];
+        bool anyp = false;
+#pragma unroll
+        for (int j = 0; j < LFR; j++) {
+            bool fin;
+            if (j == 0) {
+                val[0] = prev;
+                fin = nw != 0;
+            } else {
+                val[j] = agg[j - 1];
+                if (j == 1 && nw == 0) val[j] = (val[j] + prev) & M;
+                fin = (x[j - 1] != (j > 1 ? x[j - 2] : 0u)) && (n != (uint32_t)j);
+            }
+            fin0[j] = fin;
+            pass[j] = emitting && fin && (val[j] >= theta[j]);
+            anyp |= pass[j];
+        }
+        if (p0flags && base <= first && first < base + 32 && local0 == 0) {   // warp-uniform: packet 0 of the partition
+            if (g == first) {
+#pragma unroll
+                for (int j = 0; j < LFR; j++) p0flags[j] = fin0[j] ? 1u : 0u;
+            }
+        }
+        if (__any_sync(0xFFFFFFFFu, anyp)) {
+#pragma unroll
+            for (int j = 0; j < LFR; j++) {
+                const unsigned pm = __ballot_sync(0xFFFFFFFFu, pass[j]);
+                if (pm) {
+                    sink.put(j, pass[j], pm, val[j], start_row + (uint32_t)j - 1u);
+                    unsigned rest = pm;
+                    while (rest) {
+                        const int src = __ffs(rest) - 1;
+                        rest &= rest - 1;
+                        top[j] = lane_list_insert(top[j], __shfl_sync(0xFFFFFFFFu, val[j], src), Kp);
+                    }
+                    theta[j] = __shfl_sync(0xFFFFFFFFu, top[j], (int)Kp - 1);
+                }
+            }
+        }
+    };
+    if constexpr (PREFETCH) {
+        for (uint32_t base = begin; base < end; base += 64) {
+            iteration(base, wa, wb);
+            if (base + 32 < end) iteration(base + 32, wb, wa);
+        }
+    } else {
+        for (uint32_t base = begin; base < end; base += 32) iteration(base, wa, wb);
+    }
+}
+
+// verbatim reference packets (BSX = false) or the re-encoded device format (BSX = true, FIXED_WIDTH <= 22)
+template <int W, int LFR, int XREP, int THREADS, bool PREFETCH, bool BSX, typename Sink>
+__device__ __forceinline__ void bs_run(const uint8_t *__restrict__ packets, uint32_t begin, uint32_t first, uint32_t end,
+                                       uint32_t local0, uint32_t row_base, uint32_t Kp, const uint8_t *xsb,
+                                       uint32_t *ptab, uint32_t (&theta)[LFR], uint32_t (&top)[LFR], Sink &sink,
+                                       uint32_t *p0flags) {
+    if constexpr (BSX)
+        bsx_process<W, LFR, XREP, THREADS, PREFETCH>(packets, begin, first, end, local0, row_base, Kp, xsb, ptab, theta, top,
+                                                     sink, p0flags);
+    else
+        bs_process<W, LFR, XREP, THREADS, PREFETCH>(packets, begin, first, end, local0, row_base, Kp, xsb, ptab, theta, top,
+                                                    sink, p0flags);
+}
+
 struct BscsrSample {
     const uint32_t *first, *count, *local0, *lookback, *part;   // sample pieces (64 packets each)
     uint32_t n;
@@ -308,7 +490,7 @@ struct BscsrSample {
     uint32_t *theta_seed;               // [P][LFR]
 };
 
-template <int W, int LFR>
+template <int W, int LFR, bool BSX>
 __global__ void __launch_bounds__(kBsThreads)
 bscsr_sample_kernel(const uint8_t *__restrict__ packets, BscsrSample sm, const uint32_t *__restrict__ xq, uint32_t Kp) {
     __shared__ uint32_t xs[1024];
@@ -324,8 +506,9 @@ bscsr_sample_kernel(const uint8_t *__restrict__ packets, BscsrSample sm, const u
     for (int j = 0; j < LFR; j++) { theta[j] = 0; top[j] = 0; }
     BsTopSink<LFR> sink;
     const uint32_t first = sm.first[piece];
-    bs_process<W, LFR, 1, kBsThreads, false>(packets, first - sm.lookback[piece], first, first + sm.count[piece], sm.local0[piece], 0u, Kp,
-                       reinterpret_cast<const uint8_t *>(xs), ptab, theta, top, sink, nullptr);
+    bs_run<W, LFR, 1, kBsThreads, false, BSX>(packets, first - sm.lookback[piece], first, first + sm.count[piece],
+                                              sm.local0[piece], 0u, Kp, reinterpret_cast<const uint8_t *>(xs), ptab, theta,
+                                              top, sink, nullptr);
 #pragma unroll
     for (int j = 0; j < LFR; j++) sm.piece_top[((size_t)piece * LFR + j) * 32u + lane] = (lane < Kp) ? top[j] : 0u;
     // the last piece of the partition to finish merges the pieces' tops: K-th largest of the sampled prefix
@@ -367,7 +550,7 @@ __host__ __device__ constexpr size_t bscsr_stream_smem(int xrep, int threads) {
     return (size_t)1024 * xrep * 4 + (size_t)16 * threads * 4;
 }
 
-template <int W, int LFR, int XREP, int THREADS, bool PREFETCH>
+template <int W, int LFR, int XREP, int THREADS, bool PREFETCH, bool BSX>
 __global__ void __launch_bounds__(THREADS, (XREP <= 2 && THREADS <= 256) ? 4 : 1)
 bscsr_stream_kernel(const uint8_t *__restrict__ packets, BscsrChunks m, const uint32_t *__restrict__ xq, uint32_t Kp,
                     BscsrLogs logs, const uint32_t *__restrict__ theta_seed, uint32_t *chunk_counter) {
@@ -397,8 +580,9 @@ bscsr_stream_kernel(const uint8_t *__restrict__ packets, BscsrChunks m, const ui
             top[j] = theta[j];   // as if K candidates of that value had been seen: max(seed, own K-th largest)
             sink.lcnt[j] = 0;
         }
-        bs_process<W, LFR, XREP, THREADS, PREFETCH>(packets, first - m.lookback[c], first, first + count, local0, m.row_in[c], Kp,
-                           reinterpret_cast<const uint8_t *>(xs), ptab, theta, top, sink, logs.p0 + (size_t)c * LFR);
+        bs_run<W, LFR, XREP, THREADS, PREFETCH, BSX>(packets, first - m.lookback[c], first, first + count, local0,
+                                                     m.row_in[c], Kp, reinterpret_cast<const uint8_t *>(xs), ptab, theta, top,
+                                                     sink, logs.p0 + (size_t)c * LFR);
         if (lane == 0) {
 #pragma unroll
             for (int j = 0; j < LFR; j++) logs.cnt[(size_t)c * LFR + j] = sink.lcnt[j];

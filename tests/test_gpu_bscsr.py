@@ -39,6 +39,17 @@ def test_cfg1_all_widths(cuda_required, tks, orc, gen, W):
     assert o["idx"].size >= 100
 
 
+@pytest.mark.parametrize("W", [20, 21])
+def test_verbatim_packet_path_for_narrow_widths(cuda_required, tks, orc, gen, W, monkeypatch):
+    """FIXED_WIDTH <= 22 normally runs on the re-encoded BSX device format; TKS_BSCSR_VERBATIM=1 keeps the
+    reference's 512-bit words on the device (the path of the wider formats).  Both must be bit-exact."""
+    monkeypatch.setenv("TKS_BSCSR_VERBATIM", "1")
+    x, y, v = gen.create_sparse_matrix(60000, 1024, 20, "gamma", seed=3)
+    run_both(tks, orc, x, y, v, 60000, 1024, make_query(1024, 12), W=W, P=4)
+    x, y, v = gen.create_sparse_matrix(20000, 1024, 3, "gamma", seed=4)     # LFR overflow drift
+    run_both(tks, orc, x, y, v, 20000, 1024, make_query(1024, 13), W=W)
+
+
 @pytest.mark.parametrize("deg,dist", [(2, "gamma"), (4, "gamma"), (6, "uniform"), (40, "uniform")])
 def test_row_lengths_incl_lfr_overflow_drift(cuda_required, tks, orc, gen, deg, dist):
     """Short rows put more than LFR segments into a packet: the reference's row counter drifts and partial
