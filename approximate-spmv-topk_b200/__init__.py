@@ -10,9 +10,9 @@ The directory name carries a hyphen, so import it through the repo-root shim:
 
     from _pkg import pkg; tks = pkg()          # registers it as `approximate_spmv_topk_b200`
 """
-from . import capi, create_matrices, distributed, sharding, spmv  # noqa: F401
+from . import accuracy, capi, create_matrices, distributed, sharding, spmv  # noqa: F401
 from .spmv import SpMV, SpMVFixed  # noqa: F401
 
 from .distributed import ShardedSpMV  # noqa: F401
 
-__all__ = ["capi", "create_matrices", "distributed", "sharding", "spmv", "SpMV", "SpMVFixed", "ShardedSpMV"]
+__all__ = ["accuracy", "capi", "create_matrices", "distributed", "sharding", "spmv", "SpMV", "SpMVFixed", "ShardedSpMV"]

@@ -50,6 +50,7 @@ SYMBOLS = [
     "tks_read_result", "tks_read_partition_results", "tks_result_keys_device", "tks_merge_keys_device", "tks_merge_keys_batched_device",
     "tks_get_stats", "tks_bscsr_packet_size", "tks_fixed32_from_double", "tks_fixedW_from_fixed32",
     "tks_pack_bscsr", "tks_read_mtx", "tks_coo2csr",
+    "tks_cache_write_csr", "tks_cache_read_csr", "tks_cache_write_bscsr", "tks_cache_read_bscsr",
 ]
 
 _lib = None
@@ -184,3 +185,60 @@ def coo2csr(x, y, val, rows, cols):
     out = np.zeros(x.size, np.float32)
     check(lib().tks_coo2csr(_ptr(x), _ptr(y), _ptr(val), x.size, rows, cols, _ptr(ptr), _ptr(idx), _ptr(out)))
     return ptr, idx, out
+
+
+# ---- binary matrix cache --------------------------------------------------------------
+
+def cache_write_csr(path, ptr, idx, val, cols):
+    ptr = np.ascontiguousarray(ptr, np.uint64)
+    idx = np.ascontiguousarray(idx, np.uint32)
+    val = np.ascontiguousarray(val, np.float32)
+    L = lib()
+    L.tks_cache_write_csr.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    check(L.tks_cache_write_csr(str(path).encode(), ptr.size - 1, int(cols), idx.size, _ptr(ptr), _ptr(idx), _ptr(val)))
+
+
+def cache_read_csr(path):
+    """Returns (rows, cols, ptr uint64, idx uint32, val float32)."""
+    L = lib()
+    L.tks_cache_read_csr.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
+    rows, cols, nnz = C.c_uint64(), C.c_uint32(), C.c_uint64()
+    p = str(path).encode()
+    check(L.tks_cache_read_csr(p, C.byref(rows), C.byref(cols), C.byref(nnz), None, None, None))
+    ptr = np.zeros(rows.value + 1, np.uint64)
+    idx = np.zeros(nnz.value, np.uint32)
+    val = np.zeros(nnz.value, np.float32)
+    check(L.tks_cache_read_csr(p, C.byref(rows), C.byref(cols), C.byref(nnz), _ptr(ptr), _ptr(idx), _ptr(val)))
+    return rows.value, cols.value, ptr, idx, val
+
+
+def cache_write_bscsr(path, rows, cols, fixed_width, packets, ppp, first_row, npp):
+    packets = np.ascontiguousarray(packets, np.uint64)
+    ppp = np.ascontiguousarray(ppp, np.uint64)
+    first_row = np.ascontiguousarray(first_row, np.uint32)
+    npp = np.ascontiguousarray(npp, np.uint64)
+    L = lib()
+    L.tks_cache_write_bscsr.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
+    check(L.tks_cache_write_bscsr(str(path).encode(), int(rows), int(cols), int(fixed_width), ppp.size, _ptr(ppp),
+                                  _ptr(first_row), _ptr(npp), _ptr(packets)))
+
+
+def cache_read_bscsr(path):
+    """Returns (rows, cols, fixed_width, packets uint64[total,8], packets_per_part, first_row, nnz_per_part)."""
+    L = lib()
+    L.tks_cache_read_bscsr.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int),
+                                       C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+    rows, cols, W, P, total = C.c_uint32(), C.c_uint32(), C.c_int(), C.c_uint32(), C.c_uint64()
+    p = str(path).encode()
+    check(L.tks_cache_read_bscsr(p, C.byref(rows), C.byref(cols), C.byref(W), C.byref(P), C.byref(total), None, None,
+                                 None, None))
+    ppp = np.zeros(P.value, np.uint64)
+    first = np.zeros(P.value, np.uint32)
+    npp = np.zeros(P.value, np.uint64)
+    packets = np.zeros((total.value, 8), np.uint64)
+    check(L.tks_cache_read_bscsr(p, C.byref(rows), C.byref(cols), C.byref(W), C.byref(P), C.byref(total), _ptr(ppp),
+                                 _ptr(first), _ptr(npp), _ptr(packets)))
+    return rows.value, cols.value, W.value, packets, ppp, first, npp

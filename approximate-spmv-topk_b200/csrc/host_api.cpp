@@ -9,6 +9,7 @@
 #include "../../include/topkspmv.h"
 #include "../host/bscsr_packer.hpp"
 #include "../host/fixed_point.hpp"
+#include "../host/matrix_cache.hpp"
 #include "../host/mtx_reader.hpp"
 
 static thread_local std::string g_host_error;
@@ -90,6 +91,79 @@ int tks_coo2csr(const uint32_t *x, const uint32_t *y, const float *val, uint64_t
         g_host_error = "Error: Index out of bounds!";
         return TKS_EINVAL;
     }
+    return TKS_OK;
+}
+
+int tks_cache_write_csr(const char *path, uint64_t rows, uint32_t cols, uint64_t nnz, const uint64_t *ptr64,
+                        const uint32_t *idx, const float *val) {
+    if (!path || !ptr64 || (nnz && (!idx || !val))) { g_host_error = "null argument"; return TKS_EINVAL; }
+    if (ptr64[rows] != nnz) { g_host_error = "ptr[rows] != nnz"; return TKS_EINVAL; }
+    tkshost::CacheHeader h{};
+    h.kind = tkshost::kCacheCsr; h.cols = cols; h.rows = rows; h.nnz = nnz;
+    std::string err;
+    if (tkshost::cache_write(path, h, {{ptr64, (rows + 1) * 8}, {idx, nnz * 4}, {val, nnz * 4}}, &err) != 0) {
+        g_host_error = err; return TKS_EIO;
+    }
+    return TKS_OK;
+}
+
+int tks_cache_read_csr(const char *path, uint64_t *rows, uint32_t *cols, uint64_t *nnz, uint64_t *ptr64, uint32_t *idx,
+                       float *val) {
+    if (!path || !rows || !cols || !nnz) { g_host_error = "null argument"; return TKS_EINVAL; }
+    tkshost::CacheHeader h{};
+    FILE *f = nullptr;
+    std::string err;
+    if (tkshost::cache_open(path, tkshost::kCacheCsr, &h, &f, &err) != 0) { g_host_error = err; return TKS_EIO; }
+    if (h.payload_bytes != (h.rows + 1) * 8 + h.nnz * 8) { std::fclose(f); g_host_error = std::string(path) + ": inconsistent header"; return TKS_EIO; }
+    *rows = h.rows; *cols = h.cols; *nnz = h.nnz;
+    if (!ptr64 && !idx && !val) { std::fclose(f); return TKS_OK; }          // size query
+    if (!ptr64 || (h.nnz && (!idx || !val))) { std::fclose(f); g_host_error = "null output array"; return TKS_EINVAL; }
+    if (tkshost::cache_read_sections(f, h, {{ptr64, (h.rows + 1) * 8}, {idx, h.nnz * 4}, {val, h.nnz * 4}}, path, &err) != 0) {
+        g_host_error = err; return TKS_EIO;
+    }
+    if (ptr64[h.rows] != h.nnz) { g_host_error = std::string(path) + ": ptr[rows] != nnz"; return TKS_EIO; }
+    return TKS_OK;
+}
+
+int tks_cache_write_bscsr(const char *path, uint32_t rows, uint32_t cols, int fixed_width, uint32_t partitions,
+                          const uint64_t *packets_per_part, const uint32_t *first_row, const uint64_t *nnz_per_part,
+                          const void *packets) {
+    if (!path || !packets_per_part || !first_row || !nnz_per_part || !packets) { g_host_error = "null argument"; return TKS_EINVAL; }
+    uint64_t total = 0, nnz = 0;
+    for (uint32_t p = 0; p < partitions; p++) { total += packets_per_part[p]; nnz += nnz_per_part[p]; }
+    tkshost::CacheHeader h{};
+    h.kind = tkshost::kCacheBscsr; h.cols = cols; h.rows = rows; h.nnz = nnz; h.aux0 = partitions; h.aux1 = (uint64_t)fixed_width;
+    std::string err;
+    if (tkshost::cache_write(path, h, {{packets_per_part, (size_t)partitions * 8}, {first_row, (size_t)partitions * 4},
+                                       {nnz_per_part, (size_t)partitions * 8}, {packets, total * 64}}, &err) != 0) {
+        g_host_error = err; return TKS_EIO;
+    }
+    return TKS_OK;
+}
+
+int tks_cache_read_bscsr(const char *path, uint32_t *rows, uint32_t *cols, int *fixed_width, uint32_t *partitions,
+                         uint64_t *total_packets, uint64_t *packets_per_part, uint32_t *first_row,
+                         uint64_t *nnz_per_part, void *packets) {
+    if (!path || !rows || !cols || !fixed_width || !partitions || !total_packets) { g_host_error = "null argument"; return TKS_EINVAL; }
+    tkshost::CacheHeader h{};
+    FILE *f = nullptr;
+    std::string err;
+    if (tkshost::cache_open(path, tkshost::kCacheBscsr, &h, &f, &err) != 0) { g_host_error = err; return TKS_EIO; }
+    const uint64_t P = h.aux0;
+    if (P == 0 || P > 4096 || h.payload_bytes < P * 20 || (h.payload_bytes - P * 20) % 64 != 0) {
+        std::fclose(f); g_host_error = std::string(path) + ": inconsistent header"; return TKS_EIO;
+    }
+    *rows = (uint32_t)h.rows; *cols = h.cols; *fixed_width = (int)h.aux1; *partitions = (uint32_t)P;
+    *total_packets = (h.payload_bytes - P * 20) / 64;
+    if (!packets_per_part && !first_row && !nnz_per_part && !packets) { std::fclose(f); return TKS_OK; }   // size query
+    if (!packets_per_part || !first_row || !nnz_per_part || !packets) { std::fclose(f); g_host_error = "null output array"; return TKS_EINVAL; }
+    if (tkshost::cache_read_sections(f, h, {{packets_per_part, P * 8}, {first_row, P * 4}, {nnz_per_part, P * 8},
+                                            {packets, *total_packets * 64}}, path, &err) != 0) {
+        g_host_error = err; return TKS_EIO;
+    }
+    uint64_t total = 0;
+    for (uint64_t p = 0; p < P; p++) total += packets_per_part[p];
+    if (total != *total_packets) { g_host_error = std::string(path) + ": packet counts do not add up"; return TKS_EIO; }
     return TKS_OK;
 }
 

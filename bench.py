@@ -515,7 +515,6 @@ def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
     src = tks.SpMV(num_cols=cols, k=K)
     src.generate_synthetic(rows_total, cols, wl["deg"], wl["dist"], seed=SEED)
     ptr, idx, val = src.download_csr()
-    src.close()
     deg = np.diff(ptr.astype(np.int64))
     x = np.repeat(np.arange(rows_total, dtype=np.uint32), deg)
     nnz = int(ptr[-1])
@@ -561,6 +560,19 @@ def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
             e2e_ms.append(dt)
             main_ms.append(eng.stats().last_main_kernel_ms)
     assert np.array_equal(i_e, i_last) and np.array_equal(v_e, v_last), "e2e and resident results differ"
+    # top-K recall of the approximate design (20-bit fixed point, 32 partitions x local K=8) against the exact fp32
+    # engine on the same matrix and queries, with the reference's metrics (plot_errors.py)
+    recalls = []
+    for i in range(args.warmup, args.warmup + min(args.steps, 5)):
+        src.reset(queries[i])
+        src()
+        ev, ei, _ = src.read_result()
+        eng.reset(q32[i])
+        eng.run_timed(K)
+        av, ai = eng.read_result()
+        recalls.append(tks.accuracy.report(ei, ev, ai, av.astype(np.float64) / 2.0 ** 31))
+    src.close()
+    recall = {k2: float(np.mean([r[k2] for r in recalls if k2 in r])) for k2 in recalls[0]} if recalls else None
     e2e_ms_step = sum(e2e_ms) / len(e2e_ms)
     main = sum(main_ms) / len(main_ms)
     st = eng.stats()
@@ -601,7 +613,8 @@ def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
             "e2e": {"value": nnz / (e2e_ms_step * 1e-3), "unit": "nnz/s", "ms_per_step": e2e_ms_step,
                     "h2d_bytes_per_step": cols * 4, "d2h_bytes_per_step": P * Kp * 128,
                     "api": "SpMVFixed.reset(host vec) -> operator() -> read_result (host merge of P x K x LFR candidates)"},
-            "gpu_launches": args.steps * 3, "results_returned": int(i_last.size), "clocks": clocks}
+            "gpu_launches": args.steps * 3, "results_returned": int(i_last.size), "recall_vs_exact_fp32": recall,
+            "clocks": clocks}
     print(json.dumps(line), flush=True)
     eng.close()
 

@@ -189,6 +189,21 @@ int tks_read_mtx(const char *path, int zero_indexed, int sort_tuples, int ignore
 int tks_coo2csr(const uint32_t *x, const uint32_t *y, const float *val, uint64_t nnz, uint32_t rows,
                 uint32_t cols, uint32_t *ptr, uint32_t *idx, float *out_val);
 
+/* ---- binary matrix cache: skip re-parsing the MTX text (readMtx, utils.hpp:474-520) and
+ * re-packing the BS-CSR packets (host_spmv_bscsr.cpp:133-248) on every run of a sweep.  Versioned,
+ * checksummed container; truncated or altered files fail with TKS_EIO.  Read calls follow the two-call
+ * protocol: all output arrays NULL only fills the sizes.                                           */
+int tks_cache_write_csr(const char *path, uint64_t rows, uint32_t cols, uint64_t nnz, const uint64_t *ptr64,
+                        const uint32_t *idx, const float *val);
+int tks_cache_read_csr(const char *path, uint64_t *rows, uint32_t *cols, uint64_t *nnz, uint64_t *ptr64,
+                       uint32_t *idx, float *val);
+int tks_cache_write_bscsr(const char *path, uint32_t rows, uint32_t cols, int fixed_width, uint32_t partitions,
+                          const uint64_t *packets_per_part, const uint32_t *first_row,
+                          const uint64_t *nnz_per_part, const void *packets);
+int tks_cache_read_bscsr(const char *path, uint32_t *rows, uint32_t *cols, int *fixed_width, uint32_t *partitions,
+                         uint64_t *total_packets, uint64_t *packets_per_part, uint32_t *first_row,
+                         uint64_t *nnz_per_part, void *packets);
+
 #ifdef __cplusplus
 }
 #endif
