@@ -77,6 +77,7 @@ void launch_stream_fmt(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStrea
     if (W == 20 && LFR == 4 && BSX && b->variant == 1) launch_stream_variant<20, 4, 1, 256, false, BSX && W == 20>(h, b, m, s);
     else if (W == 20 && LFR == 4 && BSX && b->variant == 16) launch_stream_variant<20, 4, 16, 1024, false, BSX && W == 20>(h, b, m, s);
     else if (W == 20 && LFR == 4 && BSX && b->variant == 33) launch_stream_variant<20, 4, 32, 768, false, BSX && W == 20>(h, b, m, s);
+    else if (W == 20 && LFR == 4 && BSX && b->variant == 34) launch_stream_variant<20, 4, 32, 1024, false, BSX && W == 20>(h, b, m, s);
     else launch_stream_variant<W, LFR, kBsDefaultXrep, kBsDefaultThreads, true, BSX>(h, b, m, s);
     if (prof) cudaEventRecord(h->evm1, s);
 }
@@ -151,6 +152,7 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     std::vector<uint32_t> c_first, c_count, c_local0, c_row_in, c_look, c_part, part_begin(partitions + 1, 0);
     std::vector<uint32_t> s_first, s_count, s_local0, s_look, s_part, s_part_begin(partitions + 1, 0);
     uint64_t goff = 0;
+    const uint64_t tail_begin = total - total / 10u;   // last 10 % of the stream
     for (uint32_t p = 0; p < partitions; p++) {
         part_begin[p] = (uint32_t)c_first.size();
         s_part_begin[p] = (uint32_t)s_first.size();
@@ -181,7 +183,10 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
                 uint32_t L = 0;
                 if (i > 0) { L = 1; while (i - L > 0 && keepflag[i - L]) L++; }
                 // look-back + chunk = a whole number of 32-packet warp iterations (no extra iteration for the look-back)
-                const uint64_t cnt = std::min<uint64_t>(b->chunk_cap - (L % 32u), np - i);
+                // the chunks processed last are four times smaller: the persistent warps then run dry within a
+                // few iterations of each other instead of up to a whole 512-packet chunk apart
+                const uint32_t cap_here = (goff + i >= tail_begin) ? b->chunk_cap / 4u : b->chunk_cap;
+                const uint64_t cnt = std::min<uint64_t>(cap_here - (L % 32u), np - i);
                 c_first.push_back((uint32_t)(goff + i));
                 c_count.push_back((uint32_t)cnt);
                 c_local0.push_back((uint32_t)i);

@@ -366,6 +366,12 @@ __device__ __forceinline__ void bsx_process(const uint8_t *__restrict__ packets,
 #pragma unroll
                 for (int i = 0; i < 16; i++) w[i] = 0;
             }
+            // no second register set: pull the packets of the iteration after next into L2 instead
+            if (g + 64 < end) {
+                const uint8_t *pf = packets + (size_t)(g + 64) * 64u;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 32));
+            }
         }
         // ---- loops 1 + 2 (hpp:168-220, 104-149): products and their running sums ----
         uint32_t acc = 0;

@@ -5,8 +5,11 @@
 
 A "step" = one Top-K SpMV query over the resident matrix:
   N = 1   workload cfg2: synthetic 10M x 1024, gamma ~20 nnz/row, fp32 CSR, single query, k = 100
-  N > 1   workload cfg4: synthetic 200M x 1024, uniform ~40 nnz/row, fp32, k = 100, rows sharded evenly
-          over the N ranks, K candidates per rank all-gathered (NCCL) and merged on every rank
+  N > 1   the same workload weak-scaled: every rank holds a 10M-row shard of an (N x 10M) x 1024 matrix of the
+          same law (per-GPU work fixed, "scaling": "weak"), K candidates per rank all-gathered (NCCL) and
+          merged on every rank -- so that the per-N values of one command are comparable
+  --workload cfg4: synthetic 200M x 1024, uniform ~40 nnz/row, fp32, k = 100, rows sharded evenly over the
+          N ranks (fixed total work, "scaling": "strong"); fits one GPU too (64 GB)
   --workload cfg3: the cfg2 matrix as 20-bit BS-CSR packets, 32 partitions x local K=8 (FPGA semantics)
 `value` = non-zeros processed per second by the whole job with the matrix and the queries resident in HBM;
 `e2e`   = the same through the reference-facing calls reset(vec) / operator() / read_result with HOST
@@ -162,7 +165,7 @@ def reference_arm(args):
         return
     from _pkg import pkg
     tks = pkg()
-    wl = WORKLOADS[args.workload or ("cfg2" if args.gpus == 1 else "cfg4")]
+    wl = WORKLOADS[args.workload or "cfg2"]
     sample_rows = min(wl["rows"], args.ref_rows)
     x, y, v = tks.create_matrices.create_sparse_matrix(sample_rows, wl["cols"], wl["deg"], wl["dist"], seed=SEED)
     ptr = tks.create_matrices.csr_from_coo(x, sample_rows)
@@ -178,8 +181,8 @@ def reference_arm(args):
               f"(sparse_dot_topn is absent from the image)")
     line = {"impl": "reference", "metric": "topk_spmv_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": args.gpus,
             "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "k": K},
+            "scaling": "weak" if (args.workload or "cfg2") == "cfg2" else "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": wl["name"], "k": K},
             "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -206,9 +209,10 @@ def ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    wl_key = args.workload or ("cfg2" if world == 1 else "cfg4")
+    wl_key = args.workload or "cfg2"
     wl = WORKLOADS[wl_key]
-    rows_total = args.rows or wl["rows"]
+    weak = wl_key == "cfg2"                          # cfg2: 10M rows PER RANK; cfg4 / cfg5: the stated total, sharded
+    rows_total = (args.rows or wl["rows"]) * (world if weak else 1)
     cols = wl["cols"]
     shards = tks.sharding.plan_row_shards_even(rows_total, world)
     r0, r1 = shards[rank]
@@ -316,9 +320,10 @@ def ours(args):
     if rank == 0:
         line = {"metric": "topk_spmv_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": wl["name"], "rows": rows_total, "cols": cols, "nnz": nnz_total, "k": K,
-                           "sharding": f"rows/{world}" if world > 1 else "none",
+                "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["name"] + (f", weak-scaled: {world} shards of {wl['rows']} rows" if weak and world > 1 else ""),
+                           "rows": rows_total, "cols": cols, "nnz": nnz_total, "k": K,
+                           "sharding": f"rows/{world}, K-candidate all-gather + merge on every rank" if world > 1 else "none",
                            "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * 8 / 1e9),
                            "generator_s": round(gen_s, 2)},
                 "roofline": roof,
