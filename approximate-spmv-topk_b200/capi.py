@@ -24,7 +24,8 @@ class TksConfig(C.Structure):
                 ("local_k", C.c_int32), ("limited_finished_rows", C.c_int32), ("max_cols", C.c_int32),
                 ("tie_break", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_int32),
                 ("chunk_nnz", C.c_int32), ("profile_kernels", C.c_int32), ("batch_mode", C.c_int32),
-                ("batch_pool_cap", C.c_int32), ("batch_fma", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("batch_pool_cap", C.c_int32), ("batch_fma", C.c_int32), ("fixed_drift_free", C.c_int32),
+                ("reserved", C.c_int32 * 1)]
 
 
 class TksStats(C.Structure):

@@ -141,6 +141,10 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     // FIXED_WIDTH <= 22: value + column fit one word -> re-encode into the BSX device format (bscsr_topk.cuh);
     // TKS_BSCSR_VERBATIM=1 keeps the reference's words (the path the wider formats always take)
     b->bsx = (W + 10 <= 32) && !(std::getenv("TKS_BSCSR_VERBATIM") && std::atoi(std::getenv("TKS_BSCSR_VERBATIM")) != 0);
+    const bool drift_free = h->cfg.fixed_drift_free != 0;
+    if (drift_free) b->chunk_cap = 256;   // up to B rows can finish per packet: keeps the 12-bit in-chunk row offset in range
+    if (drift_free && (!b->bsx || LFR < 2))
+        return h->fail(TKS_EINVAL, "fixed_drift_free needs fixed_width <= 22 (the re-encoded device format) and limited_finished_rows >= 2");
     std::vector<std::vector<uint32_t>> enc(b->bsx ? partitions : 0);
     auto field = [](const uint8_t *pk72, int pos, int len) -> uint32_t {
         uint64_t v;
@@ -179,6 +183,30 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
             uint32_t n = 0, pe = 0;
             for (int s = 0; s < LFR; s++) { uint32_t xs = (uint32_t)((w0 >> (4 * s)) & 0xF); n += (xs != pe); pe = xs; }
             const uint32_t nw = (i != 0) ? xf : 0u;
+            // drift-free mode (not the reference, see topkspmv.h): a packet with more than LFR row segments keeps its
+            // first LFR-1 segments, has the values of the rows that finish without a lane zeroed, and ends with ONE
+            // segment that spans them and the true last segment -- so the unchanged kernel carries the true partial sum;
+            // its row counter advances by the true number of finished rows
+            uint32_t nseg = 0, zero_from = 0, zero_to = 0;
+            uint64_t xw = w0;
+            if (drift_free) {
+                uint32_t st = 0, ends[16];
+                for (int s = 0; s < B; s++) {
+                    uint32_t xs = (uint32_t)((w0 >> (4 * s)) & 0xF);
+                    if (xs != st) ends[nseg++] = xs;
+                    st = xs;
+                }
+                if (nseg > (uint32_t)LFR) {
+                    zero_from = ends[LFR - 2];        // end of segment LFR-2 = start of the first row without a lane
+                    zero_to = ends[nseg - 2];         // start of the true last segment
+                    xw = 0;
+                    for (int s = 0; s < 16; s++) {
+                        const uint32_t e = (s < LFR - 1) ? ends[s] : ends[nseg - 1];
+                        xw |= (uint64_t)e << (4 * s);
+                    }
+                }
+            }
+            const uint32_t rows_done = (drift_free && nseg > (uint32_t)LFR) ? nseg : n;
             if (i == next_chunk) {
                 uint32_t L = 0;
                 if (i > 0) { L = 1; while (i - L > 0 && keepflag[i - L]) L++; }
@@ -200,11 +228,13 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
                 uint8_t pk72[72] = {0};
                 std::memcpy(pk72, pk + i * 64, 64);
                 uint32_t *wout = enc[p].data() + (size_t)i * 16;
-                for (int j = 0; j < B; j++)
-                    wout[j] = (field(pk72, 14 * B + W * j, W) << (32 - W)) | field(pk72, 4 * B + 10 * j, 10);
+                for (int j = 0; j < B; j++) {
+                    const uint32_t v = ((uint32_t)j >= zero_from && (uint32_t)j < zero_to) ? 0u : field(pk72, 14 * B + W * j, W);
+                    wout[j] = (v << (32 - W)) | field(pk72, 4 * B + 10 * j, 10);
+                }
                 const uint32_t rel = last_row - chunk_row_in + nw;
                 if (rel > 0xFFFu) return h->fail(TKS_EINVAL, "internal: row offset inside a chunk exceeds 12 bits");
-                wout[15] = (uint32_t)(w0 & 0xFFFFu) | ((nw | (n << 1) | (rel << 4)) << 16);
+                wout[15] = (uint32_t)(xw & 0xFFFFu) | ((nw | (n << 1) | (rel << 4)) << 16);
             }
             if (i < kBsSamplePackets && i % kBsSamplePiece == 0) {
                 s_first.push_back((uint32_t)(goff + i));
@@ -215,7 +245,7 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
                 s_look.push_back(L);
                 s_part.push_back(p);
             }
-            last_row += n + nw - 1u;
+            last_row += rows_done + nw - 1u;
             keepflag[i] = (n == 1 && nw == 0) || (n == 0 && nw != 0);
         }
         goff += np;

@@ -153,11 +153,11 @@ class SpMVFixed(_Base):
     x, y: row-sorted COO; val32 / vec32: raw ap_ufixed<32,1> words (real_type_inout)."""
 
     def __init__(self, x, y, val32, num_rows, num_cols, vec32=None, k=100, fixed_width=20, partitions=32, local_k=8,
-                 limited_finished_rows=4, device=0, profile_kernels=False):
+                 limited_finished_rows=4, device=0, profile_kernels=False, drift_free=False):
         cfg = capi.default_config(mode=capi.MODE_FIXED_BSCSR, device=device, fixed_width=fixed_width,
                                   partitions=partitions, local_k=local_k,
                                   limited_finished_rows=limited_finished_rows, tie_break=capi.TIE_HIGHER_INDEX,
-                                  profile_kernels=int(profile_kernels))
+                                  profile_kernels=int(profile_kernels), fixed_drift_free=int(drift_free))
         self._create(cfg)
         self.k = k
         self.num_rows, self.num_cols = int(num_rows), int(num_cols)

@@ -64,7 +64,11 @@ typedef struct tks_config {
     int32_t batch_pool_cap;        /* candidate keys per query in batched mode (0 = 32768)     */
     int32_t batch_fma;             /* batched mode: 1 = fused multiply-add (scores no longer   */
                                    /* bit-identical to the sequential fp32 gold)               */
-    int32_t reserved[2];
+    int32_t fixed_drift_free;      /* BS-CSR mode, FIXED_WIDTH <= 22 and LFR >= 2: 1 = repair the reference's    */
+                                   /* row-counter drift: packets with more than LFR row segments   */
+                                   /* advance the row counter by the true row count and carry the true last      */
+                                   /* partial sum; 0 = the reference's semantics, bit for bit (default)          */
+    int32_t reserved[1];
 } tks_config;
 
 typedef struct tks_handle tks_handle;

@@ -301,10 +301,17 @@ static int orc_argmin(const uint32_t *res, int K) {
  * Column indices >= MAX_COLS cannot occur (10-bit field); a column >= cols
  * reads an entry of the URAM copy that COPY_INPUT never wrote; the static
  * array is zero-initialised, so it reads 0.                                  */
-ORC_API void orc_bscsr_partition(const uint64_t *packets, uint64_t npk,
-                                 const uint32_t *xq32, uint32_t cols,
-                                 int W, int Kp, int LFR,
-                                 uint32_t *out_idx, uint32_t *out_val) {
+/* drift_free != 0 is NOT the reference: it is the stated repair of SURVEY 7-H2 that the engine offers as
+ * TKS fixed_drift_free.  Two rules change, both only visible in packets with more than LFR row segments:
+ *   (1) the row counter advances by the TRUE number of rows that finish in the packet (all B segment-end
+ *       fields), so reported row indices never drift;
+ *   (2) the partial sum carried to the next packet is that of the packet's true last segment (the reference
+ *       carries agg[LFR-1], the sum of a row that has already finished).
+ * Rows that finish in such a packet without a lane (segments LFR-1 .. last-1) are still not offered.       */
+ORC_API void orc_bscsr_partition_ex(const uint64_t *packets, uint64_t npk,
+                                    const uint32_t *xq32, uint32_t cols,
+                                    int W, int Kp, int LFR, int drift_free,
+                                    uint32_t *out_idx, uint32_t *out_val) {
     const int B = orc_packet_size(W);
     const int F = W - 1;
     const uint64_t M = (W == 32) ? 0xFFFFFFFFull : ((1ull << W) - 1ull);
@@ -350,6 +357,18 @@ ORC_API void orc_bscsr_partition(const uint64_t *packets, uint64_t npk,
         for (int j = 0; j <= LFR; j++) { al[j] = 0; fin[j] = 0; }
         uint32_t nw = (i != 0) ? xf : 0u;
         uint32_t finished_rows_num = n + nw - 1u;          /* int_type arithmetic, wraps */
+        uint32_t nseg = 0, last_sum = 0;
+        if (drift_free) {
+            uint32_t st = 0, last_st = 0, last_en = 0;
+            for (int s2 = 0; s2 < B; s2++) {
+                if (x[s2] != st) { nseg++; last_st = st; last_en = x[s2]; }
+                st = x[s2];
+            }
+            uint64_t a2 = 0;
+            for (uint32_t j = last_st; j < last_en; j++) a2 = (a2 + pw[j]) & M;
+            last_sum = (uint32_t)a2;
+            if (nseg > (uint32_t)LFR) finished_rows_num = nseg + nw - 1u;
+        }
         uint32_t start_row = last_row + nw;
         last_row += finished_rows_num;
         al[1] = agg[0];
@@ -365,6 +384,7 @@ ORC_API void orc_bscsr_partition(const uint64_t *packets, uint64_t npk,
             al[0] = last_out; fin[0] = 1;
         }
         last_out = al[n];
+        if (drift_free && nseg > (uint32_t)LFR) last_out = last_sum;
 
         /* loop 4 (:366-389) */
         for (int j = 0; j < LFR; j++) {
@@ -388,6 +408,13 @@ ORC_API void orc_bscsr_partition(const uint64_t *packets, uint64_t npk,
             out_val[16 * t + q] = vv;
         }
     }
+}
+
+ORC_API void orc_bscsr_partition(const uint64_t *packets, uint64_t npk,
+                                 const uint32_t *xq32, uint32_t cols,
+                                 int W, int Kp, int LFR,
+                                 uint32_t *out_idx, uint32_t *out_val) {
+    orc_bscsr_partition_ex(packets, npk, xq32, cols, W, Kp, LFR, 0, out_idx, out_val);
 }
 
 /* host_spmv_bscsr.cpp:399-448 read_result + evaluation_utils.hpp:40-62.

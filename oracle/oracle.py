@@ -61,6 +61,8 @@ def lib() -> C.CDLL:
         L.orc_pack_query.argtypes = [_u32p, C.c_uint32, C.c_int, _u64p]
         L.orc_bscsr_partition.argtypes = [_u64p, C.c_uint64, _u32p, C.c_uint32, C.c_int, C.c_int, C.c_int,
                                           _u32p, _u32p]
+        L.orc_bscsr_partition_ex.argtypes = [_u64p, C.c_uint64, _u32p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             _u32p, _u32p]
         L.orc_read_result.argtypes = [C.c_int, C.c_int, C.c_int, _u32p, _u32p, _u32p, _u32p, _u32p]
         L.orc_read_result.restype = C.c_uint32
         L.orc_gold_topk_fx32.argtypes = [_u32p, _u32p, _u32p, C.c_uint64, _u32p, C.c_int, _u32p, _u32p]
@@ -189,9 +191,10 @@ def pack_query(vec32, W):
     return out
 
 
-def bscsr_kernel(packed, vec32, Kp=8, LFR=4):
+def bscsr_kernel(packed, vec32, Kp=8, LFR=4, drift_free=False):
     """spmv_bscsr_top_k_multicore.{hpp,cpp}: all partitions, reference result layout.
-    Returns (idx_words[P,Kp,16], val_words[P,Kp,16])."""
+    Returns (idx_words[P,Kp,16], val_words[P,Kp,16]).  drift_free=True is NOT the reference: it is the
+    engine's stated repair of the row-counter drift (see orc_bscsr_partition_ex)."""
     L = lib()
     vec32 = _c(vec32, np.uint32)
     P, W = packed["P"], packed["W"]
@@ -201,7 +204,7 @@ def bscsr_kernel(packed, vec32, Kp=8, LFR=4):
         pk = np.ascontiguousarray(packed["packets"][p]).reshape(-1)
         oi = np.zeros(Kp * 16, np.uint32)
         ov = np.zeros(Kp * 16, np.uint32)
-        L.orc_bscsr_partition(pk, packed["packets"][p].shape[0], vec32, vec32.size, W, Kp, LFR, oi, ov)
+        L.orc_bscsr_partition_ex(pk, packed["packets"][p].shape[0], vec32, vec32.size, W, Kp, LFR, int(drift_free), oi, ov)
         idx_w[p] = oi.reshape(Kp, 16)
         val_w[p] = ov.reshape(Kp, 16)
     return idx_w, val_w
@@ -217,12 +220,12 @@ def read_result(idx_w, val_w, first_row, B):
     return ri[:n].copy(), rv[:n].copy()
 
 
-def bscsr_topk(row, col, val_f64, num_rows, vec_f32, P=32, W=20, Kp=8, LFR=4):
+def bscsr_topk(row, col, val_f64, num_rows, vec_f32, P=32, W=20, Kp=8, LFR=4, drift_free=False):
     """Whole FPGA-mode pipeline on the CPU: quantise, pack, kernel, merge."""
     val32 = fx32_from_double(val_f64)
     vec32 = query_fx32_from_f32(vec_f32)
     packed = pack_bscsr(row, col, val32, num_rows, P, W)
-    idx_w, val_w = bscsr_kernel(packed, vec32, Kp, LFR)
+    idx_w, val_w = bscsr_kernel(packed, vec32, Kp, LFR, drift_free)
     ri, rv = read_result(idx_w, val_w, packed["first_row"], packed["B"])
     return dict(idx=ri, val=rv, idx_words=idx_w, val_words=val_w, packed=packed, vec32=vec32, val32=val32)
 

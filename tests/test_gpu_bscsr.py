@@ -9,16 +9,16 @@ from conftest import make_query
 pytestmark = pytest.mark.gpu
 
 
-def run_both(tks, orc, x, y, v, rows, cols, vec, k=100, W=20, P=32, Kp=8, LFR=4):
-    o = orc.bscsr_topk(x, y, v, rows, vec, P=P, W=W, Kp=Kp, LFR=LFR)
+def run_both(tks, orc, x, y, v, rows, cols, vec, k=100, W=20, P=32, Kp=8, LFR=4, drift_free=False):
+    o = orc.bscsr_topk(x, y, v, rows, vec, P=P, W=W, Kp=Kp, LFR=LFR, drift_free=drift_free)
     with tks.SpMVFixed(x, y, o["val32"], rows, cols, vec32=o["vec32"], k=k, fixed_width=W, partitions=P,
-                       local_k=Kp, limited_finished_rows=LFR) as f:
+                       local_k=Kp, limited_finished_rows=LFR, drift_free=drift_free) as f:
         f()
         gv, gi = f.read_result()
         iw, vw = f.read_partition_results()
         # a second query on the same handle (reset path)
         vec2 = make_query(cols, 4242)
-        o2 = orc.bscsr_topk(x, y, v, rows, vec2, P=P, W=W, Kp=Kp, LFR=LFR)
+        o2 = orc.bscsr_topk(x, y, v, rows, vec2, P=P, W=W, Kp=Kp, LFR=LFR, drift_free=drift_free)
         f.reset(o2["vec32"])
         f()
         gv2, gi2 = f.read_result()
@@ -56,6 +56,45 @@ def test_row_lengths_incl_lfr_overflow_drift(cuda_required, tks, orc, gen, deg, 
     sums are mis-carried; the engine must reproduce exactly that."""
     x, y, v = gen.create_sparse_matrix(20000, 1024, deg, dist, seed=deg)
     run_both(tks, orc, x, y, v, 20000, 1024, make_query(1024, 2))
+
+
+@pytest.mark.parametrize("deg,dist,LFR,W", [(2, "gamma", 4, 20), (3, "gamma", 2, 20), (4, "gamma", 3, 21),
+                                            (20, "gamma", 4, 20), (1, "uniform", 4, 20)])
+def test_drift_free_mode_bit_exact_vs_its_oracle(cuda_required, tks, orc, gen, deg, dist, LFR, W):
+    """fixed_drift_free (the repair of the reference's row-counter drift): bit-exact against the
+    oracle's statement of the repaired rules, including inputs where almost every packet overflows LFR."""
+    x, y, v = gen.create_sparse_matrix(40000, 1024, max(deg, 2), dist, seed=deg + LFR)
+    if deg == 1:                                        # one non-zero per row: 15 rows finish in every packet
+        x = np.arange(x.size, dtype=np.uint32)
+    run_both(tks, orc, x, y, v, int(x.max()) + 1, 1024, make_query(1024, 14), W=W, LFR=LFR, drift_free=True)
+
+
+def test_drift_free_restores_recall_on_gamma_rows(cuda_required, tks, orc, gen):
+    """400k gamma-20 rows: the reference semantics report shifted row indices after the first packet with more than
+    LFR segments in a partition (precision collapses); drift-free mode reports the true rows."""
+    rows = 400000
+    x, y, v = gen.create_sparse_matrix(rows, 1024, 20, "gamma", seed=0)
+    vec = make_query(1024, 1)
+    yref = orc.spmv_f32(x, y, v.astype(np.float32), vec, rows)
+    exact = set(np.argsort(-yref.astype(np.float64), kind="stable")[:100].tolist())
+    val32, vec32 = orc.fx32_from_double(v), orc.query_fx32_from_f32(vec)
+    prec = {}
+    for df in (False, True):
+        with tks.SpMVFixed(x, y, val32, rows, 1024, vec32=vec32, k=100, drift_free=df) as f:
+            f()
+            _, idx = f.read_result()
+        prec[df] = len(exact & set(idx.tolist())) / 100
+    assert prec[True] >= 0.95, prec
+    assert prec[False] < prec[True], prec
+
+
+def test_drift_free_needs_the_reencoded_format(cuda_required, tks, orc, gen):
+    x, y, v = gen.create_sparse_matrix(2000, 1024, 20, "gamma", seed=0)
+    val32 = orc.fx32_from_double(v)
+    with pytest.raises(tks.capi.TksError, match="fixed_drift_free needs"):
+        tks.SpMVFixed(x, y, val32, 2000, 1024, fixed_width=32, drift_free=True)
+    with pytest.raises(tks.capi.TksError, match="fixed_drift_free needs"):
+        tks.SpMVFixed(x, y, val32, 2000, 1024, fixed_width=20, limited_finished_rows=1, drift_free=True)
 
 
 @pytest.mark.parametrize("Kp", [1, 2, 4, 8, 16, 32])

@@ -114,3 +114,38 @@ def test_fixed32_gold_equals_reference(orc, gen):
     ri, rv = np.zeros(100, np.uint32), np.zeros(100, np.uint32)
     R.ref_gold_topk_fx32(x, y, val32, x.size, vec32, cols, 100, ri, rv)
     assert np.array_equal(gi, ri) and np.array_equal(gv, rv)
+
+
+# ---- drift-free mode (the engine's stated repair of SURVEY 7-H2; NOT the reference) ------------------------
+
+def exact_fixed_row_sums(orc, x, y, v, rows, vec, W):
+    """W-bit fixed-point row sums with the kernel's arithmetic (truncating product, wrapping sum)."""
+    val32 = orc.fx32_from_double(v)
+    vW = orc.fxW_from_fx32(val32, W).astype(np.uint64)
+    xq = (orc.query_fx32_from_f32(vec) >> np.uint32(32 - W)).astype(np.uint64)
+    pw = ((vW * xq[y]) >> np.uint64(W - 1)) & np.uint64((1 << W) - 1)
+    out = np.zeros(rows, np.uint64)
+    np.add.at(out, x, pw)
+    return (out & np.uint64((1 << W) - 1)).astype(np.uint32)
+
+
+@pytest.mark.parametrize("deg,dist", [(2, "gamma"), (4, "gamma"), (20, "gamma")])
+def test_drift_free_candidates_are_true_rows_with_true_sums(orc, gen, deg, dist):
+    """With the repaired row counter every candidate (row, value) is the exact fixed-point sum of that very row,
+    however many row segments the packets hold; the reference semantics drift on the same input."""
+    from conftest import make_query
+    rows, W = 30000, 20
+    x, y, v = gen.create_sparse_matrix(rows, 1024, deg, dist, seed=deg)
+    vec = make_query(1024, 3)
+    sums = exact_fixed_row_sums(orc, x, y, v, rows, vec, W)
+    o = orc.bscsr_topk(x, y, v, rows, vec, W=W, drift_free=True)
+    assert o["idx"].size > 0
+    assert np.array_equal(o["val"] >> np.uint32(32 - W), sums[o["idx"]])
+    ref = orc.bscsr_topk(x, y, v, rows, vec, W=W)
+    if deg <= 4:      # short rows overflow LFR: the reference's indices no longer point at the rows they scored
+        assert not np.array_equal(ref["val"] >> np.uint32(32 - W), sums[ref["idx"]])
+    # identical whenever no packet holds more than LFR segments
+    x2, y2, v2 = gen.create_sparse_matrix(5000, 1024, 40, "uniform", seed=1)
+    a = orc.bscsr_topk(x2, y2, v2, 5000, vec, W=W, drift_free=True)
+    b = orc.bscsr_topk(x2, y2, v2, 5000, vec, W=W)
+    assert np.array_equal(a["idx_words"], b["idx_words"]) and np.array_equal(a["val_words"], b["val_words"])
