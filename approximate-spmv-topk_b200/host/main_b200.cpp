@@ -133,10 +133,45 @@ int main(int argc, char *argv[]) {
     auto t1 = clock_type::now();
     std::string err;
     const char *path = options.use_sample_matrix ? DEFAULT_MTX_FILE : options.matrix_path.c_str();
-    if (tkshost::readMtx<int_type, double>(path, &x, &y, &val_d, &rows, &cols, &nnz, 0, !options.ignore_matrix_values, debug,
-                                           options.zero_indexed, false, &err) != 0) {
-        std::cerr << err << std::endl;
-        return 1;
+    // -C: the parsed matrix is kept as a checksummed binary CSR next to the text file (tks_cache_*); a sweep re-reads
+    // that instead of the Matrix-Market text
+    bool from_cache = false;
+    if (!options.cache_path.empty()) {
+        uint64_t crow = 0, cnnz = 0;
+        uint32_t ccol = 0;
+        if (tks_cache_read_csr(options.cache_path.c_str(), &crow, &ccol, &cnnz, nullptr, nullptr, nullptr) == TKS_OK) {
+            std::vector<uint64_t> p64(crow + 1);
+            std::vector<float> v32(cnnz);
+            y.resize(cnnz);
+            if (tks_cache_read_csr(options.cache_path.c_str(), &crow, &ccol, &cnnz, p64.data(), y.data(), v32.data()) != TKS_OK) {
+                std::cerr << "matrix cache " << options.cache_path << " is unusable" << std::endl;
+                return 1;
+            }
+            rows = (int_type)crow; cols = ccol; nnz = (int_type)cnnz;
+            x.resize(cnnz);
+            for (uint64_t r = 0; r < crow; r++)
+                for (uint64_t e = p64[r]; e < p64[r + 1]; e++) x[e] = (int_type)r;
+            val_d.assign(v32.begin(), v32.end());
+            from_cache = true;
+        }
+    }
+    if (!from_cache) {
+        if (tkshost::readMtx<int_type, double>(path, &x, &y, &val_d, &rows, &cols, &nnz, 0, !options.ignore_matrix_values, debug,
+                                               options.zero_indexed, false, &err) != 0) {
+            std::cerr << err << std::endl;
+            return 1;
+        }
+        if (!options.cache_path.empty() && options.use_float) {
+            // the cache holds what the float engine consumes: CSR with fp32 values
+            std::vector<float> v32(val_d.begin(), val_d.end());
+            std::vector<int_type> ptr32(rows + 1), idx(nnz);
+            std::vector<float> cv(nnz);
+            if (tkshost::coo2csr<int_type, float>(ptr32.data(), idx.data(), cv.data(), x, y, v32, rows, cols) == 0) {
+                std::vector<uint64_t> p64(ptr32.begin(), ptr32.end());
+                if (tks_cache_write_csr(options.cache_path.c_str(), rows, cols, nnz, p64.data(), idx.data(), cv.data()) != TKS_OK)
+                    std::cerr << "warning: could not write matrix cache " << options.cache_path << std::endl;
+            }
+        }
     }
     if (debug) {
         auto ms = chrono::duration_cast<chrono::milliseconds>(clock_type::now() - t1).count();
@@ -170,7 +205,8 @@ int main(int argc, char *argv[]) {
     create_sample_vector(vec.data(), (int)cols, true, false, true, options.seed);
     auto t4 = clock_type::now();
     SpMVFixed spmv(x.data(), y.data(), val.data(), rows, cols, nnz, vec.data(), options.top_k_value, options.fixed_width,
-                   options.partitions, options.local_k, options.limited_finished_rows, options.device, debug);
+                   options.partitions, options.local_k, options.limited_finished_rows, options.device, debug,
+                   options.drift_free);
     float setup_ms = (float)chrono::duration_cast<chrono::microseconds>(clock_type::now() - t4).count() / 1000;
     if (debug) std::cout << "b200 setup time=" << setup_ms << " ms" << std::endl;
     tks_stats st;

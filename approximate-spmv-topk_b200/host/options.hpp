@@ -8,6 +8,8 @@
 //   -w  FIXED_WIDTH   -p SPMV_PARTITIONS   -l LIMITED_FINISHED_ROWS   -q local K   (types.hpp:20,36,77,51)
 //   -e  seed of the query generator (0 = random_device, as the reference)
 //   -G  CUDA device ordinal              -T  ties -> higher index first (reference sort order)
+//   -D  fixed-point engine: repair the reference's row-counter drift (tks_config.fixed_drift_free)
+//   -C  <file>  binary matrix cache: loaded when present, else written after the MTX text is parsed
 #pragma once
 
 #include <getopt.h>
@@ -58,6 +60,8 @@ struct Options {
     int seed = 0;
     int device = 0;
     bool tie_higher = false;
+    bool drift_free = false;
+    std::string cache_path;
 
     Options(int argc, char *argv[]) {
         static struct option long_options[] = {{"debug", no_argument, 0, 'd'},
@@ -82,9 +86,11 @@ struct Options {
                                                {"seed", required_argument, 0, 'e'},
                                                {"gpu", required_argument, 0, 'G'},
                                                {"tie_higher", no_argument, 0, 'T'},
+                                               {"drift_free", no_argument, 0, 'D'},
+                                               {"cache", required_argument, 0, 'C'},
                                                {0, 0, 0, 0}};
         int option_index = 0, opt;
-        while ((opt = getopt_long(argc, argv, "dm:st:x:vk:rb:c:g:i:azfw:p:l:q:e:G:T", long_options, &option_index)) != EOF) {
+        while ((opt = getopt_long(argc, argv, "dm:st:x:vk:rb:c:g:i:azfw:p:l:q:e:G:TDC:", long_options, &option_index)) != EOF) {
             switch (opt) {
                 case 'd': debug = true; break;
                 case 'r': reset = true; break;   // sic: the reference's -r also sets true (options.hpp:90-92)
@@ -108,6 +114,8 @@ struct Options {
                 case 'e': seed = atoi(optarg); break;
                 case 'G': device = atoi(optarg); break;
                 case 'T': tie_higher = true; break;
+                case 'D': drift_free = true; break;
+                case 'C': cache_path = optarg; break;
                 default: break;
             }
         }
