@@ -296,8 +296,8 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     TKS_CUDA(h, cudaMemset(b->logs.p0, 0, nlog * 4));
     TKS_CUDA(h, cudaMalloc(&b->d_xq, 1024 * 4));
     TKS_CUDA(h, cudaMallocHost(&b->h_xq, 1024 * 4));
-    TKS_CUDA(h, cudaMalloc(&b->d_counter, 4));
-    TKS_CUDA(h, cudaMemset(b->d_counter, 0, 4));
+    TKS_CUDA(h, cudaMalloc(&b->d_counter, 16));   // [0] chunk scheduler, [1] log entries of the last run
+    TKS_CUDA(h, cudaMemset(b->d_counter, 0, 16));
     const size_t nres = (size_t)partitions * Kp * 16;
     // index words and value words in one block: one device-to-host copy per run
     TKS_CUDA(h, cudaMalloc(&b->d_res_idx, 2 * nres * 4));
@@ -375,6 +375,10 @@ int bscsr_fetch(Handle *h) {
     const size_t nres = (size_t)b->P * h->cfg.local_k * 16;
     TKS_CUDA(h, cudaMemcpyAsync(b->h_res_idx, b->d_res_idx, 2 * nres * 4, cudaMemcpyDeviceToHost, h->stream));
     TKS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->cfg.profile_kernels) {   // statistics: candidates the stream kernel logged for the replay
+        uint32_t logged = 0;
+        if (cudaMemcpy(&logged, b->d_counter + 1, 4, cudaMemcpyDeviceToHost) == cudaSuccess) h->stats.logged_candidates = logged;
+    }
     b->have_words = true;
     // read_result (host_spmv_bscsr.cpp:399-448): all P x Kp x B slots, idx += first_row[p], keep val > 0,
     // first insertion of an index wins, then sort_tuples (evaluation_utils.hpp:40-62)

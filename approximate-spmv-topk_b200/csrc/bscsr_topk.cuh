@@ -565,6 +565,7 @@ bscsr_stream_kernel(const uint8_t *__restrict__ packets, BscsrChunks m, const ui
     uint32_t *ptab = xs + 1024 * XREP;                      // [prefix length 0..15][thread]: running sums of the products
     for (uint32_t i = threadIdx.x; i < 1024u * XREP; i += THREADS) xs[i] = xq[i / XREP];
     ptab[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) chunk_counter[1] = 0;   // log-entry statistics of this run
     __syncthreads();
     const unsigned lane = lane_id();
     for (;;) {
@@ -619,7 +620,7 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
     __shared__ uint32_t s_wsum[kReplayThreads / 32], s_off[kReplayThreads + 1];
     __shared__ uint32_t s_n;
     if (tid == 0) s_n = 0;
-    if (blockIdx.x == 0 && tid == 0 && chunk_counter_reset) *chunk_counter_reset = 0;
+    if (blockIdx.x == 0 && tid == 0 && chunk_counter_reset) *chunk_counter_reset = 0;   // [1]: log entries, statistics
     const bool first_from_packet0 = logs.p0[(size_t)cb * LFR + j] != 0;
     __syncthreads();
 
@@ -681,6 +682,7 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
         __syncthreads();
         uint32_t before = 0, all = 0;
         for (uint32_t wv = 0; wv < blockDim.x / 32; wv++) { if (wv < tid / 32) before += s_wsum[wv]; all += s_wsum[wv]; }
+        if (tid == 0 && chunk_counter_reset) atomicAdd(chunk_counter_reset + 1, all);
         if (s_n + all > kReplaySurvivors) {   // uniform: flush what is buffered first
             __syncthreads();
             replay();

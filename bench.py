@@ -633,7 +633,8 @@ def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
             "e2e": {"value": nnz / (e2e_ms_step * 1e-3), "unit": "nnz/s", "ms_per_step": e2e_ms_step,
                     "h2d_bytes_per_step": cols * 4, "d2h_bytes_per_step": P * Kp * 128,
                     "api": "SpMVFixed.reset(host vec) -> operator() -> read_result (host merge of P x K x LFR candidates)"},
-            "gpu_launches": args.steps * 3, "results_returned": int(i_last.size), "recall_vs_exact_fp32": recall,
+            "gpu_launches": args.steps * 3, "results_returned": int(i_last.size),
+            "logged_candidates_last_step": int(st.logged_candidates), "recall_vs_exact_fp32": recall,
             "clocks": clocks}
     print(json.dumps(line), flush=True)
     eng.close()

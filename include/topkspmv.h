@@ -85,7 +85,8 @@ typedef struct tks_stats {
     uint32_t launches_per_run;    /* kernels launched by one tks_run                     */
     float last_main_kernel_ms;    /* dominant kernel alone (only with cfg.profile_kernels) */
     uint32_t batched_fallbacks;   /* batched queries re-run alone because their pool overflowed */
-    uint32_t reserved[6];
+    uint32_t logged_candidates;   /* BS-CSR mode with profile_kernels: entries the stream kernel logged */
+    uint32_t reserved[5];
 } tks_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */
