@@ -78,6 +78,8 @@ void launch_stream_fmt(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStrea
     else if (W == 20 && LFR == 4 && BSX && b->variant == 16) launch_stream_variant<20, 4, 16, 1024, false, BSX && W == 20>(h, b, m, s);
     else if (W == 20 && LFR == 4 && BSX && b->variant == 33) launch_stream_variant<20, 4, 32, 768, false, BSX && W == 20>(h, b, m, s);
     else if (W == 20 && LFR == 4 && BSX && b->variant == 34) launch_stream_variant<20, 4, 32, 1024, false, BSX && W == 20>(h, b, m, s);
+    else if (W == 20 && LFR == 4 && BSX && b->variant == 35) launch_stream_variant<20, 4, 32, 1024, true, BSX && W == 20>(h, b, m, s);
+    else if (W == 20 && LFR == 4 && BSX && b->variant == 36) launch_stream_variant<20, 4, 32, 896, true, BSX && W == 20>(h, b, m, s);
     else launch_stream_variant<W, LFR, kBsDefaultXrep, kBsDefaultThreads, true, BSX>(h, b, m, s);
     if (prof) cudaEventRecord(h->evm1, s);
 }
@@ -99,13 +101,24 @@ int dispatch_lfr(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s)
         case 4: launch_stream<W, 4>(h, b, m, s); break;
         default: return h->fail(TKS_EINVAL, "limited_finished_rows=%d is not instantiated (1..4)", h->cfg.limited_finished_rows);
     }
-    if (!b->replay_ready) {
-        cudaFuncSetAttribute(bscsr_replay_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplayDynSmem);
-        b->replay_ready = true;
+    const uint32_t rgrid = b->P * (uint32_t)h->cfg.limited_finished_rows;
+    if (h->cfg.local_k <= 8) {
+        if (!b->replay_ready) {
+            cudaFuncSetAttribute(bscsr_replay_kernel<W, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplayDynSmem);
+            b->replay_ready = true;
+        }
+        bscsr_replay_kernel<W, 8><<<rgrid, kReplayThreads, kReplayDynSmem, s>>>(
+            b->logs, b->d_part_chunk_begin, (uint32_t)h->cfg.limited_finished_rows, (uint32_t)h->cfg.local_k, b->chunk_cap,
+            b->d_res_idx, b->d_res_val, b->d_counter);
+    } else {
+        if (!b->replay_ready) {
+            cudaFuncSetAttribute(bscsr_replay_kernel<W, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplayDynSmem);
+            b->replay_ready = true;
+        }
+        bscsr_replay_kernel<W, 32><<<rgrid, kReplayThreads, kReplayDynSmem, s>>>(
+            b->logs, b->d_part_chunk_begin, (uint32_t)h->cfg.limited_finished_rows, (uint32_t)h->cfg.local_k, b->chunk_cap,
+            b->d_res_idx, b->d_res_val, b->d_counter);
     }
-    bscsr_replay_kernel<W><<<b->P * (uint32_t)h->cfg.limited_finished_rows, kReplayThreads, kReplayDynSmem, s>>>(
-        b->logs, b->d_part_chunk_begin, (uint32_t)h->cfg.limited_finished_rows, (uint32_t)h->cfg.local_k, b->chunk_cap,
-        b->d_res_idx, b->d_res_val, b->d_counter);
     return TKS_OK;
 }
 

@@ -607,7 +607,8 @@ __global__ void bscsr_query_kernel(const uint32_t *__restrict__ vec32, uint32_t 
     xq[c] = (W == 32) ? q : (q << 1);
 }
 
-template <int W>
+// KMAX: capacity of the per-thread copy of the K-entry list (8 covers the reference's K; 32 the rest).
+template <int W, int KMAX>
 __global__ void __launch_bounds__(kReplayThreads)
 bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begin, uint32_t LFR, uint32_t Kp,
                     uint32_t chunk_cap, uint32_t *res_idx_words, uint32_t *res_val_words, uint32_t *chunk_counter_reset) {
@@ -624,41 +625,49 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
     const bool first_from_packet0 = logs.p0[(size_t)cb * LFR + j] != 0;
     __syncthreads();
 
-    // Literal replace-min (hpp:366-389) over the buffered entries, by warp 0.  The K slots live one per lane
-    // (lv/li of lanes 0..Kp-1), so the argmin is a warp reduction instead of a serial scan.  Lanes screen 32
-    // entries at a time against the CURRENT worst value (it only grows, so an entry below it can never be
-    // accepted); the rare accepted entries are applied one by one, in stream order.
-    uint32_t lv = 0, li = 0;   // warp 0 only: value / row index of slot `lane`
+    // Literal replace-min (hpp:366-389) over the buffered entries, by warp 0.  Every lane of the warp keeps the
+    // whole K-entry list in registers (lv/li, identical in all lanes), so accepting a candidate is straight-line
+    // code without cross-lane traffic; the lanes only cooperate to screen 32 entries at a time against the
+    // CURRENT worst value (it only grows, so an entry below it can never be accepted).  The rare accepted
+    // entries are applied one by one, in stream order.
+    uint32_t lv[KMAX], li[KMAX];
+#pragma unroll
+    for (int t = 0; t < KMAX; t++) { lv[t] = 0; li[t] = 0; }
     uint32_t wi = 0, wv = 0, started = 0;
-    auto warp_argmin = [&](uint32_t &idx, uint32_t &val) {
-        // MIN(res,a,b) = res[a] < res[b] ? a : b  -> the HIGHEST slot among equal minima (hpp:28);
+    auto list_argmin = [&](uint32_t &idx, uint32_t &val) {
+        // MIN(res,a,b) = res[a] < res[b] ? a : b  -> the HIGHEST slot among equal minima (hpp:28, :51-63, :89-99);
         // K == 4 reproduces `MIN(res, 2, 2)` (hpp:45): slot 3 is never the minimum
-        const bool in = lane < Kp && !(Kp == 4 && lane == 3);
-        const uint32_t mn = __reduce_min_sync(0xFFFFFFFFu, in ? lv : 0xFFFFFFFFu);
-        const unsigned who = __ballot_sync(0xFFFFFFFFu, in && lv == mn);
-        idx = 31u - (uint32_t)__clz((int)who);
-        val = mn;
+        uint32_t best = lv[0], bi = 0;
+#pragma unroll
+        for (int t = 1; t < KMAX; t++) {
+            const bool in = (uint32_t)t < Kp && !(Kp == 4 && t == 3);
+            if (in && lv[t] <= best) { best = lv[t]; bi = (uint32_t)t; }
+        }
+        idx = bi;
+        val = best;
     };
     auto replay = [&]() {
         if (tid < 32) {
             const uint32_t n = s_n;
             for (uint32_t b = 0; b < n; b += 32) {
                 const uint32_t i = b + lane;
-                const uint32_t v = (i < n) ? s_sv[i] : 0u, r = (i < n) ? s_sr[i] : 0u;
+                const uint32_t v = (i < n) ? s_sv[i] : 0u;
                 if (!started) {
                     // the argmin is recomputed after EVERY packet (hpp:376-388): unless the first candidate comes
                     // from packet 0 of the partition, the all-zero list has already moved the worst slot
-                    if (!first_from_packet0) warp_argmin(wi, wv);
+                    if (!first_from_packet0) list_argmin(wi, wv);
                     started = 1;
                 }
                 unsigned rest = __ballot_sync(0xFFFFFFFFu, i < n && v >= wv);
                 while (rest) {
-                    const int src = __ffs(rest) - 1;
+                    const uint32_t src = b + (uint32_t)__ffs(rest) - 1u;
                     rest &= rest - 1;
-                    const uint32_t cv = __shfl_sync(0xFFFFFFFFu, v, src), cr = __shfl_sync(0xFFFFFFFFu, r, src);
-                    if (cv >= wv) {   // warp-uniform
-                        if (lane == wi) { li = cr; lv = cv; }
-                        warp_argmin(wi, wv);
+                    const uint32_t cv = s_sv[src];   // same address in every lane: broadcast
+                    if (cv >= wv) {                  // warp-uniform
+                        const uint32_t cr = s_sr[src];
+#pragma unroll
+                        for (int t = 0; t < KMAX; t++) if ((uint32_t)t == wi) { lv[t] = cv; li[t] = cr; }
+                        list_argmin(wi, wv);
                     }
                 }
             }
@@ -723,9 +732,12 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
     replay();
     // write-back (.cpp:151-185): word t, position j = list j slot t; values widened to ufixed<32,1>
     if (tid < Kp) {
+        uint32_t ov = 0, oi = 0;
+#pragma unroll
+        for (int t = 0; t < KMAX; t++) if ((uint32_t)t == tid) { ov = lv[t]; oi = li[t]; }
         const size_t o = ((size_t)p * Kp + tid) * 16u + j;
-        res_idx_words[o] = li;
-        res_val_words[o] = (W == 32) ? lv : (lv << (32 - W));
+        res_idx_words[o] = oi;
+        res_val_words[o] = (W == 32) ? ov : (ov << (32 - W));
     }
 }
 
