@@ -22,7 +22,8 @@ struct BscsrState {
     BscsrLogs logs{};
     // sample pieces (first kBsSamplePackets packets of every partition, kBsSamplePiece each)
     uint32_t *d_s_first = nullptr, *d_s_count = nullptr, *d_s_local0 = nullptr, *d_s_lookback = nullptr, *d_s_part = nullptr,
-             *d_s_part_begin = nullptr, *d_piece_top = nullptr, *d_ticket = nullptr, *d_theta_seed = nullptr;
+             *d_s_part_begin = nullptr, *d_piece_top = nullptr, *d_ticket = nullptr, *d_theta_seed = nullptr,
+             *d_sample_end = nullptr;   // [P] packets of the partition's prefix the sample covers
     uint32_t n_pieces = 0;
     uint32_t *d_xq = nullptr;        // 1024 pre-shifted query words
     uint32_t *h_xq = nullptr;        // pinned
@@ -62,7 +63,7 @@ void launch_stream_variant(Handle *h, BscsrState *b, const BscsrChunks &m, cudaS
         b->variant_ready = true;
     }
     bscsr_stream_kernel<W, LFR, XREP, THREADS, PREFETCH, BSX><<<b->grid, THREADS, bscsr_stream_smem(XREP, THREADS), s>>>(
-        b->d_packets, m, b->d_xq, (uint32_t)h->cfg.local_k, b->logs, b->d_theta_seed, b->d_counter);
+        b->d_packets, m, b->d_xq, (uint32_t)h->cfg.local_k, b->logs, b->d_theta_seed, b->d_sample_end, b->d_counter);
 }
 
 template <int W, int LFR, bool BSX>
@@ -101,24 +102,13 @@ int dispatch_lfr(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s)
         case 4: launch_stream<W, 4>(h, b, m, s); break;
         default: return h->fail(TKS_EINVAL, "limited_finished_rows=%d is not instantiated (1..4)", h->cfg.limited_finished_rows);
     }
-    const uint32_t rgrid = b->P * (uint32_t)h->cfg.limited_finished_rows;
-    if (h->cfg.local_k <= 8) {
-        if (!b->replay_ready) {
-            cudaFuncSetAttribute(bscsr_replay_kernel<W, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplayDynSmem);
-            b->replay_ready = true;
-        }
-        bscsr_replay_kernel<W, 8><<<rgrid, kReplayThreads, kReplayDynSmem, s>>>(
-            b->logs, b->d_part_chunk_begin, (uint32_t)h->cfg.limited_finished_rows, (uint32_t)h->cfg.local_k, b->chunk_cap,
-            b->d_res_idx, b->d_res_val, b->d_counter);
-    } else {
-        if (!b->replay_ready) {
-            cudaFuncSetAttribute(bscsr_replay_kernel<W, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplayDynSmem);
-            b->replay_ready = true;
-        }
-        bscsr_replay_kernel<W, 32><<<rgrid, kReplayThreads, kReplayDynSmem, s>>>(
-            b->logs, b->d_part_chunk_begin, (uint32_t)h->cfg.limited_finished_rows, (uint32_t)h->cfg.local_k, b->chunk_cap,
-            b->d_res_idx, b->d_res_val, b->d_counter);
+    if (!b->replay_ready) {
+        cudaFuncSetAttribute(bscsr_replay_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplayDynSmem);
+        b->replay_ready = true;
     }
+    bscsr_replay_kernel<W><<<b->P * (uint32_t)h->cfg.limited_finished_rows, kReplayThreads, kReplayDynSmem, s>>>(
+        b->logs, b->d_part_chunk_begin, (uint32_t)h->cfg.limited_finished_rows, (uint32_t)h->cfg.local_k, b->chunk_cap,
+        b->d_res_idx, b->d_res_val, b->d_counter);
     return TKS_OK;
 }
 
@@ -167,7 +157,7 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
 
     // ---- chunk tables (host, once per matrix): row counter and carry look-back at every chunk start ----
     std::vector<uint32_t> c_first, c_count, c_local0, c_row_in, c_look, c_part, part_begin(partitions + 1, 0);
-    std::vector<uint32_t> s_first, s_count, s_local0, s_look, s_part, s_part_begin(partitions + 1, 0);
+    std::vector<uint32_t> s_first, s_count, s_local0, s_look, s_part, s_part_begin(partitions + 1, 0), sample_end(partitions, 0);
     uint64_t goff = 0;
     const uint64_t tail_begin = total - total / 10u;   // last 10 % of the stream
     for (uint32_t p = 0; p < partitions; p++) {
@@ -175,8 +165,8 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
         s_part_begin[p] = (uint32_t)s_first.size();
         const uint8_t *pk = static_cast<const uint8_t *>(packets[p]);
         const uint64_t np = packets_per_part[p];
-        uint32_t last_row = 0, chunk_row_in = 0;
-        uint64_t next_chunk = 0;
+        uint32_t last_row = 0, chunk_row_in = 0, n_pieces_here = 0;
+        uint64_t next_chunk = 0, next_piece = 0;
         if (b->bsx) enc[p].assign((size_t)np * 16, 0u);
         std::vector<uint8_t> keepflag(np);   // packet passes the carried partial sum through (n == 1 && !new)
         for (uint64_t i = 0; i < np; i++) {
@@ -249,14 +239,20 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
                 if (rel > 0xFFFu) return h->fail(TKS_EINVAL, "internal: row offset inside a chunk exceeds 12 bits");
                 wout[15] = (uint32_t)(xw & 0xFFFFu) | ((nw | (n << 1) | (rel << 4)) << 16);
             }
-            if (i < kBsSamplePackets && i % kBsSamplePiece == 0) {
-                s_first.push_back((uint32_t)(goff + i));
-                s_count.push_back((uint32_t)std::min<uint64_t>(kBsSamplePiece, std::min<uint64_t>(np, kBsSamplePackets) - i));
-                s_local0.push_back((uint32_t)i);
+            if (i == next_piece && i < kBsSamplePackets && n_pieces_here < kBsMaxPieces) {
                 uint32_t L = 0;
                 if (i > 0) { L = 1; while (i - L > 0 && keepflag[i - L]) L++; }
+                // look-back + piece = two warp iterations
+                const uint64_t lim = std::min<uint64_t>(np, kBsSamplePackets);
+                const uint64_t cnt = std::min<uint64_t>(kBsSamplePiece - (L % 32u), lim - i);
+                s_first.push_back((uint32_t)(goff + i));
+                s_count.push_back((uint32_t)cnt);
+                s_local0.push_back((uint32_t)i);
                 s_look.push_back(L);
                 s_part.push_back(p);
+                next_piece = i + cnt;
+                n_pieces_here++;
+                sample_end[p] = (uint32_t)next_piece;
             }
             last_row += rows_done + nw - 1u;
             keepflag[i] = (n == 1 && nw == 0) || (n == 0 && nw != 0);
@@ -296,6 +292,7 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     TKS_CUDA(h, up(&b->d_s_lookback, s_look));
     TKS_CUDA(h, up(&b->d_s_part, s_part));
     TKS_CUDA(h, up(&b->d_s_part_begin, s_part_begin));
+    TKS_CUDA(h, up(&b->d_sample_end, sample_end));
     TKS_CUDA(h, cudaMalloc(&b->d_piece_top, (size_t)b->n_pieces * LFR * 32 * 4));
     TKS_CUDA(h, cudaMalloc(&b->d_ticket, partitions * 4));
     TKS_CUDA(h, cudaMemset(b->d_ticket, 0, partitions * 4));
@@ -467,7 +464,7 @@ void bscsr_destroy(Handle *h) {
     cudaFree(b->logs.val); cudaFree(b->logs.row); cudaFree(b->logs.cnt); cudaFree(b->logs.p0);
     cudaFree(b->d_chunk_part); cudaFree(b->d_s_first); cudaFree(b->d_s_count); cudaFree(b->d_s_local0); cudaFree(b->d_s_lookback);
     cudaFree(b->d_s_part); cudaFree(b->d_s_part_begin); cudaFree(b->d_piece_top); cudaFree(b->d_ticket); cudaFree(b->d_theta_seed);
-    cudaFree(b->d_xq); cudaFreeHost(b->h_xq); cudaFree(b->d_counter);
+    cudaFree(b->d_xq); cudaFreeHost(b->h_xq); cudaFree(b->d_counter); cudaFree(b->d_sample_end);
     cudaFree(b->d_res_idx); cudaFreeHost(b->h_res_idx);
     if (b->ev_query) cudaEventDestroy(b->ev_query);
     delete b;

@@ -38,8 +38,9 @@ constexpr int kBsDefaultXrep = 32;            // stream kernel: one query copy p
 constexpr int kBsDefaultThreads = 768;        // stream kernel: one CTA of 24 warps per SM (128 KB query + 48 KB ptab)
 constexpr uint32_t kBsMaxKp = 32;             // local K (types.hpp K) supported: 1..32
 constexpr uint32_t kBsMaxLfr = 4;             // LFR values instantiated: 1..4 (see bscsr_api.cu)
-constexpr uint32_t kBsSamplePackets = 2048;   // prefix of every partition reduced by the sample kernel
-constexpr uint32_t kBsSamplePiece = 64;       // packets per sample warp
+constexpr uint32_t kBsSamplePackets = 2048;   // prefix of every partition reduced by the sample kernel (at most)
+constexpr uint32_t kBsSamplePiece = 64;       // packets per sample warp, look-back included (two warp iterations)
+constexpr uint32_t kBsMaxPieces = 40;         // sample pieces per partition (bounds the merge's register array)
 constexpr uint32_t kReplayThreads = 1024;      // one tile covers the ~800 chunks of a cfg3 partition
 constexpr uint32_t kReplaySurvivors = 8192;   // log entries buffered between sequential replays (dynamic smem)
 constexpr uint32_t kReplayDynSmem = kReplaySurvivors * 8u;
@@ -526,27 +527,54 @@ bscsr_sample_kernel(const uint8_t *__restrict__ packets, BscsrSample sm, const u
     t = __shfl_sync(0xFFFFFFFFu, t, 0);
     if (t != pe - pb - 1) return;
     __threadfence();
-    constexpr uint32_t kMaxPieces = kBsSamplePackets / kBsSamplePiece;
-#pragma unroll 1
-    for (int j = 0; j < LFR; j++) {
-        // all loads first (independent), then the sequential merge from registers
+    constexpr uint32_t kMaxPieces = kBsMaxPieces;
+    if (Kp <= 8 && LFR <= 4) {
+        // the LFR lists are merged side by side: lanes [8j, 8j+8) hold list j (slot = lane % 8), so one pass over the
+        // pieces serves all lists; the pieces' values are fetched first (independent loads), then merged from registers
+        const uint32_t jl = lane >> 3, t8 = lane & 7u, base8 = lane & ~7u;
         uint32_t vq[kMaxPieces];
 #pragma unroll
         for (uint32_t q = 0; q < kMaxPieces; q++)
-            vq[q] = (pb + q < pe) ? __ldcg(&sm.piece_top[((size_t)(pb + q) * LFR + j) * 32u + lane]) : 0u;
+            vq[q] = (pb + q < pe && jl < (uint32_t)LFR && t8 < Kp)
+                        ? __ldcg(&sm.piece_top[((size_t)(pb + q) * LFR + jl) * 32u + t8]) : 0u;
         uint32_t rtop = 0;
 #pragma unroll
         for (uint32_t q = 0; q < kMaxPieces; q++) {
-            const uint32_t thr = __shfl_sync(0xFFFFFFFFu, rtop, (int)Kp - 1);
-            unsigned rest = __ballot_sync(0xFFFFFFFFu, lane < Kp && vq[q] > thr);
+            uint32_t thr = __shfl_sync(0xFFFFFFFFu, rtop, (int)(base8 + Kp - 1));
+            unsigned rest = __ballot_sync(0xFFFFFFFFu, vq[q] > thr);
             while (rest) {
-                const int src = __ffs(rest) - 1;
-                rest &= rest - 1;
-                rtop = lane_list_insert(rtop, __shfl_sync(0xFFFFFFFFu, vq[q], src), Kp);
+                const uint32_t t = ((uint32_t)__ffs(rest) - 1u) & 7u;          // slot t of every list's piece
+                rest &= ~(0x01010101u << t);
+                const uint32_t v = __shfl_sync(0xFFFFFFFFu, vq[q], (int)(base8 + t));
+                thr = __shfl_sync(0xFFFFFFFFu, rtop, (int)(base8 + Kp - 1));
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, rtop, 1, 8);
+                if (v > thr && t8 < Kp && rtop < v) rtop = (t8 == 0 || up >= v) ? v : up;
             }
         }
-        const uint32_t seed = __shfl_sync(0xFFFFFFFFu, rtop, (int)Kp - 1);
-        if (lane == 0) sm.theta_seed[p * LFR + j] = seed;
+        const uint32_t seed = __shfl_sync(0xFFFFFFFFu, rtop, (int)(base8 + Kp - 1));
+        if (t8 == 0 && jl < (uint32_t)LFR) sm.theta_seed[p * LFR + jl] = seed;
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < LFR; j++) {
+            // all loads first (independent), then the sequential merge from registers
+            uint32_t vq[kMaxPieces];
+#pragma unroll
+            for (uint32_t q = 0; q < kMaxPieces; q++)
+                vq[q] = (pb + q < pe) ? __ldcg(&sm.piece_top[((size_t)(pb + q) * LFR + j) * 32u + lane]) : 0u;
+            uint32_t rtop = 0;
+#pragma unroll
+            for (uint32_t q = 0; q < kMaxPieces; q++) {
+                const uint32_t thr = __shfl_sync(0xFFFFFFFFu, rtop, (int)Kp - 1);
+                unsigned rest = __ballot_sync(0xFFFFFFFFu, lane < Kp && vq[q] > thr);
+                while (rest) {
+                    const int src = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    rtop = lane_list_insert(rtop, __shfl_sync(0xFFFFFFFFu, vq[q], src), Kp);
+                }
+            }
+            const uint32_t seed = __shfl_sync(0xFFFFFFFFu, rtop, (int)Kp - 1);
+            if (lane == 0) sm.theta_seed[p * LFR + j] = seed;
+        }
     }
     if (lane == 0) sm.ticket[p] = 0;
 }
@@ -559,7 +587,8 @@ __host__ __device__ constexpr size_t bscsr_stream_smem(int xrep, int threads) {
 template <int W, int LFR, int XREP, int THREADS, bool PREFETCH, bool BSX>
 __global__ void __launch_bounds__(THREADS, (XREP <= 2 && THREADS <= 256) ? 4 : 1)
 bscsr_stream_kernel(const uint8_t *__restrict__ packets, BscsrChunks m, const uint32_t *__restrict__ xq, uint32_t Kp,
-                    BscsrLogs logs, const uint32_t *__restrict__ theta_seed, uint32_t *chunk_counter) {
+                    BscsrLogs logs, const uint32_t *__restrict__ theta_seed, const uint32_t *__restrict__ sample_end,
+                    uint32_t *chunk_counter) {
     extern __shared__ __align__(16) uint8_t bs_smem[];
     uint32_t *xs = reinterpret_cast<uint32_t *>(bs_smem);   // query, pre-shifted (bscsr_api.cu), XREP copies interleaved
     uint32_t *ptab = xs + 1024 * XREP;                      // [prefix length 0..15][thread]: running sums of the products
@@ -575,7 +604,7 @@ bscsr_stream_kernel(const uint8_t *__restrict__ packets, BscsrChunks m, const ui
         if (c >= m.n) break;
         const uint32_t first = m.first[c], count = m.count[c], local0 = m.local0[c];
         // chunks behind the sampled prefix of their partition start from the sample's K-th largest value
-        const bool seeded = local0 >= kBsSamplePackets;
+        const bool seeded = local0 >= sample_end[m.part[c]];
         uint32_t theta[LFR], top[LFR];
         BsLogSink<LFR> sink;
         sink.val = logs.val + (size_t)c * LFR * m.cap;
@@ -607,8 +636,7 @@ __global__ void bscsr_query_kernel(const uint32_t *__restrict__ vec32, uint32_t 
     xq[c] = (W == 32) ? q : (q << 1);
 }
 
-// KMAX: capacity of the per-thread copy of the K-entry list (8 covers the reference's K; 32 the rest).
-template <int W, int KMAX>
+template <int W>
 __global__ void __launch_bounds__(kReplayThreads)
 bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begin, uint32_t LFR, uint32_t Kp,
                     uint32_t chunk_cap, uint32_t *res_idx_words, uint32_t *res_val_words, uint32_t *chunk_counter_reset) {
@@ -625,49 +653,50 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
     const bool first_from_packet0 = logs.p0[(size_t)cb * LFR + j] != 0;
     __syncthreads();
 
-    // Literal replace-min (hpp:366-389) over the buffered entries, by warp 0.  Every lane of the warp keeps the
-    // whole K-entry list in registers (lv/li, identical in all lanes), so accepting a candidate is straight-line
-    // code without cross-lane traffic; the lanes only cooperate to screen 32 entries at a time against the
-    // CURRENT worst value (it only grows, so an entry below it can never be accepted).  The rare accepted
-    // entries are applied one by one, in stream order.
-    uint32_t lv[KMAX], li[KMAX];
-#pragma unroll
-    for (int t = 0; t < KMAX; t++) { lv[t] = 0; li[t] = 0; }
+    // Literal replace-min (hpp:366-389) over the buffered entries, by warp 0.  The K slots live one per lane
+    // (lv/li of lanes 0..Kp-1), so the argmin is one warp reduction instead of a serial scan.  Lanes screen 32
+    // entries at a time against the CURRENT worst value (it only grows, so an entry below it can never be
+    // accepted); the rare accepted entries are applied one by one, in stream order.
+    // (A per-lane register copy of the whole list with straight-line argmin measured slower: 41 us vs 28 us.)
+    uint32_t lv = 0, li = 0;   // warp 0 only: value / row index of slot `lane`
     uint32_t wi = 0, wv = 0, started = 0;
-    auto list_argmin = [&](uint32_t &idx, uint32_t &val) {
-        // MIN(res,a,b) = res[a] < res[b] ? a : b  -> the HIGHEST slot among equal minima (hpp:28, :51-63, :89-99);
+    auto warp_argmin = [&](uint32_t &idx, uint32_t &val) {
+        // MIN(res,a,b) = res[a] < res[b] ? a : b  -> the HIGHEST slot among equal minima (hpp:28);
         // K == 4 reproduces `MIN(res, 2, 2)` (hpp:45): slot 3 is never the minimum
-        uint32_t best = lv[0], bi = 0;
-#pragma unroll
-        for (int t = 1; t < KMAX; t++) {
-            const bool in = (uint32_t)t < Kp && !(Kp == 4 && t == 3);
-            if (in && lv[t] <= best) { best = lv[t]; bi = (uint32_t)t; }
+        const bool in = lane < Kp && !(Kp == 4 && lane == 3);
+        if (W <= 27) {
+            // one reduction: key = value * 32 + (31 - slot); the smallest key is the smallest value in the highest slot
+            const uint32_t key = in ? ((lv << 5) | (31u - lane)) : 0xFFFFFFFFu;
+            const uint32_t mk = __reduce_min_sync(0xFFFFFFFFu, key);
+            idx = 31u - (mk & 31u);
+            val = mk >> 5;
+        } else {
+            const uint32_t mn = __reduce_min_sync(0xFFFFFFFFu, in ? lv : 0xFFFFFFFFu);
+            const unsigned who = __ballot_sync(0xFFFFFFFFu, in && lv == mn);
+            idx = 31u - (uint32_t)__clz((int)who);
+            val = mn;
         }
-        idx = bi;
-        val = best;
     };
     auto replay = [&]() {
         if (tid < 32) {
             const uint32_t n = s_n;
             for (uint32_t b = 0; b < n; b += 32) {
                 const uint32_t i = b + lane;
-                const uint32_t v = (i < n) ? s_sv[i] : 0u;
+                const uint32_t v = (i < n) ? s_sv[i] : 0u, r = (i < n) ? s_sr[i] : 0u;
                 if (!started) {
                     // the argmin is recomputed after EVERY packet (hpp:376-388): unless the first candidate comes
                     // from packet 0 of the partition, the all-zero list has already moved the worst slot
-                    if (!first_from_packet0) list_argmin(wi, wv);
+                    if (!first_from_packet0) warp_argmin(wi, wv);
                     started = 1;
                 }
                 unsigned rest = __ballot_sync(0xFFFFFFFFu, i < n && v >= wv);
                 while (rest) {
-                    const uint32_t src = b + (uint32_t)__ffs(rest) - 1u;
+                    const int src = __ffs(rest) - 1;
                     rest &= rest - 1;
-                    const uint32_t cv = s_sv[src];   // same address in every lane: broadcast
-                    if (cv >= wv) {                  // warp-uniform
-                        const uint32_t cr = s_sr[src];
-#pragma unroll
-                        for (int t = 0; t < KMAX; t++) if ((uint32_t)t == wi) { lv[t] = cv; li[t] = cr; }
-                        list_argmin(wi, wv);
+                    const uint32_t cv = __shfl_sync(0xFFFFFFFFu, v, src), cr = __shfl_sync(0xFFFFFFFFu, r, src);
+                    if (cv >= wv) {   // warp-uniform
+                        if (lane == wi) { li = cr; lv = cv; }
+                        warp_argmin(wi, wv);
                     }
                 }
             }
@@ -732,12 +761,9 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
     replay();
     // write-back (.cpp:151-185): word t, position j = list j slot t; values widened to ufixed<32,1>
     if (tid < Kp) {
-        uint32_t ov = 0, oi = 0;
-#pragma unroll
-        for (int t = 0; t < KMAX; t++) if ((uint32_t)t == tid) { ov = lv[t]; oi = li[t]; }
         const size_t o = ((size_t)p * Kp + tid) * 16u + j;
-        res_idx_words[o] = oi;
-        res_val_words[o] = (W == 32) ? ov : (ov << (32 - W));
+        res_idx_words[o] = li;
+        res_val_words[o] = (W == 32) ? lv : (lv << (32 - W));
     }
 }
 
