@@ -105,7 +105,8 @@ int alloc_query_side(Handle *h) {
 
 void free_matrix(Handle *h) {
     cudaFree(h->d_val); h->d_val = nullptr;
-    cudaFree(h->d_colf); h->d_colf = nullptr;
+    cudaFree(h->d_col16); h->d_col16 = nullptr;
+    cudaFree(h->d_rowbits); h->d_rowbits = nullptr;
     cudaFree(h->d_ptr64); h->d_ptr64 = nullptr;
     cudaFree(h->d_chunk_start); h->d_chunk_start = nullptr;
     cudaFree(h->d_chunk_ord); h->d_chunk_ord = nullptr;
@@ -147,8 +148,11 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
         TKS_CUDA(h, cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_val) + nnz * sizeof(float), 0, pad, s));
         TKS_CUDA(h, cudaMemcpyAsync(h->d_val, d_val_src, nnz * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
-    TKS_CUDA(h, cudaMalloc(&h->d_colf, nnz * sizeof(uint32_t) + pad));
-    TKS_CUDA(h, cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_colf) + nnz * sizeof(uint32_t), 0, pad, s));
+    TKS_CUDA(h, cudaMalloc(&h->d_col16, nnz * sizeof(uint16_t) + pad));
+    TKS_CUDA(h, cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_col16) + nnz * sizeof(uint16_t), 0, pad, s));
+    const size_t rowbits_bytes = ((nnz + 31) / 32) * 4 + pad;
+    TKS_CUDA(h, cudaMalloc(&h->d_rowbits, rowbits_bytes));
+    TKS_CUDA(h, cudaMemsetAsync(h->d_rowbits, 0, rowbits_bytes, s));
     TKS_CUDA(h, cudaMalloc(&h->d_chunk_start, (nch + 1) * sizeof(uint64_t)));
     TKS_CUDA(h, cudaMalloc(&h->d_chunk_ord, nch * sizeof(uint32_t)));
     uint32_t *d_err = nullptr, *d_flag = nullptr;
@@ -158,9 +162,9 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
     TKS_CUDA(h, cudaMalloc(&d_flag, (rows ? rows : 1) * sizeof(uint32_t)));
     TKS_CUDA(h, cudaMalloc(&d_ord, (rows + 1) * sizeof(uint64_t)));
 
-    if (nnz > 0) csr_copy_cols_kernel<P><<<h->num_sms * 8, 256, 0, s>>>(d_idx, nnz, cols, h->d_colf, d_err);
+    if (nnz > 0) csr_copy_cols_kernel<P><<<h->num_sms * 8, 256, 0, s>>>(d_idx, nnz, cols, h->d_col16, d_err);
     if (rows > 0) {
-        csr_mark_rows_kernel<P><<<(uint32_t)((rows + 255) / 256), 256, 0, s>>>(d_ptr, rows, nnz, h->d_colf, d_flag, d_err);
+        csr_mark_rows_kernel<P><<<(uint32_t)((rows + 255) / 256), 256, 0, s>>>(d_ptr, rows, nnz, h->d_rowbits, d_flag, d_err);
         int rc = device_scan_u32(h, d_flag, rows, d_ord);
         if (rc) return rc;
     } else {
@@ -187,7 +191,7 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
                        (herr & kErrPtrOrder) ? " row_ptr not monotone / out of range;" : "");
     }
     h->rows = rows; h->cols = cols; h->nnz = nnz;
-    h->device_bytes = nnz * 8ull + (nch + 1) * 8ull + nch * 4ull + (has_empty ? n_nonempty * 4ull : 0ull);
+    h->device_bytes = nnz * 6ull + (nnz + 7) / 8 + (nch + 1) * 8ull + nch * 4ull + (has_empty ? n_nonempty * 4ull : 0ull);
     h->have_matrix = true;
     h->have_result = false;
     h->stats.rows = rows; h->stats.cols = cols; h->stats.nnz = nnz; h->stats.packets = 0;
@@ -208,7 +212,7 @@ int check_float_upload(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, ui
 void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool profile) {
     const int variant = cap_variant_for_k(k);
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
-    CsrDevice m{h->d_val, h->d_colf, h->d_chunk_start, h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols,
+    CsrDevice m{h->d_val, h->d_col16, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start, h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols,
                 (uint32_t)h->row_offset};
     uint32_t n_sample = h->n_chunks < (uint32_t)h->num_sms * 32u ? h->n_chunks : (uint32_t)h->num_sms * 32u;
     if (n_sample > h->n_sample_cap) n_sample = h->n_sample_cap;
@@ -246,7 +250,7 @@ void launch_batched_kernel(Handle *h, const CsrDevice &m, const BatchedArgs &a, 
 
 // One matrix pass per 32 queries (csr_batched.cuh).
 void launch_batched(Handle *h, uint32_t k, cudaStream_t s, bool profile) {
-    CsrDevice m{h->d_val, h->d_colf, h->d_chunk_start, h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols,
+    CsrDevice m{h->d_val, h->d_col16, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start, h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols,
                 (uint32_t)h->row_offset};
     BatchedArgs a{};
     a.xT = h->d_xT;
@@ -552,8 +556,10 @@ int tks_download_csr(tks_handle *h, uint64_t *ptr64, uint32_t *idx, float *val) 
     if (ptr64) TKS_CUDA(h, cudaMemcpy(ptr64, h->d_ptr64, (h->rows + 1) * 8, cudaMemcpyDeviceToHost));
     if (val) TKS_CUDA(h, cudaMemcpy(val, h->d_val, h->nnz * 4, cudaMemcpyDeviceToHost));
     if (idx) {
-        TKS_CUDA(h, cudaMemcpy(idx, h->d_colf, h->nnz * 4, cudaMemcpyDeviceToHost));
-        for (uint64_t i = 0; i < h->nnz; i++) idx[i] = (idx[i] & kColOffMask) >> 2;
+        // col16 holds column * 4: fetch the 16-bit words into the upper half of the output, widen in place
+        uint16_t *tmp = reinterpret_cast<uint16_t *>(idx) + h->nnz;
+        TKS_CUDA(h, cudaMemcpy(tmp, h->d_col16, h->nnz * 2, cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < h->nnz; i++) idx[i] = (uint32_t)tmp[i] >> 2;
     }
     return TKS_OK;
 }

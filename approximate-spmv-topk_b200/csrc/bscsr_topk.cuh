@@ -44,6 +44,7 @@ constexpr uint32_t kBsMaxPieces = 40;         // sample pieces per partition (bo
 constexpr uint32_t kReplayThreads = 1024;      // one tile covers the ~800 chunks of a cfg3 partition
 constexpr uint32_t kReplaySurvivors = 8192;   // log entries buffered between sequential replays (dynamic smem)
 constexpr uint32_t kReplayDynSmem = kReplaySurvivors * 8u;
+constexpr uint32_t kReplayCpt = 4;             // chunks per replay thread and tile
 
 struct BscsrChunks {
     const uint32_t *first;      // global index of the chunk's first packet
@@ -646,7 +647,7 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
     const unsigned lane = lane_id();
     extern __shared__ __align__(16) uint8_t replay_smem[];   // kReplayDynSmem bytes
     uint32_t *s_sv = reinterpret_cast<uint32_t *>(replay_smem), *s_sr = s_sv + kReplaySurvivors;
-    __shared__ uint32_t s_wsum[kReplayThreads / 32], s_off[kReplayThreads + 1];
+    __shared__ uint32_t s_wsum[kReplayThreads / 32], s_off[kReplayThreads * kReplayCpt + 1];
     __shared__ uint32_t s_n;
     if (tid == 0) s_n = 0;
     if (blockIdx.x == 0 && tid == 0 && chunk_counter_reset) *chunk_counter_reset = 0;   // [1]: log entries, statistics
@@ -705,12 +706,19 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
         __syncthreads();
     };
 
-    // chunks of the partition, kReplayThreads at a time: thread t copies the log of chunk t to its place
-    for (uint32_t t0 = cb; t0 < ce; t0 += blockDim.x) {
-        const uint32_t c = t0 + tid;
-        uint32_t cnt = (c < ce) ? logs.cnt[(size_t)c * LFR + j] : 0u;
-        // block-wide exclusive scan of cnt
-        uint32_t inc = cnt;
+    // chunks of the partition, kReplayThreads * kReplayCpt at a time (one tile covers any cfg3 partition): thread t owns
+    // kReplayCpt consecutive chunks; the tile's log entries are copied to the buffer in stream order
+    const uint32_t tile = blockDim.x * kReplayCpt;
+    for (uint32_t t0 = cb; t0 < ce; t0 += tile) {
+        uint32_t cnt[kReplayCpt], mine = 0;
+#pragma unroll
+        for (uint32_t u = 0; u < kReplayCpt; u++) {
+            const uint32_t c = t0 + tid * kReplayCpt + u;
+            cnt[u] = (c < ce) ? logs.cnt[(size_t)c * LFR + j] : 0u;
+            mine += cnt[u];
+        }
+        // block-wide exclusive scan of the per-thread totals
+        uint32_t inc = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
@@ -727,7 +735,7 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
         }
         if (all > kReplaySurvivors) {
             // logs longer than the buffer (adversarial inputs): replay them straight from memory, in order
-            const uint32_t tend = (t0 + blockDim.x < ce) ? t0 + blockDim.x : ce;
+            const uint32_t tend = (t0 + tile < ce) ? t0 + tile : ce;
             for (uint32_t cc = t0; cc < tend; cc++) {
                 const uint32_t n_c = logs.cnt[(size_t)cc * LFR + j];
                 const size_t lbc = ((size_t)cc * LFR + j) * chunk_cap;
@@ -743,12 +751,16 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
         }
         // order-preserving gather: entry f of the tile's concatenated logs belongs to the chunk whose
         // exclusive offset is the last one <= f
-        s_off[tid] = before + inc - cnt;
-        if (tid == 0) s_off[blockDim.x] = all;
+        {
+            uint32_t o = before + inc - mine;
+#pragma unroll
+            for (uint32_t u = 0; u < kReplayCpt; u++) { s_off[tid * kReplayCpt + u] = o; o += cnt[u]; }
+        }
+        if (tid == 0) s_off[tile] = all;
         __syncthreads();
         const uint32_t base_n = s_n;
         for (uint32_t f = tid; f < all; f += blockDim.x) {
-            uint32_t lo = 0, hi = blockDim.x;
+            uint32_t lo = 0, hi = tile;
             while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= f) lo = mid; else hi = mid; }
             const size_t e = ((size_t)(t0 + lo) * LFR + j) * chunk_cap + (f - s_off[lo]);
             s_sv[base_n + f] = logs.val[e];

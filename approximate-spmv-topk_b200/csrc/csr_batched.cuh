@@ -155,36 +155,37 @@ __device__ __forceinline__ void batched_stream(const CsrDevice &m, const Batched
     L.acc[0] = L.acc[1] = L.acc[2] = L.acc[3] = 0.0f;
     L.have_row = false;
     const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val + a0) + l8 * 32u;
-    const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.colf + a0) + l8 * 32u;
+    const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.col16 + a0) + l8 * 16u;
+    const uint8_t *rp = m.rowbits + (a0 >> 3) + l8;
     const uint32_t zero_off = m.cols * (kBqPerPass * 4u);   // the all-zero table row
     float *sval = reinterpret_cast<float *>(stage);
     uint32_t *scol = reinterpret_cast<uint32_t *>(stage + kBStage * 4u);
 
-    U32x8 nv, nc;
+    U32x8 nv;
+    U32x4 nc;
+    uint32_t nr = 0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) { nv.w[j] = 0; nc.w[j] = 0; }
-    if (nb > 0) { nv = ldg_stream_256(vp); nc = ldg_stream_256(cp); }
+    for (int j = 0; j < 8; j++) nv.w[j] = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) nc.w[j] = 0;
+    if (nb > 0) { nv = ldg_stream_256(vp); nc = ldg_stream_128(cp); nr = ldg_stream_u8(rp); }
     for (uint32_t b = 0; b < nb_w; b++) {
-        // column words become byte offsets of the table row (col * 128, row-start flag kept in bit 31)
+        // column offsets (col * 4) become byte offsets of the table row (col * 128), the row-start bit goes to bit 31
         uint32_t cw[8], vw[8];
+        uint32_t lo = 0, hi = 8;
         if (b == 0 || b + 1 >= nb) {
             const int64_t ebase = (int64_t)(a0 + (uint64_t)b * kBStage + l8 * 8u);
             const int64_t l64 = (int64_t)s - ebase, h64 = (int64_t)e - ebase;
-            uint32_t lo = l64 < 0 ? 0u : (l64 > 8 ? 8u : (uint32_t)l64);
-            uint32_t hi = h64 < 0 ? 0u : (h64 > 8 ? 8u : (uint32_t)h64);
+            lo = l64 < 0 ? 0u : (l64 > 8 ? 8u : (uint32_t)l64);
+            hi = h64 < 0 ? 0u : (h64 > 8 ? 8u : (uint32_t)h64);
             if (b >= nb) { lo = 0; hi = 0; }
+        }
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const bool in = ((uint32_t)j >= lo) && ((uint32_t)j < hi);
-                cw[j] = in ? (((nc.w[j] & kColOffMask) << 5) | (nc.w[j] & kRowStartBit)) : zero_off;
-                vw[j] = in ? nv.w[j] : 0u;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                cw[j] = ((nc.w[j] & kColOffMask) << 5) | (nc.w[j] & kRowStartBit);
-                vw[j] = nv.w[j];
-            }
+        for (int j = 0; j < 8; j++) {
+            const uint32_t c16 = (j & 1) ? (nc.w[j >> 1] >> 16) : (nc.w[j >> 1] & 0xFFFFu);
+            const bool in = ((uint32_t)j >= lo) && ((uint32_t)j < hi);
+            cw[j] = in ? ((c16 << 5) | (((nr >> j) & 1u) << 31)) : zero_off;
+            vw[j] = in ? nv.w[j] : 0u;
         }
         __syncwarp();   // the previous batch has been consumed
         reinterpret_cast<uint4 *>(sval)[l8 * 2] = make_uint4(vw[0], vw[1], vw[2], vw[3]);
@@ -194,7 +195,8 @@ __device__ __forceinline__ void batched_stream(const CsrDevice &m, const Batched
         __syncwarp();
         if (b + 1 < nb) {   // next batch in flight while this one is consumed
             nv = ldg_stream_256(vp + (size_t)(b + 1) * (kBStage * 4u));
-            nc = ldg_stream_256(cp + (size_t)(b + 1) * (kBStage * 4u));
+            nc = ldg_stream_128(cp + (size_t)(b + 1) * (kBStage * 2u));
+            nr = ldg_stream_u8(rp + (size_t)(b + 1) * (kBStage / 8u));
         }
 #pragma unroll 4
         for (uint32_t i = 0; i < kBStage / 4; i++) {

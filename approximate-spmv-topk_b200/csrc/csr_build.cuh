@@ -1,5 +1,5 @@
 // csr_build.cuh -- one-time (per matrix) device-side preparation for the fused CSR kernel:
-//   * colf = column | row-delta << 14   (see csr_topk.cuh)
+//   * col16 = column * 4 (u16) and the row-start bitmap   (see csr_topk.cuh)
 //   * chunk table aligned to row starts
 //   * synthetic matrices generated in HBM with the law of the reference generator
 //     (src/resources/python/create_matrices.py:84-104), for sizes no MTX file can hold.
@@ -16,14 +16,14 @@ constexpr uint32_t kErrPtrOrder = 4u;     // row_ptr not non-decreasing / out of
 
 template <typename P>
 __global__ void csr_copy_cols_kernel(const uint32_t *__restrict__ idx, uint64_t nnz, uint32_t cols,
-                                     uint32_t *__restrict__ colf, uint32_t *err) {
+                                     uint16_t *__restrict__ col16, uint32_t *err) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     bool bad = false;
     for (; i < nnz; i += stride) {
         uint32_t c = idx[i];
         bad |= (c >= cols);
-        colf[i] = (c << 2) & kColOffMask;
+        col16[i] = (uint16_t)((c << 2) & kColOffMask);
     }
     if (bad) atomicOr(err, kErrColRange);
 }
@@ -31,13 +31,13 @@ __global__ void csr_copy_cols_kernel(const uint32_t *__restrict__ idx, uint64_t 
 // One thread per row: tag the row's first non-zero; count non-empty rows.
 template <typename P>
 __global__ void csr_mark_rows_kernel(const P *__restrict__ ptr, uint64_t rows, uint64_t nnz,
-                                     uint32_t *__restrict__ colf, uint32_t *nonempty_flag, uint32_t *err) {
+                                     uint32_t *__restrict__ rowbits32, uint32_t *nonempty_flag, uint32_t *err) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const uint64_t b = ptr[r], e = ptr[r + 1];
     if (e < b || e > nnz) { atomicOr(err, kErrPtrOrder); nonempty_flag[r] = 0; return; }
     nonempty_flag[r] = (b != e) ? 1u : 0u;
-    if (b != e) colf[b] |= kRowStartBit;
+    if (b != e) atomicOr(&rowbits32[b >> 5], 1u << (b & 31u));   // little-endian: bit b%8 of byte b/8
 }
 
 // row_map[ordinal] = row for non-empty rows, given ord = exclusive scan of the non-empty flags (as u64).

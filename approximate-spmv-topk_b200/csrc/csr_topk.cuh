@@ -7,11 +7,13 @@
 // list of candidates.  See DESIGN.md for the layout, the roofline and the
 // argument that the result equals the exact top-k under the stated total order.
 //
-// Device layout (built once by tks_upload_csr, see csr_build.cuh):
-//   val  [nnz]  fp32, as uploaded
-//   colf [nnz]  u32 : bits 0..15 = column * 4 (the byte offset of x[col] in shared
-//                     memory), bit 31 = "this non-zero starts a row".  Same 4 bytes
-//                     as a CSR column index, so the kernel never reads row_ptr.
+// Device layout (built once by tks_upload_csr, see csr_build.cuh): 6.125 bytes per non-zero
+//   val     [nnz]    fp32, as uploaded
+//   col16   [nnz]    u16 : column * 4 = the byte offset of x[col] in shared memory
+//                     (columns <= 16383, so 16 bits always suffice: a third less
+//                     index traffic than CSR's 32-bit column indices)
+//   rowbits [nnz/8]  u8  : bit j of byte i <=> non-zero 8i+j starts a row, so the
+//                     kernel never reads row_ptr
 //   chunk_start[c], chunk_ord[c] : work units of ~chunk_nnz non-zeros aligned to row
 //                     starts; ord = ordinal of the chunk's first row among the
 //                     non-empty rows.  row_map[ord] -> row id exists only when the
@@ -28,7 +30,7 @@
 namespace tks {
 
 constexpr uint32_t kColOffMask = 0xFFFCu;                   // column * 4
-constexpr uint32_t kRowStartBit = 0x80000000u;
+constexpr uint32_t kRowStartBit = 0x80000000u;              // batched kernel's staged column words only
 constexpr uint32_t kMaxCols = 16384;                       // exclusive: cols <= 16383 (slot `cols` holds 0.0)
 constexpr uint32_t kEpl = 8;                                // elements per lane: one 256-bit load per array
 constexpr uint32_t kElemsPerIter = kWarp * kEpl;            // 256 non-zeros per warp iteration
@@ -38,7 +40,8 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 
 struct CsrDevice {
     const float *val;
-    const uint32_t *colf;
+    const uint16_t *col16;         // column * 4
+    const uint8_t *rowbits;        // one row-start bit per non-zero
     const uint64_t *chunk_start;   // n_chunks + 1 entries
     const uint32_t *chunk_ord;     // n_chunks entries
     const uint32_t *row_map;       // ordinal -> row id, or nullptr when every row is non-empty
@@ -58,6 +61,7 @@ struct RunState {
 };
 
 struct U32x8 { uint32_t w[8]; };
+struct U32x4 { uint32_t w[4]; };
 
 // 256-bit streaming load (LDG.E.256 on sm_100): read-only path, no L1 allocation --
 // every matrix byte is touched exactly once per query.
@@ -67,6 +71,19 @@ __device__ __forceinline__ U32x8 ldg_stream_256(const void *p) {
                  : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]),
                    "=r"(r.w[6]), "=r"(r.w[7])
                  : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ U32x4 ldg_stream_128(const void *p) {
+    U32x4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u8(const void *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
 
@@ -91,25 +108,25 @@ struct IterState {
 };
 
 template <bool MASKED>
-__device__ __forceinline__ void csr_iter(const U32x8 &vraw, const U32x8 &craw, const uint8_t *__restrict__ xs_bytes,
-                                         uint32_t zero_off, uint32_t lo, uint32_t hi, float carry_in,
-                                         float &carry_out, IterState &o) {
+__device__ __forceinline__ void csr_iter(const U32x8 &vraw, const U32x4 &craw, uint32_t rbits,
+                                         const uint8_t *__restrict__ xs_bytes, uint32_t zero_off, uint32_t lo,
+                                         uint32_t hi, float carry_in, float &carry_out, IterState &o) {
     const unsigned lane = lane_id();
-    uint32_t frev = 0;
     float cm = neg_inf();
+    // bit j <=> element j starts a row (elements outside [lo, hi) start nothing)
+    const uint32_t fb = MASKED ? (rbits & ((1u << hi) - 1u) & ~((1u << lo) - 1u)) : rbits;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        uint32_t c = craw.w[j];
+        uint32_t c = (j & 1) ? (craw.w[j >> 1] >> 16) : (craw.w[j >> 1] & 0xFFFFu);   // column * 4
         uint32_t vbits = vraw.w[j];
         if (MASKED) {
             const bool in = ((uint32_t)j >= lo) && ((uint32_t)j < hi);
-            c = in ? c : zero_off;      // column -> the zero slot behind x, no row start
+            c = in ? c : zero_off;      // column -> the zero slot behind x
             vbits = in ? vbits : 0u;
         }
-        const float x = *reinterpret_cast<const float *>(xs_bytes + (c & kColOffMask));
+        const float x = *reinterpret_cast<const float *>(xs_bytes + c);
         const float p = __fmul_rn(__uint_as_float(vbits), x);
-        const bool f = (int32_t)c < 0;
-        frev = __funnelshift_l(c, frev, 1);   // collects bit 31 of every element
+        const bool f = (fb >> j) & 1u;
         if (j == 0) {
             o.seg[0] = p;
         } else {
@@ -118,7 +135,7 @@ __device__ __forceinline__ void csr_iter(const U32x8 &vraw, const U32x8 &craw, c
         }
     }
     o.cm = cm;
-    o.fb = __brev(frev) >> 24;   // bit j <=> element j starts a row
+    o.fb = fb;
     o.nf = __popc(o.fb);
     o.fm = __ballot_sync(kFull, o.fb != 0);
 
@@ -208,20 +225,26 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
     const uint32_t n_iter = truncated ? max_iters : (uint32_t)n_iter64;
     const uint32_t last_iter = (uint32_t)n_iter64 - 1;   // chunks are far smaller than 2^32 * 256 non-zeros
     const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val + a0) + lane * 32u;
-    const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.colf + a0) + lane * 32u;
+    const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.col16 + a0) + lane * 16u;
+    const uint8_t *rp = m.rowbits + (a0 >> 3) + lane;
     const uint32_t zero_off = m.cols * 4u;
 
     uint32_t R = m.chunk_ord[c] - 1u;   // ordinal of the row "in progress" (a bogus one before the chunk at first)
     bool first_pending = true;
     float carry = 0.0f;
 
-    U32x8 nv = ldg_stream_256(vp), nc = ldg_stream_256(cp);
+    U32x8 nv = ldg_stream_256(vp);
+    U32x4 nc = ldg_stream_128(cp);
+    uint32_t nr = ldg_stream_u8(rp);
 #pragma unroll 2
     for (uint32_t it = 0; it < n_iter; it++) {
-        const U32x8 cv = nv, cc = nc;
+        const U32x8 cv = nv;
+        const U32x4 cc = nc;
+        const uint32_t cr = nr;
         vp += kElemsPerIter * 4u;
-        cp += kElemsPerIter * 4u;
-        if (it + 1 < n_iter) { nv = ldg_stream_256(vp); nc = ldg_stream_256(cp); }
+        cp += kElemsPerIter * 2u;
+        rp += kElemsPerIter / 8u;
+        if (it + 1 < n_iter) { nv = ldg_stream_256(vp); nc = ldg_stream_128(cp); nr = ldg_stream_u8(rp); }
         IterState o;
         float carry_out;
         if (it == 0 || it == last_iter) {
@@ -230,9 +253,9 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
             const int64_t l64 = (int64_t)s - ebase, h64 = (int64_t)e - ebase;
             const uint32_t lo = l64 < 0 ? 0u : (l64 > 8 ? 8u : (uint32_t)l64);
             const uint32_t hi = h64 < 0 ? 0u : (h64 > 8 ? 8u : (uint32_t)h64);
-            csr_iter<true>(cv, cc, xs_bytes, zero_off, lo, hi, carry, carry_out, o);
+            csr_iter<true>(cv, cc, cr, xs_bytes, zero_off, lo, hi, carry, carry_out, o);
         } else {
-            csr_iter<false>(cv, cc, xs_bytes, zero_off, 0u, 8u, carry, carry_out, o);
+            csr_iter<false>(cv, cc, cr, xs_bytes, zero_off, 0u, 8u, carry, carry_out, o);
         }
         carry = carry_out;
 

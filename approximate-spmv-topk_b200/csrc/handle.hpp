@@ -29,7 +29,8 @@ struct Handle {
     uint64_t rows = 0, nnz = 0, row_offset = 0;
     uint32_t cols = 0;
     float *d_val = nullptr;
-    uint32_t *d_colf = nullptr;
+    uint16_t *d_col16 = nullptr;        // column * 4
+    uint32_t *d_rowbits = nullptr;      // row-start bitmap, one bit per non-zero (zeroed words, atomicOr at build)
     uint64_t *d_ptr64 = nullptr;        // kept for tks_download_csr (exact copy of row_ptr as u64)
     uint64_t *d_chunk_start = nullptr;
     uint32_t *d_chunk_ord = nullptr;
