@@ -1,5 +1,6 @@
 // api.cu -- C ABI of libtopkspmv.so (see include/topkspmv.h), float CSR path and dispatch.
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "csr_build.cuh"
@@ -24,30 +25,52 @@ int cap_variant_for_k(uint32_t k) {
     return 3;
 }
 
-size_t main_smem_bytes(uint32_t cols, int variant) {
-    return (((cols + 1u) * 4u + 15u) & ~15u) + (size_t)(kCapThreads[variant] / 32) * kCaps[variant] * 8u;
+size_t main_smem_bytes(uint32_t cols, int variant, int xrep, int threads) {
+    return (((cols + 1u) * 4u * (uint32_t)xrep + 15u) & ~15u) + (size_t)(threads / 32) * kCaps[variant] * 8u;
 }
+
+// k <= 128 and narrow matrices: 32 query copies (conflict-free gathers), one 1024-thread CTA per SM
+constexpr int kXrepWide = 32, kXrepThreads = 1024;
 
 template <int CAP>
 cudaError_t prep_main(Handle *h, int variant) {
-    size_t smem = main_smem_bytes(h->cfg.max_cols, variant);
-    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    size_t smem = main_smem_bytes(h->cfg.max_cols, variant, 1, kCapThreads[variant]);
+    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP>, kCapThreads[variant],
-                                                      smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, 1, 512>, kCapThreads[variant], smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     h->main_grid[variant] = per_sm * h->num_sms;
     return cudaSuccess;
 }
 
+// The 32-copy variant exists for CAP = 256 only (the pool buffers of larger k do not fit beside the copies).
+cudaError_t prep_main_xrep(Handle *h, size_t smem_optin) {
+    h->use_xrep = false;
+    const char *env = std::getenv("TKS_CSR_XREP");
+    if (env && std::atoi(env) == 1) return cudaSuccess;
+    const size_t smem = main_smem_bytes(h->cfg.max_cols, 0, kXrepWide, kXrepThreads);
+    if (smem > smem_optin) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<256, kXrepWide, kXrepThreads>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    h->use_xrep = true;
+    return cudaSuccess;
+}
+
 template <int CAP>
 void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, RunState *st, uint32_t k,
                  cudaStream_t s) {
-    size_t smem = main_smem_bytes(m.cols, variant);
-    csr_topk_main_kernel<CAP><<<h->main_grid[variant], kCapThreads[variant], smem, s>>>(
+    if (CAP == 256 && h->use_xrep && main_smem_bytes(m.cols, 0, kXrepWide, kXrepThreads) <= main_smem_bytes(h->cfg.max_cols, 0, kXrepWide, kXrepThreads)) {
+        const size_t smem = main_smem_bytes(m.cols, 0, kXrepWide, kXrepThreads);
+        csr_topk_main_kernel<256, kXrepWide, kXrepThreads><<<h->num_sms, kXrepThreads, smem, s>>>(
+            m, x, st, h->d_pool, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX);
+        return;
+    }
+    size_t smem = main_smem_bytes(m.cols, variant, 1, kCapThreads[variant]);
+    csr_topk_main_kernel<CAP, 1, 512><<<h->main_grid[variant], kCapThreads[variant], smem, s>>>(
         m, x, st, h->d_pool, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX);
 }
 
@@ -424,6 +447,7 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
         if ((e = prep_main<512>(h, 1)) != cudaSuccess) return bail("prep_main<512>", e);
         if ((e = prep_main<1024>(h, 2)) != cudaSuccess) return bail("prep_main<1024>", e);
         if ((e = prep_main<2048>(h, 3)) != cudaSuccess) return bail("prep_main<2048>", e);
+        if ((e = prep_main_xrep(h, (size_t)prop.sharedMemPerBlockOptin)) != cudaSuccess) return bail("prep_main_xrep", e);
         {
             size_t ss = ((size_t)cfg->max_cols + 1u) * 4u;
             if (ss < 8192u * 4u) ss = 8192u * 4u;

@@ -107,10 +107,13 @@ struct IterState {
     unsigned fm;   // ballot: lanes with >= 1 row start
 };
 
-template <bool MASKED>
-__device__ __forceinline__ void csr_iter(const U32x8 &vraw, const U32x4 &craw, uint32_t rbits,
-                                         const uint8_t *__restrict__ xs_bytes, uint32_t zero_off, uint32_t lo,
-                                         uint32_t hi, float carry_in, float &carry_out, IterState &o) {
+// XREP: interleaved copies of the query in shared memory (word col * XREP + lane % XREP).  With 32 copies every
+// lane gathers from its own bank: the random gathers stop conflicting (3.5-way with a single copy).
+// xs_addr: 32-bit shared-memory address of this lane's copy.
+template <bool MASKED, int XREP>
+__device__ __forceinline__ void csr_iter(const U32x8 &vraw, const U32x4 &craw, uint32_t rbits, uint32_t xs_addr,
+                                         uint32_t zero_off, uint32_t lo, uint32_t hi, float carry_in,
+                                         float &carry_out, IterState &o) {
     const unsigned lane = lane_id();
     float cm = neg_inf();
     // bit j <=> element j starts a row (elements outside [lo, hi) start nothing)
@@ -124,7 +127,8 @@ __device__ __forceinline__ void csr_iter(const U32x8 &vraw, const U32x4 &craw, u
             c = in ? c : zero_off;      // column -> the zero slot behind x
             vbits = in ? vbits : 0u;
         }
-        const float x = *reinterpret_cast<const float *>(xs_bytes + c);
+        float x;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(c * (uint32_t)XREP + xs_addr));
         const float p = __fmul_rn(__uint_as_float(vbits), x);
         const bool f = (fb >> j) & 1u;
         if (j == 0) {
@@ -213,10 +217,11 @@ struct PoolSink {
 };
 
 // Stream one chunk (or its first max_iters iterations) through `sink`.
-template <typename Sink>
+template <int XREP, typename Sink>
 __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint32_t c,
                                                   uint32_t max_iters, Sink &sink) {
     const unsigned lane = lane_id();
+    const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs_bytes) + (lane & (uint32_t)(XREP - 1)) * 4u;
     const uint64_t s = m.chunk_start[c], e = m.chunk_start[c + 1];
     if (s >= e) return;
     const uint64_t a0 = s & ~7ull;                       // 32-byte aligned start of the first 256-bit load
@@ -253,9 +258,9 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
             const int64_t l64 = (int64_t)s - ebase, h64 = (int64_t)e - ebase;
             const uint32_t lo = l64 < 0 ? 0u : (l64 > 8 ? 8u : (uint32_t)l64);
             const uint32_t hi = h64 < 0 ? 0u : (h64 > 8 ? 8u : (uint32_t)h64);
-            csr_iter<true>(cv, cc, cr, xs_bytes, zero_off, lo, hi, carry, carry_out, o);
+            csr_iter<true, XREP>(cv, cc, cr, xs_addr, zero_off, lo, hi, carry, carry_out, o);
         } else {
-            csr_iter<false>(cv, cc, cr, xs_bytes, zero_off, 0u, 8u, carry, carry_out, o);
+            csr_iter<false, XREP>(cv, cc, cr, xs_addr, zero_off, 0u, 8u, carry, carry_out, o);
         }
         carry = carry_out;
 
@@ -378,7 +383,7 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
     if (gw < n_sample) {
         MaxSink sink{0.0f, false, neg_inf()};
         const uint32_t c = gw * stride;
-        if (c < m.n_chunks) csr_process_chunk(m, smem_raw, c, sample_iters, sink);
+        if (c < m.n_chunks) csr_process_chunk<1>(m, smem_raw, c, sample_iters, sink);
         uint32_t key = sink.any ? f32_to_ordered(sink.best) : 0u;
         key = __reduce_max_sync(kFull, key);
         if (lane_id() == 0) sample_keys[gw] = key;
@@ -407,14 +412,18 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
 // counter, reduces them, and keeps rows with score >= tau in a private
 // shared-memory buffer (sorted and cut to k only if it ever fills).
 // --------------------------------------------------------------------------
-template <int CAP>
-__global__ void __launch_bounds__(kMainThreads, 2)
+// XREP = 1: 2 CTAs x 512 threads per SM.  XREP = 32: one CTA x 1024 threads per SM sharing 32 copies of the query.
+template <int CAP, int XREP, int THREADS>
+__global__ void __launch_bounds__(THREADS, XREP > 1 ? 1 : 2)
 csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uint64_t *pool, uint32_t k,
                      int tie_higher) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float *xs = reinterpret_cast<float *>(smem_raw);
-    uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (((m.cols + 1u) * 4u + 15u) & ~15u));
-    for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? x[i] : 0.0f;
+    uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (((m.cols + 1u) * 4u * XREP + 15u) & ~15u));
+    for (uint32_t i = threadIdx.x; i < (m.cols + 1u) * XREP; i += blockDim.x) {
+        const uint32_t col = i / XREP;
+        xs[i] = (col < m.cols) ? x[col] : 0.0f;
+    }
     __syncthreads();
 
     const unsigned lane = lane_id();
@@ -434,7 +443,7 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
         c = __shfl_sync(kFull, c, 0);
         if (c >= m.n_chunks) break;
         sink.tau = fmaxf(sink.tau, tau_from_key(ld_relaxed_u32(&st->tau_key)));
-        csr_process_chunk(m, smem_raw, c, 0xFFFFFFFFu, sink);
+        csr_process_chunk<XREP>(m, smem_raw, c, 0xFFFFFFFFu, sink);
     }
 
     // hand the survivors to the global pool (filtered by the freshest bound)
