@@ -49,6 +49,7 @@ cudaError_t prep_main(Handle *h, int variant) {
 // The 32-copy variant exists for CAP = 256 only (the pool buffers of larger k do not fit beside the copies).
 cudaError_t prep_main_xrep(Handle *h, size_t smem_optin) {
     h->use_xrep = false;
+    if (const char *pf = std::getenv("TKS_CSR_L2PF")) h->l2_prefetch = (uint32_t)std::atoi(pf);
     const char *env = std::getenv("TKS_CSR_XREP");
     if (env && std::atoi(env) == 1) return cudaSuccess;
     const size_t smem = main_smem_bytes(h->cfg.max_cols, 0, kXrepWide, kXrepThreads);
@@ -236,7 +237,7 @@ void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool
     const int variant = cap_variant_for_k(k);
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
     CsrDevice m{h->d_val, h->d_col16, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start, h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols,
-                (uint32_t)h->row_offset};
+                (uint32_t)h->row_offset, h->l2_prefetch};
     uint32_t n_sample = h->n_chunks < (uint32_t)h->num_sms * 32u ? h->n_chunks : (uint32_t)h->num_sms * 32u;
     if (n_sample > h->n_sample_cap) n_sample = h->n_sample_cap;
     const uint32_t stride = h->n_chunks / n_sample;
@@ -274,7 +275,7 @@ void launch_batched_kernel(Handle *h, const CsrDevice &m, const BatchedArgs &a, 
 // One matrix pass per 32 queries (csr_batched.cuh).
 void launch_batched(Handle *h, uint32_t k, cudaStream_t s, bool profile) {
     CsrDevice m{h->d_val, h->d_col16, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start, h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols,
-                (uint32_t)h->row_offset};
+                (uint32_t)h->row_offset, h->l2_prefetch};
     BatchedArgs a{};
     a.xT = h->d_xT;
     a.st = h->d_state;

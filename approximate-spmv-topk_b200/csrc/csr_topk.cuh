@@ -48,6 +48,7 @@ struct CsrDevice {
     uint32_t n_chunks;
     uint32_t cols;
     uint32_t row_offset;           // added to every reported row id
+    uint32_t l2_prefetch;          // iterations ahead that are pulled into L2 (0 = off); registers hold one more
 };
 
 // Per-query scratch that lives in HBM; zeroed at creation and by the select kernel.
@@ -217,12 +218,12 @@ struct PoolSink {
 };
 
 // Stream one chunk (or its first max_iters iterations) through `sink`.
+// [s, e): the chunk's non-zeros, ord0: ordinal of its first row (chunk table entries, loaded by the caller).
 template <int XREP, typename Sink>
-__device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint32_t c,
-                                                  uint32_t max_iters, Sink &sink) {
+__device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint64_t s,
+                                                  uint64_t e, uint32_t ord0, uint32_t max_iters, Sink &sink) {
     const unsigned lane = lane_id();
     const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs_bytes) + (lane & (uint32_t)(XREP - 1)) * 4u;
-    const uint64_t s = m.chunk_start[c], e = m.chunk_start[c + 1];
     if (s >= e) return;
     const uint64_t a0 = s & ~7ull;                       // 32-byte aligned start of the first 256-bit load
     const uint64_t n_iter64 = (e - a0 + kElemsPerIter - 1) / kElemsPerIter;
@@ -234,7 +235,7 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
     const uint8_t *rp = m.rowbits + (a0 >> 3) + lane;
     const uint32_t zero_off = m.cols * 4u;
 
-    uint32_t R = m.chunk_ord[c] - 1u;   // ordinal of the row "in progress" (a bogus one before the chunk at first)
+    uint32_t R = ord0 - 1u;   // ordinal of the row "in progress" (a bogus one before the chunk at first)
     bool first_pending = true;
     float carry = 0.0f;
 
@@ -250,6 +251,13 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
         cp += kElemsPerIter * 2u;
         rp += kElemsPerIter / 8u;
         if (it + 1 < n_iter) { nv = ldg_stream_256(vp); nc = ldg_stream_128(cp); nr = ldg_stream_u8(rp); }
+        if (m.l2_prefetch && it + m.l2_prefetch < n_iter) {
+            // the registers hold one iteration ahead (1.5 KB per warp); pulling later iterations into L2 shortens the
+            // latency those loads will see, which is what bounds the kernel once the matrix is 6 B per non-zero
+            const uint32_t d = m.l2_prefetch - 1u;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + (size_t)d * (kElemsPerIter * 4u)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + (size_t)d * (kElemsPerIter * 2u)));
+        }
         IterState o;
         float carry_out;
         if (it == 0 || it == last_iter) {
@@ -383,7 +391,8 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
     if (gw < n_sample) {
         MaxSink sink{0.0f, false, neg_inf()};
         const uint32_t c = gw * stride;
-        if (c < m.n_chunks) csr_process_chunk<1>(m, smem_raw, c, sample_iters, sink);
+        if (c < m.n_chunks)
+            csr_process_chunk<1>(m, smem_raw, m.chunk_start[c], m.chunk_start[c + 1], m.chunk_ord[c], sample_iters, sink);
         uint32_t key = sink.any ? f32_to_ordered(sink.best) : 0u;
         key = __reduce_max_sync(kFull, key);
         if (lane_id() == 0) sample_keys[gw] = key;
@@ -437,13 +446,33 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
     sink.row_offset = m.row_offset;
     sink.tie_higher = tie_higher;
 
-    for (;;) {
-        uint32_t c = 0;
-        if (lane == 0) c = atomicAdd(&st->chunk_counter, 1u);
-        c = __shfl_sync(kFull, c, 0);
-        if (c >= m.n_chunks) break;
+    // The dynamic scheduler runs two chunks ahead: while chunk c streams, chunk c+1 has been claimed with its table
+    // entries in registers (its head is pulled into L2 now), and the claim of c+2 is in flight -- no warp waits on
+    // the atomic, on the chunk table or on a cold first load between chunks.
+    auto claim = [&]() { uint32_t v = 0; if (lane == 0) v = atomicAdd(&st->chunk_counter, 1u); return v; };
+    struct Unit { uint32_t c; uint64_t s, e; uint32_t ord; };
+    auto load_unit = [&](uint32_t c) {
+        Unit u{c, 0, 0, 0};
+        if (c < m.n_chunks) { u.s = m.chunk_start[c]; u.e = m.chunk_start[c + 1]; u.ord = m.chunk_ord[c]; }
+        return u;
+    };
+    Unit cur = load_unit(__shfl_sync(kFull, claim(), 0));
+    Unit nxt = load_unit(__shfl_sync(kFull, claim(), 0));
+    uint32_t pending = claim();
+    while (cur.c < m.n_chunks) {
+        if (m.l2_prefetch && nxt.c < m.n_chunks) {
+            const uint64_t a0 = nxt.s & ~7ull;
+            for (uint32_t d = 0; d < m.l2_prefetch; d++) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(m.val + a0 + (size_t)d * kElemsPerIter + lane * kEpl));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(m.col16 + a0 + (size_t)d * kElemsPerIter + lane * kEpl));
+            }
+        }
+        const Unit nn = load_unit(__shfl_sync(kFull, pending, 0));
+        pending = claim();
         sink.tau = fmaxf(sink.tau, tau_from_key(ld_relaxed_u32(&st->tau_key)));
-        csr_process_chunk<XREP>(m, smem_raw, c, 0xFFFFFFFFu, sink);
+        csr_process_chunk<XREP>(m, smem_raw, cur.s, cur.e, cur.ord, 0xFFFFFFFFu, sink);
+        cur = nxt;
+        nxt = nn;
     }
 
     // hand the survivors to the global pool (filtered by the freshest bound)
