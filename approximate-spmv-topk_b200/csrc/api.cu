@@ -29,35 +29,54 @@ size_t main_smem_bytes(uint32_t cols, int variant, int xrep, int threads) {
     return (((cols + 1u) * 4u * (uint32_t)xrep + 15u) & ~15u) + (size_t)(threads / 32) * kCaps[variant] * 8u;
 }
 
-// k <= 128 and narrow matrices: 32 query copies (conflict-free gathers), one 1024-thread CTA per SM
 constexpr int kXrepWide = 32, kXrepThreads = 1024;
+constexpr int kDefaultDepth = 1;
 
 template <int CAP>
 cudaError_t prep_main(Handle *h, int variant) {
     size_t smem = main_smem_bytes(h->cfg.max_cols, variant, 1, kCapThreads[variant]);
-    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP, 1, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, 1, 512>, kCapThreads[variant], smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, 1, 512, 1>, kCapThreads[variant], smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     h->main_grid[variant] = per_sm * h->num_sms;
     return cudaSuccess;
 }
 
-// The 32-copy variant exists for CAP = 256 only (the pool buffers of larger k do not fit beside the copies).
+// Experimental variants of the CAP = 256 kernel (k <= 128), selected by environment variables:
+//   TKS_CSR_XREP=32   32 query copies, one 1024-thread CTA per SM (measured: no gain, the gathers are not the limit)
+//   TKS_CSR_DEPTH=2   two iterations in flight per warp, 2 CTAs x 384 threads per SM
+constexpr int kDeepThreads = 448;
 cudaError_t prep_main_xrep(Handle *h, size_t smem_optin) {
     h->use_xrep = false;
+    h->use_deep = false;
     if (const char *pf = std::getenv("TKS_CSR_L2PF")) h->l2_prefetch = (uint32_t)std::atoi(pf);
     const char *env = std::getenv("TKS_CSR_XREP");
-    if (env && std::atoi(env) == 1) return cudaSuccess;
-    const size_t smem = main_smem_bytes(h->cfg.max_cols, 0, kXrepWide, kXrepThreads);
-    if (smem > smem_optin) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<256, kXrepWide, kXrepThreads>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    h->use_xrep = true;
+    if (env && std::atoi(env) == 32) {
+        const size_t smem = main_smem_bytes(h->cfg.max_cols, 0, kXrepWide, kXrepThreads);
+        if (smem <= smem_optin) {
+            cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<256, kXrepWide, kXrepThreads, 1>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            h->use_xrep = true;
+        }
+    }
+    const char *dp = std::getenv("TKS_CSR_DEPTH");
+    const int depth = dp ? std::atoi(dp) : kDefaultDepth;
+    if (depth == 2) {
+        const size_t smem = main_smem_bytes(h->cfg.max_cols, 0, 1, kDeepThreads);
+        cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<256, 1, kDeepThreads, 2>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<256, 1, kDeepThreads, 2>, kDeepThreads, smem);
+        if (e != cudaSuccess) return e;
+        h->deep_grid = (per_sm < 1 ? 1 : per_sm) * h->num_sms;
+        h->use_deep = true;
+    }
     return cudaSuccess;
 }
 
@@ -66,12 +85,18 @@ void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, Run
                  cudaStream_t s) {
     if (CAP == 256 && h->use_xrep && main_smem_bytes(m.cols, 0, kXrepWide, kXrepThreads) <= main_smem_bytes(h->cfg.max_cols, 0, kXrepWide, kXrepThreads)) {
         const size_t smem = main_smem_bytes(m.cols, 0, kXrepWide, kXrepThreads);
-        csr_topk_main_kernel<256, kXrepWide, kXrepThreads><<<h->num_sms, kXrepThreads, smem, s>>>(
+        csr_topk_main_kernel<256, kXrepWide, kXrepThreads, 1><<<h->num_sms, kXrepThreads, smem, s>>>(
+            m, x, st, h->d_pool, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX);
+        return;
+    }
+    if (CAP == 256 && h->use_deep) {
+        const size_t smem = main_smem_bytes(m.cols, 0, 1, kDeepThreads);
+        csr_topk_main_kernel<256, 1, kDeepThreads, 2><<<h->deep_grid, kDeepThreads, smem, s>>>(
             m, x, st, h->d_pool, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX);
         return;
     }
     size_t smem = main_smem_bytes(m.cols, variant, 1, kCapThreads[variant]);
-    csr_topk_main_kernel<CAP, 1, 512><<<h->main_grid[variant], kCapThreads[variant], smem, s>>>(
+    csr_topk_main_kernel<CAP, 1, 512, 1><<<h->main_grid[variant], kCapThreads[variant], smem, s>>>(
         m, x, st, h->d_pool, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX);
 }
 

@@ -219,7 +219,7 @@ struct PoolSink {
 
 // Stream one chunk (or its first max_iters iterations) through `sink`.
 // [s, e): the chunk's non-zeros, ord0: ordinal of its first row (chunk table entries, loaded by the caller).
-template <int XREP, typename Sink>
+template <int XREP, int DEPTH, typename Sink>
 __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint64_t s,
                                                   uint64_t e, uint32_t ord0, uint32_t max_iters, Sink &sink) {
     const unsigned lane = lane_id();
@@ -239,25 +239,17 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
     bool first_pending = true;
     float carry = 0.0f;
 
-    U32x8 nv = ldg_stream_256(vp);
-    U32x4 nc = ldg_stream_128(cp);
-    uint32_t nr = ldg_stream_u8(rp);
-#pragma unroll 2
-    for (uint32_t it = 0; it < n_iter; it++) {
-        const U32x8 cv = nv;
-        const U32x4 cc = nc;
-        const uint32_t cr = nr;
-        vp += kElemsPerIter * 4u;
-        cp += kElemsPerIter * 2u;
-        rp += kElemsPerIter / 8u;
-        if (it + 1 < n_iter) { nv = ldg_stream_256(vp); nc = ldg_stream_128(cp); nr = ldg_stream_u8(rp); }
-        if (m.l2_prefetch && it + m.l2_prefetch < n_iter) {
-            // the registers hold one iteration ahead (1.5 KB per warp); pulling later iterations into L2 shortens the
-            // latency those loads will see, which is what bounds the kernel once the matrix is 6 B per non-zero
-            const uint32_t d = m.l2_prefetch - 1u;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + (size_t)d * (kElemsPerIter * 4u)));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + (size_t)d * (kElemsPerIter * 2u)));
-        }
+    // DEPTH iterations (1.5 KB per warp each) are in flight ahead of the one being reduced; the register sets take
+    // turns (the loop is unrolled DEPTH + 1 times, so no set is ever copied)
+    struct Stage { U32x8 v; U32x4 c; uint32_t r; };
+    auto load_stage = [&](uint32_t it) {
+        Stage g;
+        g.v = ldg_stream_256(vp + (size_t)it * (kElemsPerIter * 4u));
+        g.c = ldg_stream_128(cp + (size_t)it * (kElemsPerIter * 2u));
+        g.r = ldg_stream_u8(rp + (size_t)it * (kElemsPerIter / 8u));
+        return g;
+    };
+    auto reduce_iter = [&](uint32_t it, const Stage &cur) {
         IterState o;
         float carry_out;
         if (it == 0 || it == last_iter) {
@@ -266,9 +258,9 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
             const int64_t l64 = (int64_t)s - ebase, h64 = (int64_t)e - ebase;
             const uint32_t lo = l64 < 0 ? 0u : (l64 > 8 ? 8u : (uint32_t)l64);
             const uint32_t hi = h64 < 0 ? 0u : (h64 > 8 ? 8u : (uint32_t)h64);
-            csr_iter<true, XREP>(cv, cc, cr, xs_addr, zero_off, lo, hi, carry, carry_out, o);
+            csr_iter<true, XREP>(cur.v, cur.c, cur.r, xs_addr, zero_off, lo, hi, carry, carry_out, o);
         } else {
-            csr_iter<false, XREP>(cv, cc, cr, xs_addr, zero_off, 0u, 8u, carry, carry_out, o);
+            csr_iter<false, XREP>(cur.v, cur.c, cur.r, xs_addr, zero_off, 0u, 8u, carry, carry_out, o);
         }
         carry = carry_out;
 
@@ -298,6 +290,20 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
         }
         if (o.fm) first_pending = false;
         R += Rtot;
+    };
+    Stage st[DEPTH + 1];
+#pragma unroll
+    for (int d = 0; d < DEPTH; d++) if ((uint32_t)d < n_iter) st[d] = load_stage((uint32_t)d);
+    for (uint32_t it0 = 0; it0 < n_iter; it0 += DEPTH + 1) {
+#pragma unroll
+        for (int u = 0; u <= DEPTH; u++) {
+            const uint32_t it = it0 + (uint32_t)u;
+            if (it < n_iter) {
+                // the set that was consumed DEPTH + 1 - DEPTH = 1 step ago is free: refill it with iteration it + DEPTH
+                if (it + DEPTH < n_iter) st[(u + DEPTH) % (DEPTH + 1)] = load_stage(it + DEPTH);
+                reduce_iter(it, st[u]);
+            }
+        }
     }
     if (!truncated) {
         // the row in progress at the end of the chunk is complete (chunks end on row boundaries)
@@ -392,7 +398,7 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
         MaxSink sink{0.0f, false, neg_inf()};
         const uint32_t c = gw * stride;
         if (c < m.n_chunks)
-            csr_process_chunk<1>(m, smem_raw, m.chunk_start[c], m.chunk_start[c + 1], m.chunk_ord[c], sample_iters, sink);
+            csr_process_chunk<1, 1>(m, smem_raw, m.chunk_start[c], m.chunk_start[c + 1], m.chunk_ord[c], sample_iters, sink);
         uint32_t key = sink.any ? f32_to_ordered(sink.best) : 0u;
         key = __reduce_max_sync(kFull, key);
         if (lane_id() == 0) sample_keys[gw] = key;
@@ -422,7 +428,8 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
 // shared-memory buffer (sorted and cut to k only if it ever fills).
 // --------------------------------------------------------------------------
 // XREP = 1: 2 CTAs x 512 threads per SM.  XREP = 32: one CTA x 1024 threads per SM sharing 32 copies of the query.
-template <int CAP, int XREP, int THREADS>
+// DEPTH: iterations in flight ahead of the one being reduced (register sets of 13 words each).
+template <int CAP, int XREP, int THREADS, int DEPTH>
 __global__ void __launch_bounds__(THREADS, XREP > 1 ? 1 : 2)
 csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uint64_t *pool, uint32_t k,
                      int tie_higher) {
@@ -470,7 +477,7 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
         const Unit nn = load_unit(__shfl_sync(kFull, pending, 0));
         pending = claim();
         sink.tau = fmaxf(sink.tau, tau_from_key(ld_relaxed_u32(&st->tau_key)));
-        csr_process_chunk<XREP>(m, smem_raw, cur.s, cur.e, cur.ord, 0xFFFFFFFFu, sink);
+        csr_process_chunk<XREP, DEPTH>(m, smem_raw, cur.s, cur.e, cur.ord, 0xFFFFFFFFu, sink);
         cur = nxt;
         nxt = nn;
     }
