@@ -1,6 +1,5 @@
 // api.cu -- C ABI of libtopkspmv.so (see include/topkspmv.h), float CSR path and dispatch.
 #include <chrono>
-#include <cstdlib>
 #include <cstring>
 
 #include "csr_build.cuh"
@@ -25,78 +24,30 @@ int cap_variant_for_k(uint32_t k) {
     return 3;
 }
 
-size_t main_smem_bytes(uint32_t cols, int variant, int xrep, int threads) {
-    return (((cols + 1u) * 4u * (uint32_t)xrep + 15u) & ~15u) + (size_t)(threads / 32) * kCaps[variant] * 8u;
+size_t main_smem_bytes(uint32_t cols, int variant) {
+    return (((cols + 1u) * 4u + 15u) & ~15u) + (size_t)(kCapThreads[variant] / 32) * kCaps[variant] * 8u;
 }
-
-constexpr int kXrepWide = 32, kXrepThreads = 1024;
-constexpr int kDefaultDepth = 1;
 
 template <int CAP>
 cudaError_t prep_main(Handle *h, int variant) {
-    size_t smem = main_smem_bytes(h->cfg.max_cols, variant, 1, kCapThreads[variant]);
-    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP, 1, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    size_t smem = main_smem_bytes(h->cfg.max_cols, variant);
+    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, 1, 512, 1>, kCapThreads[variant], smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP>, kCapThreads[variant],
+                                                      smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     h->main_grid[variant] = per_sm * h->num_sms;
     return cudaSuccess;
 }
 
-// Experimental variants of the CAP = 256 kernel (k <= 128), selected by environment variables:
-//   TKS_CSR_XREP=32   32 query copies, one 1024-thread CTA per SM (measured: no gain, the gathers are not the limit)
-//   TKS_CSR_DEPTH=2   two iterations in flight per warp, 2 CTAs x 384 threads per SM
-constexpr int kDeepThreads = 448;
-cudaError_t prep_main_xrep(Handle *h, size_t smem_optin) {
-    h->use_xrep = false;
-    h->use_deep = false;
-    if (const char *pf = std::getenv("TKS_CSR_L2PF")) h->l2_prefetch = (uint32_t)std::atoi(pf);
-    const char *env = std::getenv("TKS_CSR_XREP");
-    if (env && std::atoi(env) == 32) {
-        const size_t smem = main_smem_bytes(h->cfg.max_cols, 0, kXrepWide, kXrepThreads);
-        if (smem <= smem_optin) {
-            cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<256, kXrepWide, kXrepThreads, 1>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            h->use_xrep = true;
-        }
-    }
-    const char *dp = std::getenv("TKS_CSR_DEPTH");
-    const int depth = dp ? std::atoi(dp) : kDefaultDepth;
-    if (depth == 2) {
-        const size_t smem = main_smem_bytes(h->cfg.max_cols, 0, 1, kDeepThreads);
-        cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<256, 1, kDeepThreads, 2>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<256, 1, kDeepThreads, 2>, kDeepThreads, smem);
-        if (e != cudaSuccess) return e;
-        h->deep_grid = (per_sm < 1 ? 1 : per_sm) * h->num_sms;
-        h->use_deep = true;
-    }
-    return cudaSuccess;
-}
-
 template <int CAP>
 void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, RunState *st, uint32_t k,
                  cudaStream_t s) {
-    if (CAP == 256 && h->use_xrep && main_smem_bytes(m.cols, 0, kXrepWide, kXrepThreads) <= main_smem_bytes(h->cfg.max_cols, 0, kXrepWide, kXrepThreads)) {
-        const size_t smem = main_smem_bytes(m.cols, 0, kXrepWide, kXrepThreads);
-        csr_topk_main_kernel<256, kXrepWide, kXrepThreads, 1><<<h->num_sms, kXrepThreads, smem, s>>>(
-            m, x, st, h->d_pool, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX);
-        return;
-    }
-    if (CAP == 256 && h->use_deep) {
-        const size_t smem = main_smem_bytes(m.cols, 0, 1, kDeepThreads);
-        csr_topk_main_kernel<256, 1, kDeepThreads, 2><<<h->deep_grid, kDeepThreads, smem, s>>>(
-            m, x, st, h->d_pool, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX);
-        return;
-    }
-    size_t smem = main_smem_bytes(m.cols, variant, 1, kCapThreads[variant]);
-    csr_topk_main_kernel<CAP, 1, 512, 1><<<h->main_grid[variant], kCapThreads[variant], smem, s>>>(
+    size_t smem = main_smem_bytes(m.cols, variant);
+    csr_topk_main_kernel<CAP><<<h->main_grid[variant], kCapThreads[variant], smem, s>>>(
         m, x, st, h->d_pool, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX);
 }
 
@@ -262,7 +213,7 @@ void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool
     const int variant = cap_variant_for_k(k);
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
     CsrDevice m{h->d_val, h->d_col16, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start, h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols,
-                (uint32_t)h->row_offset, h->l2_prefetch};
+                (uint32_t)h->row_offset};
     uint32_t n_sample = h->n_chunks < (uint32_t)h->num_sms * 32u ? h->n_chunks : (uint32_t)h->num_sms * 32u;
     if (n_sample > h->n_sample_cap) n_sample = h->n_sample_cap;
     const uint32_t stride = h->n_chunks / n_sample;
@@ -300,7 +251,7 @@ void launch_batched_kernel(Handle *h, const CsrDevice &m, const BatchedArgs &a, 
 // One matrix pass per 32 queries (csr_batched.cuh).
 void launch_batched(Handle *h, uint32_t k, cudaStream_t s, bool profile) {
     CsrDevice m{h->d_val, h->d_col16, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start, h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols,
-                (uint32_t)h->row_offset, h->l2_prefetch};
+                (uint32_t)h->row_offset};
     BatchedArgs a{};
     a.xT = h->d_xT;
     a.st = h->d_state;
@@ -473,7 +424,6 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
         if ((e = prep_main<512>(h, 1)) != cudaSuccess) return bail("prep_main<512>", e);
         if ((e = prep_main<1024>(h, 2)) != cudaSuccess) return bail("prep_main<1024>", e);
         if ((e = prep_main<2048>(h, 3)) != cudaSuccess) return bail("prep_main<2048>", e);
-        if ((e = prep_main_xrep(h, (size_t)prop.sharedMemPerBlockOptin)) != cudaSuccess) return bail("prep_main_xrep", e);
         {
             size_t ss = ((size_t)cfg->max_cols + 1u) * 4u;
             if (ss < 8192u * 4u) ss = 8192u * 4u;

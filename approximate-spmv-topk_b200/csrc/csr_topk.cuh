@@ -48,7 +48,6 @@ struct CsrDevice {
     uint32_t n_chunks;
     uint32_t cols;
     uint32_t row_offset;           // added to every reported row id
-    uint32_t l2_prefetch;          // iterations ahead that are pulled into L2 (0 = off); registers hold one more
 };
 
 // Per-query scratch that lives in HBM; zeroed at creation and by the select kernel.
@@ -108,13 +107,10 @@ struct IterState {
     unsigned fm;   // ballot: lanes with >= 1 row start
 };
 
-// XREP: interleaved copies of the query in shared memory (word col * XREP + lane % XREP).  With 32 copies every
-// lane gathers from its own bank: the random gathers stop conflicting (3.5-way with a single copy).
-// xs_addr: 32-bit shared-memory address of this lane's copy.
-template <bool MASKED, int XREP>
-__device__ __forceinline__ void csr_iter(const U32x8 &vraw, const U32x4 &craw, uint32_t rbits, uint32_t xs_addr,
-                                         uint32_t zero_off, uint32_t lo, uint32_t hi, float carry_in,
-                                         float &carry_out, IterState &o) {
+template <bool MASKED>
+__device__ __forceinline__ void csr_iter(const U32x8 &vraw, const U32x4 &craw, uint32_t rbits,
+                                         const uint8_t *__restrict__ xs_bytes, uint32_t zero_off, uint32_t lo,
+                                         uint32_t hi, float carry_in, float &carry_out, IterState &o) {
     const unsigned lane = lane_id();
     float cm = neg_inf();
     // bit j <=> element j starts a row (elements outside [lo, hi) start nothing)
@@ -128,8 +124,7 @@ __device__ __forceinline__ void csr_iter(const U32x8 &vraw, const U32x4 &craw, u
             c = in ? c : zero_off;      // column -> the zero slot behind x
             vbits = in ? vbits : 0u;
         }
-        float x;
-        asm("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(c * (uint32_t)XREP + xs_addr));
+        const float x = *reinterpret_cast<const float *>(xs_bytes + c);
         const float p = __fmul_rn(__uint_as_float(vbits), x);
         const bool f = (fb >> j) & 1u;
         if (j == 0) {
@@ -218,12 +213,11 @@ struct PoolSink {
 };
 
 // Stream one chunk (or its first max_iters iterations) through `sink`.
-// [s, e): the chunk's non-zeros, ord0: ordinal of its first row (chunk table entries, loaded by the caller).
-template <int XREP, int DEPTH, typename Sink>
-__device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint64_t s,
-                                                  uint64_t e, uint32_t ord0, uint32_t max_iters, Sink &sink) {
+template <typename Sink>
+__device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint32_t c,
+                                                  uint32_t max_iters, Sink &sink) {
     const unsigned lane = lane_id();
-    const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs_bytes) + (lane & (uint32_t)(XREP - 1)) * 4u;
+    const uint64_t s = m.chunk_start[c], e = m.chunk_start[c + 1];
     if (s >= e) return;
     const uint64_t a0 = s & ~7ull;                       // 32-byte aligned start of the first 256-bit load
     const uint64_t n_iter64 = (e - a0 + kElemsPerIter - 1) / kElemsPerIter;
@@ -235,21 +229,22 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
     const uint8_t *rp = m.rowbits + (a0 >> 3) + lane;
     const uint32_t zero_off = m.cols * 4u;
 
-    uint32_t R = ord0 - 1u;   // ordinal of the row "in progress" (a bogus one before the chunk at first)
+    uint32_t R = m.chunk_ord[c] - 1u;   // ordinal of the row "in progress" (a bogus one before the chunk at first)
     bool first_pending = true;
     float carry = 0.0f;
 
-    // DEPTH iterations (1.5 KB per warp each) are in flight ahead of the one being reduced; the register sets take
-    // turns (the loop is unrolled DEPTH + 1 times, so no set is ever copied)
-    struct Stage { U32x8 v; U32x4 c; uint32_t r; };
-    auto load_stage = [&](uint32_t it) {
-        Stage g;
-        g.v = ldg_stream_256(vp + (size_t)it * (kElemsPerIter * 4u));
-        g.c = ldg_stream_128(cp + (size_t)it * (kElemsPerIter * 2u));
-        g.r = ldg_stream_u8(rp + (size_t)it * (kElemsPerIter / 8u));
-        return g;
-    };
-    auto reduce_iter = [&](uint32_t it, const Stage &cur) {
+    U32x8 nv = ldg_stream_256(vp);
+    U32x4 nc = ldg_stream_128(cp);
+    uint32_t nr = ldg_stream_u8(rp);
+#pragma unroll 2
+    for (uint32_t it = 0; it < n_iter; it++) {
+        const U32x8 cv = nv;
+        const U32x4 cc = nc;
+        const uint32_t cr = nr;
+        vp += kElemsPerIter * 4u;
+        cp += kElemsPerIter * 2u;
+        rp += kElemsPerIter / 8u;
+        if (it + 1 < n_iter) { nv = ldg_stream_256(vp); nc = ldg_stream_128(cp); nr = ldg_stream_u8(rp); }
         IterState o;
         float carry_out;
         if (it == 0 || it == last_iter) {
@@ -258,9 +253,9 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
             const int64_t l64 = (int64_t)s - ebase, h64 = (int64_t)e - ebase;
             const uint32_t lo = l64 < 0 ? 0u : (l64 > 8 ? 8u : (uint32_t)l64);
             const uint32_t hi = h64 < 0 ? 0u : (h64 > 8 ? 8u : (uint32_t)h64);
-            csr_iter<true, XREP>(cur.v, cur.c, cur.r, xs_addr, zero_off, lo, hi, carry, carry_out, o);
+            csr_iter<true>(cv, cc, cr, xs_bytes, zero_off, lo, hi, carry, carry_out, o);
         } else {
-            csr_iter<false, XREP>(cur.v, cur.c, cur.r, xs_addr, zero_off, 0u, 8u, carry, carry_out, o);
+            csr_iter<false>(cv, cc, cr, xs_bytes, zero_off, 0u, 8u, carry, carry_out, o);
         }
         carry = carry_out;
 
@@ -290,20 +285,6 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
         }
         if (o.fm) first_pending = false;
         R += Rtot;
-    };
-    Stage st[DEPTH + 1];
-#pragma unroll
-    for (int d = 0; d < DEPTH; d++) if ((uint32_t)d < n_iter) st[d] = load_stage((uint32_t)d);
-    for (uint32_t it0 = 0; it0 < n_iter; it0 += DEPTH + 1) {
-#pragma unroll
-        for (int u = 0; u <= DEPTH; u++) {
-            const uint32_t it = it0 + (uint32_t)u;
-            if (it < n_iter) {
-                // the set that was consumed DEPTH + 1 - DEPTH = 1 step ago is free: refill it with iteration it + DEPTH
-                if (it + DEPTH < n_iter) st[(u + DEPTH) % (DEPTH + 1)] = load_stage(it + DEPTH);
-                reduce_iter(it, st[u]);
-            }
-        }
     }
     if (!truncated) {
         // the row in progress at the end of the chunk is complete (chunks end on row boundaries)
@@ -397,8 +378,7 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
     if (gw < n_sample) {
         MaxSink sink{0.0f, false, neg_inf()};
         const uint32_t c = gw * stride;
-        if (c < m.n_chunks)
-            csr_process_chunk<1, 1>(m, smem_raw, m.chunk_start[c], m.chunk_start[c + 1], m.chunk_ord[c], sample_iters, sink);
+        if (c < m.n_chunks) csr_process_chunk(m, smem_raw, c, sample_iters, sink);
         uint32_t key = sink.any ? f32_to_ordered(sink.best) : 0u;
         key = __reduce_max_sync(kFull, key);
         if (lane_id() == 0) sample_keys[gw] = key;
@@ -427,19 +407,14 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
 // counter, reduces them, and keeps rows with score >= tau in a private
 // shared-memory buffer (sorted and cut to k only if it ever fills).
 // --------------------------------------------------------------------------
-// XREP = 1: 2 CTAs x 512 threads per SM.  XREP = 32: one CTA x 1024 threads per SM sharing 32 copies of the query.
-// DEPTH: iterations in flight ahead of the one being reduced (register sets of 13 words each).
-template <int CAP, int XREP, int THREADS, int DEPTH>
-__global__ void __launch_bounds__(THREADS, XREP > 1 ? 1 : 2)
+template <int CAP>
+__global__ void __launch_bounds__(kMainThreads, 2)
 csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uint64_t *pool, uint32_t k,
                      int tie_higher) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float *xs = reinterpret_cast<float *>(smem_raw);
-    uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (((m.cols + 1u) * 4u * XREP + 15u) & ~15u));
-    for (uint32_t i = threadIdx.x; i < (m.cols + 1u) * XREP; i += blockDim.x) {
-        const uint32_t col = i / XREP;
-        xs[i] = (col < m.cols) ? x[col] : 0.0f;
-    }
+    uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (((m.cols + 1u) * 4u + 15u) & ~15u));
+    for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? x[i] : 0.0f;
     __syncthreads();
 
     const unsigned lane = lane_id();
@@ -453,33 +428,13 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
     sink.row_offset = m.row_offset;
     sink.tie_higher = tie_higher;
 
-    // The dynamic scheduler runs two chunks ahead: while chunk c streams, chunk c+1 has been claimed with its table
-    // entries in registers (its head is pulled into L2 now), and the claim of c+2 is in flight -- no warp waits on
-    // the atomic, on the chunk table or on a cold first load between chunks.
-    auto claim = [&]() { uint32_t v = 0; if (lane == 0) v = atomicAdd(&st->chunk_counter, 1u); return v; };
-    struct Unit { uint32_t c; uint64_t s, e; uint32_t ord; };
-    auto load_unit = [&](uint32_t c) {
-        Unit u{c, 0, 0, 0};
-        if (c < m.n_chunks) { u.s = m.chunk_start[c]; u.e = m.chunk_start[c + 1]; u.ord = m.chunk_ord[c]; }
-        return u;
-    };
-    Unit cur = load_unit(__shfl_sync(kFull, claim(), 0));
-    Unit nxt = load_unit(__shfl_sync(kFull, claim(), 0));
-    uint32_t pending = claim();
-    while (cur.c < m.n_chunks) {
-        if (m.l2_prefetch && nxt.c < m.n_chunks) {
-            const uint64_t a0 = nxt.s & ~7ull;
-            for (uint32_t d = 0; d < m.l2_prefetch; d++) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(m.val + a0 + (size_t)d * kElemsPerIter + lane * kEpl));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(m.col16 + a0 + (size_t)d * kElemsPerIter + lane * kEpl));
-            }
-        }
-        const Unit nn = load_unit(__shfl_sync(kFull, pending, 0));
-        pending = claim();
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(&st->chunk_counter, 1u);
+        c = __shfl_sync(kFull, c, 0);
+        if (c >= m.n_chunks) break;
         sink.tau = fmaxf(sink.tau, tau_from_key(ld_relaxed_u32(&st->tau_key)));
-        csr_process_chunk<XREP, DEPTH>(m, smem_raw, cur.s, cur.e, cur.ord, 0xFFFFFFFFu, sink);
-        cur = nxt;
-        nxt = nn;
+        csr_process_chunk(m, smem_raw, c, 0xFFFFFFFFu, sink);
     }
 
     // hand the survivors to the global pool (filtered by the freshest bound)

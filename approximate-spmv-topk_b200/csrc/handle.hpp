@@ -74,10 +74,6 @@ struct Handle {
 
     // launch geometry of the main kernel, per CAP variant
     int main_grid[4] = {0, 0, 0, 0};
-    uint32_t l2_prefetch = 0;           // main kernel: iterations ahead pulled into L2 (TKS_CSR_L2PF overrides)
-    bool use_deep = false;              // two-iterations-in-flight variant of the main kernel
-    int deep_grid = 0;
-    bool use_xrep = false;              // 32-copy query variant of the main kernel (k <= 128, narrow matrices)
 
     BscsrState *bs = nullptr;
 
