@@ -17,6 +17,7 @@ LIB_PATH = _HERE / "lib" / "libtopkspmv.so"
 TKS_OK, TKS_EINVAL, TKS_ECUDA, TKS_ESTATE, TKS_ENOMEM, TKS_EIO = 0, -1, -2, -3, -4, -5
 MODE_FLOAT_CSR, MODE_FIXED_BSCSR = 0, 1
 TIE_LOWER_INDEX, TIE_HIGHER_INDEX = 0, 1
+VALUE_FP32, VALUE_FP16 = 0, 1
 
 
 class TksConfig(C.Structure):
@@ -25,7 +26,7 @@ class TksConfig(C.Structure):
                 ("tie_break", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_int32),
                 ("chunk_nnz", C.c_int32), ("profile_kernels", C.c_int32), ("batch_mode", C.c_int32),
                 ("batch_pool_cap", C.c_int32), ("batch_fma", C.c_int32), ("fixed_drift_free", C.c_int32),
-                ("reserved", C.c_int32 * 1)]
+                ("value_type", C.c_int32)]
 
 
 class TksStats(C.Structure):

@@ -28,14 +28,16 @@ size_t main_smem_bytes(uint32_t cols, int variant) {
     return (((cols + 1u) * 4u + 15u) & ~15u) + (size_t)(kCapThreads[variant] / 32) * kCaps[variant] * 8u;
 }
 
-template <int CAP>
-cudaError_t prep_main(Handle *h, int variant) {
+inline bool half_mode(const Handle *h) { return h->cfg.value_type == TKS_VALUE_FP16; }
+
+template <int CAP, bool HALF>
+cudaError_t prep_main_t(Handle *h, int variant) {
     size_t smem = main_smem_bytes(h->cfg.max_cols, variant);
-    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP>, kCapThreads[variant],
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, HALF>, kCapThreads[variant],
                                                       smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
@@ -44,11 +46,25 @@ cudaError_t prep_main(Handle *h, int variant) {
 }
 
 template <int CAP>
+cudaError_t prep_main(Handle *h, int variant) {
+    return half_mode(h) ? prep_main_t<CAP, true>(h, variant) : prep_main_t<CAP, false>(h, variant);
+}
+
+template <int CAP>
 void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, RunState *st, uint32_t k,
                  cudaStream_t s) {
     size_t smem = main_smem_bytes(m.cols, variant);
-    csr_topk_main_kernel<CAP><<<h->main_grid[variant], kCapThreads[variant], smem, s>>>(
-        m, x, st, h->d_pool, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX);
+    const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
+    if (half_mode(h))
+        csr_topk_main_kernel<CAP, true><<<h->main_grid[variant], kCapThreads[variant], smem, s>>>(m, x, st, h->d_pool, k, tie_higher);
+    else
+        csr_topk_main_kernel<CAP, false><<<h->main_grid[variant], kCapThreads[variant], smem, s>>>(m, x, st, h->d_pool, k, tie_higher);
+}
+
+CsrDevice csr_device(const Handle *h) {
+    return CsrDevice{h->d_val, h->d_col16, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start,
+                     h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols, (uint32_t)h->row_offset,
+                     half_mode(h) ? 1u : 0u};
 }
 
 __global__ void widen_u32_to_u64_kernel(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
@@ -141,7 +157,17 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
     if (nch > 0xFFFFFFF0ull) return h->fail(TKS_EINVAL, "too many chunks (%llu)", (unsigned long long)nch);
     h->n_chunks = (uint32_t)nch;
 
-    if (d_val_adopt) {
+    if (half_mode(h)) {
+        // the reference's half-precision mode (host_spmv_topk_csr_gpu.cu:133,152: float_to_half of every value)
+        const float *src = d_val_adopt ? d_val_adopt : d_val_src;
+        TKS_CUDA(h, cudaMalloc(&h->d_val, nnz * sizeof(__half) + pad));
+        TKS_CUDA(h, cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_val) + nnz * sizeof(__half), 0, pad, s));
+        if (nnz > 0) csr_vals_to_half_kernel<<<h->num_sms * 8, 256, 0, s>>>(src, nnz, reinterpret_cast<__half *>(h->d_val));
+        if (d_val_adopt) {
+            TKS_CUDA(h, cudaStreamSynchronize(s));
+            cudaFree(d_val_adopt);
+        }
+    } else if (d_val_adopt) {
         h->d_val = d_val_adopt;
     } else {
         TKS_CUDA(h, cudaMalloc(&h->d_val, nnz * sizeof(float) + pad));
@@ -191,7 +217,7 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
                        (herr & kErrPtrOrder) ? " row_ptr not monotone / out of range;" : "");
     }
     h->rows = rows; h->cols = cols; h->nnz = nnz;
-    h->device_bytes = nnz * 6ull + (nnz + 7) / 8 + (nch + 1) * 8ull + nch * 4ull + (has_empty ? n_nonempty * 4ull : 0ull);
+    h->device_bytes = nnz * (half_mode(h) ? 4ull : 6ull) + (nnz + 7) / 8 + (nch + 1) * 8ull + nch * 4ull + (has_empty ? n_nonempty * 4ull : 0ull);
     h->have_matrix = true;
     h->have_result = false;
     h->stats.rows = rows; h->stats.cols = cols; h->stats.nnz = nnz; h->stats.packets = 0;
@@ -212,8 +238,7 @@ int check_float_upload(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, ui
 void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool profile) {
     const int variant = cap_variant_for_k(k);
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
-    CsrDevice m{h->d_val, h->d_col16, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start, h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols,
-                (uint32_t)h->row_offset};
+    const CsrDevice m = csr_device(h);
     uint32_t n_sample = h->n_chunks < (uint32_t)h->num_sms * 32u ? h->n_chunks : (uint32_t)h->num_sms * 32u;
     if (n_sample > h->n_sample_cap) n_sample = h->n_sample_cap;
     const uint32_t stride = h->n_chunks / n_sample;
@@ -226,8 +251,10 @@ void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool
     uint64_t si = (h->nnz / 100u + (uint64_t)n_sample * kElemsPerIter - 1) / ((uint64_t)n_sample * kElemsPerIter);
     const uint32_t max_si = h->chunk_nnz / kElemsPerIter;
     const uint32_t sample_iters = (uint32_t)(si < 2 ? 2 : (si > max_si ? (max_si < 2 ? 2 : max_si) : si));
-    csr_sample_kernel<<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride,
-                                                                 sample_iters, k);
+    if (half_mode(h))
+        csr_sample_kernel<true><<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, sample_iters, k);
+    else
+        csr_sample_kernel<false><<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, sample_iters, k);
     if (profile) cudaEventRecord(h->evm0, s);
     switch (variant) {
         case 0: launch_main<256>(h, 0, m, x, st, k, s); break;
@@ -250,8 +277,7 @@ void launch_batched_kernel(Handle *h, const CsrDevice &m, const BatchedArgs &a, 
 
 // One matrix pass per 32 queries (csr_batched.cuh).
 void launch_batched(Handle *h, uint32_t k, cudaStream_t s, bool profile) {
-    CsrDevice m{h->d_val, h->d_col16, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start, h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols,
-                (uint32_t)h->row_offset};
+    const CsrDevice m = csr_device(h);
     BatchedArgs a{};
     a.xT = h->d_xT;
     a.st = h->d_state;
@@ -268,7 +294,7 @@ void launch_batched(Handle *h, uint32_t k, cudaStream_t s, bool profile) {
         a.sample_batches = (uint32_t)(sb < 8 ? 8 : (sb > 64 ? 64 : sb));
     }
     a.tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
-    batched_transpose_kernel<<<h->num_sms, 256, 0, s>>>(h->d_x, h->batch, h->cols, a.npass, h->d_xT);
+    batched_transpose_kernel<<<h->num_sms, 256, 0, s>>>(h->d_x, h->batch, h->cols, a.npass, h->d_xT, half_mode(h) ? 1 : 0);
     const uint32_t warps_per_cta = kBThreads / kWarp;
     uint32_t sgrid = ((a.n_sample + 3u) / 4u + warps_per_cta - 1) / warps_per_cta;
     if (sgrid > (uint32_t)h->num_sms) sgrid = (uint32_t)h->num_sms;
@@ -291,7 +317,8 @@ int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false) {
     if (!h->have_matrix) return h->fail(TKS_ESTATE, "no matrix uploaded");
     if (!h->have_query) return h->fail(TKS_ESTATE, "no query set");
     if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k=%u outside 1..%u", k, h->kmax);
-    const uint64_t matrix_bytes = h->nnz * 8ull + (h->rows + 1) * (h->nnz > 0xFFFFFFFFull ? 8ull : 4ull);
+    // 4 + 4 bytes per non-zero in fp32, 2 + 4 in the half-precision mode
+    const uint64_t matrix_bytes = h->nnz * (half_mode(h) ? 6ull : 8ull) + (h->rows + 1) * (h->nnz > 0xFFFFFFFFull ? 8ull : 4ull);
     if (use_batched(h)) {
         launch_batched(h, k, s, profile);
         h->last_run_batched = true;
@@ -387,6 +414,10 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
         if (cfg->local_k < 1 || cfg->local_k > 64) { g_create_error = "local_k outside 1..64"; return TKS_EINVAL; }
         if (cfg->partitions < 1 || cfg->partitions > 4096) { g_create_error = "partitions outside 1..4096"; return TKS_EINVAL; }
     }
+    if (cfg->value_type != TKS_VALUE_FP32 && cfg->value_type != TKS_VALUE_FP16) { g_create_error = "unknown value_type"; return TKS_EINVAL; }
+    if (cfg->value_type == TKS_VALUE_FP16 && cfg->mode != TKS_MODE_FLOAT_CSR) {
+        g_create_error = "value_type FP16 belongs to FLOAT_CSR mode"; return TKS_EINVAL;
+    }
     if (cfg->max_batch < 1 || cfg->max_batch > 1024) { g_create_error = "max_batch outside 1..1024"; return TKS_EINVAL; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -427,7 +458,8 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
         {
             size_t ss = ((size_t)cfg->max_cols + 1u) * 4u;
             if (ss < 8192u * 4u) ss = 8192u * 4u;
-            if ((e = cudaFuncSetAttribute(csr_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess)
+            if ((e = cudaFuncSetAttribute(csr_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess ||
+                (e = cudaFuncSetAttribute(csr_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess)
                 return bail("sample smem attr", e);
             if ((e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(kSelectDynSmem))) != cudaSuccess)
@@ -554,7 +586,13 @@ int tks_download_csr(tks_handle *h, uint64_t *ptr64, uint32_t *idx, float *val) 
     if (!h->have_matrix || !h->d_ptr64) return h->fail(TKS_ESTATE, "no CSR matrix resident");
     TKS_CUDA(h, cudaSetDevice(h->device));
     if (ptr64) TKS_CUDA(h, cudaMemcpy(ptr64, h->d_ptr64, (h->rows + 1) * 8, cudaMemcpyDeviceToHost));
-    if (val) TKS_CUDA(h, cudaMemcpy(val, h->d_val, h->nnz * 4, cudaMemcpyDeviceToHost));
+    if (val && !half_mode(h)) TKS_CUDA(h, cudaMemcpy(val, h->d_val, h->nnz * 4, cudaMemcpyDeviceToHost));
+    if (val && half_mode(h)) {
+        // the resident values are halves: fetch them into the upper half of the output and widen in place
+        uint16_t *tmp = reinterpret_cast<uint16_t *>(val) + h->nnz;
+        TKS_CUDA(h, cudaMemcpy(tmp, h->d_val, h->nnz * 2, cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < h->nnz; i++) val[i] = half_bits_to_float(tmp[i]);
+    }
     if (idx) {
         // col16 holds column * 4: fetch the 16-bit words into the upper half of the output, widen in place
         uint16_t *tmp = reinterpret_cast<uint16_t *>(idx) + h->nnz;

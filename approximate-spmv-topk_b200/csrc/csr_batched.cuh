@@ -54,13 +54,15 @@ __host__ __device__ inline size_t batched_smem_bytes(uint32_t cols) {
 
 // queries [batch][cols] row-major -> pass tables [npass][cols+1][32], zero padded
 __global__ void batched_transpose_kernel(const float *__restrict__ x, uint32_t batch, uint32_t cols, uint32_t npass,
-                                         float *__restrict__ xT) {
+                                         float *__restrict__ xT, int half) {
     const uint32_t n = npass * (cols + 1u) * kBqPerPass;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t q = i % kBqPerPass, r = i / kBqPerPass;
         const uint32_t col = r % (cols + 1u), pass = r / (cols + 1u);
         const uint32_t gq = pass * kBqPerPass + q;
-        xT[i] = (col < cols && gq < batch) ? x[(size_t)gq * cols + col] : 0.0f;
+        float v = (col < cols && gq < batch) ? x[(size_t)gq * cols + col] : 0.0f;
+        if (half) v = __half2float(__float2half_rn(v));   // half-precision mode: the query is rounded like the values
+        xT[i] = v;
     }
 }
 
@@ -154,10 +156,27 @@ __device__ __forceinline__ void batched_stream(const CsrDevice &m, const Batched
     const uint32_t nb_w = __reduce_max_sync(kFull, nb);
     L.acc[0] = L.acc[1] = L.acc[2] = L.acc[3] = 0.0f;
     L.have_row = false;
-    const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val + a0) + l8 * 32u;
+    const bool half = m.val_half != 0;   // warp-uniform: values are halves, widened when staged
+    const uint32_t vshift = half ? 1u : 2u;
+    const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val) + (a0 << vshift) + ((l8 * 8u) << vshift);
     const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.col16 + a0) + l8 * 16u;
     const uint8_t *rp = m.rowbits + (a0 >> 3) + l8;
-    const uint32_t zero_off = m.cols * (kBqPerPass * 4u);   // the all-zero table row
+    const uint32_t zero_off = m.cols * (kBqPerPass * 4u);
+    auto load_vals = [&](const uint8_t *p) {
+        U32x8 r;
+        if (half) {
+            const U32x4 h4 = ldg_stream_128(p);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&h4.w[j]));
+                r.w[2 * j] = __float_as_uint(f2.x);
+                r.w[2 * j + 1] = __float_as_uint(f2.y);
+            }
+        } else {
+            r = ldg_stream_256(p);
+        }
+        return r;
+    };   // the all-zero table row
     float *sval = reinterpret_cast<float *>(stage);
     uint32_t *scol = reinterpret_cast<uint32_t *>(stage + kBStage * 4u);
 
@@ -168,7 +187,7 @@ __device__ __forceinline__ void batched_stream(const CsrDevice &m, const Batched
     for (int j = 0; j < 8; j++) nv.w[j] = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) nc.w[j] = 0;
-    if (nb > 0) { nv = ldg_stream_256(vp); nc = ldg_stream_128(cp); nr = ldg_stream_u8(rp); }
+    if (nb > 0) { nv = load_vals(vp); nc = ldg_stream_128(cp); nr = ldg_stream_u8(rp); }
     for (uint32_t b = 0; b < nb_w; b++) {
         // column offsets (col * 4) become byte offsets of the table row (col * 128), the row-start bit goes to bit 31
         uint32_t cw[8], vw[8];
@@ -194,7 +213,7 @@ __device__ __forceinline__ void batched_stream(const CsrDevice &m, const Batched
         reinterpret_cast<uint4 *>(scol)[l8 * 2 + 1] = make_uint4(cw[4], cw[5], cw[6], cw[7]);
         __syncwarp();
         if (b + 1 < nb) {   // next batch in flight while this one is consumed
-            nv = ldg_stream_256(vp + (size_t)(b + 1) * (kBStage * 4u));
+            nv = load_vals(vp + ((size_t)(b + 1) * kBStage << vshift));
             nc = ldg_stream_128(cp + (size_t)(b + 1) * (kBStage * 2u));
             nr = ldg_stream_u8(rp + (size_t)(b + 1) * (kBStage / 8u));
         }

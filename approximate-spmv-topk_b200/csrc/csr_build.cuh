@@ -14,6 +14,19 @@ namespace tks {
 constexpr uint32_t kErrColRange = 1u;     // column index >= cols
 constexpr uint32_t kErrPtrOrder = 4u;     // row_ptr not non-decreasing / out of range
 
+// The reference's float_to_half (host_spmv_topk_csr_gpu.cu:152): round to nearest even.
+__global__ void csr_vals_to_half_kernel(const float *__restrict__ val, uint64_t nnz, __half *__restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < nnz; i += stride) out[i] = __float2half_rn(val[i]);
+}
+
+inline float half_bits_to_float(uint16_t bits) {
+    __half_raw r;
+    r.x = bits;
+    return __half2float(__half(r));
+}
+
 template <typename P>
 __global__ void csr_copy_cols_kernel(const uint32_t *__restrict__ idx, uint64_t nnz, uint32_t cols,
                                      uint16_t *__restrict__ col16, uint32_t *err) {

@@ -8,7 +8,10 @@
 // argument that the result equals the exact top-k under the stated total order.
 //
 // Device layout (built once by tks_upload_csr, see csr_build.cuh): 6.125 bytes per non-zero
-//   val     [nnz]    fp32, as uploaded
+//   val     [nnz]    fp32, as uploaded -- or IEEE half (round to nearest even) in the reference's half-precision
+//                     mode (host_spmv_topk_csr_gpu.cu:132-136,151-153): 4.125 bytes per non-zero.  The query is
+//                     rounded to half as well; a half x half product is exact in fp32 (11 + 11 significand bits)
+//                     and the row sums are accumulated in fp32.
 //   col16   [nnz]    u16 : column * 4 = the byte offset of x[col] in shared memory
 //                     (columns <= 16383, so 16 bits always suffice: a third less
 //                     index traffic than CSR's 32-bit column indices)
@@ -39,7 +42,7 @@ constexpr uint32_t kSampleThreads = 256;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
 struct CsrDevice {
-    const float *val;
+    const void *val;               // fp32 [nnz], or IEEE half [nnz] when the kernels are instantiated with HALF
     const uint16_t *col16;         // column * 4
     const uint8_t *rowbits;        // one row-start bit per non-zero
     const uint64_t *chunk_start;   // n_chunks + 1 entries
@@ -48,6 +51,7 @@ struct CsrDevice {
     uint32_t n_chunks;
     uint32_t cols;
     uint32_t row_offset;           // added to every reported row id
+    uint32_t val_half;             // 1: val holds halves (the batched kernel branches on it at run time)
 };
 
 // Per-query scratch that lives in HBM; zeroed at creation and by the select kernel.
@@ -107,8 +111,17 @@ struct IterState {
     unsigned fm;   // ballot: lanes with >= 1 row start
 };
 
-template <bool MASKED>
-__device__ __forceinline__ void csr_iter(const U32x8 &vraw, const U32x4 &craw, uint32_t rbits,
+template <bool HALF> struct ValRaw { using type = U32x8; };
+template <> struct ValRaw<true> { using type = U32x4; };
+
+template <bool HALF>
+__device__ __forceinline__ typename ValRaw<HALF>::type ldg_stream_vals(const void *p) {
+    if constexpr (HALF) return ldg_stream_128(p);
+    else return ldg_stream_256(p);
+}
+
+template <bool MASKED, bool HALF>
+__device__ __forceinline__ void csr_iter(const typename ValRaw<HALF>::type &vraw, const U32x4 &craw, uint32_t rbits,
                                          const uint8_t *__restrict__ xs_bytes, uint32_t zero_off, uint32_t lo,
                                          uint32_t hi, float carry_in, float &carry_out, IterState &o) {
     const unsigned lane = lane_id();
@@ -118,14 +131,20 @@ __device__ __forceinline__ void csr_iter(const U32x8 &vraw, const U32x4 &craw, u
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         uint32_t c = (j & 1) ? (craw.w[j >> 1] >> 16) : (craw.w[j >> 1] & 0xFFFFu);   // column * 4
-        uint32_t vbits = vraw.w[j];
+        float v;
+        if constexpr (HALF) {
+            const float2 v2 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.w[j >> 1]));
+            v = (j & 1) ? v2.y : v2.x;
+        } else {
+            v = __uint_as_float(vraw.w[j]);
+        }
         if (MASKED) {
             const bool in = ((uint32_t)j >= lo) && ((uint32_t)j < hi);
             c = in ? c : zero_off;      // column -> the zero slot behind x
-            vbits = in ? vbits : 0u;
+            v = in ? v : 0.0f;
         }
         const float x = *reinterpret_cast<const float *>(xs_bytes + c);
-        const float p = __fmul_rn(__uint_as_float(vbits), x);
+        const float p = __fmul_rn(v, x);
         const bool f = (fb >> j) & 1u;
         if (j == 0) {
             o.seg[0] = p;
@@ -213,7 +232,7 @@ struct PoolSink {
 };
 
 // Stream one chunk (or its first max_iters iterations) through `sink`.
-template <typename Sink>
+template <bool HALF, typename Sink>
 __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint32_t c,
                                                   uint32_t max_iters, Sink &sink) {
     const unsigned lane = lane_id();
@@ -224,7 +243,8 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
     const bool truncated = n_iter64 > max_iters;
     const uint32_t n_iter = truncated ? max_iters : (uint32_t)n_iter64;
     const uint32_t last_iter = (uint32_t)n_iter64 - 1;   // chunks are far smaller than 2^32 * 256 non-zeros
-    const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val + a0) + lane * 32u;
+    constexpr uint32_t kValBytes = HALF ? 2u : 4u;
+    const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val) + a0 * kValBytes + lane * (kEpl * kValBytes);
     const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.col16 + a0) + lane * 16u;
     const uint8_t *rp = m.rowbits + (a0 >> 3) + lane;
     const uint32_t zero_off = m.cols * 4u;
@@ -233,18 +253,18 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
     bool first_pending = true;
     float carry = 0.0f;
 
-    U32x8 nv = ldg_stream_256(vp);
+    typename ValRaw<HALF>::type nv = ldg_stream_vals<HALF>(vp);
     U32x4 nc = ldg_stream_128(cp);
     uint32_t nr = ldg_stream_u8(rp);
 #pragma unroll 2
     for (uint32_t it = 0; it < n_iter; it++) {
-        const U32x8 cv = nv;
+        const typename ValRaw<HALF>::type cv = nv;
         const U32x4 cc = nc;
         const uint32_t cr = nr;
-        vp += kElemsPerIter * 4u;
+        vp += kElemsPerIter * kValBytes;
         cp += kElemsPerIter * 2u;
         rp += kElemsPerIter / 8u;
-        if (it + 1 < n_iter) { nv = ldg_stream_256(vp); nc = ldg_stream_128(cp); nr = ldg_stream_u8(rp); }
+        if (it + 1 < n_iter) { nv = ldg_stream_vals<HALF>(vp); nc = ldg_stream_128(cp); nr = ldg_stream_u8(rp); }
         IterState o;
         float carry_out;
         if (it == 0 || it == last_iter) {
@@ -253,9 +273,9 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
             const int64_t l64 = (int64_t)s - ebase, h64 = (int64_t)e - ebase;
             const uint32_t lo = l64 < 0 ? 0u : (l64 > 8 ? 8u : (uint32_t)l64);
             const uint32_t hi = h64 < 0 ? 0u : (h64 > 8 ? 8u : (uint32_t)h64);
-            csr_iter<true>(cv, cc, cr, xs_bytes, zero_off, lo, hi, carry, carry_out, o);
+            csr_iter<true, HALF>(cv, cc, cr, xs_bytes, zero_off, lo, hi, carry, carry_out, o);
         } else {
-            csr_iter<false>(cv, cc, cr, xs_bytes, zero_off, 0u, 8u, carry, carry_out, o);
+            csr_iter<false, HALF>(cv, cc, cr, xs_bytes, zero_off, 0u, 8u, carry, carry_out, o);
         }
         carry = carry_out;
 
@@ -366,19 +386,27 @@ __device__ __forceinline__ KeyT block_radix_select(LoadF load, uint32_t n, uint3
 // distinct real rows, hence a valid lower bound on the k-th best score.
 // Dynamic shared memory: max((cols+1)*4, n_sample*4) bytes.
 // --------------------------------------------------------------------------
+// The query as the kernels see it: rounded to half and widened again in the half-precision mode.
+template <bool HALF>
+__device__ __forceinline__ float query_value(float x) {
+    if constexpr (HALF) return __half2float(__float2half_rn(x));
+    else return x;
+}
+
+template <bool HALF>
 __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m, const float *__restrict__ x,
                                                                      RunState *st, uint32_t *sample_keys,
                                                                      uint32_t n_sample, uint32_t stride,
                                                                      uint32_t sample_iters, uint32_t k) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float *xs = reinterpret_cast<float *>(smem_raw);
-    for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? x[i] : 0.0f;
+    for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<HALF>(x[i]) : 0.0f;
     __syncthreads();
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
     if (gw < n_sample) {
         MaxSink sink{0.0f, false, neg_inf()};
         const uint32_t c = gw * stride;
-        if (c < m.n_chunks) csr_process_chunk(m, smem_raw, c, sample_iters, sink);
+        if (c < m.n_chunks) csr_process_chunk<HALF>(m, smem_raw, c, sample_iters, sink);
         uint32_t key = sink.any ? f32_to_ordered(sink.best) : 0u;
         key = __reduce_max_sync(kFull, key);
         if (lane_id() == 0) sample_keys[gw] = key;
@@ -407,14 +435,14 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
 // counter, reduces them, and keeps rows with score >= tau in a private
 // shared-memory buffer (sorted and cut to k only if it ever fills).
 // --------------------------------------------------------------------------
-template <int CAP>
+template <int CAP, bool HALF>
 __global__ void __launch_bounds__(kMainThreads, 2)
 csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uint64_t *pool, uint32_t k,
                      int tie_higher) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float *xs = reinterpret_cast<float *>(smem_raw);
     uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (((m.cols + 1u) * 4u + 15u) & ~15u));
-    for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? x[i] : 0.0f;
+    for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<HALF>(x[i]) : 0.0f;
     __syncthreads();
 
     const unsigned lane = lane_id();
@@ -434,7 +462,7 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
         c = __shfl_sync(kFull, c, 0);
         if (c >= m.n_chunks) break;
         sink.tau = fmaxf(sink.tau, tau_from_key(ld_relaxed_u32(&st->tau_key)));
-        csr_process_chunk(m, smem_raw, c, 0xFFFFFFFFu, sink);
+        csr_process_chunk<HALF>(m, smem_raw, c, 0xFFFFFFFFu, sink);
     }
 
     // hand the survivors to the global pool (filtered by the freshest bound)

@@ -28,7 +28,7 @@ struct Handle {
     bool have_matrix = false;
     uint64_t rows = 0, nnz = 0, row_offset = 0;
     uint32_t cols = 0;
-    float *d_val = nullptr;
+    void *d_val = nullptr;              // fp32 values, or IEEE halves when cfg.value_type == TKS_VALUE_FP16
     uint16_t *d_col16 = nullptr;        // column * 4
     uint32_t *d_rowbits = nullptr;      // row-start bitmap, one bit per non-zero (zeroed words, atomicOr at build)
     uint64_t *d_ptr64 = nullptr;        // kept for tks_download_csr (exact copy of row_ptr as u64)

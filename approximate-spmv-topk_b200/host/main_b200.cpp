@@ -192,10 +192,10 @@ int main(int argc, char *argv[]) {
         create_sample_vector(vec.data(), (int)cols, true, false, true, options.seed);
         auto t4 = clock_type::now();
         SpMV spmv(ptr.data(), idx.data(), csr_val.data(), rows, cols, nnz, vec.data(), options.top_k_value, options.device,
-                  options.tie_higher, debug);
+                  options.tie_higher, debug, options.use_half_precision_gpu);   // -a, as host_spmv_topk_csr_gpu.cu:382
         float setup_ms = (float)chrono::duration_cast<chrono::microseconds>(clock_type::now() - t4).count() / 1000;
         if (debug) std::cout << "b200 setup time=" << setup_ms << " ms" << std::endl;
-        const double bytes = 8.0 * nnz + 4.0 * (rows + 1.0) + 4.0 * cols + 8.0 * options.top_k_value;
+        const double bytes = (options.use_half_precision_gpu ? 6.0 : 8.0) * nnz + 4.0 * (rows + 1.0) + 4.0 * cols + 8.0 * options.top_k_value;
         // GPU-host column names (host_spmv_topk_csr_gpu.cu:452)
         return run<float>(options, coo, rows, cols, nnz, spmv, vec, setup_ms, "hw_spmv_only_time_ms,hw_exec_time_ms", bytes);
     }

@@ -1,7 +1,7 @@
 // options.hpp -- command line of the host executable.  Same struct name, field names, defaults and
 // flags as the reference (src/common/utils/options.hpp:37-132: -d -s -r -m -t -x -v -k -b -c -g -i -a), so
 // test_spmv_topk.py's command templates keep working; flags that only made sense for the FPGA/cuSPARSE
-// back-ends (-x -b -c -g -i -a) are accepted and ignored.  New flags select what the reference fixed at
+// back-ends (-x -b -c -g -i) are accepted and ignored; -a selects half-precision values as in the reference.  New flags select what the reference fixed at
 // compile time (types.hpp) or hard-coded in main():
 //   -z  the MTX file is 0-indexed          (reference hosts assume this, host_spmv_bscsr.cpp:539)
 //   -f  FPGA-semantics fixed-point BS-CSR engine instead of exact fp32 CSR (USE_FLOAT, types.hpp:29)

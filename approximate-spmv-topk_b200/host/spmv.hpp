@@ -34,7 +34,8 @@ struct SpMV {
     float last_full_ms = 0.f;
 
     SpMV(int_type *ptr, int_type *idx, float *val, int_type num_rows_, int_type num_cols_, int_type num_nnz_,
-         float *vec, int k_, int device = 0, bool tie_higher = false, int debug = 0)
+         float *vec, int k_, int device = 0, bool tie_higher = false, int debug = 0,
+         bool use_half_precision_gpu = false)   // the reference ctor's last argument (host_spmv_topk_csr_gpu.cu:95)
         : num_rows(num_rows_), num_cols(num_cols_), num_nnz(num_nnz_), k(k_) {
         tks_config cfg;
         tks_default_config(&cfg);
@@ -42,6 +43,7 @@ struct SpMV {
         cfg.device = device;
         cfg.max_cols = num_cols_ > MAX_COLS ? (int)num_cols_ : MAX_COLS;
         cfg.tie_break = tie_higher ? TKS_TIE_HIGHER_INDEX : TKS_TIE_LOWER_INDEX;
+        cfg.value_type = use_half_precision_gpu ? TKS_VALUE_FP16 : TKS_VALUE_FP32;
         TKS_OR_DIE(nullptr, tks_create(&cfg, &h));
         if (debug) printf("Write inputs into device memory\n");
         TKS_OR_DIE(h, tks_upload_csr(h, num_rows, num_cols, num_nnz, ptr, 32, idx, val, 0));

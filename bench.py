@@ -40,6 +40,8 @@ sys.path.insert(0, str(ROOT))
 WORKLOADS = {
     "cfg2": dict(rows=10_000_000, cols=1024, deg=20, dist="gamma", mode="float",
                  name="cfg2: synthetic 10M x 1024, gamma ~20 nnz/row, fp32 CSR, single query, k=100"),
+    "cfg2h": dict(rows=10_000_000, cols=1024, deg=20, dist="gamma", mode="float", half=True,
+                  name="cfg2h: cfg2 with half-precision matrix values and query (the reference's -a GPU mode), fp32 accumulation, k=100"),
     "cfg3": dict(rows=10_000_000, cols=1024, deg=20, dist="gamma", mode="fixed",
                  name="cfg3: cfg2 matrix in 20-bit BS-CSR packets, 32 partitions x local K=8 (FPGA semantics)"),
     "cfg4": dict(rows=200_000_000, cols=1024, deg=40, dist="uniform", mode="float",
@@ -211,7 +213,7 @@ def ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl_key = args.workload or "cfg2"
     wl = WORKLOADS[wl_key]
-    weak = wl_key == "cfg2"                          # cfg2: 10M rows PER RANK; cfg4 / cfg5: the stated total, sharded
+    weak = wl_key in ("cfg2", "cfg2h")                          # cfg2: 10M rows PER RANK; cfg4 / cfg5: the stated total, sharded
     rows_total = (args.rows or wl["rows"]) * (world if weak else 1)
     cols = wl["cols"]
     shards = tks.sharding.plan_row_shards_even(rows_total, world)
@@ -232,7 +234,8 @@ def ours(args):
 
     # profile_kernels: tks_run (the e2e path) also brackets the dominant kernel with two events; the
     # resident path (tks_run_async) never does
-    eng = tks.SpMV(num_cols=cols, k=K, device=local, profile_kernels=True)
+    half = bool(wl.get("half", False))
+    eng = tks.SpMV(num_cols=cols, k=K, device=local, profile_kernels=True, half=half)
     t0 = time.perf_counter()
     eng.generate_synthetic(r1 - r0, cols, wl["deg"], wl["dist"], seed=SEED, row_offset=r0)
     gen_s = time.perf_counter() - t0
@@ -319,17 +322,18 @@ def ours(args):
             "streamed_frac": int(stats.device_bytes) / (main_ms * 1e-3) / 1e9 / peak_gbs}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not half:
         cpu = cpu_baseline_leg(tks, eng, hq[args.warmup:], idx_last, val_last, args)
 
     if rank == 0:
         line = {"metric": "topk_spmv_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak" if weak else "strong", "vs_baseline": None,
+                "dtype": "f16 values x f16 query, f32 products and sums" if half else "f32", "data": "synthetic",
                 "config": {"workload": wl["name"] + (f", weak-scaled: {world} shards of {wl['rows']} rows" if weak and world > 1 else ""),
                            "rows": rows_total, "cols": cols, "nnz": nnz_total, "k": K,
                            "sharding": f"rows/{world}, K-candidate all-gather + merge on every rank" if world > 1 else "none",
-                           "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * 8 / 1e9),
+                           "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * (6 if half else 8) / 1e9),
                            "generator_s": round(gen_s, 2)},
                 "roofline": roof,
                 "cpu_baseline": cpu,
@@ -502,7 +506,7 @@ def ours_batched(args, tks, wl, rows_total, peak_gbs, peak_src, world, rank, loc
                            "value_counts": "queries x non-zeros per second",
                            "arithmetic": "fma" if args.batch_fma else "separate mul/add (bit-identical to the gold)",
                            "sharding": f"rows/{world}" if world > 1 else "none",
-                           "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * 8 / 1e9),
+                           "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * (6 if half else 8) / 1e9),
                            "generator_s": round(gen_s, 2)},
                 "roofline": roof, "cpu_baseline": cpu,
                 "e2e": {"value": B * nnz_total / (e2e_ms_step * 1e-3), "unit": "nnz/s", "ms_per_step": e2e_ms_step,

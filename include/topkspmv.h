@@ -42,6 +42,10 @@ extern "C" {
 #define TKS_MODE_FIXED_BSCSR 1 /* FPGA semantics: W-bit fixed point, BS-CSR packets, P partitions x  */
                                /* LFR lanes x local K (src/fpga/src/ip/spmv/spmv_bscsr_top_k_*.{hpp,cpp}) */
 
+/* storage type of the matrix values in float mode */
+#define TKS_VALUE_FP32 0
+#define TKS_VALUE_FP16 1
+
 /* tie-break of equal scores in the final list */
 #define TKS_TIE_LOWER_INDEX 0  /* north-star contract                                          */
 #define TKS_TIE_HIGHER_INDEX 1 /* reference sort_tuples, src/common/utils/evaluation_utils.hpp:52-56 */
@@ -68,7 +72,9 @@ typedef struct tks_config {
                                    /* row-counter drift: packets with more than LFR row segments   */
                                    /* advance the row counter by the true row count and carry the true last      */
                                    /* partial sum; 0 = the reference's semantics, bit for bit (default)          */
-    int32_t reserved[1];
+    int32_t value_type;            /* float mode: TKS_VALUE_FP32 (default) or TKS_VALUE_FP16 = the reference's          */
+                                   /* half-precision GPU mode (-a, options.hpp:82; host_spmv_topk_csr_gpu.cu:132-136,   */
+                                   /* 151-153): matrix values and query rounded to IEEE half, fp32 accumulation         */
 } tks_config;
 
 typedef struct tks_handle tks_handle;

@@ -89,6 +89,19 @@ def gold_topk_f32(row, col, val, vec, k, sort=True):
     return idx, out
 
 
+def half_round(a):
+    """float_to_half then half_to_float (host_spmv_topk_csr_gpu.cu:151-153, 254; IEEE round to nearest even):
+    what the reference's half-precision GPU mode does to every matrix value and to the query."""
+    return np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
+
+
+def gold_topk_f16(row, col, val, vec, k, sort=True):
+    """The gold on half-rounded inputs with fp32 accumulation: the statement of the engine's TKS_VALUE_FP16 mode.
+    (The reference accumulates in half through cuSPARSE CUDA_R_16F / light_spmv<half>, which loses ~3 digits; the
+    engine keeps the reference's storage format and rounding of the INPUTS and is at least as accurate after.)"""
+    return gold_topk_f32(row, col, half_round(val), half_round(vec), k, sort)
+
+
 def spmv_f32(row, col, val, vec, num_rows):
     """Sequential fp32 product vector, same order as the gold (gold_algorithms.hpp:203-213)."""
     row, col, val, vec = _c(row, np.uint32), _c(col, np.uint32), _c(val, np.float32), _c(vec, np.float32)

@@ -252,3 +252,75 @@ def test_row_shards_merge_on_device_equals_unsharded(cuda_required, tks, orc, cf
     np.testing.assert_allclose(val, val0, rtol=1e-6)
     for e in engines:
         e.close()
+
+
+# ---- half-precision value mode (the reference's -a flag, host_spmv_topk_csr_gpu.cu:132-136,151-153) ----------
+
+def test_half_mode_matches_gold_on_half_rounded_inputs(cuda_required, tks, orc, cfg1):
+    """TKS_VALUE_FP16: values and query rounded to IEEE half (RNE), exact fp32 products, fp32 row sums."""
+    x, y, v, ptr = cfg1
+    vh = orc.half_round(v)
+    with tks.SpMV(ptr, y, v, 10000, 1024, k=100, half=True) as s:
+        assert s.stats().device_bytes < 4.2 * v.size + 8 * 1024            # 2 + 2 + 1/8 bytes per non-zero
+        _, _, dval = s.download_csr()
+        assert np.array_equal(dval.view(np.uint32), vh.view(np.uint32))     # resident values = RNE halves
+        for qs in range(1, 4):
+            vec = make_query(1024, qs)
+            s.reset(vec)
+            s()
+            val, idx, cnt = s.read_result()
+            yref = orc.spmv_f32(x, y, vh, orc.half_round(vec), 10000)
+            check_against_scores(idx, val, cnt, yref, 100)
+            gi, gv = orc.gold_topk_f16(x, y, v, vec, 100)
+            np.testing.assert_allclose(val, gv, rtol=RTOL)
+            # and it stays close to the exact fp32 answer: half inputs carry 11 significant bits
+            fi, fv = orc.gold_topk_f32(x, y, v, vec, 100)
+            np.testing.assert_allclose(val, fv, rtol=2e-3)
+            assert len(set(idx.tolist()) & set(fi.tolist())) >= 90
+
+
+@pytest.mark.parametrize("k,chunk_nnz", [(1, 256), (100, 128), (500, 4096), (1024, 1024)])
+def test_half_mode_k_and_chunk_sweep(cuda_required, tks, orc, cfg1, k, chunk_nnz):
+    x, y, v, ptr = cfg1
+    vec = make_query(1024, 11)
+    idx, val, cnt = run_engine(tks, ptr, y, v, 10000, 1024, vec, k, half=True, chunk_nnz=chunk_nnz)
+    check_against_scores(idx, val, cnt, orc.spmv_f32(x, y, orc.half_round(v), orc.half_round(vec), 10000), k)
+
+
+@pytest.mark.parametrize("tie_higher", [False, True])
+def test_half_mode_exact_ties_and_empty_rows(cuda_required, tks, orc, tie_higher):
+    """Powers of two are exact in half: the result must be bit-exact including the tie order."""
+    rng = np.random.default_rng(99)
+    rows, k = 4000, 100
+    ptr, x, col, val, vec = exact_matrix(rows, 256, rng, 9, 0.15)
+    yref = orc.spmv_f32(x, col, val, vec, rows)
+    nonempty = np.diff(ptr.astype(np.int64)) > 0
+    with tks.SpMV(ptr, col, val, rows, 256, vec=vec, k=k, tie_higher=tie_higher, chunk_nnz=256, half=True) as s:
+        s()
+        v, i, c = s.read_result()
+    cand = np.nonzero(nonempty)[0]
+    order = cand[np.lexsort((cand if not tie_higher else -cand, -yref[cand].astype(np.float64)))][:k]
+    assert c == min(k, cand.size)
+    assert np.array_equal(i[:c], order.astype(np.uint32))
+    assert np.array_equal(v[:c].view(np.uint32), yref[order].view(np.uint32))
+
+
+def test_half_mode_batched_queries(cuda_required, tks, orc, cfg1):
+    """Batched pass over half values: sequential fp32 sums of exact products -> bit-identical to the gold's arithmetic."""
+    x, y, v, ptr = cfg1
+    vecs = np.stack([make_query(1024, 40 + q) for q in range(5)])
+    with tks.SpMV(ptr, y, v, 10000, 1024, k=50, max_batch=8, half=True) as s:
+        s.reset(vecs)
+        s()
+        for q in range(5):
+            val, idx, cnt = s.read_result(q)
+            yref = orc.spmv_f32(x, y, orc.half_round(v), orc.half_round(vecs[q]), 10000)
+            check_against_scores(idx, val, cnt, yref, 50)
+            assert np.array_equal(val.view(np.uint32), yref[idx].view(np.uint32))
+
+
+def test_half_mode_rejected_in_fixed_mode(tks):
+    cfg = tks.capi.default_config(mode=tks.capi.MODE_FIXED_BSCSR, value_type=tks.capi.VALUE_FP16)
+    import ctypes as C
+    h = C.c_void_p()
+    assert tks.capi.lib().tks_create(C.byref(cfg), C.byref(h)) == tks.capi.TKS_EINVAL
