@@ -48,6 +48,7 @@ class TksError(RuntimeError):
 SYMBOLS = [
     "tks_version", "tks_default_config", "tks_create", "tks_destroy", "tks_last_error",
     "tks_upload_csr", "tks_upload_csr_device", "tks_upload_bscsr", "tks_generate_synthetic",
+    "tks_upload_coo_fixed", "tks_upload_coo_fixed_device", "tks_bscsr_state_digest",
     "tks_download_csr", "tks_set_query", "tks_set_query_device", "tks_run", "tks_run_async",
     "tks_read_result", "tks_read_partition_results", "tks_result_keys_device", "tks_merge_keys_device", "tks_merge_keys_batched_device",
     "tks_get_stats", "tks_bscsr_packet_size", "tks_fixed32_from_double", "tks_fixedW_from_fixed32",
@@ -80,6 +81,9 @@ def lib() -> C.CDLL:
     L.tks_upload_csr.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint64, vp, C.c_int, vp, vp, C.c_uint64]
     L.tks_upload_csr_device.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint64, vp, C.c_int, vp, vp, C.c_uint64]
     L.tks_upload_bscsr.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+    L.tks_upload_coo_fixed.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32]
+    L.tks_upload_coo_fixed_device.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32]
+    L.tks_bscsr_state_digest.argtypes = [vp, vp, C.c_uint32]
     L.tks_generate_synthetic.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64]
     L.tks_download_csr.argtypes = [vp, vp, vp, vp]
     L.tks_set_query.argtypes = [vp, vp, C.c_uint32]

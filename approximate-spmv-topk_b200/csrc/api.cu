@@ -130,20 +130,6 @@ void free_matrix(Handle *h) {
     h->have_matrix = false;
 }
 
-// Exclusive scan of n u32 values into n+1 u64 values (setup only).
-int device_scan_u32(Handle *h, const uint32_t *d_in, uint64_t n, uint64_t *d_out) {
-    cudaStream_t s = h->stream;
-    const uint32_t nb = (uint32_t)((n + kScanBlock - 1) / kScanBlock);
-    uint64_t *d_bs = nullptr;
-    TKS_CUDA(h, cudaMalloc(&d_bs, ((size_t)nb + 1) * sizeof(uint64_t)));
-    scan_block_sums_kernel<<<nb, kScanBlock, 0, s>>>(d_in, n, d_bs);
-    scan_block_offsets_kernel<<<1, 32, 0, s>>>(d_bs, nb);
-    scan_finish_kernel<<<nb, kScanBlock, 0, s>>>(d_in, n, d_bs, d_out);
-    TKS_CUDA(h, cudaStreamSynchronize(s));
-    cudaFree(d_bs);
-    return TKS_OK;
-}
-
 // Build colf + chunk table (+ row map when rows are empty) from a device CSR.  val is copied unless adopted.
 template <typename P>
 int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, const P *d_ptr,
@@ -243,7 +229,7 @@ void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool
     if (n_sample > h->n_sample_cap) n_sample = h->n_sample_cap;
     const uint32_t stride = h->n_chunks / n_sample;
     size_t sample_smem = ((size_t)h->cols + 1u) * 4u;
-    if (sample_smem < (size_t)n_sample * 4u) sample_smem = (size_t)n_sample * 4u;
+    if (sample_smem < ((size_t)n_sample + kHistScratchWords) * 4u) sample_smem = ((size_t)n_sample + kHistScratchWords) * 4u;
     const float *x = h->d_x + (size_t)q * h->cols;
     RunState *st = h->d_state + q;
     const uint32_t sgrid = (n_sample * kWarp + kSampleThreads - 1) / kSampleThreads;
@@ -371,6 +357,20 @@ int resolve_batched_overflow(Handle *h, cudaStream_t s) {
 
 }  // namespace
 
+// Exclusive scan of n u32 values into n+1 u64 values (setup only).
+int tks::device_scan_u32(Handle *h, const uint32_t *d_in, uint64_t n, uint64_t *d_out) {
+    cudaStream_t s = h->stream;
+    const uint32_t nb = (uint32_t)((n + kScanBlock - 1) / kScanBlock);
+    uint64_t *d_bs = nullptr;
+    TKS_CUDA(h, cudaMalloc(&d_bs, ((size_t)nb + 1) * sizeof(uint64_t)));
+    scan_block_sums_kernel<<<nb, kScanBlock, 0, s>>>(d_in, n, d_bs);
+    scan_block_offsets_kernel<<<1, 32, 0, s>>>(d_bs, nb);
+    scan_finish_kernel<<<nb, kScanBlock, 0, s>>>(d_in, n, d_bs, d_out);
+    TKS_CUDA(h, cudaStreamSynchronize(s));
+    cudaFree(d_bs);
+    return TKS_OK;
+}
+
 // ---------------------------------------------------------------------------
 
 extern "C" {
@@ -457,7 +457,7 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
         if ((e = prep_main<2048>(h, 3)) != cudaSuccess) return bail("prep_main<2048>", e);
         {
             size_t ss = ((size_t)cfg->max_cols + 1u) * 4u;
-            if (ss < 8192u * 4u) ss = 8192u * 4u;
+            if (ss < (8192u + kHistScratchWords) * 4u) ss = (8192u + kHistScratchWords) * 4u;
             if ((e = cudaFuncSetAttribute(csr_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess ||
                 (e = cudaFuncSetAttribute(csr_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess)
                 return bail("sample smem attr", e);

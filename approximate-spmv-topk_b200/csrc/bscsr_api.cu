@@ -6,6 +6,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "bscsr_pack.cuh"
 #include "bscsr_topk.cuh"
 #include "handle.hpp"
 
@@ -116,21 +117,41 @@ bool width_supported(int W) { return W == 20 || W == 21 || W == 25 || W == 26 ||
 
 }  // namespace
 
-int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *packets_per_part,
-                 const void *const *packets, const uint32_t *first_row, const uint64_t *nnz_per_part) {
+// Common first half of every upload path: knob validation and a fresh state object.
+static int bscsr_begin_upload(Handle *h, uint32_t cols, uint32_t partitions, BscsrState **out) {
     if (h->cfg.mode != TKS_MODE_FIXED_BSCSR) return h->fail(TKS_ESTATE, "handle is not in FIXED_BSCSR mode");
-    if (!packets_per_part || !packets || !first_row) return h->fail(TKS_EINVAL, "null argument");
     if (partitions != (uint32_t)h->cfg.partitions) return h->fail(TKS_EINVAL, "partitions != cfg.partitions");
     if (cols == 0 || cols > 1024) return h->fail(TKS_EINVAL, "cols outside 1..1024 (10-bit column field)");
     const int W = h->cfg.fixed_width, LFR = h->cfg.limited_finished_rows, Kp = h->cfg.local_k;
     if (!width_supported(W)) return h->fail(TKS_EINVAL, "fixed_width=%d is not instantiated (20, 21, 25, 26, 32)", W);
     if (Kp < 1 || Kp > (int)kBsMaxKp) return h->fail(TKS_EINVAL, "local_k outside 1..32");
     if (LFR < 1 || LFR > (int)kBsMaxLfr) return h->fail(TKS_EINVAL, "limited_finished_rows outside 1..4");
-    const int B = tks_bscsr_packet_size(W);
     bscsr_destroy(h);
     BscsrState *b = new BscsrState();
     h->bs = b;
-    b->P = partitions; b->cols = cols; b->B = (uint32_t)B;
+    b->P = partitions; b->cols = cols; b->B = (uint32_t)tks_bscsr_packet_size(W);
+    b->chunk_cap = 512;
+    // FIXED_WIDTH <= 22: value + column fit one word -> re-encode into the BSX device format (bscsr_topk.cuh);
+    // TKS_BSCSR_VERBATIM=1 keeps the reference's words (the path the wider formats always take)
+    b->bsx = (W + 10 <= 32) && !(std::getenv("TKS_BSCSR_VERBATIM") && std::atoi(std::getenv("TKS_BSCSR_VERBATIM")) != 0);
+    const bool drift_free = h->cfg.fixed_drift_free != 0;
+    if (drift_free) b->chunk_cap = 256;   // up to B rows can finish per packet: keeps the 12-bit in-chunk row offset in range
+    if (drift_free && (!b->bsx || LFR < 2))
+        return h->fail(TKS_EINVAL, "fixed_drift_free needs fixed_width <= 22 (the re-encoded device format) and limited_finished_rows >= 2");
+    *out = b;
+    return TKS_OK;
+}
+
+static int bscsr_finish_upload(Handle *h, BscsrState *b, uint32_t cols, uint64_t total);
+
+int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *packets_per_part,
+                 const void *const *packets, const uint32_t *first_row, const uint64_t *nnz_per_part) {
+    if (!packets_per_part || !packets || !first_row) return h->fail(TKS_EINVAL, "null argument");
+    BscsrState *b = nullptr;
+    int rc0 = bscsr_begin_upload(h, cols, partitions, &b);
+    if (rc0) return rc0;
+    const int W = h->cfg.fixed_width, LFR = h->cfg.limited_finished_rows;
+    const int B = (int)b->B;
     b->first_row.assign(first_row, first_row + partitions);
     uint64_t total = 0;
     for (uint32_t p = 0; p < partitions; p++) {
@@ -140,14 +161,7 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     }
     if (total > 0xFFFFFFF0ull) return h->fail(TKS_EINVAL, "more than 2^32 packets on one device");
     b->total_packets = total;
-    b->chunk_cap = 512;
-    // FIXED_WIDTH <= 22: value + column fit one word -> re-encode into the BSX device format (bscsr_topk.cuh);
-    // TKS_BSCSR_VERBATIM=1 keeps the reference's words (the path the wider formats always take)
-    b->bsx = (W + 10 <= 32) && !(std::getenv("TKS_BSCSR_VERBATIM") && std::atoi(std::getenv("TKS_BSCSR_VERBATIM")) != 0);
     const bool drift_free = h->cfg.fixed_drift_free != 0;
-    if (drift_free) b->chunk_cap = 256;   // up to B rows can finish per packet: keeps the 12-bit in-chunk row offset in range
-    if (drift_free && (!b->bsx || LFR < 2))
-        return h->fail(TKS_EINVAL, "fixed_drift_free needs fixed_width <= 22 (the re-encoded device format) and limited_finished_rows >= 2");
     std::vector<std::vector<uint32_t>> enc(b->bsx ? partitions : 0);
     auto field = [](const uint8_t *pk72, int pos, int len) -> uint32_t {
         uint64_t v;
@@ -293,6 +307,13 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     TKS_CUDA(h, up(&b->d_s_part, s_part));
     TKS_CUDA(h, up(&b->d_s_part_begin, s_part_begin));
     TKS_CUDA(h, up(&b->d_sample_end, sample_end));
+    return bscsr_finish_upload(h, b, cols, total);
+}
+
+// Common second half: per-query scratch, logs, result words, statistics.
+static int bscsr_finish_upload(Handle *h, BscsrState *b, uint32_t cols, uint64_t total) {
+    const int LFR = h->cfg.limited_finished_rows, Kp = h->cfg.local_k, B = (int)b->B;
+    const uint32_t partitions = b->P;
     TKS_CUDA(h, cudaMalloc(&b->d_piece_top, (size_t)b->n_pieces * LFR * 32 * 4));
     TKS_CUDA(h, cudaMalloc(&b->d_ticket, partitions * 4));
     TKS_CUDA(h, cudaMemset(b->d_ticket, 0, partitions * 4));
@@ -325,6 +346,159 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
     h->stats.algorithmic_bytes = 64ull * total + 64ull * ((cols + B - 1) / B) + (uint64_t)partitions * Kp * 128ull;
     h->stats.launches_per_run = 3;
     return TKS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GPU-side packer: partitioning + packets + device tables from row-sorted COO.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+template <int W>
+void launch_pack(bool bsx, uint32_t grid, cudaStream_t s, const uint32_t *row, const uint32_t *col, const uint32_t *val32,
+                 PackParts parts, uint64_t total, int LFR, int drift_free, uint8_t *packets, uint32_t *advance, uint8_t *keep) {
+    if constexpr (W + 10 <= 32) {
+        if (bsx) {
+            bscsr_pack_kernel<W, true><<<grid, 128, 0, s>>>(row, col, val32, parts, total, LFR, drift_free, packets, advance, keep);
+            return;
+        }
+    }
+    bscsr_pack_kernel<W, false><<<grid, 128, 0, s>>>(row, col, val32, parts, total, LFR, drift_free, packets, advance, keep);
+}
+
+struct DevFree {   // frees the temporaries of bscsr_upload_coo on every exit path
+    std::vector<void *> ptrs;
+    ~DevFree() { for (void *p : ptrs) cudaFree(p); }
+    template <typename T> cudaError_t alloc(T **p, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+};
+
+}  // namespace
+
+int bscsr_upload_coo(Handle *h, const uint32_t *row, const uint32_t *col, const uint32_t *val32, uint64_t nnz,
+                     uint32_t num_rows, uint32_t cols, bool arrays_on_device) {
+    if (!row || !col || !val32) return h->fail(TKS_EINVAL, "null argument");
+    if (nnz == 0 || num_rows == 0) return h->fail(TKS_EINVAL, "empty matrix");
+    BscsrState *b = nullptr;
+    const uint32_t P = (uint32_t)h->cfg.partitions;
+    int rc = bscsr_begin_upload(h, cols, P, &b);
+    if (rc) return rc;
+    const int W = h->cfg.fixed_width, LFR = h->cfg.limited_finished_rows;
+    const int B = (int)b->B;
+    const int drift_free = h->cfg.fixed_drift_free != 0;
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    DevFree tmp;
+    const uint32_t *d_row = row, *d_col = col, *d_val = val32;
+    if (!arrays_on_device) {
+        uint32_t *r = nullptr, *c = nullptr, *v = nullptr;
+        TKS_CUDA(h, tmp.alloc(&r, nnz * 4)); TKS_CUDA(h, tmp.alloc(&c, nnz * 4)); TKS_CUDA(h, tmp.alloc(&v, nnz * 4));
+        TKS_CUDA(h, cudaMemcpyAsync(r, row, nnz * 4, cudaMemcpyHostToDevice, s));
+        TKS_CUDA(h, cudaMemcpyAsync(c, col, nnz * 4, cudaMemcpyHostToDevice, s));
+        TKS_CUDA(h, cudaMemcpyAsync(v, val32, nnz * 4, cudaMemcpyHostToDevice, s));
+        d_row = r; d_col = c; d_val = v;
+    }
+    // input checks + row partitioning (host_spmv_bscsr.cpp:136-150)
+    uint32_t *d_err = nullptr;
+    uint64_t *d_nnz_start = nullptr, *d_pkt_start = nullptr;
+    TKS_CUDA(h, tmp.alloc(&d_err, 4));
+    TKS_CUDA(h, tmp.alloc(&d_nnz_start, (P + 1) * 8));
+    TKS_CUDA(h, tmp.alloc(&d_pkt_start, (P + 1) * 8));
+    TKS_CUDA(h, cudaMemsetAsync(d_err, 0, 4, s));
+    bscsr_pack_check_kernel<<<h->num_sms * 8, 256, 0, s>>>(d_row, d_col, nnz, num_rows, cols, d_err);
+    const uint32_t rpp = (num_rows + P - 1) / P;
+    bscsr_partition_kernel<<<(P + 1 + 127) / 128, 128, 0, s>>>(d_row, nnz, rpp, P, d_nnz_start);
+    std::vector<uint64_t> nnz_start(P + 1), pkt_start(P + 1, 0);
+    uint32_t herr = 0;
+    TKS_CUDA(h, cudaMemcpyAsync(nnz_start.data(), d_nnz_start, (P + 1) * 8, cudaMemcpyDeviceToHost, s));
+    TKS_CUDA(h, cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, s));
+    TKS_CUDA(h, cudaStreamSynchronize(s));
+    if (herr)
+        return h->fail(TKS_EINVAL, "invalid COO:%s%s%s", (herr & kPackErrUnsorted) ? " rows are not sorted;" : "",
+                       (herr & kPackErrRowRange) ? " row index beyond num_rows;" : "",
+                       (herr & kPackErrColRange) ? " column index >= cols;" : "");
+    for (uint32_t p = 0; p < P; p++) {
+        const uint64_t n = nnz_start[p + 1] - nnz_start[p];
+        if (n == 0)
+            return h->fail(TKS_EINVAL, "partition %u has no non-zeros (the reference requires every row range to be populated)", p);
+        pkt_start[p + 1] = pkt_start[p] + (n + (uint64_t)B - 1) / (uint64_t)B;
+    }
+    const uint64_t total = pkt_start[P];
+    if (total > 0xFFFFFFF0ull) return h->fail(TKS_EINVAL, "more than 2^32 packets on one device");
+    b->total_packets = total;
+    b->total_nnz = nnz;
+    TKS_CUDA(h, cudaMemcpyAsync(d_pkt_start, pkt_start.data(), (P + 1) * 8, cudaMemcpyHostToDevice, s));
+    // first row of every partition (host:145): one 4-byte read each
+    b->first_row.assign(P, 0);
+    for (uint32_t p = 0; p < P; p++)
+        TKS_CUDA(h, cudaMemcpyAsync(&b->first_row[p], d_row + nnz_start[p], 4, cudaMemcpyDeviceToHost, s));
+
+    // packets + per-packet row-counter advance and carry flag
+    uint32_t *d_adv = nullptr;
+    uint8_t *d_keep = nullptr;
+    uint64_t *d_rowsum = nullptr;
+    TKS_CUDA(h, cudaMalloc(&b->d_packets, total * 64));
+    TKS_CUDA(h, tmp.alloc(&d_adv, total * 4));
+    TKS_CUDA(h, tmp.alloc(&d_keep, total));
+    TKS_CUDA(h, tmp.alloc(&d_rowsum, (total + 1) * 8));
+    const PackParts parts{d_nnz_start, d_pkt_start, P};
+    const uint32_t pgrid = (uint32_t)((total + 127) / 128);
+    switch (W) {
+        case 20: launch_pack<20>(b->bsx, pgrid, s, d_row, d_col, d_val, parts, total, LFR, drift_free, b->d_packets, d_adv, d_keep); break;
+        case 21: launch_pack<21>(b->bsx, pgrid, s, d_row, d_col, d_val, parts, total, LFR, drift_free, b->d_packets, d_adv, d_keep); break;
+        case 25: launch_pack<25>(b->bsx, pgrid, s, d_row, d_col, d_val, parts, total, LFR, drift_free, b->d_packets, d_adv, d_keep); break;
+        case 26: launch_pack<26>(b->bsx, pgrid, s, d_row, d_col, d_val, parts, total, LFR, drift_free, b->d_packets, d_adv, d_keep); break;
+        default: launch_pack<32>(b->bsx, pgrid, s, d_row, d_col, d_val, parts, total, LFR, drift_free, b->d_packets, d_adv, d_keep); break;
+    }
+    TKS_CUDA(h, cudaGetLastError());
+    rc = device_scan_u32(h, d_adv, total, d_rowsum);   // synchronises the stream
+    if (rc) return rc;
+
+    // chunk and sample-piece tables: count, then fill
+    uint32_t *d_nch = nullptr, *d_npc = nullptr, *d_cbeg = nullptr, *d_pbeg = nullptr;
+    TKS_CUDA(h, tmp.alloc(&d_nch, P * 4)); TKS_CUDA(h, tmp.alloc(&d_npc, P * 4));
+    TKS_CUDA(h, cudaMalloc(&b->d_part_chunk_begin, (P + 1) * 4));
+    TKS_CUDA(h, cudaMalloc(&b->d_s_part_begin, (P + 1) * 4));
+    d_cbeg = b->d_part_chunk_begin; d_pbeg = b->d_s_part_begin;
+    WalkOut wo{};
+    wo.n_chunks = d_nch; wo.n_pieces = d_npc;
+    bscsr_chunk_walk_kernel<<<(P + 31) / 32, 32, 0, s>>>(parts, d_keep, d_rowsum, total, b->chunk_cap, wo);
+    std::vector<uint32_t> nch(P), npc(P), cbeg(P + 1, 0), pbeg(P + 1, 0);
+    TKS_CUDA(h, cudaMemcpyAsync(nch.data(), d_nch, P * 4, cudaMemcpyDeviceToHost, s));
+    TKS_CUDA(h, cudaMemcpyAsync(npc.data(), d_npc, P * 4, cudaMemcpyDeviceToHost, s));
+    TKS_CUDA(h, cudaStreamSynchronize(s));
+    for (uint32_t p = 0; p < P; p++) { cbeg[p + 1] = cbeg[p] + nch[p]; pbeg[p + 1] = pbeg[p] + npc[p]; }
+    b->n_chunks = cbeg[P];
+    b->n_pieces = pbeg[P];
+    TKS_CUDA(h, cudaMemcpyAsync(d_cbeg, cbeg.data(), (P + 1) * 4, cudaMemcpyHostToDevice, s));
+    TKS_CUDA(h, cudaMemcpyAsync(d_pbeg, pbeg.data(), (P + 1) * 4, cudaMemcpyHostToDevice, s));
+    const size_t nc4 = std::max<size_t>(1, b->n_chunks) * 4, np4 = std::max<size_t>(1, b->n_pieces) * 4;
+    TKS_CUDA(h, cudaMalloc(&b->d_chunk_first, nc4)); TKS_CUDA(h, cudaMalloc(&b->d_chunk_count, nc4));
+    TKS_CUDA(h, cudaMalloc(&b->d_chunk_local0, nc4)); TKS_CUDA(h, cudaMalloc(&b->d_chunk_row_in, nc4));
+    TKS_CUDA(h, cudaMalloc(&b->d_chunk_lookback, nc4)); TKS_CUDA(h, cudaMalloc(&b->d_chunk_part, nc4));
+    TKS_CUDA(h, cudaMalloc(&b->d_s_first, np4)); TKS_CUDA(h, cudaMalloc(&b->d_s_count, np4));
+    TKS_CUDA(h, cudaMalloc(&b->d_s_local0, np4)); TKS_CUDA(h, cudaMalloc(&b->d_s_lookback, np4));
+    TKS_CUDA(h, cudaMalloc(&b->d_s_part, np4));
+    TKS_CUDA(h, cudaMalloc(&b->d_sample_end, P * 4));
+    wo.first = b->d_chunk_first; wo.count = b->d_chunk_count; wo.local0 = b->d_chunk_local0; wo.row_in = b->d_chunk_row_in;
+    wo.look = b->d_chunk_lookback; wo.part = b->d_chunk_part;
+    wo.s_first = b->d_s_first; wo.s_count = b->d_s_count; wo.s_local0 = b->d_s_local0; wo.s_look = b->d_s_lookback;
+    wo.s_part = b->d_s_part; wo.sample_end = b->d_sample_end;
+    wo.chunk_begin = d_cbeg; wo.piece_begin = d_pbeg;
+    bscsr_chunk_walk_kernel<<<(P + 31) / 32, 32, 0, s>>>(parts, d_keep, d_rowsum, total, b->chunk_cap, wo);
+    if (b->bsx) {
+        TKS_CUDA(h, cudaMemsetAsync(d_err, 0, 4, s));
+        bscsr_patch_rel_kernel<<<(b->n_chunks * 32u + 255u) / 256u, 256, 0, s>>>(
+            b->d_packets, b->d_chunk_first, b->d_chunk_count, b->d_chunk_part, b->d_chunk_row_in, b->n_chunks, d_rowsum,
+            d_pkt_start, d_err);
+        TKS_CUDA(h, cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, s));
+    }
+    TKS_CUDA(h, cudaStreamSynchronize(s));
+    TKS_CUDA(h, cudaGetLastError());
+    if (herr & kPackErrRel) return h->fail(TKS_EINVAL, "internal: row offset inside a chunk exceeds 12 bits");
+    return bscsr_finish_upload(h, b, cols, total);
 }
 
 int bscsr_set_query(Handle *h, const uint32_t *vec32_host, const uint32_t *vec32_dev, cudaStream_t s) {
@@ -456,6 +630,44 @@ int bscsr_read_partition_results(Handle *h, uint32_t *idx_words, uint32_t *val_w
     return TKS_OK;
 }
 
+// FNV-1a digests of the resident matrix state, in a fixed order (packets, the six chunk tables, the partition
+// chunk offsets, the five sample tables, their offsets, sample_end, first_row): lets a test assert that two upload
+// paths leave byte-identical device state without shipping it back through the ABI.
+int bscsr_state_digest(Handle *h, uint64_t *digest, uint32_t n) {
+    BscsrState *b = h->bs;
+    if (!b || !h->have_matrix) return h->fail(TKS_ESTATE, "no BS-CSR matrix resident");
+    if (n < 16) return h->fail(TKS_EINVAL, "digest array needs 16 entries");
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    auto fnv = [&](const void *dptr, size_t bytes, uint64_t *out) -> cudaError_t {
+        std::vector<uint8_t> buf(bytes);
+        cudaError_t e = cudaMemcpy(buf.data(), dptr, bytes, cudaMemcpyDeviceToHost);
+        uint64_t hsh = 1469598103934665603ull;
+        for (uint8_t c : buf) { hsh ^= c; hsh *= 1099511628211ull; }
+        *out = hsh;
+        return e;
+    };
+    const size_t nc = (size_t)b->n_chunks * 4, np = (size_t)b->n_pieces * 4;
+    TKS_CUDA(h, fnv(b->d_packets, b->total_packets * 64, &digest[0]));
+    TKS_CUDA(h, fnv(b->d_chunk_first, nc, &digest[1]));
+    TKS_CUDA(h, fnv(b->d_chunk_count, nc, &digest[2]));
+    TKS_CUDA(h, fnv(b->d_chunk_local0, nc, &digest[3]));
+    TKS_CUDA(h, fnv(b->d_chunk_row_in, nc, &digest[4]));
+    TKS_CUDA(h, fnv(b->d_chunk_lookback, nc, &digest[5]));
+    TKS_CUDA(h, fnv(b->d_chunk_part, nc, &digest[6]));
+    TKS_CUDA(h, fnv(b->d_part_chunk_begin, ((size_t)b->P + 1) * 4, &digest[7]));
+    TKS_CUDA(h, fnv(b->d_s_first, np, &digest[8]));
+    TKS_CUDA(h, fnv(b->d_s_count, np, &digest[9]));
+    TKS_CUDA(h, fnv(b->d_s_local0, np, &digest[10]));
+    TKS_CUDA(h, fnv(b->d_s_lookback, np, &digest[11]));
+    TKS_CUDA(h, fnv(b->d_s_part, np, &digest[12]));
+    TKS_CUDA(h, fnv(b->d_s_part_begin, ((size_t)b->P + 1) * 4, &digest[13]));
+    TKS_CUDA(h, fnv(b->d_sample_end, (size_t)b->P * 4, &digest[14]));
+    uint64_t hsh = 1469598103934665603ull;
+    for (uint32_t r : b->first_row) for (int i = 0; i < 4; i++) { hsh ^= (r >> (8 * i)) & 0xFF; hsh *= 1099511628211ull; }
+    digest[15] = hsh ^ ((uint64_t)b->n_chunks << 32) ^ b->n_pieces;
+    return TKS_OK;
+}
+
 void bscsr_destroy(Handle *h) {
     BscsrState *b = h->bs;
     if (!b) return;
@@ -472,6 +684,23 @@ void bscsr_destroy(Handle *h) {
 }
 
 }  // namespace tks
+
+extern "C" int tks_upload_coo_fixed(tks_handle *h, const uint32_t *row, const uint32_t *col, const uint32_t *val32,
+                                    uint64_t nnz, uint32_t num_rows, uint32_t cols) {
+    if (!h) return TKS_EINVAL;
+    return tks::bscsr_upload_coo(h, row, col, val32, nnz, num_rows, cols, false);
+}
+
+extern "C" int tks_upload_coo_fixed_device(tks_handle *h, const uint32_t *d_row, const uint32_t *d_col,
+                                           const uint32_t *d_val32, uint64_t nnz, uint32_t num_rows, uint32_t cols) {
+    if (!h) return TKS_EINVAL;
+    return tks::bscsr_upload_coo(h, d_row, d_col, d_val32, nnz, num_rows, cols, true);
+}
+
+extern "C" int tks_bscsr_state_digest(tks_handle *h, uint64_t *digest, uint32_t n) {
+    if (!h || !digest) return TKS_EINVAL;
+    return tks::bscsr_state_digest(h, digest, n);
+}
 
 extern "C" int tks_upload_bscsr(tks_handle *h, uint32_t cols, uint32_t partitions, const uint64_t *packets_per_part,
                                 const void *const *packets, const uint32_t *first_row, const uint64_t *nnz_per_part) {

@@ -127,7 +127,8 @@ __device__ __forceinline__ void csr_iter(const typename ValRaw<HALF>::type &vraw
     const unsigned lane = lane_id();
     float cm = neg_inf();
     // bit j <=> element j starts a row (elements outside [lo, hi) start nothing)
-    const uint32_t fb = MASKED ? (rbits & ((1u << hi) - 1u) & ~((1u << lo) - 1u)) : rbits;
+    const uint32_t inmask = ((1u << hi) - 1u) & ~((1u << lo) - 1u);   // elements j in [lo, hi) are inside the chunk
+    const uint32_t fb = MASKED ? (rbits & inmask) : rbits;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         uint32_t c = (j & 1) ? (craw.w[j >> 1] >> 16) : (craw.w[j >> 1] & 0xFFFFu);   // column * 4
@@ -139,7 +140,7 @@ __device__ __forceinline__ void csr_iter(const typename ValRaw<HALF>::type &vraw
             v = __uint_as_float(vraw.w[j]);
         }
         if (MASKED) {
-            const bool in = ((uint32_t)j >= lo) && ((uint32_t)j < hi);
+            const bool in = (inmask >> j) & 1u;
             c = in ? c : zero_off;      // column -> the zero slot behind x
             v = in ? v : 0.0f;
         }
@@ -243,6 +244,7 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
     const bool truncated = n_iter64 > max_iters;
     const uint32_t n_iter = truncated ? max_iters : (uint32_t)n_iter64;
     const uint32_t last_iter = (uint32_t)n_iter64 - 1;   // chunks are far smaller than 2^32 * 256 non-zeros
+    const int32_t rel_s = (int32_t)(s - a0), rel_e = (int32_t)(e - a0);
     constexpr uint32_t kValBytes = HALF ? 2u : 4u;
     const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val) + a0 * kValBytes + lane * (kEpl * kValBytes);
     const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.col16 + a0) + lane * 16u;
@@ -269,10 +271,11 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
         float carry_out;
         if (it == 0 || it == last_iter) {
             // lanes' elements outside [s, e) are neutralised
-            const int64_t ebase = (int64_t)(a0 + (uint64_t)it * kElemsPerIter + lane * kEpl);
-            const int64_t l64 = (int64_t)s - ebase, h64 = (int64_t)e - ebase;
-            const uint32_t lo = l64 < 0 ? 0u : (l64 > 8 ? 8u : (uint32_t)l64);
-            const uint32_t hi = h64 < 0 ? 0u : (h64 > 8 ? 8u : (uint32_t)h64);
+            // offsets inside the chunk fit 32 bits (a chunk is far smaller than 2^31 non-zeros)
+            const int32_t ebase = (int32_t)(it * kElemsPerIter + lane * kEpl);
+            const int32_t l32 = rel_s - ebase, h32 = rel_e - ebase;
+            const uint32_t lo = l32 < 0 ? 0u : (l32 > 8 ? 8u : (uint32_t)l32);
+            const uint32_t hi = h32 < 0 ? 0u : (h32 > 8 ? 8u : (uint32_t)h32);
             csr_iter<true, HALF>(cv, cc, cr, xs_bytes, zero_off, lo, hi, carry, carry_out, o);
         } else {
             csr_iter<false, HALF>(cv, cc, cr, xs_bytes, zero_off, 0u, 8u, carry, carry_out, o);
@@ -380,11 +383,96 @@ __device__ __forceinline__ KeyT block_radix_select(LoadF load, uint32_t n, uint3
 }
 
 // --------------------------------------------------------------------------
-// Kernel 1: threshold from a sample.  Warp w reduces the first sample_iters
-// iterations (256 non-zeros each; ~1 % of the matrix in total) of chunk w*stride exactly as the main kernel will and keeps the
-// best completed row.  The k-th largest of these warp maxima is the score of k
-// distinct real rows, hence a valid lower bound on the k-th best score.
-// Dynamic shared memory: max((cols+1)*4, n_sample*4) bytes.
+// A lower bound on the k-th largest of n 32-bit keys (key 0 = absent) in ONE histogram pass: 2048 bins laid
+// linearly over [min, max] of the keys present, so that the bins are evenly filled whatever bits the keys share
+// (the ordered-float scores of one query agree in sign and most of the exponent; an MSB radix digit would put
+// them all in two or three bins).  Returns the lower edge `thr` of the bin that holds the k-th largest key:
+// at least k keys are >= thr, and at most (k - 1 + that bin's count) are.  Returns 0 when fewer than k keys
+// are present.  Every thread of the CTA calls it and gets the same value.
+// scratch: kHistScratchWords words of shared memory.
+// --------------------------------------------------------------------------
+constexpr uint32_t kHistBins = 2048;
+constexpr uint32_t kHistGroups = kHistBins / 32;
+constexpr uint32_t kHistScratchWords = kHistBins + kHistGroups + 3 * 32 + 4;
+
+template <typename LoadF>
+__device__ __forceinline__ uint32_t block_hist_threshold(LoadF load32, uint32_t n, uint32_t k, uint32_t *scratch,
+                                                         uint32_t *bin_count_out = nullptr) {
+    uint32_t *hist = scratch, *gs = scratch + kHistBins, *red = gs + kHistGroups, *res = red + 3 * 32;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x, nwarps = nthr / kWarp;
+    const unsigned lane = lane_id();
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u, cnt = 0u;
+    for (uint32_t i = tid; i < n; i += nthr) {
+        const uint32_t key = load32(i);
+        if (key) { lo = min(lo, key); hi = max(hi, key); cnt++; }
+    }
+    lo = __reduce_min_sync(kFull, lo);
+    hi = __reduce_max_sync(kFull, hi);
+    cnt = __reduce_add_sync(kFull, cnt);
+    __syncthreads();   // scratch may still be read by the caller's previous use
+    if (lane == 0) { red[tid / kWarp] = lo; red[32 + tid / kWarp] = hi; red[64 + tid / kWarp] = cnt; }
+    for (uint32_t i = tid; i < kHistBins; i += nthr) hist[i] = 0u;
+    __syncthreads();
+    lo = 0xFFFFFFFFu; hi = 0u; cnt = 0u;
+    for (uint32_t w = 0; w < nwarps; w++) { lo = min(lo, red[w]); hi = max(hi, red[32 + w]); cnt += red[64 + w]; }
+    if (cnt < k) return 0u;   // uniform: every thread computed the same cnt
+    const uint32_t range = hi - lo;
+    const uint32_t sh = range < kHistBins ? 0u : (32u - (uint32_t)__clz(range)) - 11u;   // (range >> sh) < 2048
+    for (uint32_t i = tid; i < n; i += nthr) {
+        const uint32_t key = load32(i);
+        if (key) atomicAdd(&hist[(key - lo) >> sh], 1u);
+    }
+    __syncthreads();
+    if (tid < kHistGroups) {   // group t = bins [32t, 32t + 32), read skewed: conflict-free
+        uint32_t sum = 0;
+#pragma unroll 8
+        for (uint32_t i = 0; i < 32; i++) sum += hist[tid * 32u + ((i + tid) & 31u)];
+        gs[tid] = sum;
+    }
+    __syncthreads();
+    if (tid < kWarp) {
+        // lane l owns groups 2l (lower) and 2l + 1 (higher); suffix sums over lanes
+        const uint32_t g0 = gs[2 * lane], g1 = gs[2 * lane + 1], tot = g0 + g1;
+        uint32_t suf = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t dn = __shfl_down_sync(kFull, suf, d);
+            if (lane + d < 32) suf += dn;
+        }
+        const uint32_t above = suf - tot;   // keys in groups of higher lanes
+        int grp = -1;
+        uint32_t above_g = 0;
+        if (above < k && above + g1 >= k) { grp = 2 * (int)lane + 1; above_g = above; }
+        else if (above + g1 < k && above + tot >= k) { grp = 2 * (int)lane; above_g = above + g1; }
+        const unsigned who = __ballot_sync(kFull, grp >= 0);
+        const int src = __ffs(who) - 1;   // exactly one lane (cnt >= k)
+        grp = __shfl_sync(kFull, grp, src);
+        above_g = __shfl_sync(kFull, above_g, src);
+        const uint32_t c = hist[(uint32_t)grp * 32u + lane];
+        uint32_t sufb = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t dn = __shfl_down_sync(kFull, sufb, d);
+            if (lane + d < 32) sufb += dn;
+        }
+        const uint32_t ab = above_g + sufb - c;   // keys in higher bins
+        if (ab < k && ab + c >= k) {
+            res[0] = lo + (((uint32_t)grp * 32u + lane) << sh);
+            res[1] = ab + c;                      // keys >= the returned threshold
+        }
+    }
+    __syncthreads();
+    if (bin_count_out) *bin_count_out = res[1];
+    return res[0];
+}
+
+// --------------------------------------------------------------------------
+// Kernel 1: the sample.  Warp w reduces the first sample_iters iterations (256 non-zeros each; ~1 % of the
+// matrix in total) of chunk w*stride exactly as the main kernel will and publishes its best completed row.
+// The k-th largest of these warp maxima is the score of k distinct real rows, hence a valid lower bound on
+// the k-th best score; the last CTA to finish derives it in one histogram pass (block_hist_threshold: the lower
+// edge of the bin that holds the k-th largest maximum -- still a lower bound) and publishes it in st->tau_key.
+// Dynamic shared memory: max((cols+1)*4, (n_sample + kHistScratchWords)*4) bytes.
 // --------------------------------------------------------------------------
 // The query as the kernels see it: rounded to half and widened again in the half-precision mode.
 template <bool HALF>
@@ -411,9 +499,8 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
         key = __reduce_max_sync(kFull, key);
         if (lane_id() == 0) sample_keys[gw] = key;
     }
-    // last block picks the k-th largest
-    __shared__ uint32_t s_ticket, s_bin, s_above[2];
-    __shared__ uint32_t hist[(kSampleThreads / kWarp) * 256];
+    // last block: threshold from all the maxima
+    __shared__ uint32_t s_ticket;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_ticket = atomicAdd(&st->sample_ticket, 1u);
@@ -423,7 +510,7 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
     uint32_t *skeys = reinterpret_cast<uint32_t *>(smem_raw);   // x is no longer needed by this block
     for (uint32_t i = threadIdx.x; i < n_sample; i += blockDim.x) skeys[i] = __ldcg(sample_keys + i);
     __syncthreads();
-    const uint32_t thr = block_radix_select<uint32_t, false>([&](uint32_t i) { return skeys[i]; }, n_sample, k, hist, &s_bin, s_above);
+    const uint32_t thr = block_hist_threshold([&](uint32_t i) { return skeys[i]; }, n_sample, k, skeys + n_sample);
     if (threadIdx.x == 0) {
         if (thr != 0) atomicMax(&st->tau_key, thr);
         st->sample_ticket = 0;
@@ -491,6 +578,7 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
 // --------------------------------------------------------------------------
 constexpr uint32_t kSelectThreads = 1024;
 constexpr uint32_t kSelectSortCap = 2048;     // keys sorted directly (16 KB static)
+constexpr uint32_t kSelectRankSortMax = 512;  // up to here by rank (one pass, no barriers), above by a bitonic network
 constexpr uint32_t kSelectSmemKeys = 16384;   // pool keys staged in dynamic shared memory (128 KB)
 constexpr uint32_t kSelectDynSmem = (kSelectThreads / kWarp) * 1024u + kSelectSmemKeys * 8u;
 
@@ -532,7 +620,7 @@ select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunS
     }
 
     uint32_t m = 0;   // number of keys in keys[]
-    if (n <= kSelectSortCap) {
+    if (n <= kSelectRankSortMax) {
         for (uint32_t i = tid; i < n; i += blockDim.x) keys[i] = pool[i];
         m = n;
     } else {
@@ -542,7 +630,15 @@ select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunS
             __syncthreads();
         }
         auto load = [&](uint32_t i) { return in_smem ? staged[i] : pool[i]; };
-        const uint64_t thr = block_radix_select<uint64_t, true>(load, n, k, hist, &s_bin, s_above);
+        // one histogram pass over the score halves: every key whose score reaches the bin of the k-th best score
+        // is kept (at least k keys, a few more), the exact order is settled by the sort below
+        uint32_t reach = 0;
+        const uint32_t thr32 = block_hist_threshold([&](uint32_t i) { return (uint32_t)(load(i) >> 32); }, n, k, hist, &reach);
+        uint64_t thr = (uint64_t)thr32 << 32;
+        if (thr32 == 0 || reach > kSelectSortCap) {
+            // fewer than k keys, or a bin crowded with (nearly) equal scores: the exact radix select on the full keys
+            thr = block_radix_select<uint64_t, true>(load, n, k, hist, &s_bin, s_above);
+        }
         if (tid == 0) s_cnt = 0;
         __syncthreads();
         for (uint32_t i = tid; i < n; i += blockDim.x) {
@@ -555,17 +651,40 @@ select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunS
         __syncthreads();
         m = s_cnt < kSelectSortCap ? s_cnt : kSelectSortCap;
     }
-    uint32_t n2 = 32;
-    while (n2 < m) n2 <<= 1;
-    __syncthreads();
-    for (uint32_t i = m + tid; i < n2; i += blockDim.x) keys[i] = 0ull;
-    bitonic_sort_desc(keys, n2, tid, blockDim.x, [] { __syncthreads(); });
     const uint32_t cnt = m < k ? m : k;
-    for (uint32_t i = tid; i < k; i += blockDim.x) {
-        const uint64_t key = (i < cnt) ? keys[i] : 0ull;
-        out_keys[i] = key;
-        out_idx[i] = (i < cnt) ? key_row(key, tie_higher) : 0u;
-        out_val[i] = (i < cnt) ? ordered_to_f32(key_score(key)) : 0.0f;
+    __syncthreads();
+    if (m <= kSelectRankSortMax) {
+        // rank sort: four adjacent lanes count the keys above key i (keys are unique: they embed the row id;
+        // equal keys would still get distinct ranks through the position tie-break), the rank is the output slot
+        const uint32_t items = (4u * m + kWarp - 1u) & ~(kWarp - 1u);
+        for (uint32_t w = tid; w < items; w += blockDim.x) {
+            const uint32_t i = w >> 2, part = w & 3u;
+            const uint64_t mine = (i < m) ? keys[i] : 0ull;
+            uint32_t r = 0;
+            for (uint32_t j = part; j < m; j += 4u) {
+                const uint64_t other = keys[j];
+                r += (other > mine) || (other == mine && j < i);
+            }
+            r += __shfl_xor_sync(kFull, r, 1);
+            r += __shfl_xor_sync(kFull, r, 2);
+            if (part == 0 && i < m && r < k) {
+                out_keys[r] = mine;
+                out_idx[r] = key_row(mine, tie_higher);
+                out_val[r] = ordered_to_f32(key_score(mine));
+            }
+        }
+        for (uint32_t i = cnt + tid; i < k; i += blockDim.x) { out_keys[i] = 0ull; out_idx[i] = 0u; out_val[i] = 0.0f; }
+    } else {
+        uint32_t n2 = 32;
+        while (n2 < m) n2 <<= 1;
+        for (uint32_t i = m + tid; i < n2; i += blockDim.x) keys[i] = 0ull;
+        bitonic_sort_desc(keys, n2, tid, blockDim.x, [] { __syncthreads(); });
+        for (uint32_t i = tid; i < k; i += blockDim.x) {
+            const uint64_t key = (i < cnt) ? keys[i] : 0ull;
+            out_keys[i] = key;
+            out_idx[i] = (i < cnt) ? key_row(key, tie_higher) : 0u;
+            out_val[i] = (i < cnt) ? ordered_to_f32(key_score(key)) : 0.0f;
+        }
     }
     if (tid == 0) {
         *out_count = cnt;

@@ -98,14 +98,21 @@ struct Handle {
                              __FILE__, __LINE__);                                                      \
     } while (0)
 
+// api.cu: exclusive scan of n u32 values into n+1 u64 values on the handle's stream (setup only; synchronises)
+int device_scan_u32(Handle *h, const uint32_t *d_in, uint64_t n, uint64_t *d_out);
+
 // bscsr_api.cu
 int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *packets_per_part,
                  const void *const *packets, const uint32_t *first_row, const uint64_t *nnz_per_part);
+// GPU-side packer (bscsr_pack.cuh): row-sorted COO with raw ap_ufixed<32,1> values, host or device arrays
+int bscsr_upload_coo(Handle *h, const uint32_t *row, const uint32_t *col, const uint32_t *val32, uint64_t nnz,
+                     uint32_t num_rows, uint32_t cols, bool arrays_on_device);
 int bscsr_set_query(Handle *h, const uint32_t *vec32_host, const uint32_t *vec32_dev, cudaStream_t s);
 int bscsr_launch(Handle *h, cudaStream_t s);
 int bscsr_fetch(Handle *h);   // D2H of partition result words + host merge
 int bscsr_read_result(Handle *h, uint32_t *idx_out, uint32_t *val_out, uint32_t k, uint32_t *count);
 int bscsr_read_partition_results(Handle *h, uint32_t *idx_words, uint32_t *val_words);
+int bscsr_state_digest(Handle *h, uint64_t *digest, uint32_t n);
 void bscsr_destroy(Handle *h);
 
 }  // namespace tks

@@ -206,7 +206,7 @@ int main(int argc, char *argv[]) {
     auto t4 = clock_type::now();
     SpMVFixed spmv(x.data(), y.data(), val.data(), rows, cols, nnz, vec.data(), options.top_k_value, options.fixed_width,
                    options.partitions, options.local_k, options.limited_finished_rows, options.device, debug,
-                   options.drift_free);
+                   options.drift_free, options.device_pack);
     float setup_ms = (float)chrono::duration_cast<chrono::microseconds>(clock_type::now() - t4).count() / 1000;
     if (debug) std::cout << "b200 setup time=" << setup_ms << " ms" << std::endl;
     tks_stats st;

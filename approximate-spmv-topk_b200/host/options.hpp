@@ -9,6 +9,7 @@
 //   -e  seed of the query generator (0 = random_device, as the reference)
 //   -G  CUDA device ordinal              -T  ties -> higher index first (reference sort order)
 //   -D  fixed-point engine: repair the reference's row-counter drift (tks_config.fixed_drift_free)
+//   -P  fixed-point engine: build the BS-CSR packets on the GPU (tks_upload_coo_fixed) instead of on the host
 //   -C  <file>  binary matrix cache: loaded when present, else written after the MTX text is parsed
 #pragma once
 
@@ -61,6 +62,7 @@ struct Options {
     int device = 0;
     bool tie_higher = false;
     bool drift_free = false;
+    bool device_pack = false;
     std::string cache_path;
 
     Options(int argc, char *argv[]) {
@@ -87,10 +89,11 @@ struct Options {
                                                {"gpu", required_argument, 0, 'G'},
                                                {"tie_higher", no_argument, 0, 'T'},
                                                {"drift_free", no_argument, 0, 'D'},
+                                               {"device_pack", no_argument, 0, 'P'},
                                                {"cache", required_argument, 0, 'C'},
                                                {0, 0, 0, 0}};
         int option_index = 0, opt;
-        while ((opt = getopt_long(argc, argv, "dm:st:x:vk:rb:c:g:i:azfw:p:l:q:e:G:TDC:", long_options, &option_index)) != EOF) {
+        while ((opt = getopt_long(argc, argv, "dm:st:x:vk:rb:c:g:i:azfw:p:l:q:e:G:TDPC:", long_options, &option_index)) != EOF) {
             switch (opt) {
                 case 'd': debug = true; break;
                 case 'r': reset = true; break;   // sic: the reference's -r also sets true (options.hpp:90-92)
@@ -116,6 +119,7 @@ struct Options {
                 case 'T': tie_higher = true; break;
                 case 'D': drift_free = true; break;
                 case 'C': cache_path = optarg; break;
+                case 'P': device_pack = true; break;
                 default: break;
             }
         }

@@ -83,7 +83,8 @@ struct SpMVFixed {
 
     SpMVFixed(int_type *x, int_type *y, ufixed32 *val, int_type num_rows_, int_type num_cols_, int_type num_nnz_,
               ufixed32 *vec, int k_, int fixed_width_ = FIXED_WIDTH, int partitions_ = SPMV_PARTITIONS,
-              int local_k = K, int lfr = LIMITED_FINISHED_ROWS, int device = 0, int debug = 0, bool drift_free = false)
+              int local_k = K, int lfr = LIMITED_FINISHED_ROWS, int device = 0, int debug = 0, bool drift_free = false,
+              bool device_pack = false)
         : num_rows(num_rows_), num_cols(num_cols_), num_nnz(num_nnz_), k(k_), fixed_width(fixed_width_), partitions(partitions_) {
         tks_config cfg;
         tks_default_config(&cfg);
@@ -96,8 +97,15 @@ struct SpMVFixed {
         cfg.tie_break = TKS_TIE_HIGHER_INDEX;   // sort_tuples order of the reference merge (host:447)
         cfg.fixed_drift_free = drift_free ? 1 : 0;
         TKS_OR_DIE(nullptr, tks_create(&cfg, &h));
-        // packet_coo (host:133-187)
         static_assert(sizeof(ufixed32) == 4, "ufixed32 must be a bare 32-bit word");
+        if (device_pack) {
+            // packet_coo (host:133-187) and the device tables, built on the GPU from the COO arrays
+            if (debug) printf("Pack and write inputs on the device\n");
+            TKS_OR_DIE(h, tks_upload_coo_fixed(h, x, y, reinterpret_cast<uint32_t *>(val), num_nnz, num_rows, num_cols));
+            TKS_OR_DIE(h, tks_set_query(h, vec, 1));
+            return;
+        }
+        // packet_coo (host:133-187)
         std::vector<uint64_t> ppp(partitions), npp(partitions);
         std::vector<uint32_t> first_row(partitions);
         TKS_OR_DIE(h, tks_pack_bscsr(x, y, reinterpret_cast<uint32_t *>(val), num_nnz, num_rows, partitions, fixed_width,

@@ -156,7 +156,9 @@ class SpMVFixed(_Base):
     x, y: row-sorted COO; val32 / vec32: raw ap_ufixed<32,1> words (real_type_inout)."""
 
     def __init__(self, x, y, val32, num_rows, num_cols, vec32=None, k=100, fixed_width=20, partitions=32, local_k=8,
-                 limited_finished_rows=4, device=0, profile_kernels=False, drift_free=False):
+                 limited_finished_rows=4, device=0, profile_kernels=False, drift_free=False, device_pack=False):
+        # device_pack: partitioning, packets and device tables are built on the GPU from the COO arrays
+        # (tks_upload_coo_fixed) instead of tks_pack_bscsr on the host + tks_upload_bscsr; same resident state
         cfg = capi.default_config(mode=capi.MODE_FIXED_BSCSR, device=device, fixed_width=fixed_width,
                                   partitions=partitions, local_k=local_k,
                                   limited_finished_rows=limited_finished_rows, tie_break=capi.TIE_HIGHER_INDEX,
@@ -165,10 +167,26 @@ class SpMVFixed(_Base):
         self.k = k
         self.num_rows, self.num_cols = int(num_rows), int(num_cols)
         self.B = capi.bscsr_packet_size(fixed_width)
-        packets, ppp, first, npp = capi.pack_bscsr(x, y, val32, num_rows, partitions, fixed_width)
-        self.upload_packets(packets, ppp, first, npp)
+        if device_pack:
+            self.upload_coo(x, y, val32, num_rows, num_cols)
+        else:
+            packets, ppp, first, npp = capi.pack_bscsr(x, y, val32, num_rows, partitions, fixed_width)
+            self.upload_packets(packets, ppp, first, npp)
         if vec32 is not None:
             self.reset(vec32)
+
+    def upload_coo(self, x, y, val32, num_rows, num_cols):
+        x = np.ascontiguousarray(x, np.uint32)
+        y = np.ascontiguousarray(y, np.uint32)
+        val32 = np.ascontiguousarray(val32, np.uint32)
+        check(capi.lib().tks_upload_coo_fixed(self.handle, _ptr(x), _ptr(y), _ptr(val32), x.size, int(num_rows),
+                                              int(num_cols)), self.handle)
+        self.partitions = int(self.cfg.partitions)
+
+    def state_digest(self):
+        d = np.zeros(16, np.uint64)
+        check(capi.lib().tks_bscsr_state_digest(self.handle, _ptr(d), 16), self.handle)
+        return d
 
     def upload_packets(self, packets, ppp, first_row, npp):
         P = len(ppp)

@@ -122,6 +122,20 @@ int tks_upload_bscsr(tks_handle *h, uint32_t cols, uint32_t partitions,
                      const uint64_t *packets_per_part, const void *const *packets,
                      const uint32_t *first_row, const uint64_t *nnz_per_part);
 
+/* GPU-side packer: what the reference FPGA constructor does on the host with one thread --
+ * row partitioning (host_spmv_bscsr.cpp:112-121,136-150), packet_coo / packet_coo_partition (:133-248) with
+ * the bit layout of fpga_utils.hpp:307-365 -- plus this engine's device tables, all on the device.
+ * row/col/val32: row-sorted COO, val32 = raw ap_ufixed<32,1> words (the reference ctor's x, y, val arguments,
+ * host:104).  Leaves exactly the resident state of tks_pack_bscsr + tks_upload_bscsr.  BS-CSR mode only.   */
+int tks_upload_coo_fixed(tks_handle *h, const uint32_t *row, const uint32_t *col, const uint32_t *val32,
+                         uint64_t nnz, uint32_t num_rows, uint32_t cols);
+/* Same, with DEVICE pointers. */
+int tks_upload_coo_fixed_device(tks_handle *h, const uint32_t *d_row, const uint32_t *d_col,
+                                const uint32_t *d_val32, uint64_t nnz, uint32_t num_rows, uint32_t cols);
+/* FNV-1a digests (16 words) of the resident BS-CSR state -- packets, chunk tables, sample tables, first rows --
+ * so that a checker can assert two upload paths are byte-identical.                                      */
+int tks_bscsr_state_digest(tks_handle *h, uint64_t *digest, uint32_t n);
+
 /* Synthetic matrix generated in HBM with the law of
  * src/resources/python/create_matrices.py:84-104 (dist 0 = uniform, 1 = gamma).
  * Float mode only.  row_offset/global_rows let N ranks generate disjoint shards. */
