@@ -13,6 +13,6 @@ The directory name carries a hyphen, so import it through the repo-root shim:
 from . import accuracy, capi, create_matrices, distributed, sharding, spmv  # noqa: F401
 from .spmv import SpMV, SpMVFixed  # noqa: F401
 
-from .distributed import ShardedSpMV  # noqa: F401
+from .distributed import ShardedSpMV, ShardedSpMVFixed  # noqa: F401
 
-__all__ = ["accuracy", "capi", "create_matrices", "distributed", "sharding", "spmv", "SpMV", "SpMVFixed", "ShardedSpMV"]
+__all__ = ["accuracy", "capi", "create_matrices", "distributed", "sharding", "spmv", "SpMV", "SpMVFixed", "ShardedSpMV", "ShardedSpMVFixed"]

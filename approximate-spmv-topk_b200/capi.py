@@ -52,7 +52,7 @@ SYMBOLS = [
     "tks_download_csr", "tks_set_query", "tks_set_query_device", "tks_run", "tks_run_async",
     "tks_read_result", "tks_read_partition_results", "tks_result_keys_device", "tks_merge_keys_device", "tks_merge_keys_batched_device",
     "tks_get_stats", "tks_bscsr_packet_size", "tks_fixed32_from_double", "tks_fixedW_from_fixed32",
-    "tks_pack_bscsr", "tks_read_mtx", "tks_coo2csr",
+    "tks_pack_bscsr", "tks_merge_partition_words", "tks_read_mtx", "tks_coo2csr",
     "tks_cache_write_csr", "tks_cache_read_csr", "tks_cache_write_bscsr", "tks_cache_read_bscsr",
 ]
 
@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
     L.tks_fixedW_from_fixed32.argtypes = [C.c_uint32, C.c_int]
     L.tks_fixedW_from_fixed32.restype = C.c_uint32
     L.tks_pack_bscsr.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_int, C.c_int, vp, vp, vp, vp]
+    L.tks_merge_partition_words.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_int, C.c_uint32, vp, vp, u32p]
     L.tks_read_mtx.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, u32p, u32p, u64p, C.c_uint64, vp, vp, vp]
     L.tks_coo2csr.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp]
     _lib = L
@@ -164,6 +165,22 @@ def pack_bscsr(row, col, val32, num_rows, partitions=32, fixed_width=20):
     check(L.tks_pack_bscsr(_ptr(row), _ptr(col), _ptr(val32), row.size, num_rows, partitions, fixed_width,
                            _ptr(ppp), _ptr(first), _ptr(npp), _ptr(packets)))
     return packets, ppp, first, npp
+
+
+def merge_partition_words(idx_words, val_words, first_row, packet_size, k, tie_break=TIE_HIGHER_INDEX):
+    """tks_merge_partition_words: idx_words/val_words uint32[P, Kp, 16] -> (values uint32[n], indices uint32[n]), n <= k."""
+    iw = np.ascontiguousarray(idx_words, np.uint32)
+    vw = np.ascontiguousarray(val_words, np.uint32)
+    fr = np.ascontiguousarray(first_row, np.uint32)
+    P, Kp = iw.shape[0], iw.shape[1]
+    assert iw.shape == vw.shape == (P, Kp, 16) and fr.size == P
+    idx = np.zeros(k, np.uint32)
+    val = np.zeros(k, np.uint32)
+    cnt = C.c_uint32()
+    check(lib().tks_merge_partition_words(P, Kp, int(packet_size), _ptr(iw), _ptr(vw), _ptr(fr), int(tie_break), k,
+                                          _ptr(idx), _ptr(val), C.byref(cnt)))
+    n = min(k, cnt.value)
+    return val[:n], idx[:n]
 
 
 def read_mtx(path, zero_indexed=False, sort_tuples=False, ignore_values=False):

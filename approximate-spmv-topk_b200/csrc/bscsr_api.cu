@@ -564,37 +564,17 @@ int bscsr_fetch(Handle *h) {
         if (cudaMemcpy(&logged, b->d_counter + 1, 4, cudaMemcpyDeviceToHost) == cudaSuccess) h->stats.logged_candidates = logged;
     }
     b->have_words = true;
-    // read_result (host_spmv_bscsr.cpp:399-448): all P x Kp x B slots, idx += first_row[p], keep val > 0,
-    // first insertion of an index wins, then sort_tuples (evaluation_utils.hpp:40-62)
-    // (<= P x Kp x LFR candidates: a sort instead of the reference's unordered_map; same outcome)
-    struct Cand { uint32_t idx, val, order; };
-    std::vector<Cand> cand;
-    const int Kp = h->cfg.local_k;
-    cand.reserve((size_t)b->P * Kp * 4);
-    for (uint32_t p = 0; p < b->P; p++)
-        for (int t = 0; t < Kp; t++)
-            for (uint32_t q = 0; q < b->B; q++) {
-                const size_t o = ((size_t)p * Kp + t) * 16 + q;
-                const uint32_t v = b->h_res_val[o];
-                if (v == 0) continue;
-                cand.push_back({b->h_res_idx[o] + b->first_row[p], v, (uint32_t)cand.size()});
-            }
-    std::sort(cand.begin(), cand.end(), [](const Cand &l, const Cand &r) {
-        return l.idx != r.idx ? l.idx < r.idx : l.order < r.order;
-    });
-    std::vector<std::pair<uint32_t, uint32_t>> out;   // (idx, val): the first insertion of an index wins
-    out.reserve(cand.size());
-    for (size_t i = 0; i < cand.size(); i++)
-        if (i == 0 || cand[i].idx != cand[i - 1].idx) out.emplace_back(cand[i].idx, cand[i].val);
-    const bool higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
-    std::sort(out.begin(), out.end(), [&](const std::pair<uint32_t, uint32_t> &l, const std::pair<uint32_t, uint32_t> &r) {
-        if (l.second != r.second) return l.second > r.second;
-        return higher ? (l.first > r.first) : (l.first < r.first);
-    });
-    b->merged_idx.resize(out.size());
-    b->merged_val.resize(out.size());
-    for (size_t i = 0; i < out.size(); i++) { b->merged_idx[i] = out[i].first; b->merged_val[i] = out[i].second; }
-    h->stats.last_candidates = (uint32_t)out.size();
+    // read_result (host_spmv_bscsr.cpp:399-448) + sort_tuples: the host-side merge of host_api.cpp
+    const uint32_t cap = b->P * (uint32_t)h->cfg.local_k * b->B;
+    b->merged_idx.assign(cap, 0u);
+    b->merged_val.assign(cap, 0u);
+    uint32_t n_out = 0;
+    if (tks_merge_partition_words(b->P, (uint32_t)h->cfg.local_k, b->B, b->h_res_idx, b->h_res_val, b->first_row.data(),
+                                  h->cfg.tie_break, cap, b->merged_idx.data(), b->merged_val.data(), &n_out) != TKS_OK)
+        return h->fail(TKS_EINVAL, "merge of the partition results failed");
+    b->merged_idx.resize(n_out);
+    b->merged_val.resize(n_out);
+    h->stats.last_candidates = n_out;
     return TKS_OK;
 }
 

@@ -2,8 +2,10 @@
 // around the accelerator (MTX loader, COO->CSR, value quantisation, BS-CSR packet builder), exported
 // through the same C ABI so that non-C++ callers (ctypes tests, bench.py) use the very code the
 // host executable uses.  No CUDA here and no top-k computation: nothing in this file is a fallback.
+#include <algorithm>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/topkspmv.h"
@@ -27,6 +29,46 @@ uint32_t tks_fixed32_from_double(double v) { return ufixed32::from_double(v); }
 
 uint32_t tks_fixedW_from_fixed32(uint32_t raw32, int fixed_width) {
     return tkshost::fixedW_from_fixed32(raw32, fixed_width);
+}
+
+// read_result (host_spmv_bscsr.cpp:399-448): all P x Kp x B slots, idx += first_row[p], keep val > 0, the first
+// insertion of an index wins, then sort_tuples (evaluation_utils.hpp:40-62).  At most P x Kp x LFR candidates:
+// a sort replaces the reference's unordered_map; same outcome.
+int tks_merge_partition_words(uint32_t partitions, uint32_t local_k, uint32_t packet_size, const uint32_t *idx_words,
+                              const uint32_t *val_words, const uint32_t *first_row, int tie_break, uint32_t k,
+                              uint32_t *idx_out, uint32_t *val_out, uint32_t *count) {
+    if (!idx_words || !val_words || !first_row || !count) { g_host_error = "null argument"; return TKS_EINVAL; }
+    if (packet_size == 0 || packet_size > 16) { g_host_error = "packet_size outside 1..16"; return TKS_EINVAL; }
+    struct Cand { uint32_t idx, val, order; };
+    std::vector<Cand> cand;
+    cand.reserve((size_t)partitions * local_k * 4);
+    for (uint32_t p = 0; p < partitions; p++)
+        for (uint32_t t = 0; t < local_k; t++)
+            for (uint32_t q = 0; q < packet_size; q++) {
+                const size_t o = ((size_t)p * local_k + t) * 16 + q;
+                const uint32_t v = val_words[o];
+                if (v == 0) continue;
+                cand.push_back({idx_words[o] + first_row[p], v, (uint32_t)cand.size()});
+            }
+    std::sort(cand.begin(), cand.end(), [](const Cand &l, const Cand &r) {
+        return l.idx != r.idx ? l.idx < r.idx : l.order < r.order;
+    });
+    std::vector<std::pair<uint32_t, uint32_t>> out;   // (idx, val): the first insertion of an index wins
+    out.reserve(cand.size());
+    for (size_t i = 0; i < cand.size(); i++)
+        if (i == 0 || cand[i].idx != cand[i - 1].idx) out.emplace_back(cand[i].idx, cand[i].val);
+    const bool higher = tie_break == TKS_TIE_HIGHER_INDEX;
+    std::sort(out.begin(), out.end(), [&](const std::pair<uint32_t, uint32_t> &l, const std::pair<uint32_t, uint32_t> &r) {
+        if (l.second != r.second) return l.second > r.second;
+        return higher ? (l.first > r.first) : (l.first < r.first);
+    });
+    *count = (uint32_t)out.size();   // all distinct candidates; the caller's buffers receive the first min(k, count)
+    if (idx_out && val_out)
+        for (uint32_t i = 0; i < k; i++) {
+            idx_out[i] = i < out.size() ? out[i].first : 0u;
+            val_out[i] = i < out.size() ? out[i].second : 0u;
+        }
+    return TKS_OK;
 }
 
 int tks_pack_bscsr(const uint32_t *row, const uint32_t *col, const uint32_t *val32, uint64_t nnz, uint32_t num_rows,

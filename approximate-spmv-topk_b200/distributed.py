@@ -73,6 +73,90 @@ class ShardedSpMV:
             eng.merge_keys_batched_device(regrouped.data_ptr(), self.world * k, B, k, stream)
 
 
+def plan_partition_shards(num_rows, partitions, world):
+    """FPGA mode: the P row partitions of host_spmv_bscsr.cpp:136-141 (rows_per_part = ceil(N / P)) are dealt
+    out contiguously, P / world per rank.  Returns (rows_per_part, parts_per_rank, [(row_begin, row_end)] per rank);
+    every shard is handed to its engine with P / world partitions and parts_per_rank * rows_per_part (virtual) rows, so
+    the partition boundaries are the ones of the unsharded matrix."""
+    if partitions % world != 0:
+        raise ValueError(f"partitions={partitions} must be a multiple of the number of ranks ({world})")
+    rpp = (int(num_rows) + partitions - 1) // partitions
+    ppr = partitions // world
+    return rpp, ppr, [(min(r * ppr * rpp, int(num_rows)), min((r + 1) * ppr * rpp, int(num_rows))) for r in range(world)]
+
+
+class ShardedSpMVFixed:
+    """FPGA-semantics engine over several GPUs, one process per GPU: rank r owns partitions [r*P/N, (r+1)*P/N) of the
+    reference's 32 (the rows [r0, r1) of plan_partition_shards), runs the unchanged kernels on them, and the ONLY
+    exchange per query is an all-gather of the result words (P/N x local_k x 128 bytes per rank: 32 KB in total for the
+    reference's knobs) followed by the reference's host merge (host_spmv_bscsr.cpp:399-448) over all P partitions on
+    every rank -- bit-identical to one device holding all partitions.
+
+    x, y, val32: the WHOLE row-sorted COO (every rank slices its own part); engine_factory builds the local
+    `spmv.SpMVFixed` (tests inject a stand-in under gloo)."""
+
+    def __init__(self, x, y, val32, num_rows, num_cols, k=100, fixed_width=20, partitions=32, local_k=8,
+                 limited_finished_rows=4, drift_free=False, device=0, device_pack=True, group=None, engine_factory=None):
+        import torch
+        import torch.distributed as dist
+        from . import capi, spmv
+        self.torch, self.dist, self.capi, self.group = torch, dist, capi, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.k, self.P, self.Kp = int(k), int(partitions), int(local_k)
+        self.B = capi.bscsr_packet_size(fixed_width)
+        self.rpp, self.ppr, shards = plan_partition_shards(num_rows, partitions, self.world)
+        self.r0, self.r1 = shards[self.rank]
+        x = np.asarray(x)
+        b, e = np.searchsorted(x, self.r0, side="left"), np.searchsorted(x, self.r1, side="left")
+        lx = (x[b:e] - self.r0).astype(np.uint32)
+        factory = engine_factory or (lambda *a, **kw: spmv.SpMVFixed(*a, **kw))
+        self.engine = factory(lx, np.asarray(y)[b:e], np.asarray(val32)[b:e], self.ppr * self.rpp, num_cols, k=k,
+                              fixed_width=fixed_width, partitions=self.ppr, local_k=local_k,
+                              limited_finished_rows=limited_finished_rows, drift_free=drift_free, device=device,
+                              device_pack=device_pack)
+        self.nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        # global first row of every partition: local first_row (host:145) + the shard's row offset, gathered once
+        mine = (np.asarray(self.engine.first_row_array(), np.int64) + self.r0).astype(np.int32)
+        self.first_row = self._all_gather(mine.view(np.uint32)).reshape(self.P)
+
+    def _all_gather(self, words):
+        """uint32 array of equal size on every rank -> concatenation over ranks (rank order)."""
+        t = self.torch.from_numpy(np.ascontiguousarray(words).view(np.int32).reshape(-1).copy())
+        if self.world == 1:
+            return t.numpy().view(np.uint32)
+        if self.nccl:
+            t = t.cuda()
+        out = self.torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t, group=self.group)
+        return out.cpu().numpy().view(np.uint32)
+
+    def reset(self, vec32):
+        return self.engine.reset(vec32)
+
+    def __call__(self, debug=0):
+        """operator(): run the local partitions, exchange the result words, merge.  Returns the local kernel ns."""
+        ns = self.engine()
+        iw, vw = self.engine.read_partition_results()
+        allw = self._all_gather(np.concatenate([iw.reshape(-1), vw.reshape(-1)]))
+        per = self.ppr * self.Kp * 16
+        allw = allw.reshape(self.world, 2, per)
+        self.idx_words = allw[:, 0, :].reshape(self.P, self.Kp, 16)
+        self.val_words = allw[:, 1, :].reshape(self.P, self.Kp, 16)
+        self._val, self._idx = self.capi.merge_partition_words(self.idx_words, self.val_words, self.first_row, self.B, self.k)
+        return ns
+
+    def read_result(self):
+        """(raw values uint32[n], GLOBAL row indices uint32[n]), n <= k; identical on every rank."""
+        return self._val, self._idx
+
+    def read_partition_results(self):
+        return self.idx_words, self.val_words
+
+    def close(self):
+        self.engine.close()
+
+
 def merge_gathered_host(gathered, k):
     """Host stand-in of the merge kernel for the gloo tests: gathered [batch, world*k] uint64 keys."""
     g = np.asarray(gathered).view(np.uint64)

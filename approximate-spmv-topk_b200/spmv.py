@@ -182,6 +182,14 @@ class SpMVFixed(_Base):
         check(capi.lib().tks_upload_coo_fixed(self.handle, _ptr(x), _ptr(y), _ptr(val32), x.size, int(num_rows),
                                               int(num_cols)), self.handle)
         self.partitions = int(self.cfg.partitions)
+        # first row of every partition = row of the first non-zero of its row range (host:136-145)
+        rpp = (int(num_rows) + self.partitions - 1) // self.partitions
+        starts = np.searchsorted(x, np.arange(self.partitions, dtype=np.int64) * rpp, side="left")
+        self.first_row = x[starts].astype(np.uint32)
+
+    def first_row_array(self):
+        """First row of every partition (host_spmv_bscsr.cpp:145), local to this engine's matrix."""
+        return np.asarray(self.first_row, np.uint32)
 
     def state_digest(self):
         d = np.zeros(16, np.uint64)

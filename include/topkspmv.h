@@ -202,6 +202,15 @@ int tks_pack_bscsr(const uint32_t *row, const uint32_t *col, const uint32_t *val
                    uint32_t num_rows, int partitions, int fixed_width, uint64_t *packets_per_part,
                    uint32_t *first_row, uint64_t *nnz_per_part, void *packets);
 
+/* read_result's merge (host_spmv_bscsr.cpp:399-448 + sort_tuples, evaluation_utils.hpp:40-62) over caller-held result
+ * words in the kernel's layout (partitions x local_k words of 16 x u32, as tks_read_partition_results returns them):
+ * idx += first_row[p], val > 0 kept, first insertion of an index wins, sorted (val desc, tie_break).  Lets a caller
+ * merge the partitions of SEVERAL devices (FPGA mode, partitions spread over GPUs) exactly like one.
+ * *count = number of distinct candidates; idx_out/val_out (k entries, may be NULL) get the first min(k, count).  */
+int tks_merge_partition_words(uint32_t partitions, uint32_t local_k, uint32_t packet_size, const uint32_t *idx_words,
+                              const uint32_t *val_words, const uint32_t *first_row, int tie_break, uint32_t k,
+                              uint32_t *idx_out, uint32_t *val_out, uint32_t *count);
+
 /* readMtx (utils.hpp:474-520 + mmio.hpp): coordinate real/integer/pattern general.
  * zero_indexed: the file's indices are 0-based (the reference hosts hard-code
  * true, host_spmv_bscsr.cpp:539; the MTX standard and its generator are 1-based).

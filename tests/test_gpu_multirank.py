@@ -83,3 +83,58 @@ def test_sharded_ranks_agree_with_global_topk(cuda_required, tks, orc, gen, batc
             if batch > 1:      # the batched kernel's sums are sequential fp32: exact, in the exact order
                 assert np.array_equal(idx, order.astype(np.uint32))
                 assert np.array_equal(val.view(np.uint32), yref[order].view(np.uint32))
+
+
+def _worker_fixed(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle
+    from _pkg import pkg
+    from conftest import make_query
+    tks = pkg()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    rows, cols = 30001, 1024
+    x, y, v = tks.create_matrices.create_sparse_matrix(rows, cols, 20, "gamma", seed=6)
+    s = tks.ShardedSpMVFixed(x, y, oracle.fx32_from_double(v), rows, cols, k=100, device=rank)
+    out = []
+    for qs in (1, 2):
+        s.reset(oracle.query_fx32_from_f32(make_query(cols, qs)))
+        s()
+        val, idx = s.read_result()
+        out.append((val.copy(), idx.copy(), s.idx_words.copy(), s.val_words.copy()))
+    q.put((rank, out))
+    dist.barrier()
+    s.close()
+    dist.destroy_process_group()
+
+
+def test_fixed_mode_partitions_over_ranks_equal_oracle(cuda_required, tks, orc, gen):
+    """FPGA mode over NCCL: 32 partitions dealt out over the ranks (16 + 16 on 2 GPUs), result words all-gathered,
+    the reference's merge on every rank: bit-exact against the oracle of the UNSHARDED matrix."""
+    import torch
+    import torch.multiprocessing as mp
+    from conftest import make_query
+    world = 2 if torch.cuda.device_count() >= 2 else 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_fixed, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rows, cols = 30001, 1024
+    x, y, v = gen.create_sparse_matrix(rows, cols, 20, "gamma", seed=6)
+    for i, qs in enumerate((1, 2)):
+        o = orc.bscsr_topk(x, y, v, rows, make_query(cols, qs))
+        for rank in range(world):
+            val, idx, iw, vw = results[rank][i]
+            assert np.array_equal(iw, o["idx_words"]) and np.array_equal(vw, o["val_words"])
+            assert np.array_equal(idx, o["idx"][:100]) and np.array_equal(val, o["val"][:100])

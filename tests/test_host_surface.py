@@ -147,3 +147,27 @@ def test_sharding_plans(tks):
         top = sh.merge_topk_host([keys[:2], keys[2:]], 3)
         s3, r3 = sh.split_keys(top, th)
         assert s3.tolist() == [0.5, 0.5, 0.25] and r3.tolist() == ([7, 2, 3] if th else [2, 7, 3])
+
+
+def test_merge_partition_words_equals_reference_read_result(tks, orc, gen):
+    """tks_merge_partition_words = read_result + sort_tuples (host_spmv_bscsr.cpp:399-448) over the kernel's result
+    words; the oracle's read_result is pinned against the compiled reference (tests/test_oracle_fixed.py)."""
+    x, y, v = gen.create_sparse_matrix(10000, 1024, 20, "gamma", seed=0)
+    rng = np.random.default_rng(7)
+    vec = rng.random(1024); vec = (vec / np.linalg.norm(vec)).astype(np.float32)
+    for W, P, Kp, LFR in [(20, 32, 8, 4), (32, 8, 4, 2), (26, 32, 8, 4)]:
+        o = orc.bscsr_topk(x, y, v, 10000, vec, P=P, W=W, Kp=Kp, LFR=LFR)
+        val, idx = tks.capi.merge_partition_words(o["idx_words"], o["val_words"], o["packed"]["first_row"],
+                                                  tks.capi.bscsr_packet_size(W), 4096)
+        assert np.array_equal(idx, o["idx"]) and np.array_equal(val, o["val"])
+        val, idx = tks.capi.merge_partition_words(o["idx_words"], o["val_words"], o["packed"]["first_row"],
+                                                  tks.capi.bscsr_packet_size(W), 10)
+        assert np.array_equal(idx, o["idx"][:10]) and np.array_equal(val, o["val"][:10])
+    # duplicates of an index across slots: the first insertion wins; zero values are dropped
+    iw = np.zeros((2, 2, 16), np.uint32); vw = np.zeros((2, 2, 16), np.uint32)
+    iw[0, 0, 0], vw[0, 0, 0] = 5, 100
+    iw[0, 1, 1], vw[0, 1, 1] = 5, 900          # same row again, later slot: ignored
+    iw[1, 0, 0], vw[1, 0, 0] = 1, 100          # row 1 + first_row 10 = 11: ties with row 5 -> higher index first
+    iw[1, 1, 3], vw[1, 1, 3] = 2, 0            # val == 0: not a candidate
+    val, idx = tks.capi.merge_partition_words(iw, vw, np.array([0, 10], np.uint32), 15, 8)
+    assert idx.tolist() == [11, 5] and val.tolist() == [100, 100]

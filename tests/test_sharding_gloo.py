@@ -133,3 +133,87 @@ def test_two_rank_batched_exchange_regroups_by_query(batch):
         order = np.lexsort((np.arange(4000), -scores[b].astype(np.float64)))[:k]
         ms, mr = sh.split_keys(merged[b])
         assert np.array_equal(mr, order.astype(np.uint32)) and np.array_equal(ms, scores[b][order])
+
+
+# ---- FPGA mode: the P row partitions dealt out over the ranks, result words all-gathered, the reference's merge ----
+
+class _OracleFixedEngine:
+    """Stand-in for spmv.SpMVFixed under gloo (no GPU here): the oracle's literal kernel on the local partitions.
+    Test infrastructure only -- it exercises ShardedSpMVFixed's shard planning, exchange and merge."""
+
+    def __init__(self, x, y, val32, num_rows, num_cols, k=100, fixed_width=20, partitions=32, local_k=8,
+                 limited_finished_rows=4, drift_free=False, device=0, device_pack=True):
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import oracle
+        self.o, self.Kp, self.LFR, self.df = oracle, local_k, limited_finished_rows, drift_free
+        self.packed = oracle.pack_bscsr(x, y, val32, num_rows, partitions, fixed_width)
+
+    def first_row_array(self):
+        return self.packed["first_row"]
+
+    def reset(self, vec32):
+        self.vec32 = np.asarray(vec32, np.uint32)
+
+    def __call__(self):
+        self.words = self.o.bscsr_kernel(self.packed, self.vec32, self.Kp, self.LFR, self.df)
+        return 0
+
+    def read_partition_results(self):
+        return self.words
+
+    def close(self):
+        pass
+
+
+def _worker_fixed(rank, world, port, rows, P, q):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from _pkg import pkg
+    tks = pkg()
+    x, y, v = tks.create_matrices.create_sparse_matrix(rows, 1024, 12, "gamma", seed=4)
+    val32 = oracle.fx32_from_double(v)
+    rng = np.random.default_rng(2)
+    vec = rng.random(1024); vec = (vec / np.linalg.norm(vec)).astype(np.float32)
+    s = tks.ShardedSpMVFixed(x, y, val32, rows, 1024, k=100, partitions=P, engine_factory=_OracleFixedEngine)
+    s.reset(oracle.query_fx32_from_f32(vec))
+    s()
+    val, idx = s.read_result()
+    q.put((rank, val.copy(), idx.copy(), s.first_row.copy(), (s.r0, s.r1)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("rows,P", [(8000, 32), (7777, 8)])
+def test_two_rank_fixed_mode_partitions_equal_one_device(rows, P):
+    """Partitions dealt out over 2 ranks (incl. a row count that does not divide: the last shard is padded with virtual
+    rows so that rows_per_part stays the unsharded one) == all partitions on one device, bit for bit."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_fixed, args=(r, world, port, rows, P, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r, val, idx, first_row, shard = q.get(timeout=180)
+        got[r] = (val, idx, first_row, shard)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle
+    from _pkg import pkg
+    x, y, v = pkg().create_matrices.create_sparse_matrix(rows, 1024, 12, "gamma", seed=4)
+    rng = np.random.default_rng(2)
+    vec = rng.random(1024); vec = (vec / np.linalg.norm(vec)).astype(np.float32)
+    o = oracle.bscsr_topk(x, y, v, rows, vec, P=P)
+    for r in range(world):
+        val, idx, first_row, shard = got[r]
+        assert np.array_equal(first_row, o["packed"]["first_row"])
+        assert np.array_equal(idx, o["idx"][:100]) and np.array_equal(val, o["val"][:100])
+    assert got[0][3][1] == got[1][3][0]
