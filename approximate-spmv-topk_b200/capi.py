@@ -18,6 +18,7 @@ TKS_OK, TKS_EINVAL, TKS_ECUDA, TKS_ESTATE, TKS_ENOMEM, TKS_EIO = 0, -1, -2, -3, 
 MODE_FLOAT_CSR, MODE_FIXED_BSCSR = 0, 1
 TIE_LOWER_INDEX, TIE_HIGHER_INDEX = 0, 1
 VALUE_FP32, VALUE_FP16 = 0, 1
+IPC_HANDLE_BYTES = 128
 
 
 class TksConfig(C.Structure):
@@ -51,6 +52,7 @@ SYMBOLS = [
     "tks_upload_coo_fixed", "tks_upload_coo_fixed_device", "tks_bscsr_state_digest",
     "tks_download_csr", "tks_set_query", "tks_set_query_device", "tks_run", "tks_run_async",
     "tks_read_result", "tks_read_partition_results", "tks_result_keys_device", "tks_merge_keys_device", "tks_merge_keys_batched_device",
+    "tks_peer_init", "tks_peer_connect", "tks_run_exchange_async", "tks_peer_exchange_async",
     "tks_get_stats", "tks_bscsr_packet_size", "tks_fixed32_from_double", "tks_fixedW_from_fixed32",
     "tks_pack_bscsr", "tks_merge_partition_words", "tks_read_mtx", "tks_coo2csr",
     "tks_cache_write_csr", "tks_cache_read_csr", "tks_cache_write_bscsr", "tks_cache_read_bscsr",
@@ -95,6 +97,10 @@ def lib() -> C.CDLL:
     L.tks_result_keys_device.argtypes = [vp, C.c_uint32, C.POINTER(vp), u32p]
     L.tks_merge_keys_device.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, vp]
     L.tks_merge_keys_batched_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+    L.tks_peer_init.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
+    L.tks_peer_connect.argtypes = [vp, vp]
+    L.tks_run_exchange_async.argtypes = [vp, C.c_uint32, vp]
+    L.tks_peer_exchange_async.argtypes = [vp, C.c_uint32, vp]
     L.tks_get_stats.argtypes = [vp, C.POINTER(TksStats)]
     L.tks_bscsr_packet_size.argtypes = [C.c_int]
     L.tks_fixed32_from_double.argtypes = [C.c_double]

@@ -1,5 +1,6 @@
 // api.cu -- C ABI of libtopkspmv.so (see include/topkspmv.h), float CSR path and dispatch.
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "csr_build.cuh"
@@ -50,15 +51,36 @@ cudaError_t prep_main(Handle *h, int variant) {
     return half_mode(h) ? prep_main_t<CAP, true>(h, variant) : prep_main_t<CAP, false>(h, variant);
 }
 
+// Launch with the programmatic-stream-serialization attribute: the grid may start before the previous kernel of the
+// stream has finished (csr_topk.cuh: pdl_trigger / pdl_wait).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+bool pdl_enabled() {
+    static const bool on = !(std::getenv("TKS_PDL") && std::atoi(std::getenv("TKS_PDL")) == 0);
+    return on;
+}
+
 template <int CAP>
 void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, RunState *st, uint32_t k,
-                 cudaStream_t s) {
+                 cudaStream_t s, bool pdl) {
     size_t smem = main_smem_bytes(m.cols, variant);
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
     if (half_mode(h))
-        csr_topk_main_kernel<CAP, true><<<h->main_grid[variant], kCapThreads[variant], smem, s>>>(m, x, st, h->d_pool, k, tie_higher);
+        launch_pdl(csr_topk_main_kernel<CAP, true>, dim3(h->main_grid[variant]), dim3(kCapThreads[variant]), smem, s, pdl,
+                   m, x, st, h->d_pool, k, tie_higher);
     else
-        csr_topk_main_kernel<CAP, false><<<h->main_grid[variant], kCapThreads[variant], smem, s>>>(m, x, st, h->d_pool, k, tie_higher);
+        launch_pdl(csr_topk_main_kernel<CAP, false>, dim3(h->main_grid[variant]), dim3(kCapThreads[variant]), smem, s, pdl,
+                   m, x, st, h->d_pool, k, tie_higher);
 }
 
 CsrDevice csr_device(const Handle *h) {
@@ -241,17 +263,21 @@ void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool
         csr_sample_kernel<true><<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, sample_iters, k);
     else
         csr_sample_kernel<false><<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, sample_iters, k);
+    // the three kernels of a query overlap their launch and set-up with the previous one's tail (programmatic
+    // dependent launch); not while the dominant kernel is being timed alone
+    const bool pdl = pdl_enabled() && !profile;
     if (profile) cudaEventRecord(h->evm0, s);
     switch (variant) {
-        case 0: launch_main<256>(h, 0, m, x, st, k, s); break;
-        case 1: launch_main<512>(h, 1, m, x, st, k, s); break;
-        case 2: launch_main<1024>(h, 2, m, x, st, k, s); break;
-        default: launch_main<2048>(h, 3, m, x, st, k, s); break;
+        case 0: launch_main<256>(h, 0, m, x, st, k, s, pdl); break;
+        case 1: launch_main<512>(h, 1, m, x, st, k, s, pdl); break;
+        case 2: launch_main<1024>(h, 2, m, x, st, k, s, pdl); break;
+        default: launch_main<2048>(h, 3, m, x, st, k, s, pdl); break;
     }
     if (profile) cudaEventRecord(h->evm1, s);
-    select_topk_kernel<<<1, kSelectThreads, kSelectDynSmem, s>>>(
-        h->d_pool, 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
-        h->d_res_idx + (size_t)q * h->kmax, h->d_res_val + (size_t)q * h->kmax, 0u, h->d_res_count + q, nullptr);
+    launch_pdl(select_topk_kernel, dim3(1), dim3(kSelectThreads), (size_t)kSelectDynSmem, s, pdl,
+               (const uint64_t *)h->d_pool, 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
+               h->d_res_idx + (size_t)q * h->kmax, h->d_res_val + (size_t)q * h->kmax, 0u, h->d_res_count + q,
+               (uint32_t *)nullptr);
 }
 
 template <bool SAMPLE>
@@ -486,6 +512,9 @@ void tks_destroy(tks_handle *h) {
     cudaSetDevice(h->device);
     free_matrix(h);
     bscsr_destroy(h);
+    for (uint32_t r = 0; r < h->peer_world; r++)
+        if (r != h->peer_rank && h->peer_mapped[r]) cudaIpcCloseMemHandle(h->peer_mapped[r]);
+    cudaFree(h->d_peer_window);
     cudaFree(h->d_x); cudaFree(h->d_state); cudaFree(h->d_pool); cudaFree(h->d_sample_keys);
     cudaFree(h->d_res_keys); cudaFree(h->d_res_block);
     cudaFree(h->d_xT); cudaFree(h->d_bpool); cudaFree(h->d_pass_counter); cudaFree(h->d_bsample_keys);
@@ -712,6 +741,8 @@ int tks_read_result(tks_handle *h, uint32_t query, uint32_t *idx_out, void *val_
         h->have_result = true;
     }
     if (query >= h->batch) return h->fail(TKS_EINVAL, "query index out of range");
+    if (h->h_res_count[query] == kPeerTimeout)
+        return h->fail(TKS_ECUDA, "peer exchange timed out: a rank of the box never delivered its candidates");
     const uint32_t k = h->last_k;
     std::memcpy(idx_out, h->h_res_idx + (size_t)query * h->kmax, k * 4);
     std::memcpy(val_out, h->h_res_val + (size_t)query * h->kmax, k * 4);
@@ -782,6 +813,68 @@ int tks_merge_keys_batched_device(tks_handle *h, const uint64_t *d_keys, uint32_
     if (h->batch < batch) h->batch = batch;
     h->have_result = false;
     h->overflow_check_pending = false;
+    return TKS_OK;
+}
+
+// ---- peer-memory candidate exchange ------------------------------------------------------------------------------
+
+int tks_peer_init(tks_handle *h, uint32_t world, uint32_t rank, void *ipc_handle_out) {
+    if (!h || !ipc_handle_out) return TKS_EINVAL;
+    if (h->cfg.mode != TKS_MODE_FLOAT_CSR) return h->fail(TKS_ESTATE, "float mode only");
+    if (world < 1 || world > kPeerMaxWorld || rank >= world) return h->fail(TKS_EINVAL, "world outside 1..8 or rank >= world");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= TKS_IPC_HANDLE_BYTES, "IPC handle does not fit");
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    if (!h->d_peer_window) {
+        const size_t bytes = peer_window_bytes(h->kmax);
+        TKS_CUDA(h, cudaMalloc(&h->d_peer_window, bytes));
+        TKS_CUDA(h, cudaMemset(h->d_peer_window, 0, bytes));
+    }
+    cudaIpcMemHandle_t ih;
+    TKS_CUDA(h, cudaIpcGetMemHandle(&ih, h->d_peer_window));
+    std::memset(ipc_handle_out, 0, TKS_IPC_HANDLE_BYTES);
+    std::memcpy(ipc_handle_out, &ih, sizeof ih);
+    h->peer_world = world; h->peer_rank = rank; h->peer_seq = 0; h->peer_ready = false;
+    return TKS_OK;
+}
+
+int tks_peer_connect(tks_handle *h, const void *all_handles) {
+    if (!h || !all_handles) return TKS_EINVAL;
+    if (!h->d_peer_window || h->peer_world == 0) return h->fail(TKS_ESTATE, "tks_peer_init first");
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    for (uint32_t r = 0; r < h->peer_world; r++) {
+        if (r == h->peer_rank) { h->peer_mapped[r] = h->d_peer_window; continue; }
+        cudaIpcMemHandle_t ih;
+        std::memcpy(&ih, static_cast<const uint8_t *>(all_handles) + (size_t)r * TKS_IPC_HANDLE_BYTES, sizeof ih);
+        TKS_CUDA(h, cudaIpcOpenMemHandle(&h->peer_mapped[r], ih, cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->peer_ready = true;
+    return TKS_OK;
+}
+
+int tks_run_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream) {
+    if (!h) return TKS_EINVAL;
+    if (!h->peer_ready) return h->fail(TKS_ESTATE, "tks_peer_connect first");
+    if (h->batch != 1) return h->fail(TKS_EINVAL, "the peer exchange serves one query per run (batched runs use the all-gather path)");
+    if ((uint64_t)h->peer_world * k > kSelectSortCap) return h->fail(TKS_EINVAL, "world * k exceeds %u", kSelectSortCap);
+    int rc = tks_run_async(h, k, cuda_stream);
+    if (rc) return rc;
+    return tks_peer_exchange_async(h, k, cuda_stream);
+}
+
+int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream) {
+    if (!h) return TKS_EINVAL;
+    if (!h->peer_ready) return h->fail(TKS_ESTATE, "tks_peer_connect first");
+    if (k != h->last_k || h->batch != 1) return h->fail(TKS_ESTATE, "no single-query run with this k precedes the exchange");
+    if ((uint64_t)h->peer_world * k > kSelectSortCap) return h->fail(TKS_EINVAL, "world * k exceeds %u", kSelectSortCap);
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    PeerExchange px{};
+    for (uint32_t r = 0; r < h->peer_world; r++) px.window[r] = static_cast<uint64_t *>(h->peer_mapped[r]);
+    px.world = h->peer_world; px.rank = h->peer_rank; px.kmax = h->kmax;
+    h->peer_seq += 1;
+    TKS_CUDA(h, launch_pdl(peer_exchange_merge_kernel, dim3(1), dim3(kSelectThreads), (size_t)0, s, pdl_enabled(), px,
+                           h->peer_seq, k, (int)(h->cfg.tie_break == TKS_TIE_HIGHER_INDEX), h->d_res_keys, h->d_res_idx,
+                           h->d_res_val, h->d_res_count));
     return TKS_OK;
 }
 

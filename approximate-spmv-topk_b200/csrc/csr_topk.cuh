@@ -91,6 +91,13 @@ __device__ __forceinline__ uint32_t ldg_stream_u8(const void *p) {
     return r;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmaticStreamSerialization attribute may
+// start while its predecessor in the stream is still running; it must not touch anything the predecessor writes
+// before pdl_wait() (which returns once the predecessor grid has completed and its writes are visible).
+// pdl_trigger() in the predecessor allows that early start.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
 __device__ __forceinline__ float tau_from_key(uint32_t key) { return key == 0 ? neg_inf() : ordered_to_f32(key); }
 
@@ -487,6 +494,7 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
                                                                      uint32_t n_sample, uint32_t stride,
                                                                      uint32_t sample_iters, uint32_t k) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    pdl_trigger();   // the main kernel's CTAs may take the SMs this grid leaves and stage the query meanwhile
     float *xs = reinterpret_cast<float *>(smem_raw);
     for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<HALF>(x[i]) : 0.0f;
     __syncthreads();
@@ -529,8 +537,10 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float *xs = reinterpret_cast<float *>(smem_raw);
     uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (((m.cols + 1u) * 4u + 15u) & ~15u));
+    pdl_trigger();   // the select kernel's CTA may be set up while this grid drains
     for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<HALF>(x[i]) : 0.0f;
     __syncthreads();
+    pdl_wait();      // the query was complete before the sample kernel started; tau and the counters are not
 
     const unsigned lane = lane_id();
     PoolSink<CAP> sink;
@@ -604,6 +614,7 @@ select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunS
     out_idx += (size_t)q * out_stride;
     out_val += (size_t)q * out_stride;
     out_count += q;
+    pdl_wait();      // the pool and its count belong to the kernel before this one
     const uint32_t n = st_reset ? st_reset->pool_count : pool_count_imm;
     if (pool_cap != 0 && n > pool_cap) {
         __syncthreads();   // everyone has read pool_count
@@ -697,6 +708,124 @@ select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunS
         }
         if (pass_counter && (q % 32u) == 0) pass_counter[q / 32u] = 0;
     }
+}
+
+// --------------------------------------------------------------------------
+// Kernel 4 (several GPUs): candidate exchange over peer memory + merge, ONE launch.
+// Every rank owns a window in HBM that all ranks of the box have mapped (CUDA IPC over NVLink/NVSwitch):
+//   rec[2][world][kmax][2] u64    rec[s][r][i] = the i-th key of rank r for a step of parity s, as two words
+//                                 (sequence number << 32 | upper half) and (sequence number << 32 | lower half)
+// The CTA stores this rank's k keys straight into every peer's window -- 16 bytes per key and peer -- and every
+// word carries the step's sequence number, so data and "it has arrived" travel in the same 8-byte store: no
+// fence, no separate flag, one NVLink traversal (the low-latency protocol of collective libraries).  Each
+// thread then polls one record of its OWN window until both words show this step's sequence number, and the
+// world x k keys are merged with a rank sort.  No NCCL launch, no second merge launch, nothing through the host.
+// Two parity slots make reuse safe without relying on timing: a rank cannot finish step s+1 before every peer
+// has sent its step s+1 list, which a peer only does after it has consumed step s.
+// The wait is bounded (~2 s of %globaltimer): a missing peer yields *res_count = kPeerTimeout, not a hung GPU.
+// --------------------------------------------------------------------------
+constexpr uint32_t kPeerMaxWorld = 8;
+constexpr uint32_t kPeerTimeout = 0xFFFFFFFEu;
+
+struct PeerExchange {
+    uint64_t *window[kPeerMaxWorld];   // window[r]: rank r's window as mapped in THIS process (window[rank] = local)
+    uint32_t world, rank, kmax;
+};
+
+__host__ __device__ constexpr size_t peer_window_bytes(uint32_t kmax) { return 2ull * kPeerMaxWorld * kmax * 2ull * sizeof(uint64_t); }
+
+__device__ __forceinline__ void st_volatile_v2_u64(uint64_t *p, uint64_t a, uint64_t b) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_volatile_v2_u64(const uint64_t *p, uint64_t &a, uint64_t &b) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(kSelectThreads)
+peer_exchange_merge_kernel(PeerExchange px, uint32_t seq, uint32_t k, int tie_higher, uint64_t *res_keys,
+                           uint32_t *res_idx, float *res_val, uint32_t *res_count) {
+    __shared__ uint64_t keys[kSelectSortCap];
+    __shared__ uint32_t s_timeout, s_present;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t parity = seq & 1u;
+    const uint64_t tag = (uint64_t)seq << 32;
+    if (tid == 0) { s_timeout = 0; s_present = 0; }
+    pdl_wait();   // this rank's list comes from the select kernel right before
+    const uint32_t mine_n = *res_count;
+    if (tid < k) {
+        const uint64_t key = (tid < mine_n) ? res_keys[tid] : 0ull;
+        const size_t slot = (((size_t)parity * px.world + px.rank) * px.kmax + tid) * 2u;
+        for (uint32_t d = 0; d < px.world; d++) {
+            const uint32_t p = (px.rank + 1u + d) % px.world;   // peers first, the local copy last
+            st_volatile_v2_u64(px.window[p] + slot, tag | (key >> 32), tag | (key & 0xFFFFFFFFull));
+        }
+    }
+    __syncthreads();   // s_timeout / s_present are initialised; every read of res_keys is done
+    const uint32_t n = px.world * k;   // <= kSelectSortCap (checked by the host)
+    uint32_t present = 0;
+    for (uint32_t t = tid; t < n; t += blockDim.x) {
+        const uint32_t r = t / k, i = t - r * k;
+        const uint64_t *src = px.window[px.rank] + (((size_t)parity * px.world + r) * px.kmax + i) * 2u;
+        uint64_t a, b;
+        uint64_t t0 = 0;
+        uint32_t spins = 0;
+        for (;;) {
+            ld_volatile_v2_u64(src, a, b);
+            if ((a >> 32) == seq && (b >> 32) == seq) break;
+            if ((++spins & 63u) == 0) {
+                const uint64_t now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > 2000000000ull || *reinterpret_cast<volatile uint32_t *>(&s_timeout)) { s_timeout = 1; break; }
+            }
+        }
+        const uint64_t key = (a << 32) | (b & 0xFFFFFFFFull);
+        keys[t] = key;
+        present += key != 0ull;
+    }
+    present = __reduce_add_sync(kFull, present);
+    if (lane_id() == 0 && present) atomicAdd(&s_present, present);
+    __syncthreads();
+    if (s_timeout) {
+        if (tid == 0) *res_count = kPeerTimeout;
+        return;
+    }
+    const uint32_t cnt = s_present < k ? s_present : k;
+    if (n <= kSelectRankSortMax) {
+        const uint32_t items = (4u * n + kWarp - 1u) & ~(kWarp - 1u);
+        for (uint32_t w = tid; w < items; w += blockDim.x) {
+            const uint32_t i = w >> 2, part = w & 3u;
+            const uint64_t mine = (i < n) ? keys[i] : 0ull;
+            uint32_t r = 0;
+            for (uint32_t j = part; j < n; j += 4u) {
+                const uint64_t other = keys[j];
+                r += (other > mine) || (other == mine && j < i);
+            }
+            r += __shfl_xor_sync(kFull, r, 1);
+            r += __shfl_xor_sync(kFull, r, 2);
+            if (part == 0 && i < n && r < cnt) {
+                res_keys[r] = mine;
+                res_idx[r] = key_row(mine, tie_higher);
+                res_val[r] = ordered_to_f32(key_score(mine));
+            }
+        }
+    } else {
+        uint32_t n2 = 32;
+        while (n2 < n) n2 <<= 1;
+        for (uint32_t i = n + tid; i < n2; i += blockDim.x) keys[i] = 0ull;
+        bitonic_sort_desc(keys, n2, tid, blockDim.x, [] { __syncthreads(); });
+        for (uint32_t i = tid; i < cnt; i += blockDim.x) {
+            res_keys[i] = keys[i];
+            res_idx[i] = key_row(keys[i], tie_higher);
+            res_val[i] = ordered_to_f32(key_score(keys[i]));
+        }
+    }
+    for (uint32_t i = cnt + tid; i < k; i += blockDim.x) { res_keys[i] = 0ull; res_idx[i] = 0u; res_val[i] = 0.0f; }
+    if (tid == 0) *res_count = cnt;
 }
 
 }  // namespace tks

@@ -72,6 +72,12 @@ struct Handle {
     bool last_run_batched = false;
     bool overflow_check_pending = false; // an async batched run has not been checked for pool overflow yet
 
+    // peer-memory candidate exchange (several GPUs of one box; csr_topk.cuh peer_exchange_merge_kernel)
+    uint64_t *d_peer_window = nullptr;  // this rank's window of tagged key records, exported through CUDA IPC
+    void *peer_mapped[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // peers' windows
+    uint32_t peer_world = 0, peer_rank = 0, peer_seq = 0;
+    bool peer_ready = false;
+
     // launch geometry of the main kernel, per CAP variant
     int main_grid[4] = {0, 0, 0, 0};
 

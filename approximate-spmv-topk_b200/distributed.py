@@ -32,7 +32,10 @@ class ShardedSpMV:
     step(k, stream): run on the shard, all-gather the candidates, merge; afterwards `engine.read_result(q)`
     returns the GLOBAL top-k on every rank."""
 
-    def __init__(self, engine, k, batch=1, group=None):
+    def __init__(self, engine, k, batch=1, group=None, exchange="auto"):
+        """exchange: "peer" = one kernel stores the candidates into every rank's CUDA-IPC-mapped window over NVLink and
+        merges (tks_run_exchange_async: no NCCL launch, no separate merge launch); "nccl" = all-gather + merge kernel;
+        "auto" = peer when it can be set up (NCCL backend, one query per step, world * k <= 2048), else nccl."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -40,6 +43,31 @@ class ShardedSpMV:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.gathered = None
+        self.exchange_mode = "none" if exchange == "none" else "nccl"   # "none": timing experiments only (local top-k)
+        want_peer = exchange in ("auto", "peer") and self.world > 1 and engine is not None and self.batch == 1 \
+            and self.world <= 8 and self.world * self.k <= 2048 and dist.get_backend(group) == "nccl"
+        if exchange == "peer" and not want_peer:
+            raise ValueError("peer exchange needs the NCCL backend, batch == 1, world <= 8 and world * k <= 2048")
+        if want_peer:
+            ok, handles = 1, [None] * self.world
+            try:
+                mine = engine.peer_init(self.world, self.rank)
+            except Exception as e:                     # e.g. IPC not permitted in this container
+                ok, mine, self.peer_error = 0, b"", str(e)
+            dist.all_gather_object(handles, (ok, mine), group=group)
+            if all(h[0] for h in handles):
+                try:
+                    engine.peer_connect([h[1] for h in handles])
+                except Exception as e:
+                    ok, self.peer_error = 0, str(e)
+            else:
+                ok = 0
+            flags = [None] * self.world
+            dist.all_gather_object(flags, ok, group=group)   # every rank must agree on the mode
+            if all(flags):
+                self.exchange_mode = "peer"
+            elif exchange == "peer":
+                raise RuntimeError("peer exchange could not be set up: " + getattr(self, "peer_error", "a peer failed"))
 
     def _alloc(self, device):
         if self.gathered is None:
@@ -58,8 +86,11 @@ class ShardedSpMV:
 
     def step(self, stream=0):
         eng, k, B = self.engine, self.k, self.batch
+        if self.exchange_mode == "peer":
+            eng.run_exchange_async(k, stream)
+            return
         eng.run_async(k, stream)
-        if self.world == 1:
+        if self.world == 1 or self.exchange_mode == "none":
             return
         kp, _ = eng.result_keys_device(0)
         mine = self.torch.as_tensor(_DevView(kp, (B, KMAX)), device="cuda")[:, :k]

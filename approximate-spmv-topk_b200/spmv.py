@@ -138,6 +138,26 @@ class SpMV(_Base):
         check(capi.lib().tks_result_keys_device(self.handle, query, C.byref(p), C.byref(n)), self.handle)
         return p.value, n.value
 
+    # ---- candidate exchange over peer memory (several GPUs of one box) ----
+    def peer_init(self, world, rank) -> bytes:
+        buf = (C.c_uint8 * capi.IPC_HANDLE_BYTES)()
+        check(capi.lib().tks_peer_init(self.handle, world, rank, C.cast(buf, C.c_void_p)), self.handle)
+        return bytes(buf)
+
+    def peer_connect(self, handles):
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        check(capi.lib().tks_peer_connect(self.handle, C.cast(buf, C.c_void_p)), self.handle)
+
+    def run_exchange_async(self, k=None, stream=0):
+        k = self.k if k is None else k
+        check(capi.lib().tks_run_exchange_async(self.handle, k, C.c_void_p(stream)), self.handle)
+        self.k = k
+
+    def peer_exchange_async(self, k=None, stream=0):
+        k = self.k if k is None else k
+        check(capi.lib().tks_peer_exchange_async(self.handle, k, C.c_void_p(stream)), self.handle)
+
     def merge_keys_device(self, dptr, n_keys, k=None, query=0, stream=0):
         k = self.k if k is None else k
         check(capi.lib().tks_merge_keys_device(self.handle, query, C.c_void_p(dptr), n_keys, k, C.c_void_p(stream)),

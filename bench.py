@@ -247,7 +247,9 @@ def ours(args):
     nnz_total = int(nnz_t.item())
 
     dq = torch.from_numpy(queries).cuda()            # queries resident in HBM for `value`
-    sharded = tks.ShardedSpMV(eng, K, batch=1)       # run + all-gather of K candidates + merge (no-op exchange at N=1)
+    # run + exchange of the K candidates + merge (nothing to exchange at N=1): one peer-memory kernel over NVLink when
+    # the ranks can map each other's windows (CUDA IPC), else NCCL all-gather + merge kernel; TKS_EXCHANGE=nccl forces that
+    sharded = tks.ShardedSpMV(eng, K, batch=1, exchange=os.environ.get("TKS_EXCHANGE", "auto"))
 
     def step(i):
         eng.reset_device(dq[i].data_ptr(), 1, stream)
@@ -332,7 +334,10 @@ def ours(args):
                 "dtype": "f16 values x f16 query, f32 products and sums" if half else "f32", "data": "synthetic",
                 "config": {"workload": wl["name"] + (f", weak-scaled: {world} shards of {wl['rows']} rows" if weak and world > 1 else ""),
                            "rows": rows_total, "cols": cols, "nnz": nnz_total, "k": K,
-                           "sharding": f"rows/{world}, K-candidate all-gather + merge on every rank" if world > 1 else "none",
+                           "sharding": (f"rows/{world}, K candidates exchanged by " +
+                                        ("one peer-memory kernel (stores into every rank's IPC window over NVLink, wait, merge)"
+                                         if sharded.exchange_mode == "peer" else "NCCL all-gather + merge kernel") +
+                                        " on every rank") if world > 1 else "none",
                            "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * (6 if half else 8) / 1e9),
                            "generator_s": round(gen_s, 2)},
                 "roofline": roof,

@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, batch, q):
+def _worker(rank, world, port, batch, q, exchange="auto"):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, str(ROOT))
@@ -40,21 +40,24 @@ def _worker(rank, world, port, batch, q):
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         eng = tks.SpMV(p, idx, val, r1 - r0, cols, k=k, device=rank, row_offset=r0, max_batch=max(batch, 1))
-        sharded = tks.ShardedSpMV(eng, k, batch=batch)
+        sharded = tks.ShardedSpMV(eng, k, batch=batch, exchange=exchange)
+        mode = sharded.exchange_mode
         out = []
-        for rep in range(2):                      # twice: the exchange buffers are reused
+        for rep in range(3):                      # three times: the exchange buffers (and parity slots) are reused
             eng.reset(Q if batch > 1 else Q[0])
             sharded.step(stream.cuda_stream)
             torch.cuda.synchronize()
             out = [eng.read_result(b) for b in range(batch)]
-    q.put((rank, [(a.copy(), b.copy(), c) for a, b, c in out]))
+    q.put((rank, [(a.copy(), b.copy(), c) for a, b, c in out] + [mode]))
     dist.barrier()
     eng.close()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("batch", [1, 33])
-def test_sharded_ranks_agree_with_global_topk(cuda_required, tks, orc, gen, batch):
+@pytest.mark.parametrize("batch,exchange", [(1, "auto"), (1, "nccl"), (33, "auto")])
+def test_sharded_ranks_agree_with_global_topk(cuda_required, tks, orc, gen, batch, exchange):
+    """exchange "auto" with one query per step = the peer-memory kernel (CUDA IPC windows over NVLink) when there are
+    2 GPUs; "nccl" = all-gather + merge kernel; batched steps always take the all-gather path."""
     import torch
     import torch.multiprocessing as mp
     from conftest import make_query
@@ -62,7 +65,7 @@ def test_sharded_ranks_agree_with_global_topk(cuda_required, tks, orc, gen, batc
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, batch, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, batch, q, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     results = dict(q.get(timeout=300) for _ in range(world))
@@ -72,6 +75,12 @@ def test_sharded_ranks_agree_with_global_topk(cuda_required, tks, orc, gen, batc
     rows, cols, k = 20000, 1024, 100
     x, y, v = gen.create_sparse_matrix(rows, cols, 20, "gamma", seed=5)
     v = v.astype(np.float32)
+    modes = {results[r][-1] for r in range(world)}
+    assert len(modes) == 1, "ranks disagree on the exchange mode"
+    if world > 1 and batch == 1 and exchange == "auto":
+        assert modes == {"peer"}, "peer-memory exchange was not set up on a multi-GPU box"
+    else:
+        assert modes == {"nccl"}
     for b in range(batch):
         yref = orc.spmv_f32(x, y, v, make_query(cols, 300 + b), rows)
         order = np.lexsort((np.arange(rows), -yref.astype(np.float64)))[:k]
