@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, batch, q, exchange="auto"):
+def _worker(rank, world, port, batch, q, exchange="auto", k=100):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, str(ROOT))
@@ -30,7 +30,7 @@ def _worker(rank, world, port, batch, q, exchange="auto"):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     gen, sh = tks.create_matrices, tks.sharding
-    rows, cols, k = 20000, 1024, 100
+    rows, cols = 20000, 1024
     x, y, v = gen.create_sparse_matrix(rows, cols, 20, "gamma", seed=5)
     v = v.astype(np.float32)
     ptr = gen.csr_from_coo(x, rows)
@@ -54,10 +54,11 @@ def _worker(rank, world, port, batch, q, exchange="auto"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("batch,exchange", [(1, "auto"), (1, "nccl"), (33, "auto")])
-def test_sharded_ranks_agree_with_global_topk(cuda_required, tks, orc, gen, batch, exchange):
+@pytest.mark.parametrize("batch,exchange,k", [(1, "auto", 100), (1, "auto", 300), (1, "auto", 1024), (1, "nccl", 100), (33, "auto", 100)])
+def test_sharded_ranks_agree_with_global_topk(cuda_required, tks, orc, gen, batch, exchange, k):
     """exchange "auto" with one query per step = the peer-memory kernel (CUDA IPC windows over NVLink) when there are
-    2 GPUs; "nccl" = all-gather + merge kernel; batched steps always take the all-gather path."""
+    2 GPUs; "nccl" = all-gather + merge kernel; batched steps always take the all-gather path.  k = 300 makes the
+    exchange kernel merge 600 keys (its bitonic branch), k = 1024 fills the windows (world * k = 2048)."""
     import torch
     import torch.multiprocessing as mp
     from conftest import make_query
@@ -65,14 +66,14 @@ def test_sharded_ranks_agree_with_global_topk(cuda_required, tks, orc, gen, batc
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, batch, q, exchange)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, batch, q, exchange, k)) for r in range(world)]
     for p in procs:
         p.start()
     results = dict(q.get(timeout=300) for _ in range(world))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    rows, cols, k = 20000, 1024, 100
+    rows, cols = 20000, 1024
     x, y, v = gen.create_sparse_matrix(rows, cols, 20, "gamma", seed=5)
     v = v.astype(np.float32)
     modes = {results[r][-1] for r in range(world)}
@@ -87,7 +88,8 @@ def test_sharded_ranks_agree_with_global_topk(cuda_required, tks, orc, gen, batc
         for rank in range(world):
             val, idx, cnt = results[rank][b]
             assert cnt == k
-            assert set(idx.tolist()) == set(order.tolist())
+            # larger k: rows whose scores tie within fp32 rounding may swap across the k-th place
+            assert len(set(idx.tolist()) ^ set(order.tolist())) <= (0 if k <= 100 else 4)
             np.testing.assert_allclose(val, yref[idx], rtol=1e-5)
             if batch > 1:      # the batched kernel's sums are sequential fp32: exact, in the exact order
                 assert np.array_equal(idx, order.astype(np.uint32))
