@@ -511,7 +511,7 @@ def ours_batched(args, tks, wl, rows_total, peak_gbs, peak_src, world, rank, loc
                            "value_counts": "queries x non-zeros per second",
                            "arithmetic": "fma" if args.batch_fma else "separate mul/add (bit-identical to the gold)",
                            "sharding": f"rows/{world}" if world > 1 else "none",
-                           "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * (6 if half else 8) / 1e9),
+                           "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * 8 / 1e9),
                            "generator_s": round(gen_s, 2)},
                 "roofline": roof, "cpu_baseline": cpu,
                 "e2e": {"value": B * nnz_total / (e2e_ms_step * 1e-3), "unit": "nnz/s", "ms_per_step": e2e_ms_step,
