@@ -16,7 +16,8 @@ namespace {
 
 constexpr uint32_t kKMax = 1024;
 const int kCaps[4] = {256, 512, 1024, 2048};
-const int kCapThreads[4] = {512, 512, 512, 256};
+// CTA size per CAP variant; the k <= 128 variant runs 18 warps per CTA (TKS_MAIN_THREADS=512 restores 16)
+int kCapThreads[4] = {(std::getenv("TKS_MAIN_THREADS") && std::atoi(std::getenv("TKS_MAIN_THREADS")) == 512) ? 512 : 576, 512, 512, 256};
 
 int cap_variant_for_k(uint32_t k) {
     if (k <= 128) return 0;
@@ -243,7 +244,7 @@ int check_float_upload(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, ui
 }
 
 // sample -> main -> select for query q alone (also the fallback of a batched query whose pool overflowed)
-void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool profile) {
+void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool profile, bool to_host = false) {
     const int variant = cap_variant_for_k(k);
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
     const CsrDevice m = csr_device(h);
@@ -274,10 +275,14 @@ void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool
         default: launch_main<2048>(h, 3, m, x, st, k, s, pdl); break;
     }
     if (profile) cudaEventRecord(h->evm1, s);
+    // to_host (blocking tks_run, one query): indices, scores and the count go straight into the pinned host block the
+    // caller reads (zero-copy stores, 1.2 KB), which saves the device-to-host copy after the kernel; the keys stay in HBM
+    uint32_t *o_idx = (to_host ? h->h_res_idx : h->d_res_idx) + (size_t)q * h->kmax;
+    float *o_val = (to_host ? h->h_res_val : h->d_res_val) + (size_t)q * h->kmax;
+    uint32_t *o_cnt = (to_host ? h->h_res_count : h->d_res_count) + q;
     launch_pdl(select_topk_kernel, dim3(1), dim3(kSelectThreads), (size_t)kSelectDynSmem, s, pdl,
                (const uint64_t *)h->d_pool, 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
-               h->d_res_idx + (size_t)q * h->kmax, h->d_res_val + (size_t)q * h->kmax, 0u, h->d_res_count + q,
-               (uint32_t *)nullptr);
+               o_idx, o_val, 0u, o_cnt, (uint32_t *)nullptr);
 }
 
 template <bool SAMPLE>
@@ -325,7 +330,7 @@ bool use_batched(const Handle *h) {
            batched_smem_bytes(h->cols) <= batched_smem_bytes((uint32_t)h->cfg.max_cols);
 }
 
-int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false) {
+int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false, bool to_host = false) {
     if (!h->have_matrix) return h->fail(TKS_ESTATE, "no matrix uploaded");
     if (!h->have_query) return h->fail(TKS_ESTATE, "no query set");
     if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k=%u outside 1..%u", k, h->kmax);
@@ -339,7 +344,7 @@ int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false) {
         // that is not counted)
         h->stats.algorithmic_bytes = matrix_bytes + (uint64_t)h->batch * ((uint64_t)h->cols * 4ull + k * 8ull);
     } else {
-        for (uint32_t q = 0; q < h->batch; q++) launch_single_query(h, q, k, s, profile && q == 0);
+        for (uint32_t q = 0; q < h->batch; q++) launch_single_query(h, q, k, s, profile && q == 0, to_host && h->batch == 1);
         h->last_run_batched = false;
         h->stats.launches_per_run = 3 * h->batch;
         h->stats.algorithmic_bytes = matrix_bytes + (uint64_t)h->cols * 4ull + k * 8ull;
@@ -687,15 +692,18 @@ int tks_run(tks_handle *h, uint32_t k, float *kernel_ms, float *total_ms) {
     TKS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     int rc;
     if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) { h->last_k = k; rc = bscsr_launch(h, h->stream); }
-    else rc = launch_float(h, k, h->stream, h->cfg.profile_kernels != 0);
+    else rc = launch_float(h, k, h->stream, h->cfg.profile_kernels != 0, true);
     if (rc) return rc;
     TKS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) {
         rc = bscsr_fetch(h);
         if (rc) return rc;
     } else {
-        rc = fetch_results_async(h, h->stream);
-        if (rc) return rc;
+        const bool direct = !h->last_run_batched && h->batch == 1;   // the select kernel wrote the pinned host block itself
+        if (!direct) {
+            rc = fetch_results_async(h, h->stream);
+            if (rc) return rc;
+        }
         TKS_CUDA(h, cudaStreamSynchronize(h->stream));
         if (h->last_run_batched) {
             rc = resolve_batched_overflow(h, h->stream);
@@ -875,6 +883,12 @@ int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream) {
     TKS_CUDA(h, launch_pdl(peer_exchange_merge_kernel, dim3(1), dim3(kSelectThreads), (size_t)0, s, pdl_enabled(), px,
                            h->peer_seq, k, (int)(h->cfg.tie_break == TKS_TIE_HIGHER_INDEX), h->d_res_keys, h->d_res_idx,
                            h->d_res_val, h->d_res_count));
+    return TKS_OK;
+}
+
+int tks_set_profile_kernels(tks_handle *h, int on) {
+    if (!h) return TKS_EINVAL;
+    h->cfg.profile_kernels = on ? 1 : 0;
     return TKS_OK;
 }
 

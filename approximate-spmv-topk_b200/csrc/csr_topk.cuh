@@ -38,6 +38,7 @@ constexpr uint32_t kMaxCols = 16384;                       // exclusive: cols <=
 constexpr uint32_t kEpl = 8;                                // elements per lane: one 256-bit load per array
 constexpr uint32_t kElemsPerIter = kWarp * kEpl;            // 256 non-zeros per warp iteration
 constexpr uint32_t kMainThreads = 512;
+constexpr uint32_t kMainThreadsWide = 576;   // k <= 128 variant: 2 x 18 warps per SM at <= 56 registers per thread
 constexpr uint32_t kSampleThreads = 256;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
 // shared-memory buffer (sorted and cut to k only if it ever fills).
 // --------------------------------------------------------------------------
 template <int CAP, bool HALF>
-__global__ void __launch_bounds__(kMainThreads, 2)
+__global__ void __launch_bounds__(CAP == 256 ? kMainThreadsWide : kMainThreads, 2)
 csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uint64_t *pool, uint32_t k,
                      int tie_higher) {
     extern __shared__ __align__(16) uint8_t smem_raw[];

@@ -48,6 +48,9 @@ class _Base:
         check(capi.lib().tks_get_stats(self.handle, C.byref(st)), self.handle)
         return st
 
+    def set_profile_kernels(self, on=True):
+        check(capi.lib().tks_set_profile_kernels(self.handle, int(bool(on))), self.handle)
+
     def run_timed(self, k=None):
         """operator() with both timings: (kernel_ms, total_ms)."""
         k = self.k if k is None else k

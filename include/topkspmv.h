@@ -196,6 +196,10 @@ int tks_peer_connect(tks_handle *h, const void *all_handles);
 int tks_run_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream);   /* = tks_run_async + tks_peer_exchange_async */
 int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream);  /* the exchange + merge kernel alone */
 
+/* Switch tks_config.profile_kernels at run time: while on, tks_run brackets the dominant kernel with two extra
+ * events (tks_stats.last_main_kernel_ms) and launches the kernels without overlap.                              */
+int tks_set_profile_kernels(tks_handle *h, int on);
+
 int tks_get_stats(tks_handle *h, tks_stats *out);
 
 /* ---- host-side surface the reference hosts use around the accelerator ---- */
