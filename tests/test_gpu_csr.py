@@ -324,3 +324,27 @@ def test_half_mode_rejected_in_fixed_mode(tks):
     import ctypes as C
     h = C.c_void_p()
     assert tks.capi.lib().tks_create(C.byref(cfg), C.byref(h)) == tks.capi.TKS_EINVAL
+
+
+def test_profile_switch_and_direct_host_results(cuda_required, tks, orc, cfg1):
+    """tks_run writes indices / scores / count straight into the pinned host block; tks_run_async + read_result fetches
+    them with a copy; with kernel profiling switched on at run time the kernels run without launch overlap and the
+    dominant kernel's time is reported.  All three give the same answer."""
+    x, y, v, ptr = cfg1
+    vec = make_query(1024, 21)
+    with tks.SpMV(ptr, y, v, 10000, 1024, vec=vec, k=100) as s:
+        s()
+        a = s.read_result()
+        assert s.stats().last_main_kernel_ms == 0.0
+        s.run_async(100)
+        b = s.read_result()
+        s.set_profile_kernels(True)
+        s()
+        c = s.read_result()
+        assert 0.0 < s.stats().last_main_kernel_ms < s.stats().last_kernel_ms
+        s.set_profile_kernels(False)
+        s()
+        d = s.read_result()
+    for r in (b, c, d):
+        assert r[2] == a[2] and np.array_equal(r[1], a[1]) and np.array_equal(r[0].view(np.uint32), a[0].view(np.uint32))
+    check_against_scores(a[1], a[0], a[2], orc.spmv_f32(x, y, v, vec, 10000), 100)

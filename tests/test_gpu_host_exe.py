@@ -62,6 +62,29 @@ def test_fixed_engine_cli_reference_and_drift_free(cuda_required, tks, mtx):
     assert p_fix >= 0.9 and p_fix >= p_ref
 
 
+def test_half_precision_flag_matches_the_reference_cli(cuda_required, tks, mtx):
+    """-a = the reference's half_precision_gpu flag (options.hpp:82): values and query rounded to half.  Against the
+    exact fp32 gold the scores now differ beyond 1e-5 (error_val counts them, like the reference's CSV does), the top-100
+    barely moves."""
+    full = run_exe("-m", mtx, "-k", 100, "-t", 3, "-e", 7)
+    half = run_exe("-m", mtx, "-k", 100, "-t", 3, "-e", 7, "-a")
+    assert all(int(r["error_val"]) == 0 for r in full)
+    assert any(int(r["error_val"]) > 0 for r in half)
+    assert all(float(r["precision"]) >= 0.95 for r in half)
+    assert [r["sw_res_idx"] for r in full] == [r["sw_res_idx"] for r in half]          # same queries, same gold
+
+
+def test_device_pack_flag_gives_identical_rows(cuda_required, tks, mtx):
+    """-P builds the BS-CSR packets on the GPU: every CSV row's hardware result equals the host-packed run's."""
+    host = run_exe("-m", mtx, "-k", 100, "-t", 3, "-e", 7, "-f", "-w", 20)
+    dev = run_exe("-m", mtx, "-k", 100, "-t", 3, "-e", 7, "-f", "-w", 20, "-P")
+    assert [r["hw_res_idx"] for r in host] == [r["hw_res_idx"] for r in dev]
+    assert [r["hw_res_val"] for r in host] == [r["hw_res_val"] for r in dev]
+    host32 = run_exe("-m", mtx, "-k", 100, "-t", 2, "-e", 7, "-f", "-w", 32, "-T")
+    dev32 = run_exe("-m", mtx, "-k", 100, "-t", 2, "-e", 7, "-f", "-w", 32, "-T", "-P")
+    assert [r["hw_res_idx"] for r in host32] == [r["hw_res_idx"] for r in dev32]
+
+
 def test_cli_rejects_missing_file(cuda_required):
     out = subprocess.run([str(EXE), "-m", "/nonexistent.mtx"], capture_output=True, text=True)
     assert out.returncode != 0 and "not found" in out.stderr
