@@ -52,25 +52,6 @@ cudaError_t prep_main(Handle *h, int variant) {
     return half_mode(h) ? prep_main_t<CAP, true>(h, variant) : prep_main_t<CAP, false>(h, variant);
 }
 
-// Launch with the programmatic-stream-serialization attribute: the grid may start before the previous kernel of the
-// stream has finished (csr_topk.cuh: pdl_trigger / pdl_wait).
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-
-bool pdl_enabled() {
-    static const bool on = !(std::getenv("TKS_PDL") && std::atoi(std::getenv("TKS_PDL")) == 0);
-    return on;
-}
-
 template <int CAP>
 void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, RunState *st, uint32_t k,
                  cudaStream_t s, bool pdl) {

@@ -63,8 +63,12 @@ void launch_stream_variant(Handle *h, BscsrState *b, const BscsrChunks &m, cudaS
         if ((uint32_t)b->grid * wpc > b->n_chunks) b->grid = (int)((b->n_chunks + wpc - 1) / wpc);
         b->variant_ready = true;
     }
-    bscsr_stream_kernel<W, LFR, XREP, THREADS, PREFETCH, BSX><<<b->grid, THREADS, bscsr_stream_smem(XREP, THREADS), s>>>(
-        b->d_packets, m, b->d_xq, (uint32_t)h->cfg.local_k, b->logs, b->d_theta_seed, b->d_sample_end, b->d_counter);
+    // programmatic dependent launch: the grid starts (and stages its query copies) while the sample kernel still runs
+    const bool pdl = pdl_enabled() && !(h->cfg.profile_kernels != 0 && s == h->stream);
+    launch_pdl(bscsr_stream_kernel<W, LFR, XREP, THREADS, PREFETCH, BSX>, dim3(b->grid), dim3(THREADS),
+               bscsr_stream_smem(XREP, THREADS), s, pdl, (const uint8_t *)b->d_packets, m, (const uint32_t *)b->d_xq,
+               (uint32_t)h->cfg.local_k, b->logs, (const uint32_t *)b->d_theta_seed, (const uint32_t *)b->d_sample_end,
+               b->d_counter);
 }
 
 template <int W, int LFR, bool BSX>
@@ -107,9 +111,10 @@ int dispatch_lfr(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s)
         cudaFuncSetAttribute(bscsr_replay_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplayDynSmem);
         b->replay_ready = true;
     }
-    bscsr_replay_kernel<W><<<b->P * (uint32_t)h->cfg.limited_finished_rows, kReplayThreads, kReplayDynSmem, s>>>(
-        b->logs, b->d_part_chunk_begin, (uint32_t)h->cfg.limited_finished_rows, (uint32_t)h->cfg.local_k, b->chunk_cap,
-        b->d_res_idx, b->d_res_val, b->d_counter);
+    launch_pdl(bscsr_replay_kernel<W>, dim3(b->P * (uint32_t)h->cfg.limited_finished_rows), dim3(kReplayThreads),
+               (size_t)kReplayDynSmem, s, pdl_enabled() && !(h->cfg.profile_kernels != 0 && s == h->stream), b->logs,
+               (const uint32_t *)b->d_part_chunk_begin, (uint32_t)h->cfg.limited_finished_rows, (uint32_t)h->cfg.local_k,
+               b->chunk_cap, b->d_res_idx, b->d_res_val, b->d_counter);
     return TKS_OK;
 }
 

@@ -503,6 +503,7 @@ __global__ void __launch_bounds__(kBsThreads)
 bscsr_sample_kernel(const uint8_t *__restrict__ packets, BscsrSample sm, const uint32_t *__restrict__ xq, uint32_t Kp) {
     __shared__ uint32_t xs[1024];
     __shared__ uint32_t ptab[16 * kBsThreads];
+    pdl_trigger();   // the stream kernel may start staging its query copies while the pieces are reduced
     for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) xs[i] = xq[i];
     ptab[threadIdx.x] = 0;
     __syncthreads();
@@ -593,10 +594,13 @@ bscsr_stream_kernel(const uint8_t *__restrict__ packets, BscsrChunks m, const ui
     extern __shared__ __align__(16) uint8_t bs_smem[];
     uint32_t *xs = reinterpret_cast<uint32_t *>(bs_smem);   // query, pre-shifted (bscsr_api.cu), XREP copies interleaved
     uint32_t *ptab = xs + 1024 * XREP;                      // [prefix length 0..15][thread]: running sums of the products
+    pdl_trigger();   // the replay kernel's CTAs may be set up while this grid drains
+    // the query words were complete before the sample kernel started: the 128 KB of copies are staged while it still runs
     for (uint32_t i = threadIdx.x; i < 1024u * XREP; i += THREADS) xs[i] = xq[i / XREP];
     ptab[threadIdx.x] = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) chunk_counter[1] = 0;   // log-entry statistics of this run
     __syncthreads();
+    pdl_wait();      // the sample's seeds (theta_seed) are not
     const unsigned lane = lane_id();
     for (;;) {
         uint32_t c = 0;
@@ -650,6 +654,7 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
     __shared__ uint32_t s_wsum[kReplayThreads / 32], s_off[kReplayThreads * kReplayCpt + 1];
     __shared__ uint32_t s_n;
     if (tid == 0) s_n = 0;
+    pdl_wait();      // the logs belong to the stream kernel right before
     if (blockIdx.x == 0 && tid == 0 && chunk_counter_reset) *chunk_counter_reset = 0;   // [1]: log entries, statistics
     const bool first_from_packet0 = logs.p0[(size_t)cb * LFR + j] != 0;
     __syncthreads();

@@ -94,6 +94,13 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t *keys, uint32_t n, ui
     sync();
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmaticStreamSerialization attribute may
+// start while its predecessor in the stream is still running; it must not touch anything the predecessor writes
+// before pdl_wait() (which returns once the predecessor grid has completed and its writes are visible).
+// pdl_trigger() in the predecessor allows that early start.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 #endif  // __CUDACC__
 
 }  // namespace tks

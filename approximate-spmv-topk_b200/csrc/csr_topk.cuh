@@ -92,13 +92,6 @@ __device__ __forceinline__ uint32_t ldg_stream_u8(const void *p) {
     return r;
 }
 
-// Programmatic dependent launch (sm_90+): a kernel launched with the programmaticStreamSerialization attribute may
-// start while its predecessor in the stream is still running; it must not touch anything the predecessor writes
-// before pdl_wait() (which returns once the predecessor grid has completed and its writes are visible).
-// pdl_trigger() in the predecessor allows that early start.  Both are no-ops for ordinary launches.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
 __device__ __forceinline__ float tau_from_key(uint32_t key) { return key == 0 ? neg_inf() : ordered_to_f32(key); }
 

@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -103,6 +104,28 @@ struct Handle {
             return (h)->fail(TKS_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),       \
                              __FILE__, __LINE__);                                                      \
     } while (0)
+
+#ifdef __CUDACC__
+// Launch with the programmatic-stream-serialization attribute: the grid may start before the previous kernel of the
+// stream has finished (csr_topk.cuh: pdl_trigger / pdl_wait).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+inline bool pdl_enabled() {
+    static const bool on = !(std::getenv("TKS_PDL") && std::atoi(std::getenv("TKS_PDL")) == 0);
+    return on;
+}
+
+#endif
 
 // api.cu: exclusive scan of n u32 values into n+1 u64 values on the handle's stream (setup only; synchronises)
 int device_scan_u32(Handle *h, const uint32_t *d_in, uint64_t n, uint64_t *d_out);

@@ -171,3 +171,27 @@ def test_errors(cuda_required, tks, orc, gen):
     with pytest.raises(tks.capi.TksError, match="no query"):
         f()
     f.close()
+
+
+@pytest.mark.parametrize("P,LFR,Kp", [(4, 4, 8), (2, 2, 4), (8, 3, 16)])
+def test_long_candidate_logs_are_pruned_exactly(cuda_required, tks, orc, gen, P, LFR, Kp):
+    """Few partitions over many rows: thousands of logged candidates per (partition, lane) list, so the replay kernel's
+    parallel pruning (segment thresholds = K-th largest of everything before the segment) does real work; the result
+    words must still be the sequential machine's, slot for slot (incl. K = 4 with the reference's argmin_4 typo)."""
+    rows = 600000
+    x, y, v = gen.create_sparse_matrix(rows, 1024, 20, "gamma", seed=21)
+    run_both(tks, orc, x, y, v, rows, 1024, make_query(1024, 9), P=P, LFR=LFR, Kp=Kp)
+
+
+def test_long_logs_with_massive_ties(cuda_required, tks, orc):
+    """One non-zero per pair of rows pattern with values from a tiny set and a constant query: almost every candidate
+    ties with the list's minimum -- the `>=` acceptance and the "highest slot among equal minima" rule decide which
+    row index survives, and pruning must not change a single slot."""
+    rng = np.random.default_rng(5)
+    rows, cols = 300000, 64
+    deg = rng.integers(1, 4, rows)
+    x = np.repeat(np.arange(rows, dtype=np.uint32), deg)
+    y = rng.integers(0, cols, x.size).astype(np.uint32)
+    v = rng.choice(np.array([0.125, 0.25, 0.5]), x.size)
+    vec = np.full(cols, 0.5, np.float32)
+    run_both(tks, orc, x, y, v, rows, cols, vec, P=4)
