@@ -389,10 +389,21 @@ def cpu_baseline_leg(tks, eng, queries, idx_gpu, val_gpu, args):
     e = int(ptr[sample_rows])
     times, kind, cores, _ = cpu_reference(ptr[:sample_rows + 1], idx[:e], val[:e], queries, K, max_seconds=20.0)
     sec = sum(times) / len(times)
+    # top-K recall (the reference's "precision", host_spmv_bscsr.cpp:646-648) of the engine's last result against the
+    # reference gold over the WHOLE matrix for that query (one query: a fraction of a second on the host cores)
+    _, _, _, full = cpu_reference(ptr, idx, val, queries[-1:], K, max_seconds=1e9)
+    gi, gv = full[0]
+    inter = len(set(gi.tolist()) & set(np.asarray(idx_gpu).tolist()))
+    # rows outside the intersection must be near-ties of the K-th score (fp32 summation order), never real misses
+    kth = float(gv[-1])
+    miss = [float(v) for i, v in zip(gi.tolist(), gv.tolist()) if i not in set(np.asarray(idx_gpu).tolist())]
     return {"value": e / sec, "unit": "nnz/s", "cores": cores, "kind": kind,
             "sample": f"first {sample_rows} rows ({e} nnz) of the benchmark matrix, {len(times)} queries, "
                       f"reference spmv_coo_gold_top_k over {cores} row blocks in {cores} threads",
-            "ms_per_query_on_sample": sec * 1e3}
+            "ms_per_query_on_sample": sec * 1e3,
+            "recall_vs_reference_gold_full_matrix": {"k": K, "precision": inter / K,
+                                                     "max_rel_gap_of_missed_rows_to_kth": max([abs(v - kth) / kth for v in miss], default=0.0),
+                                                     "max_abs_score_diff": float(np.max(np.abs(np.sort(gv)[::-1] - np.sort(np.asarray(val_gpu))[::-1])))}}
 
 
 def ours_batched(args, tks, wl, rows_total, peak_gbs, peak_src, world, rank, local, stream):
