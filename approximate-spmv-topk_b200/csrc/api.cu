@@ -225,7 +225,8 @@ int check_float_upload(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, ui
 }
 
 // sample -> main -> select for query q alone (also the fallback of a batched query whose pool overflowed)
-void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool profile, bool to_host = false) {
+void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool profile, bool to_host = false,
+                         const PeerExchange *px = nullptr, uint32_t seq = 0) {
     const int variant = cap_variant_for_k(k);
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
     const CsrDevice m = csr_device(h);
@@ -261,9 +262,16 @@ void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool
     uint32_t *o_idx = (to_host ? h->h_res_idx : h->d_res_idx) + (size_t)q * h->kmax;
     float *o_val = (to_host ? h->h_res_val : h->d_res_val) + (size_t)q * h->kmax;
     uint32_t *o_cnt = (to_host ? h->h_res_count : h->d_res_count) + q;
-    launch_pdl(select_topk_kernel, dim3(1), dim3(kSelectThreads), (size_t)kSelectDynSmem, s, pdl,
+    if (px && px->world > 1) {
+        // several GPUs: local select + exchange over the peer windows + merge in this one launch
+        launch_pdl(select_topk_kernel<true>, dim3(1), dim3(kSelectThreads), (size_t)kSelectDynSmem, s, pdl,
+                   (const uint64_t *)h->d_pool, 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
+                   o_idx, o_val, 0u, o_cnt, (uint32_t *)nullptr, *px, seq);
+        return;
+    }
+    launch_pdl(select_topk_kernel<false>, dim3(1), dim3(kSelectThreads), (size_t)kSelectDynSmem, s, pdl,
                (const uint64_t *)h->d_pool, 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
-               o_idx, o_val, 0u, o_cnt, (uint32_t *)nullptr);
+               o_idx, o_val, 0u, o_cnt, (uint32_t *)nullptr, PeerExchange{}, 0u);
 }
 
 template <bool SAMPLE>
@@ -301,9 +309,9 @@ void launch_batched(Handle *h, uint32_t k, cudaStream_t s, bool profile) {
     if (profile) cudaEventRecord(h->evm0, s);
     launch_batched_kernel<false>(h, m, a, (uint32_t)h->num_sms, s);
     if (profile) cudaEventRecord(h->evm1, s);
-    select_topk_kernel<<<h->batch, kSelectThreads, kSelectDynSmem, s>>>(
+    select_topk_kernel<false><<<h->batch, kSelectThreads, kSelectDynSmem, s>>>(
         h->d_bpool, h->bpool_cap, h->d_state, 0u, h->bpool_cap, k, a.tie_higher, h->d_res_keys, h->d_res_idx,
-        h->d_res_val, h->kmax, h->d_res_count, h->d_pass_counter);
+        h->d_res_val, h->kmax, h->d_res_count, h->d_pass_counter, PeerExchange{}, 0u);
 }
 
 bool use_batched(const Handle *h) {
@@ -473,7 +481,9 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
             if ((e = cudaFuncSetAttribute(csr_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess ||
                 (e = cudaFuncSetAttribute(csr_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess)
                 return bail("sample smem attr", e);
-            if ((e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            if ((e = cudaFuncSetAttribute(select_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(kSelectDynSmem))) != cudaSuccess ||
+                (e = cudaFuncSetAttribute(select_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(kSelectDynSmem))) != cudaSuccess)
                 return bail("select smem attr", e);
         }
@@ -775,10 +785,10 @@ int tks_merge_keys_device(tks_handle *h, uint32_t query, const uint64_t *d_keys,
     if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k out of range");
     TKS_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
-    select_topk_kernel<<<1, kSelectThreads, kSelectDynSmem, s>>>(
+    select_topk_kernel<false><<<1, kSelectThreads, kSelectDynSmem, s>>>(
         d_keys, 0u, nullptr, n_keys, 0u, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX,
         h->d_res_keys + (size_t)query * h->kmax, h->d_res_idx + (size_t)query * h->kmax,
-        h->d_res_val + (size_t)query * h->kmax, 0u, h->d_res_count + query, nullptr);
+        h->d_res_val + (size_t)query * h->kmax, 0u, h->d_res_count + query, nullptr, PeerExchange{}, 0u);
     TKS_CUDA(h, cudaGetLastError());
     h->last_k = k;
     if (h->batch < query + 1) h->batch = query + 1;
@@ -794,9 +804,9 @@ int tks_merge_keys_batched_device(tks_handle *h, const uint64_t *d_keys, uint32_
     if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k out of range");
     TKS_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
-    select_topk_kernel<<<batch, kSelectThreads, kSelectDynSmem, s>>>(
+    select_topk_kernel<false><<<batch, kSelectThreads, kSelectDynSmem, s>>>(
         d_keys, keys_per_query, nullptr, keys_per_query, 0u, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX,
-        h->d_res_keys, h->d_res_idx, h->d_res_val, h->kmax, h->d_res_count, nullptr);
+        h->d_res_keys, h->d_res_idx, h->d_res_val, h->kmax, h->d_res_count, nullptr, PeerExchange{}, 0u);
     TKS_CUDA(h, cudaGetLastError());
     h->last_k = k;
     if (h->batch < batch) h->batch = batch;
@@ -840,14 +850,36 @@ int tks_peer_connect(tks_handle *h, const void *all_handles) {
     return TKS_OK;
 }
 
+static PeerExchange peer_args(const tks_handle *h) {
+    PeerExchange px{};
+    for (uint32_t r = 0; r < h->peer_world; r++) px.window[r] = static_cast<uint64_t *>(h->peer_mapped[r]);
+    px.world = h->peer_world; px.rank = h->peer_rank; px.kmax = h->kmax;
+    return px;
+}
+
 int tks_run_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream) {
     if (!h) return TKS_EINVAL;
     if (!h->peer_ready) return h->fail(TKS_ESTATE, "tks_peer_connect first");
+    if (h->cfg.mode != TKS_MODE_FLOAT_CSR) return h->fail(TKS_ESTATE, "float mode only");
+    if (!h->have_matrix) return h->fail(TKS_ESTATE, "no matrix uploaded");
+    if (!h->have_query) return h->fail(TKS_ESTATE, "no query set");
     if (h->batch != 1) return h->fail(TKS_EINVAL, "the peer exchange serves one query per run (batched runs use the all-gather path)");
+    if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k=%u outside 1..%u", k, h->kmax);
     if ((uint64_t)h->peer_world * k > kSelectSortCap) return h->fail(TKS_EINVAL, "world * k exceeds %u", kSelectSortCap);
-    int rc = tks_run_async(h, k, cuda_stream);
-    if (rc) return rc;
-    return tks_peer_exchange_async(h, k, cuda_stream);
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    if (s != h->stream) TKS_CUDA(h, cudaStreamWaitEvent(s, h->ev_query, 0));
+    const PeerExchange px = peer_args(h);
+    h->peer_seq += 1;
+    // sample -> main -> select; the select kernel also exchanges the candidates with the peers and merges
+    launch_single_query(h, 0, k, s, false, false, &px, h->peer_seq);
+    TKS_CUDA(h, cudaGetLastError());
+    h->last_run_batched = false;
+    h->stats.launches_per_run = 3;
+    h->last_k = k;
+    h->have_result = false;
+    h->overflow_check_pending = false;
+    return TKS_OK;
 }
 
 int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream) {
@@ -857,9 +889,7 @@ int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream) {
     if ((uint64_t)h->peer_world * k > kSelectSortCap) return h->fail(TKS_EINVAL, "world * k exceeds %u", kSelectSortCap);
     TKS_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
-    PeerExchange px{};
-    for (uint32_t r = 0; r < h->peer_world; r++) px.window[r] = static_cast<uint64_t *>(h->peer_mapped[r]);
-    px.world = h->peer_world; px.rank = h->peer_rank; px.kmax = h->kmax;
+    const PeerExchange px = peer_args(h);
     h->peer_seq += 1;
     TKS_CUDA(h, launch_pdl(peer_exchange_merge_kernel, dim3(1), dim3(kSelectThreads), (size_t)0, s, pdl_enabled(), px,
                            h->peer_seq, k, (int)(h->cfg.tie_break == TKS_TIE_HIGHER_INDEX), h->d_res_keys, h->d_res_idx,

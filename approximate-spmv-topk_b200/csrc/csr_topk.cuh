@@ -573,6 +573,117 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
     }
 }
 
+// ---- constants of the select kernel (Kernel 3) ----
+constexpr uint32_t kSelectThreads = 1024;
+constexpr uint32_t kSelectSortCap = 2048;     // keys sorted directly (16 KB static)
+constexpr uint32_t kSelectRankSortMax = 512;  // up to here by rank (one pass, no barriers), above by a bitonic network
+constexpr uint32_t kSelectSmemKeys = 16384;   // pool keys staged in dynamic shared memory (128 KB)
+constexpr uint32_t kSelectDynSmem = (kSelectThreads / kWarp) * 1024u + kSelectSmemKeys * 8u;
+
+// ---- candidate exchange over peer memory: shared pieces (the protocol is described at Kernel 4 below) ----
+constexpr uint32_t kPeerMaxWorld = 8;
+constexpr uint32_t kPeerTimeout = 0xFFFFFFFEu;
+
+struct PeerExchange {
+    uint64_t *window[kPeerMaxWorld];   // window[r]: rank r's window as mapped in THIS process (window[rank] = local)
+    uint32_t world, rank, kmax;
+};
+
+__host__ __device__ constexpr size_t peer_window_bytes(uint32_t kmax) { return 2ull * kPeerMaxWorld * kmax * 2ull * sizeof(uint64_t); }
+
+__device__ __forceinline__ void st_volatile_v2_u64(uint64_t *p, uint64_t a, uint64_t b) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_volatile_v2_u64(const uint64_t *p, uint64_t &a, uint64_t &b) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// This rank's key of output slot `slot` (0 = absent) into every rank's window, each word tagged with the step.
+__device__ __forceinline__ void peer_push_key(const PeerExchange &px, uint32_t seq, uint32_t slot, uint64_t key) {
+    const uint64_t tag = (uint64_t)seq << 32;
+    const size_t rec = ((((size_t)(seq & 1u)) * px.world + px.rank) * px.kmax + slot) * 2u;
+    for (uint32_t d = 0; d < px.world; d++) {
+        const uint32_t p = (px.rank + 1u + d) % px.world;   // peers first, the local copy last
+        st_volatile_v2_u64(px.window[p] + rec, tag | (key >> 32), tag | (key & 0xFFFFFFFFull));
+    }
+}
+
+// Whole CTA: wait until every rank's k records of this step sit in the local window, gather them into `keys`
+// (shared memory, kSelectSortCap entries), merge and write the global top-k.  *s_timeout / *s_present: shared words
+// zeroed by the caller before a barrier.
+__device__ __forceinline__ void peer_poll_and_merge(const PeerExchange &px, uint32_t seq, uint32_t k, int tie_higher,
+                                                    uint64_t *keys, uint32_t *s_timeout, uint32_t *s_present,
+                                                    uint64_t *res_keys, uint32_t *res_idx, float *res_val,
+                                                    uint32_t *res_count) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t parity = seq & 1u;
+    const uint32_t n = px.world * k;   // <= kSelectSortCap (checked by the host)
+    uint32_t present = 0;
+    for (uint32_t t = tid; t < n; t += blockDim.x) {
+        const uint32_t r = t / k, i = t - r * k;
+        const uint64_t *src = px.window[px.rank] + (((size_t)parity * px.world + r) * px.kmax + i) * 2u;
+        uint64_t a, b;
+        uint64_t t0 = 0;
+        uint32_t spins = 0;
+        for (;;) {
+            ld_volatile_v2_u64(src, a, b);
+            if ((a >> 32) == seq && (b >> 32) == seq) break;
+            if ((++spins & 63u) == 0) {
+                const uint64_t now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > 2000000000ull || *reinterpret_cast<volatile uint32_t *>(s_timeout)) { *s_timeout = 1; break; }
+            }
+        }
+        const uint64_t key = (a << 32) | (b & 0xFFFFFFFFull);
+        keys[t] = key;
+        present += key != 0ull;
+    }
+    present = __reduce_add_sync(kFull, present);
+    if (lane_id() == 0 && present) atomicAdd(s_present, present);
+    __syncthreads();
+    if (*s_timeout) {
+        if (tid == 0) *res_count = kPeerTimeout;
+        return;
+    }
+    const uint32_t cnt = *s_present < k ? *s_present : k;
+    if (n <= kSelectRankSortMax) {
+        const uint32_t items = (4u * n + kWarp - 1u) & ~(kWarp - 1u);
+        for (uint32_t w = tid; w < items; w += blockDim.x) {
+            const uint32_t i = w >> 2, part = w & 3u;
+            const uint64_t mine = (i < n) ? keys[i] : 0ull;
+            uint32_t r = 0;
+            for (uint32_t j = part; j < n; j += 4u) {
+                const uint64_t other = keys[j];
+                r += (other > mine) || (other == mine && j < i);
+            }
+            r += __shfl_xor_sync(kFull, r, 1);
+            r += __shfl_xor_sync(kFull, r, 2);
+            if (part == 0 && i < n && r < cnt) {
+                res_keys[r] = mine;
+                res_idx[r] = key_row(mine, tie_higher);
+                res_val[r] = ordered_to_f32(key_score(mine));
+            }
+        }
+    } else {
+        uint32_t n2 = 32;
+        while (n2 < n) n2 <<= 1;
+        for (uint32_t i = n + tid; i < n2; i += blockDim.x) keys[i] = 0ull;
+        bitonic_sort_desc(keys, n2, tid, blockDim.x, [] { __syncthreads(); });
+        for (uint32_t i = tid; i < cnt; i += blockDim.x) {
+            res_keys[i] = keys[i];
+            res_idx[i] = key_row(keys[i], tie_higher);
+            res_val[i] = ordered_to_f32(key_score(keys[i]));
+        }
+    }
+    for (uint32_t i = cnt + tid; i < k; i += blockDim.x) { res_keys[i] = 0ull; res_idx[i] = 0u; res_val[i] = 0.0f; }
+    if (tid == 0) *res_count = cnt;
+}
+
 // --------------------------------------------------------------------------
 // Kernel 3: k best keys of a pool, one CTA.  The pool is staged in shared memory
 // (up to kSelectSmemKeys keys; larger pools are read from L2 on every pass),
@@ -580,28 +691,29 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
 // threshold, and those are sorted.  Also resets the per-query scratch.
 // Dynamic shared memory: kSelectDynSmem bytes (per-warp histograms + staged keys).
 // --------------------------------------------------------------------------
-constexpr uint32_t kSelectThreads = 1024;
-constexpr uint32_t kSelectSortCap = 2048;     // keys sorted directly (16 KB static)
-constexpr uint32_t kSelectRankSortMax = 512;  // up to here by rank (one pass, no barriers), above by a bitonic network
-constexpr uint32_t kSelectSmemKeys = 16384;   // pool keys staged in dynamic shared memory (128 KB)
-constexpr uint32_t kSelectDynSmem = (kSelectThreads / kWarp) * 1024u + kSelectSmemKeys * 8u;
 
 constexpr uint32_t kPoolOverflow = 0xFFFFFFFFu;   // *out_count when a capped pool overflowed (batched mode)
 
 // Grid: one CTA per query.  CTA q reads pool + q * pool_stride; its key count is st[q].pool_count (st != nullptr)
 // or pool_count_imm; results go to out_* + q * out_stride and out_count[q].  pool_cap != 0: a count above it
 // means keys were dropped -> out_count = kPoolOverflow and nothing else is written.
+// EXCHANGE (several GPUs, one query): the k sorted keys do not go to out_* but straight into every rank's peer window
+// (peer_push_key), and the same CTA then waits for the other ranks' lists and writes the GLOBAL top-k to out_*
+// (peer_poll_and_merge) -- local select, exchange and merge in one launch.
+template <bool EXCHANGE>
 __global__ void __launch_bounds__(kSelectThreads)
 select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunState *st, uint32_t pool_count_imm,
                    uint32_t pool_cap, uint32_t k, int tie_higher, uint64_t *out_keys, uint32_t *out_idx,
-                   float *out_val, uint32_t out_stride, uint32_t *out_count, uint32_t *pass_counter) {
+                   float *out_val, uint32_t out_stride, uint32_t *out_count, uint32_t *pass_counter,
+                   PeerExchange px, uint32_t seq) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);                                  // 32 KB
     uint64_t *staged = reinterpret_cast<uint64_t *>(smem_raw + (kSelectThreads / kWarp) * 1024u);
     __shared__ uint64_t keys[kSelectSortCap];
-    __shared__ uint32_t s_bin, s_above[2], s_cnt;
+    __shared__ uint32_t s_bin, s_above[2], s_cnt, s_timeout, s_present;
     const uint32_t tid = threadIdx.x;
     const uint32_t q = blockIdx.x;
+    if (EXCHANGE && tid == 0) { s_timeout = 0; s_present = 0; }
     RunState *st_reset = st ? st + q : nullptr;
     pool += (size_t)q * pool_stride;
     out_keys += (size_t)q * out_stride;
@@ -673,12 +785,19 @@ select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunS
             r += __shfl_xor_sync(kFull, r, 1);
             r += __shfl_xor_sync(kFull, r, 2);
             if (part == 0 && i < m && r < k) {
-                out_keys[r] = mine;
-                out_idx[r] = key_row(mine, tie_higher);
-                out_val[r] = ordered_to_f32(key_score(mine));
+                if (EXCHANGE) {
+                    peer_push_key(px, seq, r, mine);
+                } else {
+                    out_keys[r] = mine;
+                    out_idx[r] = key_row(mine, tie_higher);
+                    out_val[r] = ordered_to_f32(key_score(mine));
+                }
             }
         }
-        for (uint32_t i = cnt + tid; i < k; i += blockDim.x) { out_keys[i] = 0ull; out_idx[i] = 0u; out_val[i] = 0.0f; }
+        for (uint32_t i = cnt + tid; i < k; i += blockDim.x) {
+            if (EXCHANGE) peer_push_key(px, seq, i, 0ull);
+            else { out_keys[i] = 0ull; out_idx[i] = 0u; out_val[i] = 0.0f; }
+        }
     } else {
         uint32_t n2 = 32;
         while (n2 < m) n2 <<= 1;
@@ -686,10 +805,26 @@ select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunS
         bitonic_sort_desc(keys, n2, tid, blockDim.x, [] { __syncthreads(); });
         for (uint32_t i = tid; i < k; i += blockDim.x) {
             const uint64_t key = (i < cnt) ? keys[i] : 0ull;
-            out_keys[i] = key;
-            out_idx[i] = (i < cnt) ? key_row(key, tie_higher) : 0u;
-            out_val[i] = (i < cnt) ? ordered_to_f32(key_score(key)) : 0.0f;
+            if (EXCHANGE) {
+                peer_push_key(px, seq, i, key);
+            } else {
+                out_keys[i] = key;
+                out_idx[i] = (i < cnt) ? key_row(key, tie_higher) : 0u;
+                out_val[i] = (i < cnt) ? ordered_to_f32(key_score(key)) : 0.0f;
+            }
         }
+    }
+    if (EXCHANGE) {
+        __syncthreads();   // every thread is done with keys[] (the rank sort reads it) before the gather overwrites it
+        peer_poll_and_merge(px, seq, k, tie_higher, keys, &s_timeout, &s_present, out_keys, out_idx, out_val, out_count);
+        if (tid == 0 && st_reset) {
+            st_reset->result_count = n;
+            st_reset->chunk_counter = 0;
+            st_reset->pool_count = 0;
+            st_reset->tau_key = 0;
+            st_reset->sample_ticket = 0;
+        }
+        return;
     }
     if (tid == 0) {
         *out_count = cnt;
@@ -718,108 +853,18 @@ select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunS
 // has sent its step s+1 list, which a peer only does after it has consumed step s.
 // The wait is bounded (~2 s of %globaltimer): a missing peer yields *res_count = kPeerTimeout, not a hung GPU.
 // --------------------------------------------------------------------------
-constexpr uint32_t kPeerMaxWorld = 8;
-constexpr uint32_t kPeerTimeout = 0xFFFFFFFEu;
-
-struct PeerExchange {
-    uint64_t *window[kPeerMaxWorld];   // window[r]: rank r's window as mapped in THIS process (window[rank] = local)
-    uint32_t world, rank, kmax;
-};
-
-__host__ __device__ constexpr size_t peer_window_bytes(uint32_t kmax) { return 2ull * kPeerMaxWorld * kmax * 2ull * sizeof(uint64_t); }
-
-__device__ __forceinline__ void st_volatile_v2_u64(uint64_t *p, uint64_t a, uint64_t b) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
-}
-__device__ __forceinline__ void ld_volatile_v2_u64(const uint64_t *p, uint64_t &a, uint64_t &b) {
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-}
-__device__ __forceinline__ uint64_t global_timer_ns() {
-    uint64_t t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
 __global__ void __launch_bounds__(kSelectThreads)
 peer_exchange_merge_kernel(PeerExchange px, uint32_t seq, uint32_t k, int tie_higher, uint64_t *res_keys,
                            uint32_t *res_idx, float *res_val, uint32_t *res_count) {
     __shared__ uint64_t keys[kSelectSortCap];
     __shared__ uint32_t s_timeout, s_present;
     const uint32_t tid = threadIdx.x;
-    const uint32_t parity = seq & 1u;
-    const uint64_t tag = (uint64_t)seq << 32;
     if (tid == 0) { s_timeout = 0; s_present = 0; }
     pdl_wait();   // this rank's list comes from the select kernel right before
     const uint32_t mine_n = *res_count;
-    if (tid < k) {
-        const uint64_t key = (tid < mine_n) ? res_keys[tid] : 0ull;
-        const size_t slot = (((size_t)parity * px.world + px.rank) * px.kmax + tid) * 2u;
-        for (uint32_t d = 0; d < px.world; d++) {
-            const uint32_t p = (px.rank + 1u + d) % px.world;   // peers first, the local copy last
-            st_volatile_v2_u64(px.window[p] + slot, tag | (key >> 32), tag | (key & 0xFFFFFFFFull));
-        }
-    }
+    if (tid < k) peer_push_key(px, seq, tid, (tid < mine_n) ? res_keys[tid] : 0ull);
     __syncthreads();   // s_timeout / s_present are initialised; every read of res_keys is done
-    const uint32_t n = px.world * k;   // <= kSelectSortCap (checked by the host)
-    uint32_t present = 0;
-    for (uint32_t t = tid; t < n; t += blockDim.x) {
-        const uint32_t r = t / k, i = t - r * k;
-        const uint64_t *src = px.window[px.rank] + (((size_t)parity * px.world + r) * px.kmax + i) * 2u;
-        uint64_t a, b;
-        uint64_t t0 = 0;
-        uint32_t spins = 0;
-        for (;;) {
-            ld_volatile_v2_u64(src, a, b);
-            if ((a >> 32) == seq && (b >> 32) == seq) break;
-            if ((++spins & 63u) == 0) {
-                const uint64_t now = global_timer_ns();
-                if (t0 == 0) t0 = now;
-                if (now - t0 > 2000000000ull || *reinterpret_cast<volatile uint32_t *>(&s_timeout)) { s_timeout = 1; break; }
-            }
-        }
-        const uint64_t key = (a << 32) | (b & 0xFFFFFFFFull);
-        keys[t] = key;
-        present += key != 0ull;
-    }
-    present = __reduce_add_sync(kFull, present);
-    if (lane_id() == 0 && present) atomicAdd(&s_present, present);
-    __syncthreads();
-    if (s_timeout) {
-        if (tid == 0) *res_count = kPeerTimeout;
-        return;
-    }
-    const uint32_t cnt = s_present < k ? s_present : k;
-    if (n <= kSelectRankSortMax) {
-        const uint32_t items = (4u * n + kWarp - 1u) & ~(kWarp - 1u);
-        for (uint32_t w = tid; w < items; w += blockDim.x) {
-            const uint32_t i = w >> 2, part = w & 3u;
-            const uint64_t mine = (i < n) ? keys[i] : 0ull;
-            uint32_t r = 0;
-            for (uint32_t j = part; j < n; j += 4u) {
-                const uint64_t other = keys[j];
-                r += (other > mine) || (other == mine && j < i);
-            }
-            r += __shfl_xor_sync(kFull, r, 1);
-            r += __shfl_xor_sync(kFull, r, 2);
-            if (part == 0 && i < n && r < cnt) {
-                res_keys[r] = mine;
-                res_idx[r] = key_row(mine, tie_higher);
-                res_val[r] = ordered_to_f32(key_score(mine));
-            }
-        }
-    } else {
-        uint32_t n2 = 32;
-        while (n2 < n) n2 <<= 1;
-        for (uint32_t i = n + tid; i < n2; i += blockDim.x) keys[i] = 0ull;
-        bitonic_sort_desc(keys, n2, tid, blockDim.x, [] { __syncthreads(); });
-        for (uint32_t i = tid; i < cnt; i += blockDim.x) {
-            res_keys[i] = keys[i];
-            res_idx[i] = key_row(keys[i], tie_higher);
-            res_val[i] = ordered_to_f32(key_score(keys[i]));
-        }
-    }
-    for (uint32_t i = cnt + tid; i < k; i += blockDim.x) { res_keys[i] = 0ull; res_idx[i] = 0u; res_val[i] = 0.0f; }
-    if (tid == 0) *res_count = cnt;
+    peer_poll_and_merge(px, seq, k, tie_higher, keys, &s_timeout, &s_present, res_keys, res_idx, res_val, res_count);
 }
 
 }  // namespace tks

@@ -335,7 +335,7 @@ def ours(args):
                 "config": {"workload": wl["name"] + (f", weak-scaled: {world} shards of {wl['rows']} rows" if weak and world > 1 else ""),
                            "rows": rows_total, "cols": cols, "nnz": nnz_total, "k": K,
                            "sharding": (f"rows/{world}, K candidates exchanged by " +
-                                        ("one peer-memory kernel (stores into every rank's IPC window over NVLink, wait, merge)"
+                                        ("the select kernel itself (stores into every rank's IPC window over NVLink, wait, merge: no extra launch)"
                                          if sharded.exchange_mode == "peer" else "NCCL all-gather + merge kernel") +
                                         " on every rank") if world > 1 else "none",
                            "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * (6 if half else 8) / 1e9),
@@ -345,7 +345,8 @@ def ours(args):
                 "e2e": {"value": nnz_total / (e2e_ms_step * 1e-3), "unit": "nnz/s", "ms_per_step": e2e_ms_step,
                         "h2d_bytes_per_step": cols * 4, "d2h_bytes_per_step": K * 8 + 4,
                         "api": "SpMV.reset(host vec) -> operator() -> read_result(host)"},
-                "gpu_launches": args.steps * (3 if world == 1 else 4),
+                # ours per step: sample + main + select (which also exchanges and merges in peer mode); the NCCL path adds a merge launch
+                "gpu_launches": args.steps * (3 if (world == 1 or sharded.exchange_mode == "peer") else 4),
                 "candidates_last_step": int(stats.last_candidates),
                 "hbm_gbs_effective": alg_bytes_local * world / (ms_step * 1e-3) / 1e9,
                 "clocks": clocks}
