@@ -17,7 +17,7 @@ LIB_PATH = _HERE / "lib" / "libtopkspmv.so"
 TKS_OK, TKS_EINVAL, TKS_ECUDA, TKS_ESTATE, TKS_ENOMEM, TKS_EIO = 0, -1, -2, -3, -4, -5
 MODE_FLOAT_CSR, MODE_FIXED_BSCSR = 0, 1
 TIE_LOWER_INDEX, TIE_HIGHER_INDEX = 0, 1
-VALUE_FP32, VALUE_FP16 = 0, 1
+VALUE_FP32, VALUE_FP16, VALUE_BF16 = 0, 1, 2
 IPC_HANDLE_BYTES = 128
 
 

@@ -30,16 +30,17 @@ size_t main_smem_bytes(uint32_t cols, int variant) {
     return (((cols + 1u) * 4u + 15u) & ~15u) + (size_t)(kCapThreads[variant] / 32) * kCaps[variant] * 8u;
 }
 
-inline bool half_mode(const Handle *h) { return h->cfg.value_type == TKS_VALUE_FP16; }
+inline bool half_mode(const Handle *h) { return h->cfg.value_type != TKS_VALUE_FP32; }   // 16-bit storage (half or bfloat16)
+inline int value_type(const Handle *h) { return h->cfg.value_type; }
 
-template <int CAP, bool HALF>
+template <int CAP, int VT>
 cudaError_t prep_main_t(Handle *h, int variant) {
     size_t smem = main_smem_bytes(h->cfg.max_cols, variant);
-    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, HALF>, kCapThreads[variant],
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, VT>, kCapThreads[variant],
                                                       smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
@@ -49,7 +50,11 @@ cudaError_t prep_main_t(Handle *h, int variant) {
 
 template <int CAP>
 cudaError_t prep_main(Handle *h, int variant) {
-    return half_mode(h) ? prep_main_t<CAP, true>(h, variant) : prep_main_t<CAP, false>(h, variant);
+    switch (value_type(h)) {
+        case TKS_VALUE_FP16: return prep_main_t<CAP, 1>(h, variant);
+        case TKS_VALUE_BF16: return prep_main_t<CAP, 2>(h, variant);
+        default: return prep_main_t<CAP, 0>(h, variant);
+    }
 }
 
 template <int CAP>
@@ -57,18 +62,18 @@ void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, Run
                  cudaStream_t s, bool pdl) {
     size_t smem = main_smem_bytes(m.cols, variant);
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
-    if (half_mode(h))
-        launch_pdl(csr_topk_main_kernel<CAP, true>, dim3(h->main_grid[variant]), dim3(kCapThreads[variant]), smem, s, pdl,
-                   m, x, st, h->d_pool, k, tie_higher);
-    else
-        launch_pdl(csr_topk_main_kernel<CAP, false>, dim3(h->main_grid[variant]), dim3(kCapThreads[variant]), smem, s, pdl,
-                   m, x, st, h->d_pool, k, tie_higher);
+    const dim3 grid(h->main_grid[variant]), block(kCapThreads[variant]);
+    switch (value_type(h)) {
+        case TKS_VALUE_FP16: launch_pdl(csr_topk_main_kernel<CAP, 1>, grid, block, smem, s, pdl, m, x, st, h->d_pool, k, tie_higher); break;
+        case TKS_VALUE_BF16: launch_pdl(csr_topk_main_kernel<CAP, 2>, grid, block, smem, s, pdl, m, x, st, h->d_pool, k, tie_higher); break;
+        default: launch_pdl(csr_topk_main_kernel<CAP, 0>, grid, block, smem, s, pdl, m, x, st, h->d_pool, k, tie_higher); break;
+    }
 }
 
 CsrDevice csr_device(const Handle *h) {
     return CsrDevice{h->d_val, h->d_col16, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start,
                      h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols, (uint32_t)h->row_offset,
-                     half_mode(h) ? 1u : 0u};
+                     (uint32_t)value_type(h)};
 }
 
 __global__ void widen_u32_to_u64_kernel(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
@@ -152,7 +157,10 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
         const float *src = d_val_adopt ? d_val_adopt : d_val_src;
         TKS_CUDA(h, cudaMalloc(&h->d_val, nnz * sizeof(__half) + pad));
         TKS_CUDA(h, cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_val) + nnz * sizeof(__half), 0, pad, s));
-        if (nnz > 0) csr_vals_to_half_kernel<<<h->num_sms * 8, 256, 0, s>>>(src, nnz, reinterpret_cast<__half *>(h->d_val));
+        if (nnz > 0 && value_type(h) == TKS_VALUE_FP16)
+            csr_vals_to_half_kernel<<<h->num_sms * 8, 256, 0, s>>>(src, nnz, reinterpret_cast<__half *>(h->d_val));
+        if (nnz > 0 && value_type(h) == TKS_VALUE_BF16)
+            csr_vals_to_bf16_kernel<<<h->num_sms * 8, 256, 0, s>>>(src, nnz, reinterpret_cast<__nv_bfloat16 *>(h->d_val));
         if (d_val_adopt) {
             TKS_CUDA(h, cudaStreamSynchronize(s));
             cudaFree(d_val_adopt);
@@ -242,10 +250,11 @@ void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool
     uint64_t si = (h->nnz / 100u + (uint64_t)n_sample * kElemsPerIter - 1) / ((uint64_t)n_sample * kElemsPerIter);
     const uint32_t max_si = h->chunk_nnz / kElemsPerIter;
     const uint32_t sample_iters = (uint32_t)(si < 2 ? 2 : (si > max_si ? (max_si < 2 ? 2 : max_si) : si));
-    if (half_mode(h))
-        csr_sample_kernel<true><<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, sample_iters, k);
-    else
-        csr_sample_kernel<false><<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, sample_iters, k);
+    switch (value_type(h)) {
+        case TKS_VALUE_FP16: csr_sample_kernel<1><<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, sample_iters, k); break;
+        case TKS_VALUE_BF16: csr_sample_kernel<2><<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, sample_iters, k); break;
+        default: csr_sample_kernel<0><<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, sample_iters, k); break;
+    }
     // the three kernels of a query overlap their launch and set-up with the previous one's tail (programmatic
     // dependent launch); not while the dominant kernel is being timed alone
     const bool pdl = pdl_enabled() && !profile;
@@ -300,7 +309,7 @@ void launch_batched(Handle *h, uint32_t k, cudaStream_t s, bool profile) {
         a.sample_batches = (uint32_t)(sb < 8 ? 8 : (sb > 64 ? 64 : sb));
     }
     a.tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
-    batched_transpose_kernel<<<h->num_sms, 256, 0, s>>>(h->d_x, h->batch, h->cols, a.npass, h->d_xT, half_mode(h) ? 1 : 0);
+    batched_transpose_kernel<<<h->num_sms, 256, 0, s>>>(h->d_x, h->batch, h->cols, a.npass, h->d_xT, value_type(h));
     const uint32_t warps_per_cta = kBThreads / kWarp;
     uint32_t sgrid = ((a.n_sample + 3u) / 4u + warps_per_cta - 1) / warps_per_cta;
     if (sgrid > (uint32_t)h->num_sms) sgrid = (uint32_t)h->num_sms;
@@ -434,9 +443,11 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
         if (cfg->local_k < 1 || cfg->local_k > 64) { g_create_error = "local_k outside 1..64"; return TKS_EINVAL; }
         if (cfg->partitions < 1 || cfg->partitions > 4096) { g_create_error = "partitions outside 1..4096"; return TKS_EINVAL; }
     }
-    if (cfg->value_type != TKS_VALUE_FP32 && cfg->value_type != TKS_VALUE_FP16) { g_create_error = "unknown value_type"; return TKS_EINVAL; }
-    if (cfg->value_type == TKS_VALUE_FP16 && cfg->mode != TKS_MODE_FLOAT_CSR) {
-        g_create_error = "value_type FP16 belongs to FLOAT_CSR mode"; return TKS_EINVAL;
+    if (cfg->value_type != TKS_VALUE_FP32 && cfg->value_type != TKS_VALUE_FP16 && cfg->value_type != TKS_VALUE_BF16) {
+        g_create_error = "unknown value_type"; return TKS_EINVAL;
+    }
+    if (cfg->value_type != TKS_VALUE_FP32 && cfg->mode != TKS_MODE_FLOAT_CSR) {
+        g_create_error = "16-bit value types belong to FLOAT_CSR mode"; return TKS_EINVAL;
     }
     if (cfg->max_batch < 1 || cfg->max_batch > 1024) { g_create_error = "max_batch outside 1..1024"; return TKS_EINVAL; }
     int ndev = 0;
@@ -478,8 +489,9 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
         {
             size_t ss = ((size_t)cfg->max_cols + 1u) * 4u;
             if (ss < (8192u + kHistScratchWords) * 4u) ss = (8192u + kHistScratchWords) * 4u;
-            if ((e = cudaFuncSetAttribute(csr_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess ||
-                (e = cudaFuncSetAttribute(csr_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess)
+            if ((e = cudaFuncSetAttribute(csr_sample_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess ||
+                (e = cudaFuncSetAttribute(csr_sample_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess ||
+                (e = cudaFuncSetAttribute(csr_sample_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess)
                 return bail("sample smem attr", e);
             if ((e = cudaFuncSetAttribute(select_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(kSelectDynSmem))) != cudaSuccess ||
@@ -616,7 +628,11 @@ int tks_download_csr(tks_handle *h, uint64_t *ptr64, uint32_t *idx, float *val) 
         // the resident values are halves: fetch them into the upper half of the output and widen in place
         uint16_t *tmp = reinterpret_cast<uint16_t *>(val) + h->nnz;
         TKS_CUDA(h, cudaMemcpy(tmp, h->d_val, h->nnz * 2, cudaMemcpyDeviceToHost));
-        for (uint64_t i = 0; i < h->nnz; i++) val[i] = half_bits_to_float(tmp[i]);
+        if (value_type(h) == TKS_VALUE_BF16) {
+            for (uint64_t i = 0; i < h->nnz; i++) { const uint32_t w = (uint32_t)tmp[i] << 16; std::memcpy(&val[i], &w, 4); }
+        } else {
+            for (uint64_t i = 0; i < h->nnz; i++) val[i] = half_bits_to_float(tmp[i]);
+        }
     }
     if (idx) {
         // col16 holds column * 4: fetch the 16-bit words into the upper half of the output, widen in place

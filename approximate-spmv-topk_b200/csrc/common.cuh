@@ -1,6 +1,7 @@
 // common.cuh -- shared device/host helpers for libtopkspmv (sm_100a).
 #pragma once
 
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -61,7 +61,8 @@ __global__ void batched_transpose_kernel(const float *__restrict__ x, uint32_t b
         const uint32_t col = r % (cols + 1u), pass = r / (cols + 1u);
         const uint32_t gq = pass * kBqPerPass + q;
         float v = (col < cols && gq < batch) ? x[(size_t)gq * cols + col] : 0.0f;
-        if (half) v = __half2float(__float2half_rn(v));   // half-precision mode: the query is rounded like the values
+        if (half == 1) v = __half2float(__float2half_rn(v));            // 16-bit value modes: the query is rounded like the values
+        else if (half == 2) v = __bfloat162float(__float2bfloat16_rn(v));
         xT[i] = v;
     }
 }
@@ -156,7 +157,8 @@ __device__ __forceinline__ void batched_stream(const CsrDevice &m, const Batched
     const uint32_t nb_w = __reduce_max_sync(kFull, nb);
     L.acc[0] = L.acc[1] = L.acc[2] = L.acc[3] = 0.0f;
     L.have_row = false;
-    const bool half = m.val_half != 0;   // warp-uniform: values are halves, widened when staged
+    const bool half = m.val_type != 0;   // warp-uniform: 16-bit values (half or bfloat16), widened when staged
+    const bool bf16 = m.val_type == 2;
     const uint32_t vshift = half ? 1u : 2u;
     const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val) + (a0 << vshift) + ((l8 * 8u) << vshift);
     const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.col16 + a0) + l8 * 16u;
@@ -168,9 +170,14 @@ __device__ __forceinline__ void batched_stream(const CsrDevice &m, const Batched
             const U32x4 h4 = ldg_stream_128(p);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&h4.w[j]));
-                r.w[2 * j] = __float_as_uint(f2.x);
-                r.w[2 * j + 1] = __float_as_uint(f2.y);
+                if (bf16) {
+                    r.w[2 * j] = h4.w[j] << 16;
+                    r.w[2 * j + 1] = h4.w[j] & 0xFFFF0000u;
+                } else {
+                    const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&h4.w[j]));
+                    r.w[2 * j] = __float_as_uint(f2.x);
+                    r.w[2 * j + 1] = __float_as_uint(f2.y);
+                }
             }
         } else {
             r = ldg_stream_256(p);

@@ -21,6 +21,12 @@ __global__ void csr_vals_to_half_kernel(const float *__restrict__ val, uint64_t 
     for (; i < nnz; i += stride) out[i] = __float2half_rn(val[i]);
 }
 
+__global__ void csr_vals_to_bf16_kernel(const float *__restrict__ val, uint64_t nnz, __nv_bfloat16 *__restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < nnz; i += stride) out[i] = __float2bfloat16_rn(val[i]);
+}
+
 inline float half_bits_to_float(uint16_t bits) {
     __half_raw r;
     r.x = bits;

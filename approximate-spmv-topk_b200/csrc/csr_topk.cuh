@@ -43,7 +43,7 @@ constexpr uint32_t kSampleThreads = 256;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
 struct CsrDevice {
-    const void *val;               // fp32 [nnz], or IEEE half [nnz] when the kernels are instantiated with HALF
+    const void *val;               // fp32 [nnz], or IEEE half / bfloat16 [nnz] when the kernels are instantiated with VT = 1 / 2
     const uint16_t *col16;         // column * 4
     const uint8_t *rowbits;        // one row-start bit per non-zero
     const uint64_t *chunk_start;   // n_chunks + 1 entries
@@ -52,7 +52,7 @@ struct CsrDevice {
     uint32_t n_chunks;
     uint32_t cols;
     uint32_t row_offset;           // added to every reported row id
-    uint32_t val_half;             // 1: val holds halves (the batched kernel branches on it at run time)
+    uint32_t val_type;             // TKS_VALUE_*: 0 fp32, 1 half, 2 bfloat16 (the batched kernel branches on it at run time)
 };
 
 // Per-query scratch that lives in HBM; zeroed at creation and by the select kernel.
@@ -112,17 +112,19 @@ struct IterState {
     unsigned fm;   // ballot: lanes with >= 1 row start
 };
 
-template <bool HALF> struct ValRaw { using type = U32x8; };
-template <> struct ValRaw<true> { using type = U32x4; };
+// VT: storage type of the matrix values -- 0 fp32, 1 IEEE half, 2 bfloat16 (TKS_VALUE_*); the 16-bit types arrive as
+// one 128-bit load per lane and are widened to fp32 before the multiply.
+template <int VT> struct ValRaw { using type = U32x4; };
+template <> struct ValRaw<0> { using type = U32x8; };
 
-template <bool HALF>
-__device__ __forceinline__ typename ValRaw<HALF>::type ldg_stream_vals(const void *p) {
-    if constexpr (HALF) return ldg_stream_128(p);
+template <int VT>
+__device__ __forceinline__ typename ValRaw<VT>::type ldg_stream_vals(const void *p) {
+    if constexpr (VT != 0) return ldg_stream_128(p);
     else return ldg_stream_256(p);
 }
 
-template <bool MASKED, bool HALF>
-__device__ __forceinline__ void csr_iter(const typename ValRaw<HALF>::type &vraw, const U32x4 &craw, uint32_t rbits,
+template <bool MASKED, int VT>
+__device__ __forceinline__ void csr_iter(const typename ValRaw<VT>::type &vraw, const U32x4 &craw, uint32_t rbits,
                                          const uint8_t *__restrict__ xs_bytes, uint32_t zero_off, uint32_t lo,
                                          uint32_t hi, float carry_in, float &carry_out, IterState &o) {
     const unsigned lane = lane_id();
@@ -134,9 +136,12 @@ __device__ __forceinline__ void csr_iter(const typename ValRaw<HALF>::type &vraw
     for (int j = 0; j < 8; j++) {
         uint32_t c = (j & 1) ? (craw.w[j >> 1] >> 16) : (craw.w[j >> 1] & 0xFFFFu);   // column * 4
         float v;
-        if constexpr (HALF) {
+        if constexpr (VT == 1) {
             const float2 v2 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.w[j >> 1]));
             v = (j & 1) ? v2.y : v2.x;
+        } else if constexpr (VT == 2) {
+            // bfloat16 = the upper half of the fp32 word: one shift or mask
+            v = __uint_as_float((j & 1) ? (vraw.w[j >> 1] & 0xFFFF0000u) : (vraw.w[j >> 1] << 16));
         } else {
             v = __uint_as_float(vraw.w[j]);
         }
@@ -234,7 +239,7 @@ struct PoolSink {
 };
 
 // Stream one chunk (or its first max_iters iterations) through `sink`.
-template <bool HALF, typename Sink>
+template <int VT, typename Sink>
 __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint32_t c,
                                                   uint32_t max_iters, Sink &sink) {
     const unsigned lane = lane_id();
@@ -246,7 +251,7 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
     const uint32_t n_iter = truncated ? max_iters : (uint32_t)n_iter64;
     const uint32_t last_iter = (uint32_t)n_iter64 - 1;   // chunks are far smaller than 2^32 * 256 non-zeros
     const int32_t rel_s = (int32_t)(s - a0), rel_e = (int32_t)(e - a0);
-    constexpr uint32_t kValBytes = HALF ? 2u : 4u;
+    constexpr uint32_t kValBytes = VT != 0 ? 2u : 4u;
     const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val) + a0 * kValBytes + lane * (kEpl * kValBytes);
     const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.col16 + a0) + lane * 16u;
     const uint8_t *rp = m.rowbits + (a0 >> 3) + lane;
@@ -256,18 +261,18 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
     bool first_pending = true;
     float carry = 0.0f;
 
-    typename ValRaw<HALF>::type nv = ldg_stream_vals<HALF>(vp);
+    typename ValRaw<VT>::type nv = ldg_stream_vals<VT>(vp);
     U32x4 nc = ldg_stream_128(cp);
     uint32_t nr = ldg_stream_u8(rp);
 #pragma unroll 2
     for (uint32_t it = 0; it < n_iter; it++) {
-        const typename ValRaw<HALF>::type cv = nv;
+        const typename ValRaw<VT>::type cv = nv;
         const U32x4 cc = nc;
         const uint32_t cr = nr;
         vp += kElemsPerIter * kValBytes;
         cp += kElemsPerIter * 2u;
         rp += kElemsPerIter / 8u;
-        if (it + 1 < n_iter) { nv = ldg_stream_vals<HALF>(vp); nc = ldg_stream_128(cp); nr = ldg_stream_u8(rp); }
+        if (it + 1 < n_iter) { nv = ldg_stream_vals<VT>(vp); nc = ldg_stream_128(cp); nr = ldg_stream_u8(rp); }
         IterState o;
         float carry_out;
         if (it == 0 || it == last_iter) {
@@ -277,9 +282,9 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
             const int32_t l32 = rel_s - ebase, h32 = rel_e - ebase;
             const uint32_t lo = l32 < 0 ? 0u : (l32 > 8 ? 8u : (uint32_t)l32);
             const uint32_t hi = h32 < 0 ? 0u : (h32 > 8 ? 8u : (uint32_t)h32);
-            csr_iter<true, HALF>(cv, cc, cr, xs_bytes, zero_off, lo, hi, carry, carry_out, o);
+            csr_iter<true, VT>(cv, cc, cr, xs_bytes, zero_off, lo, hi, carry, carry_out, o);
         } else {
-            csr_iter<false, HALF>(cv, cc, cr, xs_bytes, zero_off, 0u, 8u, carry, carry_out, o);
+            csr_iter<false, VT>(cv, cc, cr, xs_bytes, zero_off, 0u, 8u, carry, carry_out, o);
         }
         carry = carry_out;
 
@@ -475,14 +480,15 @@ __device__ __forceinline__ uint32_t block_hist_threshold(LoadF load32, uint32_t 
 // edge of the bin that holds the k-th largest maximum -- still a lower bound) and publishes it in st->tau_key.
 // Dynamic shared memory: max((cols+1)*4, (n_sample + kHistScratchWords)*4) bytes.
 // --------------------------------------------------------------------------
-// The query as the kernels see it: rounded to half and widened again in the half-precision mode.
-template <bool HALF>
+// The query as the kernels see it: rounded to the storage type of the values and widened again.
+template <int VT>
 __device__ __forceinline__ float query_value(float x) {
-    if constexpr (HALF) return __half2float(__float2half_rn(x));
+    if constexpr (VT == 1) return __half2float(__float2half_rn(x));
+    else if constexpr (VT == 2) return __bfloat162float(__float2bfloat16_rn(x));
     else return x;
 }
 
-template <bool HALF>
+template <int VT>
 __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m, const float *__restrict__ x,
                                                                      RunState *st, uint32_t *sample_keys,
                                                                      uint32_t n_sample, uint32_t stride,
@@ -490,13 +496,13 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
     extern __shared__ __align__(16) uint8_t smem_raw[];
     pdl_trigger();   // the main kernel's CTAs may take the SMs this grid leaves and stage the query meanwhile
     float *xs = reinterpret_cast<float *>(smem_raw);
-    for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<HALF>(x[i]) : 0.0f;
+    for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<VT>(x[i]) : 0.0f;
     __syncthreads();
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
     if (gw < n_sample) {
         MaxSink sink{0.0f, false, neg_inf()};
         const uint32_t c = gw * stride;
-        if (c < m.n_chunks) csr_process_chunk<HALF>(m, smem_raw, c, sample_iters, sink);
+        if (c < m.n_chunks) csr_process_chunk<VT>(m, smem_raw, c, sample_iters, sink);
         uint32_t key = sink.any ? f32_to_ordered(sink.best) : 0u;
         key = __reduce_max_sync(kFull, key);
         if (lane_id() == 0) sample_keys[gw] = key;
@@ -524,7 +530,7 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
 // counter, reduces them, and keeps rows with score >= tau in a private
 // shared-memory buffer (sorted and cut to k only if it ever fills).
 // --------------------------------------------------------------------------
-template <int CAP, bool HALF>
+template <int CAP, int VT>
 __global__ void __launch_bounds__(CAP == 256 ? kMainThreadsWide : kMainThreads, 2)
 csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uint64_t *pool, uint32_t k,
                      int tie_higher) {
@@ -532,7 +538,7 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
     float *xs = reinterpret_cast<float *>(smem_raw);
     uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (((m.cols + 1u) * 4u + 15u) & ~15u));
     pdl_trigger();   // the select kernel's CTA may be set up while this grid drains
-    for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<HALF>(x[i]) : 0.0f;
+    for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<VT>(x[i]) : 0.0f;
     __syncthreads();
     pdl_wait();      // the query was complete before the sample kernel started; tau and the counters are not
 
@@ -553,7 +559,7 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
         c = __shfl_sync(kFull, c, 0);
         if (c >= m.n_chunks) break;
         sink.tau = fmaxf(sink.tau, tau_from_key(ld_relaxed_u32(&st->tau_key)));
-        csr_process_chunk<HALF>(m, smem_raw, c, 0xFFFFFFFFu, sink);
+        csr_process_chunk<VT>(m, smem_raw, c, 0xFFFFFFFFu, sink);
     }
 
     // hand the survivors to the global pool (filtered by the freshest bound)

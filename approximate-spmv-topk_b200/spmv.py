@@ -74,7 +74,7 @@ class SpMV(_Base):
 
     def __init__(self, ptr=None, idx=None, val=None, num_rows=0, num_cols=0, num_nnz=None, vec=None, k=100,
                  device=0, tie_higher=False, max_batch=1, max_cols=None, chunk_nnz=0, row_offset=0,
-                 profile_kernels=False, batch_mode=0, batch_pool_cap=0, batch_fma=False, half=False):
+                 profile_kernels=False, batch_mode=0, batch_pool_cap=0, batch_fma=False, half=False, bf16=False):
         # half: the reference's use_half_precision_gpu (host_spmv_topk_csr_gpu.cu:95): values and query rounded to
         # IEEE half; this engine still accumulates in fp32
         cfg = capi.default_config(mode=capi.MODE_FLOAT_CSR, device=device, max_batch=max_batch,
@@ -82,7 +82,7 @@ class SpMV(_Base):
                                   max_cols=max(1024, int(max_cols or num_cols or 1024)), chunk_nnz=chunk_nnz,
                                   profile_kernels=int(profile_kernels), batch_mode=int(batch_mode),
                                   batch_pool_cap=int(batch_pool_cap), batch_fma=int(batch_fma),
-                                  value_type=capi.VALUE_FP16 if half else capi.VALUE_FP32)
+                                  value_type=capi.VALUE_BF16 if bf16 else (capi.VALUE_FP16 if half else capi.VALUE_FP32))
         self._create(cfg)
         self.k = k
         self.num_rows, self.num_cols = int(num_rows), int(num_cols)

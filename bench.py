@@ -42,6 +42,8 @@ WORKLOADS = {
                  name="cfg2: synthetic 10M x 1024, gamma ~20 nnz/row, fp32 CSR, single query, k=100"),
     "cfg2h": dict(rows=10_000_000, cols=1024, deg=20, dist="gamma", mode="float", half=True,
                   name="cfg2h: cfg2 with half-precision matrix values and query (the reference's -a GPU mode), fp32 accumulation, k=100"),
+    "cfg2b": dict(rows=10_000_000, cols=1024, deg=20, dist="gamma", mode="float", bf16=True,
+                  name="cfg2b: cfg2 with bfloat16 matrix values and query, fp32 accumulation, k=100"),
     "cfg3": dict(rows=10_000_000, cols=1024, deg=20, dist="gamma", mode="fixed",
                  name="cfg3: cfg2 matrix in 20-bit BS-CSR packets, 32 partitions x local K=8 (FPGA semantics)"),
     "cfg4": dict(rows=200_000_000, cols=1024, deg=40, dist="uniform", mode="float",
@@ -213,7 +215,7 @@ def ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl_key = args.workload or "cfg2"
     wl = WORKLOADS[wl_key]
-    weak = wl_key in ("cfg2", "cfg2h")                          # cfg2: 10M rows PER RANK; cfg4 / cfg5: the stated total, sharded
+    weak = wl_key in ("cfg2", "cfg2h", "cfg2b")                          # cfg2: 10M rows PER RANK; cfg4 / cfg5: the stated total, sharded
     rows_total = (args.rows or wl["rows"]) * (world if weak else 1)
     cols = wl["cols"]
     shards = tks.sharding.plan_row_shards_even(rows_total, world)
@@ -234,8 +236,8 @@ def ours(args):
 
     # profile_kernels (two extra events around the dominant kernel, no launch overlap) is switched on only for the
     # roofline leg (measure_main_kernel); `value` and `e2e` are measured on the production path
-    half = bool(wl.get("half", False))
-    eng = tks.SpMV(num_cols=cols, k=K, device=local, half=half)
+    half = bool(wl.get("half", False) or wl.get("bf16", False))      # 16-bit values
+    eng = tks.SpMV(num_cols=cols, k=K, device=local, half=bool(wl.get("half", False)), bf16=bool(wl.get("bf16", False)))
     t0 = time.perf_counter()
     eng.generate_synthetic(r1 - r0, cols, wl["deg"], wl["dist"], seed=SEED, row_offset=r0)
     gen_s = time.perf_counter() - t0
@@ -331,7 +333,8 @@ def ours(args):
         line = {"metric": "topk_spmv_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak" if weak else "strong", "vs_baseline": None,
-                "dtype": "f16 values x f16 query, f32 products and sums" if half else "f32", "data": "synthetic",
+                "dtype": ("bf16 values x bf16 query, f32 products and sums" if wl.get("bf16") else
+                          "f16 values x f16 query, f32 products and sums" if half else "f32"), "data": "synthetic",
                 "config": {"workload": wl["name"] + (f", weak-scaled: {world} shards of {wl['rows']} rows" if weak and world > 1 else ""),
                            "rows": rows_total, "cols": cols, "nnz": nnz_total, "k": K,
                            "sharding": (f"rows/{world}, K candidates exchanged by " +

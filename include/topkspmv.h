@@ -45,6 +45,7 @@ extern "C" {
 /* storage type of the matrix values in float mode */
 #define TKS_VALUE_FP32 0
 #define TKS_VALUE_FP16 1
+#define TKS_VALUE_BF16 2   /* bfloat16 storage; not a mode of the reference */
 
 /* tie-break of equal scores in the final list */
 #define TKS_TIE_LOWER_INDEX 0  /* north-star contract                                          */
@@ -74,7 +75,8 @@ typedef struct tks_config {
                                    /* partial sum; 0 = the reference's semantics, bit for bit (default)          */
     int32_t value_type;            /* float mode: TKS_VALUE_FP32 (default) or TKS_VALUE_FP16 = the reference's          */
                                    /* half-precision GPU mode (-a, options.hpp:82; host_spmv_topk_csr_gpu.cu:132-136,   */
-                                   /* 151-153): matrix values and query rounded to IEEE half, fp32 accumulation         */
+                                   /* 151-153): matrix values and query rounded to IEEE half, fp32 accumulation;        */
+                                   /* TKS_VALUE_BF16: the same with bfloat16 storage                                    */
 } tks_config;
 
 typedef struct tks_handle tks_handle;

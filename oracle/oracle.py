@@ -95,6 +95,19 @@ def half_round(a):
     return np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
 
 
+def bf16_round(a):
+    """float -> bfloat16 (round to nearest even, what __float2bfloat16_rn does) -> float: keep the upper 16 bits."""
+    b = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    b = (b + np.uint64(0x7FFF) + ((b >> np.uint64(16)) & np.uint64(1))) & np.uint64(0xFFFF0000)
+    return b.astype(np.uint32).view(np.float32)
+
+
+def gold_topk_bf16(row, col, val, vec, k, sort=True):
+    """The gold on bfloat16-rounded inputs with fp32 accumulation: the statement of the engine's TKS_VALUE_BF16 mode
+    (not a mode of the reference).  A bf16 x bf16 product is exact in fp32 (8 + 8 significand bits)."""
+    return gold_topk_f32(row, col, bf16_round(val), bf16_round(vec), k, sort)
+
+
 def gold_topk_f16(row, col, val, vec, k, sort=True):
     """The gold on half-rounded inputs with fp32 accumulation: the statement of the engine's TKS_VALUE_FP16 mode.
     (The reference accumulates in half through cuSPARSE CUDA_R_16F / light_spmv<half>, which loses ~3 digits; the

@@ -348,3 +348,58 @@ def test_profile_switch_and_direct_host_results(cuda_required, tks, orc, cfg1):
     for r in (b, c, d):
         assert r[2] == a[2] and np.array_equal(r[1], a[1]) and np.array_equal(r[0].view(np.uint32), a[0].view(np.uint32))
     check_against_scores(a[1], a[0], a[2], orc.spmv_f32(x, y, v, vec, 10000), 100)
+
+
+# ---- bfloat16 value mode (not a mode of the reference) ---------------------------------------------
+
+def test_bf16_mode_matches_gold_on_bf16_rounded_inputs(cuda_required, tks, orc, cfg1):
+    x, y, v, ptr = cfg1
+    vb = orc.bf16_round(v)
+    with tks.SpMV(ptr, y, v, 10000, 1024, k=100, bf16=True) as s:
+        assert s.stats().device_bytes < 4.2 * v.size + 8 * 1024
+        _, _, dval = s.download_csr()
+        assert np.array_equal(dval.view(np.uint32), vb.view(np.uint32))       # resident values = RNE bfloat16
+        for qs in range(1, 4):
+            vec = make_query(1024, qs)
+            s.reset(vec)
+            s()
+            val, idx, cnt = s.read_result()
+            yref = orc.spmv_f32(x, y, vb, orc.bf16_round(vec), 10000)
+            check_against_scores(idx, val, cnt, yref, 100)
+            gi, gv = orc.gold_topk_bf16(x, y, v, vec, 100)
+            np.testing.assert_allclose(val, gv, rtol=RTOL)
+            fi, fv = orc.gold_topk_f32(x, y, v, vec, 100)                      # 8 significant bits: close, not equal
+            np.testing.assert_allclose(val, fv, rtol=2e-2)
+            assert len(set(idx.tolist()) & set(fi.tolist())) >= 80
+
+
+@pytest.mark.parametrize("k,chunk_nnz,tie_higher", [(1, 256, False), (100, 128, True), (1024, 4096, False)])
+def test_bf16_mode_k_chunks_and_exact_ties(cuda_required, tks, orc, cfg1, k, chunk_nnz, tie_higher):
+    x, y, v, ptr = cfg1
+    vec = make_query(1024, 12)
+    idx, val, cnt = run_engine(tks, ptr, y, v, 10000, 1024, vec, k, bf16=True, chunk_nnz=chunk_nnz)
+    check_against_scores(idx, val, cnt, orc.spmv_f32(x, y, orc.bf16_round(v), orc.bf16_round(vec), 10000), k)
+    # powers of two are exact in bfloat16: bit-exact incl. the tie order
+    rng = np.random.default_rng(k)
+    eptr, ex, ecol, eval_, evec = exact_matrix(3000, 256, rng, 7, 0.1)
+    yref = orc.spmv_f32(ex, ecol, eval_, evec, 3000)
+    with tks.SpMV(eptr, ecol, eval_, 3000, 256, vec=evec, k=64, tie_higher=tie_higher, chunk_nnz=256, bf16=True) as s:
+        s()
+        v2, i2, c2 = s.read_result()
+    cand = np.nonzero(np.diff(eptr.astype(np.int64)) > 0)[0]
+    order = cand[np.lexsort((cand if not tie_higher else -cand, -yref[cand].astype(np.float64)))][:64]
+    assert c2 == 64 and np.array_equal(i2, order.astype(np.uint32))
+    assert np.array_equal(v2.view(np.uint32), yref[order].view(np.uint32))
+
+
+def test_bf16_mode_batched_queries(cuda_required, tks, orc, cfg1):
+    x, y, v, ptr = cfg1
+    vecs = np.stack([make_query(1024, 60 + q) for q in range(4)])
+    with tks.SpMV(ptr, y, v, 10000, 1024, k=50, max_batch=8, bf16=True) as s:
+        s.reset(vecs)
+        s()
+        for q in range(4):
+            val, idx, cnt = s.read_result(q)
+            yref = orc.spmv_f32(x, y, orc.bf16_round(v), orc.bf16_round(vecs[q]), 10000)
+            check_against_scores(idx, val, cnt, yref, 50)
+            assert np.array_equal(val.view(np.uint32), yref[idx].view(np.uint32))
