@@ -657,33 +657,30 @@ __device__ __forceinline__ void peer_poll_and_merge(const PeerExchange &px, uint
         return;
     }
     const uint32_t cnt = *s_present < k ? *s_present : k;
-    if (n <= kSelectRankSortMax) {
-        const uint32_t items = (4u * n + kWarp - 1u) & ~(kWarp - 1u);
-        for (uint32_t w = tid; w < items; w += blockDim.x) {
-            const uint32_t i = w >> 2, part = w & 3u;
-            const uint64_t mine = (i < n) ? keys[i] : 0ull;
-            uint32_t r = 0;
-            for (uint32_t j = part; j < n; j += 4u) {
-                const uint64_t other = keys[j];
-                r += (other > mine) || (other == mine && j < i);
+    // Merge of `world` lists that are each sorted descending (absent = 0 at the tail): the output slot of a key is its
+    // position in its own list plus, for every other list, the number of keys ahead of it there -- one binary search
+    // per list (world x log2(k) probes per key instead of world x k comparisons).  Equal keys (only zeros, or the same
+    // row reported twice) are ordered by rank so that slots stay unique.
+    for (uint32_t t = tid; t < n; t += blockDim.x) {
+        const uint32_t r = t / k, i = t - r * k;
+        const uint64_t mine = keys[t];
+        uint32_t slot = i;
+        for (uint32_t o = 0; o < px.world; o++) {
+            if (o == r) continue;
+            const uint64_t *lst = keys + (size_t)o * k;
+            uint32_t lo = 0, hi = k;   // first index whose key is not ahead of `mine`
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const uint64_t other = lst[mid];
+                const bool ahead = (other > mine) || (other == mine && o < r);
+                if (ahead) lo = mid + 1; else hi = mid;
             }
-            r += __shfl_xor_sync(kFull, r, 1);
-            r += __shfl_xor_sync(kFull, r, 2);
-            if (part == 0 && i < n && r < cnt) {
-                res_keys[r] = mine;
-                res_idx[r] = key_row(mine, tie_higher);
-                res_val[r] = ordered_to_f32(key_score(mine));
-            }
+            slot += lo;
         }
-    } else {
-        uint32_t n2 = 32;
-        while (n2 < n) n2 <<= 1;
-        for (uint32_t i = n + tid; i < n2; i += blockDim.x) keys[i] = 0ull;
-        bitonic_sort_desc(keys, n2, tid, blockDim.x, [] { __syncthreads(); });
-        for (uint32_t i = tid; i < cnt; i += blockDim.x) {
-            res_keys[i] = keys[i];
-            res_idx[i] = key_row(keys[i], tie_higher);
-            res_val[i] = ordered_to_f32(key_score(keys[i]));
+        if (slot < cnt) {
+            res_keys[slot] = mine;
+            res_idx[slot] = key_row(mine, tie_higher);
+            res_val[slot] = ordered_to_f32(key_score(mine));
         }
     }
     for (uint32_t i = cnt + tid; i < k; i += blockDim.x) { res_keys[i] = 0ull; res_idx[i] = 0u; res_val[i] = 0.0f; }
