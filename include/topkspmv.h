@@ -186,17 +186,19 @@ int tks_merge_keys_batched_device(tks_handle *h, const uint64_t *d_keys, uint32_
                                   uint32_t batch, uint32_t k, void *cuda_stream);
 
 /* Candidate exchange over PEER MEMORY (NVLink / NVSwitch), one process per GPU: every rank maps every other rank's
- * exchange window through CUDA IPC; tks_run_exchange_async then runs the query on the local shard and ONE more kernel
- * stores the k candidates into every peer's window, waits for theirs and merges -- no NCCL launch and no separate merge
- * launch per query.  Protocol: tks_peer_init on every rank (fills a TKS_IPC_HANDLE_BYTES blob), exchange the blobs by
- * any means (torch.distributed all_gather_object), tks_peer_connect with all of them in rank order.  Float mode,
- * one query per run, world <= 8, world * k <= 2048.  A peer that never delivers makes tks_read_result fail after a
- * bounded wait instead of hanging the device.                                                                    */
+ * exchange window through CUDA IPC; tks_run_exchange_async then runs the query on the local shard with the SAME three
+ * launches as tks_run_async, but the select kernel stores its k candidates into every peer's window, waits for
+ * theirs and merges -- no NCCL launch and no merge launch per query; afterwards every rank holds the global top-k.
+ * Protocol: tks_peer_init on every rank (fills a TKS_IPC_HANDLE_BYTES blob), exchange the blobs by any means
+ * (torch.distributed all_gather_object), tks_peer_connect with all of them in rank order.  Float mode, one query
+ * per run, world <= 8, world * k <= 2048; every rank must make the same call for the same step.  A peer that never
+ * delivers makes tks_read_result fail after a bounded wait instead of hanging the device.                         */
 #define TKS_IPC_HANDLE_BYTES 128
 int tks_peer_init(tks_handle *h, uint32_t world, uint32_t rank, void *ipc_handle_out);
 int tks_peer_connect(tks_handle *h, const void *all_handles);
-int tks_run_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream);   /* = tks_run_async + tks_peer_exchange_async */
-int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream);  /* the exchange + merge kernel alone */
+int tks_run_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream);
+int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream);  /* exchange + merge as a stand-alone
+                                                                              launch after tks_run_async     */
 
 /* Switch tks_config.profile_kernels at run time: while on, tks_run brackets the dominant kernel with two extra
  * events (tks_stats.last_main_kernel_ms) and launches the kernels without overlap.                              */

@@ -171,3 +171,17 @@ def test_merge_partition_words_equals_reference_read_result(tks, orc, gen):
     iw[1, 1, 3], vw[1, 1, 3] = 2, 0            # val == 0: not a candidate
     val, idx = tks.capi.merge_partition_words(iw, vw, np.array([0, 10], np.uint32), 15, 8)
     assert idx.tolist() == [11, 5] and val.tolist() == [100, 100]
+
+
+def test_partition_shards_keep_the_unsharded_boundaries(tks):
+    """FPGA mode over several ranks: P / N partitions per rank, rows_per_part of the UNSHARDED matrix (ceil(N / P),
+    host_spmv_bscsr.cpp:136); the last shard may be short, every other one is exactly parts_per_rank * rows_per_part."""
+    plan = tks.distributed.plan_partition_shards
+    rpp, ppr, shards = plan(10_000_000, 32, 8)
+    assert (rpp, ppr) == (312500, 4) and shards[0] == (0, 1250000) and shards[-1] == (8750000, 10_000_000)
+    rpp, ppr, shards = plan(7777, 8, 2)
+    assert (rpp, ppr) == (973, 4) and shards == [(0, 3892), (3892, 7777)]
+    rpp, ppr, shards = plan(100, 32, 4)          # more partitions than some shards have rows: clipped, never negative
+    assert rpp == 4 and all(0 <= a <= b <= 100 for a, b in shards) and shards[-1][1] == 100
+    with pytest.raises(ValueError):
+        plan(1000, 32, 3)
