@@ -238,8 +238,13 @@ void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool
     const int variant = cap_variant_for_k(k);
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
     const CsrDevice m = csr_device(h);
-    uint32_t n_sample = h->n_chunks < (uint32_t)h->num_sms * 32u ? h->n_chunks : (uint32_t)h->num_sms * 32u;
-    if (n_sample > h->n_sample_cap) n_sample = h->n_sample_cap;
+    // one sample warp per resident warp slot of the main kernel's grid; large shards get more warps (up to the key
+    // buffer's capacity) so that the ~1 % sample stays a few iterations deep instead of a long latency-bound walk
+    uint64_t want = (uint64_t)h->num_sms * 32u;
+    const uint64_t for_depth4 = h->nnz / 100u / (4u * kElemsPerIter);
+    if (for_depth4 > want) want = for_depth4;
+    if (want > h->n_sample_cap) want = h->n_sample_cap;
+    uint32_t n_sample = h->n_chunks < want ? h->n_chunks : (uint32_t)want;
     const uint32_t stride = h->n_chunks / n_sample;
     size_t sample_smem = ((size_t)h->cols + 1u) * 4u;
     if (sample_smem < ((size_t)n_sample + kHistScratchWords) * 4u) sample_smem = ((size_t)n_sample + kHistScratchWords) * 4u;
