@@ -120,7 +120,18 @@ class SpMV(_Base):
         vec = np.ascontiguousarray(vec, np.float32)
         batch = 1 if vec.ndim == 1 else vec.shape[0]
         assert vec.shape[-1] == self.num_cols, "query length must equal num_cols"
-        check(capi.lib().tks_set_query(self.handle, _ptr(vec), batch), self.handle)
+        if batch == 1:
+            # one query: through a staging array whose ctypes pointer is made once (building `.ctypes` for a fresh array
+            # costs more host time than copying 4 KB)
+            st = self.__dict__.get("_q_stage")
+            if st is None or st[0].size != self.num_cols:
+                buf = np.empty(self.num_cols, np.float32)
+                st = self._q_stage = (buf, _ptr(buf))
+            st[0][:] = vec.reshape(-1)
+            qp = st[1]
+        else:
+            qp = _ptr(vec)
+        check(capi.lib().tks_set_query(self.handle, qp, batch), self.handle)
         self.batch = batch
         return 0
 
@@ -130,11 +141,12 @@ class SpMV(_Base):
 
     def read_result(self, query=0):
         """Returns (values float32[k], indices uint32[k], count)."""
-        idx = np.zeros(self.k, np.uint32)
-        val = np.zeros(self.k, np.float32)
-        cnt = C.c_uint32()
-        check(capi.lib().tks_read_result(self.handle, query, _ptr(idx), _ptr(val), C.byref(cnt)), self.handle)
-        return val, idx, cnt.value
+        out = self.__dict__.get("_out_stage")
+        if out is None or out[0].size < self.k:
+            idx, val, cnt = np.zeros(max(self.k, 1024), np.uint32), np.zeros(max(self.k, 1024), np.float32), C.c_uint32()
+            out = self._out_stage = (idx, val, cnt, _ptr(idx), _ptr(val), C.byref(cnt))   # pointers made once
+        check(capi.lib().tks_read_result(self.handle, query, out[3], out[4], out[5]), self.handle)
+        return out[1][:self.k].copy(), out[0][:self.k].copy(), out[2].value
 
     def result_keys_device(self, query=0):
         p, n = C.c_void_p(), C.c_uint32()
