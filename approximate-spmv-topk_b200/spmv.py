@@ -248,7 +248,12 @@ class SpMVFixed(_Base):
     def reset(self, vec32, debug=0):
         vec32 = np.ascontiguousarray(vec32, np.uint32)
         assert vec32.size == self.num_cols
-        check(capi.lib().tks_set_query(self.handle, _ptr(vec32), 1), self.handle)
+        st = self.__dict__.get("_q_stage")          # staging array whose ctypes pointer is made once
+        if st is None:
+            buf = np.empty(self.num_cols, np.uint32)
+            st = self._q_stage = (buf, _ptr(buf))
+        st[0][:] = vec32.reshape(-1)
+        check(capi.lib().tks_set_query(self.handle, st[1], 1), self.handle)
         return 0
 
     def reset_device(self, dptr, stream=0):
@@ -256,11 +261,13 @@ class SpMVFixed(_Base):
 
     def read_result(self):
         """Returns (raw values uint32[count], indices uint32[count]) -- may be shorter than k."""
-        idx = np.zeros(self.k, np.uint32)
-        val = np.zeros(self.k, np.uint32)
-        cnt = C.c_uint32()
-        check(capi.lib().tks_read_result(self.handle, 0, _ptr(idx), _ptr(val), C.byref(cnt)), self.handle)
-        return val[:cnt.value], idx[:cnt.value]
+        out = self.__dict__.get("_out_stage")
+        if out is None or out[0].size < self.k:
+            idx, val, cnt = np.zeros(max(self.k, 1024), np.uint32), np.zeros(max(self.k, 1024), np.uint32), C.c_uint32()
+            out = self._out_stage = (idx, val, cnt, _ptr(idx), _ptr(val), C.byref(cnt))   # pointers made once
+        check(capi.lib().tks_read_result(self.handle, 0, out[3], out[4], out[5]), self.handle)
+        n = out[2].value
+        return out[1][:n].copy(), out[0][:n].copy()
 
     def read_partition_results(self):
         Kp = self.cfg.local_k
