@@ -570,15 +570,18 @@ int bscsr_fetch(Handle *h) {
     }
     b->have_words = true;
     // read_result (host_spmv_bscsr.cpp:399-448) + sort_tuples: the host-side merge of host_api.cpp
+    // only the first k of the merged list are ever read (tks_read_result with the run's k): a partial sort is enough
     const uint32_t cap = b->P * (uint32_t)h->cfg.local_k * b->B;
-    b->merged_idx.assign(cap, 0u);
-    b->merged_val.assign(cap, 0u);
+    const uint32_t want = h->last_k && h->last_k < cap ? h->last_k : cap;
+    b->merged_idx.assign(want, 0u);
+    b->merged_val.assign(want, 0u);
     uint32_t n_out = 0;
     if (tks_merge_partition_words(b->P, (uint32_t)h->cfg.local_k, b->B, b->h_res_idx, b->h_res_val, b->first_row.data(),
-                                  h->cfg.tie_break, cap, b->merged_idx.data(), b->merged_val.data(), &n_out) != TKS_OK)
+                                  h->cfg.tie_break, want, b->merged_idx.data(), b->merged_val.data(), &n_out) != TKS_OK)
         return h->fail(TKS_EINVAL, "merge of the partition results failed");
-    b->merged_idx.resize(n_out);
-    b->merged_val.resize(n_out);
+    const uint32_t have = n_out < want ? n_out : want;
+    b->merged_idx.resize(have);
+    b->merged_val.resize(have);
     h->stats.last_candidates = n_out;
     return TKS_OK;
 }

@@ -39,35 +39,53 @@ int tks_merge_partition_words(uint32_t partitions, uint32_t local_k, uint32_t pa
                               uint32_t *idx_out, uint32_t *val_out, uint32_t *count) {
     if (!idx_words || !val_words || !first_row || !count) { g_host_error = "null argument"; return TKS_EINVAL; }
     if (packet_size == 0 || packet_size > 16) { g_host_error = "packet_size outside 1..16"; return TKS_EINVAL; }
-    struct Cand { uint32_t idx, val, order; };
-    std::vector<Cand> cand;
-    cand.reserve((size_t)partitions * local_k * 4);
-    for (uint32_t p = 0; p < partitions; p++)
-        for (uint32_t t = 0; t < local_k; t++)
-            for (uint32_t q = 0; q < packet_size; q++) {
-                const size_t o = ((size_t)p * local_k + t) * 16 + q;
-                const uint32_t v = val_words[o];
-                if (v == 0) continue;
-                cand.push_back({idx_words[o] + first_row[p], v, (uint32_t)cand.size()});
-            }
-    std::sort(cand.begin(), cand.end(), [](const Cand &l, const Cand &r) {
-        return l.idx != r.idx ? l.idx < r.idx : l.order < r.order;
-    });
-    std::vector<std::pair<uint32_t, uint32_t>> out;   // (idx, val): the first insertion of an index wins
-    out.reserve(cand.size());
-    for (size_t i = 0; i < cand.size(); i++)
-        if (i == 0 || cand[i].idx != cand[i - 1].idx) out.emplace_back(cand[i].idx, cand[i].val);
+    // candidates in insertion order; an open-addressing table keeps the first insertion of every index (the
+    // reference's unordered_map::insert, host:415-430); one 64-bit key per survivor orders them like sort_tuples:
+    // value descending, then index descending (TKS_TIE_HIGHER_INDEX) or ascending
+    static thread_local std::vector<uint64_t> keys, cand;
+    static thread_local std::vector<uint32_t> table;
     const bool higher = tie_break == TKS_TIE_HIGHER_INDEX;
-    std::sort(out.begin(), out.end(), [&](const std::pair<uint32_t, uint32_t> &l, const std::pair<uint32_t, uint32_t> &r) {
-        if (l.second != r.second) return l.second > r.second;
-        return higher ? (l.first > r.first) : (l.first < r.first);
-    });
-    *count = (uint32_t)out.size();   // all distinct candidates; the caller's buffers receive the first min(k, count)
-    if (idx_out && val_out)
-        for (uint32_t i = 0; i < k; i++) {
-            idx_out[i] = i < out.size() ? out[i].first : 0u;
-            val_out[i] = i < out.size() ? out[i].second : 0u;
+    cand.clear();
+    for (uint32_t p = 0; p < partitions; p++) {
+        const uint32_t base_row = first_row[p];
+        const uint32_t *iw = idx_words + (size_t)p * local_k * 16, *vw = val_words + (size_t)p * local_k * 16;
+        for (uint32_t t = 0; t < local_k; t++, iw += 16, vw += 16)
+            for (uint32_t q = 0; q < packet_size; q++)
+                if (vw[q] != 0) cand.push_back(((uint64_t)vw[q] << 32) | (uint32_t)(iw[q] + base_row));
+    }
+    size_t tsize = 64;
+    while (tsize < 2 * cand.size()) tsize <<= 1;
+    table.assign(tsize, 0u);   // idx + 1, 0 = empty (idx + 1 == 0 only for idx = 0xFFFFFFFF, which no 32-bit row count produces)
+    keys.clear();
+    for (const uint64_t c : cand) {
+        const uint32_t idx = (uint32_t)c;
+        size_t hpos = ((size_t)idx * 2654435761u >> 7) & (tsize - 1);
+        bool seen = false;
+        while (table[hpos] != 0) {
+            if (table[hpos] == idx + 1u) { seen = true; break; }
+            hpos = (hpos + 1) & (tsize - 1);
         }
+        if (seen) continue;
+        table[hpos] = idx + 1u;
+        keys.push_back((c & 0xFFFFFFFF00000000ull) | (higher ? idx : ~idx));
+    }
+    *count = (uint32_t)keys.size();   // all distinct candidates; the caller's buffers receive the first min(k, count)
+    if (idx_out && val_out) {
+        const size_t want = k < keys.size() ? k : keys.size();
+        auto desc = [](uint64_t l, uint64_t r) { return l > r; };
+        if (want < keys.size()) {   // the k largest first (linear), then only those are ordered
+            std::nth_element(keys.begin(), keys.begin() + (ptrdiff_t)want, keys.end(), desc);
+            std::sort(keys.begin(), keys.begin() + (ptrdiff_t)want, desc);
+        } else {
+            std::sort(keys.begin(), keys.end(), desc);
+        }
+        for (uint32_t i = 0; i < k; i++) {
+            const bool in = i < want;
+            const uint32_t lo = in ? (uint32_t)keys[i] : 0u;
+            idx_out[i] = in ? (higher ? lo : ~lo) : 0u;
+            val_out[i] = in ? (uint32_t)(keys[i] >> 32) : 0u;
+        }
+    }
     return TKS_OK;
 }
 
