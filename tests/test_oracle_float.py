@@ -71,3 +71,20 @@ def test_sort_tuples_order(orc):
     orc.lib().orc_sort_tuples_f32(5, idx, val)
     assert idx.tolist() == [7, 4, 3, 1, 9]          # equal values: higher index first
     assert val.tolist() == pytest.approx([0.9, 0.9, 0.5, 0.5, 0.1])
+
+
+def test_half_and_bf16_rounding_helpers_match_an_independent_conversion(orc):
+    """oracle.half_round / bf16_round state what the engine's 16-bit value modes do to every matrix value and to the
+    query (round to nearest even); torch's CPU conversions are an independent implementation of the same rounding."""
+    import torch
+    rng = np.random.default_rng(0)
+    a = np.concatenate([rng.random(200000).astype(np.float32), (rng.random(1000) * 1e-6).astype(np.float32),
+                        np.array([0.0, 1.0, 0.5, 1.0 + 2.0 ** -8, 1.0 + 2.0 ** -9, 1.0 + 3 * 2.0 ** -9, 65504.0], np.float32)])
+    t = torch.from_numpy(a)
+    assert np.array_equal(orc.half_round(a).view(np.uint32), t.to(torch.float16).to(torch.float32).numpy().view(np.uint32))
+    assert np.array_equal(orc.bf16_round(a).view(np.uint32), t.to(torch.bfloat16).to(torch.float32).numpy().view(np.uint32))
+    # a 16-bit x 16-bit product is exact in fp32 (11 + 11 and 8 + 8 significand bits): the engine's multiply never rounds
+    h, b = orc.half_round(a[:50000]), orc.bf16_round(a[:50000])
+    for u in (h, b):
+        p32 = u * u[::-1]
+        assert np.array_equal(p32.astype(np.float64), u.astype(np.float64) * u[::-1].astype(np.float64))
