@@ -185,3 +185,12 @@ def test_partition_shards_keep_the_unsharded_boundaries(tks):
     assert rpp == 4 and all(0 <= a <= b <= 100 for a, b in shards) and shards[-1][1] == 100
     with pytest.raises(ValueError):
         plan(1000, 32, 3)
+
+
+def test_exchange_mode_selection_without_peers(tks):
+    """One rank (or no NCCL): "auto" quietly uses the all-gather path, an explicit "peer" request is refused loudly."""
+    s = tks.ShardedSpMV(engine=None, k=10)
+    assert s.exchange_mode == "nccl" and s.world == 1
+    assert tks.ShardedSpMV(engine=None, k=10, exchange="none").exchange_mode == "none"
+    with pytest.raises(ValueError):
+        tks.ShardedSpMV(engine=None, k=10, exchange="peer")
