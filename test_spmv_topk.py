@@ -31,8 +31,9 @@ NITER = 30
 ZERO_INDEXED = False   # the generator writes 1-indexed files (create_matrices.py:120,124)
 
 # B200 designs: (name, extra flags).  They mirror the FPGA builds of test_spmv_topk.py:41-47
-# (32/26/21-bit fixed, float) plus the paper's 20-bit design, all from ONE binary.
-B200_DESIGNS = [("float", ""), ("20bit", "-f -w 20"), ("21bit", "-f -w 21"), ("26bit", "-f -w 26"), ("32bit", "-f -w 32")]
+# (32/26/21-bit fixed, float) plus the paper's 20-bit design and the GPU sweep's half-precision variant
+# (GPU_USE_HALF, test_spmv_topk.py:54), all from ONE binary.
+B200_DESIGNS = [("float", ""), ("half", "-a"), ("20bit", "-f -w 20"), ("21bit", "-f -w 21"), ("26bit", "-f -w 26"), ("32bit", "-f -w 32")]
 B200_EXE = str(ROOT / "build" / "topk-spmv-b200")
 
 B200_CMD = "{} {} -t {} -m {} -k {} {} {} | tee {}"
