@@ -3,6 +3,7 @@ coo2csr, symbol table.  No GPU, no compute calls."""
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -194,3 +195,19 @@ def test_exchange_mode_selection_without_peers(tks):
     assert tks.ShardedSpMV(engine=None, k=10, exchange="none").exchange_mode == "none"
     with pytest.raises(ValueError):
         tks.ShardedSpMV(engine=None, k=10, exchange="peer")
+
+
+def test_cpu_driver_runs_and_keeps_the_reference_csv_schema(gen, tmp_path):
+    """test_cpu.py (BASELINE config 1's driver): same CLI and CSV columns as the reference's (test_cpu.py:30-122)."""
+    import pandas as pd
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    x, y, v = gen.create_sparse_matrix(2000, 1024, 20, "gamma", seed=0)
+    mtx = tmp_path / gen.matrix_name(2000, 1024, 20, "gamma")
+    gen.write_mtx(mtx, x, y, v, 2000, 1024)
+    out = tmp_path / "cpu.csv"
+    r = subprocess.run([sys.executable, os.path.join(root, "test_cpu.py"), "-i", str(mtx), "-t", "3", "-k", "100", "-o", str(out),
+                        "-s", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-1000:]
+    df = pd.read_csv(out)
+    assert list(df.columns) == ["iter", "rows", "cols", "nnz", "K", "exec_time_ms"] and len(df) == 3
+    assert int(df.rows[0]) == 2000 and int(df.cols[0]) == 1024 and int(df.nnz[0]) == x.size and int(df.K[0]) == 100
