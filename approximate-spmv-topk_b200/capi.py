@@ -19,6 +19,7 @@ MODE_FLOAT_CSR, MODE_FIXED_BSCSR = 0, 1
 TIE_LOWER_INDEX, TIE_HIGHER_INDEX = 0, 1
 VALUE_FP32, VALUE_FP16, VALUE_BF16 = 0, 1, 2
 IPC_HANDLE_BYTES = 128
+SUBMIT_EXCHANGE, SUBMIT_QUERY_READY = 1, 2
 
 
 class TksConfig(C.Structure):
@@ -50,9 +51,10 @@ SYMBOLS = [
     "tks_version", "tks_default_config", "tks_create", "tks_destroy", "tks_last_error",
     "tks_upload_csr", "tks_upload_csr_device", "tks_upload_bscsr", "tks_generate_synthetic",
     "tks_upload_coo_fixed", "tks_upload_coo_fixed_device", "tks_bscsr_state_digest",
-    "tks_download_csr", "tks_set_query", "tks_set_query_device", "tks_run", "tks_run_async",
+    "tks_download_csr", "tks_download_csr_rows", "tks_set_query", "tks_set_query_device", "tks_run", "tks_run_async",
     "tks_read_result", "tks_read_partition_results", "tks_result_keys_device", "tks_merge_keys_device", "tks_merge_keys_batched_device",
     "tks_peer_init", "tks_peer_connect", "tks_run_exchange_async", "tks_peer_exchange_async",
+    "tks_submit", "tks_pipeline_wait", "tks_pipeline_stamps",
     "tks_set_profile_kernels", "tks_get_stats", "tks_bscsr_packet_size", "tks_fixed32_from_double", "tks_fixedW_from_fixed32",
     "tks_pack_bscsr", "tks_merge_partition_words", "tks_read_mtx", "tks_coo2csr",
     "tks_cache_write_csr", "tks_cache_read_csr", "tks_cache_write_bscsr", "tks_cache_read_bscsr",
@@ -88,6 +90,7 @@ def lib() -> C.CDLL:
     L.tks_bscsr_state_digest.argtypes = [vp, vp, C.c_uint32]
     L.tks_generate_synthetic.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64]
     L.tks_download_csr.argtypes = [vp, vp, vp, vp]
+    L.tks_download_csr_rows.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp, vp]
     L.tks_set_query.argtypes = [vp, vp, C.c_uint32]
     L.tks_set_query_device.argtypes = [vp, vp, C.c_uint32, vp]
     L.tks_run.argtypes = [vp, C.c_uint32, f32p, f32p]
@@ -101,6 +104,9 @@ def lib() -> C.CDLL:
     L.tks_peer_connect.argtypes = [vp, vp]
     L.tks_run_exchange_async.argtypes = [vp, C.c_uint32, vp]
     L.tks_peer_exchange_async.argtypes = [vp, C.c_uint32, vp]
+    L.tks_submit.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
+    L.tks_pipeline_wait.argtypes = [vp, vp]
+    L.tks_pipeline_stamps.argtypes = [vp, vp, C.c_uint32, u32p]
     L.tks_set_profile_kernels.argtypes = [vp, C.c_int]
     L.tks_get_stats.argtypes = [vp, C.POINTER(TksStats)]
     L.tks_bscsr_packet_size.argtypes = [C.c_int]

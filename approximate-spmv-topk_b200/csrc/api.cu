@@ -26,9 +26,30 @@ int cap_variant_for_k(uint32_t k) {
     return 3;
 }
 
-size_t main_smem_bytes(uint32_t cols, int variant) {
-    return (((cols + 1u) * 4u + 15u) & ~15u) + (size_t)(kCapThreads[variant] / 32) * kCaps[variant] * 8u;
+// CTA size of the main kernel inside a pipelined submit: 2 x 16 warps per SM at 56 registers leave 8192 registers per
+// SM, exactly one 128-thread CTA of the sample kernel, which runs BESIDE the previous query's main kernel there
+uint32_t env_u32(const char *name, uint32_t dflt) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? (uint32_t)std::strtoul(v, nullptr, 10) : dflt;
 }
+int pipe_threads(int variant) {
+    static const int t0 = (int)env_u32("TKS_PIPE_THREADS", 512u) / 32 * 32;   // A/B switch: 256..576
+    return variant == 0 ? (t0 < 256 ? 256 : (t0 > 576 ? 576 : t0)) : kCapThreads[variant];
+}
+int pipe_sample_threads() { static const int t = (int)env_u32("TKS_PIPE_SAMPLE_THREADS", 128u) / 32 * 32; return t < 32 ? 32 : (t > 256 ? 256 : t); }
+// L1 / shared-memory split requested for every kernel of the float path, in percent of the maximum (-1: the driver's
+// choice per kernel).  Kernels that share an SM in the pipelined path must agree on it: an SM cannot change the split
+// while CTAs are resident.
+int carveout_pct() { static const int v = std::getenv("TKS_CARVEOUT_PCT") ? std::atoi(std::getenv("TKS_CARVEOUT_PCT")) : -1; return v; }
+
+size_t main_smem_bytes(uint32_t cols, int variant, int threads = 0) {
+    if (threads == 0) threads = kCapThreads[variant];
+    return (((cols + 1u) * 4u + 15u) & ~15u) + (size_t)(threads / 32) * kCaps[variant] * 8u;
+}
+
+// bounds of the device-side waits (peer records, pipelined hand-overs); raise them under compute-sanitizer
+uint32_t spin_timeout_ms() { static const uint32_t v = env_u32("TKS_SPIN_TIMEOUT_MS", 2000u); return v; }
+uint32_t tau_wait_us() { static const uint32_t v = env_u32("TKS_TAU_WAIT_US", 20000u); return v; }
 
 inline bool half_mode(const Handle *h) { return h->cfg.value_type != TKS_VALUE_FP32; }   // 16-bit storage (half or bfloat16)
 inline int value_type(const Handle *h) { return h->cfg.value_type; }
@@ -39,12 +60,25 @@ cudaError_t prep_main_t(Handle *h, int variant) {
     cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
+    // Kernels of different queries share an SM in the pipelined path (sample and select CTAs beside main-kernel CTAs).
+    // An SM cannot change its L1 / shared-memory split while CTAs are resident, so every kernel of the path asks for
+    // the same split -- all shared memory (the matrix stream bypasses L1 anyway) -- or a CTA that needs a larger
+    // carve-out than the resident kernel's would wait for the SM to drain.
+    if (carveout_pct() >= 0) {
+        e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP, VT>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct());
+        if (e != cudaSuccess) return e;
+    }
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, VT>, kCapThreads[variant],
                                                       smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     h->main_grid[variant] = per_sm * h->num_sms;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, VT>, pipe_threads(variant),
+                                                      main_smem_bytes(h->cfg.max_cols, variant, pipe_threads(variant)));
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    h->pipe_main_grid[variant] = per_sm * h->num_sms;
     return cudaSuccess;
 }
 
@@ -57,16 +91,29 @@ cudaError_t prep_main(Handle *h, int variant) {
     }
 }
 
+// seq != 0: a pipelined submit (512-thread CTAs for the k <= 128 variant, hand-over by sequence numbers)
 template <int CAP>
-void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, RunState *st, uint32_t k,
-                 cudaStream_t s, bool pdl) {
-    size_t smem = main_smem_bytes(m.cols, variant);
+void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, RunState *st, uint64_t *pool, uint32_t k,
+                 cudaStream_t s, bool pdl, uint32_t seq = 0, uint64_t *stamp = nullptr) {
+    const int threads = seq ? pipe_threads(variant) : kCapThreads[variant];
+    size_t smem = main_smem_bytes(m.cols, variant, threads);
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
-    const dim3 grid(h->main_grid[variant]), block(kCapThreads[variant]);
+    const dim3 grid(seq ? h->pipe_main_grid[variant] : h->main_grid[variant]), block(threads);
+    const uint32_t tw = tau_wait_us();
     switch (value_type(h)) {
-        case TKS_VALUE_FP16: launch_pdl(csr_topk_main_kernel<CAP, 1>, grid, block, smem, s, pdl, m, x, st, h->d_pool, k, tie_higher); break;
-        case TKS_VALUE_BF16: launch_pdl(csr_topk_main_kernel<CAP, 2>, grid, block, smem, s, pdl, m, x, st, h->d_pool, k, tie_higher); break;
-        default: launch_pdl(csr_topk_main_kernel<CAP, 0>, grid, block, smem, s, pdl, m, x, st, h->d_pool, k, tie_higher); break;
+        case TKS_VALUE_FP16: launch_pdl(csr_topk_main_kernel<CAP, 1>, grid, block, smem, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
+        case TKS_VALUE_BF16: launch_pdl(csr_topk_main_kernel<CAP, 2>, grid, block, smem, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
+        default: launch_pdl(csr_topk_main_kernel<CAP, 0>, grid, block, smem, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
+    }
+}
+
+void launch_main_variant(Handle *h, int variant, const CsrDevice &m, const float *x, RunState *st, uint64_t *pool,
+                         uint32_t k, cudaStream_t s, bool pdl, uint32_t seq = 0, uint64_t *stamp = nullptr) {
+    switch (variant) {
+        case 0: launch_main<256>(h, 0, m, x, st, pool, k, s, pdl, seq, stamp); break;
+        case 1: launch_main<512>(h, 1, m, x, st, pool, k, s, pdl, seq, stamp); break;
+        case 2: launch_main<1024>(h, 2, m, x, st, pool, k, s, pdl, seq, stamp); break;
+        default: launch_main<2048>(h, 3, m, x, st, pool, k, s, pdl, seq, stamp); break;
     }
 }
 
@@ -232,14 +279,11 @@ int check_float_upload(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, ui
     return TKS_OK;
 }
 
-// sample -> main -> select for query q alone (also the fallback of a batched query whose pool overflowed)
-void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool profile, bool to_host = false,
-                         const PeerExchange *px = nullptr, uint32_t seq = 0) {
-    const int variant = cap_variant_for_k(k);
-    const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
-    const CsrDevice m = csr_device(h);
-    // one sample warp per resident warp slot of the main kernel's grid; large shards get more warps (up to the key
-    // buffer's capacity) so that the ~1 % sample stays a few iterations deep instead of a long latency-bound walk
+// The sample kernel of one query: one warp per resident warp slot of the main kernel's grid; large shards get more
+// warps (up to the key buffer's capacity) so that the ~1 % sample stays a few iterations deep instead of a long
+// latency-bound walk.  threads: CTA size (256 alone on the device, 128 beside a running main kernel).
+void launch_sample(Handle *h, const CsrDevice &m, const float *x, RunState *st, uint32_t *sample_keys, uint32_t k,
+                   cudaStream_t s, uint32_t threads, uint32_t seq, uint64_t *stamp = nullptr) {
     uint64_t want = (uint64_t)h->num_sms * 32u;
     const uint64_t for_depth4 = h->nnz / 100u / (4u * kElemsPerIter);
     if (for_depth4 > want) want = for_depth4;
@@ -247,45 +291,90 @@ void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool
     uint32_t n_sample = h->n_chunks < want ? h->n_chunks : (uint32_t)want;
     const uint32_t stride = h->n_chunks / n_sample;
     size_t sample_smem = ((size_t)h->cols + 1u) * 4u;
-    if (sample_smem < ((size_t)n_sample + kHistScratchWords) * 4u) sample_smem = ((size_t)n_sample + kHistScratchWords) * 4u;
-    const float *x = h->d_x + (size_t)q * h->cols;
-    RunState *st = h->d_state + q;
-    const uint32_t sgrid = (n_sample * kWarp + kSampleThreads - 1) / kSampleThreads;
+    if (sample_smem < (size_t)kHistScratchWords * 4u) sample_smem = (size_t)kHistScratchWords * 4u;
+    const uint32_t sgrid = (n_sample * kWarp + threads - 1) / threads;
     // the sample grows with the matrix (~1 % of the non-zeros) so that the candidates stay a few thousand
     uint64_t si = (h->nnz / 100u + (uint64_t)n_sample * kElemsPerIter - 1) / ((uint64_t)n_sample * kElemsPerIter);
     const uint32_t max_si = h->chunk_nnz / kElemsPerIter;
     const uint32_t sample_iters = (uint32_t)(si < 2 ? 2 : (si > max_si ? (max_si < 2 ? 2 : max_si) : si));
     switch (value_type(h)) {
-        case TKS_VALUE_FP16: csr_sample_kernel<1><<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, sample_iters, k); break;
-        case TKS_VALUE_BF16: csr_sample_kernel<2><<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, sample_iters, k); break;
-        default: csr_sample_kernel<0><<<sgrid, kSampleThreads, sample_smem, s>>>(m, x, st, h->d_sample_keys, n_sample, stride, sample_iters, k); break;
+        case TKS_VALUE_FP16: csr_sample_kernel<1><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
+        case TKS_VALUE_BF16: csr_sample_kernel<2><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
+        default: csr_sample_kernel<0><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
     }
+}
+
+// sample -> main -> select for query q alone (also the fallback of a batched query whose pool overflowed)
+void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool profile, bool to_host = false,
+                         const PeerExchange *px = nullptr, uint32_t seq = 0) {
+    const int variant = cap_variant_for_k(k);
+    const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
+    const CsrDevice m = csr_device(h);
+    const float *x = h->d_x + (size_t)q * h->cols;
+    RunState *st = h->d_state + q;
+    launch_sample(h, m, x, st, h->d_sample_keys, k, s, kSampleThreads, 0u);
     // the three kernels of a query overlap their launch and set-up with the previous one's tail (programmatic
     // dependent launch); not while the dominant kernel is being timed alone
     const bool pdl = pdl_enabled() && !profile;
     if (profile) cudaEventRecord(h->evm0, s);
-    switch (variant) {
-        case 0: launch_main<256>(h, 0, m, x, st, k, s, pdl); break;
-        case 1: launch_main<512>(h, 1, m, x, st, k, s, pdl); break;
-        case 2: launch_main<1024>(h, 2, m, x, st, k, s, pdl); break;
-        default: launch_main<2048>(h, 3, m, x, st, k, s, pdl); break;
-    }
+    launch_main_variant(h, variant, m, x, st, h->d_pool, k, s, pdl);
     if (profile) cudaEventRecord(h->evm1, s);
     // to_host (blocking tks_run, one query): indices, scores and the count go straight into the pinned host block the
     // caller reads (zero-copy stores, 1.2 KB), which saves the device-to-host copy after the kernel; the keys stay in HBM
     uint32_t *o_idx = (to_host ? h->h_res_idx : h->d_res_idx) + (size_t)q * h->kmax;
     float *o_val = (to_host ? h->h_res_val : h->d_res_val) + (size_t)q * h->kmax;
     uint32_t *o_cnt = (to_host ? h->h_res_count : h->d_res_count) + q;
+    h->res_on_host = to_host;
     if (px && px->world > 1) {
         // several GPUs: local select + exchange over the peer windows + merge in this one launch
         launch_pdl(select_topk_kernel<true>, dim3(1), dim3(kSelectThreads), (size_t)kSelectDynSmem, s, pdl,
                    (const uint64_t *)h->d_pool, 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
-                   o_idx, o_val, 0u, o_cnt, (uint32_t *)nullptr, *px, seq);
+                   o_idx, o_val, 0u, o_cnt, (uint32_t *)nullptr, *px, seq, 0u, 0u, (uint64_t *)nullptr, kSelectSmemKeys);
         return;
     }
     launch_pdl(select_topk_kernel<false>, dim3(1), dim3(kSelectThreads), (size_t)kSelectDynSmem, s, pdl,
                (const uint64_t *)h->d_pool, 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys + (size_t)q * h->kmax,
-               o_idx, o_val, 0u, o_cnt, (uint32_t *)nullptr, PeerExchange{}, 0u);
+               o_idx, o_val, 0u, o_cnt, (uint32_t *)nullptr, PeerExchange{}, 0u, 0u, 0u, (uint64_t *)nullptr, kSelectSmemKeys);
+}
+
+// ---- pipelined submits -------------------------------------------------------------------------------------------
+
+int pipe_init(Handle *h) {
+    if (h->d_pipe_state) return TKS_OK;
+    int lo = 0, hi = 0;
+    TKS_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically lowest = greatest priority
+    // The block scheduler serves pending grids by priority, then age, and does not look past one whose CTAs do not fit:
+    // the select CTA of the previous query (too large to sit beside two main-kernel CTAs, so it is pending until one
+    // retires) must not stand in front of the sample CTAs of the next query (small, they fit at once).  Hence sample >
+    // select > the caller's stream (main kernels).
+    int sel = hi + (int)env_u32("TKS_PIPE_SELECT_PRIO_DELTA", 1u);
+    if (sel > lo) sel = lo;
+    TKS_CUDA(h, cudaStreamCreateWithPriority(&h->pipe_sample_stream, cudaStreamNonBlocking, hi));
+    TKS_CUDA(h, cudaStreamCreateWithPriority(&h->pipe_select_stream, cudaStreamNonBlocking, sel));
+    for (int i = 0; i < Handle::kPipeSlots; i++) {
+        TKS_CUDA(h, cudaEventCreateWithFlags(&h->pipe_ev_done[i], cudaEventDisableTiming));
+        TKS_CUDA(h, cudaMalloc(&h->d_pipe_pool[i], h->pool_cap * sizeof(uint64_t)));
+    }
+    TKS_CUDA(h, cudaEventCreateWithFlags(&h->pipe_ev_query, cudaEventDisableTiming));
+    TKS_CUDA(h, cudaMalloc(&h->d_pipe_sample_keys, h->n_sample_cap * sizeof(uint32_t)));
+    const size_t stamp_bytes = (size_t)Handle::kPipeStamps * kStampWords * sizeof(uint64_t);
+    TKS_CUDA(h, cudaMalloc(&h->d_pipe_stamps, stamp_bytes));
+    TKS_CUDA(h, cudaMemset(h->d_pipe_stamps, 0, stamp_bytes));
+    TKS_CUDA(h, cudaMallocHost(&h->h_pipe_stamps, stamp_bytes));
+    TKS_CUDA(h, cudaMalloc(&h->d_pipe_state, Handle::kPipeSlots * sizeof(RunState)));
+    TKS_CUDA(h, cudaMemset(h->d_pipe_state, 0, Handle::kPipeSlots * sizeof(RunState)));
+    return TKS_OK;
+}
+
+// Block the host until every pipelined query in flight has been selected (the un-pipelined entry points share the
+// result block with them).
+int pipe_drain(Handle *h) {
+    for (int i = 0; i < Handle::kPipeSlots; i++) {
+        if (!h->pipe_busy[i]) continue;
+        TKS_CUDA(h, cudaEventSynchronize(h->pipe_ev_done[i]));
+        h->pipe_busy[i] = false;
+    }
+    return TKS_OK;
 }
 
 template <bool SAMPLE>
@@ -325,7 +414,8 @@ void launch_batched(Handle *h, uint32_t k, cudaStream_t s, bool profile) {
     if (profile) cudaEventRecord(h->evm1, s);
     select_topk_kernel<false><<<h->batch, kSelectThreads, kSelectDynSmem, s>>>(
         h->d_bpool, h->bpool_cap, h->d_state, 0u, h->bpool_cap, k, a.tie_higher, h->d_res_keys, h->d_res_idx,
-        h->d_res_val, h->kmax, h->d_res_count, h->d_pass_counter, PeerExchange{}, 0u);
+        h->d_res_val, h->kmax, h->d_res_count, h->d_pass_counter, PeerExchange{}, 0u, 0u, 0u, nullptr, kSelectSmemKeys);
+    h->res_on_host = false;
 }
 
 bool use_batched(const Handle *h) {
@@ -333,12 +423,19 @@ bool use_batched(const Handle *h) {
            batched_smem_bytes(h->cols) <= batched_smem_bytes((uint32_t)h->cfg.max_cols);
 }
 
+// 4 + 4 bytes per non-zero in fp32, 2 + 4 in the half-precision mode, + row_ptr
+uint64_t algorithmic_matrix_bytes(const Handle *h) {
+    return h->nnz * (half_mode(h) ? 6ull : 8ull) + (h->rows + 1) * (h->nnz > 0xFFFFFFFFull ? 8ull : 4ull);
+}
+
 int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false, bool to_host = false) {
     if (!h->have_matrix) return h->fail(TKS_ESTATE, "no matrix uploaded");
     if (!h->have_query) return h->fail(TKS_ESTATE, "no query set");
     if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k=%u outside 1..%u", k, h->kmax);
-    // 4 + 4 bytes per non-zero in fp32, 2 + 4 in the half-precision mode
-    const uint64_t matrix_bytes = h->nnz * (half_mode(h) ? 6ull : 8ull) + (h->rows + 1) * (h->nnz > 0xFFFFFFFFull ? 8ull : 4ull);
+    int rcd = pipe_drain(h);
+    if (rcd) return rcd;
+    h->last_run_pipelined = false;
+    const uint64_t matrix_bytes = algorithmic_matrix_bytes(h);
     if (use_batched(h)) {
         launch_batched(h, k, s, profile);
         h->last_run_batched = true;
@@ -493,7 +590,7 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
         if ((e = prep_main<2048>(h, 3)) != cudaSuccess) return bail("prep_main<2048>", e);
         {
             size_t ss = ((size_t)cfg->max_cols + 1u) * 4u;
-            if (ss < (8192u + kHistScratchWords) * 4u) ss = (8192u + kHistScratchWords) * 4u;
+            if (ss < (size_t)kHistScratchWords * 4u) ss = (size_t)kHistScratchWords * 4u;
             if ((e = cudaFuncSetAttribute(csr_sample_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess ||
                 (e = cudaFuncSetAttribute(csr_sample_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess ||
                 (e = cudaFuncSetAttribute(csr_sample_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess)
@@ -503,6 +600,13 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
                 (e = cudaFuncSetAttribute(select_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(kSelectDynSmem))) != cudaSuccess)
                 return bail("select smem attr", e);
+            const int mx = carveout_pct();
+            if (mx >= 0 && ((e = cudaFuncSetAttribute(csr_sample_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, mx)) != cudaSuccess ||
+                (e = cudaFuncSetAttribute(csr_sample_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, mx)) != cudaSuccess ||
+                (e = cudaFuncSetAttribute(csr_sample_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, mx)) != cudaSuccess ||
+                (e = cudaFuncSetAttribute(select_topk_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx)) != cudaSuccess ||
+                (e = cudaFuncSetAttribute(select_topk_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx)) != cudaSuccess))
+                return bail("carve-out attr", e);
         }
         if (cfg->max_batch > 1 && batched_smem_bytes((uint32_t)cfg->max_cols) <= (size_t)prop.sharedMemPerBlockOptin) {
             const int bs = (int)batched_smem_bytes((uint32_t)cfg->max_cols);
@@ -532,6 +636,15 @@ void tks_destroy(tks_handle *h) {
     cudaFree(h->d_res_keys); cudaFree(h->d_res_block);
     cudaFree(h->d_xT); cudaFree(h->d_bpool); cudaFree(h->d_pass_counter); cudaFree(h->d_bsample_keys);
     cudaFreeHost(h->h_res_block); cudaFreeHost(h->h_x);
+    cudaFree(h->d_pipe_state); cudaFree(h->d_pipe_sample_keys); cudaFree(h->d_pipe_stamps);
+    cudaFreeHost(h->h_pipe_stamps);
+    for (int i = 0; i < tks::Handle::kPipeSlots; i++) {
+        cudaFree(h->d_pipe_pool[i]);
+        if (h->pipe_ev_done[i]) cudaEventDestroy(h->pipe_ev_done[i]);
+    }
+    if (h->pipe_ev_query) cudaEventDestroy(h->pipe_ev_query);
+    if (h->pipe_sample_stream) cudaStreamDestroy(h->pipe_sample_stream);
+    if (h->pipe_select_stream) cudaStreamDestroy(h->pipe_select_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_query) cudaEventDestroy(h->ev_query);
@@ -623,29 +736,39 @@ int tks_generate_synthetic(tks_handle *h, uint64_t rows, uint32_t cols, uint32_t
     return rc;
 }
 
-int tks_download_csr(tks_handle *h, uint64_t *ptr64, uint32_t *idx, float *val) {
+int tks_download_csr_rows(tks_handle *h, uint64_t row_begin, uint64_t row_end, uint64_t *ptr64, uint32_t *idx, float *val) {
     if (!h) return TKS_EINVAL;
     if (!h->have_matrix || !h->d_ptr64) return h->fail(TKS_ESTATE, "no CSR matrix resident");
+    if (row_begin > row_end || row_end > h->rows) return h->fail(TKS_EINVAL, "row range outside 0..rows");
     TKS_CUDA(h, cudaSetDevice(h->device));
-    if (ptr64) TKS_CUDA(h, cudaMemcpy(ptr64, h->d_ptr64, (h->rows + 1) * 8, cudaMemcpyDeviceToHost));
-    if (val && !half_mode(h)) TKS_CUDA(h, cudaMemcpy(val, h->d_val, h->nnz * 4, cudaMemcpyDeviceToHost));
+    uint64_t ends[2] = {0, 0};
+    TKS_CUDA(h, cudaMemcpy(&ends[0], h->d_ptr64 + row_begin, 8, cudaMemcpyDeviceToHost));
+    TKS_CUDA(h, cudaMemcpy(&ends[1], h->d_ptr64 + row_end, 8, cudaMemcpyDeviceToHost));
+    const uint64_t b = ends[0], n = ends[1] - ends[0];
+    if (ptr64) TKS_CUDA(h, cudaMemcpy(ptr64, h->d_ptr64 + row_begin, (row_end - row_begin + 1) * 8, cudaMemcpyDeviceToHost));
+    if (val && !half_mode(h)) TKS_CUDA(h, cudaMemcpy(val, reinterpret_cast<const float *>(h->d_val) + b, n * 4, cudaMemcpyDeviceToHost));
     if (val && half_mode(h)) {
         // the resident values are halves: fetch them into the upper half of the output and widen in place
-        uint16_t *tmp = reinterpret_cast<uint16_t *>(val) + h->nnz;
-        TKS_CUDA(h, cudaMemcpy(tmp, h->d_val, h->nnz * 2, cudaMemcpyDeviceToHost));
+        uint16_t *tmp = reinterpret_cast<uint16_t *>(val) + n;
+        TKS_CUDA(h, cudaMemcpy(tmp, reinterpret_cast<const uint16_t *>(h->d_val) + b, n * 2, cudaMemcpyDeviceToHost));
         if (value_type(h) == TKS_VALUE_BF16) {
-            for (uint64_t i = 0; i < h->nnz; i++) { const uint32_t w = (uint32_t)tmp[i] << 16; std::memcpy(&val[i], &w, 4); }
+            for (uint64_t i = 0; i < n; i++) { const uint32_t w = (uint32_t)tmp[i] << 16; std::memcpy(&val[i], &w, 4); }
         } else {
-            for (uint64_t i = 0; i < h->nnz; i++) val[i] = half_bits_to_float(tmp[i]);
+            for (uint64_t i = 0; i < n; i++) val[i] = half_bits_to_float(tmp[i]);
         }
     }
     if (idx) {
         // col16 holds column * 4: fetch the 16-bit words into the upper half of the output, widen in place
-        uint16_t *tmp = reinterpret_cast<uint16_t *>(idx) + h->nnz;
-        TKS_CUDA(h, cudaMemcpy(tmp, h->d_col16, h->nnz * 2, cudaMemcpyDeviceToHost));
-        for (uint64_t i = 0; i < h->nnz; i++) idx[i] = (uint32_t)tmp[i] >> 2;
+        uint16_t *tmp = reinterpret_cast<uint16_t *>(idx) + n;
+        TKS_CUDA(h, cudaMemcpy(tmp, h->d_col16 + b, n * 2, cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < n; i++) idx[i] = (uint32_t)tmp[i] >> 2;
     }
     return TKS_OK;
+}
+
+int tks_download_csr(tks_handle *h, uint64_t *ptr64, uint32_t *idx, float *val) {
+    if (!h) return TKS_EINVAL;
+    return tks_download_csr_rows(h, 0, h->rows, ptr64, idx, val);
 }
 
 int tks_set_query_device(tks_handle *h, const void *d_vec, uint32_t batch, void *cuda_stream) {
@@ -750,6 +873,8 @@ int tks_read_result(tks_handle *h, uint32_t query, uint32_t *idx_out, void *val_
         if (h->last_k == 0) return h->fail(TKS_ESTATE, "no run yet");
         TKS_CUDA(h, cudaSetDevice(h->device));
         TKS_CUDA(h, cudaDeviceSynchronize());
+        int rcd = pipe_drain(h);
+        if (rcd) return rcd;
         int rcf = fetch_results_async(h, h->stream);
         if (rcf) return rcf;
         TKS_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -762,7 +887,8 @@ int tks_read_result(tks_handle *h, uint32_t query, uint32_t *idx_out, void *val_
     }
     if (query >= h->batch) return h->fail(TKS_EINVAL, "query index out of range");
     if (h->h_res_count[query] == kPeerTimeout)
-        return h->fail(TKS_ECUDA, "peer exchange timed out: a rank of the box never delivered its candidates");
+        return h->fail(TKS_ECUDA, "device-side wait timed out (TKS_SPIN_TIMEOUT_MS): a rank of the box never delivered its "
+                                  "candidates, or the main kernel of a pipelined submit never completed");
     const uint32_t k = h->last_k;
     std::memcpy(idx_out, h->h_res_idx + (size_t)query * h->kmax, k * 4);
     std::memcpy(val_out, h->h_res_val + (size_t)query * h->kmax, k * 4);
@@ -809,7 +935,8 @@ int tks_merge_keys_device(tks_handle *h, uint32_t query, const uint64_t *d_keys,
     select_topk_kernel<false><<<1, kSelectThreads, kSelectDynSmem, s>>>(
         d_keys, 0u, nullptr, n_keys, 0u, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX,
         h->d_res_keys + (size_t)query * h->kmax, h->d_res_idx + (size_t)query * h->kmax,
-        h->d_res_val + (size_t)query * h->kmax, 0u, h->d_res_count + query, nullptr, PeerExchange{}, 0u);
+        h->d_res_val + (size_t)query * h->kmax, 0u, h->d_res_count + query, nullptr, PeerExchange{}, 0u, 0u, 0u, nullptr, kSelectSmemKeys);
+    h->res_on_host = false;
     TKS_CUDA(h, cudaGetLastError());
     h->last_k = k;
     if (h->batch < query + 1) h->batch = query + 1;
@@ -827,7 +954,8 @@ int tks_merge_keys_batched_device(tks_handle *h, const uint64_t *d_keys, uint32_
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     select_topk_kernel<false><<<batch, kSelectThreads, kSelectDynSmem, s>>>(
         d_keys, keys_per_query, nullptr, keys_per_query, 0u, k, h->cfg.tie_break == TKS_TIE_HIGHER_INDEX,
-        h->d_res_keys, h->d_res_idx, h->d_res_val, h->kmax, h->d_res_count, nullptr, PeerExchange{}, 0u);
+        h->d_res_keys, h->d_res_idx, h->d_res_val, h->kmax, h->d_res_count, nullptr, PeerExchange{}, 0u, 0u, 0u, nullptr, kSelectSmemKeys);
+    h->res_on_host = false;
     TKS_CUDA(h, cudaGetLastError());
     h->last_k = k;
     if (h->batch < batch) h->batch = batch;
@@ -844,9 +972,13 @@ int tks_peer_init(tks_handle *h, uint32_t world, uint32_t rank, void *ipc_handle
     if (world < 1 || world > kPeerMaxWorld || rank >= world) return h->fail(TKS_EINVAL, "world outside 1..8 or rank >= world");
     static_assert(sizeof(cudaIpcMemHandle_t) <= TKS_IPC_HANDLE_BYTES, "IPC handle does not fit");
     TKS_CUDA(h, cudaSetDevice(h->device));
-    if (!h->d_peer_window) {
+    {
+        // the step counter restarts at 0 below: records of an earlier session must not satisfy the new steps' polls
+        int rcd = pipe_drain(h);
+        if (rcd) return rcd;
         const size_t bytes = peer_window_bytes(h->kmax);
-        TKS_CUDA(h, cudaMalloc(&h->d_peer_window, bytes));
+        if (!h->d_peer_window) TKS_CUDA(h, cudaMalloc(&h->d_peer_window, bytes));
+        TKS_CUDA(h, cudaDeviceSynchronize());
         TKS_CUDA(h, cudaMemset(h->d_peer_window, 0, bytes));
     }
     cudaIpcMemHandle_t ih;
@@ -875,6 +1007,7 @@ static PeerExchange peer_args(const tks_handle *h) {
     PeerExchange px{};
     for (uint32_t r = 0; r < h->peer_world; r++) px.window[r] = static_cast<uint64_t *>(h->peer_mapped[r]);
     px.world = h->peer_world; px.rank = h->peer_rank; px.kmax = h->kmax;
+    px.timeout_ms = spin_timeout_ms();
     return px;
 }
 
@@ -890,13 +1023,17 @@ int tks_run_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream) {
     TKS_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     if (s != h->stream) TKS_CUDA(h, cudaStreamWaitEvent(s, h->ev_query, 0));
+    int rcd = pipe_drain(h);
+    if (rcd) return rcd;
     const PeerExchange px = peer_args(h);
     h->peer_seq += 1;
     // sample -> main -> select; the select kernel also exchanges the candidates with the peers and merges
     launch_single_query(h, 0, k, s, false, false, &px, h->peer_seq);
     TKS_CUDA(h, cudaGetLastError());
     h->last_run_batched = false;
+    h->last_run_pipelined = false;
     h->stats.launches_per_run = 3;
+    h->stats.algorithmic_bytes = algorithmic_matrix_bytes(h) + (uint64_t)h->cols * 4ull + k * 8ull;
     h->last_k = k;
     h->have_result = false;
     h->overflow_check_pending = false;
@@ -907,6 +1044,9 @@ int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream) {
     if (!h) return TKS_EINVAL;
     if (!h->peer_ready) return h->fail(TKS_ESTATE, "tks_peer_connect first");
     if (k != h->last_k || h->batch != 1) return h->fail(TKS_ESTATE, "no single-query run with this k precedes the exchange");
+    if (h->res_on_host || h->last_run_pipelined)
+        return h->fail(TKS_ESTATE, "the last run left its result in host memory (blocking tks_run) or was a pipelined submit: "
+                                   "run with tks_run_async before tks_peer_exchange_async");
     if ((uint64_t)h->peer_world * k > kSelectSortCap) return h->fail(TKS_EINVAL, "world * k exceeds %u", kSelectSortCap);
     TKS_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
@@ -915,6 +1055,106 @@ int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream) {
     TKS_CUDA(h, launch_pdl(peer_exchange_merge_kernel, dim3(1), dim3(kSelectThreads), (size_t)0, s, pdl_enabled(), px,
                            h->peer_seq, k, (int)(h->cfg.tie_break == TKS_TIE_HIGHER_INDEX), h->d_res_keys, h->d_res_idx,
                            h->d_res_val, h->d_res_count));
+    return TKS_OK;
+}
+
+// ---- pipelined submits ---------------------------------------------------------------------------------------------
+
+int tks_submit(tks_handle *h, const float *d_query, uint32_t k, uint32_t flags, void *cuda_stream) {
+    if (!h || !d_query) return TKS_EINVAL;
+    if (h->cfg.mode != TKS_MODE_FLOAT_CSR) return h->fail(TKS_ESTATE, "float mode only");
+    if (!h->have_matrix) return h->fail(TKS_ESTATE, "no matrix uploaded");
+    if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k=%u outside 1..%u", k, h->kmax);
+    const bool exchange = (flags & TKS_SUBMIT_EXCHANGE) != 0;
+    if (exchange) {
+        if (!h->peer_ready) return h->fail(TKS_ESTATE, "tks_peer_connect first");
+        if ((uint64_t)h->peer_world * k > kSelectSortCap) return h->fail(TKS_EINVAL, "world * k exceeds %u", kSelectSortCap);
+    }
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    int rc = pipe_init(h);
+    if (rc) return rc;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    const uint32_t seq = h->pipe_seq + 1u;
+    const int slot = (int)(seq % (uint32_t)tks::Handle::kPipeSlots);
+    if (h->pipe_busy[slot]) {
+        // the slot's previous query (two submits ago) must have been selected before its scratch is reused: this is the
+        // only place a submit blocks the host, and it bounds the queries in flight
+        TKS_CUDA(h, cudaEventSynchronize(h->pipe_ev_done[slot]));
+        h->pipe_busy[slot] = false;
+    }
+    const int variant = cap_variant_for_k(k);
+    const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
+    const CsrDevice m = csr_device(h);
+    RunState *st = h->d_pipe_state + slot;
+    if (!(flags & TKS_SUBMIT_QUERY_READY)) {
+        // the query is produced by earlier work of the caller's stream: the sample stream has to see it too
+        TKS_CUDA(h, cudaEventRecord(h->pipe_ev_query, s));
+        TKS_CUDA(h, cudaStreamWaitEvent(h->pipe_sample_stream, h->pipe_ev_query, 0));
+    }
+    // 1. threshold of THIS query on the sample stream: small CTAs that fit beside the main kernel still streaming the
+    //    previous query
+    uint64_t *stamp = h->d_pipe_stamps + (size_t)(seq % tks::Handle::kPipeStamps) * kStampWords;
+    launch_sample(h, m, d_query, st, h->d_pipe_sample_keys, k, h->pipe_sample_stream, (uint32_t)pipe_sample_threads(), seq, stamp);
+    // 2. the stream on the caller's stream, chained to the previous main kernel by programmatic dependent launch and
+    //    never waiting for it: its CTAs take over as that grid's CTAs retire
+    launch_main_variant(h, variant, m, d_query, st, h->d_pipe_pool[slot], k, s, pdl_enabled(), seq, stamp);
+    // 3. select (+ exchange over the peer windows + merge) on the select stream; waits for the main kernel's last CTA
+    constexpr uint32_t lean_threads = kSelectLeanThreads;
+    if (exchange && h->peer_world > 1) {
+        const PeerExchange px = peer_args(h);
+        h->peer_seq += 1;
+        select_topk_kernel<true><<<1, lean_threads, lean_threads / 32u * 1024u, h->pipe_select_stream>>>(
+            h->d_pipe_pool[slot], 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys, h->d_res_idx, h->d_res_val, 0u,
+            h->d_res_count, nullptr, px, h->peer_seq, seq, spin_timeout_ms(), stamp, 0u);
+    } else {
+        select_topk_kernel<false><<<1, lean_threads, lean_threads / 32u * 1024u, h->pipe_select_stream>>>(
+            h->d_pipe_pool[slot], 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys, h->d_res_idx, h->d_res_val, 0u,
+            h->d_res_count, nullptr, PeerExchange{}, 0u, seq, spin_timeout_ms(), stamp, 0u);
+    }
+    TKS_CUDA(h, cudaGetLastError());
+    TKS_CUDA(h, cudaEventRecord(h->pipe_ev_done[slot], h->pipe_select_stream));
+    h->pipe_busy[slot] = true;
+    h->pipe_seq = seq;
+    h->pipe_last_slot = slot;
+    h->batch = 1;
+    h->last_k = k;
+    h->have_result = false;
+    h->res_on_host = false;
+    h->last_run_batched = false;
+    h->last_run_pipelined = true;
+    h->overflow_check_pending = false;
+    h->stats.launches_per_run = 3;
+    h->stats.algorithmic_bytes = algorithmic_matrix_bytes(h) + (uint64_t)h->cols * 4ull + k * 8ull;
+    return TKS_OK;
+}
+
+int tks_pipeline_wait(tks_handle *h, void *cuda_stream) {
+    if (!h) return TKS_EINVAL;
+    if (h->pipe_last_slot < 0) return TKS_OK;
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    TKS_CUDA(h, cudaStreamWaitEvent(s, h->pipe_ev_done[h->pipe_last_slot], 0));
+    return TKS_OK;
+}
+
+int tks_pipeline_stamps(tks_handle *h, uint64_t *stamps_ns, uint32_t capacity, uint32_t *count) {
+    if (!h || !count) return TKS_EINVAL;
+    *count = 0;
+    if (!h->d_pipe_stamps) return TKS_OK;
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    int rc = pipe_drain(h);
+    if (rc) return rc;
+    static_assert(kStampWords == TKS_PIPE_STAMP_WORDS, "header and kernels disagree on the stamp record");
+    TKS_CUDA(h, cudaMemcpy(h->h_pipe_stamps, h->d_pipe_stamps, (size_t)tks::Handle::kPipeStamps * kStampWords * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    uint32_t n = h->pipe_seq < tks::Handle::kPipeStamps - 1 ? h->pipe_seq : tks::Handle::kPipeStamps - 1;
+    if (n > capacity) n = capacity;
+    for (uint32_t i = 0; i < n; i++) {   // oldest first
+        const uint32_t seq = h->pipe_seq - n + 1u + i;
+        if (stamps_ns)
+            std::memcpy(stamps_ns + (size_t)i * kStampWords, h->h_pipe_stamps + (size_t)(seq % tks::Handle::kPipeStamps) * kStampWords,
+                        kStampWords * sizeof(uint64_t));
+    }
+    *count = n;
     return TKS_OK;
 }
 
@@ -929,7 +1169,8 @@ int tks_get_stats(tks_handle *h, tks_stats *out) {
     if (h->cfg.mode == TKS_MODE_FLOAT_CSR && h->d_state) {
         cudaSetDevice(h->device);
         RunState st{};
-        if (cudaMemcpy(&st, h->d_state, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess)
+        const RunState *src = (h->last_run_pipelined && h->pipe_last_slot >= 0) ? h->d_pipe_state + h->pipe_last_slot : h->d_state;
+        if (cudaMemcpy(&st, src, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess)
             h->stats.last_candidates = st.result_count;
     }
     *out = h->stats;

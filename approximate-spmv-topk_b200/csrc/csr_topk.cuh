@@ -62,7 +62,11 @@ struct RunState {
     uint32_t tau_key;         // ordered-float lower bound on the k-th best score (0 = none)
     uint32_t sample_ticket;   // last-block election of the sample kernel
     uint32_t result_count;    // pool size of the last run (statistics)
-    uint32_t pad[3];
+    // pipelined submits only (tks_submit): the three kernels of a query run on three streams and hand over through
+    // sequence numbers in HBM instead of stream order, so that consecutive queries overlap
+    uint32_t tau_seq;         // = seq once the sample kernel has published tau_key
+    uint32_t main_ticket;     // CTAs of the main kernel that have handed over their survivors
+    uint32_t main_seq;        // = seq once every CTA of the main kernel has
 };
 
 struct U32x8 { uint32_t w[8]; };
@@ -94,6 +98,39 @@ __device__ __forceinline__ uint32_t ldg_stream_u8(const void *p) {
 
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
 __device__ __forceinline__ float tau_from_key(uint32_t key) { return key == 0 ? neg_inf() : ordered_to_f32(key); }
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// %globaltimer stamps of one pipelined submit (tks_pipeline_stamps): TKS_PIPE_STAMP_WORDS words per query
+enum : uint32_t { kStampSampleBegin = 0, kStampSampleEnd = 1, kStampMainBegin = 2, kStampMainEnd = 3,
+                  kStampSelectResident = 4, kStampSelectBegin = 5, kStampSelectEnd = 6, kStampWords = 8 };
+
+// One thread waits until *p == want (a sequence number published with st_release_u32 by another grid).  Bounded:
+// returns false after timeout_ns of %globaltimer, so a producer that never runs surfaces as an error or a slow path
+// instead of a hung device.
+__device__ __forceinline__ bool spin_until_eq(const uint32_t *p, uint32_t want, uint64_t timeout_ns) {
+    uint64_t t0 = 0;
+    for (uint32_t spins = 1;; spins++) {
+        if (ld_acquire_u32(p) == want) return true;
+        __nanosleep(spins < 64 ? 32 : 256);
+        if ((spins & 31u) == 0) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > timeout_ns) return false;
+        }
+    }
+}
 
 // --------------------------------------------------------------------------
 // One warp iteration: 256 consecutive non-zeros, 8 per lane.
@@ -478,7 +515,7 @@ __device__ __forceinline__ uint32_t block_hist_threshold(LoadF load32, uint32_t 
 // The k-th largest of these warp maxima is the score of k distinct real rows, hence a valid lower bound on
 // the k-th best score; the last CTA to finish derives it in one histogram pass (block_hist_threshold: the lower
 // edge of the bin that holds the k-th largest maximum -- still a lower bound) and publishes it in st->tau_key.
-// Dynamic shared memory: max((cols+1)*4, (n_sample + kHistScratchWords)*4) bytes.
+// Dynamic shared memory: max((cols+1)*4, kHistScratchWords*4) bytes.
 // --------------------------------------------------------------------------
 // The query as the kernels see it: rounded to the storage type of the values and widened again.
 template <int VT>
@@ -492,9 +529,11 @@ template <int VT>
 __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m, const float *__restrict__ x,
                                                                      RunState *st, uint32_t *sample_keys,
                                                                      uint32_t n_sample, uint32_t stride,
-                                                                     uint32_t sample_iters, uint32_t k) {
+                                                                     uint32_t sample_iters, uint32_t k, uint32_t seq,
+                                                                     uint64_t *stamp) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     pdl_trigger();   // the main kernel's CTAs may take the SMs this grid leaves and stage the query meanwhile
+    if (stamp && blockIdx.x == 0 && threadIdx.x == 0) stamp[kStampSampleBegin] = global_timer_ns();
     float *xs = reinterpret_cast<float *>(smem_raw);
     for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<VT>(x[i]) : 0.0f;
     __syncthreads();
@@ -515,13 +554,19 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
     __threadfence();
-    uint32_t *skeys = reinterpret_cast<uint32_t *>(smem_raw);   // x is no longer needed by this block
-    for (uint32_t i = threadIdx.x; i < n_sample; i += blockDim.x) skeys[i] = __ldcg(sample_keys + i);
+    // x is no longer needed by this block: its shared memory becomes the histogram scratch; the maxima are read from
+    // L2 (three passes over <= 32 KB), so that a sample CTA needs only ~9 KB and fits beside two main-kernel CTAs
     __syncthreads();
-    const uint32_t thr = block_hist_threshold([&](uint32_t i) { return skeys[i]; }, n_sample, k, skeys + n_sample);
+    const uint32_t thr = block_hist_threshold([&](uint32_t i) { return __ldcg(sample_keys + i); }, n_sample, k,
+                                              reinterpret_cast<uint32_t *>(smem_raw));
     if (threadIdx.x == 0) {
         if (thr != 0) atomicMax(&st->tau_key, thr);
         st->sample_ticket = 0;
+        if (stamp) stamp[kStampSampleEnd] = global_timer_ns();
+        if (seq) {   // pipelined submit: the main kernel of this query waits for this number, not for stream order
+            __threadfence();
+            st_release_u32(&st->tau_seq, seq);
+        }
     }
 }
 
@@ -533,14 +578,27 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
 template <int CAP, int VT>
 __global__ void __launch_bounds__(CAP == 256 ? kMainThreadsWide : kMainThreads, 2)
 csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uint64_t *pool, uint32_t k,
-                     int tie_higher) {
+                     int tie_higher, uint32_t seq, uint32_t tau_wait_us, uint64_t *stamp) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float *xs = reinterpret_cast<float *>(smem_raw);
     uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (((m.cols + 1u) * 4u + 15u) & ~15u));
     pdl_trigger();   // the select kernel's CTA may be set up while this grid drains
     for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<VT>(x[i]) : 0.0f;
     __syncthreads();
-    pdl_wait();      // the query was complete before the sample kernel started; tau and the counters are not
+    if (seq == 0) {
+        pdl_wait();  // the query was complete before the sample kernel started; tau and the counters are not
+    } else {
+        // Pipelined submit (tks_submit): this grid follows the PREVIOUS query's main kernel in its stream and shares
+        // nothing with it (per-slot state), so it does not wait for it -- its CTAs start streaming as that grid's CTAs
+        // retire, and consecutive queries form one continuous stream.  What it needs is this query's threshold, which
+        // the sample kernel published from another stream (normally long ago).  Should it never arrive, the stream
+        // runs unfiltered: slower, still exact (the per-warp buffers compact).
+        if (threadIdx.x == 0) {
+            spin_until_eq(&st->tau_seq, seq, (uint64_t)tau_wait_us * 1000ull);
+            if (stamp && blockIdx.x == 0) stamp[kStampMainBegin] = global_timer_ns();
+        }
+        __syncthreads();
+    }
 
     const unsigned lane = lane_id();
     PoolSink<CAP> sink;
@@ -577,6 +635,16 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
             if (keep) pool[pos + __popc(mk & lanemask_lt())] = key;
         }
     }
+    if (seq) {
+        // the last CTA to hand over its survivors tells the select kernel (another stream) that the pool is complete
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(&st->main_ticket, 1u) == gridDim.x - 1) {
+            if (stamp) stamp[kStampMainEnd] = global_timer_ns();
+            __threadfence();
+            st_release_u32(&st->main_seq, seq);
+        }
+    }
 }
 
 // ---- constants of the select kernel (Kernel 3) ----
@@ -585,6 +653,8 @@ constexpr uint32_t kSelectSortCap = 2048;     // keys sorted directly (16 KB sta
 constexpr uint32_t kSelectRankSortMax = 512;  // up to here by rank (one pass, no barriers), above by a bitonic network
 constexpr uint32_t kSelectSmemKeys = 16384;   // pool keys staged in dynamic shared memory (128 KB)
 constexpr uint32_t kSelectDynSmem = (kSelectThreads / kWarp) * 1024u + kSelectSmemKeys * 8u;
+constexpr uint32_t kSelectLeanThreads = 512;   // pipelined submits: no staged keys, per-warp histograms only
+constexpr uint32_t kSelectLeanDynSmem = (kSelectLeanThreads / kWarp) * 1024u;
 
 // ---- candidate exchange over peer memory: shared pieces (the protocol is described at Kernel 4 below) ----
 constexpr uint32_t kPeerMaxWorld = 8;
@@ -593,6 +663,7 @@ constexpr uint32_t kPeerTimeout = 0xFFFFFFFEu;
 struct PeerExchange {
     uint64_t *window[kPeerMaxWorld];   // window[r]: rank r's window as mapped in THIS process (window[rank] = local)
     uint32_t world, rank, kmax;
+    uint32_t timeout_ms;               // bound of the wait for the peers' records (TKS_SPIN_TIMEOUT_MS, default 2000)
 };
 
 __host__ __device__ constexpr size_t peer_window_bytes(uint32_t kmax) { return 2ull * kPeerMaxWorld * kmax * 2ull * sizeof(uint64_t); }
@@ -602,11 +673,6 @@ __device__ __forceinline__ void st_volatile_v2_u64(uint64_t *p, uint64_t a, uint
 }
 __device__ __forceinline__ void ld_volatile_v2_u64(const uint64_t *p, uint64_t &a, uint64_t &b) {
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-}
-__device__ __forceinline__ uint64_t global_timer_ns() {
-    uint64_t t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
 }
 
 // This rank's key of output slot `slot` (0 = absent) into every rank's window, each word tagged with the step.
@@ -642,7 +708,7 @@ __device__ __forceinline__ void peer_poll_and_merge(const PeerExchange &px, uint
             if ((++spins & 63u) == 0) {
                 const uint64_t now = global_timer_ns();
                 if (t0 == 0) t0 = now;
-                if (now - t0 > 2000000000ull || *reinterpret_cast<volatile uint32_t *>(s_timeout)) { *s_timeout = 1; break; }
+                if (now - t0 > (uint64_t)px.timeout_ms * 1000000ull || *reinterpret_cast<volatile uint32_t *>(s_timeout)) { *s_timeout = 1; break; }
             }
         }
         const uint64_t key = (a << 32) | (b & 0xFFFFFFFFull);
@@ -697,6 +763,16 @@ __device__ __forceinline__ void peer_poll_and_merge(const PeerExchange &px, uint
 
 constexpr uint32_t kPoolOverflow = 0xFFFFFFFFu;   // *out_count when a capped pool overflowed (batched mode)
 
+// The select kernel leaves the per-query scratch ready for the next run (one thread).
+__device__ __forceinline__ void reset_run_state(RunState *st, uint32_t pool_size) {
+    st->result_count = pool_size;   // for tks_get_stats
+    st->chunk_counter = 0;
+    st->pool_count = 0;
+    st->tau_key = 0;
+    st->sample_ticket = 0;
+    st->main_ticket = 0;
+}
+
 // Grid: one CTA per query.  CTA q reads pool + q * pool_stride; its key count is st[q].pool_count (st != nullptr)
 // or pool_count_imm; results go to out_* + q * out_stride and out_count[q].  pool_cap != 0: a count above it
 // means keys were dropped -> out_count = kPoolOverflow and nothing else is written.
@@ -704,14 +780,17 @@ constexpr uint32_t kPoolOverflow = 0xFFFFFFFFu;   // *out_count when a capped po
 // (peer_push_key), and the same CTA then waits for the other ranks' lists and writes the GLOBAL top-k to out_*
 // (peer_poll_and_merge) -- local select, exchange and merge in one launch.
 template <bool EXCHANGE>
-__global__ void __launch_bounds__(kSelectThreads)
+__global__ void __launch_bounds__(kSelectThreads, 2)   // <= 32 registers: the CTA of a pipelined submit waits beside a main-kernel CTA
 select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunState *st, uint32_t pool_count_imm,
                    uint32_t pool_cap, uint32_t k, int tie_higher, uint64_t *out_keys, uint32_t *out_idx,
                    float *out_val, uint32_t out_stride, uint32_t *out_count, uint32_t *pass_counter,
-                   PeerExchange px, uint32_t seq) {
+                   PeerExchange px, uint32_t seq, uint32_t main_wait_seq, uint32_t main_wait_ms, uint64_t *stamp,
+                   uint32_t stage_keys) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);                                  // 32 KB
-    uint64_t *staged = reinterpret_cast<uint64_t *>(smem_raw + (kSelectThreads / kWarp) * 1024u);
+    // stage_keys: keys the dynamic shared memory holds behind the histograms (kSelectSmemKeys in the ordinary launch;
+    // 0 in the lean launch of a pipelined submit, whose CTA has to fit beside a main-kernel CTA: 512 threads, 16 KB)
+    uint64_t *staged = reinterpret_cast<uint64_t *>(smem_raw + (blockDim.x / kWarp) * 1024u);
     __shared__ uint64_t keys[kSelectSortCap];
     __shared__ uint32_t s_bin, s_above[2], s_cnt, s_timeout, s_present;
     const uint32_t tid = threadIdx.x;
@@ -724,16 +803,27 @@ select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunS
     out_val += (size_t)q * out_stride;
     out_count += q;
     pdl_wait();      // the pool and its count belong to the kernel before this one
+    if (main_wait_seq) {
+        // pipelined submit: this CTA was launched on its own stream, possibly long before the main kernel of its
+        // query finished; the last CTA of that grid publishes main_seq (csr_topk_main_kernel)
+        __shared__ uint32_t s_main_ok;
+        if (tid == 0) {
+            if (stamp) stamp[kStampSelectResident] = global_timer_ns();
+            s_main_ok = spin_until_eq(&st_reset->main_seq, main_wait_seq, (uint64_t)main_wait_ms * 1000000ull) ? 1u : 0u;
+            if (stamp) stamp[kStampSelectBegin] = global_timer_ns();
+        }
+        __syncthreads();
+        if (!s_main_ok) {
+            if (tid == 0) *out_count = kPeerTimeout;
+            return;
+        }
+    }
     const uint32_t n = st_reset ? st_reset->pool_count : pool_count_imm;
     if (pool_cap != 0 && n > pool_cap) {
         __syncthreads();   // everyone has read pool_count
         if (tid == 0) {
             *out_count = kPoolOverflow;
-            st_reset->result_count = n;
-            st_reset->chunk_counter = 0;
-            st_reset->pool_count = 0;
-            st_reset->tau_key = 0;
-            st_reset->sample_ticket = 0;
+            reset_run_state(st_reset, n);
             if (pass_counter && (q % 32u) == 0) pass_counter[q / 32u] = 0;
         }
         return;
@@ -741,15 +831,16 @@ select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunS
 
     uint32_t m = 0;   // number of keys in keys[]
     if (n <= kSelectRankSortMax) {
-        for (uint32_t i = tid; i < n; i += blockDim.x) keys[i] = pool[i];
+        for (uint32_t i = tid; i < n; i += blockDim.x) keys[i] = __ldcg(pool + i);
         m = n;
     } else {
-        const bool in_smem = n <= kSelectSmemKeys;
+        const bool in_smem = n <= stage_keys;
         if (in_smem) {
-            for (uint32_t i = tid; i < n; i += blockDim.x) staged[i] = pool[i];
+            for (uint32_t i = tid; i < n; i += blockDim.x) staged[i] = __ldcg(pool + i);
             __syncthreads();
         }
-        auto load = [&](uint32_t i) { return in_smem ? staged[i] : pool[i]; };
+        // the pool was written by another grid, possibly while this CTA was already resident: L2, never L1
+        auto load = [&](uint32_t i) { return in_smem ? staged[i] : __ldcg(pool + i); };
         // one histogram pass over the score halves: every key whose score reaches the bin of the k-th best score
         // is kept (at least k keys, a few more), the exact order is settled by the sort below
         uint32_t reach = 0;
@@ -820,25 +911,17 @@ select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunS
     if (EXCHANGE) {
         __syncthreads();   // every thread is done with keys[] (the rank sort reads it) before the gather overwrites it
         peer_poll_and_merge(px, seq, k, tie_higher, keys, &s_timeout, &s_present, out_keys, out_idx, out_val, out_count);
-        if (tid == 0 && st_reset) {
-            st_reset->result_count = n;
-            st_reset->chunk_counter = 0;
-            st_reset->pool_count = 0;
-            st_reset->tau_key = 0;
-            st_reset->sample_ticket = 0;
+        if (tid == 0) {
+            if (st_reset) reset_run_state(st_reset, n);
+            if (stamp) stamp[kStampSelectEnd] = global_timer_ns();
         }
         return;
     }
     if (tid == 0) {
         *out_count = cnt;
-        if (st_reset) {
-            st_reset->result_count = n;   // pool size, for tks_get_stats
-            st_reset->chunk_counter = 0;
-            st_reset->pool_count = 0;
-            st_reset->tau_key = 0;
-            st_reset->sample_ticket = 0;
-        }
+        if (st_reset) reset_run_state(st_reset, n);
         if (pass_counter && (q % 32u) == 0) pass_counter[q / 32u] = 0;
+        if (stamp) stamp[kStampSelectEnd] = global_timer_ns();
     }
 }
 

@@ -61,6 +61,8 @@ struct Handle {
     float *h_x = nullptr;               // pinned staging for tks_set_query
     uint32_t last_k = 0;
     bool have_result = false;
+    bool res_on_host = false;           // the last select wrote indices / scores / count to the pinned host block only
+    bool last_run_pipelined = false;
 
     // batched mode (csr_batched.cuh), allocated when max_batch > 1
     float *d_xT = nullptr;              // [npass][max_cols+1][32] transposed query tables
@@ -81,6 +83,23 @@ struct Handle {
 
     // launch geometry of the main kernel, per CAP variant
     int main_grid[4] = {0, 0, 0, 0};
+
+    // pipelined submits (tks_submit; api.cu): per-slot scratch so that consecutive queries overlap.  The sample and
+    // the select kernels run on two engine-owned streams, the main kernels on the caller's; hand-over by sequence
+    // numbers in RunState.  At most kPipeSlots queries are in flight.
+    static constexpr int kPipeSlots = 2;
+    cudaStream_t pipe_sample_stream = nullptr, pipe_select_stream = nullptr;
+    cudaEvent_t pipe_ev_done[kPipeSlots] = {nullptr, nullptr};     // recorded after the slot's select kernel
+    cudaEvent_t pipe_ev_query = nullptr;
+    bool pipe_busy[kPipeSlots] = {false, false};
+    RunState *d_pipe_state = nullptr;                              // [kPipeSlots]
+    uint64_t *d_pipe_pool[kPipeSlots] = {nullptr, nullptr};
+    uint32_t *d_pipe_sample_keys = nullptr;
+    uint64_t *d_pipe_stamps = nullptr, *h_pipe_stamps = nullptr;   // %globaltimer at the end of every select, ring of kPipeStamps
+    static constexpr uint32_t kPipeStamps = 4096;
+    uint32_t pipe_seq = 0;                                         // sequence number of the last submitted query
+    int pipe_last_slot = -1;
+    int pipe_main_grid[4] = {0, 0, 0, 0};                          // grids of the 512-thread main kernels used here
 
     BscsrState *bs = nullptr;
 

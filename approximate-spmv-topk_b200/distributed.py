@@ -84,8 +84,36 @@ class ShardedSpMV:
             return self.gathered.view(1, self.world * self.k)           # already grouped by query
         return self.gathered.permute(1, 0, 2).reshape(self.batch, self.world * self.k).contiguous()
 
+    def _stream(self, stream):
+        """stream 0 would mean "the engine's private stream" to the C ABI, but NCCL orders its collectives against
+        torch's CURRENT stream only: on the all-gather path the two must be the same stream."""
+        if stream == 0 and self.world > 1 and self.exchange_mode == "nccl":
+            return self.torch.cuda.current_stream().cuda_stream
+        return stream
+
+    def submit(self, dptr, stream=0, query_ready=True):
+        """Pipelined step (tks_submit): the query at device pointer `dptr` is enqueued and consecutive steps overlap;
+        with several ranks the select kernel of every step also exchanges and merges (peer mode).  The all-gather
+        path has no pipelined form and runs the step in stream order."""
+        eng, k = self.engine, self.k
+        if self.batch != 1:
+            raise ValueError("pipelined submits take one query per step")
+        if self.exchange_mode == "peer" or self.world == 1 or self.exchange_mode == "none":
+            eng.submit(dptr, k, stream, exchange=self.exchange_mode == "peer", query_ready=query_ready)
+            self.pipelined = True
+            return
+        stream = self._stream(stream)
+        eng.reset_device(dptr, 1, stream)
+        self.step(stream)
+
+    def wait(self, stream=0):
+        """Make `stream` wait for the last submitted step's (global) result."""
+        if getattr(self, "pipelined", False):
+            self.engine.pipeline_wait(stream)
+
     def step(self, stream=0):
         eng, k, B = self.engine, self.k, self.batch
+        stream = self._stream(stream)
         if self.exchange_mode == "peer":
             eng.run_exchange_async(k, stream)
             return

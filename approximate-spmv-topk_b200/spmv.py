@@ -116,6 +116,17 @@ class SpMV(_Base):
         check(capi.lib().tks_download_csr(self.handle, _ptr(ptr), _ptr(idx), _ptr(val)), self.handle)
         return ptr, idx, val
 
+    def download_csr_rows(self, row_begin, row_end):
+        """(ptr uint64[n+1] rebased to 0, idx, val) of the resident rows [row_begin, row_end)."""
+        n = int(row_end) - int(row_begin)
+        ptr = np.zeros(n + 1, np.uint64)
+        check(capi.lib().tks_download_csr_rows(self.handle, int(row_begin), int(row_end), _ptr(ptr), None, None), self.handle)
+        nnz = int(ptr[-1] - ptr[0])
+        idx = np.zeros(max(nnz, 1), np.uint32)
+        val = np.zeros(max(nnz, 1), np.float32)
+        check(capi.lib().tks_download_csr_rows(self.handle, int(row_begin), int(row_end), None, _ptr(idx), _ptr(val)), self.handle)
+        return ptr - ptr[0], idx[:nnz], val[:nnz]
+
     def reset(self, vec, debug=0):
         vec = np.ascontiguousarray(vec, np.float32)
         batch = 1 if vec.ndim == 1 else vec.shape[0]
@@ -172,6 +183,27 @@ class SpMV(_Base):
     def peer_exchange_async(self, k=None, stream=0):
         k = self.k if k is None else k
         check(capi.lib().tks_peer_exchange_async(self.handle, k, C.c_void_p(stream)), self.handle)
+
+    # ---- pipelined submits: consecutive queries overlap (tks_submit) ----
+    def submit(self, dptr, k=None, stream=0, exchange=False, query_ready=False):
+        """Enqueue one query (device pointer to num_cols fp32 values, read in place).  At most two are in flight."""
+        k = self.k if k is None else k
+        flags = (capi.SUBMIT_EXCHANGE if exchange else 0) | (capi.SUBMIT_QUERY_READY if query_ready else 0)
+        check(capi.lib().tks_submit(self.handle, C.c_void_p(dptr), k, flags, C.c_void_p(stream)), self.handle)
+        self.k = k
+        self.batch = 1
+
+    def pipeline_wait(self, stream=0):
+        """Make `stream` wait (on the device) for the result of the last submitted query."""
+        check(capi.lib().tks_pipeline_wait(self.handle, C.c_void_p(stream)), self.handle)
+
+    def pipeline_stamps(self, n=1024):
+        """%globaltimer nanoseconds of the last n submits, oldest first: uint64[n, 8] with columns sample begin / end,
+        main begin / end, select resident / begin / end (see topkspmv.h)."""
+        buf = np.zeros((n, 8), np.uint64)
+        cnt = C.c_uint32()
+        check(capi.lib().tks_pipeline_stamps(self.handle, _ptr(buf), n, C.byref(cnt)), self.handle)
+        return buf[:cnt.value].copy()
 
     def merge_keys_device(self, dptr, n_keys, k=None, query=0, stream=0):
         k = self.k if k is None else k

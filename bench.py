@@ -67,47 +67,73 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  The timed region of a
+    default run is a few milliseconds, far below nvidia-smi's sampling period, so the sampler polls NVML itself
+    (nvidia_ml_py) from a thread about once per millisecond; mark(name) labels what follows, and the summary reports
+    the samples that fell inside the label "timed" next to those of the whole measurement."""
+
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("hw_power_brake_slowdown", 0x80), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.label, self.stop_flag, self.thread, self.err = index, [], "setup", False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # torch's device ordinal follows CUDA_VISIBLE_DEVICES; NVML's does not
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except Exception:
+                    phys = index
+            self.nv, self.dev = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+        except Exception as e:   # no NVML: say so in the line instead of failing the bench
+            self.nv, self.err = None, repr(e)
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)
+                try:
+                    why = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                except Exception:
+                    why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                self.rows.append((self.label, float(mhz), int(why)))
+            except Exception as e:
+                self.err = repr(e)
+                return
+            time.sleep(0.0007)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def mark(self, label):
+        self.label = label
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["NVML unavailable: " + str(self.err)]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        timed = [r for r in self.rows if r[0] == "timed"]
+
+        def summary(rows):
+            why = 0
+            for r in rows:
+                why |= r[2]
+            return {"sm_mhz": statistics.median([r[1] for r in rows]) if rows else None, "samples": len(rows),
+                    "reasons": sorted(n for n, bit in self.REASONS if why & bit)}
+        t, a = summary(timed), summary(self.rows)
+        return {"sm_mhz": t["sm_mhz"] if t["samples"] else a["sm_mhz"], "sm_max_mhz": self.max_mhz,
+                "samples": t["samples"], "reasons": sorted(set(t["reasons"]) | set(a["reasons"])),
+                "whole_measurement": a, "source": "NVML polled every ~1 ms; `samples` = inside the timed region"}
 
 
 def make_queries(cols, n, seed0=1):
@@ -234,8 +260,60 @@ def ours(args):
     if wl["mode"] == "batched":
         return ours_batched(args, tks, wl, rows_total, peak_gbs, peak_src, world, rank, local, stream)
 
-    # profile_kernels (two extra events around the dominant kernel, no launch overlap) is switched on only for the
-    # roofline leg (measure_main_kernel); `value` and `e2e` are measured on the production path
+    line = float_workload(tks, torch, dist, wl_key, args, world, rank, local, tstream, peak_gbs, peak_src,
+                          steps=args.steps, warmup=args.warmup, full=True)
+    if world > 1 and wl_key == "cfg2" and not args.no_cfg4:
+        # BASELINE config 4 rides along in every multi-GPU line of the default run: 200M x 1024 uniform-40, rows / N
+        sub = float_workload(tks, torch, dist, "cfg4", args, world, rank, local, tstream, peak_gbs, peak_src,
+                             steps=min(args.steps, 10), warmup=3, full=False)
+        if rank == 0:
+            line["cfg4"] = sub
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ok = (line or {}).get("parity_n", True) is not False and ((line or {}).get("cfg4") or {}).get("parity_n", True) is not False
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0 and not ok:
+        raise SystemExit("parity check failed (see parity_n / parity in the line above)")
+
+
+def merge_lists(lists, k):
+    """Per-rank (rows, scores) lists -> global top-k under (score desc, row asc)."""
+    ai = np.concatenate([np.asarray(a[0], np.int64) for a in lists])
+    av = np.concatenate([np.asarray(a[1], np.float32) for a in lists])
+    order = np.lexsort((ai, -av.astype(np.float64)))[:k]
+    return ai[order], av[order]
+
+
+def lists_agree(idx, val, gi, gv, rtol=1e-5):
+    """The north-star bar: scores within rtol, index sets identical except where scores tie within rtol of the k-th."""
+    idx, gi = np.asarray(idx, np.int64), np.asarray(gi, np.int64)
+    val, gv = np.asarray(val, np.float32), np.asarray(gv, np.float32)
+    if idx.size != gi.size:
+        return False, {"reason": f"{idx.size} results vs {gi.size} expected"}
+    kth = float(gv[-1])
+    tol = abs(kth) * rtol + 1e-7
+    only_e = [(int(i), float(v)) for i, v in zip(idx, val) if i not in set(gi.tolist())]
+    only_g = [(int(i), float(v)) for i, v in zip(gi, gv) if i not in set(idx.tolist())]
+    ties_ok = all(abs(v - kth) <= tol for _, v in only_e + only_g)
+    scores_ok = bool(np.allclose(np.sort(val)[::-1], np.sort(gv)[::-1], rtol=rtol, atol=1e-7))
+    return bool(ties_ok and scores_ok), {"set_difference": len(only_e) + len(only_g), "k_th_score": kth,
+                                         "max_abs_score_diff": float(np.max(np.abs(np.sort(val)[::-1] - np.sort(gv)[::-1])))}
+
+
+def float_workload(tks, torch, dist, wl_key, args, world, rank, local, tstream, peak_gbs, peak_src, steps, warmup, full):
+    """One float workload (cfg2 / cfg2h / cfg2b weak-scaled, cfg4 strong-scaled) on `world` ranks.  Returns the record
+    (rank 0) or None.  full = the main line (e2e, roofline leg, CPU baseline); otherwise a sub-record with value,
+    per-step statistics and parity."""
+    wl = WORKLOADS[wl_key]
+    weak = wl_key in ("cfg2", "cfg2h", "cfg2b")                          # cfg2: 10M rows PER RANK; cfg4: the stated total, sharded
+    rows_total = (args.rows or wl["rows"]) * (world if weak else 1)
+    cols = wl["cols"]
+    r0, r1 = tks.sharding.plan_row_shards_even(rows_total, world)[rank]
+    stream = tstream.cuda_stream
+    nsteps = warmup + steps
+    queries = make_queries(cols, nsteps)
     half = bool(wl.get("half", False) or wl.get("bf16", False))      # 16-bit values
     eng = tks.SpMV(num_cols=cols, k=K, device=local, half=bool(wl.get("half", False)), bf16=bool(wl.get("bf16", False)))
     t0 = time.perf_counter()
@@ -249,16 +327,24 @@ def ours(args):
     nnz_total = int(nnz_t.item())
 
     dq = torch.from_numpy(queries).cuda()            # queries resident in HBM for `value`
-    # run + exchange of the K candidates + merge (nothing to exchange at N=1): one peer-memory kernel over NVLink when
-    # the ranks can map each other's windows (CUDA IPC), else NCCL all-gather + merge kernel; TKS_EXCHANGE=nccl forces that
+    torch.cuda.synchronize()
+    # run + exchange of the K candidates + merge (nothing to exchange at N=1): the select kernel itself stores the
+    # candidates into every rank's IPC window over NVLink, waits and merges when the ranks can map each other's windows,
+    # else NCCL all-gather + merge kernel; TKS_EXCHANGE=nccl forces that
     sharded = tks.ShardedSpMV(eng, K, batch=1, exchange=os.environ.get("TKS_EXCHANGE", "auto"))
+    pipelined = os.environ.get("TKS_BENCH_PIPELINE", "1") != "0" and (world == 1 or sharded.exchange_mode in ("peer", "none"))
 
     def step(i):
-        eng.reset_device(dq[i].data_ptr(), 1, stream)
-        sharded.step(stream)
+        if pipelined:
+            # consecutive queries overlap (tks_submit): sample(i+1) beside main(i), select(i) beside main(i+1)
+            sharded.submit(dq[i].data_ptr(), stream, query_ready=True)
+        else:
+            eng.reset_device(dq[i].data_ptr(), 1, stream)
+            sharded.step(stream)
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
+    sharded.wait(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -267,53 +353,83 @@ def ours(args):
         sampler.start()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark("timed")
     e0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
+    for i in range(steps):
+        step(warmup + i)
+    sharded.wait(stream)                             # the last query's select (+ exchange + merge) is inside the region
     e1.record()
     torch.cuda.synchronize()
+    sampler.mark("after")
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     value = nnz_total / (ms_step * 1e-3)
     val_last, idx_last, cnt_last = eng.read_result()
+    per_step = None
+    if pipelined:
+        # completion time of every step's select kernel (%globaltimer, written by the kernel): intervals = per-step times
+        stamps = eng.pipeline_stamps(steps).astype(np.int64)
+        if stamps.shape[0] >= 3:
+            d = np.diff(stamps[:, 6]) * 1e-6
+            us = lambda a: round(float(np.mean(a)) * 1e-3, 2)
+            per_step = {"mean_ms": float(d.mean()), "std_ms": float(d.std()), "min_ms": float(d.min()), "max_ms": float(d.max()),
+                        "n": int(d.size), "source": "intervals between the select kernels' %globaltimer stamps (this rank)",
+                        # where the kernels of a step sit relative to each other (mean over the timed steps, microseconds)
+                        "timeline_us": {"sample": us(stamps[:, 1] - stamps[:, 0]), "main": us(stamps[:, 3] - stamps[:, 2]),
+                                        "select_after_main_end": us(stamps[:, 6] - stamps[:, 3]),
+                                        "select": us(stamps[:, 6] - stamps[:, 5]),
+                                        "sample_end_before_main_begin": us(stamps[:, 2] - stamps[:, 1]),
+                                        "main_begin_after_previous_main_end": us(stamps[1:, 2] - stamps[:-1, 3])}}
 
-    # e2e: reference-facing calls with HOST buffers (reset -> operator() -> read_result), every step
-    hq = [np.ascontiguousarray(q) for q in queries]
-    e2e_ms = []
-    for i in range(nsteps):
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        eng.reset(hq[i])
-        if world == 1:
-            eng.run_timed(K)
-            v_e, i_e, _ = eng.read_result()
-        else:
-            sharded.step(stream)
-            torch.cuda.synchronize()
-            v_e, i_e, _ = eng.read_result()
-        dt = (time.perf_counter() - t0) * 1e3
-        if i >= args.warmup:
-            e2e_ms.append(dt)
-    e2e_t = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_ms_step = float(e2e_t.item())
-    # the device-resident and the host-buffer paths must agree on the last query
-    assert np.array_equal(i_e, idx_last) and np.array_equal(v_e, val_last), "e2e and resident results differ"
+    # ---- parity at N ranks: every rank runs the reference's CPU gold over its own shard (or a bounded sample of it)
+    q_chk = queries[nsteps - 1]
+    if wl.get("half"):
+        q_chk = q_chk.astype(np.float16).astype(np.float32)        # the engine rounds the query to the storage type
+    elif wl.get("bf16"):
+        b = q_chk.view(np.uint32).astype(np.uint64)
+        q_chk = (((b + 0x7FFF + ((b >> 16) & 1)) >> 16) << 16).astype(np.uint32).view(np.float32)
+    parity = parity_check(tks, torch, dist, eng, sharded, q_chk, queries[nsteps - 1], idx_last, val_last, world, rank,
+                          r0, r1, stream, whole_shard=(r1 - r0) <= 12_000_000)
 
-    # roofline of the dominant kernel (csr_topk_main_kernel), timed alone with CUDA events on its stream
     stats = eng.stats()
     alg_bytes_local = int(stats.algorithmic_bytes)
-    main_ms = measure_main_kernel(tks, eng, hq, args, K)
+    hq = [np.ascontiguousarray(q) for q in queries]
+    rec = None
+    e2e_ms_step = None
+    if full:
+        # e2e: reference-facing calls with HOST buffers (reset -> operator() -> read_result), every step
+        e2e_ms = []
+        for i in range(nsteps):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            eng.reset(hq[i])
+            if world == 1:
+                eng.run_timed(K)
+                v_e, i_e, _ = eng.read_result()
+            else:
+                sharded.step(stream)
+                torch.cuda.synchronize()
+                v_e, i_e, _ = eng.read_result()
+            dt = (time.perf_counter() - t0) * 1e3
+            if i >= warmup:
+                e2e_ms.append(dt)
+        e2e_t = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e_ms_step = float(e2e_t.item())
+        # the device-resident and the host-buffer paths must agree on the last query
+        assert np.array_equal(i_e, idx_last) and np.array_equal(v_e, val_last), "e2e and resident results differ"
+
+    # roofline of the dominant kernel (csr_topk_main_kernel), timed alone with CUDA events on its stream
+    main_ms = measure_main_kernel(tks, eng, hq, warmup, steps if full else min(steps, 5), K)
     achieved = alg_bytes_local / (main_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "csr_topk_main_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
             "frac": achieved / peak_gbs, "traffic": load_traffic(wl_key), "peak_source": peak_src,
@@ -323,53 +439,127 @@ def ours(args):
             # row-start bitmap instead of 32-bit indices + row_ptr): bytes the kernel actually streams, and their rate
             "streamed_bytes_per_launch": int(stats.device_bytes),
             "streamed_gbs": int(stats.device_bytes) / (main_ms * 1e-3) / 1e9,
-            "streamed_frac": int(stats.device_bytes) / (main_ms * 1e-3) / 1e9 / peak_gbs}
+            "streamed_frac": int(stats.device_bytes) / (main_ms * 1e-3) / 1e9 / peak_gbs,
+            "streamed_step_frac": int(stats.device_bytes) / (ms_step * 1e-3) / 1e9 / peak_gbs}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu and not half:
-        cpu = cpu_baseline_leg(tks, eng, hq[args.warmup:], idx_last, val_last, args)
+    if full and rank == 0 and world == 1 and not args.no_cpu and not half:
+        cpu = cpu_baseline_leg(tks, eng, hq[warmup:], idx_last, val_last, args)
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
-        line = {"metric": "topk_spmv_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak" if weak else "strong", "vs_baseline": None,
-                "dtype": ("bf16 values x bf16 query, f32 products and sums" if wl.get("bf16") else
-                          "f16 values x f16 query, f32 products and sums" if half else "f32"), "data": "synthetic",
-                "config": {"workload": wl["name"] + (f", weak-scaled: {world} shards of {wl['rows']} rows" if weak and world > 1 else ""),
-                           "rows": rows_total, "cols": cols, "nnz": nnz_total, "k": K,
-                           "sharding": (f"rows/{world}, K candidates exchanged by " +
-                                        ("the select kernel itself (stores into every rank's IPC window over NVLink, wait, merge: no extra launch)"
-                                         if sharded.exchange_mode == "peer" else "NCCL all-gather + merge kernel") +
-                                        " on every rank") if world > 1 else "none",
-                           "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * (6 if half else 8) / 1e9),
-                           "generator_s": round(gen_s, 2)},
-                "roofline": roof,
-                "cpu_baseline": cpu,
-                "e2e": {"value": nnz_total / (e2e_ms_step * 1e-3), "unit": "nnz/s", "ms_per_step": e2e_ms_step,
-                        "h2d_bytes_per_step": cols * 4, "d2h_bytes_per_step": K * 8 + 4,
-                        "api": "SpMV.reset(host vec) -> operator() -> read_result(host)"},
-                # ours per step: sample + main + select (which also exchanges and merges in peer mode); the NCCL path adds a merge launch
-                "gpu_launches": args.steps * (3 if (world == 1 or sharded.exchange_mode == "peer") else 4),
-                "candidates_last_step": int(stats.last_candidates),
-                "hbm_gbs_effective": alg_bytes_local * world / (ms_step * 1e-3) / 1e9,
-                "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        exchange_txt = ("the select kernel itself (stores into every rank's IPC window over NVLink, wait, merge: no extra launch)"
+                        if sharded.exchange_mode == "peer" else "NCCL all-gather + merge kernel")
+        rec = {"metric": "topk_spmv_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": steps,
+               "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
+               "scaling": "weak" if weak else "strong", "vs_baseline": None,
+               "dtype": ("bf16 values x bf16 query, f32 products and sums" if wl.get("bf16") else
+                         "f16 values x f16 query, f32 products and sums" if half else "f32"), "data": "synthetic",
+               "config": {"workload": wl["name"] + (f", weak-scaled: {world} shards of {wl['rows']} rows" if weak and world > 1 else ""),
+                          "rows": rows_total, "cols": cols, "nnz": nnz_total, "k": K,
+                          "sharding": (f"rows/{world}, K candidates exchanged by " + exchange_txt + " on every rank") if world > 1 else "none",
+                          "pipeline": ("tks_submit: consecutive queries overlap (sample of query i+1 beside the main kernel of query i, "
+                                       "main kernels chained by programmatic dependent launch, select on its own stream); "
+                                       "every query's three kernels complete inside the timed region") if pipelined else "none (stream order)",
+                          "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * (6 if half else 8) / 1e9),
+                          "generator_s": round(gen_s, 2)},
+               "per_step": per_step, "parity_n": parity["ok"], "parity": parity,
+               "roofline": roof,
+               # ours per step: sample + main + select (which also exchanges and merges in peer mode); the NCCL path adds a merge launch
+               "gpu_launches": steps * (3 if (world == 1 or sharded.exchange_mode == "peer") else 4),
+               "candidates_last_step": int(stats.last_candidates),
+               "hbm_gbs_effective": alg_bytes_local * world / (ms_step * 1e-3) / 1e9,
+               "clocks": clocks}
+        if full:
+            rec["cpu_baseline"] = cpu
+            rec["e2e"] = {"value": nnz_total / (e2e_ms_step * 1e-3), "unit": "nnz/s", "ms_per_step": e2e_ms_step,
+                          "h2d_bytes_per_step": cols * 4, "d2h_bytes_per_step": K * 8 + 4,
+                          "api": "SpMV.reset(host vec) -> operator() -> read_result(host)"}
     eng.close()
+    torch.cuda.empty_cache()
+    return rec
+
+
+def parity_check(tks, torch, dist, eng, sharded, query, query_raw, idx_last, val_last, world, rank, r0, r1, stream, whole_shard):
+    """Is the engine's GLOBAL top-k for `query` the reference's?  Every rank runs the reference's CPU gold
+    (spmv_coo_gold_top_k, all host threads) over its own shard -- the whole shard when it is small enough to copy
+    back (cfg2: 10M rows), else a bounded sample of it plus an exact re-computation of every returned row -- the
+    per-rank lists are gathered and merged on the host, and the engine's result must match (north-star tolerance)."""
+    out = {"ok": True, "ranks": world}
+    mine = None
+    rows_local = r1 - r0
+    sample_rows = rows_local if whole_shard else min(rows_local, 500_000)
+    ptr, idx, val = eng.download_csr_rows(0, sample_rows)
+    _, kind, cores, res = cpu_reference(ptr, idx, val, [query], K, max_seconds=1e9)
+    gi, gv = res[0]
+    mine = (gi.astype(np.int64) + r0, gv)
+    gathered = [mine]
+    results = [(np.asarray(idx_last, np.int64), np.asarray(val_last, np.float32))]
     if world > 1:
-        dist.destroy_process_group()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        results = [None] * world
+        dist.all_gather_object(results, (np.asarray(idx_last, np.int64), np.asarray(val_last, np.float32)))
+    out["ranks_hold_identical_results"] = all(np.array_equal(r[0], results[0][0]) and np.array_equal(r[1], results[0][1]) for r in results)
+    out["ok"] &= out["ranks_hold_identical_results"]
+    out["oracle"] = f"reference spmv_coo_gold_top_k ({kind}) on every rank's own shard, {cores} host threads per rank"
+    if whole_shard:
+        gi, gv = merge_lists(gathered, K)
+        ok, detail = lists_agree(idx_last, val_last, gi, gv)
+        out.update(detail)
+        out["scope"] = f"whole matrix: {world} shards of {rows_local} rows"
+        out["ok"] &= ok
+    else:
+        # (i) no sampled row that clearly beats the engine's k-th score may be missing from the engine's list
+        kth = float(val_last[-1])
+        gi, gv = merge_lists(gathered, K)
+        have = set(np.asarray(idx_last, np.int64).tolist())
+        missed = [(int(i), float(v)) for i, v in zip(gi, gv) if v > kth * (1 + 1e-5) + 1e-7 and int(i) not in have]
+        # (ii) every returned row this rank owns: its exact fp32 score re-computed on the host from the resident CSR
+        worst = 0.0
+        for i, v in zip(np.asarray(idx_last, np.int64), np.asarray(val_last, np.float32)):
+            if r0 <= i < r1:
+                p, c, w = eng.download_csr_rows(int(i - r0), int(i - r0) + 1)
+                acc = np.float32(0)
+                for cc, ww in zip(c, w):
+                    acc = np.float32(acc + np.float32(ww * query[cc]))
+                worst = max(worst, abs(float(acc) - float(v)) / max(abs(float(acc)), 1e-30))
+        worst_t = torch.tensor([worst], dtype=torch.float64, device="cuda")
+        miss_t = torch.tensor([len(missed)], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(worst_t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(miss_t)
+        # (iii) the exchange + merge: the un-exchanged local lists of all ranks merged on the host = the engine's list
+        eng.reset(np.ascontiguousarray(query_raw))
+        eng.run_async(K, stream)
+        lv, li, lc = eng.read_result()
+        locs = [(np.asarray(li[:lc], np.int64), np.asarray(lv[:lc], np.float32))]
+        if world > 1:
+            locs = [None] * world
+            dist.all_gather_object(locs, (np.asarray(li[:lc], np.int64), np.asarray(lv[:lc], np.float32)))
+        mi, mv = merge_lists(locs, K)
+        same_merge = bool(np.array_equal(mi, np.asarray(idx_last, np.int64)) and np.array_equal(mv, np.asarray(val_last, np.float32)))
+        out.update({"scope": f"first {sample_rows} rows of each of the {world} shards ({rows_local} rows per shard) through the gold, "
+                             f"every returned row re-computed exactly, exchange + merge against the host merge of the local lists",
+                    "sampled_rows_beating_kth_but_missing": int(miss_t.item()),
+                    "max_rel_score_error_of_returned_rows": float(worst_t.item()),
+                    "device_merge_equals_host_merge_of_local_lists": same_merge})
+        out["ok"] &= int(miss_t.item()) == 0 and float(worst_t.item()) <= 1e-5 and same_merge
+    out["ok"] = bool(out["ok"])
+    return out
 
 
-def measure_main_kernel(tks, eng, hq, args, k):
+def measure_main_kernel(tks, eng, hq, warmup, steps, k):
     """Average duration of the dominant kernel alone (CUDA events recorded by tks_run on its own stream
     right before and after csr_topk_main_kernel; cfg.profile_kernels)."""
     ms = []
     eng.set_profile_kernels(True)
-    for i in range(args.warmup + args.steps):
+    for i in range(warmup + steps):
         eng.reset(hq[i % len(hq)])
         km, _ = eng.run_timed(k)
         st = eng.stats()
         v = st.last_main_kernel_ms if st.last_main_kernel_ms > 0 else km
-        if i >= args.warmup:
+        if i >= warmup:
             ms.append(v)
     eng.set_profile_kernels(False)
     return sum(ms) / len(ms)
@@ -692,6 +882,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override the workload's total rows (debug)")
     ap.add_argument("--ref-rows", type=int, default=2_000_000, help="rows of the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true", help="N > 1: skip the BASELINE config 4 sub-record")
     ap.add_argument("--batch-fma", action="store_true", help="cfg5: fused multiply-add arithmetic")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -147,6 +147,11 @@ int tks_generate_synthetic(tks_handle *h, uint64_t rows, uint32_t cols, uint32_t
 /* Copy the resident CSR back to the host (ptr64: rows+1, idx/val: nnz; any may be NULL).
  * Lets a checker see exactly the matrix tks_generate_synthetic made.           */
 int tks_download_csr(tks_handle *h, uint64_t *ptr64, uint32_t *idx, float *val);
+/* The same for the rows [row_begin, row_end) only: ptr64 gets row_end - row_begin + 1 offsets into the WHOLE matrix
+ * (so ptr64[last] - ptr64[0] non-zeros follow in idx / val).  Call once with idx = val = NULL to size the arrays.
+ * Lets a checker look at a bounded sample of a shard too large to copy back (BASELINE config 4).               */
+int tks_download_csr_rows(tks_handle *h, uint64_t row_begin, uint64_t row_end, uint64_t *ptr64, uint32_t *idx,
+                          float *val);
 
 /* ---- per query ---------------------------------------------------------- */
 
@@ -199,6 +204,34 @@ int tks_peer_connect(tks_handle *h, const void *all_handles);
 int tks_run_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream);
 int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream);  /* exchange + merge as a stand-alone
                                                                               launch after tks_run_async     */
+
+/* ---- pipelined submits: consecutive queries overlap (float mode, one query per submit) -------------------------
+ * The reference hosts loop  reset(vec) -> operator() -> read_result()  strictly one query after the other
+ * (src/gpu/host_spmv_topk_csr_gpu.cu:399-423); a caller that has the next query ready before it needs the previous
+ * result can instead SUBMIT queries: tks_submit enqueues the three kernels of one query on three streams -- the
+ * threshold sample on an engine stream (it runs beside the main kernel of the previous query), the matrix stream on
+ * `cuda_stream` (chained to the previous query's by programmatic dependent launch without waiting for it, so the
+ * stream of non-zeros never pauses between queries), the select (+ peer exchange + merge with TKS_SUBMIT_EXCHANGE,
+ * see tks_peer_init) on a second engine stream -- with per-slot scratch and sequence-number hand-overs in HBM instead
+ * of stream order.  Results are those of tks_run_async for the same query, bit for bit.
+ *   d_query  DEVICE pointer to cols fp32 values; it is read in place and must stay valid and unchanged until the
+ *            query's result is complete (tks_pipeline_wait / tks_read_result).
+ *   flags    TKS_SUBMIT_QUERY_READY: the query's bytes are already complete in memory at the time of the call
+ *            (otherwise the sample stream is made to wait for the work enqueued on `cuda_stream` so far);
+ *            TKS_SUBMIT_EXCHANGE: several GPUs -- every rank submits the same step (tks_run_exchange_async rules).
+ * At most two queries are in flight: a third submit blocks the host until the first one's select has finished.
+ * tks_read_result (synchronises) returns the LAST submitted query's result; tks_pipeline_wait makes `cuda_stream`
+ * wait for it on the device without blocking the host.  tks_pipeline_stamps returns, for each of the last `capacity`
+ * submits (oldest first), TKS_PIPE_STAMP_WORDS %globaltimer nanosecond stamps written by the kernels themselves:
+ * [0] sample begin, [1] sample end, [2] main kernel begins streaming, [3] main kernel's last CTA done, [4] select CTA
+ * resident, [5] select begins (pool complete), [6] select (+ exchange + merge) done -- the pipeline's timeline
+ * without any event in the streams.  stamps_ns holds capacity * TKS_PIPE_STAMP_WORDS words.                   */
+#define TKS_PIPE_STAMP_WORDS 8
+#define TKS_SUBMIT_EXCHANGE 1u
+#define TKS_SUBMIT_QUERY_READY 2u
+int tks_submit(tks_handle *h, const float *d_query, uint32_t k, uint32_t flags, void *cuda_stream);
+int tks_pipeline_wait(tks_handle *h, void *cuda_stream);
+int tks_pipeline_stamps(tks_handle *h, uint64_t *stamps_ns, uint32_t capacity, uint32_t *count);
 
 /* Switch tks_config.profile_kernels at run time: while on, tks_run brackets the dominant kernel with two extra
  * events (tks_stats.last_main_kernel_ms) and launches the kernels without overlap.                              */
