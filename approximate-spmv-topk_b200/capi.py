@@ -57,7 +57,7 @@ SYMBOLS = [
     "tks_submit", "tks_pipeline_wait", "tks_pipeline_stamps",
     "tks_set_profile_kernels", "tks_get_stats", "tks_bscsr_packet_size", "tks_fixed32_from_double", "tks_fixedW_from_fixed32",
     "tks_pack_bscsr", "tks_merge_partition_words", "tks_read_mtx", "tks_coo2csr",
-    "tks_cache_write_csr", "tks_cache_read_csr", "tks_cache_write_bscsr", "tks_cache_read_bscsr",
+    "tks_cache_write_csr", "tks_cache_read_csr", "tks_cache_source_tag", "tks_cache_write_csr_tagged", "tks_cache_read_csr_tagged", "tks_cache_write_bscsr", "tks_cache_read_bscsr",
 ]
 
 _lib = None

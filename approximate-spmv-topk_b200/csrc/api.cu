@@ -259,7 +259,7 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
     if (herr) {
         free_matrix(h);
         return h->fail(TKS_EINVAL, "invalid CSR:%s%s", (herr & kErrColRange) ? " column index >= cols;" : "",
-                       (herr & kErrPtrOrder) ? " row_ptr not monotone / out of range;" : "");
+                       (herr & kErrPtrOrder) ? " row_ptr not monotone, out of range, or not running from 0 to nnz;" : "");
     }
     h->rows = rows; h->cols = cols; h->nnz = nnz;
     h->device_bytes = nnz * (half_mode(h) ? 4ull : 6ull) + (nnz + 7) / 8 + (nch + 1) * 8ull + nch * 4ull + (has_empty ? n_nonempty * 4ull : 0ull);
@@ -341,6 +341,10 @@ void launch_single_query(Handle *h, uint32_t q, uint32_t k, cudaStream_t s, bool
 
 int pipe_init(Handle *h) {
     if (h->d_pipe_state) return TKS_OK;
+    {
+        const int want = (int)env_u32("TKS_PIPE_SLOTS", (uint32_t)Handle::kPipeSlots);
+        h->pipe_slots = want < 2 ? 2 : (want > Handle::kPipeSlots ? Handle::kPipeSlots : want);
+    }
     int lo = 0, hi = 0;
     TKS_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically lowest = greatest priority
     // The block scheduler serves pending grids by priority, then age, and does not look past one whose CTAs do not fit:
@@ -539,8 +543,10 @@ int tks_create(const tks_config *cfg, tks_handle **out) {
         if (cfg->fixed_width < 17 || cfg->fixed_width > 32) { g_create_error = "fixed_width outside 17..32"; return TKS_EINVAL; }
         if (cfg->max_cols > 1024) { g_create_error = "BS-CSR column field is 10 bits: max_cols <= 1024"; return TKS_EINVAL; }
         const int B = tks_bscsr_packet_size(cfg->fixed_width);
-        if (cfg->limited_finished_rows < 1 || cfg->limited_finished_rows > B || cfg->limited_finished_rows > 16) {
-            g_create_error = "limited_finished_rows outside 1..min(B,16)"; return TKS_EINVAL;
+        // the kernels are instantiated for LIMITED_FINISHED_ROWS 1..4 (types.hpp:77 ships 4; its "clean" design
+        // LFR = BSCSR_PACKET_SIZE, types.hpp:76, is not built): say so at create, not at the first run
+        if (cfg->limited_finished_rows < 1 || cfg->limited_finished_rows > B || cfg->limited_finished_rows > 4) {
+            g_create_error = "limited_finished_rows outside 1..4"; return TKS_EINVAL;
         }
         if (cfg->local_k < 1 || cfg->local_k > 64) { g_create_error = "local_k outside 1..64"; return TKS_EINVAL; }
         if (cfg->partitions < 1 || cfg->partitions > 4096) { g_create_error = "partitions outside 1..4096"; return TKS_EINVAL; }
@@ -1075,10 +1081,13 @@ int tks_submit(tks_handle *h, const float *d_query, uint32_t k, uint32_t flags, 
     if (rc) return rc;
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     const uint32_t seq = h->pipe_seq + 1u;
-    const int slot = (int)(seq % (uint32_t)tks::Handle::kPipeSlots);
+    const int slot = (int)(seq % (uint32_t)h->pipe_slots);
     if (h->pipe_busy[slot]) {
-        // the slot's previous query (two submits ago) must have been selected before its scratch is reused: this is the
-        // only place a submit blocks the host, and it bounds the queries in flight
+        // the slot's previous query (pipe_slots submits ago) must have been selected before its scratch is reused: this
+        // is the only place a submit blocks the host, and it bounds the queries in flight.  Four slots let the host
+        // enqueue the sample of a query a whole step before its main kernel needs the threshold (the sample takes
+        // ~130 us beside a running main kernel), and let the select of a step wait for a slow peer GPU for up to two
+        // steps without stalling this GPU's stream.
         TKS_CUDA(h, cudaEventSynchronize(h->pipe_ev_done[slot]));
         h->pipe_busy[slot] = false;
     }

@@ -54,7 +54,10 @@ __global__ void csr_mark_rows_kernel(const P *__restrict__ ptr, uint64_t rows, u
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const uint64_t b = ptr[r], e = ptr[r + 1];
-    if (e < b || e > nnz) { atomicOr(err, kErrPtrOrder); nonempty_flag[r] = 0; return; }
+    // row_ptr must run from 0 to nnz: non-zeros in front of ptr[0] or behind ptr[rows] would silently join a
+    // neighbouring row's score
+    const bool bad_ends = (r == 0 && b != 0) || (r + 1 == rows && e != nnz);
+    if (e < b || e > nnz || bad_ends) { atomicOr(err, kErrPtrOrder); nonempty_flag[r] = 0; return; }
     nonempty_flag[r] = (b != e) ? 1u : 0u;
     if (b != e) atomicOr(&rowbits32[b >> 5], 1u << (b & 31u));   // little-endian: bit b%8 of byte b/8
 }

@@ -86,14 +86,15 @@ struct Handle {
 
     // pipelined submits (tks_submit; api.cu): per-slot scratch so that consecutive queries overlap.  The sample and
     // the select kernels run on two engine-owned streams, the main kernels on the caller's; hand-over by sequence
-    // numbers in RunState.  At most kPipeSlots queries are in flight.
-    static constexpr int kPipeSlots = 2;
+    // numbers in RunState.  At most pipe_slots (<= kPipeSlots) queries are in flight.
+    static constexpr int kPipeSlots = 4;
+    int pipe_slots = kPipeSlots;                                   // TKS_PIPE_SLOTS (2..4): A/B switch
     cudaStream_t pipe_sample_stream = nullptr, pipe_select_stream = nullptr;
-    cudaEvent_t pipe_ev_done[kPipeSlots] = {nullptr, nullptr};     // recorded after the slot's select kernel
+    cudaEvent_t pipe_ev_done[kPipeSlots] = {};                     // recorded after the slot's select kernel
     cudaEvent_t pipe_ev_query = nullptr;
-    bool pipe_busy[kPipeSlots] = {false, false};
+    bool pipe_busy[kPipeSlots] = {};
     RunState *d_pipe_state = nullptr;                              // [kPipeSlots]
-    uint64_t *d_pipe_pool[kPipeSlots] = {nullptr, nullptr};
+    uint64_t *d_pipe_pool[kPipeSlots] = {};
     uint32_t *d_pipe_sample_keys = nullptr;
     uint64_t *d_pipe_stamps = nullptr, *h_pipe_stamps = nullptr;   // %globaltimer at the end of every select, ring of kPipeStamps
     static constexpr uint32_t kPipeStamps = 4096;

@@ -154,12 +154,21 @@ int tks_coo2csr(const uint32_t *x, const uint32_t *y, const float *val, uint64_t
     return TKS_OK;
 }
 
+uint64_t tks_cache_source_tag(const char *source_path, int zero_indexed, int ignore_values) {
+    return source_path ? tkshost::cache_source_tag(source_path, zero_indexed, ignore_values) : 0;
+}
+
 int tks_cache_write_csr(const char *path, uint64_t rows, uint32_t cols, uint64_t nnz, const uint64_t *ptr64,
                         const uint32_t *idx, const float *val) {
+    return tks_cache_write_csr_tagged(path, rows, cols, nnz, ptr64, idx, val, 0);
+}
+
+int tks_cache_write_csr_tagged(const char *path, uint64_t rows, uint32_t cols, uint64_t nnz, const uint64_t *ptr64,
+                               const uint32_t *idx, const float *val, uint64_t source_tag) {
     if (!path || !ptr64 || (nnz && (!idx || !val))) { g_host_error = "null argument"; return TKS_EINVAL; }
     if (ptr64[rows] != nnz) { g_host_error = "ptr[rows] != nnz"; return TKS_EINVAL; }
     tkshost::CacheHeader h{};
-    h.kind = tkshost::kCacheCsr; h.cols = cols; h.rows = rows; h.nnz = nnz;
+    h.kind = tkshost::kCacheCsr; h.cols = cols; h.rows = rows; h.nnz = nnz; h.aux0 = source_tag;
     std::string err;
     if (tkshost::cache_write(path, h, {{ptr64, (rows + 1) * 8}, {idx, nnz * 4}, {val, nnz * 4}}, &err) != 0) {
         g_host_error = err; return TKS_EIO;
@@ -169,6 +178,11 @@ int tks_cache_write_csr(const char *path, uint64_t rows, uint32_t cols, uint64_t
 
 int tks_cache_read_csr(const char *path, uint64_t *rows, uint32_t *cols, uint64_t *nnz, uint64_t *ptr64, uint32_t *idx,
                        float *val) {
+    return tks_cache_read_csr_tagged(path, rows, cols, nnz, ptr64, idx, val, nullptr);
+}
+
+int tks_cache_read_csr_tagged(const char *path, uint64_t *rows, uint32_t *cols, uint64_t *nnz, uint64_t *ptr64,
+                              uint32_t *idx, float *val, uint64_t *source_tag) {
     if (!path || !rows || !cols || !nnz) { g_host_error = "null argument"; return TKS_EINVAL; }
     tkshost::CacheHeader h{};
     FILE *f = nullptr;
@@ -176,6 +190,7 @@ int tks_cache_read_csr(const char *path, uint64_t *rows, uint32_t *cols, uint64_
     if (tkshost::cache_open(path, tkshost::kCacheCsr, &h, &f, &err) != 0) { g_host_error = err; return TKS_EIO; }
     if (h.payload_bytes != (h.rows + 1) * 8 + h.nnz * 8) { std::fclose(f); g_host_error = std::string(path) + ": inconsistent header"; return TKS_EIO; }
     *rows = h.rows; *cols = h.cols; *nnz = h.nnz;
+    if (source_tag) *source_tag = h.aux0;
     if (!ptr64 && !idx && !val) { std::fclose(f); return TKS_OK; }          // size query
     if (!ptr64 || (h.nnz && (!idx || !val))) { std::fclose(f); g_host_error = "null output array"; return TKS_EINVAL; }
     if (tkshost::cache_read_sections(f, h, {{ptr64, (h.rows + 1) * 8}, {idx, h.nnz * 4}, {val, h.nnz * 4}}, path, &err) != 0) {

@@ -135,11 +135,18 @@ int main(int argc, char *argv[]) {
     const char *path = options.use_sample_matrix ? DEFAULT_MTX_FILE : options.matrix_path.c_str();
     // -C: the parsed matrix is kept as a checksummed binary CSR next to the text file (tks_cache_*); a sweep re-reads
     // that instead of the Matrix-Market text
+    // The cache holds fp32 values, so only the float engine reads it (the fixed-point engine quantises the parsed
+    // doubles, utils.hpp:401, and must not depend on whether an earlier float run left a cache behind); and it is used
+    // only if it was made from THIS file as it is now, with the same -z / -v flags.
     bool from_cache = false;
-    if (!options.cache_path.empty()) {
-        uint64_t crow = 0, cnnz = 0;
+    const uint64_t want_tag = tks_cache_source_tag(path, options.zero_indexed, options.ignore_matrix_values);
+    if (!options.cache_path.empty() && options.use_float) {
+        uint64_t crow = 0, cnnz = 0, have_tag = 0;
         uint32_t ccol = 0;
-        if (tks_cache_read_csr(options.cache_path.c_str(), &crow, &ccol, &cnnz, nullptr, nullptr, nullptr) == TKS_OK) {
+        const int rc_size = tks_cache_read_csr_tagged(options.cache_path.c_str(), &crow, &ccol, &cnnz, nullptr, nullptr, nullptr, &have_tag);
+        if (rc_size == TKS_OK && have_tag != want_tag && debug)
+            std::cout << "matrix cache " << options.cache_path << " was made from another file, an older version of it or other -z/-v flags: ignored" << std::endl;
+        if (rc_size == TKS_OK && have_tag == want_tag) {
             std::vector<uint64_t> p64(crow + 1);
             std::vector<float> v32(cnnz);
             y.resize(cnnz);
@@ -168,7 +175,7 @@ int main(int argc, char *argv[]) {
             std::vector<float> cv(nnz);
             if (tkshost::coo2csr<int_type, float>(ptr32.data(), idx.data(), cv.data(), x, y, v32, rows, cols) == 0) {
                 std::vector<uint64_t> p64(ptr32.begin(), ptr32.end());
-                if (tks_cache_write_csr(options.cache_path.c_str(), rows, cols, nnz, p64.data(), idx.data(), cv.data()) != TKS_OK)
+                if (tks_cache_write_csr_tagged(options.cache_path.c_str(), rows, cols, nnz, p64.data(), idx.data(), cv.data(), want_tag) != TKS_OK)
                     std::cerr << "warning: could not write matrix cache " << options.cache_path << std::endl;
             }
         }

@@ -6,12 +6,14 @@
 // loaded CSR and, for the fixed-point engine, the packed partitions are kept in a versioned binary container:
 //
 //   header  (64 bytes)  magic "TKSMAT01" | kind (1 = CSR fp32, 2 = BS-CSR packets) | rows | cols | nnz |
-//                       aux0 (CSR: 0; BS-CSR: partitions) | aux1 (BS-CSR: fixed_width) | payload bytes |
+//                       aux0 (CSR: tag of the source file, 0 = untagged; BS-CSR: partitions) | aux1 (BS-CSR: fixed_width) | payload bytes |
 //                       FNV-1a 64 checksum of the payload
 //   payload             CSR:    ptr[rows+1] u64 | idx[nnz] u32 | val[nnz] f32
 //                       BS-CSR: packets_per_part[P] u64 | first_row[P] u32 | nnz_per_part[P] u64 | packets (64 B each)
 // Little-endian, no alignment padding inside the payload.  Truncated or altered files are rejected.
 #pragma once
+
+#include <sys/stat.h>
 
 #include <cstdint>
 #include <cstdio>
@@ -43,6 +45,11 @@ inline uint64_t fnv1a64(const void *data, size_t n, uint64_t h = 146959810393466
     for (; i < n; i++) h = (h ^ p[i]) * 1099511628211ull;
     return h;
 }
+
+// What a CSR cache was made from: path, size and modification time of the Matrix-Market file and the two loader flags
+// that change what the same text parses to (-z index base, -v ignore values).  A cache whose tag differs from the tag
+// of the matrix a run asks for is stale or foreign and must not be used.  Never 0 (0 = "untagged").
+inline uint64_t cache_source_tag(const char *source_path, int zero_indexed, int ignore_values);
 
 struct CacheSection { const void *data; size_t bytes; };
 
@@ -89,6 +96,18 @@ inline int cache_read_sections(FILE *f, const CacheHeader &hdr, const std::vecto
     if (total != hdr.payload_bytes) { if (err) *err = std::string(path) + ": section sizes do not add up to the payload"; return -1; }
     if (h != hdr.checksum) { if (err) *err = std::string(path) + ": checksum mismatch (corrupted cache)"; return -1; }
     return 0;
+}
+
+inline uint64_t cache_source_tag(const char *source_path, int zero_indexed, int ignore_values) {
+    struct stat st {};
+    uint64_t meta[4] = {0, 0, (uint64_t)(zero_indexed != 0), (uint64_t)(ignore_values != 0)};
+    if (::stat(source_path, &st) == 0) {
+        meta[0] = (uint64_t)st.st_size;
+        meta[1] = (uint64_t)st.st_mtim.tv_sec * 1000000000ull + (uint64_t)st.st_mtim.tv_nsec;
+    }
+    uint64_t h = fnv1a64(source_path, std::strlen(source_path));
+    h = fnv1a64(meta, sizeof meta, h);
+    return h ? h : 1;
 }
 
 }  // namespace tkshost

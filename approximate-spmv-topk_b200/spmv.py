@@ -186,7 +186,7 @@ class SpMV(_Base):
 
     # ---- pipelined submits: consecutive queries overlap (tks_submit) ----
     def submit(self, dptr, k=None, stream=0, exchange=False, query_ready=False):
-        """Enqueue one query (device pointer to num_cols fp32 values, read in place).  At most two are in flight."""
+        """Enqueue one query (device pointer to num_cols fp32 values, read in place).  At most four are in flight."""
         k = self.k if k is None else k
         flags = (capi.SUBMIT_EXCHANGE if exchange else 0) | (capi.SUBMIT_QUERY_READY if query_ready else 0)
         check(capi.lib().tks_submit(self.handle, C.c_void_p(dptr), k, flags, C.c_void_p(stream)), self.handle)

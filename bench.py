@@ -188,32 +188,90 @@ def cpu_reference(ptr, idx, val, queries, k, max_seconds=25.0, min_steps=1):
     return times, kind, cores, results
 
 
+def standin_f64(ptr, idx, val, queries, k, max_seconds=15.0):
+    """BASELINE.md section 3 item 2 / test_cpu.py:91-105 semantics with the absent sparse_dot_topn replaced by what that
+    call computes for a one-column right-hand side: float64 scipy `csr @ vec`, entries <= 0 dropped, global top-k by
+    argpartition (test_cpu.py's own stand-in, imported from the repo-root driver).  The CSR is built before the clock
+    starts, as test_cpu.py builds it before its timed loop.  scipy's product is single-threaded."""
+    import scipy.sparse as sp
+    import test_cpu
+    a = sp.csr_matrix((val.astype(np.float64), idx.astype(np.int64), ptr.astype(np.int64)),
+                      shape=(ptr.size - 1, int(queries[0].size)))
+    times, t_start = [], time.perf_counter()
+    for q in queries:
+        t0 = time.perf_counter()
+        test_cpu.topk_standin(a, q.astype(np.float64), k)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > max_seconds:
+            break
+    return times
+
+
+def reference_matrix(wl, rows_wanted, args):
+    """The benchmark matrix for the CPU arm: generated in HBM by the same generator the GPU arm uses (input
+    preparation, nothing of it is timed) and copied to the host; without a GPU, the NumPy restatement of the
+    reference's generator on a bounded number of rows.  Returns (ptr, idx, val, rows, how)."""
+    from _pkg import pkg
+    tks = pkg()
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    rows = rows_wanted
+    while rows > 1_000_000 and rows * wl["deg"] * 24 > avail // 2:      # ptr + idx + val + COO rows + slack
+        rows //= 2
+    try:
+        import torch
+        gpu = torch.cuda.is_available()
+    except Exception:
+        gpu = False
+    if gpu:
+        eng = tks.SpMV(num_cols=wl["cols"], k=K)
+        eng.generate_synthetic(rows, wl["cols"], wl["deg"], wl["dist"], seed=SEED)
+        ptr, idx, val = eng.download_csr()
+        eng.close()
+        return ptr, idx, val, rows, "generated in HBM by tks_generate_synthetic (the GPU arm's matrix, seed 0) and copied to the host"
+    rows = min(rows, args.ref_rows or 2_000_000)
+    x, y, v = tks.create_matrices.create_sparse_matrix(rows, wl["cols"], wl["deg"], wl["dist"], seed=SEED)
+    return tks.create_matrices.csr_from_coo(x, rows), y, v.astype(np.float32), rows, "NumPy restatement of create_matrices.py (no GPU here)"
+
+
 def reference_arm(args):
-    """`--impl reference`: rank 0 only; bounded sample of the same workload on the host cores."""
+    """`--impl reference`: rank 0 only.  The reference's CPU Top-K SpMV over the GPU arm's configuration -- the whole
+    matrix (N = 1: 10M rows; N > 1: the N x 10M rows of the weak-scaled run), every step one query -- on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from _pkg import pkg
-    tks = pkg()
-    wl = WORKLOADS[args.workload or "cfg2"]
-    sample_rows = min(wl["rows"], args.ref_rows)
-    x, y, v = tks.create_matrices.create_sparse_matrix(sample_rows, wl["cols"], wl["deg"], wl["dist"], seed=SEED)
-    ptr = tks.create_matrices.csr_from_coo(x, sample_rows)
-    val = v.astype(np.float32)
+    wl_key = args.workload or "cfg2"
+    wl = WORKLOADS[wl_key]
+    world = max(1, args.gpus)
+    weak = wl_key in ("cfg2", "cfg2h", "cfg2b")
+    rows_cfg = (args.rows or wl["rows"]) * (world if weak else 1)
+    rows_wanted = min(rows_cfg, args.ref_rows) if args.ref_rows else rows_cfg
+    ptr, idx, val, rows, how = reference_matrix(wl, rows_wanted, args)
     nnz = int(ptr[-1])
     queries = make_queries(wl["cols"], args.warmup + args.steps)
-    cpu_reference(ptr, y, val, queries[:args.warmup], K, max_seconds=1e9)
-    times, kind, cores, _ = cpu_reference(ptr, y, val, queries[args.warmup:], K, max_seconds=240.0, min_steps=args.steps)
+    cpu_reference(ptr, idx, val, queries[:args.warmup], K, max_seconds=1e9)
+    times, kind, cores, _ = cpu_reference(ptr, idx, val, queries[args.warmup:], K, max_seconds=600.0, min_steps=args.steps)
     sec = sum(times) / len(times)
     value = nnz / sec
-    sample = (f"{sample_rows} of {wl['rows']} rows of the same synthetic law ({nnz} nnz), {len(times)} queries, "
+    stand = standin_f64(ptr, idx, val, queries[args.warmup:args.warmup + 5], K) if rows <= 20_000_000 else []
+    sample = (f"{rows} of {rows_cfg} rows of the configuration ({nnz} nnz; {how}), {len(times)} queries, "
               f"reference spmv_coo_gold_top_k over {cores} row blocks in {cores} host threads "
               f"(sparse_dot_topn is absent from the image)")
+    cpu = {"value": value, "unit": "nnz/s", "cores": cores, "kind": kind, "sample": sample, "same_config": rows == rows_cfg}
+    if stand:
+        ssec = sum(stand) / len(stand)
+        cpu["stand_in"] = {"value": nnz / ssec, "unit": "nnz/s", "cores": 1, "kind": "port", "ms_per_query": ssec * 1e3,
+                           "what": "test_cpu.py:91-105 with sparse_dot_topn (absent, un-pinned) replaced by float64 scipy csr @ vec + "
+                                   "argpartition top-k (BASELINE.md 3.2), same matrix, %d queries; scipy's product runs on one thread" % len(stand)}
     line = {"impl": "reference", "metric": "topk_spmv_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": args.gpus,
             "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak" if (args.workload or "cfg2") == "cfg2" else "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": wl["name"], "k": K},
-            "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": cores, "kind": kind, "sample": sample},
+            "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": wl["name"] + (f", weak-scaled: {world} shards of {wl['rows']} rows" if weak and world > 1 else ""),
+                                            "rows": rows, "cols": wl["cols"], "nnz": nnz, "k": K},
+            "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -276,6 +334,21 @@ def ours(args):
         dist.destroy_process_group()
     if rank == 0 and not ok:
         raise SystemExit("parity check failed (see parity_n / parity in the line above)")
+
+
+def aligned_start(torch, dist, world):
+    """The ranks leave a barrier hundreds of microseconds apart (host scheduling), and with a per-step exchange the
+    first step of the timed region would wait for the last rank to arrive -- a start-up skew charged to K = 20 short
+    steps.  All ranks are processes of one host, so they agree on a wall-clock instant a few milliseconds ahead and
+    spin until it: every rank's timed region then opens within microseconds of the others'."""
+    if world <= 1:
+        return
+    t = torch.tensor([time.time() + 0.004], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    torch.cuda.synchronize()
+    t_go = float(t.item())
+    while time.time() < t_go:
+        pass
 
 
 def merge_lists(lists, k):
@@ -353,6 +426,7 @@ def float_workload(tks, torch, dist, wl_key, args, world, rank, local, tstream, 
         sampler.start()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    aligned_start(torch, dist, world)
     sampler.mark("timed")
     e0.record()
     for i in range(steps):
@@ -577,14 +651,18 @@ def load_traffic(wl_key):
 
 
 def cpu_baseline_leg(tks, eng, queries, idx_gpu, val_gpu, args):
-    """cpu_baseline on a bounded sample of the SAME matrix (first rows of the resident CSR)."""
+    """cpu_baseline over the SAME matrix: the reference's CPU gold on all host threads for a bounded number of queries
+    (~20 s), and the float64 stand-in of test_cpu.py's sparse_dot_topn call beside it."""
     ptr, idx, val = eng.download_csr()
-    sample_rows = min(ptr.size - 1, args.ref_rows)
+    rows = ptr.size - 1
+    sample_rows = min(rows, args.ref_rows) if args.ref_rows else rows
     e = int(ptr[sample_rows])
-    times, kind, cores, _ = cpu_reference(ptr[:sample_rows + 1], idx[:e], val[:e], queries, K, max_seconds=20.0)
+    times, kind, cores, _ = cpu_reference(ptr[:sample_rows + 1], idx[:e], val[:e], queries, K, max_seconds=15.0)
     sec = sum(times) / len(times)
+    stand = standin_f64(ptr[:sample_rows + 1], idx[:e], val[:e], queries[:5], K, max_seconds=10.0)
+    ssec = sum(stand) / len(stand)
     # top-K recall (the reference's "precision", host_spmv_bscsr.cpp:646-648) of the engine's last result against the
-    # reference gold over the WHOLE matrix for that query (one query: a fraction of a second on the host cores)
+    # reference gold over the WHOLE matrix for that query
     _, _, _, full = cpu_reference(ptr, idx, val, queries[-1:], K, max_seconds=1e9)
     gi, gv = full[0]
     inter = len(set(gi.tolist()) & set(np.asarray(idx_gpu).tolist()))
@@ -592,9 +670,12 @@ def cpu_baseline_leg(tks, eng, queries, idx_gpu, val_gpu, args):
     kth = float(gv[-1])
     miss = [float(v) for i, v in zip(gi.tolist(), gv.tolist()) if i not in set(np.asarray(idx_gpu).tolist())]
     return {"value": e / sec, "unit": "nnz/s", "cores": cores, "kind": kind,
-            "sample": f"first {sample_rows} rows ({e} nnz) of the benchmark matrix, {len(times)} queries, "
-                      f"reference spmv_coo_gold_top_k over {cores} row blocks in {cores} threads",
+            "sample": f"{'the whole' if sample_rows == rows else 'first ' + str(sample_rows) + ' rows of the'} benchmark matrix "
+                      f"({sample_rows} rows, {e} nnz), {len(times)} queries, reference spmv_coo_gold_top_k over {cores} row blocks in {cores} threads",
             "ms_per_query_on_sample": sec * 1e3,
+            "stand_in": {"value": e / ssec, "unit": "nnz/s", "cores": 1, "kind": "port", "ms_per_query": ssec * 1e3,
+                         "what": "test_cpu.py:91-105 with sparse_dot_topn (absent, un-pinned) replaced by float64 scipy csr @ vec + "
+                                 "argpartition top-k (BASELINE.md 3.2), same rows, %d queries; scipy's product runs on one thread" % len(stand)},
             "recall_vs_reference_gold_full_matrix": {"k": K, "precision": inter / K,
                                                      "max_rel_gap_of_missed_rows_to_kth": max([abs(v - kth) / kth for v in miss], default=0.0),
                                                      "max_abs_score_diff": float(np.max(np.abs(np.sort(gv)[::-1] - np.sort(np.asarray(val_gpu))[::-1])))}}
@@ -702,7 +783,7 @@ def ours_batched(args, tks, wl, rows_total, peak_gbs, peak_src, world, rank, loc
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         ptr, idx, val = eng.download_csr()
-        sample_rows = min(ptr.size - 1, args.ref_rows // 4)
+        sample_rows = min(ptr.size - 1, (args.ref_rows or 2_000_000) // 4)
         e = int(ptr[sample_rows])
         times, kind, cores, _ = cpu_reference(ptr[:sample_rows + 1], idx[:e], val[:e], hq[0][:8], K, max_seconds=20.0)
         sec = sum(times) / len(times)
@@ -837,7 +918,7 @@ def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
     if not args.no_cpu:
         sys.path.insert(0, str(ROOT / "oracle"))
         import oracle
-        sample_rows = min(rows_total, args.ref_rows // 4)
+        sample_rows = min(rows_total, (args.ref_rows or 2_000_000) // 4)
         e = int(ptr[sample_rows])
         t0 = time.perf_counter()
         packed = oracle.pack_bscsr(x[:e], idx[:e], val32[:e], sample_rows, P, W)
@@ -880,7 +961,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS.keys()])
     ap.add_argument("--rows", type=int, default=0, help="override the workload's total rows (debug)")
-    ap.add_argument("--ref-rows", type=int, default=2_000_000, help="rows of the CPU sample")
+    ap.add_argument("--ref-rows", type=int, default=0, help="cap on the rows the CPU legs run over (0 = the whole configuration)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cfg4", action="store_true", help="N > 1: skip the BASELINE config 4 sub-record")
     ap.add_argument("--batch-fma", action="store_true", help="cfg5: fused multiply-add arithmetic")

@@ -219,7 +219,7 @@ int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream);  /* e
  *   flags    TKS_SUBMIT_QUERY_READY: the query's bytes are already complete in memory at the time of the call
  *            (otherwise the sample stream is made to wait for the work enqueued on `cuda_stream` so far);
  *            TKS_SUBMIT_EXCHANGE: several GPUs -- every rank submits the same step (tks_run_exchange_async rules).
- * At most two queries are in flight: a third submit blocks the host until the first one's select has finished.
+ * At most four queries are in flight: a fifth submit blocks the host until the first one's select has finished.
  * tks_read_result (synchronises) returns the LAST submitted query's result; tks_pipeline_wait makes `cuda_stream`
  * wait for it on the device without blocking the host.  tks_pipeline_stamps returns, for each of the last `capacity`
  * submits (oldest first), TKS_PIPE_STAMP_WORDS %globaltimer nanosecond stamps written by the kernels themselves:
@@ -285,6 +285,15 @@ int tks_cache_write_csr(const char *path, uint64_t rows, uint32_t cols, uint64_t
                         const uint32_t *idx, const float *val);
 int tks_cache_read_csr(const char *path, uint64_t *rows, uint32_t *cols, uint64_t *nnz, uint64_t *ptr64,
                        uint32_t *idx, float *val);
+/* The same with a tag that says what the cache was made from: tks_cache_source_tag hashes the path, size and
+ * modification time of the Matrix-Market file and the loader flags that change what the text parses to (index base,
+ * ignore values).  A reader compares the stored tag with the tag of the matrix it was asked for and ignores a cache
+ * that is stale or belongs to another file (0 = the cache is untagged).                                         */
+uint64_t tks_cache_source_tag(const char *source_path, int zero_indexed, int ignore_values);
+int tks_cache_write_csr_tagged(const char *path, uint64_t rows, uint32_t cols, uint64_t nnz, const uint64_t *ptr64,
+                               const uint32_t *idx, const float *val, uint64_t source_tag);
+int tks_cache_read_csr_tagged(const char *path, uint64_t *rows, uint32_t *cols, uint64_t *nnz, uint64_t *ptr64,
+                              uint32_t *idx, float *val, uint64_t *source_tag);
 int tks_cache_write_bscsr(const char *path, uint32_t rows, uint32_t cols, int fixed_width, uint32_t partitions,
                           const uint64_t *packets_per_part, const uint32_t *first_row,
                           const uint64_t *nnz_per_part, const void *packets);

@@ -47,7 +47,9 @@ def test(t, s, c, d, n, input_matrix, out_folder, designs, niter, k):
             output_file = os.path.join(out_folder, f"{t}_{s}_{c}_{d}_{n}_{name}_{k}_{niter}.csv")
             cmd = B200_CMD.format(B200_EXE, "-d" if DEBUG else "", niter, input_matrix, k, "-z" if ZERO_INDEXED else "", flags, output_file)
             print(f"running {cmd}", flush=True)
-            results.append(subprocess.run(cmd, shell=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE))
+            # `| tee` (kept from the reference's command templates, test_spmv_topk.py:62-64) would make the shell report
+            # tee's status: pipefail keeps the executable's, so that a failing run is counted
+            results.append(subprocess.run(["bash", "-o", "pipefail", "-c", cmd], stdout=subprocess.PIPE, stderr=subprocess.PIPE))
     elif t == "cpu":
         output_file = os.path.join(out_folder, f"{t}_{s}_{c}_{d}_{n}_{k}_{niter}.csv")
         cmd = CPU_CMD.format(sys.executable, "-d" if DEBUG else "", niter, "-z" if ZERO_INDEXED else "", input_matrix, k, output_file)

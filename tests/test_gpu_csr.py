@@ -170,7 +170,12 @@ def test_errors(cuda_required, tks):
     val = np.ones(4, np.float32)
     with pytest.raises(tks.capi.TksError, match="column index"):
         tks.SpMV(ptr, col, val, 2, 1024)
-    with tks.SpMV(ptr, np.array([0, 1, 2, 3], np.uint32), val, 2, 1024, k=100) as s:
+    good_col = np.array([0, 1, 2, 3], np.uint32)
+    # row_ptr must run from 0 to nnz: stray non-zeros in front of ptr[0] or behind ptr[rows] are rejected, not scored
+    for bad_ptr in ([1, 2, 4], [0, 2, 3], [0, 3, 2]):
+        with pytest.raises(tks.capi.TksError, match="row_ptr"):
+            tks.SpMV(np.array(bad_ptr, np.uint64), good_col, val, 2, 1024)
+    with tks.SpMV(ptr, good_col, val, 2, 1024, k=100) as s:
         with pytest.raises(tks.capi.TksError, match="no query"):
             s()
         s.reset(np.ones(1024, np.float32))

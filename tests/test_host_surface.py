@@ -32,6 +32,18 @@ def test_create_without_gpu_fails_loudly(tks):
         tks.SpMV(num_cols=1024)
 
 
+def test_create_rejects_knob_values_the_kernels_are_not_built_for(tks):
+    """Checked before any CUDA call: LIMITED_FINISHED_ROWS above 4 (types.hpp:76's "clean" design LFR = B is not
+    instantiated) must fail at create with a message, not at the first run."""
+    import ctypes as C
+    L = tks.capi.lib()
+    for lfr in (0, 5, 15):
+        cfg = tks.capi.default_config(mode=tks.capi.MODE_FIXED_BSCSR, limited_finished_rows=lfr)
+        h = C.c_void_p()
+        assert L.tks_create(C.byref(cfg), C.byref(h)) == tks.capi.TKS_EINVAL
+        assert b"limited_finished_rows" in L.tks_last_error(None)
+
+
 @pytest.mark.parametrize("W", [20, 21, 25, 26, 32])
 def test_packet_size_and_quantisation(tks, orc, W):
     assert tks.capi.bscsr_packet_size(W) == orc.packet_size(W) == 511 // (W + 14)

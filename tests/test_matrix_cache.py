@@ -65,3 +65,37 @@ def test_corruption_is_detected(tks, csr, tmp_path):
     # the writer refuses an inconsistent CSR
     with pytest.raises(tks.capi.TksError, match="ptr"):
         tks.capi.cache_write_csr(tmp_path / "x", ptr[:-1], idx, val, 1024)
+
+
+def test_csr_cache_carries_a_tag_of_its_source(tks, tmp_path):
+    """The host executable only trusts a cache made from the same Matrix-Market file (path, size, mtime) with the same
+    -z / -v flags (main_b200.cpp): the tag travels in the header."""
+    import ctypes as C
+    import os
+    L = tks.capi.lib()
+    L.tks_cache_source_tag.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    L.tks_cache_source_tag.restype = C.c_uint64
+    L.tks_cache_write_csr_tagged.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.tks_cache_read_csr_tagged.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    src = tmp_path / "m.mtx"
+    src.write_text("%%MatrixMarket matrix coordinate real general\n%\n2 2 2\n1 1 0.5\n2 2 0.25\n")
+    t0 = L.tks_cache_source_tag(str(src).encode(), 0, 0)
+    assert t0 != 0 and t0 == L.tks_cache_source_tag(str(src).encode(), 0, 0)
+    assert t0 != L.tks_cache_source_tag(str(src).encode(), 1, 0) and t0 != L.tks_cache_source_tag(str(src).encode(), 0, 1)
+    ptr = np.array([0, 1, 2], np.uint64)
+    idx = np.array([0, 1], np.uint32)
+    val = np.array([0.5, 0.25], np.float32)
+    cache = str(tmp_path / "m.tkscsr").encode()
+    assert L.tks_cache_write_csr_tagged(cache, 2, 2, 2, ptr.ctypes.data, idx.ctypes.data, val.ctypes.data, t0) == 0
+    rows, cols, nnz, tag = C.c_uint64(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+    assert L.tks_cache_read_csr_tagged(cache, C.byref(rows), C.byref(cols), C.byref(nnz), None, None, None, C.byref(tag)) == 0
+    assert (rows.value, cols.value, nnz.value, tag.value) == (2, 2, 2, t0)
+    # the file changes (content and mtime): its tag no longer matches the cache's
+    src.write_text("%%MatrixMarket matrix coordinate real general\n%\n2 2 2\n1 1 0.75\n2 2 0.25\n")
+    os.utime(src, ns=(1, 1))
+    assert L.tks_cache_source_tag(str(src).encode(), 0, 0) != t0
+    # untagged writes read back as tag 0
+    tks.capi.cache_write_csr(tmp_path / "u.tkscsr", ptr, idx, val, 2)
+    assert L.tks_cache_read_csr_tagged(str(tmp_path / "u.tkscsr").encode(), C.byref(rows), C.byref(cols), C.byref(nnz), None, None, None, C.byref(tag)) == 0
+    assert tag.value == 0
