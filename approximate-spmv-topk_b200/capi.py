@@ -54,7 +54,7 @@ SYMBOLS = [
     "tks_download_csr", "tks_download_csr_rows", "tks_set_query", "tks_set_query_device", "tks_run", "tks_run_async",
     "tks_read_result", "tks_read_partition_results", "tks_result_keys_device", "tks_merge_keys_device", "tks_merge_keys_batched_device",
     "tks_peer_init", "tks_peer_connect", "tks_run_exchange_async", "tks_peer_exchange_async",
-    "tks_submit", "tks_pipeline_wait", "tks_pipeline_stamps",
+    "tks_submit", "tks_submit_host", "tks_fetch", "tks_pipeline_wait", "tks_pipeline_stamps",
     "tks_set_profile_kernels", "tks_get_stats", "tks_bscsr_packet_size", "tks_fixed32_from_double", "tks_fixedW_from_fixed32",
     "tks_pack_bscsr", "tks_merge_partition_words", "tks_read_mtx", "tks_coo2csr",
     "tks_cache_write_csr", "tks_cache_read_csr", "tks_cache_source_tag", "tks_cache_write_csr_tagged", "tks_cache_read_csr_tagged", "tks_cache_write_bscsr", "tks_cache_read_bscsr",
@@ -105,6 +105,8 @@ def lib() -> C.CDLL:
     L.tks_run_exchange_async.argtypes = [vp, C.c_uint32, vp]
     L.tks_peer_exchange_async.argtypes = [vp, C.c_uint32, vp]
     L.tks_submit.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
+    L.tks_submit_host.argtypes = [vp, vp, C.c_uint32, C.c_uint32, u64p]
+    L.tks_fetch.argtypes = [vp, C.c_uint64, vp, vp, u32p]
     L.tks_pipeline_wait.argtypes = [vp, vp]
     L.tks_pipeline_stamps.argtypes = [vp, vp, C.c_uint32, u32p]
     L.tks_set_profile_kernels.argtypes = [vp, C.c_int]

@@ -365,6 +365,10 @@ int pipe_init(Handle *h) {
     TKS_CUDA(h, cudaMalloc(&h->d_pipe_stamps, stamp_bytes));
     TKS_CUDA(h, cudaMemset(h->d_pipe_stamps, 0, stamp_bytes));
     TKS_CUDA(h, cudaMallocHost(&h->h_pipe_stamps, stamp_bytes));
+    const size_t qbytes = (size_t)Handle::kPipeSlots * h->cfg.max_cols * sizeof(float);
+    TKS_CUDA(h, cudaMalloc(&h->d_pipe_query, qbytes));
+    TKS_CUDA(h, cudaMallocHost(&h->h_pipe_query, qbytes));
+    TKS_CUDA(h, cudaMallocHost(&h->h_pipe_res, (size_t)Handle::kPipeSlots * (64u + 2u * (size_t)h->kmax) * 4u));
     TKS_CUDA(h, cudaMalloc(&h->d_pipe_state, Handle::kPipeSlots * sizeof(RunState)));
     TKS_CUDA(h, cudaMemset(h->d_pipe_state, 0, Handle::kPipeSlots * sizeof(RunState)));
     return TKS_OK;
@@ -644,6 +648,7 @@ void tks_destroy(tks_handle *h) {
     cudaFreeHost(h->h_res_block); cudaFreeHost(h->h_x);
     cudaFree(h->d_pipe_state); cudaFree(h->d_pipe_sample_keys); cudaFree(h->d_pipe_stamps);
     cudaFreeHost(h->h_pipe_stamps);
+    cudaFree(h->d_pipe_query); cudaFreeHost(h->h_pipe_query); cudaFreeHost(h->h_pipe_res);
     for (int i = 0; i < tks::Handle::kPipeSlots; i++) {
         cudaFree(h->d_pipe_pool[i]);
         if (h->pipe_ev_done[i]) cudaEventDestroy(h->pipe_ev_done[i]);
@@ -874,6 +879,8 @@ int tks_read_result(tks_handle *h, uint32_t query, uint32_t *idx_out, void *val_
         if (query != 0) return h->fail(TKS_EINVAL, "BS-CSR mode has a single query");
         return bscsr_read_result(h, idx_out, (uint32_t *)val_out, h->last_k, count);
     }
+    if (h->last_run_pipelined && h->res_on_host)
+        return h->fail(TKS_ESTATE, "the last query went through tks_submit_host: its result is read with tks_fetch(ticket)");
     if (!h->have_result) {
         // results of an async run: fetch now
         if (h->last_k == 0) return h->fail(TKS_ESTATE, "no run yet");
@@ -1066,8 +1073,16 @@ int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream) {
 
 // ---- pipelined submits ---------------------------------------------------------------------------------------------
 
-int tks_submit(tks_handle *h, const float *d_query, uint32_t k, uint32_t flags, void *cuda_stream) {
-    if (!h || !d_query) return TKS_EINVAL;
+}  // extern "C"
+
+namespace {
+
+size_t pipe_res_words(const Handle *h) { return 64u + 2u * (size_t)h->kmax; }
+
+// One query into the pipeline.  host_query != nullptr: the query comes from host memory (copied on the sample stream
+// in front of the sample kernel) and the result goes to the slot's pinned host block (tks_fetch).
+int pipe_submit(tks_handle *h, const float *d_query, const float *host_query, uint32_t k, uint32_t flags, cudaStream_t s,
+                uint64_t *ticket) {
     if (h->cfg.mode != TKS_MODE_FLOAT_CSR) return h->fail(TKS_ESTATE, "float mode only");
     if (!h->have_matrix) return h->fail(TKS_ESTATE, "no matrix uploaded");
     if (k == 0 || k > h->kmax) return h->fail(TKS_EINVAL, "k=%u outside 1..%u", k, h->kmax);
@@ -1079,7 +1094,6 @@ int tks_submit(tks_handle *h, const float *d_query, uint32_t k, uint32_t flags, 
     TKS_CUDA(h, cudaSetDevice(h->device));
     int rc = pipe_init(h);
     if (rc) return rc;
-    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     const uint32_t seq = h->pipe_seq + 1u;
     const int slot = (int)(seq % (uint32_t)h->pipe_slots);
     if (h->pipe_busy[slot]) {
@@ -1095,11 +1109,26 @@ int tks_submit(tks_handle *h, const float *d_query, uint32_t k, uint32_t flags, 
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
     const CsrDevice m = csr_device(h);
     RunState *st = h->d_pipe_state + slot;
-    if (!(flags & TKS_SUBMIT_QUERY_READY)) {
-        // the query is produced by earlier work of the caller's stream: the sample stream has to see it too
-        TKS_CUDA(h, cudaEventRecord(h->pipe_ev_query, s));
-        TKS_CUDA(h, cudaStreamWaitEvent(h->pipe_sample_stream, h->pipe_ev_query, 0));
+    uint32_t *o_idx = h->d_res_idx, *o_cnt = h->d_res_count;
+    float *o_val = h->d_res_val;
+    if (host_query) {
+        float *hq = h->h_pipe_query + (size_t)slot * h->cfg.max_cols, *dq = h->d_pipe_query + (size_t)slot * h->cfg.max_cols;
+        std::memcpy(hq, host_query, (size_t)h->cols * sizeof(float));
+        TKS_CUDA(h, cudaMemcpyAsync(dq, hq, (size_t)h->cols * sizeof(float), cudaMemcpyHostToDevice, h->pipe_sample_stream));
+        d_query = dq;
+        // the select kernel stores indices, scores and the count straight into the slot's pinned host block
+        uint32_t *blk = h->h_pipe_res + (size_t)slot * pipe_res_words(h);
+        o_cnt = blk; o_idx = blk + 64; o_val = reinterpret_cast<float *>(blk + 64 + h->kmax);
+        h->pipe_slot_ticket[slot] = seq;
+    } else {
+        h->pipe_slot_ticket[slot] = 0;
+        if (!(flags & TKS_SUBMIT_QUERY_READY)) {
+            // the query is produced by earlier work of the caller's stream: the sample stream has to see it too
+            TKS_CUDA(h, cudaEventRecord(h->pipe_ev_query, s));
+            TKS_CUDA(h, cudaStreamWaitEvent(h->pipe_sample_stream, h->pipe_ev_query, 0));
+        }
     }
+    h->pipe_slot_k[slot] = k;
     // 1. threshold of THIS query on the sample stream: small CTAs that fit beside the main kernel still streaming the
     //    previous query
     uint64_t *stamp = h->d_pipe_stamps + (size_t)(seq % tks::Handle::kPipeStamps) * kStampWords;
@@ -1113,12 +1142,12 @@ int tks_submit(tks_handle *h, const float *d_query, uint32_t k, uint32_t flags, 
         const PeerExchange px = peer_args(h);
         h->peer_seq += 1;
         select_topk_kernel<true><<<1, lean_threads, lean_threads / 32u * 1024u, h->pipe_select_stream>>>(
-            h->d_pipe_pool[slot], 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys, h->d_res_idx, h->d_res_val, 0u,
-            h->d_res_count, nullptr, px, h->peer_seq, seq, spin_timeout_ms(), stamp, 0u);
+            h->d_pipe_pool[slot], 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys, o_idx, o_val, 0u,
+            o_cnt, nullptr, px, h->peer_seq, seq, spin_timeout_ms(), stamp, 0u);
     } else {
         select_topk_kernel<false><<<1, lean_threads, lean_threads / 32u * 1024u, h->pipe_select_stream>>>(
-            h->d_pipe_pool[slot], 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys, h->d_res_idx, h->d_res_val, 0u,
-            h->d_res_count, nullptr, PeerExchange{}, 0u, seq, spin_timeout_ms(), stamp, 0u);
+            h->d_pipe_pool[slot], 0u, st, 0u, 0u, k, tie_higher, h->d_res_keys, o_idx, o_val, 0u,
+            o_cnt, nullptr, PeerExchange{}, 0u, seq, spin_timeout_ms(), stamp, 0u);
     }
     TKS_CUDA(h, cudaGetLastError());
     TKS_CUDA(h, cudaEventRecord(h->pipe_ev_done[slot], h->pipe_select_stream));
@@ -1128,12 +1157,48 @@ int tks_submit(tks_handle *h, const float *d_query, uint32_t k, uint32_t flags, 
     h->batch = 1;
     h->last_k = k;
     h->have_result = false;
-    h->res_on_host = false;
+    h->res_on_host = host_query != nullptr;
     h->last_run_batched = false;
     h->last_run_pipelined = true;
     h->overflow_check_pending = false;
     h->stats.launches_per_run = 3;
     h->stats.algorithmic_bytes = algorithmic_matrix_bytes(h) + (uint64_t)h->cols * 4ull + k * 8ull;
+    if (ticket) *ticket = seq;
+    return TKS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tks_submit(tks_handle *h, const float *d_query, uint32_t k, uint32_t flags, void *cuda_stream) {
+    if (!h || !d_query) return TKS_EINVAL;
+    return pipe_submit(h, d_query, nullptr, k, flags, cuda_stream ? (cudaStream_t)cuda_stream : h->stream, nullptr);
+}
+
+int tks_submit_host(tks_handle *h, const float *query, uint32_t k, uint32_t flags, uint64_t *ticket) {
+    if (!h || !query || !ticket) return TKS_EINVAL;
+    return pipe_submit(h, nullptr, query, k, flags, h->stream, ticket);
+}
+
+int tks_fetch(tks_handle *h, uint64_t ticket, uint32_t *idx_out, float *val_out, uint32_t *count) {
+    if (!h || !idx_out || !val_out) return TKS_EINVAL;
+    if (!h->d_pipe_state || ticket == 0 || ticket > h->pipe_seq) return h->fail(TKS_EINVAL, "unknown ticket");
+    const int slot = (int)(ticket % (uint64_t)h->pipe_slots);
+    if (h->pipe_slot_ticket[slot] != ticket)
+        return h->fail(TKS_ESTATE, "the result of ticket %llu is gone: at most %d queries are kept, fetch before submitting further",
+                       (unsigned long long)ticket, h->pipe_slots);
+    TKS_CUDA(h, cudaSetDevice(h->device));
+    TKS_CUDA(h, cudaEventSynchronize(h->pipe_ev_done[slot]));
+    h->pipe_busy[slot] = false;
+    const uint32_t *blk = h->h_pipe_res + (size_t)slot * pipe_res_words(h);
+    if (blk[0] == kPeerTimeout)
+        return h->fail(TKS_ECUDA, "device-side wait timed out (TKS_SPIN_TIMEOUT_MS): a rank of the box never delivered its "
+                                  "candidates, or a kernel of the pipelined submit never completed");
+    const uint32_t k = h->pipe_slot_k[slot];
+    std::memcpy(idx_out, blk + 64, k * 4u);
+    std::memcpy(val_out, blk + 64 + h->kmax, k * 4u);
+    if (count) *count = blk[0];
     return TKS_OK;
 }
 

@@ -67,6 +67,8 @@ struct RunState {
     uint32_t tau_seq;         // = seq once the sample kernel has published tau_key
     uint32_t main_ticket;     // CTAs of the main kernel that have handed over their survivors
     uint32_t main_seq;        // = seq once every CTA of the main kernel has
+    uint32_t error;           // a main-kernel CTA gave up waiting for the threshold (the query may not have arrived)
+    uint32_t pad[7];
 };
 
 struct U32x8 { uint32_t w[8]; };
@@ -583,20 +585,23 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
     float *xs = reinterpret_cast<float *>(smem_raw);
     uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (((m.cols + 1u) * 4u + 15u) & ~15u));
     pdl_trigger();   // the select kernel's CTA may be set up while this grid drains
-    for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<VT>(x[i]) : 0.0f;
-    __syncthreads();
     if (seq == 0) {
+        for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<VT>(x[i]) : 0.0f;
+        __syncthreads();
         pdl_wait();  // the query was complete before the sample kernel started; tau and the counters are not
     } else {
         // Pipelined submit (tks_submit): this grid follows the PREVIOUS query's main kernel in its stream and shares
         // nothing with it (per-slot state), so it does not wait for it -- its CTAs start streaming as that grid's CTAs
         // retire, and consecutive queries form one continuous stream.  What it needs is this query's threshold, which
-        // the sample kernel published from another stream (normally long ago).  Should it never arrive, the stream
-        // runs unfiltered: slower, still exact (the per-warp buffers compact).
+        // the sample kernel published from another stream (normally long ago); that kernel ran after the query's bytes
+        // had arrived (tks_submit_host copies them on the sample stream), so the query is staged only now.  Should the
+        // threshold never arrive in time, the stream runs unfiltered and the query is reported as failed (RunState::error).
         if (threadIdx.x == 0) {
-            spin_until_eq(&st->tau_seq, seq, (uint64_t)tau_wait_us * 1000ull);
+            if (!spin_until_eq(&st->tau_seq, seq, (uint64_t)tau_wait_us * 1000ull)) atomicOr(&st->error, 1u);
             if (stamp && blockIdx.x == 0) stamp[kStampMainBegin] = global_timer_ns();
         }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<VT>(__ldcg(x + i)) : 0.0f;
         __syncthreads();
     }
 
@@ -813,8 +818,18 @@ select_topk_kernel(const uint64_t *__restrict__ pool, uint32_t pool_stride, RunS
             if (stamp) stamp[kStampSelectBegin] = global_timer_ns();
         }
         __syncthreads();
-        if (!s_main_ok) {
-            if (tid == 0) *out_count = kPeerTimeout;
+        if (s_main_ok && st_reset->error) {
+            // the stream ran without its threshold, i.e. the sample kernel (and with it, possibly, the query's copy)
+            // never completed in time: the result cannot be trusted
+            __syncthreads();
+            if (tid == 0) { st_reset->error = 0; s_main_ok = 2; }
+            __syncthreads();
+        }
+        if (s_main_ok != 1) {
+            if (tid == 0) {
+                *out_count = kPeerTimeout;
+                if (s_main_ok == 2) reset_run_state(st_reset, st_reset->pool_count);   // the main kernel is done: the slot is reusable
+            }
             return;
         }
     }

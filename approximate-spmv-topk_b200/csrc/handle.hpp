@@ -98,6 +98,10 @@ struct Handle {
     uint32_t *d_pipe_sample_keys = nullptr;
     uint64_t *d_pipe_stamps = nullptr, *h_pipe_stamps = nullptr;   // %globaltimer at the end of every select, ring of kPipeStamps
     static constexpr uint32_t kPipeStamps = 4096;
+    float *d_pipe_query = nullptr, *h_pipe_query = nullptr;        // [kPipeSlots][max_cols]: queries of tks_submit_host (device / pinned)
+    uint32_t *h_pipe_res = nullptr;                                // [kPipeSlots][64 + 2 * kmax]: count | idx | val per slot, pinned
+    uint32_t pipe_slot_k[kPipeSlots] = {};                         // k of the query in the slot
+    uint64_t pipe_slot_ticket[kPipeSlots] = {};                    // ticket of the host-result query in the slot (0 = none)
     uint32_t pipe_seq = 0;                                         // sequence number of the last submitted query
     int pipe_last_slot = -1;
     int pipe_main_grid[4] = {0, 0, 0, 0};                          // grids of the 512-thread main kernels used here

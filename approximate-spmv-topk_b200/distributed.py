@@ -106,6 +106,17 @@ class ShardedSpMV:
         eng.reset_device(dptr, 1, stream)
         self.step(stream)
 
+    def submit_host(self, vec):
+        """Pipelined step fed from host memory (tks_submit_host): returns a ticket for fetch().  Peer mode or one rank."""
+        if self.batch != 1 or not (self.exchange_mode == "peer" or self.world == 1 or self.exchange_mode == "none"):
+            raise ValueError("host-fed pipelined steps need one query per step and the peer-memory exchange (or one rank)")
+        self.pipelined = True
+        return self.engine.submit_host(vec, self.k, exchange=self.exchange_mode == "peer")
+
+    def fetch(self, ticket):
+        """(values, GLOBAL row indices, count) of the step submit_host() gave `ticket` for; identical on every rank."""
+        return self.engine.fetch(ticket)
+
     def wait(self, stream=0):
         """Make `stream` wait for the last submitted step's (global) result."""
         if getattr(self, "pipelined", False):

@@ -193,6 +193,30 @@ class SpMV(_Base):
         self.k = k
         self.batch = 1
 
+    def submit_host(self, vec, k=None, exchange=False):
+        """The pipeline fed from host memory: enqueue `vec` (num_cols fp32 values), return a ticket for fetch().
+        The throughput form of reset(vec) + operator(): up to four queries are in flight."""
+        k = self.k if k is None else k
+        st = self.__dict__.get("_sh_stage")
+        if st is None or st[0].size != self.num_cols:
+            buf = np.empty(self.num_cols, np.float32)
+            st = self._sh_stage = (buf, _ptr(buf), C.c_uint64())
+        st[0][:] = np.asarray(vec, np.float32).reshape(-1)
+        check(capi.lib().tks_submit_host(self.handle, st[1], k, capi.SUBMIT_EXCHANGE if exchange else 0, C.byref(st[2])),
+              self.handle)
+        self.k = k
+        self.batch = 1
+        return st[2].value
+
+    def fetch(self, ticket):
+        """read_result() of the query submit_host() gave `ticket` for: (values float32[k], indices uint32[k], count)."""
+        out = self.__dict__.get("_fetch_stage")
+        if out is None:
+            idx, val, cnt = np.zeros(1024, np.uint32), np.zeros(1024, np.float32), C.c_uint32()
+            out = self._fetch_stage = (idx, val, cnt, _ptr(idx), _ptr(val), C.byref(cnt))
+        check(capi.lib().tks_fetch(self.handle, int(ticket), out[3], out[4], out[5]), self.handle)
+        return out[1][:self.k].copy(), out[0][:self.k].copy(), out[2].value
+
     def pipeline_wait(self, stream=0):
         """Make `stream` wait (on the device) for the result of the last submitted query."""
         check(capi.lib().tks_pipeline_wait(self.handle, C.c_void_p(stream)), self.handle)

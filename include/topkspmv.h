@@ -227,6 +227,15 @@ int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream);  /* e
  * resident, [5] select begins (pool complete), [6] select (+ exchange + merge) done -- the pipeline's timeline
  * without any event in the streams.  stamps_ns holds capacity * TKS_PIPE_STAMP_WORDS words.                   */
 #define TKS_PIPE_STAMP_WORDS 8
+/* The same pipeline fed from and read back into HOST memory -- the throughput form of reset(vec) + operator() +
+ * read_result(): tks_submit_host copies `query` (cols fp32 values, any host memory; it may be reused as soon as the
+ * call returns) to the device on the sample stream and returns a ticket; the select kernel of that query stores the
+ * sorted indices, scores and the count straight into a pinned host block; tks_fetch(ticket) waits for that query alone
+ * and copies its first k results out (val_out float[k]).  Results are kept for the last four tickets: fetch ticket t
+ * before submitting ticket t + 4.  Host-to-device and device-to-host traffic of every query is part of its step.  */
+int tks_submit_host(tks_handle *h, const float *query, uint32_t k, uint32_t flags, uint64_t *ticket);
+int tks_fetch(tks_handle *h, uint64_t ticket, uint32_t *idx_out, float *val_out, uint32_t *count);
+
 #define TKS_SUBMIT_EXCHANGE 1u
 #define TKS_SUBMIT_QUERY_READY 2u
 int tks_submit(tks_handle *h, const float *d_query, uint32_t k, uint32_t flags, void *cuda_stream);

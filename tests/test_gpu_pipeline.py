@@ -144,6 +144,40 @@ def test_pipeline_in_the_other_modes(cuda_required, tks, gen, mode):
                 assert cnt == want[i][2] and np.array_equal(idx, want[i][1]) and np.array_equal(val, want[i][0])
 
 
+@pytest.mark.parametrize("k", [100, 1024])
+def test_host_fed_pipeline_equals_the_blocking_verbs(cuda_required, tks, big, k):
+    """tks_submit_host / tks_fetch: host query in, host result out, up to four queries in flight; every result equals
+    reset(vec) + operator() + read_result() for the same query, bit for bit."""
+    x, y, v, ptr, rows = big
+    n = 30
+    queries = np.stack([make_query(1024, 2100 + i) for i in range(n)])
+    want = _plain_results(tks, ptr, y, v, rows, queries, k)
+    with tks.SpMV(ptr, y, v, rows, 1024, k=k) as s:
+        tickets, got = [], {}
+        for i in range(n):
+            tickets.append(s.submit_host(queries[i], k))
+            if i >= 3:
+                got[i - 3] = s.fetch(tickets[i - 3])
+        for i in range(n - 3, n):
+            got[i] = s.fetch(tickets[i])
+        for i in range(n):
+            val, idx, cnt = got[i]
+            assert cnt == want[i][2] and np.array_equal(idx, want[i][1]) and np.array_equal(val, want[i][0]), f"query {i}"
+        # a result that has been pushed out of the four slots is refused, not silently replaced
+        t_old = s.submit_host(queries[0], k)
+        for i in range(1, 5):
+            s.submit_host(queries[i], k)
+        with pytest.raises(tks.capi.TksError, match="gone"):
+            s.fetch(t_old)
+        with pytest.raises(tks.capi.TksError, match="tks_fetch"):
+            s.read_result()
+        # the blocking verbs still work afterwards
+        s.reset(queries[5])
+        s()
+        val, idx, cnt = s.read_result()
+        assert np.array_equal(idx, want[5][1]) and np.array_equal(val, want[5][0])
+
+
 def test_submit_rejects_bad_calls(cuda_required, tks, gen):
     x, y, v = gen.create_sparse_matrix(2000, 1024, 20, "gamma", seed=1)
     ptr = gen.csr_from_coo(x, 2000)
@@ -196,6 +230,16 @@ def _worker(rank, world, port, q, k, n):
             if i % 5 == 4 or i == n - 1:             # free-running in between
                 a, b, c = eng.read_result()
                 out.append((i, a.copy(), b.copy(), c))
+        # the host-fed form of the same steps: every step's global result is fetched, three steps behind
+        tickets = [None] * n
+        for i in range(n):
+            tickets[i] = sharded.submit_host(Q[i])
+            if i >= 3:
+                a, b, c = sharded.fetch(tickets[i - 3])
+                out.append((i - 3, a.copy(), b.copy(), c))
+        for i in range(n - 3, n):
+            a, b, c = sharded.fetch(tickets[i])
+            out.append((i, a.copy(), b.copy(), c))
     q.put((rank, out, sharded.exchange_mode))
     dist.barrier()
     eng.close()
@@ -225,8 +269,11 @@ def test_pipelined_exchange_over_ranks_equals_global_topk(cuda_required, tks, or
     v = v.astype(np.float32)
     if world > 1:
         assert {results[r][1] for r in results} == {"peer"}
+    yrefs = {}
     for j, (i, _, _, _) in enumerate(results[0][0]):
-        yref = orc.spmv_f32(x, y, v, make_query(cols, 300 + i), rows)
+        if i not in yrefs:
+            yrefs[i] = orc.spmv_f32(x, y, v, make_query(cols, 300 + i), rows)
+        yref = yrefs[i]
         order = np.lexsort((np.arange(rows), -yref.astype(np.float64)))[:k]
         for rank in range(world):
             _, val, idx, cnt = results[rank][0][j]
