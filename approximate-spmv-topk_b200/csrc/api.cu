@@ -32,18 +32,35 @@ uint32_t env_u32(const char *name, uint32_t dflt) {
     const char *v = std::getenv(name);
     return (v && *v) ? (uint32_t)std::strtoul(v, nullptr, 10) : dflt;
 }
-int pipe_threads(int variant) {
-    static const int t0 = (int)env_u32("TKS_PIPE_THREADS", 512u) / 32 * 32;   // A/B switch: 256..576
-    return variant == 0 ? (t0 < 256 ? 256 : (t0 > 576 ? 576 : t0)) : kCapThreads[variant];
+// CTA size of the main kernel.  16-bit value modes work on 16 non-zeros per lane (~80 registers): 2 x 12 warps per SM.
+int cap_threads(int variant, int vt) {
+    static const int half_t = (int)env_u32("TKS_MAIN_THREADS_16BIT", 384u) / 32 * 32;   // A/B switch
+    const int t = kCapThreads[variant];
+    if (vt == 0) return t;
+    const int ht = half_t < 128 ? 128 : (half_t > 384 ? 384 : half_t);
+    return t < ht ? t : ht;
 }
-int pipe_sample_threads() { static const int t = (int)env_u32("TKS_PIPE_SAMPLE_THREADS", 128u) / 32 * 32; return t < 32 ? 32 : (t > 256 ? 256 : t); }
+// ... inside a pipelined submit: leave room for one CTA of the sample kernel per SM (registers)
+int pipe_threads(int variant, int vt) {
+    static const int t0 = (int)env_u32("TKS_PIPE_THREADS", 512u) / 32 * 32;   // A/B switch: 256..576
+    // 72 registers: 2 x 10 warps; with 2 x 11 the sample CTAs (80 registers per thread) were measured NOT to fit beside
+    // them (r02i/j: the register file is allocated per SM sub-partition, and 6 x 2304 of its 16384 leave one sample warp)
+    static const int t16 = (int)env_u32("TKS_PIPE_THREADS_16BIT", 320u) / 32 * 32;
+    if (vt != 0) { const int c = cap_threads(variant, vt); return c < t16 ? c : t16; }
+    if (variant == 0) return t0 < 256 ? 256 : (t0 > 576 ? 576 : t0);
+    return variant == 1 ? 448 : kCapThreads[variant];   // CAP 512 uses 64 registers: 2 x 14 warps leave 8192 for the sample CTA
+}
+int pipe_sample_threads(int vt) {
+    static const int t = (int)env_u32("TKS_PIPE_SAMPLE_THREADS", 0u) / 32 * 32;
+    if (t >= 32) return t > 256 ? 256 : t;
+    return vt != 0 ? 64 : 128;   // 80 registers per thread in the 16-bit modes: 64 threads = 5120 registers
+}
 // L1 / shared-memory split requested for every kernel of the float path, in percent of the maximum (-1: the driver's
 // choice per kernel).  Kernels that share an SM in the pipelined path must agree on it: an SM cannot change the split
 // while CTAs are resident.
 int carveout_pct() { static const int v = std::getenv("TKS_CARVEOUT_PCT") ? std::atoi(std::getenv("TKS_CARVEOUT_PCT")) : -1; return v; }
 
-size_t main_smem_bytes(uint32_t cols, int variant, int threads = 0) {
-    if (threads == 0) threads = kCapThreads[variant];
+size_t main_smem_bytes(uint32_t cols, int variant, int threads) {
     return (((cols + 1u) * 4u + 15u) & ~15u) + (size_t)(threads / 32) * kCaps[variant] * 8u;
 }
 
@@ -56,7 +73,8 @@ inline int value_type(const Handle *h) { return h->cfg.value_type; }
 
 template <int CAP, int VT>
 cudaError_t prep_main_t(Handle *h, int variant) {
-    size_t smem = main_smem_bytes(h->cfg.max_cols, variant);
+    const int threads = cap_threads(variant, VT), pthreads = pipe_threads(variant, VT);
+    size_t smem = main_smem_bytes(h->cfg.max_cols, variant, threads);
     cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
@@ -64,18 +82,33 @@ cudaError_t prep_main_t(Handle *h, int variant) {
     // An SM cannot change its L1 / shared-memory split while CTAs are resident, so every kernel of the path asks for
     // the same split -- all shared memory (the matrix stream bypasses L1 anyway) -- or a CTA that needs a larger
     // carve-out than the resident kernel's would wait for the SM to drain.
-    if (carveout_pct() >= 0) {
-        e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP, VT>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct());
-        if (e != cudaSuccess) return e;
+    {
+        // The split the main kernel asks for must leave room for what shares its SMs in a pipelined submit: two of its
+        // own CTAs, two sample CTAs and the lean select CTA (left to itself the driver sizes the carve-out for the main
+        // kernel's CTAs alone, and a sample CTA that does not fit waits for the SM to drain).  The rest stays L1, which
+        // the stream needs for its loads in flight (with all of it turned into shared memory the kernel is 20 % slower).
+        int pct = carveout_pct();
+        if (pct < 0 && variant <= 1) {
+            size_t ss = ((size_t)h->cfg.max_cols + 1u) * 4u;
+            if (ss < (size_t)kHistScratchWords * 4u) ss = (size_t)kHistScratchWords * 4u;
+            const size_t need = 2u * (main_smem_bytes(h->cfg.max_cols, variant, pthreads) + 1024u) + 2u * (ss + 1024u + 64u) +
+                                (kSelectLeanDynSmem + sizeof(uint64_t) * kSelectSortCap + 2048u);
+            const size_t total = 228u * 1024u;
+            pct = (int)((need * 100u + total - 1u) / total);
+            if (pct > 100) pct = 100;
+        }
+        if (pct >= 0) {
+            e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP, VT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            if (e != cudaSuccess) return e;
+        }
     }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, VT>, kCapThreads[variant],
-                                                      smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, VT>, threads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     h->main_grid[variant] = per_sm * h->num_sms;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, VT>, pipe_threads(variant),
-                                                      main_smem_bytes(h->cfg.max_cols, variant, pipe_threads(variant)));
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, VT>, pthreads,
+                                                      main_smem_bytes(h->cfg.max_cols, variant, pthreads));
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     h->pipe_main_grid[variant] = per_sm * h->num_sms;
@@ -95,7 +128,7 @@ cudaError_t prep_main(Handle *h, int variant) {
 template <int CAP>
 void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, RunState *st, uint64_t *pool, uint32_t k,
                  cudaStream_t s, bool pdl, uint32_t seq = 0, uint64_t *stamp = nullptr) {
-    const int threads = seq ? pipe_threads(variant) : kCapThreads[variant];
+    const int threads = seq ? pipe_threads(variant, value_type(h)) : cap_threads(variant, value_type(h));
     size_t smem = main_smem_bytes(m.cols, variant, threads);
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
     const dim3 grid(seq ? h->pipe_main_grid[variant] : h->main_grid[variant]), block(threads);
@@ -131,7 +164,9 @@ __global__ void widen_u32_to_u64_kernel(const uint32_t *__restrict__ in, uint64_
 uint64_t max_pool_keys(const Handle *h) {
     uint64_t best = 0;
     for (int v = 0; v < 4; v++) {
-        uint64_t n = (uint64_t)h->main_grid[v] * (kCapThreads[v] / 32) * kCaps[v];
+        uint64_t n = (uint64_t)h->main_grid[v] * (cap_threads(v, value_type(h)) / 32) * kCaps[v];
+        const uint64_t np = (uint64_t)h->pipe_main_grid[v] * (pipe_threads(v, value_type(h)) / 32) * kCaps[v];
+        if (np > n) n = np;
         if (n > best) best = n;
     }
     return best;
@@ -284,8 +319,9 @@ int check_float_upload(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, ui
 // latency-bound walk.  threads: CTA size (256 alone on the device, 128 beside a running main kernel).
 void launch_sample(Handle *h, const CsrDevice &m, const float *x, RunState *st, uint32_t *sample_keys, uint32_t k,
                    cudaStream_t s, uint32_t threads, uint32_t seq, uint64_t *stamp = nullptr) {
+    const uint32_t epi = elems_per_iter(value_type(h));   // non-zeros per warp iteration: 256 (fp32) or 512 (16-bit values)
     uint64_t want = (uint64_t)h->num_sms * 32u;
-    const uint64_t for_depth4 = h->nnz / 100u / (4u * kElemsPerIter);
+    const uint64_t for_depth4 = h->nnz / 100u / (4u * epi);
     if (for_depth4 > want) want = for_depth4;
     if (want > h->n_sample_cap) want = h->n_sample_cap;
     uint32_t n_sample = h->n_chunks < want ? h->n_chunks : (uint32_t)want;
@@ -294,8 +330,8 @@ void launch_sample(Handle *h, const CsrDevice &m, const float *x, RunState *st, 
     if (sample_smem < (size_t)kHistScratchWords * 4u) sample_smem = (size_t)kHistScratchWords * 4u;
     const uint32_t sgrid = (n_sample * kWarp + threads - 1) / threads;
     // the sample grows with the matrix (~1 % of the non-zeros) so that the candidates stay a few thousand
-    uint64_t si = (h->nnz / 100u + (uint64_t)n_sample * kElemsPerIter - 1) / ((uint64_t)n_sample * kElemsPerIter);
-    const uint32_t max_si = h->chunk_nnz / kElemsPerIter;
+    uint64_t si = (h->nnz / 100u + (uint64_t)n_sample * epi - 1) / ((uint64_t)n_sample * epi);
+    const uint32_t max_si = h->chunk_nnz / epi;
     const uint32_t sample_iters = (uint32_t)(si < 2 ? 2 : (si > max_si ? (max_si < 2 ? 2 : max_si) : si));
     switch (value_type(h)) {
         case TKS_VALUE_FP16: csr_sample_kernel<1><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
@@ -408,12 +444,12 @@ void launch_batched(Handle *h, uint32_t k, cudaStream_t s, bool profile) {
     a.stride = h->n_chunks / a.n_sample;
     {
         uint64_t sb = (h->nnz / 50u + (uint64_t)a.n_sample * kBStage - 1) / ((uint64_t)a.n_sample * kBStage);
-        a.sample_batches = (uint32_t)(sb < 8 ? 8 : (sb > 64 ? 64 : sb));
+        a.sample_batches = (uint32_t)(sb < 16 ? 16 : (sb > 128 ? 128 : sb));   // batches of kBStage = 32 non-zeros
     }
     a.tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
     batched_transpose_kernel<<<h->num_sms, 256, 0, s>>>(h->d_x, h->batch, h->cols, a.npass, h->d_xT, value_type(h));
     const uint32_t warps_per_cta = kBThreads / kWarp;
-    uint32_t sgrid = ((a.n_sample + 3u) / 4u + warps_per_cta - 1) / warps_per_cta;
+    uint32_t sgrid = ((a.n_sample + kBStreams - 1u) / kBStreams + warps_per_cta - 1) / warps_per_cta;
     if (sgrid > (uint32_t)h->num_sms) sgrid = (uint32_t)h->num_sms;
     launch_batched_kernel<true>(h, m, a, sgrid, s);
     batched_tau_kernel<<<h->batch, 256, (size_t)a.n_sample * 4u, s>>>(a, k);
@@ -1132,7 +1168,7 @@ int pipe_submit(tks_handle *h, const float *d_query, const float *host_query, ui
     // 1. threshold of THIS query on the sample stream: small CTAs that fit beside the main kernel still streaming the
     //    previous query
     uint64_t *stamp = h->d_pipe_stamps + (size_t)(seq % tks::Handle::kPipeStamps) * kStampWords;
-    launch_sample(h, m, d_query, st, h->d_pipe_sample_keys, k, h->pipe_sample_stream, (uint32_t)pipe_sample_threads(), seq, stamp);
+    launch_sample(h, m, d_query, st, h->d_pipe_sample_keys, k, h->pipe_sample_stream, (uint32_t)pipe_sample_threads(value_type(h)), seq, stamp);
     // 2. the stream on the caller's stream, chained to the previous main kernel by programmatic dependent launch and
     //    never waiting for it: its CTAs take over as that grid's CTAs retire
     launch_main_variant(h, variant, m, d_query, st, h->d_pipe_pool[slot], k, s, pdl_enabled(), seq, stamp);

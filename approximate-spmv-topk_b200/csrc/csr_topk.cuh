@@ -35,10 +35,10 @@ namespace tks {
 constexpr uint32_t kColOffMask = 0xFFFCu;                   // column * 4
 constexpr uint32_t kRowStartBit = 0x80000000u;              // batched kernel's staged column words only
 constexpr uint32_t kMaxCols = 16384;                       // exclusive: cols <= 16383 (slot `cols` holds 0.0)
-constexpr uint32_t kEpl = 8;                                // elements per lane: one 256-bit load per array
-constexpr uint32_t kElemsPerIter = kWarp * kEpl;            // 256 non-zeros per warp iteration
+constexpr uint32_t kElemsPerIter = kWarp * 8u;              // 256 non-zeros per warp iteration with fp32 values (512 with 16-bit values)
 constexpr uint32_t kMainThreads = 512;
 constexpr uint32_t kMainThreadsWide = 576;   // k <= 128 variant: 2 x 18 warps per SM at <= 56 registers per thread
+constexpr uint32_t kMainThreads16 = 384;     // 16-bit value modes: 16 non-zeros per lane, ~80 registers, 2 x 12 warps per SM
 constexpr uint32_t kSampleThreads = 256;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
@@ -135,7 +135,9 @@ __device__ __forceinline__ bool spin_until_eq(const uint32_t *p, uint32_t want, 
 }
 
 // --------------------------------------------------------------------------
-// One warp iteration: 256 consecutive non-zeros, 8 per lane.
+// One warp iteration: 32 x EPL consecutive non-zeros, EPL per lane (8 with fp32 values, 16 with 16-bit values:
+// both are one 256-bit load of values per lane; with 16 the per-iteration work -- the warp scan, the ballots, the
+// loop itself -- is spread over twice as many non-zeros, which is what bounds the 16-bit modes).
 //   seg[j]  inclusive segmented sum inside the lane (restarts at row starts)
 //   fb      bit j set <=> element j starts a row
 //   T       total of the row that ends at the lane's first row start
@@ -144,35 +146,54 @@ __device__ __forceinline__ bool spin_until_eq(const uint32_t *p, uint32_t want, 
 // All float ops are explicit __fmul_rn/__fadd_rn so that the sample kernel and the
 // main kernel produce bit-identical row sums (no FMA contraction either way).
 // --------------------------------------------------------------------------
+// VT: storage type of the matrix values -- 0 fp32, 1 IEEE half, 2 bfloat16 (TKS_VALUE_*); the 16-bit types are
+// widened to fp32 before the multiply.
+template <int VT> struct Epl { static constexpr uint32_t v = (VT != 0) ? 16u : 8u; };
+constexpr uint32_t elems_per_iter(int vt) { return kWarp * (vt != 0 ? 16u : 8u); }
+
+template <uint32_t EPL>
 struct IterState {
-    float seg[8];
+    float seg[EPL];
     float T, cm;
     uint32_t fb, nf;
     unsigned fm;   // ballot: lanes with >= 1 row start
 };
 
-// VT: storage type of the matrix values -- 0 fp32, 1 IEEE half, 2 bfloat16 (TKS_VALUE_*); the 16-bit types arrive as
-// one 128-bit load per lane and are widened to fp32 before the multiply.
-template <int VT> struct ValRaw { using type = U32x4; };
-template <> struct ValRaw<0> { using type = U32x8; };
+template <int VT> struct ValRaw { using type = U32x8; };   // 8 fp32 words or 16 halves
+template <int VT> struct ColRaw { using type = U32x8; };   // 16 x u16
+template <> struct ColRaw<0> { using type = U32x4; };      //  8 x u16
 
 template <int VT>
-__device__ __forceinline__ typename ValRaw<VT>::type ldg_stream_vals(const void *p) {
-    if constexpr (VT != 0) return ldg_stream_128(p);
-    else return ldg_stream_256(p);
+__device__ __forceinline__ typename ValRaw<VT>::type ldg_stream_vals(const void *p) { return ldg_stream_256(p); }
+template <int VT>
+__device__ __forceinline__ typename ColRaw<VT>::type ldg_stream_cols(const void *p) {
+    if constexpr (VT != 0) return ldg_stream_256(p);
+    else return ldg_stream_128(p);
+}
+template <int VT>
+__device__ __forceinline__ uint32_t ldg_stream_rowbits(const void *p) {
+    if constexpr (VT != 0) {
+        uint32_t r;
+        asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=r"(r) : "l"(p));
+        return r;
+    } else {
+        return ldg_stream_u8(p);
+    }
 }
 
 template <bool MASKED, int VT>
-__device__ __forceinline__ void csr_iter(const typename ValRaw<VT>::type &vraw, const U32x4 &craw, uint32_t rbits,
-                                         const uint8_t *__restrict__ xs_bytes, uint32_t zero_off, uint32_t lo,
-                                         uint32_t hi, float carry_in, float &carry_out, IterState &o) {
+__device__ __forceinline__ void csr_iter(const typename ValRaw<VT>::type &vraw, const typename ColRaw<VT>::type &craw,
+                                         uint32_t rbits, const uint8_t *__restrict__ xs_bytes, uint32_t zero_off,
+                                         uint32_t lo, uint32_t hi, float carry_in, float &carry_out,
+                                         IterState<Epl<VT>::v> &o) {
+    constexpr int EPL = (int)Epl<VT>::v;
     const unsigned lane = lane_id();
     float cm = neg_inf();
     // bit j <=> element j starts a row (elements outside [lo, hi) start nothing)
     const uint32_t inmask = ((1u << hi) - 1u) & ~((1u << lo) - 1u);   // elements j in [lo, hi) are inside the chunk
     const uint32_t fb = MASKED ? (rbits & inmask) : rbits;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
+    for (int j = 0; j < EPL; j++) {
         uint32_t c = (j & 1) ? (craw.w[j >> 1] >> 16) : (craw.w[j >> 1] & 0xFFFFu);   // column * 4
         float v;
         if constexpr (VT == 1) {
@@ -204,18 +225,25 @@ __device__ __forceinline__ void csr_iter(const typename ValRaw<VT>::type &vraw, 
     o.nf = __popc(o.fb);
     o.fm = __ballot_sync(kFull, o.fb != 0);
 
-    // head = sum of the elements before the lane's first row start (whole lane if none)
+    // head = sum of the elements before the lane's first row start (whole lane if none): seg[t - 1] for the first
+    // row start t >= 1, 0 for t == 0, picked by a select tree over the bits of t
     const uint32_t t = (uint32_t)__ffs((int)o.fb) - 1u;   // first row start (undefined when fb == 0)
-    const bool b0 = t & 1u, b1 = t & 2u, b2 = t & 4u;
-    const float a0 = b0 ? o.seg[0] : 0.0f, a1 = b0 ? o.seg[2] : o.seg[1];
-    const float a2 = b0 ? o.seg[4] : o.seg[3], a3 = b0 ? o.seg[6] : o.seg[5];
-    const float c0 = b1 ? a1 : a0, c1 = b1 ? a3 : a2;
-    const float head = (o.fb == 0) ? o.seg[7] : (b2 ? c1 : c0);
+    float sel[EPL];
+    sel[0] = 0.0f;
+#pragma unroll
+    for (int j = 1; j < EPL; j++) sel[j] = o.seg[j - 1];
+#pragma unroll
+    for (int bit = 0; (1 << bit) < EPL; bit++) {
+        const bool b = (t >> bit) & 1u;
+#pragma unroll
+        for (int i = 0; i < (EPL >> (bit + 1)); i++) sel[i] = b ? sel[2 * i + 1] : sel[2 * i];
+    }
+    const float head = (o.fb == 0) ? o.seg[EPL - 1] : sel[0];
 
     // inclusive segmented scan of the lane tails; segments restart at lanes with a row start
     const unsigned le = o.fm & lanemask_le();
     const int dist = (int)lane - (le ? (31 - __clz(le)) : 0);
-    float I = o.seg[7];
+    float I = o.seg[EPL - 1];
 #pragma unroll
     for (int dlt = 1; dlt < 32; dlt <<= 1) {
         const float up = __shfl_up_sync(kFull, I, dlt);
@@ -281,19 +309,20 @@ struct PoolSink {
 template <int VT, typename Sink>
 __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint32_t c,
                                                   uint32_t max_iters, Sink &sink) {
+    constexpr uint32_t EPL = Epl<VT>::v, EPI = kWarp * EPL;
     const unsigned lane = lane_id();
     const uint64_t s = m.chunk_start[c], e = m.chunk_start[c + 1];
     if (s >= e) return;
-    const uint64_t a0 = s & ~7ull;                       // 32-byte aligned start of the first 256-bit load
-    const uint64_t n_iter64 = (e - a0 + kElemsPerIter - 1) / kElemsPerIter;
+    const uint64_t a0 = s & ~(uint64_t)(EPL - 1u);       // 32-byte aligned start of the first 256-bit load
+    const uint64_t n_iter64 = (e - a0 + EPI - 1) / EPI;
     const bool truncated = n_iter64 > max_iters;
     const uint32_t n_iter = truncated ? max_iters : (uint32_t)n_iter64;
     const uint32_t last_iter = (uint32_t)n_iter64 - 1;   // chunks are far smaller than 2^32 * 256 non-zeros
     const int32_t rel_s = (int32_t)(s - a0), rel_e = (int32_t)(e - a0);
     constexpr uint32_t kValBytes = VT != 0 ? 2u : 4u;
-    const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val) + a0 * kValBytes + lane * (kEpl * kValBytes);
-    const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.col16 + a0) + lane * 16u;
-    const uint8_t *rp = m.rowbits + (a0 >> 3) + lane;
+    const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val) + a0 * kValBytes + lane * (EPL * kValBytes);
+    const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.col16 + a0) + lane * (EPL * 2u);
+    const uint8_t *rp = m.rowbits + (a0 >> 3) + lane * (EPL / 8u);
     const uint32_t zero_off = m.cols * 4u;
 
     uint32_t R = m.chunk_ord[c] - 1u;   // ordinal of the row "in progress" (a bogus one before the chunk at first)
@@ -301,29 +330,29 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
     float carry = 0.0f;
 
     typename ValRaw<VT>::type nv = ldg_stream_vals<VT>(vp);
-    U32x4 nc = ldg_stream_128(cp);
-    uint32_t nr = ldg_stream_u8(rp);
+    typename ColRaw<VT>::type nc = ldg_stream_cols<VT>(cp);
+    uint32_t nr = ldg_stream_rowbits<VT>(rp);
 #pragma unroll 2
     for (uint32_t it = 0; it < n_iter; it++) {
         const typename ValRaw<VT>::type cv = nv;
-        const U32x4 cc = nc;
+        const typename ColRaw<VT>::type cc = nc;
         const uint32_t cr = nr;
-        vp += kElemsPerIter * kValBytes;
-        cp += kElemsPerIter * 2u;
-        rp += kElemsPerIter / 8u;
-        if (it + 1 < n_iter) { nv = ldg_stream_vals<VT>(vp); nc = ldg_stream_128(cp); nr = ldg_stream_u8(rp); }
-        IterState o;
+        vp += EPI * kValBytes;
+        cp += EPI * 2u;
+        rp += EPI / 8u;
+        if (it + 1 < n_iter) { nv = ldg_stream_vals<VT>(vp); nc = ldg_stream_cols<VT>(cp); nr = ldg_stream_rowbits<VT>(rp); }
+        IterState<EPL> o;
         float carry_out;
         if (it == 0 || it == last_iter) {
             // lanes' elements outside [s, e) are neutralised
             // offsets inside the chunk fit 32 bits (a chunk is far smaller than 2^31 non-zeros)
-            const int32_t ebase = (int32_t)(it * kElemsPerIter + lane * kEpl);
+            const int32_t ebase = (int32_t)(it * EPI + lane * EPL);
             const int32_t l32 = rel_s - ebase, h32 = rel_e - ebase;
-            const uint32_t lo = l32 < 0 ? 0u : (l32 > 8 ? 8u : (uint32_t)l32);
-            const uint32_t hi = h32 < 0 ? 0u : (h32 > 8 ? 8u : (uint32_t)h32);
+            const uint32_t lo = l32 < 0 ? 0u : (l32 > (int32_t)EPL ? EPL : (uint32_t)l32);
+            const uint32_t hi = h32 < 0 ? 0u : (h32 > (int32_t)EPL ? EPL : (uint32_t)h32);
             csr_iter<true, VT>(cv, cc, cr, xs_bytes, zero_off, lo, hi, carry, carry_out, o);
         } else {
-            csr_iter<false, VT>(cv, cc, cr, xs_bytes, zero_off, 0u, 8u, carry, carry_out, o);
+            csr_iter<false, VT>(cv, cc, cr, xs_bytes, zero_off, 0u, EPL, carry, carry_out, o);
         }
         carry = carry_out;
 
@@ -342,11 +371,12 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
             const bool bogus = first_pending && (lane == (unsigned)(__ffs(o.fm) - 1));
             sink.emit(passT && !bogus, o.T, ord_l);
             if (__any_sync(kFull, o.nf >= 2)) {
-                // rows that start AND end inside one lane (length <= 7)
+                // rows that start AND end inside one lane (length <= EPL - 1)
 #pragma unroll
-                for (int j = 1; j < 8; j++) {
+                for (int j = 1; j < (int)EPL; j++) {
                     const uint32_t below = o.fb & ((1u << j) - 1u);
                     const bool ends_here = ((o.fb >> j) & 1u) && below != 0;
+                    if (EPL > 8 && !__any_sync(kFull, ends_here)) continue;   // warp-uniform skip
                     sink.emit(ends_here && (o.seg[j - 1] >= sink.tau), o.seg[j - 1], ord_l + __popc(below));
                 }
             }
@@ -527,8 +557,10 @@ __device__ __forceinline__ float query_value(float x) {
     else return x;
 }
 
+// <= 64 registers (4 CTAs of 256 threads per SM): its warps must fit into the register holes two main-kernel CTAs leave
+// in every SM sub-partition when it runs beside them (pipelined submits)
 template <int VT>
-__global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m, const float *__restrict__ x,
+__global__ void __launch_bounds__(kSampleThreads, 4) csr_sample_kernel(CsrDevice m, const float *__restrict__ x,
                                                                      RunState *st, uint32_t *sample_keys,
                                                                      uint32_t n_sample, uint32_t stride,
                                                                      uint32_t sample_iters, uint32_t k, uint32_t seq,
@@ -578,7 +610,7 @@ __global__ void __launch_bounds__(kSampleThreads) csr_sample_kernel(CsrDevice m,
 // shared-memory buffer (sorted and cut to k only if it ever fills).
 // --------------------------------------------------------------------------
 template <int CAP, int VT>
-__global__ void __launch_bounds__(CAP == 256 ? kMainThreadsWide : kMainThreads, 2)
+__global__ void __launch_bounds__(VT != 0 ? kMainThreads16 : (CAP == 256 ? kMainThreadsWide : kMainThreads), 2)
 csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uint64_t *pool, uint32_t k,
                      int tie_higher, uint32_t seq, uint32_t tau_wait_us, uint64_t *stamp) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
