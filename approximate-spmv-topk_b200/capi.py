@@ -54,6 +54,9 @@ SYMBOLS = [
     "tks_download_csr", "tks_download_csr_rows", "tks_set_query", "tks_set_query_device", "tks_run", "tks_run_async",
     "tks_read_result", "tks_read_partition_results", "tks_result_keys_device", "tks_merge_keys_device", "tks_merge_keys_batched_device",
     "tks_peer_init", "tks_peer_connect", "tks_run_exchange_async", "tks_peer_exchange_async",
+    "tks_group_create", "tks_group_destroy", "tks_group_last_error", "tks_group_size", "tks_group_member",
+    "tks_group_upload_csr", "tks_group_generate_synthetic", "tks_group_set_query", "tks_group_run", "tks_group_read_result",
+    "tks_group_submit_host", "tks_group_fetch",
     "tks_submit", "tks_submit_host", "tks_fetch", "tks_pipeline_wait", "tks_pipeline_stamps",
     "tks_set_profile_kernels", "tks_get_stats", "tks_bscsr_packet_size", "tks_fixed32_from_double", "tks_fixedW_from_fixed32",
     "tks_pack_bscsr", "tks_merge_partition_words", "tks_read_mtx", "tks_coo2csr",
@@ -104,6 +107,22 @@ def lib() -> C.CDLL:
     L.tks_peer_connect.argtypes = [vp, vp]
     L.tks_run_exchange_async.argtypes = [vp, C.c_uint32, vp]
     L.tks_peer_exchange_async.argtypes = [vp, C.c_uint32, vp]
+    L.tks_group_create.argtypes = [C.POINTER(TksConfig), vp, C.c_uint32, C.POINTER(vp)]
+    L.tks_group_destroy.argtypes = [vp]
+    L.tks_group_destroy.restype = None
+    L.tks_group_last_error.argtypes = [vp]
+    L.tks_group_last_error.restype = C.c_char_p
+    L.tks_group_size.argtypes = [vp]
+    L.tks_group_size.restype = C.c_uint32
+    L.tks_group_member.argtypes = [vp, C.c_uint32]
+    L.tks_group_member.restype = vp
+    L.tks_group_upload_csr.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint64, vp, C.c_int, vp, vp]
+    L.tks_group_generate_synthetic.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64]
+    L.tks_group_set_query.argtypes = [vp, vp]
+    L.tks_group_run.argtypes = [vp, C.c_uint32, f32p, f32p]
+    L.tks_group_read_result.argtypes = [vp, C.c_uint32, vp, vp, u32p]
+    L.tks_group_submit_host.argtypes = [vp, vp, C.c_uint32, u64p]
+    L.tks_group_fetch.argtypes = [vp, C.c_uint64, vp, vp, u32p]
     L.tks_submit.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
     L.tks_submit_host.argtypes = [vp, vp, C.c_uint32, C.c_uint32, u64p]
     L.tks_fetch.argtypes = [vp, C.c_uint64, vp, vp, u32p]

@@ -1288,3 +1288,204 @@ int tks_get_stats(tks_handle *h, tks_stats *out) {
 }
 
 }  // extern "C"
+
+// ---- several GPUs driven by ONE process (SURVEY 8b `num_gpus / device_ids`, 8e) ------------------------------------
+// A group owns one handle per device.  The devices map each other's exchange windows by plain peer access (one address
+// space, no IPC), every shard runs the same three launches as a single device, and the select kernel of every shard
+// exchanges its K candidates over NVLink and merges (csr_topk.cuh) -- afterwards every device holds the global top-k.
+
+struct tks_group {
+    std::vector<tks_handle *> h;
+    std::vector<uint64_t> row_begin;   // first global row of every shard (+ total rows at the end)
+    std::string err;
+    uint32_t cols = 0;
+    bool have_matrix = false;
+    int fail(int code, const std::string &m) { err = m; return code; }
+    int adopt(int rc, tks_handle *hh) { if (rc) err = hh->err; return rc; }
+};
+
+extern "C" {
+
+const char *tks_group_last_error(const tks_group *g) { return g ? g->err.c_str() : g_create_error.c_str(); }
+
+void tks_group_destroy(tks_group *g) {
+    if (!g) return;
+    for (tks_handle *hh : g->h) {
+        if (!hh) continue;
+        // the windows of the other members were never opened through IPC: forget them before the handle closes them
+        for (uint32_t r = 0; r < kPeerMaxWorld; r++) hh->peer_mapped[r] = nullptr;
+        hh->peer_world = 0;
+        tks_destroy(hh);
+    }
+    delete g;
+}
+
+int tks_group_create(const tks_config *cfg, const int32_t *devices, uint32_t n, tks_group **out) {
+    if (!cfg || !devices || !out) { g_create_error = "null argument"; return TKS_EINVAL; }
+    *out = nullptr;
+    if (n < 1 || n > kPeerMaxWorld) { g_create_error = "a group has 1..8 devices"; return TKS_EINVAL; }
+    if (cfg->mode != TKS_MODE_FLOAT_CSR) { g_create_error = "groups run the float CSR engine (FPGA mode spreads its partitions with ShardedSpMVFixed)"; return TKS_EINVAL; }
+    tks_group *g = new (std::nothrow) tks_group();
+    if (!g) { g_create_error = "out of memory"; return TKS_ENOMEM; }
+    g->h.assign(n, nullptr);
+    for (uint32_t r = 0; r < n; r++) {
+        tks_config c = *cfg;
+        c.device = devices[r];
+        int rc = tks_create(&c, &g->h[r]);
+        if (rc) { tks_group_destroy(g); return rc; }   // g_create_error is set
+    }
+    // peer access between every pair of distinct devices, then the exchange windows
+    for (uint32_t a = 0; a < n && n > 1; a++) {
+        cudaSetDevice(devices[a]);
+        for (uint32_t b = 0; b < n; b++) {
+            if (devices[a] == devices[b]) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[a], devices[b]);
+            if (!can) { g_create_error = "devices of the group cannot access each other's memory"; tks_group_destroy(g); return TKS_ECUDA; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) { g_create_error = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); tks_group_destroy(g); return TKS_ECUDA; }
+        }
+    }
+    if (n > 1) {
+        const size_t bytes = peer_window_bytes(kKMax);
+        for (uint32_t r = 0; r < n; r++) {
+            tks_handle *hh = g->h[r];
+            cudaSetDevice(hh->device);
+            if (cudaMalloc(&hh->d_peer_window, bytes) != cudaSuccess || cudaMemset(hh->d_peer_window, 0, bytes) != cudaSuccess) {
+                g_create_error = "exchange window allocation failed"; tks_group_destroy(g); return TKS_ECUDA;
+            }
+        }
+        for (uint32_t r = 0; r < n; r++) {
+            tks_handle *hh = g->h[r];
+            for (uint32_t o = 0; o < n; o++) hh->peer_mapped[o] = g->h[o]->d_peer_window;
+            hh->peer_world = n; hh->peer_rank = r; hh->peer_seq = 0; hh->peer_ready = true;
+        }
+    }
+    *out = g;
+    return TKS_OK;
+}
+
+uint32_t tks_group_size(const tks_group *g) { return g ? (uint32_t)g->h.size() : 0u; }
+
+tks_handle *tks_group_member(tks_group *g, uint32_t i) { return (g && i < g->h.size()) ? g->h[i] : nullptr; }
+
+int tks_group_upload_csr(tks_group *g, uint64_t rows, uint32_t cols, uint64_t nnz, const void *ptr, int ptr_bits,
+                         const uint32_t *idx, const float *val) {
+    if (!g || !ptr || (nnz && (!idx || !val))) return TKS_EINVAL;
+    if (ptr_bits != 32 && ptr_bits != 64) return g->fail(TKS_EINVAL, "ptr_bits must be 32 or 64");
+    const uint32_t n = (uint32_t)g->h.size();
+    auto at = [&](uint64_t r) -> uint64_t {
+        return ptr_bits == 64 ? static_cast<const uint64_t *>(ptr)[r] : static_cast<const uint32_t *>(ptr)[r];
+    };
+    if (at(rows) != nnz) return g->fail(TKS_EINVAL, "ptr[rows] != nnz");
+    // contiguous row shards balanced by non-zeros (the reference's partition rule, host_spmv_bscsr.cpp:136-141, with
+    // boundaries balanced by nnz instead of by row count)
+    g->row_begin.assign(n + 1, rows);
+    g->row_begin[0] = 0;
+    for (uint32_t s = 1; s < n; s++) {
+        const uint64_t target = nnz / n * s;
+        uint64_t lo = g->row_begin[s - 1], hi = rows;
+        while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (at(mid) < target) lo = mid + 1; else hi = mid; }
+        g->row_begin[s] = lo;
+    }
+    for (uint32_t s = 0; s < n; s++) {
+        const uint64_t r0 = g->row_begin[s], r1 = g->row_begin[s + 1], b = at(r0), e = at(r1);
+        std::vector<uint64_t> p(r1 - r0 + 1);
+        for (uint64_t r = r0; r <= r1; r++) p[r - r0] = at(r) - b;
+        int rc = tks_upload_csr(g->h[s], r1 - r0, cols, e - b, p.data(), 64, idx + b, val + b, r0);
+        if (rc) return g->adopt(rc, g->h[s]);
+    }
+    g->cols = cols;
+    g->have_matrix = true;
+    return TKS_OK;
+}
+
+int tks_group_generate_synthetic(tks_group *g, uint64_t rows, uint32_t cols, uint32_t avg_degree, int dist, uint64_t seed) {
+    if (!g) return TKS_EINVAL;
+    const uint32_t n = (uint32_t)g->h.size();
+    g->row_begin.assign(n + 1, rows);
+    for (uint32_t s = 0; s <= n; s++) g->row_begin[s] = rows / n * s + (s < rows % n ? s : rows % n);
+    for (uint32_t s = 0; s < n; s++) {
+        int rc = tks_generate_synthetic(g->h[s], g->row_begin[s + 1] - g->row_begin[s], cols, avg_degree, dist, seed, g->row_begin[s]);
+        if (rc) return g->adopt(rc, g->h[s]);
+    }
+    g->cols = cols;
+    g->have_matrix = true;
+    return TKS_OK;
+}
+
+int tks_group_set_query(tks_group *g, const float *vec) {
+    if (!g || !vec) return TKS_EINVAL;
+    for (tks_handle *hh : g->h) {
+        int rc = tks_set_query(hh, vec, 1);
+        if (rc) return g->adopt(rc, hh);
+    }
+    return TKS_OK;
+}
+
+int tks_group_run(tks_group *g, uint32_t k, float *kernel_ms, float *total_ms) {
+    if (!g) return TKS_EINVAL;
+    if (!g->have_matrix) return g->fail(TKS_ESTATE, "no matrix uploaded");
+    if (g->h.size() == 1) return g->adopt(tks_run(g->h[0], k, kernel_ms, total_ms), g->h[0]);
+    auto t0 = std::chrono::high_resolution_clock::now();
+    // every shard: sample -> main -> select (+ exchange over the peer windows + merge), enqueued back to back; the
+    // devices run concurrently and meet inside their select kernels
+    for (tks_handle *hh : g->h) {
+        cudaSetDevice(hh->device);
+        cudaEventRecord(hh->ev0, hh->stream);
+        int rc = tks_run_exchange_async(hh, k, nullptr);
+        if (rc) return g->adopt(rc, hh);
+        cudaEventRecord(hh->ev1, hh->stream);
+    }
+    float worst = 0.f;
+    for (tks_handle *hh : g->h) {
+        cudaSetDevice(hh->device);
+        cudaError_t e = cudaStreamSynchronize(hh->stream);
+        if (e != cudaSuccess) return g->fail(TKS_ECUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, hh->ev0, hh->ev1);
+        if (ms > worst) worst = ms;
+    }
+    const float tot = std::chrono::duration<float, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+    for (tks_handle *hh : g->h) { hh->stats.last_kernel_ms = worst; hh->stats.last_total_ms = tot; }
+    if (kernel_ms) *kernel_ms = worst;   // the slowest device, exchange and merge included
+    if (total_ms) *total_ms = tot;
+    return TKS_OK;
+}
+
+int tks_group_read_result(tks_group *g, uint32_t member, uint32_t *idx_out, float *val_out, uint32_t *count) {
+    if (!g || member >= g->h.size()) return TKS_EINVAL;
+    return g->adopt(tks_read_result(g->h[member], 0, idx_out, val_out, count), g->h[member]);
+}
+
+int tks_group_submit_host(tks_group *g, const float *query, uint32_t k, uint64_t *ticket) {
+    if (!g || !query || !ticket) return TKS_EINVAL;
+    if (!g->have_matrix) return g->fail(TKS_ESTATE, "no matrix uploaded");
+    const uint32_t flags = g->h.size() > 1 ? TKS_SUBMIT_EXCHANGE : 0u;
+    uint64_t t = 0;
+    for (tks_handle *hh : g->h) {
+        int rc = tks_submit_host(hh, query, k, flags, &t);
+        if (rc) return g->adopt(rc, hh);
+    }
+    *ticket = t;   // the members are submitted to in lock step: one ticket names the step on all of them
+    return TKS_OK;
+}
+
+int tks_group_fetch(tks_group *g, uint64_t ticket, uint32_t *idx_out, float *val_out, uint32_t *count) {
+    if (!g) return TKS_EINVAL;
+    // every member holds the global result; member 0's copy is returned, the others' slots are released
+    for (size_t i = g->h.size(); i-- > 1;) {
+        tks_handle *hh = g->h[i];
+        const int slot = (int)(ticket % (uint64_t)hh->pipe_slots);
+        cudaSetDevice(hh->device);
+        if (hh->pipe_busy[slot] && hh->pipe_slot_ticket[slot] == ticket) {
+            cudaEventSynchronize(hh->pipe_ev_done[slot]);
+            hh->pipe_busy[slot] = false;
+        }
+    }
+    return g->adopt(tks_fetch(g->h[0], ticket, idx_out, val_out, count), g->h[0]);
+}
+
+}  // extern "C"
+

@@ -706,6 +706,7 @@ bscsr_replay_kernel(BscsrLogs logs, const uint32_t *__restrict__ part_chunk_begi
                     }
                 }
             }
+            __syncwarp();   // every lane has read s_n (racecheck: the loop's votes order execution, not this read against the write)
             if (lane == 0) s_n = 0;
         }
         __syncthreads();

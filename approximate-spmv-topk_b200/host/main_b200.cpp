@@ -198,6 +198,15 @@ int main(int argc, char *argv[]) {
         std::vector<float> vec(cols);
         create_sample_vector(vec.data(), (int)cols, true, false, true, options.seed);
         auto t4 = clock_type::now();
+        const double bytes_g = (options.use_half_precision_gpu ? 6.0 : 8.0) * nnz + 4.0 * (rows + 1.0) + 4.0 * cols + 8.0 * options.top_k_value;
+        if (options.devices.size() > 1) {
+            // -G a,b,...: one shard per listed device, all driven by this process (tks_group_*); same loop, same CSV
+            SpMVGroup group(ptr.data(), idx.data(), csr_val.data(), rows, cols, nnz, vec.data(), options.top_k_value,
+                            options.devices, options.tie_higher, debug, options.use_half_precision_gpu);
+            float setup_g = (float)chrono::duration_cast<chrono::microseconds>(clock_type::now() - t4).count() / 1000;
+            if (debug) std::cout << "b200 setup time=" << setup_g << " ms (" << options.devices.size() << " devices)" << std::endl;
+            return run<float>(options, coo, rows, cols, nnz, group, vec, setup_g, "hw_spmv_only_time_ms,hw_exec_time_ms", bytes_g);
+        }
         SpMV spmv(ptr.data(), idx.data(), csr_val.data(), rows, cols, nnz, vec.data(), options.top_k_value, options.device,
                   options.tie_higher, debug, options.use_half_precision_gpu);   // -a, as host_spmv_topk_csr_gpu.cu:382
         float setup_ms = (float)chrono::duration_cast<chrono::microseconds>(clock_type::now() - t4).count() / 1000;

@@ -7,7 +7,8 @@
 //   -f  FPGA-semantics fixed-point BS-CSR engine instead of exact fp32 CSR (USE_FLOAT, types.hpp:29)
 //   -w  FIXED_WIDTH   -p SPMV_PARTITIONS   -l LIMITED_FINISHED_ROWS   -q local K   (types.hpp:20,36,77,51)
 //   -e  seed of the query generator (0 = random_device, as the reference)
-//   -G  CUDA device ordinal              -T  ties -> higher index first (reference sort order)
+//   -G  CUDA device ordinal, or a list "0,1,...,7": rows sharded over those GPUs, driven by this one process (float engine)
+//   -T  ties -> higher index first (reference sort order)
 //   -D  fixed-point engine: repair the reference's row-counter drift (tks_config.fixed_drift_free)
 //   -P  fixed-point engine: build the BS-CSR packets on the GPU (tks_upload_coo_fixed) instead of on the host
 //   -C  <file>  binary matrix cache: loaded when present, else written after the MTX text is parsed
@@ -17,6 +18,7 @@
 
 #include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "types.hpp"
 
@@ -60,6 +62,7 @@ struct Options {
     int local_k = K;
     int seed = 0;
     int device = 0;
+    std::vector<int> devices;   // -G a,b,...: more than one entry = one shard per listed device (a device may repeat)
     bool tie_higher = false;
     bool drift_free = false;
     bool device_pack = false;
@@ -115,7 +118,19 @@ struct Options {
                 case 'l': limited_finished_rows = atoi(optarg); break;
                 case 'q': local_k = atoi(optarg); break;
                 case 'e': seed = atoi(optarg); break;
-                case 'G': device = atoi(optarg); break;
+                case 'G': {
+                    devices.clear();
+                    for (const char *p = optarg; *p;) {
+                        char *end = nullptr;
+                        const long d = strtol(p, &end, 10);
+                        if (end == p) break;
+                        devices.push_back((int)d);
+                        p = (*end == ',') ? end + 1 : end;
+                        if (*end != ',' && *end != 0) break;
+                    }
+                    device = devices.empty() ? 0 : devices[0];
+                    break;
+                }
                 case 'T': tie_higher = true; break;
                 case 'D': drift_free = true; break;
                 case 'C': cache_path = optarg; break;

@@ -73,6 +73,64 @@ struct SpMV {
     }
 };
 
+// The same functor over SEVERAL GPUs driven by this one process (tks_group_*): rows sharded contiguously over the
+// devices, K candidates exchanged over NVLink by the select kernels; the four verbs are unchanged.
+struct SpMVGroup {
+    tks_group *g = nullptr;
+    int_type num_rows, num_cols, num_nnz;
+    int k;
+    float last_full_ms = 0.f;
+
+#define TKS_G_OR_DIE(call)                                                                       \
+    do {                                                                                         \
+        int rc__ = (call);                                                                       \
+        if (rc__ != 0) {                                                                         \
+            fprintf(stderr, "%s failed (%d): %s\n", #call, rc__, tks_group_last_error(g));       \
+            exit(EXIT_FAILURE);                                                                  \
+        }                                                                                        \
+    } while (0)
+
+    SpMVGroup(int_type *ptr, int_type *idx, float *val, int_type num_rows_, int_type num_cols_, int_type num_nnz_,
+              float *vec, int k_, const std::vector<int> &devices, bool tie_higher = false, int debug = 0,
+              bool use_half_precision_gpu = false)
+        : num_rows(num_rows_), num_cols(num_cols_), num_nnz(num_nnz_), k(k_) {
+        tks_config cfg;
+        tks_default_config(&cfg);
+        cfg.mode = TKS_MODE_FLOAT_CSR;
+        cfg.max_cols = num_cols_ > MAX_COLS ? (int)num_cols_ : MAX_COLS;
+        cfg.tie_break = tie_higher ? TKS_TIE_HIGHER_INDEX : TKS_TIE_LOWER_INDEX;
+        cfg.value_type = use_half_precision_gpu ? TKS_VALUE_FP16 : TKS_VALUE_FP32;
+        std::vector<int32_t> dev(devices.begin(), devices.end());
+        TKS_G_OR_DIE(tks_group_create(&cfg, dev.data(), (uint32_t)dev.size(), &g));
+        if (debug) printf("Write inputs into the memory of %zu devices\n", dev.size());
+        TKS_G_OR_DIE(tks_group_upload_csr(g, num_rows, num_cols, num_nnz, ptr, 32, idx, val));
+        TKS_G_OR_DIE(tks_group_set_query(g, vec));
+    }
+    ~SpMVGroup() { tks_group_destroy(g); }
+    SpMVGroup(const SpMVGroup &) = delete;
+
+    float operator()(int debug) {
+        float kernel_ms = 0.f;
+        TKS_G_OR_DIE(tks_group_run(g, (uint32_t)k, &kernel_ms, &last_full_ms));
+        if (debug) printf("Kernels terminated\nComputation took %f ms on the slowest device (%f ms with read-back)\n", kernel_ms, last_full_ms);
+        return kernel_ms * 1e6f;
+    }
+    void read_result(std::vector<float> &res, std::vector<int_type> &res_idx, int debug = 0) {
+        (void)debug;
+        res.resize(k); res_idx.resize(k);
+        uint32_t count = 0;
+        TKS_G_OR_DIE(tks_group_read_result(g, 0, res_idx.data(), res.data(), &count));
+    }
+    long reset(float *vec, int debug) {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        TKS_G_OR_DIE(tks_group_set_query(g, vec));
+        long ns = (long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::high_resolution_clock::now() - t0).count();
+        if (debug) printf("Reset took %f ms\n", ns / 1e6);
+        return ns;
+    }
+#undef TKS_G_OR_DIE
+};
+
 // FPGA-semantics engine: constructor signature of the reference FPGA host (COO + fixed-point values).
 struct SpMVFixed {
     tks_handle *h = nullptr;

@@ -242,6 +242,28 @@ int tks_submit(tks_handle *h, const float *d_query, uint32_t k, uint32_t flags, 
 int tks_pipeline_wait(tks_handle *h, void *cuda_stream);
 int tks_pipeline_stamps(tks_handle *h, uint64_t *stamps_ns, uint32_t capacity, uint32_t *count);
 
+/* ---- several GPUs driven by ONE process (SURVEY 8b num_gpus / device_ids, 8e) ------------------------------------
+ * The counterpart of the one-process-per-GPU plumbing above for a plain C/C++ host such as the reference's main()
+ * (src/gpu/host_spmv_topk_csr_gpu.cu:291-480): a group owns one engine per device, the devices map each other's
+ * exchange windows by peer access (no IPC, no NCCL, no torch), rows are sharded contiguously (balanced by non-zeros),
+ * every shard runs the usual three launches and the select kernels exchange the K candidates over NVLink and merge.
+ * After a run every member holds the GLOBAL top-k.  The same device may be listed more than once (two shards on one
+ * GPU): that exercises the whole exchange on a single-GPU box.  Float CSR mode, world * k <= 2048.               */
+typedef struct tks_group tks_group;
+int tks_group_create(const tks_config *cfg, const int32_t *devices, uint32_t n, tks_group **out);   /* cfg->device is ignored */
+void tks_group_destroy(tks_group *g);
+const char *tks_group_last_error(const tks_group *g);
+uint32_t tks_group_size(const tks_group *g);
+tks_handle *tks_group_member(tks_group *g, uint32_t i);                         /* e.g. for tks_get_stats */
+int tks_group_upload_csr(tks_group *g, uint64_t rows, uint32_t cols, uint64_t nnz, const void *ptr, int ptr_bits,
+                         const uint32_t *idx, const float *val);
+int tks_group_generate_synthetic(tks_group *g, uint64_t rows, uint32_t cols, uint32_t avg_degree, int dist, uint64_t seed);
+int tks_group_set_query(tks_group *g, const float *vec);                        /* reset(vec) on every member      */
+int tks_group_run(tks_group *g, uint32_t k, float *kernel_ms, float *total_ms); /* operator(): launch all, wait    */
+int tks_group_read_result(tks_group *g, uint32_t member, uint32_t *idx_out, float *val_out, uint32_t *count);
+int tks_group_submit_host(tks_group *g, const float *query, uint32_t k, uint64_t *ticket);   /* pipelined, see above */
+int tks_group_fetch(tks_group *g, uint64_t ticket, uint32_t *idx_out, float *val_out, uint32_t *count);
+
 /* Switch tks_config.profile_kernels at run time: while on, tks_run brackets the dominant kernel with two extra
  * events (tks_stats.last_main_kernel_ms) and launches the kernels without overlap.                              */
 int tks_set_profile_kernels(tks_handle *h, int on);

@@ -88,3 +88,20 @@ def test_device_pack_flag_gives_identical_rows(cuda_required, tks, mtx):
 def test_cli_rejects_missing_file(cuda_required):
     out = subprocess.run([str(EXE), "-m", "/nonexistent.mtx"], capture_output=True, text=True)
     assert out.returncode != 0 and "not found" in out.stderr
+
+
+def test_group_cli_over_several_devices_gives_the_one_device_rows(cuda_required, tks, mtx):
+    """-G a,b: the C++ host drives one shard per listed device from ONE process (tks_group_*, no torch, no NCCL); the
+    select kernels exchange the candidates over the peer windows.  Two GPUs when the box has them; otherwise the same
+    device twice, which runs the very same exchange between two shards of one GPU."""
+    import torch
+    devs = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
+    one = run_exe("-m", mtx, "-k", 100, "-t", 4, "-e", 7)
+    two = run_exe("-m", mtx, "-k", 100, "-t", 4, "-e", 7, "-G", devs)
+    assert len(one) == len(two) == 4
+    for a, b in zip(one, two):
+        # a shard's rows sit at other lane offsets than in the unsharded stream: near-ties at the k-th place may swap
+        assert len(set(a["hw_res_idx"].split(";")) ^ set(b["hw_res_idx"].split(";"))) <= 2, "sharded run returned other rows"
+        assert a["sw_res_idx"] == b["sw_res_idx"]
+        assert int(b["error_val"]) == 0 and float(b["precision"]) >= 0.99
+        np.testing.assert_allclose([float(v) for v in a["hw_res_val"].split(";")], [float(v) for v in b["hw_res_val"].split(";")], rtol=1e-5)
