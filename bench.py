@@ -546,7 +546,7 @@ def float_workload(tks, torch, dist, wl_key, args, world, rank, local, tstream, 
     main_ms = measure_main_kernel(tks, eng, hq, warmup, steps if full else min(steps, 5), K)
     achieved = alg_bytes_local / (main_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "csr_topk_main_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-            "frac": achieved / peak_gbs, "traffic": load_traffic(wl_key), "peak_source": peak_src,
+            "frac": achieved / peak_gbs, "traffic": load_traffic(wl_key), "traffic_source": traffic_source(wl_key), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes_local, "main_kernel_ms": main_ms,
             "step_frac": alg_bytes_local / (ms_step * 1e-3) / 1e9 / peak_gbs,
             # the device layout is smaller than the CSR the algorithmic figure counts (16-bit column offsets + a
@@ -682,14 +682,25 @@ def measure_main_kernel(tks, eng, hq, warmup, steps, k):
 
 
 def load_traffic(wl_key):
-    """dram bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, if any (profiles/traffic.json; the
+    entry names the capture file and the git revision it came from -- see `traffic_source` in the line)."""
     p = ROOT / "profiles" / "traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get(wl_key)
+            e = json.loads(p.read_text()).get(wl_key)
+            return e.get("bytes") if isinstance(e, dict) else e
         except Exception:
             return None
     return None
+
+
+def traffic_source(wl_key):
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        e = json.loads(p.read_text()).get(wl_key)
+        return {"capture": "profiles/" + e["capture"], "git": e["git"]} if isinstance(e, dict) else None
+    except Exception:
+        return None
 
 
 def cpu_baseline_leg(tks, eng, queries, idx_gpu, val_gpu, args):
@@ -837,7 +848,7 @@ def batched_workload(tks, torch, dist, args, wl, rows_total, peak_gbs, peak_src,
     # lanes per warp instruction, one warp instruction per scheduler and clock, 4 schedulers per SM
     fp32_bound_ms = nnz_local * B * (1 if args.batch_fma else 2) / 32 / (148 * 4 * sm_clk * 1e6) * 1e3
     roof = {"bound": "hbm", "kernel": "csr_batched_kernel<MAIN>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-            "frac": achieved / peak_gbs, "traffic": load_traffic("cfg5"), "peak_source": peak_src,
+            "frac": achieved / peak_gbs, "traffic": load_traffic("cfg5"), "traffic_source": traffic_source("cfg5"), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg, "main_kernel_ms": main,
             "note": "SURVEY 7-H8: the binding resource is shared-memory bandwidth (one 4-byte table word per query x "
                     "non-zero), not HBM; all three bounds are reported",
@@ -1015,7 +1026,7 @@ def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
     achieved = alg / (main * 1e-3) / 1e9
     # issue-rate bound: the decode is integer work; report both bounds
     roof = {"bound": "hbm", "kernel": "bscsr_stream_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-            "frac": achieved / peak_gbs, "traffic": load_traffic("cfg3"), "peak_source": peak_src,
+            "frac": achieved / peak_gbs, "traffic": load_traffic("cfg3"), "traffic_source": traffic_source("cfg3"), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg, "main_kernel_ms": main,
             "step_frac": alg / (ms_step * 1e-3) / 1e9 / peak_gbs}
     cpu = None
