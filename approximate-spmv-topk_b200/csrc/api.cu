@@ -1207,18 +1207,35 @@ int pipe_submit(tks_handle *h, const float *d_query, const float *host_query, ui
 
 extern "C" {
 
-int tks_submit(tks_handle *h, const float *d_query, uint32_t k, uint32_t flags, void *cuda_stream) {
-    if (!h || !d_query) return TKS_EINVAL;
+int tks_submit(tks_handle *h, const void *d_query_v, uint32_t k, uint32_t flags, void *cuda_stream) {
+    if (!h || !d_query_v) return TKS_EINVAL;
+    if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) {
+        if (flags & TKS_SUBMIT_EXCHANGE) return h->fail(TKS_EINVAL, "BS-CSR mode spreads partitions, not candidates (ShardedSpMVFixed)");
+        TKS_CUDA(h, cudaSetDevice(h->device));
+        return bscsr_submit(h, nullptr, static_cast<const uint32_t *>(d_query_v), k, cuda_stream ? (cudaStream_t)cuda_stream : h->stream,
+                            (flags & TKS_SUBMIT_QUERY_READY) != 0, nullptr);
+    }
+    const float *d_query = static_cast<const float *>(d_query_v);
     return pipe_submit(h, d_query, nullptr, k, flags, cuda_stream ? (cudaStream_t)cuda_stream : h->stream, nullptr);
 }
 
-int tks_submit_host(tks_handle *h, const float *query, uint32_t k, uint32_t flags, uint64_t *ticket) {
+int tks_submit_host(tks_handle *h, const void *query, uint32_t k, uint32_t flags, uint64_t *ticket) {
     if (!h || !query || !ticket) return TKS_EINVAL;
-    return pipe_submit(h, nullptr, query, k, flags, h->stream, ticket);
+    if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) {
+        if (flags & TKS_SUBMIT_EXCHANGE) return h->fail(TKS_EINVAL, "BS-CSR mode spreads partitions, not candidates (ShardedSpMVFixed)");
+        TKS_CUDA(h, cudaSetDevice(h->device));
+        return bscsr_submit_host(h, static_cast<const uint32_t *>(query), k, ticket);
+    }
+    return pipe_submit(h, nullptr, static_cast<const float *>(query), k, flags, h->stream, ticket);
 }
 
-int tks_fetch(tks_handle *h, uint64_t ticket, uint32_t *idx_out, float *val_out, uint32_t *count) {
-    if (!h || !idx_out || !val_out) return TKS_EINVAL;
+int tks_fetch(tks_handle *h, uint64_t ticket, uint32_t *idx_out, void *val_out_v, uint32_t *count) {
+    if (!h || !idx_out || !val_out_v) return TKS_EINVAL;
+    if (h->cfg.mode == TKS_MODE_FIXED_BSCSR) {
+        TKS_CUDA(h, cudaSetDevice(h->device));
+        return bscsr_fetch_ticket(h, ticket, idx_out, static_cast<uint32_t *>(val_out_v), count);
+    }
+    float *val_out = static_cast<float *>(val_out_v);
     if (!h->d_pipe_state || ticket == 0 || ticket > h->pipe_seq) return h->fail(TKS_EINVAL, "unknown ticket");
     const int slot = (int)(ticket % (uint64_t)h->pipe_slots);
     if (h->pipe_slot_ticket[slot] != ticket)

@@ -38,6 +38,17 @@ struct BscsrState {
     bool replay_ready = false;
     cudaEvent_t ev_query = nullptr;
     bool bsx = false;            // packets re-encoded into the BSX device format (FIXED_WIDTH <= 22)
+    // pipelined submits (tks_submit_host / tks_fetch in BS-CSR mode): the query of step i+1 is transformed, copied and
+    // SAMPLED on a second stream while the stream and replay kernels of step i run, and the replay kernel writes the
+    // result words straight into a pinned host block, so a step costs stream + replay only (bscsr_submit_host)
+    static constexpr int kSlots = 2;
+    cudaStream_t p_sample_stream = nullptr;
+    cudaEvent_t p_ev_sample[kSlots] = {}, p_ev_done[kSlots] = {};
+    uint32_t *p_d_xq[kSlots] = {}, *p_h_xq[kSlots] = {}, *p_d_theta[kSlots] = {}, *p_h_words[kSlots] = {};
+    bool p_busy[kSlots] = {};
+    uint64_t p_ticket[kSlots] = {};
+    uint32_t p_k[kSlots] = {};
+    uint64_t p_seq = 0;
     std::vector<uint32_t> merged_idx, merged_val;          // read_result() output of the last run
 };
 
@@ -52,8 +63,18 @@ cudaError_t prep_stream_variant(int *ctas_per_sm) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kern, THREADS, smem);
 }
 
+// Where one run reads its query and seeds and writes its result words.  sample_stream != nullptr: the sample kernel
+// runs there (the query and the seeds of the slot belong to it) and the main stream joins it through ev_sample.
+struct BsRun {
+    const uint32_t *xq;
+    uint32_t *theta_seed;
+    uint32_t *res_idx, *res_val;
+    cudaStream_t sample_stream;
+    cudaEvent_t ev_sample;
+};
+
 template <int W, int LFR, int XREP, int THREADS, bool PREFETCH, bool BSX>
-void launch_stream_variant(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s) {
+void launch_stream_variant(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s, const BsRun &r) {
     if (!b->variant_ready) {
         int per_sm = 1;
         cudaError_t e = prep_stream_variant<W, LFR, XREP, THREADS, PREFETCH, BSX>(&per_sm);
@@ -66,45 +87,52 @@ void launch_stream_variant(Handle *h, BscsrState *b, const BscsrChunks &m, cudaS
     // programmatic dependent launch: the grid starts (and stages its query copies) while the sample kernel still runs
     const bool pdl = pdl_enabled() && !(h->cfg.profile_kernels != 0 && s == h->stream);
     launch_pdl(bscsr_stream_kernel<W, LFR, XREP, THREADS, PREFETCH, BSX>, dim3(b->grid), dim3(THREADS),
-               bscsr_stream_smem(XREP, THREADS), s, pdl, (const uint8_t *)b->d_packets, m, (const uint32_t *)b->d_xq,
-               (uint32_t)h->cfg.local_k, b->logs, (const uint32_t *)b->d_theta_seed, (const uint32_t *)b->d_sample_end,
+               bscsr_stream_smem(XREP, THREADS), s, pdl && r.sample_stream == nullptr, (const uint8_t *)b->d_packets, m, r.xq,
+               (uint32_t)h->cfg.local_k, b->logs, (const uint32_t *)r.theta_seed, (const uint32_t *)b->d_sample_end,
                b->d_counter);
 }
 
 template <int W, int LFR, bool BSX>
-void launch_stream_fmt(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s) {
-    const bool prof = h->cfg.profile_kernels != 0 && s == h->stream;
+void launch_stream_fmt(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s, const BsRun &r) {
+    const bool prof = h->cfg.profile_kernels != 0 && s == h->stream && r.sample_stream == nullptr;
     BscsrSample sm{b->d_s_first, b->d_s_count, b->d_s_local0, b->d_s_lookback, b->d_s_part, b->n_pieces,
-                   b->d_s_part_begin, b->d_piece_top, b->d_ticket, b->d_theta_seed};
+                   b->d_s_part_begin, b->d_piece_top, b->d_ticket, r.theta_seed};
     const uint32_t sgrid = (b->n_pieces * 32u + kBsThreads - 1) / kBsThreads;
-    bscsr_sample_kernel<W, LFR, BSX><<<sgrid, kBsThreads, 0, s>>>(b->d_packets, sm, b->d_xq, (uint32_t)h->cfg.local_k);
+    if (r.sample_stream) {
+        // pipelined submit: the sample of this query ran (or runs) on the sample stream, beside the previous query's kernels
+        bscsr_sample_kernel<W, LFR, BSX><<<sgrid, kBsThreads, 0, r.sample_stream>>>(b->d_packets, sm, r.xq, (uint32_t)h->cfg.local_k);
+        cudaEventRecord(r.ev_sample, r.sample_stream);
+        cudaStreamWaitEvent(s, r.ev_sample, 0);
+    } else {
+        bscsr_sample_kernel<W, LFR, BSX><<<sgrid, kBsThreads, 0, s>>>(b->d_packets, sm, r.xq, (uint32_t)h->cfg.local_k);
+    }
     if (prof) cudaEventRecord(h->evm0, s);
     // stream-kernel variants (query copies x CTA size); the alternatives exist for the headline format only
-    if (W == 20 && LFR == 4 && BSX && b->variant == 1) launch_stream_variant<20, 4, 1, 256, false, BSX && W == 20>(h, b, m, s);
-    else if (W == 20 && LFR == 4 && BSX && b->variant == 16) launch_stream_variant<20, 4, 16, 1024, false, BSX && W == 20>(h, b, m, s);
-    else if (W == 20 && LFR == 4 && BSX && b->variant == 33) launch_stream_variant<20, 4, 32, 768, false, BSX && W == 20>(h, b, m, s);
-    else if (W == 20 && LFR == 4 && BSX && b->variant == 34) launch_stream_variant<20, 4, 32, 1024, false, BSX && W == 20>(h, b, m, s);
-    else if (W == 20 && LFR == 4 && BSX && b->variant == 35) launch_stream_variant<20, 4, 32, 1024, true, BSX && W == 20>(h, b, m, s);
-    else if (W == 20 && LFR == 4 && BSX && b->variant == 36) launch_stream_variant<20, 4, 32, 896, true, BSX && W == 20>(h, b, m, s);
-    else launch_stream_variant<W, LFR, kBsDefaultXrep, kBsDefaultThreads, true, BSX>(h, b, m, s);
+    if (W == 20 && LFR == 4 && BSX && b->variant == 1) launch_stream_variant<20, 4, 1, 256, false, BSX && W == 20>(h, b, m, s, r);
+    else if (W == 20 && LFR == 4 && BSX && b->variant == 16) launch_stream_variant<20, 4, 16, 1024, false, BSX && W == 20>(h, b, m, s, r);
+    else if (W == 20 && LFR == 4 && BSX && b->variant == 33) launch_stream_variant<20, 4, 32, 768, false, BSX && W == 20>(h, b, m, s, r);
+    else if (W == 20 && LFR == 4 && BSX && b->variant == 34) launch_stream_variant<20, 4, 32, 1024, false, BSX && W == 20>(h, b, m, s, r);
+    else if (W == 20 && LFR == 4 && BSX && b->variant == 35) launch_stream_variant<20, 4, 32, 1024, true, BSX && W == 20>(h, b, m, s, r);
+    else if (W == 20 && LFR == 4 && BSX && b->variant == 36) launch_stream_variant<20, 4, 32, 896, true, BSX && W == 20>(h, b, m, s, r);
+    else launch_stream_variant<W, LFR, kBsDefaultXrep, kBsDefaultThreads, true, BSX>(h, b, m, s, r);
     if (prof) cudaEventRecord(h->evm1, s);
 }
 
 template <int W, int LFR>
-void launch_stream(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s) {
+void launch_stream(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s, const BsRun &r) {
     if constexpr (W + 10 <= 32) {
-        if (b->bsx) { launch_stream_fmt<W, LFR, true>(h, b, m, s); return; }
+        if (b->bsx) { launch_stream_fmt<W, LFR, true>(h, b, m, s, r); return; }
     }
-    launch_stream_fmt<W, LFR, false>(h, b, m, s);
+    launch_stream_fmt<W, LFR, false>(h, b, m, s, r);
 }
 
 template <int W>
-int dispatch_lfr(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s) {
+int dispatch_lfr(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s, const BsRun &r) {
     switch (h->cfg.limited_finished_rows) {
-        case 1: launch_stream<W, 1>(h, b, m, s); break;
-        case 2: launch_stream<W, 2>(h, b, m, s); break;
-        case 3: launch_stream<W, 3>(h, b, m, s); break;
-        case 4: launch_stream<W, 4>(h, b, m, s); break;
+        case 1: launch_stream<W, 1>(h, b, m, s, r); break;
+        case 2: launch_stream<W, 2>(h, b, m, s, r); break;
+        case 3: launch_stream<W, 3>(h, b, m, s, r); break;
+        case 4: launch_stream<W, 4>(h, b, m, s, r); break;
         default: return h->fail(TKS_EINVAL, "limited_finished_rows=%d is not instantiated (1..4)", h->cfg.limited_finished_rows);
     }
     if (!b->replay_ready) {
@@ -114,7 +142,7 @@ int dispatch_lfr(Handle *h, BscsrState *b, const BscsrChunks &m, cudaStream_t s)
     launch_pdl(bscsr_replay_kernel<W>, dim3(b->P * (uint32_t)h->cfg.limited_finished_rows), dim3(kReplayThreads),
                (size_t)kReplayDynSmem, s, pdl_enabled() && !(h->cfg.profile_kernels != 0 && s == h->stream), b->logs,
                (const uint32_t *)b->d_part_chunk_begin, (uint32_t)h->cfg.limited_finished_rows, (uint32_t)h->cfg.local_k,
-               b->chunk_cap, b->d_res_idx, b->d_res_val, b->d_counter);
+               b->chunk_cap, r.res_idx, r.res_val, b->d_counter);
     return TKS_OK;
 }
 
@@ -506,6 +534,8 @@ int bscsr_upload_coo(Handle *h, const uint32_t *row, const uint32_t *col, const 
     return bscsr_finish_upload(h, b, cols, total);
 }
 
+static void bscsr_transform_query(const BscsrState *b, int W, const uint32_t *vec32, uint32_t *xq);
+
 int bscsr_set_query(Handle *h, const uint32_t *vec32_host, const uint32_t *vec32_dev, cudaStream_t s) {
     BscsrState *b = h->bs;
     if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");
@@ -526,13 +556,36 @@ int bscsr_set_query(Handle *h, const uint32_t *vec32_host, const uint32_t *vec32
     // umulhi product (see bscsr_stream_kernel); columns >= cols read 0 like the zero-initialised URAM
     if (!b->ev_query) TKS_CUDA(h, cudaEventCreateWithFlags(&b->ev_query, cudaEventDisableTiming));
     TKS_CUDA(h, cudaEventSynchronize(b->ev_query));   // h_xq (pinned staging) may still feed the previous copy
-    for (uint32_t c = 0; c < 1024; c++) {
-        uint32_t xq = (c < b->cols) ? (vec32_host[c] >> (32 - W)) : 0u;
-        b->h_xq[c] = (W == 32) ? xq : (xq << 1);
-    }
+    bscsr_transform_query(b, W, vec32_host, b->h_xq);
     TKS_CUDA(h, cudaMemcpyAsync(b->d_xq, b->h_xq, 1024 * 4, cudaMemcpyHostToDevice, s));
     TKS_CUDA(h, cudaEventRecord(b->ev_query, s));
     b->have_query = true;
+    return TKS_OK;
+}
+
+static int bscsr_dispatch(Handle *h, BscsrState *b, cudaStream_t s, const BsRun &r) {
+    BscsrChunks m{b->d_chunk_first, b->d_chunk_count, b->d_chunk_local0, b->d_chunk_row_in, b->d_chunk_lookback,
+                  b->d_chunk_part, b->n_chunks, b->chunk_cap};
+    int rc;
+    switch (h->cfg.fixed_width) {
+        case 20: rc = dispatch_lfr<20>(h, b, m, s, r); break;
+        case 21: rc = dispatch_lfr<21>(h, b, m, s, r); break;
+        case 25: rc = dispatch_lfr<25>(h, b, m, s, r); break;
+        case 26: rc = dispatch_lfr<26>(h, b, m, s, r); break;
+        case 32: rc = dispatch_lfr<32>(h, b, m, s, r); break;
+        default: return h->fail(TKS_EINVAL, "fixed_width not instantiated");
+    }
+    if (rc) return rc;
+    TKS_CUDA(h, cudaGetLastError());
+    return TKS_OK;
+}
+
+static int bscsr_pipe_drain(Handle *h, BscsrState *b) {
+    for (int i = 0; i < BscsrState::kSlots; i++) {
+        if (!b->p_busy[i]) continue;
+        TKS_CUDA(h, cudaEventSynchronize(b->p_ev_done[i]));
+        b->p_busy[i] = false;
+    }
     return TKS_OK;
 }
 
@@ -540,21 +593,122 @@ int bscsr_launch(Handle *h, cudaStream_t s) {
     BscsrState *b = h->bs;
     if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");
     if (!b->have_query) return h->fail(TKS_ESTATE, "no query set");
+    int rcd = bscsr_pipe_drain(h, b);   // the logs and the chunk scheduler are shared with pipelined submits
+    if (rcd) return rcd;
     if (s != h->stream && b->ev_query) TKS_CUDA(h, cudaStreamWaitEvent(s, b->ev_query, 0));
-    BscsrChunks m{b->d_chunk_first, b->d_chunk_count, b->d_chunk_local0, b->d_chunk_row_in, b->d_chunk_lookback,
-                  b->d_chunk_part, b->n_chunks, b->chunk_cap};
-    int rc;
-    switch (h->cfg.fixed_width) {
-        case 20: rc = dispatch_lfr<20>(h, b, m, s); break;
-        case 21: rc = dispatch_lfr<21>(h, b, m, s); break;
-        case 25: rc = dispatch_lfr<25>(h, b, m, s); break;
-        case 26: rc = dispatch_lfr<26>(h, b, m, s); break;
-        case 32: rc = dispatch_lfr<32>(h, b, m, s); break;
-        default: return h->fail(TKS_EINVAL, "fixed_width not instantiated");
-    }
+    const BsRun r{b->d_xq, b->d_theta_seed, b->d_res_idx, b->d_res_val, nullptr, nullptr};
+    int rc = bscsr_dispatch(h, b, s, r);
     if (rc) return rc;
-    TKS_CUDA(h, cudaGetLastError());
     b->have_words = false;
+    return TKS_OK;
+}
+
+// W-bit truncation of the raw query words, pre-shifted for the umulhi product (kernel vec load, .cpp:127-137)
+static void bscsr_transform_query(const BscsrState *b, int W, const uint32_t *vec32, uint32_t *xq) {
+    for (uint32_t c = 0; c < 1024; c++) {
+        const uint32_t q = (c < b->cols) ? (vec32[c] >> (32 - W)) : 0u;
+        xq[c] = (W == 32) ? q : (q << 1);
+    }
+}
+
+static int bscsr_pipe_init(Handle *h, BscsrState *b) {
+    if (b->p_sample_stream) return TKS_OK;
+    int lo = 0, hi = 0;
+    TKS_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    TKS_CUDA(h, cudaStreamCreateWithPriority(&b->p_sample_stream, cudaStreamNonBlocking, hi));
+    const size_t nres = (size_t)b->P * h->cfg.local_k * 16;
+    for (int i = 0; i < BscsrState::kSlots; i++) {
+        TKS_CUDA(h, cudaEventCreateWithFlags(&b->p_ev_sample[i], cudaEventDisableTiming));
+        TKS_CUDA(h, cudaEventCreateWithFlags(&b->p_ev_done[i], cudaEventDisableTiming));
+        TKS_CUDA(h, cudaMalloc(&b->p_d_xq[i], 1024 * 4));
+        TKS_CUDA(h, cudaMallocHost(&b->p_h_xq[i], 1024 * 4));
+        TKS_CUDA(h, cudaMalloc(&b->p_d_theta[i], (size_t)b->P * h->cfg.limited_finished_rows * 4));
+        TKS_CUDA(h, cudaMemset(b->p_d_theta[i], 0, (size_t)b->P * h->cfg.limited_finished_rows * 4));
+        TKS_CUDA(h, cudaMallocHost(&b->p_h_words[i], 2 * nres * 4));
+        std::memset(b->p_h_words[i], 0, 2 * nres * 4);   // positions >= LFR stay 0 (.cpp:100-110)
+    }
+    return TKS_OK;
+}
+
+// One query into the two-slot pipeline: transform + H2D + sample on the sample stream (they overlap the previous
+// query's stream and replay kernels), then stream + replay on stream `s`; for a host query the replay kernel stores the
+// result words into the slot's pinned host block and bscsr_fetch_ticket() waits for that query alone and merges.
+int bscsr_submit(Handle *h, const uint32_t *vec32_host, const uint32_t *vec32_dev, uint32_t k, cudaStream_t s,
+                 bool query_ready, uint64_t *ticket) {
+    BscsrState *b = h->bs;
+    if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");
+    int rc = bscsr_pipe_init(h, b);
+    if (rc) return rc;
+    const uint64_t seq = b->p_seq + 1;
+    const int slot = (int)(seq % BscsrState::kSlots);
+    if (b->p_busy[slot]) {
+        TKS_CUDA(h, cudaEventSynchronize(b->p_ev_done[slot]));
+        b->p_busy[slot] = false;
+    }
+    const size_t nres = (size_t)b->P * h->cfg.local_k * 16;
+    uint32_t *res_idx = b->d_res_idx, *res_val = b->d_res_val;
+    if (vec32_host) {
+        bscsr_transform_query(b, h->cfg.fixed_width, vec32_host, b->p_h_xq[slot]);
+        TKS_CUDA(h, cudaMemcpyAsync(b->p_d_xq[slot], b->p_h_xq[slot], 1024 * 4, cudaMemcpyHostToDevice, b->p_sample_stream));
+        res_idx = b->p_h_words[slot];            // the replay kernel writes the words straight to pinned host memory
+        res_val = b->p_h_words[slot] + nres;
+        b->p_ticket[slot] = seq;
+    } else {
+        // a query already in HBM (raw words): transformed on the sample stream; the result words stay on the device
+        if (!query_ready) {
+            if (!b->ev_query) TKS_CUDA(h, cudaEventCreateWithFlags(&b->ev_query, cudaEventDisableTiming));
+            TKS_CUDA(h, cudaEventRecord(b->ev_query, s));
+            TKS_CUDA(h, cudaStreamWaitEvent(b->p_sample_stream, b->ev_query, 0));
+        }
+        switch (h->cfg.fixed_width) {
+            case 20: bscsr_query_kernel<20><<<4, 256, 0, b->p_sample_stream>>>(vec32_dev, b->cols, b->p_d_xq[slot]); break;
+            case 21: bscsr_query_kernel<21><<<4, 256, 0, b->p_sample_stream>>>(vec32_dev, b->cols, b->p_d_xq[slot]); break;
+            case 25: bscsr_query_kernel<25><<<4, 256, 0, b->p_sample_stream>>>(vec32_dev, b->cols, b->p_d_xq[slot]); break;
+            case 26: bscsr_query_kernel<26><<<4, 256, 0, b->p_sample_stream>>>(vec32_dev, b->cols, b->p_d_xq[slot]); break;
+            default: bscsr_query_kernel<32><<<4, 256, 0, b->p_sample_stream>>>(vec32_dev, b->cols, b->p_d_xq[slot]); break;
+        }
+        b->p_ticket[slot] = 0;
+    }
+    const BsRun r{b->p_d_xq[slot], b->p_d_theta[slot], res_idx, res_val, b->p_sample_stream, b->p_ev_sample[slot]};
+    rc = bscsr_dispatch(h, b, s, r);
+    if (rc) return rc;
+    TKS_CUDA(h, cudaEventRecord(b->p_ev_done[slot], s));
+    b->p_busy[slot] = true;
+    b->p_k[slot] = k;
+    b->p_seq = seq;
+    b->have_words = false;
+    h->last_k = k;
+    if (ticket) *ticket = seq;
+    return TKS_OK;
+}
+
+int bscsr_submit_host(Handle *h, const uint32_t *vec32, uint32_t k, uint64_t *ticket) {
+    return bscsr_submit(h, vec32, nullptr, k, h->stream, true, ticket);
+}
+
+int bscsr_fetch_ticket(Handle *h, uint64_t ticket, uint32_t *idx_out, uint32_t *val_out, uint32_t *count) {
+    BscsrState *b = h->bs;
+    if (!b || !b->p_sample_stream || ticket == 0 || ticket > b->p_seq) return h->fail(TKS_EINVAL, "unknown ticket");
+    const int slot = (int)(ticket % BscsrState::kSlots);
+    if (b->p_ticket[slot] != ticket)
+        return h->fail(TKS_ESTATE, "the result of ticket %llu is gone: at most %d queries are kept, fetch before submitting further",
+                       (unsigned long long)ticket, BscsrState::kSlots);
+    TKS_CUDA(h, cudaEventSynchronize(b->p_ev_done[slot]));
+    b->p_busy[slot] = false;
+    const size_t nres = (size_t)b->P * h->cfg.local_k * 16;
+    const uint32_t k = b->p_k[slot];
+    std::vector<uint32_t> mi(k, 0u), mv(k, 0u);
+    uint32_t n_out = 0;
+    // read_result (host_spmv_bscsr.cpp:399-448) + sort_tuples over the slot's words
+    if (tks_merge_partition_words(b->P, (uint32_t)h->cfg.local_k, b->B, b->p_h_words[slot], b->p_h_words[slot] + nres,
+                                  b->first_row.data(), h->cfg.tie_break, k, mi.data(), mv.data(), &n_out) != TKS_OK)
+        return h->fail(TKS_EINVAL, "merge of the partition results failed");
+    const uint32_t n = n_out < k ? n_out : k;
+    std::memcpy(idx_out, mi.data(), n * 4);
+    std::memcpy(val_out, mv.data(), n * 4);
+    for (uint32_t i = n; i < k; i++) { idx_out[i] = 0; val_out[i] = 0; }
+    if (count) *count = n;
+    h->stats.last_candidates = n_out;
     return TKS_OK;
 }
 
@@ -667,6 +821,12 @@ void bscsr_destroy(Handle *h) {
     cudaFree(b->d_xq); cudaFreeHost(b->h_xq); cudaFree(b->d_counter); cudaFree(b->d_sample_end);
     cudaFree(b->d_res_idx); cudaFreeHost(b->h_res_idx);
     if (b->ev_query) cudaEventDestroy(b->ev_query);
+    for (int i = 0; i < BscsrState::kSlots; i++) {
+        if (b->p_ev_sample[i]) cudaEventDestroy(b->p_ev_sample[i]);
+        if (b->p_ev_done[i]) cudaEventDestroy(b->p_ev_done[i]);
+        cudaFree(b->p_d_xq[i]); cudaFreeHost(b->p_h_xq[i]); cudaFree(b->p_d_theta[i]); cudaFreeHost(b->p_h_words[i]);
+    }
+    if (b->p_sample_stream) cudaStreamDestroy(b->p_sample_stream);
     delete b;
     h->bs = nullptr;
 }

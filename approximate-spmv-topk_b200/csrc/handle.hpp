@@ -162,6 +162,10 @@ int bscsr_upload_coo(Handle *h, const uint32_t *row, const uint32_t *col, const 
                      uint32_t num_rows, uint32_t cols, bool arrays_on_device);
 int bscsr_set_query(Handle *h, const uint32_t *vec32_host, const uint32_t *vec32_dev, cudaStream_t s);
 int bscsr_launch(Handle *h, cudaStream_t s);
+int bscsr_submit_host(Handle *h, const uint32_t *vec32, uint32_t k, uint64_t *ticket);   // pipelined: sample of query i+1 beside query i
+int bscsr_submit(Handle *h, const uint32_t *vec32_host, const uint32_t *vec32_dev, uint32_t k, cudaStream_t s,
+                 bool query_ready, uint64_t *ticket);
+int bscsr_fetch_ticket(Handle *h, uint64_t ticket, uint32_t *idx_out, uint32_t *val_out, uint32_t *count);
 int bscsr_fetch(Handle *h);   // D2H of partition result words + host merge
 int bscsr_read_result(Handle *h, uint32_t *idx_out, uint32_t *val_out, uint32_t k, uint32_t *count);
 int bscsr_read_partition_results(Handle *h, uint32_t *idx_words, uint32_t *val_words);

@@ -315,6 +315,37 @@ class SpMVFixed(_Base):
     def reset_device(self, dptr, stream=0):
         check(capi.lib().tks_set_query_device(self.handle, C.c_void_p(dptr), 1, C.c_void_p(stream)), self.handle)
 
+    def submit(self, dptr, k=None, stream=0, query_ready=False):
+        """Pipelined reset_device + run_async for a query (raw words) already in HBM: its transform and sample run on
+        a second stream beside the previous query's stream and replay kernels; read_result() returns the last one."""
+        k = self.k if k is None else k
+        check(capi.lib().tks_submit(self.handle, C.c_void_p(dptr), k, capi.SUBMIT_QUERY_READY if query_ready else 0,
+                                    C.c_void_p(stream)), self.handle)
+        self.k = k
+
+    def submit_host(self, vec32, k=None):
+        """Pipelined reset(vec) + operator(): the query's transform, copy and sample overlap the previous query's stream
+        and replay kernels; returns a ticket for fetch().  Two queries are kept."""
+        k = self.k if k is None else k
+        st = self.__dict__.get("_sh_stage")
+        if st is None:
+            buf = np.empty(self.num_cols, np.uint32)
+            st = self._sh_stage = (buf, _ptr(buf), C.c_uint64())
+        st[0][:] = np.asarray(vec32, np.uint32).reshape(-1)
+        check(capi.lib().tks_submit_host(self.handle, st[1], k, 0, C.byref(st[2])), self.handle)
+        self.k = k
+        return st[2].value
+
+    def fetch(self, ticket):
+        """read_result() of the query submit_host() gave `ticket` for: (raw values uint32[n], indices uint32[n]), n <= k."""
+        out = self.__dict__.get("_fetch_stage")
+        if out is None:
+            idx, val, cnt = np.zeros(1024, np.uint32), np.zeros(1024, np.uint32), C.c_uint32()
+            out = self._fetch_stage = (idx, val, cnt, _ptr(idx), _ptr(val), C.byref(cnt))
+        check(capi.lib().tks_fetch(self.handle, int(ticket), out[3], out[4], out[5]), self.handle)
+        n = out[2].value
+        return out[1][:n].copy(), out[0][:n].copy()
+
     def read_result(self):
         """Returns (raw values uint32[count], indices uint32[count]) -- may be shorter than k."""
         out = self.__dict__.get("_out_stage")

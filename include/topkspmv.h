@@ -232,13 +232,17 @@ int tks_peer_exchange_async(tks_handle *h, uint32_t k, void *cuda_stream);  /* e
  * call returns) to the device on the sample stream and returns a ticket; the select kernel of that query stores the
  * sorted indices, scores and the count straight into a pinned host block; tks_fetch(ticket) waits for that query alone
  * and copies its first k results out (val_out float[k]).  Results are kept for the last four tickets: fetch ticket t
- * before submitting ticket t + 4.  Host-to-device and device-to-host traffic of every query is part of its step.  */
-int tks_submit_host(tks_handle *h, const float *query, uint32_t k, uint32_t flags, uint64_t *ticket);
-int tks_fetch(tks_handle *h, uint64_t ticket, uint32_t *idx_out, float *val_out, uint32_t *count);
+ * before submitting ticket t + 4.  Host-to-device and device-to-host traffic of every query is part of its step.
+ * BS-CSR mode: `query` is the 1024 raw ap_ufixed<32,1> words of tks_set_query, val_out receives raw uint32 scores and
+ * *count may be < k (read_result semantics of host_spmv_bscsr.cpp:399-448); two queries are kept; the sample of query
+ * i + 1 (and its copy) overlaps the stream and replay kernels of query i, and the host merge of query i runs in
+ * tks_fetch while the device works on query i + 1.                                                              */
+int tks_submit_host(tks_handle *h, const void *query, uint32_t k, uint32_t flags, uint64_t *ticket);
+int tks_fetch(tks_handle *h, uint64_t ticket, uint32_t *idx_out, void *val_out, uint32_t *count);
 
 #define TKS_SUBMIT_EXCHANGE 1u
 #define TKS_SUBMIT_QUERY_READY 2u
-int tks_submit(tks_handle *h, const float *d_query, uint32_t k, uint32_t flags, void *cuda_stream);
+int tks_submit(tks_handle *h, const void *d_query, uint32_t k, uint32_t flags, void *cuda_stream);   /* BS-CSR mode: 1024 raw words, sample overlap only */
 int tks_pipeline_wait(tks_handle *h, void *cuda_stream);
 int tks_pipeline_stamps(tks_handle *h, uint64_t *stamps_ns, uint32_t capacity, uint32_t *count);
 

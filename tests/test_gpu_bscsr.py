@@ -195,3 +195,53 @@ def test_long_logs_with_massive_ties(cuda_required, tks, orc):
     v = rng.choice(np.array([0.125, 0.25, 0.5]), x.size)
     vec = np.full(cols, 0.5, np.float32)
     run_both(tks, orc, x, y, v, rows, cols, vec, P=4)
+
+
+@pytest.mark.parametrize("W,drift_free", [(20, False), (20, True), (32, False)])
+def test_pipelined_submits_are_bit_exact(cuda_required, tks, orc, gen, W, drift_free):
+    """tks_submit_host / tks_fetch in BS-CSR mode: the sample of query i+1 runs on a second stream beside the stream and
+    replay kernels of query i and the replay kernel writes the result words straight to pinned host memory; every
+    result must be the oracle's, bit for bit, and the blocking verbs must still work afterwards."""
+    rows = 60000
+    x, y, v = gen.create_sparse_matrix(rows, 1024, 20, "gamma", seed=9)
+    qs = [make_query(1024, 500 + i) for i in range(9)]
+    want = [orc.bscsr_topk(x, y, v, rows, q, W=W, drift_free=drift_free) for q in qs]
+    with tks.SpMVFixed(x, y, want[0]["val32"], rows, 1024, k=100, fixed_width=W, drift_free=drift_free) as f:
+        tickets, got = [], {}
+        for i, o in enumerate(want):
+            tickets.append(f.submit_host(o["vec32"], 100))
+            if i >= 1:
+                got[i - 1] = f.fetch(tickets[i - 1])
+        got[len(want) - 1] = f.fetch(tickets[-1])
+        for i, o in enumerate(want):
+            n = min(100, o["idx"].size)
+            gv, gi = got[i]
+            assert np.array_equal(gi, o["idx"][:n]) and np.array_equal(gv, o["val"][:n]), f"query {i}"
+        # a result pushed out of the two slots is refused
+        t0 = f.submit_host(want[0]["vec32"], 100)
+        f.submit_host(want[1]["vec32"], 100)
+        f.submit_host(want[2]["vec32"], 100)
+        with pytest.raises(tks.capi.TksError, match="gone"):
+            f.fetch(t0)
+        f.reset(want[3]["vec32"])
+        f()
+        gv, gi = f.read_result()
+        n = min(100, want[3]["idx"].size)
+        assert np.array_equal(gi, want[3]["idx"][:n]) and np.array_equal(gv, want[3]["val"][:n])
+
+
+def test_pipelined_device_queries_bit_exact(cuda_required, tks, orc, gen):
+    import torch
+    rows = 60000
+    x, y, v = gen.create_sparse_matrix(rows, 1024, 20, "gamma", seed=9)
+    qs = [make_query(1024, 800 + i) for i in range(6)]
+    want = [orc.bscsr_topk(x, y, v, rows, q) for q in qs]
+    dq = torch.from_numpy(np.stack([o["vec32"] for o in want]).view(np.int32)).cuda()
+    torch.cuda.synchronize()
+    with tks.SpMVFixed(x, y, want[0]["val32"], rows, 1024, k=100) as f:
+        for i, o in enumerate(want):
+            f.submit(dq[i].data_ptr(), 100, 0, query_ready=True)
+            if i % 2 == 1 or i == len(want) - 1:
+                gv, gi = f.read_result()
+                n = min(100, o["idx"].size)
+                assert np.array_equal(gi, o["idx"][:n]) and np.array_equal(gv, o["val"][:n]), f"query {i}"
