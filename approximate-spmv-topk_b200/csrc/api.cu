@@ -43,8 +43,8 @@ int cap_threads(int variant, int vt) {
 // ... inside a pipelined submit: leave room for one CTA of the sample kernel per SM (registers)
 int pipe_threads(int variant, int vt) {
     static const int t0 = (int)env_u32("TKS_PIPE_THREADS", 512u) / 32 * 32;   // A/B switch: 256..576
-    // 72 registers: 2 x 10 warps; with 2 x 11 the sample CTAs (80 registers per thread) were measured NOT to fit beside
-    // them (r02i/j: the register file is allocated per SM sub-partition, and 6 x 2304 of its 16384 leave one sample warp)
+    // 72 registers: 2 x 10 warps leave room for the sample CTAs in every SM sub-partition (with 2 x 11 they were measured
+    // NOT to fit, r02i/j: the register file is allocated per sub-partition, 6 x 2304 of its 16384 leave one warp)
     static const int t16 = (int)env_u32("TKS_PIPE_THREADS_16BIT", 320u) / 32 * 32;
     if (vt != 0) { const int c = cap_threads(variant, vt); return c < t16 ? c : t16; }
     if (variant == 0) return t0 < 256 ? 256 : (t0 > 576 ? 576 : t0);
@@ -53,7 +53,8 @@ int pipe_threads(int variant, int vt) {
 int pipe_sample_threads(int vt) {
     static const int t = (int)env_u32("TKS_PIPE_SAMPLE_THREADS", 0u) / 32 * 32;
     if (t >= 32) return t > 256 ? 256 : t;
-    return vt != 0 ? 64 : 128;   // 80 registers per thread in the 16-bit modes: 64 threads = 5120 registers
+    (void)vt;
+    return 128;   // the sample kernel is capped at 64 registers: 8192 per CTA; 64-thread CTAs made the 16-bit sample 200 us long (r02r)
 }
 // L1 / shared-memory split requested for every kernel of the float path, in percent of the maximum (-1: the driver's
 // choice per kernel).  Kernels that share an SM in the pipelined path must agree on it: an SM cannot change the split
@@ -210,7 +211,14 @@ int alloc_query_side(Handle *h) {
     return TKS_OK;
 }
 
+void drop_run_graph(Handle *h) {
+    if (h->run_graph) cudaGraphExecDestroy(h->run_graph);
+    h->run_graph = nullptr;
+    h->run_graph_k = 0;
+}
+
 void free_matrix(Handle *h) {
+    drop_run_graph(h);
     cudaFree(h->d_val); h->d_val = nullptr;
     cudaFree(h->d_col16); h->d_col16 = nullptr;
     cudaFree(h->d_rowbits); h->d_rowbits = nullptr;
@@ -462,6 +470,38 @@ void launch_batched(Handle *h, uint32_t k, cudaStream_t s, bool profile) {
     h->res_on_host = false;
 }
 
+bool graphs_enabled() {
+    static const bool on = !(std::getenv("TKS_GRAPH") && std::atoi(std::getenv("TKS_GRAPH")) == 0);
+    return on;
+}
+
+// The three launches of one blocking query (results straight to the pinned host block) as ONE graph launch: captured
+// from the very calls launch_single_query makes, programmatic-dependent-launch edges included, once per k.  Returns
+// false when the capture is not possible (the caller then launches the kernels one by one).
+bool launch_query_graph(Handle *h, uint32_t k, cudaStream_t s) {
+    if (h->run_graph_failed || !graphs_enabled()) return false;
+    if (!h->run_graph || h->run_graph_k != k) {
+        drop_run_graph(h);
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); h->run_graph_failed = true; return false; }
+        launch_single_query(h, 0, k, s, false, true);
+        const cudaError_t e1 = cudaStreamEndCapture(s, &g);
+        cudaError_t e2 = cudaErrorUnknown;
+        if (e1 == cudaSuccess && g) e2 = cudaGraphInstantiate(&h->run_graph, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            cudaGetLastError();
+            h->run_graph = nullptr;
+            h->run_graph_failed = true;
+            return false;
+        }
+        h->run_graph_k = k;
+    }
+    if (cudaGraphLaunch(h->run_graph, s) != cudaSuccess) { cudaGetLastError(); drop_run_graph(h); h->run_graph_failed = true; return false; }
+    h->res_on_host = true;
+    return true;
+}
+
 bool use_batched(const Handle *h) {
     return h->batch > 1 && h->batched_ok && h->cfg.batch_mode == 0 && h->d_xT != nullptr &&
            batched_smem_bytes(h->cols) <= batched_smem_bytes((uint32_t)h->cfg.max_cols);
@@ -488,7 +528,10 @@ int launch_float(Handle *h, uint32_t k, cudaStream_t s, bool profile = false, bo
         // that is not counted)
         h->stats.algorithmic_bytes = matrix_bytes + (uint64_t)h->batch * ((uint64_t)h->cols * 4ull + k * 8ull);
     } else {
-        for (uint32_t q = 0; q < h->batch; q++) launch_single_query(h, q, k, s, profile && q == 0, to_host && h->batch == 1);
+        // blocking tks_run of one query: one graph launch instead of three kernel launches
+        const bool graphed = to_host && h->batch == 1 && !profile && s == h->stream && launch_query_graph(h, k, s);
+        if (!graphed)
+            for (uint32_t q = 0; q < h->batch; q++) launch_single_query(h, q, k, s, profile && q == 0, to_host && h->batch == 1);
         h->last_run_batched = false;
         h->stats.launches_per_run = 3 * h->batch;
         h->stats.algorithmic_bytes = matrix_bytes + (uint64_t)h->cols * 4ull + k * 8ull;
@@ -682,6 +725,7 @@ void tks_destroy(tks_handle *h) {
     cudaFree(h->d_res_keys); cudaFree(h->d_res_block);
     cudaFree(h->d_xT); cudaFree(h->d_bpool); cudaFree(h->d_pass_counter); cudaFree(h->d_bsample_keys);
     cudaFreeHost(h->h_res_block); cudaFreeHost(h->h_x);
+    drop_run_graph(h);
     cudaFree(h->d_pipe_state); cudaFree(h->d_pipe_sample_keys); cudaFree(h->d_pipe_stamps);
     cudaFreeHost(h->h_pipe_stamps);
     cudaFree(h->d_pipe_query); cudaFreeHost(h->h_pipe_query); cudaFreeHost(h->h_pipe_res);

@@ -38,7 +38,9 @@ constexpr uint32_t kMaxCols = 16384;                       // exclusive: cols <=
 constexpr uint32_t kElemsPerIter = kWarp * 8u;              // 256 non-zeros per warp iteration with fp32 values (512 with 16-bit values)
 constexpr uint32_t kMainThreads = 512;
 constexpr uint32_t kMainThreadsWide = 576;   // k <= 128 variant: 2 x 18 warps per SM at <= 56 registers per thread
-constexpr uint32_t kMainThreads16 = 384;     // 16-bit value modes: 16 non-zeros per lane, ~80 registers, 2 x 12 warps per SM
+// 16-bit value modes: 16 non-zeros per lane, 72-80 registers, 2 x 12 warps per SM.  (Capped at 64 registers the kernel
+// runs 2 x 16 warps without spills but measured slower alone: 0.1708 vs 0.167 ms, r02r.)
+constexpr uint32_t kMainThreads16 = 384;
 constexpr uint32_t kSampleThreads = 256;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 

@@ -61,6 +61,11 @@ struct Handle {
     float *h_x = nullptr;               // pinned staging for tks_set_query
     uint32_t last_k = 0;
     bool have_result = false;
+    // blocking tks_run, one query: sample -> main -> select captured once per k into a CUDA graph and replayed with one
+    // launch (api.cu run_graph_*); dropped whenever the matrix changes
+    cudaGraphExec_t run_graph = nullptr;
+    uint32_t run_graph_k = 0;
+    bool run_graph_failed = false;
     bool res_on_host = false;           // the last select wrote indices / scores / count to the pinned host block only
     bool last_run_pipelined = false;
 
