@@ -65,6 +65,11 @@ size_t main_smem_bytes(uint32_t cols, int variant, int threads) {
     return (((cols + 1u) * 4u + 15u) & ~15u) + (size_t)(threads / 32) * kCaps[variant] * 8u;
 }
 
+// TKS_TMA=1: the k <= 128 main kernel streams through per-warp rings of bulk copies (cp.async.bulk + mbarrier) instead
+// of register loads; chunk loads then start on 128-non-zero boundaries (in the sample kernel too)
+bool tma_enabled() { static const bool on = std::getenv("TKS_TMA") && std::atoi(std::getenv("TKS_TMA")) != 0; return on; }
+int tma_threads(int vt) { static const int t = (int)env_u32("TKS_TMA_THREADS", 0u) / 32 * 32; return t >= 64 ? t : (vt != 0 ? 384 : 448); }
+
 // bounds of the device-side waits (peer records, pipelined hand-overs); raise them under compute-sanitizer
 uint32_t spin_timeout_ms() { static const uint32_t v = env_u32("TKS_SPIN_TIMEOUT_MS", 2000u); return v; }
 uint32_t tau_wait_us() { static const uint32_t v = env_u32("TKS_TAU_WAIT_US", 20000u); return v; }
@@ -116,8 +121,25 @@ cudaError_t prep_main_t(Handle *h, int variant) {
     return cudaSuccess;
 }
 
+template <int VT>
+cudaError_t prep_main_tma(Handle *h) {
+    const int threads = tma_threads(VT);
+    const size_t smem = main_smem_bytes(h->cfg.max_cols, 0, threads) + main_tma_extra_smem<VT>(threads / 32);
+    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<256, VT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<256, VT, true>, threads, smem);
+    if (e != cudaSuccess) return e;
+    h->tma_grid = (per_sm < 1 ? 1 : per_sm) * h->num_sms;
+    return cudaSuccess;
+}
+
 template <int CAP>
 cudaError_t prep_main(Handle *h, int variant) {
+    if (CAP == 256 && tma_enabled()) {
+        cudaError_t e = value_type(h) == TKS_VALUE_FP16 ? prep_main_tma<1>(h) : value_type(h) == TKS_VALUE_BF16 ? prep_main_tma<2>(h) : prep_main_tma<0>(h);
+        if (e != cudaSuccess) return e;
+    }
     switch (value_type(h)) {
         case TKS_VALUE_FP16: return prep_main_t<CAP, 1>(h, variant);
         case TKS_VALUE_BF16: return prep_main_t<CAP, 2>(h, variant);
@@ -134,6 +156,17 @@ void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, Run
     const int tie_higher = h->cfg.tie_break == TKS_TIE_HIGHER_INDEX;
     const dim3 grid(seq ? h->pipe_main_grid[variant] : h->main_grid[variant]), block(threads);
     const uint32_t tw = tau_wait_us();
+    if (CAP == 256 && tma_enabled()) {
+        const int tt = tma_threads(value_type(h));
+        const dim3 tgrid(h->tma_grid), tblock(tt);
+        const size_t base = main_smem_bytes(m.cols, 0, tt);
+        switch (value_type(h)) {
+            case TKS_VALUE_FP16: launch_pdl(csr_topk_main_kernel<256, 1, true>, tgrid, tblock, base + main_tma_extra_smem<1>(tt / 32), s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
+            case TKS_VALUE_BF16: launch_pdl(csr_topk_main_kernel<256, 2, true>, tgrid, tblock, base + main_tma_extra_smem<2>(tt / 32), s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
+            default: launch_pdl(csr_topk_main_kernel<256, 0, true>, tgrid, tblock, base + main_tma_extra_smem<0>(tt / 32), s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
+        }
+        return;
+    }
     switch (value_type(h)) {
         case TKS_VALUE_FP16: launch_pdl(csr_topk_main_kernel<CAP, 1>, grid, block, smem, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
         case TKS_VALUE_BF16: launch_pdl(csr_topk_main_kernel<CAP, 2>, grid, block, smem, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
@@ -154,7 +187,7 @@ void launch_main_variant(Handle *h, int variant, const CsrDevice &m, const float
 CsrDevice csr_device(const Handle *h) {
     return CsrDevice{h->d_val, h->d_col16, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start,
                      h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols, (uint32_t)h->row_offset,
-                     (uint32_t)value_type(h)};
+                     (uint32_t)value_type(h), tma_enabled() ? 128u : (value_type(h) != 0 ? 16u : 8u)};
 }
 
 __global__ void widen_u32_to_u64_kernel(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {

@@ -55,6 +55,7 @@ struct CsrDevice {
     uint32_t cols;
     uint32_t row_offset;           // added to every reported row id
     uint32_t val_type;             // TKS_VALUE_*: 0 fp32, 1 half, 2 bfloat16 (the batched kernel branches on it at run time)
+    uint32_t start_align;          // chunk loads start on a multiple of this many non-zeros: 8 / 16 (one lane), 128 with bulk copies
 };
 
 // Per-query scratch that lives in HBM; zeroed at creation and by the select kernel.
@@ -307,6 +308,65 @@ struct PoolSink {
     }
 };
 
+// What a warp carries from iteration to iteration inside a chunk.
+struct ChunkCarry {
+    uint32_t R;            // ordinal of the row "in progress" (a bogus one before the chunk at first)
+    bool first_pending;
+    float carry;
+};
+
+// One warp iteration's loaded words -> products, segmented sums, candidates.  `edge`: the iteration holds elements
+// outside [rel_s, rel_e) (first / last iteration of the chunk), which are neutralised.
+template <int VT, typename Sink>
+__device__ __forceinline__ void csr_consume_iter(const typename ValRaw<VT>::type &cv, const typename ColRaw<VT>::type &cc,
+                                                 uint32_t cr, bool edge, uint32_t it, int32_t rel_s, int32_t rel_e,
+                                                 const uint8_t *__restrict__ xs_bytes, uint32_t zero_off, ChunkCarry &cy,
+                                                 Sink &sink) {
+    constexpr uint32_t EPL = Epl<VT>::v, EPI = kWarp * EPL;
+    const unsigned lane = lane_id();
+    IterState<EPL> o;
+    float carry_out;
+    if (edge) {
+        // offsets inside the chunk fit 32 bits (a chunk is far smaller than 2^31 non-zeros)
+        const int32_t ebase = (int32_t)(it * EPI + lane * EPL);
+        const int32_t l32 = rel_s - ebase, h32 = rel_e - ebase;
+        const uint32_t lo = l32 < 0 ? 0u : (l32 > (int32_t)EPL ? EPL : (uint32_t)l32);
+        const uint32_t hi = h32 < 0 ? 0u : (h32 > (int32_t)EPL ? EPL : (uint32_t)h32);
+        csr_iter<true, VT>(cv, cc, cr, xs_bytes, zero_off, lo, hi, cy.carry, carry_out, o);
+    } else {
+        csr_iter<false, VT>(cv, cc, cr, xs_bytes, zero_off, 0u, EPL, cy.carry, carry_out, o);
+    }
+    cy.carry = carry_out;
+
+    const bool passT = (o.fb != 0) && (o.T >= sink.tau);
+    const unsigned pm = __ballot_sync(kFull, passT || (o.cm >= sink.tau));
+    const uint32_t Rtot = __reduce_add_sync(kFull, o.nf);
+    if (pm) {
+        // ordinal of the row in progress when entering this lane = R + rows started in lower lanes
+        uint32_t pre = o.nf;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const uint32_t up = __shfl_up_sync(kFull, pre, dlt);
+            if ((int)lane >= dlt) pre += up;
+        }
+        const uint32_t ord_l = cy.R + (pre - o.nf);
+        const bool bogus = cy.first_pending && (lane == (unsigned)(__ffs(o.fm) - 1));
+        sink.emit(passT && !bogus, o.T, ord_l);
+        if (__any_sync(kFull, o.nf >= 2)) {
+            // rows that start AND end inside one lane (length <= EPL - 1)
+#pragma unroll
+            for (int j = 1; j < (int)EPL; j++) {
+                const uint32_t below = o.fb & ((1u << j) - 1u);
+                const bool ends_here = ((o.fb >> j) & 1u) && below != 0;
+                if (EPL > 8 && !__any_sync(kFull, ends_here)) continue;   // warp-uniform skip
+                sink.emit(ends_here && (o.seg[j - 1] >= sink.tau), o.seg[j - 1], ord_l + __popc(below));
+            }
+        }
+    }
+    if (o.fm) cy.first_pending = false;
+    cy.R += Rtot;
+}
+
 // Stream one chunk (or its first max_iters iterations) through `sink`.
 template <int VT, typename Sink>
 __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint32_t c,
@@ -315,7 +375,10 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
     const unsigned lane = lane_id();
     const uint64_t s = m.chunk_start[c], e = m.chunk_start[c + 1];
     if (s >= e) return;
-    const uint64_t a0 = s & ~(uint64_t)(EPL - 1u);       // 32-byte aligned start of the first 256-bit load
+    // start of the first load: aligned to one lane's elements (32 bytes of values), or to 128 non-zeros when the matrix is
+    // also streamed by the bulk-copy variant (16-byte aligned row-start bits); the sample and the main kernel must agree
+    // on it -- the lane a non-zero lands in decides how its row's sum associates
+    const uint64_t a0 = s & ~(uint64_t)(m.start_align - 1u);
     const uint64_t n_iter64 = (e - a0 + EPI - 1) / EPI;
     const bool truncated = n_iter64 > max_iters;
     const uint32_t n_iter = truncated ? max_iters : (uint32_t)n_iter64;
@@ -327,9 +390,7 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
     const uint8_t *rp = m.rowbits + (a0 >> 3) + lane * (EPL / 8u);
     const uint32_t zero_off = m.cols * 4u;
 
-    uint32_t R = m.chunk_ord[c] - 1u;   // ordinal of the row "in progress" (a bogus one before the chunk at first)
-    bool first_pending = true;
-    float carry = 0.0f;
+    ChunkCarry cy{m.chunk_ord[c] - 1u, true, 0.0f};
 
     typename ValRaw<VT>::type nv = ldg_stream_vals<VT>(vp);
     typename ColRaw<VT>::type nc = ldg_stream_cols<VT>(cp);
@@ -343,53 +404,129 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
         cp += EPI * 2u;
         rp += EPI / 8u;
         if (it + 1 < n_iter) { nv = ldg_stream_vals<VT>(vp); nc = ldg_stream_cols<VT>(cp); nr = ldg_stream_rowbits<VT>(rp); }
-        IterState<EPL> o;
-        float carry_out;
-        if (it == 0 || it == last_iter) {
-            // lanes' elements outside [s, e) are neutralised
-            // offsets inside the chunk fit 32 bits (a chunk is far smaller than 2^31 non-zeros)
-            const int32_t ebase = (int32_t)(it * EPI + lane * EPL);
-            const int32_t l32 = rel_s - ebase, h32 = rel_e - ebase;
-            const uint32_t lo = l32 < 0 ? 0u : (l32 > (int32_t)EPL ? EPL : (uint32_t)l32);
-            const uint32_t hi = h32 < 0 ? 0u : (h32 > (int32_t)EPL ? EPL : (uint32_t)h32);
-            csr_iter<true, VT>(cv, cc, cr, xs_bytes, zero_off, lo, hi, carry, carry_out, o);
-        } else {
-            csr_iter<false, VT>(cv, cc, cr, xs_bytes, zero_off, 0u, EPL, carry, carry_out, o);
-        }
-        carry = carry_out;
-
-        const bool passT = (o.fb != 0) && (o.T >= sink.tau);
-        const unsigned pm = __ballot_sync(kFull, passT || (o.cm >= sink.tau));
-        const uint32_t Rtot = __reduce_add_sync(kFull, o.nf);
-        if (pm) {
-            // ordinal of the row in progress when entering this lane = R + rows started in lower lanes
-            uint32_t pre = o.nf;
-#pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                const uint32_t up = __shfl_up_sync(kFull, pre, dlt);
-                if ((int)lane >= dlt) pre += up;
-            }
-            const uint32_t ord_l = R + (pre - o.nf);
-            const bool bogus = first_pending && (lane == (unsigned)(__ffs(o.fm) - 1));
-            sink.emit(passT && !bogus, o.T, ord_l);
-            if (__any_sync(kFull, o.nf >= 2)) {
-                // rows that start AND end inside one lane (length <= EPL - 1)
-#pragma unroll
-                for (int j = 1; j < (int)EPL; j++) {
-                    const uint32_t below = o.fb & ((1u << j) - 1u);
-                    const bool ends_here = ((o.fb >> j) & 1u) && below != 0;
-                    if (EPL > 8 && !__any_sync(kFull, ends_here)) continue;   // warp-uniform skip
-                    sink.emit(ends_here && (o.seg[j - 1] >= sink.tau), o.seg[j - 1], ord_l + __popc(below));
-                }
-            }
-        }
-        if (o.fm) first_pending = false;
-        R += Rtot;
+        csr_consume_iter<VT>(cv, cc, cr, it == 0 || it == last_iter, it, rel_s, rel_e, xs_bytes, zero_off, cy, sink);
     }
     if (!truncated) {
         // the row in progress at the end of the chunk is complete (chunks end on row boundaries)
-        sink.emit(lane == 0 && !first_pending && (carry >= sink.tau), carry, R);
+        sink.emit(lane == 0 && !cy.first_pending && (cy.carry >= sink.tau), cy.carry, cy.R);
     }
+}
+
+// --------------------------------------------------------------------------
+// The same stream staged through shared memory by bulk copies (the north-star's "TMA bulk copies and mbarrier
+// double-buffering"): every warp owns a ring of kTmaStages stages of one iteration each (values | column offsets |
+// row-start bits, three `cp.async.bulk` per stage issued by lane 0, completion counted on the stage's mbarrier), so
+// kTmaStages - 1 iterations are in flight per warp without holding them in registers.  Lanes read their 32 bytes of
+// values (and, with 16-bit values, of column offsets) as two LDS.128 whose halves are swapped for every second group of
+// four lanes, which makes them conflict-free.  Requires chunk loads to start on 128-non-zero boundaries
+// (CsrDevice::start_align = 128: `cp.async.bulk` wants 16-byte aligned sources, also for the row-start bits).
+// --------------------------------------------------------------------------
+constexpr uint32_t kTmaStages = 3;
+
+template <int VT>
+struct TmaStage {
+    static constexpr uint32_t EPL = Epl<VT>::v, EPI = kWarp * EPL;
+    static constexpr uint32_t kValBytes = EPI * (VT != 0 ? 2u : 4u), kColBytes = EPI * 2u, kBitBytes = EPI / 8u;
+    static constexpr uint32_t kBytes = kValBytes + kColBytes + kBitBytes;
+    static constexpr uint32_t kStride = (kBytes + 127u) & ~127u;
+};
+
+struct TmaRing {
+    uint32_t base;     // shared address of this warp's kTmaStages stages
+    uint32_t bar;      // shared address of this warp's kTmaStages mbarriers
+    uint32_t slot;     // stage the next iteration is consumed from
+    uint32_t parity;   // its phase
+};
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{ .reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ U32x4 lds_128(uint32_t addr) {
+    U32x4 r;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "r"(addr));
+    return r;
+}
+// a lane's 32 bytes at base + lane * 32, conflict-free: groups of four lanes alternate which half they fetch first
+__device__ __forceinline__ U32x8 lds_lane32(uint32_t base, unsigned lane) {
+    const uint32_t sw = (lane >> 2) & 1u;
+    const uint32_t a = base + lane * 32u;
+    const U32x4 f = lds_128(a + sw * 16u), g = lds_128(a + (sw ^ 1u) * 16u);
+    U32x8 r;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { r.w[j] = sw ? g.w[j] : f.w[j]; r.w[4 + j] = sw ? f.w[j] : g.w[j]; }
+    return r;
+}
+
+template <int VT, typename Sink>
+__device__ __forceinline__ void csr_process_chunk_tma(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint32_t c,
+                                                      Sink &sink, TmaRing &ring) {
+    using S = TmaStage<VT>;
+    constexpr uint32_t EPL = S::EPL, EPI = S::EPI;
+    const unsigned lane = lane_id();
+    const uint64_t s = m.chunk_start[c], e = m.chunk_start[c + 1];
+    if (s >= e) return;
+    const uint64_t a0 = s & ~127ull;
+    const uint32_t n_iter = (uint32_t)((e - a0 + EPI - 1) / EPI);
+    const int32_t rel_s = (int32_t)(s - a0), rel_e = (int32_t)(e - a0);
+    const uint8_t *gv = reinterpret_cast<const uint8_t *>(m.val) + a0 * (VT != 0 ? 2u : 4u);
+    const uint8_t *gc = reinterpret_cast<const uint8_t *>(m.col16 + a0);
+    const uint8_t *gr = m.rowbits + (a0 >> 3);
+    const uint32_t zero_off = m.cols * 4u;
+    ChunkCarry cy{m.chunk_ord[c] - 1u, true, 0.0f};
+
+    // producer side (lane 0): stage of iteration `it` = (ring.slot + it) mod kTmaStages
+    uint32_t pslot = ring.slot;
+    auto issue = [&](uint32_t it) {
+        const uint32_t dst = ring.base + pslot * S::kStride, bar = ring.bar + pslot * 8u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the lanes' reads of this stage come first
+        mbar_expect_tx(bar, S::kBytes);
+        bulk_g2s(dst, gv + (size_t)it * S::kValBytes, S::kValBytes, bar);
+        bulk_g2s(dst + S::kValBytes, gc + (size_t)it * S::kColBytes, S::kColBytes, bar);
+        bulk_g2s(dst + S::kValBytes + S::kColBytes, gr + (size_t)it * S::kBitBytes, S::kBitBytes, bar);
+        pslot = (pslot + 1u == kTmaStages) ? 0u : pslot + 1u;
+    };
+    if (lane == 0) {
+        const uint32_t pre = n_iter < kTmaStages - 1u ? n_iter : kTmaStages - 1u;
+        for (uint32_t i = 0; i < pre; i++) issue(i);
+    }
+    for (uint32_t it = 0; it < n_iter; it++) {
+        // refill the stage the previous iteration was consumed from (every lane has read it: __syncwarp below)
+        if (lane == 0 && it + kTmaStages - 1u < n_iter) issue(it + kTmaStages - 1u);
+        const uint32_t st = ring.base + ring.slot * S::kStride, bar = ring.bar + ring.slot * 8u;
+        uint32_t tries = 0;
+        while (!mbar_try_wait(bar, ring.parity)) {
+            if (++tries > (1u << 22)) __trap();   // a copy that never lands must not hang the device
+        }
+        typename ValRaw<VT>::type cv = lds_lane32(st, lane);
+        typename ColRaw<VT>::type cc;
+        uint32_t cr;
+        if constexpr (VT != 0) {
+            cc = lds_lane32(st + S::kValBytes, lane);
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(cr) : "r"(st + S::kValBytes + S::kColBytes + lane * 2u));
+        } else {
+            cc = lds_128(st + S::kValBytes + lane * 16u);
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cr) : "r"(st + S::kValBytes + S::kColBytes + lane));
+        }
+        __syncwarp();
+        if (++ring.slot == kTmaStages) { ring.slot = 0; ring.parity ^= 1u; }
+        csr_consume_iter<VT>(cv, cc, cr, it == 0 || it + 1 == n_iter, it, rel_s, rel_e, xs_bytes, zero_off, cy, sink);
+    }
+    sink.emit(lane == 0 && !cy.first_pending && (cy.carry >= sink.tau), cy.carry, cy.R);
 }
 
 // --------------------------------------------------------------------------
@@ -611,13 +748,35 @@ __global__ void __launch_bounds__(kSampleThreads, 4) csr_sample_kernel(CsrDevice
 // counter, reduces them, and keeps rows with score >= tau in a private
 // shared-memory buffer (sorted and cut to k only if it ever fills).
 // --------------------------------------------------------------------------
-template <int CAP, int VT>
+// TMA: the stream arrives through per-warp rings of bulk copies (csr_process_chunk_tma) instead of register loads.
+// Shared memory then holds, behind the query and the candidate buffers, warps x kTmaStages stages (128-byte aligned)
+// and warps x kTmaStages mbarriers: main_tma_extra_smem().
+template <int VT>
+__host__ __device__ constexpr size_t main_tma_extra_smem(uint32_t warps) {
+    return 128u + (size_t)warps * kTmaStages * (TmaStage<VT>::kStride + 8u);
+}
+
+template <int CAP, int VT, bool TMA = false>
 __global__ void __launch_bounds__(VT != 0 ? kMainThreads16 : (CAP == 256 ? kMainThreadsWide : kMainThreads), 2)
 csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uint64_t *pool, uint32_t k,
                      int tie_higher, uint32_t seq, uint32_t tau_wait_us, uint64_t *stamp) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float *xs = reinterpret_cast<float *>(smem_raw);
     uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (((m.cols + 1u) * 4u + 15u) & ~15u));
+    TmaRing ring{0u, 0u, 0u, 0u};
+    if constexpr (TMA) {
+        const uint32_t warps = blockDim.x / kWarp, w = threadIdx.x / kWarp;
+        const uint32_t after_bufs = (uint32_t)__cvta_generic_to_shared(bufs + (size_t)warps * CAP);
+        const uint32_t ring0 = (after_bufs + 127u) & ~127u;
+        ring.base = ring0 + w * kTmaStages * TmaStage<VT>::kStride;
+        ring.bar = ring0 + warps * kTmaStages * TmaStage<VT>::kStride + w * kTmaStages * 8u;
+        if (lane_id() == 0) {
+            for (uint32_t i = 0; i < kTmaStages; i++) mbar_init(ring.bar + i * 8u, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
     pdl_trigger();   // the select kernel's CTA may be set up while this grid drains
     if (seq == 0) {
         for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<VT>(x[i]) : 0.0f;
@@ -656,7 +815,8 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
         c = __shfl_sync(kFull, c, 0);
         if (c >= m.n_chunks) break;
         sink.tau = fmaxf(sink.tau, tau_from_key(ld_relaxed_u32(&st->tau_key)));
-        csr_process_chunk<VT>(m, smem_raw, c, 0xFFFFFFFFu, sink);
+        if constexpr (TMA) csr_process_chunk_tma<VT>(m, smem_raw, c, sink, ring);
+        else csr_process_chunk<VT>(m, smem_raw, c, 0xFFFFFFFFu, sink);
     }
 
     // hand the survivors to the global pool (filtered by the freshest bound)
