@@ -117,6 +117,21 @@ class ClockSampler:
     def mark(self, label):
         self.label = label
 
+    def sample_now(self, label):
+        """One sample taken by the calling thread (the polling thread may not get a turn inside a 4 ms region)."""
+        if self.nv is None:
+            return
+        try:
+            nv = self.nv
+            mhz = nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)
+            try:
+                why = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+            except Exception:
+                why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+            self.rows.append((label, float(mhz), int(why)))
+        except Exception as e:
+            self.err = repr(e)
+
     def stop(self):
         if self.nv is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["NVML unavailable: " + str(self.err)]}
@@ -320,6 +335,16 @@ def ours(args):
 
     line = float_workload(tks, torch, dist, wl_key, args, world, rank, local, tstream, peak_gbs, peak_src,
                           steps=args.steps, warmup=args.warmup, full=True)
+    if world == 1 and wl_key == "cfg2" and not args.no_sub:
+        # the default single-GPU line also carries BASELINE configs 3 and 5 (reduced legs: value, e2e, roofline)
+        wl3 = WORKLOADS["cfg3"]
+        sub3 = fixed_workload(args, tks, wl3, wl3["rows"], make_queries(wl3["cols"], 3 + min(args.steps, 10)), peak_gbs, peak_src,
+                              min(args.steps, 10), 3, False)
+        torch.cuda.set_stream(tstream)
+        wl5 = WORKLOADS["cfg5"]
+        sub5 = batched_workload(tks, torch, dist, args, wl5, wl5["rows"], peak_gbs, peak_src, world, rank, local, stream,
+                                steps=min(args.steps, 5), warmup=3, full=False)
+        line["cfg3"], line["cfg5"] = sub3, sub5
     if world > 1 and wl_key == "cfg2" and not args.no_cfg4:
         # BASELINE config 4 rides along in every multi-GPU line of the default run: 200M x 1024 uniform-40, rows / N
         sub = float_workload(tks, torch, dist, "cfg4", args, world, rank, local, tstream, peak_gbs, peak_src,
@@ -440,6 +465,8 @@ def float_workload(tks, torch, dist, wl_key, args, world, rank, local, tstream, 
         step(warmup + i)
     sharded.wait(stream)                             # the last query's select (+ exchange + merge) is inside the region
     e1.record()
+    if rank == 0:
+        sampler.sample_now("timed")                  # the host runs ahead: the device is still inside the timed steps here
     torch.cuda.synchronize()
     sampler.mark("after")
     if world > 1:
@@ -958,7 +985,7 @@ def lfr_overflow_packets(x, num_rows, partitions, B, LFR):
             "mean_position_of_first_event_in_its_partition": float(np.mean(hit)) if hit else None}
 
 
-def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
+def fixed_workload(args, tks, wl, rows_total, queries, peak_gbs, peak_src, steps, warmup, full):
     """cfg3: the cfg2 matrix quantised to 20-bit fixed point and packed into BS-CSR packets by the host
     packet builder (the reference does this on the host too), 32 partitions x LFR 4 x local K 8."""
     import torch
@@ -990,30 +1017,30 @@ def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
             eng.reset_device(dq[i].data_ptr(), stream)
             eng.run_async(K, stream)
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
+    for i in range(steps):
+        step(warmup + i)
     e1.record()
     torch.cuda.synchronize()
-    ms_step = e0.elapsed_time(e1) / args.steps
+    ms_step = e0.elapsed_time(e1) / steps
     clocks = sampler.stop()
     v_last, i_last = eng.read_result()
 
     e2e_ms, main_ms = [], []
-    for i in range(args.warmup + args.steps):
+    for i in range(warmup + steps):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         eng.reset(q32[i])
         eng.run_timed(K)
         v_e, i_e = eng.read_result()
         dt = (time.perf_counter() - t0) * 1e3
-        if i >= args.warmup:
+        if i >= warmup:
             e2e_ms.append(dt)
     assert np.array_equal(i_e, i_last) and np.array_equal(v_e, v_last), "e2e and resident results differ"
     e2e_blocking_ms = sum(e2e_ms) / len(e2e_ms)
@@ -1028,80 +1055,85 @@ def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
                 last = eng.fetch(prev)
             prev = t
         return eng.fetch(prev)
-    host_loop(0, args.warmup)
+    host_loop(0, warmup)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    v_p, i_p = host_loop(args.warmup, args.warmup + args.steps)
-    e2e_pipe_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    v_p, i_p = host_loop(warmup, warmup + steps)
+    e2e_pipe_ms = (time.perf_counter() - t0) * 1e3 / steps
     assert np.array_equal(i_p, i_last) and np.array_equal(v_p, v_last), "pipelined e2e and resident results differ"
     e2e_ms = [e2e_pipe_ms]
     # roofline leg: the dominant kernel bracketed alone (profile_kernels adds two events and a statistics read-back
     # per run, so it is switched on only here)
     eng.set_profile_kernels(True)
-    for i in range(args.warmup + args.steps):
+    for i in range(warmup + steps):
         eng.reset(q32[i])
         eng.run_timed(K)
-        if i >= args.warmup:
+        if i >= warmup:
             main_ms.append(eng.stats().last_main_kernel_ms)
-    # top-K recall of the approximate design (20-bit fixed point, 32 partitions x local K=8) against the exact fp32
-    # engine on the same matrix and queries, with the reference's metrics (plot_errors.py)
-    # ... for the reference's semantics (bit-exact, incl. its row-counter drift) and for the engine's
-    # drift-free mode (same kernel, same speed; true row indices)
-    t0 = time.perf_counter()
-    eng_df = tks.SpMVFixed(x, idx, val32, rows_total, cols, k=K, fixed_width=W, partitions=P, local_k=Kp,
-                           limited_finished_rows=LFR, drift_free=True)
-    host_pack_s = time.perf_counter() - t0
-    recalls, recalls_df, df_ms = [], [], []
-    for i in range(args.warmup, args.warmup + min(args.steps, 5)):
-        src.reset(queries[i])
-        src()
-        ev, ei, _ = src.read_result()
-        eng.reset(q32[i])
-        eng.run_timed(K)
-        av, ai = eng.read_result()
-        recalls.append(tks.accuracy.report(ei, ev, ai, av.astype(np.float64) / 2.0 ** 31))
-        eng_df.reset(q32[i])
-        km, _ = eng_df.run_timed(K)
-        dv, di = eng_df.read_result()
-        recalls_df.append(tks.accuracy.report(ei, ev, di, dv.astype(np.float64) / 2.0 ** 31))
-        df_ms.append(km)
-    eng_df.close()
-    mean_of = lambda rs: {k2: float(np.mean([r[k2] for r in rs if k2 in r])) for k2 in rs[0]} if rs else None
-    overflow_gamma = lfr_overflow_packets(x, rows_total, P, tks.capi.bscsr_packet_size(W), LFR)
-    # The published accuracy of the 20-bit design (errors_2021_03_07.png: 96.7-98.4 % precision at N = 10^7 for K = 8..100)
-    # is the reference's "uniform + GloVe" plot (plot_errors.py:38,253-256: KIND "uniform" has its axis floor at 0.96,
-    # KIND "gamma" at 0.80): uniform row degrees (10..30 for 20 nnz per row) never put more than LFR = 4 row ends into
-    # a 15-entry packet, so the row counter never drifts.  The same engine on a uniform-20 matrix of the same size:
-    uniform = None
-    if not args.no_uniform:
-        src.generate_synthetic(rows_total, cols, wl["deg"], "uniform", seed=SEED)
-        uptr, uidx, uval = src.download_csr()
-        ux = np.repeat(np.arange(rows_total, dtype=np.uint32), np.diff(uptr.astype(np.int64)))
-        uval32 = tks.capi.fixed32_from_double_np(uval.astype(np.float64))
-        eng_u = tks.SpMVFixed(ux, uidx, uval32, rows_total, cols, k=K, fixed_width=W, partitions=P, local_k=Kp,
-                              limited_finished_rows=LFR, device_pack=True)
-        ur, ums = [], []
-        for i in range(warmup_steps(args), warmup_steps(args) + min(args.steps, 5)):
+    recall = None
+    host_pack_s = None
+    if full:
+        # top-K recall of the approximate design (20-bit fixed point, 32 partitions x local K=8) against the exact fp32
+        # engine on the same matrix and queries, with the reference's metrics (plot_errors.py)
+        # ... for the reference's semantics (bit-exact, incl. its row-counter drift) and for the engine's
+        # drift-free mode (same kernel, same speed; true row indices)
+        t0 = time.perf_counter()
+        eng_df = tks.SpMVFixed(x, idx, val32, rows_total, cols, k=K, fixed_width=W, partitions=P, local_k=Kp,
+                               limited_finished_rows=LFR, drift_free=True)
+        host_pack_s = time.perf_counter() - t0
+        recalls, recalls_df, df_ms = [], [], []
+        for i in range(warmup, warmup + min(steps, 5)):
             src.reset(queries[i])
             src()
             ev, ei, _ = src.read_result()
-            eng_u.reset(q32[i])
-            km, _ = eng_u.run_timed(K)
-            av, ai = eng_u.read_result()
-            ur.append(tks.accuracy.report(ei, ev, ai, av.astype(np.float64) / 2.0 ** 31))
-            ums.append(km)
-        uniform = {"matrix": f"synthetic {rows_total} x {cols}, uniform ~{wl['deg']} nnz/row, same engine knobs",
-                   "reference_semantics": mean_of(ur), "step_ms": float(np.mean(ums[1:])) if len(ums) > 1 else None,
-                   "packets_with_more_than_LFR_row_segments": lfr_overflow_packets(ux, rows_total, P, tks.capi.bscsr_packet_size(W), LFR),
-                   "published": "FPGA 20-bit, N = 10^7: 96.7-98.4 % precision for K = 8..100 (uniform + GloVe matrices)"}
-        eng_u.close()
-    src.close()
-    recall = {"reference_semantics": mean_of(recalls), "drift_free_mode": mean_of(recalls_df),
-              "packets_with_more_than_LFR_row_segments": overflow_gamma, "uniform_rows": uniform,
-              "drift_free_step_ms": float(np.mean(df_ms[1:])) if len(df_ms) > 1 else None,
-              "note": "precision / Kendall tau / NDCG of plot_errors.py against the exact fp32 engine on the same matrix and "
-                      "queries; gamma-distributed rows put more than LFR row segments into ~6e-5 of the packets, after which "
-                      "the reference's row counter (and therefore every later row index of the partition) is off by one per event"}
+            eng.reset(q32[i])
+            eng.run_timed(K)
+            av, ai = eng.read_result()
+            recalls.append(tks.accuracy.report(ei, ev, ai, av.astype(np.float64) / 2.0 ** 31))
+            eng_df.reset(q32[i])
+            km, _ = eng_df.run_timed(K)
+            dv, di = eng_df.read_result()
+            recalls_df.append(tks.accuracy.report(ei, ev, di, dv.astype(np.float64) / 2.0 ** 31))
+            df_ms.append(km)
+        eng_df.close()
+        mean_of = lambda rs: {k2: float(np.mean([r[k2] for r in rs if k2 in r])) for k2 in rs[0]} if rs else None
+        overflow_gamma = lfr_overflow_packets(x, rows_total, P, tks.capi.bscsr_packet_size(W), LFR)
+        # The published accuracy of the 20-bit design (errors_2021_03_07.png: 96.7-98.4 % precision at N = 10^7 for K = 8..100)
+        # is the reference's "uniform + GloVe" plot (plot_errors.py:38,253-256: KIND "uniform" has its axis floor at 0.96,
+        # KIND "gamma" at 0.80): uniform row degrees (10..30 for 20 nnz per row) never put more than LFR = 4 row ends into
+        # a 15-entry packet, so the row counter never drifts.  The same engine on a uniform-20 matrix of the same size:
+        uniform = None
+        if not args.no_uniform:
+            src.generate_synthetic(rows_total, cols, wl["deg"], "uniform", seed=SEED)
+            uptr, uidx, uval = src.download_csr()
+            ux = np.repeat(np.arange(rows_total, dtype=np.uint32), np.diff(uptr.astype(np.int64)))
+            uval32 = tks.capi.fixed32_from_double_np(uval.astype(np.float64))
+            eng_u = tks.SpMVFixed(ux, uidx, uval32, rows_total, cols, k=K, fixed_width=W, partitions=P, local_k=Kp,
+                                  limited_finished_rows=LFR, device_pack=True)
+            ur, ums = [], []
+            for i in range(warmup, warmup + min(steps, 5)):
+                src.reset(queries[i])
+                src()
+                ev, ei, _ = src.read_result()
+                eng_u.reset(q32[i])
+                km, _ = eng_u.run_timed(K)
+                av, ai = eng_u.read_result()
+                ur.append(tks.accuracy.report(ei, ev, ai, av.astype(np.float64) / 2.0 ** 31))
+                ums.append(km)
+            uniform = {"matrix": f"synthetic {rows_total} x {cols}, uniform ~{wl['deg']} nnz/row, same engine knobs",
+                       "reference_semantics": mean_of(ur), "step_ms": float(np.mean(ums[1:])) if len(ums) > 1 else None,
+                       "packets_with_more_than_LFR_row_segments": lfr_overflow_packets(ux, rows_total, P, tks.capi.bscsr_packet_size(W), LFR),
+                       "published": "FPGA 20-bit, N = 10^7: 96.7-98.4 % precision for K = 8..100 (uniform + GloVe matrices)"}
+            eng_u.close()
+        src.close()
+        recall = {"reference_semantics": mean_of(recalls), "drift_free_mode": mean_of(recalls_df),
+                  "packets_with_more_than_LFR_row_segments": overflow_gamma, "uniform_rows": uniform,
+                  "drift_free_step_ms": float(np.mean(df_ms[1:])) if len(df_ms) > 1 else None,
+                  "note": "precision / Kendall tau / NDCG of plot_errors.py against the exact fp32 engine on the same matrix and "
+                          "queries; gamma-distributed rows put more than LFR row segments into ~6e-5 of the packets, after which "
+                          "the reference's row counter (and therefore every later row index of the partition) is off by one per event"}
+    else:
+        src.close()
     e2e_ms_step = sum(e2e_ms) / len(e2e_ms)
     main = sum(main_ms) / len(main_ms)
     st = eng.stats()
@@ -1113,7 +1145,7 @@ def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
             "algorithmic_bytes_per_launch": alg, "main_kernel_ms": main,
             "step_frac": alg / (ms_step * 1e-3) / 1e9 / peak_gbs}
     cpu = None
-    if not args.no_cpu:
+    if full and not args.no_cpu:
         sys.path.insert(0, str(ROOT / "oracle"))
         import oracle
         sample_rows = min(rows_total, (args.ref_rows or 2_000_000) // 4)
@@ -1124,7 +1156,7 @@ def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
         times = []
         for qi in range(min(3, len(q32))):
             t0 = time.perf_counter()
-            iw, vw = oracle.bscsr_kernel(packed, q32[args.warmup + qi], Kp, LFR)
+            iw, vw = oracle.bscsr_kernel(packed, q32[warmup + qi], Kp, LFR)
             oracle.read_result(iw, vw, packed["first_row"], packed["B"])
             times.append(time.perf_counter() - t0)
         sec = sum(times) / len(times)
@@ -1132,12 +1164,12 @@ def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
                "sample": f"first {sample_rows} rows ({e} nnz), {len(times)} queries, oracle's sequential transcription of the "
                          f"HLS kernel (the reference has no CPU build of this path); packing took {tp:.1f} s"}
     line = {"metric": "topk_spmv_nnz_per_s", "value": nnz / (ms_step * 1e-3), "unit": "nnz/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 (20-bit fixed point)", "data": "synthetic",
             "config": {"workload": wl["name"], "rows": rows_total, "cols": cols, "nnz": nnz, "k": K,
                        "fixed_width": W, "partitions": P, "local_k": Kp, "limited_finished_rows": LFR,
                        "packets": int(st.packets), "l2": "inputs larger than L2 (%.2f GB of packets), no flush" % (st.packets * 64 / 1e9),
-                       "device_pack_upload_s": round(pack_s, 2), "host_pack_upload_s": round(host_pack_s, 2),
+                       "device_pack_upload_s": round(pack_s, 2), "host_pack_upload_s": round(host_pack_s, 2) if host_pack_s is not None else None,
                            "pack": "BS-CSR packets and chunk tables built on the GPU (tks_upload_coo_fixed, H2D of the COO included); "
                                    "host_pack_upload_s is the host packer + upload of the drift-free engine beside it"},
             "roofline": roof, "cpu_baseline": cpu,
@@ -1146,11 +1178,19 @@ def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
                     "api": "SpMVFixed.submit_host(host vec) -> ticket ... fetch(ticket) (host merge of P x K x LFR candidates), two steps in flight",
                     "blocking": {"value": nnz / (e2e_blocking_ms * 1e-3), "ms_per_step": e2e_blocking_ms,
                                  "api": "SpMVFixed.reset(host vec) -> operator() -> read_result, one query at a time"}},
-            "gpu_launches": args.steps * 3, "results_returned": int(i_last.size),
+            "gpu_launches": steps * 3, "results_returned": int(i_last.size),
             "logged_candidates_last_step": int(st.logged_candidates), "recall_vs_exact_fp32": recall,
             "clocks": clocks}
-    print(json.dumps(line), flush=True)
+    line["parity"] = ("the stream-order, pipelined and host-fed paths return identical lists (asserted above); bit-exactness against the "
+                      "oracle at this size: tests/test_gpu_full_size.py")
     eng.close()
+    torch.cuda.empty_cache()
+    return line
+
+
+
+def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
+    print(json.dumps(fixed_workload(args, tks, wl, rows_total, queries, peak_gbs, peak_src, args.steps, args.warmup, True)), flush=True)
 
 
 def main():
@@ -1163,6 +1203,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override the workload's total rows (debug)")
     ap.add_argument("--ref-rows", type=int, default=0, help="cap on the rows the CPU legs run over (0 = the whole configuration)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="N = 1: skip the cfg3 / cfg5 sub-records of the default line")
     ap.add_argument("--no-uniform", action="store_true", help="cfg3: skip the uniform-rows accuracy leg")
     ap.add_argument("--no-cfg4", action="store_true", help="N > 1: skip the BASELINE config 4 sub-record")
     ap.add_argument("--batch-fma", action="store_true", help="cfg5: fused multiply-add arithmetic")
