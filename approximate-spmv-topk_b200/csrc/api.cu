@@ -67,6 +67,8 @@ size_t main_smem_bytes(uint32_t cols, int variant, int threads) {
 
 // TKS_TMA=1: the k <= 128 main kernel streams through per-warp rings of bulk copies (cp.async.bulk + mbarrier) instead
 // of register loads; chunk loads then start on 128-non-zero boundaries (in the sample kernel too)
+// TKS_COL12=0: stream 16-bit column offsets even when 12 bits would do (A/B switch)
+bool col12_enabled() { static const bool on = !(std::getenv("TKS_COL12") && std::atoi(std::getenv("TKS_COL12")) == 0); return on; }
 bool tma_enabled() { static const bool on = std::getenv("TKS_TMA") && std::atoi(std::getenv("TKS_TMA")) != 0; return on; }
 int tma_threads(int vt) { static const int t = (int)env_u32("TKS_TMA_THREADS", 0u) / 32 * 32; return t >= 64 ? t : (vt != 0 ? 384 : 448); }
 
@@ -106,6 +108,10 @@ cudaError_t prep_main_t(Handle *h, int variant) {
         if (pct >= 0) {
             e = cudaFuncSetAttribute(csr_topk_main_kernel<CAP, VT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             if (e != cudaSuccess) return e;
+            if constexpr (CAP == 256) {   // the instantiation that streams 12-bit column offsets
+                e = cudaFuncSetAttribute(csr_topk_main_kernel<256, VT, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+                if (e != cudaSuccess) return e;
+            }
         }
     }
     int per_sm = 0;
@@ -113,6 +119,11 @@ cudaError_t prep_main_t(Handle *h, int variant) {
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     h->main_grid[variant] = per_sm * h->num_sms;
+    if constexpr (CAP == 256) {
+        // the instantiation that streams 12-bit column offsets: same geometry, same attributes
+        e = cudaFuncSetAttribute(csr_topk_main_kernel<256, VT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_topk_main_kernel<CAP, VT>, pthreads,
                                                       main_smem_bytes(h->cfg.max_cols, variant, pthreads));
     if (e != cudaSuccess) return e;
@@ -167,6 +178,14 @@ void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, Run
         }
         return;
     }
+    if (CAP == 256 && h->d_col12) {
+        switch (value_type(h)) {
+            case TKS_VALUE_FP16: launch_pdl(csr_topk_main_kernel<256, 1, false, true>, grid, block, smem, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
+            case TKS_VALUE_BF16: launch_pdl(csr_topk_main_kernel<256, 2, false, true>, grid, block, smem, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
+            default: launch_pdl(csr_topk_main_kernel<256, 0, false, true>, grid, block, smem, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
+        }
+        return;
+    }
     switch (value_type(h)) {
         case TKS_VALUE_FP16: launch_pdl(csr_topk_main_kernel<CAP, 1>, grid, block, smem, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
         case TKS_VALUE_BF16: launch_pdl(csr_topk_main_kernel<CAP, 2>, grid, block, smem, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
@@ -185,7 +204,7 @@ void launch_main_variant(Handle *h, int variant, const CsrDevice &m, const float
 }
 
 CsrDevice csr_device(const Handle *h) {
-    return CsrDevice{h->d_val, h->d_col16, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start,
+    return CsrDevice{h->d_val, h->d_col16, h->d_col12, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start,
                      h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols, (uint32_t)h->row_offset,
                      (uint32_t)value_type(h), tma_enabled() ? 128u : (value_type(h) != 0 ? 16u : 8u)};
 }
@@ -254,6 +273,7 @@ void free_matrix(Handle *h) {
     drop_run_graph(h);
     cudaFree(h->d_val); h->d_val = nullptr;
     cudaFree(h->d_col16); h->d_col16 = nullptr;
+    cudaFree(h->d_col12); h->d_col12 = nullptr;
     cudaFree(h->d_rowbits); h->d_rowbits = nullptr;
     cudaFree(h->d_ptr64); h->d_ptr64 = nullptr;
     cudaFree(h->d_chunk_start); h->d_chunk_start = nullptr;
@@ -310,6 +330,13 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
     TKS_CUDA(h, cudaMalloc(&d_ord, (rows + 1) * sizeof(uint64_t)));
 
     if (nnz > 0) csr_copy_cols_kernel<P><<<h->num_sms * 8, 256, 0, s>>>(d_idx, nnz, cols, h->d_col16, d_err);
+    if (cols <= 1024 && col12_enabled() && !tma_enabled()) {
+        // columns <= 1023: column * 4 fits 12 bits -- the stream the k <= 128 single-query kernels read (1.5 B / non-zero)
+        const size_t c12_bytes = (nnz + 7) / 8 * 12 + pad;
+        TKS_CUDA(h, cudaMalloc(&h->d_col12, c12_bytes));
+        TKS_CUDA(h, cudaMemsetAsync(h->d_col12, 0, c12_bytes, s));
+        if (nnz > 0) csr_pack_cols12_kernel<<<h->num_sms * 8, 256, 0, s>>>(h->d_col16, nnz, h->d_col12);
+    }
     if (rows > 0) {
         csr_mark_rows_kernel<P><<<(uint32_t)((rows + 255) / 256), 256, 0, s>>>(d_ptr, rows, nnz, h->d_rowbits, d_flag, d_err);
         int rc = device_scan_u32(h, d_flag, rows, d_ord);
@@ -338,7 +365,9 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
                        (herr & kErrPtrOrder) ? " row_ptr not monotone, out of range, or not running from 0 to nnz;" : "");
     }
     h->rows = rows; h->cols = cols; h->nnz = nnz;
-    h->device_bytes = nnz * (half_mode(h) ? 4ull : 6ull) + (nnz + 7) / 8 + (nch + 1) * 8ull + nch * 4ull + (has_empty ? n_nonempty * 4ull : 0ull);
+    // bytes one k <= 128 query streams: values + column offsets (2 bytes, or 1.5 when packed to 12 bits) + row-start bits + tables
+    h->device_bytes = nnz * (half_mode(h) ? 2ull : 4ull) + (h->d_col12 ? nnz * 3ull / 2ull : nnz * 2ull) + (nnz + 7) / 8 +
+                      (nch + 1) * 8ull + nch * 4ull + (has_empty ? n_nonempty * 4ull : 0ull);
     h->have_matrix = true;
     h->have_result = false;
     h->stats.rows = rows; h->stats.cols = cols; h->stats.nnz = nnz; h->stats.packets = 0;
@@ -354,6 +383,9 @@ int check_float_upload(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz, ui
     (void)nnz;
     return TKS_OK;
 }
+
+// the k <= 128 kernels stream the 12-bit column offsets when the matrix has them
+bool use_col12(const Handle *h, uint32_t k) { return h->d_col12 != nullptr && k <= 128; }
 
 // The sample kernel of one query: one warp per resident warp slot of the main kernel's grid; large shards get more
 // warps (up to the key buffer's capacity) so that the ~1 % sample stays a few iterations deep instead of a long
@@ -374,6 +406,14 @@ void launch_sample(Handle *h, const CsrDevice &m, const float *x, RunState *st, 
     uint64_t si = (h->nnz / 100u + (uint64_t)n_sample * epi - 1) / ((uint64_t)n_sample * epi);
     const uint32_t max_si = h->chunk_nnz / epi;
     const uint32_t sample_iters = (uint32_t)(si < 2 ? 2 : (si > max_si ? (max_si < 2 ? 2 : max_si) : si));
+    if (use_col12(h, k)) {
+        switch (value_type(h)) {
+            case TKS_VALUE_FP16: csr_sample_kernel<1, true><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
+            case TKS_VALUE_BF16: csr_sample_kernel<2, true><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
+            default: csr_sample_kernel<0, true><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
+        }
+        return;
+    }
     switch (value_type(h)) {
         case TKS_VALUE_FP16: csr_sample_kernel<1><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
         case TKS_VALUE_BF16: csr_sample_kernel<2><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;

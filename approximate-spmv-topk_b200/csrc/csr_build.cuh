@@ -47,6 +47,31 @@ __global__ void csr_copy_cols_kernel(const uint32_t *__restrict__ idx, uint64_t 
     if (bad) atomicOr(err, kErrColRange);
 }
 
+// col12: the column offsets (column * 4 <= 4092) of 8 consecutive non-zeros packed into three 32-bit words, element j at
+// bits [12j, 12j + 12) -- one thread per group of 8; the tail group is padded with zeros
+__global__ void csr_pack_cols12_kernel(const uint16_t *__restrict__ col16, uint64_t nnz, uint32_t *__restrict__ col12) {
+    const uint64_t ngroups = (nnz + 7) / 8;
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; g < ngroups; g += stride) {
+        uint64_t lo = 0, hi = 0;   // 96 bits
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint64_t i = g * 8 + j;
+            const uint64_t c = (i < nnz) ? (uint64_t)(col16[i] & 0xFFFu) : 0ull;
+            const int bit = 12 * j;
+            if (bit >= 64) hi |= c << (bit - 64);
+            else {
+                lo |= c << bit;
+                if (bit + 12 > 64) hi |= c >> (64 - bit);
+            }
+        }
+        col12[g * 3 + 0] = (uint32_t)lo;
+        col12[g * 3 + 1] = (uint32_t)(lo >> 32);
+        col12[g * 3 + 2] = (uint32_t)hi;
+    }
+}
+
 // One thread per row: tag the row's first non-zero; count non-empty rows.
 template <typename P>
 __global__ void csr_mark_rows_kernel(const P *__restrict__ ptr, uint64_t rows, uint64_t nnz,

@@ -47,6 +47,8 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 struct CsrDevice {
     const void *val;               // fp32 [nnz], or IEEE half / bfloat16 [nnz] when the kernels are instantiated with VT = 1 / 2
     const uint16_t *col16;         // column * 4
+    const uint32_t *col12;         // the same offsets packed to 12 bits each (cols <= 1024 only, else nullptr): what the
+                                   // single-query kernels stream when they are instantiated with C12
     const uint8_t *rowbits;        // one row-start bit per non-zero
     const uint64_t *chunk_start;   // n_chunks + 1 entries
     const uint32_t *chunk_ord;     // n_chunks entries
@@ -162,16 +164,55 @@ struct IterState {
     unsigned fm;   // ballot: lanes with >= 1 row start
 };
 
+struct U32x3 { uint32_t w[3]; };
+struct U32x6 { uint32_t w[6]; };
 template <int VT> struct ValRaw { using type = U32x8; };   // 8 fp32 words or 16 halves
-template <int VT> struct ColRaw { using type = U32x8; };   // 16 x u16
-template <> struct ColRaw<0> { using type = U32x4; };      //  8 x u16
+// column offsets of one lane: 16-bit each (8 -> 4 words, 16 -> 8 words) or packed to 12 bits (C12: 3 / 6 words).  Columns
+// are at most 1023 whenever the matrix obeys the reference's MAX_COLS = 1024 (types.hpp:55), so column * 4 fits 12 bits
+// and the stream shrinks from 6.125 to 5.625 bytes per non-zero (4.125 -> 3.625 with 16-bit values).
+template <int VT, bool C12> struct ColRaw { using type = U32x8; };            // 16 x u16
+template <> struct ColRaw<0, false> { using type = U32x4; };                  //  8 x u16
+template <> struct ColRaw<0, true> { using type = U32x3; };                   //  8 x 12 bits
+template <> struct ColRaw<1, true> { using type = U32x6; };                   // 16 x 12 bits
+template <> struct ColRaw<2, true> { using type = U32x6; };
 
 template <int VT>
 __device__ __forceinline__ typename ValRaw<VT>::type ldg_stream_vals(const void *p) { return ldg_stream_256(p); }
-template <int VT>
-__device__ __forceinline__ typename ColRaw<VT>::type ldg_stream_cols(const void *p) {
-    if constexpr (VT != 0) return ldg_stream_256(p);
-    else return ldg_stream_128(p);
+__device__ __forceinline__ uint32_t ldg_stream_32(const void *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+template <int VT, bool C12>
+__device__ __forceinline__ typename ColRaw<VT, C12>::type ldg_stream_cols(const void *p) {
+    if constexpr (C12 && VT != 0) {
+        U32x6 r;   // 24 bytes per lane, 8-byte aligned
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r.w[2 * i]), "=r"(r.w[2 * i + 1])
+                         : "l"(reinterpret_cast<const uint8_t *>(p) + 8 * i));
+        return r;
+    } else if constexpr (C12) {
+        U32x3 r;   // 12 bytes per lane, 4-byte aligned
+#pragma unroll
+        for (int i = 0; i < 3; i++) r.w[i] = ldg_stream_32(reinterpret_cast<const uint8_t *>(p) + 4 * i);
+        return r;
+    } else if constexpr (VT != 0) {
+        return ldg_stream_256(p);
+    } else {
+        return ldg_stream_128(p);
+    }
+}
+// column * 4 of element j of the lane
+template <bool C12, typename CR>
+__device__ __forceinline__ uint32_t col_off_at(const CR &craw, int j) {
+    if constexpr (C12) {
+        const int bit = 12 * j, wd = bit >> 5, sh = bit & 31;
+        if (sh + 12 <= 32) return (sh == 20) ? (craw.w[wd] >> 20) : ((craw.w[wd] >> sh) & 0xFFFu);
+        return __funnelshift_r(craw.w[wd], craw.w[wd + 1], sh) & 0xFFFu;
+    } else {
+        return (j & 1) ? (craw.w[j >> 1] >> 16) : (craw.w[j >> 1] & 0xFFFFu);
+    }
 }
 template <int VT>
 __device__ __forceinline__ uint32_t ldg_stream_rowbits(const void *p) {
@@ -184,8 +225,8 @@ __device__ __forceinline__ uint32_t ldg_stream_rowbits(const void *p) {
     }
 }
 
-template <bool MASKED, int VT>
-__device__ __forceinline__ void csr_iter(const typename ValRaw<VT>::type &vraw, const typename ColRaw<VT>::type &craw,
+template <bool MASKED, int VT, bool C12>
+__device__ __forceinline__ void csr_iter(const typename ValRaw<VT>::type &vraw, const typename ColRaw<VT, C12>::type &craw,
                                          uint32_t rbits, const uint8_t *__restrict__ xs_bytes, uint32_t zero_off,
                                          uint32_t lo, uint32_t hi, float carry_in, float &carry_out,
                                          IterState<Epl<VT>::v> &o) {
@@ -197,7 +238,7 @@ __device__ __forceinline__ void csr_iter(const typename ValRaw<VT>::type &vraw, 
     const uint32_t fb = MASKED ? (rbits & inmask) : rbits;
 #pragma unroll
     for (int j = 0; j < EPL; j++) {
-        uint32_t c = (j & 1) ? (craw.w[j >> 1] >> 16) : (craw.w[j >> 1] & 0xFFFFu);   // column * 4
+        uint32_t c = col_off_at<C12>(craw, j);   // column * 4
         float v;
         if constexpr (VT == 1) {
             const float2 v2 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.w[j >> 1]));
@@ -317,8 +358,8 @@ struct ChunkCarry {
 
 // One warp iteration's loaded words -> products, segmented sums, candidates.  `edge`: the iteration holds elements
 // outside [rel_s, rel_e) (first / last iteration of the chunk), which are neutralised.
-template <int VT, typename Sink>
-__device__ __forceinline__ void csr_consume_iter(const typename ValRaw<VT>::type &cv, const typename ColRaw<VT>::type &cc,
+template <int VT, bool C12, typename Sink>
+__device__ __forceinline__ void csr_consume_iter(const typename ValRaw<VT>::type &cv, const typename ColRaw<VT, C12>::type &cc,
                                                  uint32_t cr, bool edge, uint32_t it, int32_t rel_s, int32_t rel_e,
                                                  const uint8_t *__restrict__ xs_bytes, uint32_t zero_off, ChunkCarry &cy,
                                                  Sink &sink) {
@@ -332,9 +373,9 @@ __device__ __forceinline__ void csr_consume_iter(const typename ValRaw<VT>::type
         const int32_t l32 = rel_s - ebase, h32 = rel_e - ebase;
         const uint32_t lo = l32 < 0 ? 0u : (l32 > (int32_t)EPL ? EPL : (uint32_t)l32);
         const uint32_t hi = h32 < 0 ? 0u : (h32 > (int32_t)EPL ? EPL : (uint32_t)h32);
-        csr_iter<true, VT>(cv, cc, cr, xs_bytes, zero_off, lo, hi, cy.carry, carry_out, o);
+        csr_iter<true, VT, C12>(cv, cc, cr, xs_bytes, zero_off, lo, hi, cy.carry, carry_out, o);
     } else {
-        csr_iter<false, VT>(cv, cc, cr, xs_bytes, zero_off, 0u, EPL, cy.carry, carry_out, o);
+        csr_iter<false, VT, C12>(cv, cc, cr, xs_bytes, zero_off, 0u, EPL, cy.carry, carry_out, o);
     }
     cy.carry = carry_out;
 
@@ -368,7 +409,7 @@ __device__ __forceinline__ void csr_consume_iter(const typename ValRaw<VT>::type
 }
 
 // Stream one chunk (or its first max_iters iterations) through `sink`.
-template <int VT, typename Sink>
+template <int VT, bool C12, typename Sink>
 __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint32_t c,
                                                   uint32_t max_iters, Sink &sink) {
     constexpr uint32_t EPL = Epl<VT>::v, EPI = kWarp * EPL;
@@ -386,25 +427,36 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
     const int32_t rel_s = (int32_t)(s - a0), rel_e = (int32_t)(e - a0);
     constexpr uint32_t kValBytes = VT != 0 ? 2u : 4u;
     const uint8_t *vp = reinterpret_cast<const uint8_t *>(m.val) + a0 * kValBytes + lane * (EPL * kValBytes);
-    const uint8_t *cp = reinterpret_cast<const uint8_t *>(m.col16 + a0) + lane * (EPL * 2u);
+    // column offsets: 2 bytes each, or 1.5 (a0 is a multiple of 8, so a0 * 3 / 2 is exact and 4-byte aligned)
+    constexpr uint32_t kColLaneBytes = C12 ? EPL * 3u / 2u : EPL * 2u;
+    const uint8_t *cp = (C12 ? reinterpret_cast<const uint8_t *>(m.col12) + a0 / 2u * 3u
+                             : reinterpret_cast<const uint8_t *>(m.col16 + a0)) + lane * kColLaneBytes;
     const uint8_t *rp = m.rowbits + (a0 >> 3) + lane * (EPL / 8u);
     const uint32_t zero_off = m.cols * 4u;
 
     ChunkCarry cy{m.chunk_ord[c] - 1u, true, 0.0f};
 
     typename ValRaw<VT>::type nv = ldg_stream_vals<VT>(vp);
-    typename ColRaw<VT>::type nc = ldg_stream_cols<VT>(cp);
+    typename ColRaw<VT, C12>::type nc = ldg_stream_cols<VT, C12>(cp);
     uint32_t nr = ldg_stream_rowbits<VT>(rp);
 #pragma unroll 2
     for (uint32_t it = 0; it < n_iter; it++) {
         const typename ValRaw<VT>::type cv = nv;
-        const typename ColRaw<VT>::type cc = nc;
+        const typename ColRaw<VT, C12>::type cc = nc;
         const uint32_t cr = nr;
         vp += EPI * kValBytes;
-        cp += EPI * 2u;
+        cp += kWarp * kColLaneBytes;
         rp += EPI / 8u;
-        if (it + 1 < n_iter) { nv = ldg_stream_vals<VT>(vp); nc = ldg_stream_cols<VT>(cp); nr = ldg_stream_rowbits<VT>(rp); }
-        csr_consume_iter<VT>(cv, cc, cr, it == 0 || it == last_iter, it, rel_s, rel_e, xs_bytes, zero_off, cy, sink);
+        if (it + 1 < n_iter) {
+            // lanes whose elements all lie behind the chunk's end (last iteration) fetch nothing: on average half an
+            // iteration per chunk, ~3 % of the bytes of a 4096-non-zero chunk
+            if ((int32_t)((it + 1u) * EPI + lane * EPL) < rel_e) {
+                nv = ldg_stream_vals<VT>(vp); nc = ldg_stream_cols<VT, C12>(cp); nr = ldg_stream_rowbits<VT>(rp);
+            } else {
+                nr = 0u;   // no row starts; values and columns of this lane are masked by the edge iteration anyway
+            }
+        }
+        csr_consume_iter<VT, C12>(cv, cc, cr, it == 0 || it == last_iter, it, rel_s, rel_e, xs_bytes, zero_off, cy, sink);
     }
     if (!truncated) {
         // the row in progress at the end of the chunk is complete (chunks end on row boundaries)
@@ -513,7 +565,7 @@ __device__ __forceinline__ void csr_process_chunk_tma(const CsrDevice &m, const 
             if (++tries > (1u << 22)) __trap();   // a copy that never lands must not hang the device
         }
         typename ValRaw<VT>::type cv = lds_lane32(st, lane);
-        typename ColRaw<VT>::type cc;
+        typename ColRaw<VT, false>::type cc;
         uint32_t cr;
         if constexpr (VT != 0) {
             cc = lds_lane32(st + S::kValBytes, lane);
@@ -524,7 +576,7 @@ __device__ __forceinline__ void csr_process_chunk_tma(const CsrDevice &m, const 
         }
         __syncwarp();
         if (++ring.slot == kTmaStages) { ring.slot = 0; ring.parity ^= 1u; }
-        csr_consume_iter<VT>(cv, cc, cr, it == 0 || it + 1 == n_iter, it, rel_s, rel_e, xs_bytes, zero_off, cy, sink);
+        csr_consume_iter<VT, false>(cv, cc, cr, it == 0 || it + 1 == n_iter, it, rel_s, rel_e, xs_bytes, zero_off, cy, sink);
     }
     sink.emit(lane == 0 && !cy.first_pending && (cy.carry >= sink.tau), cy.carry, cy.R);
 }
@@ -698,7 +750,7 @@ __device__ __forceinline__ float query_value(float x) {
 
 // <= 64 registers (4 CTAs of 256 threads per SM): its warps must fit into the register holes two main-kernel CTAs leave
 // in every SM sub-partition when it runs beside them (pipelined submits)
-template <int VT>
+template <int VT, bool C12 = false>
 __global__ void __launch_bounds__(kSampleThreads, 4) csr_sample_kernel(CsrDevice m, const float *__restrict__ x,
                                                                      RunState *st, uint32_t *sample_keys,
                                                                      uint32_t n_sample, uint32_t stride,
@@ -714,7 +766,7 @@ __global__ void __launch_bounds__(kSampleThreads, 4) csr_sample_kernel(CsrDevice
     if (gw < n_sample) {
         MaxSink sink{0.0f, false, neg_inf()};
         const uint32_t c = gw * stride;
-        if (c < m.n_chunks) csr_process_chunk<VT>(m, smem_raw, c, sample_iters, sink);
+        if (c < m.n_chunks) csr_process_chunk<VT, C12>(m, smem_raw, c, sample_iters, sink);
         uint32_t key = sink.any ? f32_to_ordered(sink.best) : 0u;
         key = __reduce_max_sync(kFull, key);
         if (lane_id() == 0) sample_keys[gw] = key;
@@ -756,7 +808,7 @@ __host__ __device__ constexpr size_t main_tma_extra_smem(uint32_t warps) {
     return 128u + (size_t)warps * kTmaStages * (TmaStage<VT>::kStride + 8u);
 }
 
-template <int CAP, int VT, bool TMA = false>
+template <int CAP, int VT, bool TMA = false, bool C12 = false>
 __global__ void __launch_bounds__(VT != 0 ? kMainThreads16 : (CAP == 256 ? kMainThreadsWide : kMainThreads), 2)
 csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uint64_t *pool, uint32_t k,
                      int tie_higher, uint32_t seq, uint32_t tau_wait_us, uint64_t *stamp) {
@@ -816,7 +868,7 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
         if (c >= m.n_chunks) break;
         sink.tau = fmaxf(sink.tau, tau_from_key(ld_relaxed_u32(&st->tau_key)));
         if constexpr (TMA) csr_process_chunk_tma<VT>(m, smem_raw, c, sink, ring);
-        else csr_process_chunk<VT>(m, smem_raw, c, 0xFFFFFFFFu, sink);
+        else csr_process_chunk<VT, C12>(m, smem_raw, c, 0xFFFFFFFFu, sink);
     }
 
     // hand the survivors to the global pool (filtered by the freshest bound)

@@ -31,6 +31,7 @@ struct Handle {
     uint32_t cols = 0;
     void *d_val = nullptr;              // fp32 values, or IEEE halves when cfg.value_type == TKS_VALUE_FP16
     uint16_t *d_col16 = nullptr;        // column * 4
+    uint32_t *d_col12 = nullptr;        // the same packed to 12 bits (cols <= 1024): streamed by the single-query kernels
     uint32_t *d_rowbits = nullptr;      // row-start bitmap, one bit per non-zero (zeroed words, atomicOr at build)
     uint64_t *d_ptr64 = nullptr;        // kept for tks_download_csr (exact copy of row_ptr as u64)
     uint64_t *d_chunk_start = nullptr;
