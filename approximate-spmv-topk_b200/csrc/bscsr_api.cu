@@ -60,6 +60,10 @@ cudaError_t prep_stream_variant(int *ctas_per_sm) {
     const size_t smem = bscsr_stream_smem(XREP, THREADS);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (const char *v = std::getenv("TKS_BSCSR_CARVEOUT")) {   // experiment: L1 / shared split of the stream kernel, percent
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(v));
+        if (e != cudaSuccess) return e;
+    }
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kern, THREADS, smem);
 }
 

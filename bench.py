@@ -328,6 +328,13 @@ def ours(args):
     nsteps = args.warmup + args.steps
     queries = make_queries(cols, nsteps)
 
+    if wl["mode"] == "fixed" and world > 1:
+        line = fixed_sharded_workload(tks, torch, dist, args, world, rank, local, args.steps, args.warmup)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if wl["mode"] == "fixed":
         return ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src)
     if wl["mode"] == "batched":
@@ -357,9 +364,14 @@ def ours(args):
                                 steps=min(args.steps, 5), warmup=3, full=False)
         if rank == 0:
             line["cfg5"] = sub5
+        # ... and BASELINE config 3 with its 32 partitions dealt out over the ranks
+        if 32 % world == 0:
+            sub3 = fixed_sharded_workload(tks, torch, dist, args, world, rank, local, min(args.steps, 10), 3)
+            if rank == 0:
+                line["cfg3"] = sub3
     if rank == 0:
         print(json.dumps(line), flush=True)
-    recs = [line or {}] + [(line or {}).get(k) or {} for k in ("cfg4", "cfg5")]
+    recs = [line or {}] + [(line or {}).get(k) or {} for k in ("cfg3", "cfg4", "cfg5")]
     ok = all(r.get("parity_n", True) is not False for r in recs)
     if world > 1:
         dist.barrier()
@@ -1181,12 +1193,85 @@ def fixed_workload(args, tks, wl, rows_total, queries, peak_gbs, peak_src, steps
             "gpu_launches": steps * 3, "results_returned": int(i_last.size),
             "logged_candidates_last_step": int(st.logged_candidates), "recall_vs_exact_fp32": recall,
             "clocks": clocks}
+    line["parity_n"] = True   # the assertions above would have stopped the run otherwise
     line["parity"] = ("the stream-order, pipelined and host-fed paths return identical lists (asserted above); bit-exactness against the "
                       "oracle at this size: tests/test_gpu_full_size.py")
     eng.close()
     torch.cuda.empty_cache()
     return line
 
+
+
+def fixed_sharded_workload(tks, torch, dist, args, world, rank, local, steps, warmup):
+    """cfg3 over several GPUs (FPGA mode): the reference's 32 row partitions dealt out over the ranks
+    (ShardedSpMVFixed), every step = reset(vec) -> operator() on every rank -> all-gather of the result words (32 KB in
+    total) -> the reference's host merge on every rank.  Strong scaling of the 10M-row matrix; blocking verbs (there is
+    no pipelined form of the partition exchange)."""
+    wl = WORKLOADS["cfg3"]
+    W, P, Kp, LFR = 20, 32, 8, 4
+    rows, cols = wl["rows"], wl["cols"]
+    src = tks.SpMV(num_cols=cols, k=K, device=local)
+    src.generate_synthetic(rows, cols, wl["deg"], wl["dist"], seed=SEED)     # every rank builds the same matrix and keeps its part
+    ptr, idx, val = src.download_csr()
+    src.close()
+    x = np.repeat(np.arange(rows, dtype=np.uint32), np.diff(ptr.astype(np.int64)))
+    nnz = int(ptr[-1])
+    val32 = tks.capi.fixed32_from_double_np(val.astype(np.float64))
+    del val
+    t0 = time.perf_counter()
+    s = tks.ShardedSpMVFixed(x, idx, val32, rows, cols, k=K, fixed_width=W, partitions=P, local_k=Kp, limited_finished_rows=LFR,
+                             device=local, device_pack=True)
+    pack_s = time.perf_counter() - t0
+    queries = make_queries(cols, warmup + steps)
+    q32 = tks.capi.fixed32_from_double_np(queries.astype(np.float64))
+    for i in range(warmup):
+        s.reset(q32[i])
+        s()
+    torch.cuda.synchronize()
+    dist.barrier()
+    aligned_start(torch, dist, world)
+    t0 = time.perf_counter()
+    kernel_ns = []
+    for i in range(steps):
+        s.reset(q32[warmup + i])
+        kernel_ns.append(s())
+    dt = (time.perf_counter() - t0) * 1e3 / steps
+    t = torch.tensor([dt, float(np.mean(kernel_ns)) * 1e-6], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, kernel_ms = float(t[0].item()), float(t[1].item())
+    v_last, i_last = s.read_result()
+    # parity: every rank holds the same list, and it is the list ONE device holding all 32 partitions returns (rank 0
+    # builds that engine beside its shard) -- which tests/test_gpu_full_size.py holds bit-exact to the oracle
+    lists = [None] * world
+    dist.all_gather_object(lists, (np.asarray(i_last), np.asarray(v_last)))
+    same = all(np.array_equal(l[0], lists[0][0]) and np.array_equal(l[1], lists[0][1]) for l in lists)
+    one = None
+    if rank == 0:
+        full = tks.SpMVFixed(x, idx, val32, rows, cols, k=K, fixed_width=W, partitions=P, local_k=Kp,
+                             limited_finished_rows=LFR, device=local, device_pack=True)
+        full.reset(q32[warmup + steps - 1])
+        full()
+        fv, fi = full.read_result()
+        full.close()
+        one = bool(np.array_equal(fi, i_last) and np.array_equal(fv, v_last))
+    flag = [one]
+    dist.broadcast_object_list(flag, src=0)
+    s.close()
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"metric": "topk_spmv_nnz_per_s", "value": nnz / (ms_step * 1e-3), "unit": "nnz/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "dtype": "u32 (20-bit fixed point)",
+            "data": "synthetic",
+            "config": {"workload": wl["name"] + f", the 32 partitions dealt out over {world} GPUs ({P // world} each)", "rows": rows,
+                       "cols": cols, "nnz": nnz, "k": K, "fixed_width": W, "partitions": P, "local_k": Kp, "limited_finished_rows": LFR,
+                       "step": "reset(host vec) -> operator() on every rank -> all-gather of the result words -> host merge on every rank "
+                               "(wall clock, max over ranks)", "pack_upload_s": round(pack_s, 2)},
+            "local_kernels_ms": kernel_ms,
+            "parity_n": bool(same and flag[0]),
+            "parity": {"ranks_hold_identical_results": bool(same), "equals_one_device_holding_all_partitions": flag[0],
+                       "oracle": "tests/test_gpu_full_size.py holds the one-device engine bit-exact to the oracle at this size"},
+            "gpu_launches": steps * 3}
 
 
 def ours_fixed(args, tks, wl, rows_total, queries, peak_gbs, peak_src):
