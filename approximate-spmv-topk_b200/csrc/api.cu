@@ -69,6 +69,7 @@ size_t main_smem_bytes(uint32_t cols, int variant, int threads) {
 // of register loads; chunk loads then start on 128-non-zero boundaries (in the sample kernel too)
 // TKS_COL12=0: stream 16-bit column offsets even when 12 bits would do (A/B switch)
 bool col12_enabled() { static const bool on = !(std::getenv("TKS_COL12") && std::atoi(std::getenv("TKS_COL12")) == 0); return on; }
+uint32_t l2_prefetch_depth() { static const uint32_t v = env_u32("TKS_L2PF", 0u); return v > 8u ? 8u : v; }
 bool tma_enabled() { static const bool on = std::getenv("TKS_TMA") && std::atoi(std::getenv("TKS_TMA")) != 0; return on; }
 int tma_threads(int vt) { static const int t = (int)env_u32("TKS_TMA_THREADS", 0u) / 32 * 32; return t >= 64 ? t : (vt != 0 ? 384 : 448); }
 
@@ -206,7 +207,7 @@ void launch_main_variant(Handle *h, int variant, const CsrDevice &m, const float
 CsrDevice csr_device(const Handle *h) {
     return CsrDevice{h->d_val, h->d_col16, h->d_col12, reinterpret_cast<const uint8_t *>(h->d_rowbits), h->d_chunk_start,
                      h->d_chunk_ord, h->d_row_map, h->n_chunks, h->cols, (uint32_t)h->row_offset,
-                     (uint32_t)value_type(h), tma_enabled() ? 128u : (value_type(h) != 0 ? 16u : 8u)};
+                     (uint32_t)value_type(h), tma_enabled() ? 128u : (value_type(h) != 0 ? 16u : 8u), l2_prefetch_depth()};
 }
 
 __global__ void widen_u32_to_u64_kernel(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {

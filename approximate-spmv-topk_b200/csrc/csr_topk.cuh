@@ -58,6 +58,7 @@ struct CsrDevice {
     uint32_t row_offset;           // added to every reported row id
     uint32_t val_type;             // TKS_VALUE_*: 0 fp32, 1 half, 2 bfloat16 (the batched kernel branches on it at run time)
     uint32_t start_align;          // chunk loads start on a multiple of this many non-zeros: 8 / 16 (one lane), 128 with bulk copies
+    uint32_t l2_prefetch;          // experiment (TKS_L2PF=n): lane 0 bulk-prefetches the iteration n ahead into L2
 };
 
 // Per-query scratch that lives in HBM; zeroed at creation and by the select kernel.
@@ -447,6 +448,18 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
         vp += EPI * kValBytes;
         cp += kWarp * kColLaneBytes;
         rp += EPI / 8u;
+#ifdef TKS_EXPERIMENT_L2PF   // measured slower (r02ab: cfg2 main kernel 0.205 -> 0.230-0.234 ms at depth 2..4); compiled out, since
+                            // even the untaken branch cost the 16-bit kernel 5 %
+        if (m.l2_prefetch && it + m.l2_prefetch < n_iter && lane == 0) {
+            // one instruction per array pulls a whole later iteration into L2: no registers, no shared memory, no barrier
+            const uint8_t *pv = vp - lane * (EPL * kValBytes) + (size_t)(m.l2_prefetch - 1u) * EPI * kValBytes;
+            const uint8_t *pc = cp - lane * kColLaneBytes + (size_t)(m.l2_prefetch - 1u) * kWarp * kColLaneBytes;
+            const uint8_t *pr = rp - lane * (EPL / 8u) + (size_t)(m.l2_prefetch - 1u) * (EPI / 8u);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pv), "r"(EPI * kValBytes) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((uintptr_t)pc & ~(uintptr_t)15), "r"((kWarp * kColLaneBytes + 31u) & ~15u) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((uintptr_t)pr & ~(uintptr_t)15), "r"((EPI / 8u + 31u) & ~15u) : "memory");
+        }
+#endif
         if (it + 1 < n_iter) {
             // lanes whose elements all lie behind the chunk's end (last iteration) fetch nothing: on average half an
             // iteration per chunk, ~3 % of the bytes of a 4096-non-zero chunk
