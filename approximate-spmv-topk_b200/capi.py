@@ -52,7 +52,7 @@ SYMBOLS = [
     "tks_upload_csr", "tks_upload_csr_device", "tks_upload_bscsr", "tks_generate_synthetic",
     "tks_upload_coo_fixed", "tks_upload_coo_fixed_device", "tks_bscsr_state_digest",
     "tks_download_csr", "tks_download_csr_rows", "tks_set_query", "tks_set_query_device", "tks_run", "tks_run_async",
-    "tks_read_result", "tks_read_partition_results", "tks_result_keys_device", "tks_merge_keys_device", "tks_merge_keys_batched_device",
+    "tks_read_result", "tks_read_partition_results", "tks_partition_words_device", "tks_result_keys_device", "tks_merge_keys_device", "tks_merge_keys_batched_device",
     "tks_peer_init", "tks_peer_connect", "tks_run_exchange_async", "tks_peer_exchange_async",
     "tks_group_create", "tks_group_destroy", "tks_group_last_error", "tks_group_size", "tks_group_member",
     "tks_group_upload_csr", "tks_group_generate_synthetic", "tks_group_set_query", "tks_group_run", "tks_group_read_result",
@@ -100,6 +100,7 @@ def lib() -> C.CDLL:
     L.tks_run_async.argtypes = [vp, C.c_uint32, vp]
     L.tks_read_result.argtypes = [vp, C.c_uint32, vp, vp, u32p]
     L.tks_read_partition_results.argtypes = [vp, vp, vp]
+    L.tks_partition_words_device.argtypes = [vp, C.POINTER(vp), u32p]
     L.tks_result_keys_device.argtypes = [vp, C.c_uint32, C.POINTER(vp), u32p]
     L.tks_merge_keys_device.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, vp]
     L.tks_merge_keys_batched_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]

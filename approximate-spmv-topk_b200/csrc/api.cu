@@ -270,7 +270,11 @@ void drop_run_graph(Handle *h) {
     h->run_graph_k = 0;
 }
 
+int pipe_drain(Handle *h);
+
 void free_matrix(Handle *h) {
+    // a matrix is replaced: nothing submitted against the old one may still be running
+    if (h->d_pipe_state) { pipe_drain(h); cudaDeviceSynchronize(); }
     drop_run_graph(h);
     cudaFree(h->d_val); h->d_val = nullptr;
     cudaFree(h->d_col16); h->d_col16 = nullptr;
@@ -1067,6 +1071,12 @@ int tks_read_partition_results(tks_handle *h, uint32_t *idx_words, uint32_t *val
     if (!h) return TKS_EINVAL;
     if (h->cfg.mode != TKS_MODE_FIXED_BSCSR) return h->fail(TKS_ESTATE, "BS-CSR mode only");
     return bscsr_read_partition_results(h, idx_words, val_words);
+}
+
+int tks_partition_words_device(tks_handle *h, const uint32_t **d_words, uint32_t *n_words) {
+    if (!h || !d_words) return TKS_EINVAL;
+    if (h->cfg.mode != TKS_MODE_FIXED_BSCSR) return h->fail(TKS_ESTATE, "BS-CSR mode only");
+    return bscsr_partition_words_device(h, d_words, n_words);
 }
 
 int tks_result_keys_device(tks_handle *h, uint32_t query, const uint64_t **d_keys, uint32_t *count) {

@@ -761,6 +761,16 @@ int bscsr_read_result(Handle *h, uint32_t *idx_out, uint32_t *val_out, uint32_t 
     return TKS_OK;
 }
 
+// Device address of the last un-pipelined run's result words: partitions x local_k x 16 index words, then as many value
+// words (one block), for a device-side all-gather between ranks.
+int bscsr_partition_words_device(Handle *h, const uint32_t **d_words, uint32_t *n_words) {
+    BscsrState *b = h->bs;
+    if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");
+    *d_words = b->d_res_idx;
+    if (n_words) *n_words = (uint32_t)(2u * (size_t)b->P * h->cfg.local_k * 16u);
+    return TKS_OK;
+}
+
 int bscsr_read_partition_results(Handle *h, uint32_t *idx_words, uint32_t *val_words) {
     BscsrState *b = h->bs;
     if (!b) return h->fail(TKS_ESTATE, "no packets uploaded");

@@ -176,6 +176,7 @@ int bscsr_fetch_ticket(Handle *h, uint64_t ticket, uint32_t *idx_out, uint32_t *
 int bscsr_fetch(Handle *h);   // D2H of partition result words + host merge
 int bscsr_read_result(Handle *h, uint32_t *idx_out, uint32_t *val_out, uint32_t k, uint32_t *count);
 int bscsr_read_partition_results(Handle *h, uint32_t *idx_words, uint32_t *val_words);
+int bscsr_partition_words_device(Handle *h, const uint32_t **d_words, uint32_t *n_words);
 int bscsr_state_digest(Handle *h, uint64_t *digest, uint32_t n);
 void bscsr_destroy(Handle *h);
 

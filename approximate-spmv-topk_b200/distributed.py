@@ -206,6 +206,8 @@ class ShardedSpMVFixed:
 
     def __call__(self, debug=0):
         """operator(): run the local partitions, exchange the result words, merge.  Returns the local kernel ns."""
+        if self.nccl and self.world > 1:
+            return self._call_device_gather()
         ns = self.engine()
         iw, vw = self.engine.read_partition_results()
         allw = self._all_gather(np.concatenate([iw.reshape(-1), vw.reshape(-1)]))
@@ -215,6 +217,31 @@ class ShardedSpMVFixed:
         self.val_words = allw[:, 1, :].reshape(self.P, self.Kp, 16)
         self._val, self._idx = self.capi.merge_partition_words(self.idx_words, self.val_words, self.first_row, self.B, self.k)
         return ns
+
+    def _call_device_gather(self):
+        """NCCL ranks: the kernels, the all-gather of the result words (device to device, straight from the engine's result
+        block) and ONE device-to-host copy of all P partitions' words are enqueued on torch's current stream; the host
+        waits once, then merges."""
+        torch = self.torch
+        stream = torch.cuda.current_stream()
+        if getattr(self, "_gath", None) is None:
+            ptr, n = self.engine.partition_words_device()
+            self._words = torch.as_tensor(_DevView(ptr, (n,), "<i4"), device="cuda")
+            self._gath = torch.empty(self.world * n, dtype=torch.int32, device="cuda")
+            self._host = torch.empty(self.world * n, dtype=torch.int32).pin_memory()
+            self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        self._ev[0].record(stream)
+        self.engine.run_async(self.k, stream.cuda_stream)
+        self._ev[1].record(stream)
+        self.dist.all_gather_into_tensor(self._gath, self._words, group=self.group)
+        self._host.copy_(self._gath, non_blocking=True)
+        stream.synchronize()
+        per = self.ppr * self.Kp * 16
+        allw = self._host.numpy().view(np.uint32).reshape(self.world, 2, per)
+        self.idx_words = allw[:, 0, :].reshape(self.P, self.Kp, 16)
+        self.val_words = allw[:, 1, :].reshape(self.P, self.Kp, 16)
+        self._val, self._idx = self.capi.merge_partition_words(self.idx_words, self.val_words, self.first_row, self.B, self.k)
+        return self._ev[0].elapsed_time(self._ev[1]) * 1e6
 
     def read_result(self):
         """(raw values uint32[n], GLOBAL row indices uint32[n]), n <= k; identical on every rank."""

@@ -356,6 +356,12 @@ class SpMVFixed(_Base):
         n = out[2].value
         return out[1][:n].copy(), out[0][:n].copy()
 
+    def partition_words_device(self):
+        """(device pointer, word count) of the last async run's result words: index words, then value words."""
+        p, n = C.c_void_p(), C.c_uint32()
+        check(capi.lib().tks_partition_words_device(self.handle, C.byref(p), C.byref(n)), self.handle)
+        return p.value, n.value
+
     def read_partition_results(self):
         Kp = self.cfg.local_k
         idx_w = np.zeros((self.partitions, Kp, 16), np.uint32)

@@ -176,6 +176,11 @@ int tks_read_result(tks_handle *h, uint32_t query, uint32_t *idx_out, void *val_
  * 16 x u32 (row index local to the partition) and 16 x u32 (ap_ufixed<32,1>). */
 int tks_read_partition_results(tks_handle *h, uint32_t *idx_words, uint32_t *val_words);
 
+/* BS-CSR mode, several GPUs: device address of the result words of the last tks_run_async (index words, then value
+ * words, one block of *n_words 32-bit words), so that ranks can all-gather them device to device before the host
+ * merge (tks_merge_partition_words).                                                                            */
+int tks_partition_words_device(tks_handle *h, const uint32_t **d_words, uint32_t *n_words);
+
 /* ---- multi-GPU plumbing: K candidates per rank, merged after an all-gather */
 
 /* Device pointer to the last run's sorted candidates of query q as 64-bit keys
