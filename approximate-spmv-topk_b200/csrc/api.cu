@@ -293,9 +293,28 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
                           const uint32_t *d_idx, const float *d_val_src, float *d_val_adopt) {
     cudaStream_t s = h->stream;
     const size_t pad = 2048;   // over-read slack of the 256-bit streaming loads (zero filled)
-    h->chunk_nnz = h->cfg.chunk_nnz > 0 ? (uint32_t)h->cfg.chunk_nnz : 4096u;
+    // work units: cfg.chunk_nnz if given; else 8192 non-zeros for large streams, 4096 for small matrices.  Every chunk start
+    // costs a warp three dependent round trips (scheduler atomic, chunk table, first loads), ~2 us: cfg2 steps with 2048 /
+    // 4096 / 8192 / 16384 take 0.283 / 0.201 / 0.191 / 0.193 ms (r02af).  A tail of quarter-size chunks (TKS_CHUNK_TAIL=1),
+    // meant to let the persistent warps run dry together, costs more than it balances: 0.2041 vs 0.1915 ms (r02ag).
+    uint32_t n_big = 0, chunk_small = 0;
+    if (h->cfg.chunk_nnz > 0) {
+        h->chunk_nnz = (uint32_t)h->cfg.chunk_nnz;
+    } else {
+        h->chunk_nnz = env_u32("TKS_CHUNK_NNZ", nnz >= (32ull << 20) ? 8192u : 4096u);   // env: A/B switch
+        if (nnz >= (32ull << 20) && env_u32("TKS_CHUNK_TAIL", 0u)) chunk_small = h->chunk_nnz / 4u;
+    }
     h->chunk_nnz = (h->chunk_nnz + kElemsPerIter - 1) / kElemsPerIter * kElemsPerIter;
     uint64_t nch = (nnz + h->chunk_nnz - 1) / h->chunk_nnz;
+    if (chunk_small) {
+        chunk_small = (chunk_small + kElemsPerIter - 1) / kElemsPerIter * kElemsPerIter;
+        n_big = (uint32_t)(nnz / 10u * 9u / h->chunk_nnz);
+        const uint64_t rest = nnz - (uint64_t)n_big * h->chunk_nnz;
+        nch = n_big + (rest + chunk_small - 1) / chunk_small;
+    } else {
+        n_big = (uint32_t)(nch > 0xFFFFFFF0ull ? 0u : nch);
+        chunk_small = h->chunk_nnz;
+    }
     if (nch == 0) nch = 1;
     if (nch > 0xFFFFFFF0ull) return h->fail(TKS_EINVAL, "too many chunks (%llu)", (unsigned long long)nch);
     h->n_chunks = (uint32_t)nch;
@@ -358,7 +377,8 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
         csr_row_map_kernel<<<(uint32_t)((rows + 255) / 256), 256, 0, s>>>(d_flag, d_ord, rows, h->d_row_map);
     }
     csr_chunk_table_kernel<P><<<(uint32_t)((nch + 1 + 127) / 128), 128, 0, s>>>(
-        d_ptr, rows, nnz, h->chunk_nnz, h->n_chunks, has_empty ? d_ord : nullptr, h->d_chunk_start, h->d_chunk_ord);
+        d_ptr, rows, nnz, h->chunk_nnz, n_big, chunk_small, h->n_chunks, has_empty ? d_ord : nullptr, h->d_chunk_start,
+        h->d_chunk_ord);
     uint32_t herr = 0;
     TKS_CUDA(h, cudaMemcpyAsync(&herr, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     TKS_CUDA(h, cudaStreamSynchronize(s));

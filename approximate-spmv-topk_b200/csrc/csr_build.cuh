@@ -94,15 +94,19 @@ __global__ void csr_row_map_kernel(const uint32_t *__restrict__ nonempty_flag, c
     if (r < rows && nonempty_flag[r]) row_map[ord[r]] = (uint32_t)r;
 }
 
-// One thread per chunk: first row starting at or after c*chunk_nnz, and its ordinal among non-empty rows.
+// One thread per chunk: first row starting at or after the chunk's nominal offset, and its ordinal among non-empty rows.
+// The first n_big chunks are chunk_nnz non-zeros long, the rest (the tail of the stream) chunk_small: every chunk start
+// costs a warp three dependent round trips (scheduler atomic, this table, first loads), so the work units are large --
+// but the persistent warps should still run dry together, so the last tenth of the stream is handed out in quarters.
 template <typename P>
 __global__ void csr_chunk_table_kernel(const P *__restrict__ ptr, uint64_t rows, uint64_t nnz, uint32_t chunk_nnz,
-                                       uint32_t n_chunks, const uint64_t *__restrict__ ord,
-                                       uint64_t *__restrict__ chunk_start, uint32_t *__restrict__ chunk_ord) {
+                                       uint32_t n_big, uint32_t chunk_small, uint32_t n_chunks,
+                                       const uint64_t *__restrict__ ord, uint64_t *__restrict__ chunk_start,
+                                       uint32_t *__restrict__ chunk_ord) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > n_chunks) return;
     if (c == n_chunks) { chunk_start[c] = nnz; return; }
-    const uint64_t target = (uint64_t)c * chunk_nnz;
+    const uint64_t target = c < n_big ? (uint64_t)c * chunk_nnz : (uint64_t)n_big * chunk_nnz + (uint64_t)(c - n_big) * chunk_small;
     uint64_t lo = 0, hi = rows;   // lower_bound over ptr[0..rows)
     while (lo < hi) {
         uint64_t mid = (lo + hi) >> 1;
