@@ -301,7 +301,9 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
     if (h->cfg.chunk_nnz > 0) {
         h->chunk_nnz = (uint32_t)h->cfg.chunk_nnz;
     } else {
-        h->chunk_nnz = env_u32("TKS_CHUNK_NNZ", nnz >= (32ull << 20) ? 8192u : 4096u);   // env: A/B switch
+        // handles made for batched queries keep 4096: the batched kernel runs eight streams per warp, which want twice as
+        // many units to balance (cfg5 main kernel 10.85 ms with 4096, 11.42 ms with 8192, r02ah)
+        h->chunk_nnz = env_u32("TKS_CHUNK_NNZ", (nnz >= (32ull << 20) && h->cfg.max_batch == 1) ? 8192u : 4096u);   // env: A/B switch
         if (nnz >= (32ull << 20) && env_u32("TKS_CHUNK_TAIL", 0u)) chunk_small = h->chunk_nnz / 4u;
     }
     h->chunk_nnz = (h->chunk_nnz + kElemsPerIter - 1) / kElemsPerIter * kElemsPerIter;
