@@ -19,7 +19,7 @@ struct BscsrState {
     uint8_t *d_packets = nullptr;
     uint32_t *d_chunk_first = nullptr, *d_chunk_count = nullptr, *d_chunk_local0 = nullptr, *d_chunk_row_in = nullptr,
              *d_chunk_lookback = nullptr, *d_chunk_part = nullptr, *d_part_chunk_begin = nullptr;
-    uint32_t n_chunks = 0, chunk_cap = 0;
+    uint32_t n_chunks = 0, chunk_cap = 0, tail_div = 4;
     BscsrLogs logs{};
     // sample pieces (first kBsSamplePackets packets of every partition, kBsSamplePiece each)
     uint32_t *d_s_first = nullptr, *d_s_count = nullptr, *d_s_local0 = nullptr, *d_s_lookback = nullptr, *d_s_part = nullptr,
@@ -173,6 +173,15 @@ static int bscsr_begin_upload(Handle *h, uint32_t cols, uint32_t partitions, Bsc
     b->bsx = (W + 10 <= 32) && !(std::getenv("TKS_BSCSR_VERBATIM") && std::atoi(std::getenv("TKS_BSCSR_VERBATIM")) != 0);
     const bool drift_free = h->cfg.fixed_drift_free != 0;
     if (drift_free) b->chunk_cap = 256;   // up to B rows can finish per packet: keeps the 12-bit in-chunk row offset in range
+    // measurement knobs: packets per work unit (multiple of 32) and the divisor of the tail units
+    if (const char *e = std::getenv("TKS_BSCSR_CHUNK")) {
+        const uint32_t v = (uint32_t)std::atoi(e);
+        if (v >= 64 && v <= 4096 && v % 32 == 0) b->chunk_cap = v;
+    }
+    if (const char *e = std::getenv("TKS_BSCSR_TAIL_DIV")) {
+        const uint32_t v = (uint32_t)std::atoi(e);
+        if (v >= 1 && v <= 8 && (b->chunk_cap / v) % 32 == 0) b->tail_div = v;
+    }
     if (drift_free && (!b->bsx || LFR < 2))
         return h->fail(TKS_EINVAL, "fixed_drift_free needs fixed_width <= 22 (the re-encoded device format) and limited_finished_rows >= 2");
     *out = b;
@@ -267,7 +276,7 @@ int bscsr_upload(Handle *h, uint32_t cols, uint32_t partitions, const uint64_t *
                 // look-back + chunk = a whole number of 32-packet warp iterations (no extra iteration for the look-back)
                 // the chunks processed last are four times smaller: the persistent warps then run dry within a
                 // few iterations of each other instead of up to a whole 512-packet chunk apart
-                const uint32_t cap_here = (goff + i >= tail_begin) ? b->chunk_cap / 4u : b->chunk_cap;
+                const uint32_t cap_here = (goff + i >= tail_begin) ? b->chunk_cap / b->tail_div : b->chunk_cap;
                 const uint64_t cnt = std::min<uint64_t>(cap_here - (L % 32u), np - i);
                 c_first.push_back((uint32_t)(goff + i));
                 c_count.push_back((uint32_t)cnt);
@@ -501,7 +510,7 @@ int bscsr_upload_coo(Handle *h, const uint32_t *row, const uint32_t *col, const 
     d_cbeg = b->d_part_chunk_begin; d_pbeg = b->d_s_part_begin;
     WalkOut wo{};
     wo.n_chunks = d_nch; wo.n_pieces = d_npc;
-    bscsr_chunk_walk_kernel<<<(P + 31) / 32, 32, 0, s>>>(parts, d_keep, d_rowsum, total, b->chunk_cap, wo);
+    bscsr_chunk_walk_kernel<<<(P + 31) / 32, 32, 0, s>>>(parts, d_keep, d_rowsum, total, b->chunk_cap, b->tail_div, wo);
     std::vector<uint32_t> nch(P), npc(P), cbeg(P + 1, 0), pbeg(P + 1, 0);
     TKS_CUDA(h, cudaMemcpyAsync(nch.data(), d_nch, P * 4, cudaMemcpyDeviceToHost, s));
     TKS_CUDA(h, cudaMemcpyAsync(npc.data(), d_npc, P * 4, cudaMemcpyDeviceToHost, s));
@@ -524,7 +533,7 @@ int bscsr_upload_coo(Handle *h, const uint32_t *row, const uint32_t *col, const 
     wo.s_first = b->d_s_first; wo.s_count = b->d_s_count; wo.s_local0 = b->d_s_local0; wo.s_look = b->d_s_lookback;
     wo.s_part = b->d_s_part; wo.sample_end = b->d_sample_end;
     wo.chunk_begin = d_cbeg; wo.piece_begin = d_pbeg;
-    bscsr_chunk_walk_kernel<<<(P + 31) / 32, 32, 0, s>>>(parts, d_keep, d_rowsum, total, b->chunk_cap, wo);
+    bscsr_chunk_walk_kernel<<<(P + 31) / 32, 32, 0, s>>>(parts, d_keep, d_rowsum, total, b->chunk_cap, b->tail_div, wo);
     if (b->bsx) {
         TKS_CUDA(h, cudaMemsetAsync(d_err, 0, 4, s));
         bscsr_patch_rel_kernel<<<(b->n_chunks * 32u + 255u) / 256u, 256, 0, s>>>(

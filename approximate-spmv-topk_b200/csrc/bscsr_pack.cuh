@@ -183,7 +183,7 @@ __device__ __forceinline__ uint32_t pack_lookback(const uint8_t *keep, uint64_t 
 // rowsum: exclusive scan of `advance` over ALL packets (u64); the kernel's row counter before packet g of
 // partition p is rowsum[g] - rowsum[pkt_start[p]].
 __global__ void bscsr_chunk_walk_kernel(PackParts parts, const uint8_t *__restrict__ keep, const uint64_t *__restrict__ rowsum,
-                                        uint64_t total_packets, uint32_t chunk_cap, WalkOut o) {
+                                        uint64_t total_packets, uint32_t chunk_cap, uint32_t tail_div, WalkOut o) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= parts.P) return;
     const uint64_t g0 = parts.pkt_start[p], np = parts.pkt_start[p + 1] - g0;
@@ -193,7 +193,7 @@ __global__ void bscsr_chunk_walk_kernel(PackParts parts, const uint8_t *__restri
     uint32_t nc = 0, cb = fill ? o.chunk_begin[p] : 0u;
     for (uint64_t i = 0; i < np;) {
         const uint32_t L = pack_lookback(kp, i);
-        const uint32_t cap_here = (g0 + i >= tail_begin) ? chunk_cap / 4u : chunk_cap;
+        const uint32_t cap_here = (g0 + i >= tail_begin) ? chunk_cap / tail_div : chunk_cap;
         const uint64_t room = cap_here - (L % 32u);
         const uint64_t cnt = room < np - i ? room : np - i;
         if (fill) {

@@ -1036,10 +1036,13 @@ def fixed_workload(args, tks, wl, rows_total, queries, peak_gbs, peak_src, steps
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    sampler.mark("timed")
     for i in range(steps):
         step(warmup + i)
     e1.record()
+    sampler.sample_now("timed")                      # the host runs ahead: the device is still inside the timed steps here
     torch.cuda.synchronize()
+    sampler.mark("after")
     ms_step = e0.elapsed_time(e1) / steps
     clocks = sampler.stop()
     v_last, i_last = eng.read_result()
