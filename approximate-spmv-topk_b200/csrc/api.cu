@@ -73,6 +73,16 @@ uint32_t l2_prefetch_depth() { static const uint32_t v = env_u32("TKS_L2PF", 0u)
 bool tma_enabled() { static const bool on = std::getenv("TKS_TMA") && std::atoi(std::getenv("TKS_TMA")) != 0; return on; }
 int tma_threads(int vt) { static const int t = (int)env_u32("TKS_TMA_THREADS", 0u) / 32 * 32; return t >= 64 ? t : (vt != 0 ? 384 : 448); }
 
+// TKS_XCOPIES=1 (measurement variant): the k <= 128 main kernel keeps 32 interleaved copies of the query in shared memory
+// (conflict-free gathers) and runs as ONE CTA per SM
+bool xcopies_enabled() { static const bool on = std::getenv("TKS_XCOPIES") && std::atoi(std::getenv("TKS_XCOPIES")) != 0; return on; }
+int xcopies_threads(int vt) {
+    static const int t = (int)env_u32("TKS_XCOPIES_THREADS", 0u) / 32 * 32;
+    const int cap = vt != 0 ? (int)kMainThreadsX16 : (int)kMainThreadsX;
+    return (t >= 64 && t <= cap) ? t : cap;
+}
+size_t xcopies_smem_bytes(uint32_t cols, int threads) { return ((size_t)cols + 1u) * 128u + (size_t)(threads / 32) * 256u * 8u; }
+
 // bounds of the device-side waits (peer records, pipelined hand-overs); raise them under compute-sanitizer
 uint32_t spin_timeout_ms() { static const uint32_t v = env_u32("TKS_SPIN_TIMEOUT_MS", 2000u); return v; }
 uint32_t tau_wait_us() { static const uint32_t v = env_u32("TKS_TAU_WAIT_US", 20000u); return v; }
@@ -146,8 +156,31 @@ cudaError_t prep_main_tma(Handle *h) {
     return cudaSuccess;
 }
 
+// Measured slower than the default kernel (r02ak: cfg2 main kernel 0.1939 -> 0.2083 ms, cfg2h 0.1479 -> 0.1563 ms): the
+// 128 KB of copies push the carve-out to 196 KB, and the stream's loads in flight miss the L1 that is left (DESIGN.md
+// section 4.1).  Compiled only with -DTKS_EXPERIMENT_XCOPIES (three more instantiations of the largest kernel).
+#ifdef TKS_EXPERIMENT_XCOPIES
+template <int VT>
+cudaError_t prep_main_x(Handle *h) {
+    const int threads = xcopies_threads(VT);
+    const size_t smem = xcopies_smem_bytes(h->cfg.max_cols, threads);
+    h->x_grid = 0;
+    if (smem > 227u * 1024u) return cudaSuccess;   // too many columns for 32 copies: the default kernel runs
+    cudaError_t e = cudaFuncSetAttribute(csr_topk_main_kernel<256, VT, false, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    h->x_grid = h->num_sms;
+    return cudaSuccess;
+}
+#endif
+
 template <int CAP>
 cudaError_t prep_main(Handle *h, int variant) {
+#ifdef TKS_EXPERIMENT_XCOPIES
+    if (CAP == 256 && xcopies_enabled()) {
+        cudaError_t e = value_type(h) == TKS_VALUE_FP16 ? prep_main_x<1>(h) : value_type(h) == TKS_VALUE_BF16 ? prep_main_x<2>(h) : prep_main_x<0>(h);
+        if (e != cudaSuccess) return e;
+    }
+#endif
     if (CAP == 256 && tma_enabled()) {
         cudaError_t e = value_type(h) == TKS_VALUE_FP16 ? prep_main_tma<1>(h) : value_type(h) == TKS_VALUE_BF16 ? prep_main_tma<2>(h) : prep_main_tma<0>(h);
         if (e != cudaSuccess) return e;
@@ -179,6 +212,19 @@ void launch_main(Handle *h, int variant, const CsrDevice &m, const float *x, Run
         }
         return;
     }
+#ifdef TKS_EXPERIMENT_XCOPIES
+    if (CAP == 256 && h->d_col12 && xcopies_enabled() && h->x_grid) {
+        const int xt = xcopies_threads(value_type(h));
+        const dim3 xgrid(h->x_grid), xblock(xt);
+        const size_t xs = xcopies_smem_bytes(m.cols, xt);
+        switch (value_type(h)) {
+            case TKS_VALUE_FP16: launch_pdl(csr_topk_main_kernel<256, 1, false, true, 5>, xgrid, xblock, xs, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
+            case TKS_VALUE_BF16: launch_pdl(csr_topk_main_kernel<256, 2, false, true, 5>, xgrid, xblock, xs, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
+            default: launch_pdl(csr_topk_main_kernel<256, 0, false, true, 5>, xgrid, xblock, xs, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;
+        }
+        return;
+    }
+#endif
     if (CAP == 256 && h->d_col12) {
         switch (value_type(h)) {
             case TKS_VALUE_FP16: launch_pdl(csr_topk_main_kernel<256, 1, false, true>, grid, block, smem, s, pdl, m, x, st, pool, k, tie_higher, seq, tw, stamp); break;

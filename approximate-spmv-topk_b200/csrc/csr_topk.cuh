@@ -226,7 +226,10 @@ __device__ __forceinline__ uint32_t ldg_stream_rowbits(const void *p) {
     }
 }
 
-template <bool MASKED, int VT, bool C12>
+// XSH: the query sits in shared memory as 2^XSH interleaved copies, cell (column, copy) at byte (column * 4 << XSH) +
+// copy * 4, and xs_bytes already points at this lane's copy (XSH = 5: one copy per lane, so the gather of a warp's 32
+// random columns never meets in a bank; XSH = 0: one copy, ~3.5 wavefronts per gather)
+template <bool MASKED, int VT, bool C12, int XSH = 0>
 __device__ __forceinline__ void csr_iter(const typename ValRaw<VT>::type &vraw, const typename ColRaw<VT, C12>::type &craw,
                                          uint32_t rbits, const uint8_t *__restrict__ xs_bytes, uint32_t zero_off,
                                          uint32_t lo, uint32_t hi, float carry_in, float &carry_out,
@@ -255,7 +258,7 @@ __device__ __forceinline__ void csr_iter(const typename ValRaw<VT>::type &vraw, 
             c = in ? c : zero_off;      // column -> the zero slot behind x
             v = in ? v : 0.0f;
         }
-        const float x = *reinterpret_cast<const float *>(xs_bytes + c);
+        const float x = *reinterpret_cast<const float *>(xs_bytes + (c << XSH));
         const float p = __fmul_rn(v, x);
         const bool f = (fb >> j) & 1u;
         if (j == 0) {
@@ -359,7 +362,7 @@ struct ChunkCarry {
 
 // One warp iteration's loaded words -> products, segmented sums, candidates.  `edge`: the iteration holds elements
 // outside [rel_s, rel_e) (first / last iteration of the chunk), which are neutralised.
-template <int VT, bool C12, typename Sink>
+template <int VT, bool C12, int XSH = 0, typename Sink>
 __device__ __forceinline__ void csr_consume_iter(const typename ValRaw<VT>::type &cv, const typename ColRaw<VT, C12>::type &cc,
                                                  uint32_t cr, bool edge, uint32_t it, int32_t rel_s, int32_t rel_e,
                                                  const uint8_t *__restrict__ xs_bytes, uint32_t zero_off, ChunkCarry &cy,
@@ -374,9 +377,9 @@ __device__ __forceinline__ void csr_consume_iter(const typename ValRaw<VT>::type
         const int32_t l32 = rel_s - ebase, h32 = rel_e - ebase;
         const uint32_t lo = l32 < 0 ? 0u : (l32 > (int32_t)EPL ? EPL : (uint32_t)l32);
         const uint32_t hi = h32 < 0 ? 0u : (h32 > (int32_t)EPL ? EPL : (uint32_t)h32);
-        csr_iter<true, VT, C12>(cv, cc, cr, xs_bytes, zero_off, lo, hi, cy.carry, carry_out, o);
+        csr_iter<true, VT, C12, XSH>(cv, cc, cr, xs_bytes, zero_off, lo, hi, cy.carry, carry_out, o);
     } else {
-        csr_iter<false, VT, C12>(cv, cc, cr, xs_bytes, zero_off, 0u, EPL, cy.carry, carry_out, o);
+        csr_iter<false, VT, C12, XSH>(cv, cc, cr, xs_bytes, zero_off, 0u, EPL, cy.carry, carry_out, o);
     }
     cy.carry = carry_out;
 
@@ -410,7 +413,7 @@ __device__ __forceinline__ void csr_consume_iter(const typename ValRaw<VT>::type
 }
 
 // Stream one chunk (or its first max_iters iterations) through `sink`.
-template <int VT, bool C12, typename Sink>
+template <int VT, bool C12, int XSH = 0, typename Sink>
 __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint8_t *__restrict__ xs_bytes, uint32_t c,
                                                   uint32_t max_iters, Sink &sink) {
     constexpr uint32_t EPL = Epl<VT>::v, EPI = kWarp * EPL;
@@ -469,7 +472,7 @@ __device__ __forceinline__ void csr_process_chunk(const CsrDevice &m, const uint
                 nr = 0u;   // no row starts; values and columns of this lane are masked by the edge iteration anyway
             }
         }
-        csr_consume_iter<VT, C12>(cv, cc, cr, it == 0 || it == last_iter, it, rel_s, rel_e, xs_bytes, zero_off, cy, sink);
+        csr_consume_iter<VT, C12, XSH>(cv, cc, cr, it == 0 || it == last_iter, it, rel_s, rel_e, xs_bytes, zero_off, cy, sink);
     }
     if (!truncated) {
         // the row in progress at the end of the chunk is complete (chunks end on row boundaries)
@@ -821,13 +824,19 @@ __host__ __device__ constexpr size_t main_tma_extra_smem(uint32_t warps) {
     return 128u + (size_t)warps * kTmaStages * (TmaStage<VT>::kStride + 8u);
 }
 
-template <int CAP, int VT, bool TMA = false, bool C12 = false>
-__global__ void __launch_bounds__(VT != 0 ? kMainThreads16 : (CAP == 256 ? kMainThreadsWide : kMainThreads), 2)
+// XSH = 5 (TKS_XCOPIES=1, measurement variant): one CTA per SM whose 32 query copies (128 bytes per column) make the
+// gather conflict-free; CTA size kMainThreadsX / kMainThreadsX16.
+constexpr uint32_t kMainThreadsX = 1024, kMainThreadsX16 = 768;
+template <int CAP, int VT, bool TMA = false, bool C12 = false, int XSH = 0>
+__global__ void __launch_bounds__(XSH ? (VT != 0 ? kMainThreadsX16 : kMainThreadsX)
+                                      : (VT != 0 ? kMainThreads16 : (CAP == 256 ? kMainThreadsWide : kMainThreads)), XSH ? 1 : 2)
 csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uint64_t *pool, uint32_t k,
                      int tie_higher, uint32_t seq, uint32_t tau_wait_us, uint64_t *stamp) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float *xs = reinterpret_cast<float *>(smem_raw);
-    uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (((m.cols + 1u) * 4u + 15u) & ~15u));
+    uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + ((((m.cols + 1u) * 4u << XSH) + 15u) & ~15u));
+    // cell i of the staged query: column i >> XSH (every copy holds the same value)
+    const uint32_t n_cells = (m.cols + 1u) << XSH;
     TmaRing ring{0u, 0u, 0u, 0u};
     if constexpr (TMA) {
         const uint32_t warps = blockDim.x / kWarp, w = threadIdx.x / kWarp;
@@ -844,7 +853,7 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
     }
     pdl_trigger();   // the select kernel's CTA may be set up while this grid drains
     if (seq == 0) {
-        for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<VT>(x[i]) : 0.0f;
+        for (uint32_t i = threadIdx.x; i < n_cells; i += blockDim.x) xs[i] = ((i >> XSH) < m.cols) ? query_value<VT>(x[i >> XSH]) : 0.0f;
         __syncthreads();
         pdl_wait();  // the query was complete before the sample kernel started; tau and the counters are not
     } else {
@@ -859,11 +868,12 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
             if (stamp && blockIdx.x == 0) stamp[kStampMainBegin] = global_timer_ns();
         }
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i <= m.cols; i += blockDim.x) xs[i] = (i < m.cols) ? query_value<VT>(__ldcg(x + i)) : 0.0f;
+        for (uint32_t i = threadIdx.x; i < n_cells; i += blockDim.x) xs[i] = ((i >> XSH) < m.cols) ? query_value<VT>(__ldcg(x + (i >> XSH))) : 0.0f;
         __syncthreads();
     }
 
     const unsigned lane = lane_id();
+    const uint8_t *xs_lane = smem_raw + (XSH ? lane * 4u : 0u);   // this lane's copy
     PoolSink<CAP> sink;
     sink.buf = bufs + (threadIdx.x / kWarp) * CAP;
     sink.cnt = 0;
@@ -881,7 +891,7 @@ csr_topk_main_kernel(CsrDevice m, const float *__restrict__ x, RunState *st, uin
         if (c >= m.n_chunks) break;
         sink.tau = fmaxf(sink.tau, tau_from_key(ld_relaxed_u32(&st->tau_key)));
         if constexpr (TMA) csr_process_chunk_tma<VT>(m, smem_raw, c, sink, ring);
-        else csr_process_chunk<VT, C12>(m, smem_raw, c, 0xFFFFFFFFu, sink);
+        else csr_process_chunk<VT, C12, XSH>(m, xs_lane, c, 0xFFFFFFFFu, sink);
     }
 
     // hand the survivors to the global pool (filtered by the freshest bound)

@@ -90,6 +90,7 @@ struct Handle {
     // launch geometry of the main kernel, per CAP variant
     int main_grid[4] = {0, 0, 0, 0};
     int tma_grid = 0;                    // grid of the bulk-copy variant of the k <= 128 main kernel (TKS_TMA=1)
+    int x_grid = 0;                                                // TKS_XCOPIES=1 variant (0: does not fit, not used)
 
     // pipelined submits (tks_submit; api.cu): per-slot scratch so that consecutive queries overlap.  The sample and
     // the select kernels run on two engine-owned streams, the main kernels on the caller's; hand-over by sequence
