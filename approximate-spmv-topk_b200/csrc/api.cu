@@ -349,7 +349,11 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
     } else {
         // handles made for batched queries keep 4096: the batched kernel runs eight streams per warp, which want twice as
         // many units to balance (cfg5 main kernel 10.85 ms with 4096, 11.42 ms with 8192, r02ah)
-        h->chunk_nnz = env_u32("TKS_CHUNK_NNZ", (nnz >= (32ull << 20) && h->cfg.max_batch == 1) ? 8192u : 4096u);   // env: A/B switch
+        // 16-bit value modes reduce 512 non-zeros per warp iteration: the same 32 iterations per unit are 16384 non-zeros
+        // (cfg2h step 0.170 / 0.155 / 0.1445 ms with 4096 / 8192 / 16384, r02al)
+        uint32_t dflt = 4096u;
+        if (h->cfg.max_batch == 1 && nnz >= (32ull << 20)) dflt = (half_mode(h) && nnz >= (64ull << 20)) ? 16384u : 8192u;
+        h->chunk_nnz = env_u32("TKS_CHUNK_NNZ", dflt);   // env: A/B switch
         if (nnz >= (32ull << 20) && env_u32("TKS_CHUNK_TAIL", 0u)) chunk_small = h->chunk_nnz / 4u;
     }
     h->chunk_nnz = (h->chunk_nnz + kElemsPerIter - 1) / kElemsPerIter * kElemsPerIter;

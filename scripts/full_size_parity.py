@@ -4,6 +4,7 @@ cfg3: the 10M x 1024 gamma-20 matrix in 20-bit BS-CSR, 32 partitions x LFR 4 x l
 words (every slot of every partition) and the merged list against the oracle's literal sequential kernel, bit for
 bit, for the reference semantics and the drift-free mode, host-packed and device-packed.
 cfg2: the same matrix in fp32 -- top-100 against the reference gold restatement, slot by slot.
+cfg2h: the same with half-precision values and query (fp32 accumulation) against the gold on half-rounded inputs.
 
     python scripts/full_size_parity.py [--rows 10000000] > gpurun_out/full_size_parity.json
 
@@ -51,6 +52,16 @@ def main():
     ev, ei, cnt = src.read_result()
     out["cfg2"] = {"count": int(cnt), "same_index_set": bool(set(ei.tolist()) == set(gi.tolist())),
                    "max_rel_score_diff": float(np.max(np.abs(np.sort(ev)[::-1] - np.sort(gv)[::-1]) / np.sort(gv)[::-1]))}
+    # cfg2h: half-precision values and query (the reference's -a mode), fp32 accumulation, against the gold on
+    # half-rounded inputs; the engine is fed the same fp32 CSR and rounds it itself
+    t0 = time.time()
+    hi, hv = oracle.gold_topk_f16(x, idx, val, vec, k)
+    out["gold_f16_s"] = round(time.time() - t0, 1)
+    with tks.SpMV(ptr, idx, val, rows, cols, vec=vec, k=k, half=True) as eng:
+        eng()
+        hev, hei, hcnt = eng.read_result()
+    out["cfg2h"] = {"count": int(hcnt), "same_index_set": bool(set(hei.tolist()) == set(hi.tolist())),
+                    "max_rel_score_diff": float(np.max(np.abs(np.sort(hev)[::-1] - np.sort(hv)[::-1]) / np.sort(hv)[::-1]))}
     src.close()
 
     # cfg3: fixed point, bit for bit
@@ -77,6 +88,7 @@ def main():
                 "oracle_kernel_s": round(t_or, 1)}
     out["cfg3"] = res
     out["all_ok"] = bool(out["cfg2"]["same_index_set"] and out["cfg2"]["max_rel_score_diff"] < 1e-5 and
+                         out["cfg2h"]["same_index_set"] and out["cfg2h"]["max_rel_score_diff"] < 1e-5 and
                          all(r["result_words_identical"] and r["merged_list_identical"] for r in res.values()))
     print(json.dumps(out, indent=1))
     sys.exit(0 if out["all_ok"] else 1)

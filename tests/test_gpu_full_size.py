@@ -2,7 +2,8 @@
 oracle's literal sequential kernel over the whole matrix (about 7 s per mode on the host) and compares
   cfg3: every result word of every partition and the merged list, bit for bit -- reference semantics and drift-free
         mode, host-packed and GPU-packed packets;
-  cfg2: the fp32 top-100 against the reference gold restatement (identical index set, scores within 1e-5 relative)."""
+  cfg2: the fp32 top-100 against the reference gold restatement (identical index set, scores within 1e-5 relative);
+  cfg2h: the same in the half-precision value mode against the gold on half-rounded inputs."""
 import json
 import subprocess
 import sys
@@ -21,6 +22,7 @@ def test_full_size_cfg2_cfg3_parity(cuda_required):
     res = json.loads(out.stdout)
     assert res["nnz"] > 1.9e8 and res["all_ok"]
     assert res["cfg2"]["same_index_set"] and res["cfg2"]["max_rel_score_diff"] < 1e-5
+    assert res["cfg2h"]["same_index_set"] and res["cfg2h"]["max_rel_score_diff"] < 1e-5   # 16-bit values, fp32 sums
     assert len(res["cfg3"]) == 4
     for name, r in res["cfg3"].items():
         assert r["result_words_identical"] and r["merged_list_identical"], name
