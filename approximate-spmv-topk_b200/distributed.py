@@ -26,6 +26,17 @@ class _DevView:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
+_CUDA_STREAM_LEGACY = 1   # cudaStreamLegacy: the handle that NAMES the legacy default stream
+
+
+def _current_stream_handle(torch):
+    """torch's current stream as the C ABI wants it.  The ABI reads a NULL stream as "the handle's private stream", and
+    torch's default stream IS handle 0: named by cudaStreamLegacy instead, the engine's kernels land on the stream the
+    collectives and copies of the caller are ordered against."""
+    h = torch.cuda.current_stream().cuda_stream
+    return h if h else _CUDA_STREAM_LEGACY
+
+
 class ShardedSpMV:
     """engine: a `spmv.SpMV` holding this rank's shard (uploaded or generated with row_offset = first row).
 
@@ -88,7 +99,7 @@ class ShardedSpMV:
         """stream 0 would mean "the engine's private stream" to the C ABI, but NCCL orders its collectives against
         torch's CURRENT stream only: on the all-gather path the two must be the same stream."""
         if stream == 0 and self.world > 1 and self.exchange_mode == "nccl":
-            return self.torch.cuda.current_stream().cuda_stream
+            return _current_stream_handle(self.torch)
         return stream
 
     def submit(self, dptr, stream=0, query_ready=True):
@@ -231,7 +242,7 @@ class ShardedSpMVFixed:
             self._host = torch.empty(self.world * n, dtype=torch.int32).pin_memory()
             self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         self._ev[0].record(stream)
-        self.engine.run_async(self.k, stream.cuda_stream)
+        self.engine.run_async(self.k, _current_stream_handle(torch))
         self._ev[1].record(stream)
         self.dist.all_gather_into_tensor(self._gath, self._words, group=self.group)
         self._host.copy_(self._gath, non_blocking=True)
@@ -242,6 +253,68 @@ class ShardedSpMVFixed:
         self.val_words = allw[:, 1, :].reshape(self.P, self.Kp, 16)
         self._val, self._idx = self.capi.merge_partition_words(self.idx_words, self.val_words, self.first_row, self.B, self.k)
         return self._ev[0].elapsed_time(self._ev[1]) * 1e6
+
+    # ---- pipelined form: two queries in flight -------------------------------------------------------------------
+    def submit(self, vec32):
+        """reset(vec) + operator() without waiting: the query's copy, transform and sample run beside the previous
+        query's stream and replay kernels (tks_submit), the all-gather of the result words and ONE device-to-host copy
+        follow on torch's current stream, and the host returns at once with a ticket for fetch().  Two queries are kept
+        in flight: fetch(t) before submit() number t + 2.  Without NCCL (gloo tests, one rank without CUDA) the call
+        runs the blocking verbs and fetch() returns what they produced."""
+        self._n_sub = getattr(self, "_n_sub", 0) + 1
+        ticket = self._n_sub
+        slot = ticket % 2
+        if not hasattr(self, "_kept"):
+            self._kept = [None, None]
+        if not (self.nccl or (self.world == 1 and self.torch.cuda.is_available() and hasattr(self.engine, "submit"))):
+            self.reset(vec32)
+            self()
+            self._kept[slot] = (ticket, None, (self._val, self._idx, self.idx_words, self.val_words))
+            return ticket
+        torch = self.torch
+        stream = torch.cuda.current_stream()
+        if getattr(self, "_pslots", None) is None:
+            ptr, n = self.engine.partition_words_device()
+            self._pwords = torch.as_tensor(_DevView(ptr, (n,), "<i4"), device="cuda")
+            cols = int(self.engine.num_cols)
+            self._pslots = [dict(hq=torch.empty(cols, dtype=torch.int32).pin_memory(),
+                                 dq=torch.empty(cols, dtype=torch.int32, device="cuda"),
+                                 gath=torch.empty(self.world * n, dtype=torch.int32, device="cuda"),
+                                 host=torch.empty(self.world * n, dtype=torch.int32).pin_memory(),
+                                 done=torch.cuda.Event()) for _ in range(2)]
+        sl = self._pslots[slot]
+        if self._kept[slot] is not None:
+            sl["done"].synchronize()   # the slot's query of two submits ago was never fetched: its buffers are reused now
+        sl["hq"].numpy()[:] = np.ascontiguousarray(vec32, np.uint32).view(np.int32).reshape(-1)
+        sl["dq"].copy_(sl["hq"], non_blocking=True)
+        self.engine.submit(sl["dq"].data_ptr(), self.k, _current_stream_handle(torch))
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(sl["gath"], self._pwords, group=self.group)
+            sl["host"].copy_(sl["gath"], non_blocking=True)
+        else:
+            sl["host"].copy_(self._pwords, non_blocking=True)
+        sl["done"].record(stream)
+        self._kept[slot] = (ticket, sl, None)
+        return ticket
+
+    def fetch(self, ticket):
+        """read_result() of submit()'s `ticket`: (raw values uint32[n], GLOBAL row indices uint32[n]); also sets
+        idx_words / val_words like operator()."""
+        kept = getattr(self, "_kept", [None, None])[int(ticket) % 2]
+        if kept is None or kept[0] != ticket:
+            raise self.capi.TksError(self.capi.TKS_ESTATE, f"the result of ticket {ticket} is gone: two queries are kept")
+        self._kept[int(ticket) % 2] = None
+        _, sl, ready = kept
+        if ready is not None:
+            self._val, self._idx, self.idx_words, self.val_words = ready
+            return self._val, self._idx
+        sl["done"].synchronize()
+        per = self.ppr * self.Kp * 16
+        allw = sl["host"].numpy().view(np.uint32).reshape(self.world, 2, per).copy()
+        self.idx_words = allw[:, 0, :].reshape(self.P, self.Kp, 16)
+        self.val_words = allw[:, 1, :].reshape(self.P, self.Kp, 16)
+        self._val, self._idx = self.capi.merge_partition_words(self.idx_words, self.val_words, self.first_row, self.B, self.k)
+        return self._val, self._idx
 
     def read_result(self):
         """(raw values uint32[n], GLOBAL row indices uint32[n]), n <= k; identical on every rank."""

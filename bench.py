@@ -1208,8 +1208,8 @@ def fixed_workload(args, tks, wl, rows_total, queries, peak_gbs, peak_src, steps
 def fixed_sharded_workload(tks, torch, dist, args, world, rank, local, steps, warmup):
     """cfg3 over several GPUs (FPGA mode): the reference's 32 row partitions dealt out over the ranks
     (ShardedSpMVFixed), every step = reset(vec) -> operator() on every rank -> all-gather of the result words (32 KB in
-    total) -> the reference's host merge on every rank.  Strong scaling of the 10M-row matrix; blocking verbs (there is
-    no pipelined form of the partition exchange)."""
+    total) -> the reference's host merge on every rank, measured with the blocking verbs and, as the line's value, with
+    submit / fetch (two queries in flight).  Strong scaling of the 10M-row matrix."""
     wl = WORKLOADS["cfg3"]
     W, P, Kp, LFR = 20, 32, 8, 4
     rows, cols = wl["rows"], wl["cols"]
@@ -1239,10 +1239,29 @@ def fixed_sharded_workload(tks, torch, dist, args, world, rank, local, steps, wa
         s.reset(q32[warmup + i])
         kernel_ns.append(s())
     dt = (time.perf_counter() - t0) * 1e3 / steps
-    t = torch.tensor([dt, float(np.mean(kernel_ns)) * 1e-6], dtype=torch.float64, device="cuda")
+    v_blk, i_blk = s.read_result()
+    # throughput form: submit(vec) / fetch(ticket), two queries in flight -- the query copy, transform and sample of step
+    # i+1 overlap the kernels of step i, the all-gather and the device-to-host copy follow on the stream, and the host
+    # merge of step i runs while the device works on step i+1
+    def pipe_loop(lo, hi):
+        prev, last = None, None
+        for i in range(lo, hi):
+            t = s.submit(q32[i])
+            if prev is not None:
+                last = s.fetch(prev)
+            prev = t
+        return s.fetch(prev)
+    pipe_loop(0, warmup)
+    torch.cuda.synchronize()
+    dist.barrier()
+    aligned_start(torch, dist, world)
+    t0 = time.perf_counter()
+    v_last, i_last = pipe_loop(warmup, warmup + steps)
+    dt_pipe = (time.perf_counter() - t0) * 1e3 / steps
+    assert np.array_equal(i_last, i_blk) and np.array_equal(v_last, v_blk), "pipelined and blocking partition exchange differ"
+    t = torch.tensor([dt, float(np.mean(kernel_ns)) * 1e-6, dt_pipe], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, kernel_ms = float(t[0].item()), float(t[1].item())
-    v_last, i_last = s.read_result()
+    ms_blocking, kernel_ms, ms_step = float(t[0].item()), float(t[1].item()), float(t[2].item())
     # parity: every rank holds the same list, and it is the list ONE device holding all 32 partitions returns (rank 0
     # builds that engine beside its shard) -- which tests/test_gpu_full_size.py holds bit-exact to the oracle
     lists = [None] * world
@@ -1268,8 +1287,11 @@ def fixed_sharded_workload(tks, torch, dist, args, world, rank, local, steps, wa
             "data": "synthetic",
             "config": {"workload": wl["name"] + f", the 32 partitions dealt out over {world} GPUs ({P // world} each)", "rows": rows,
                        "cols": cols, "nnz": nnz, "k": K, "fixed_width": W, "partitions": P, "local_k": Kp, "limited_finished_rows": LFR,
-                       "step": "reset(host vec) -> operator() on every rank -> all-gather of the result words -> host merge on every rank "
-                               "(wall clock, max over ranks)", "pack_upload_s": round(pack_s, 2)},
+                       "step": "submit(host vec) -> kernels on every rank -> all-gather of the result words -> one device-to-host copy "
+                               "-> fetch(): host merge on every rank; two queries in flight (wall clock, max over ranks)",
+                       "pack_upload_s": round(pack_s, 2)},
+            "blocking": {"ms_per_step": ms_blocking, "value": nnz / (ms_blocking * 1e-3),
+                         "api": "reset(host vec) -> operator() -> read_result(), one query at a time"},
             "local_kernels_ms": kernel_ms,
             "parity_n": bool(same and flag[0]),
             "parity": {"ranks_hold_identical_results": bool(same), "equals_one_device_holding_all_partitions": flag[0],

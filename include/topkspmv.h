@@ -163,7 +163,11 @@ int tks_set_query_device(tks_handle *h, const void *d_vec, uint32_t batch, void 
 
 /* operator(): launch and wait.  k = CLI -k (options.hpp:103).  Timings optional. */
 int tks_run(tks_handle *h, uint32_t k, float *kernel_ms, float *total_ms);
-/* Enqueue only (no sync) on the caller's stream; result stays on the device.   */
+/* Enqueue only (no sync) on the caller's stream; result stays on the device.
+ * Every `cuda_stream` argument of this header is a cudaStream_t; NULL means the
+ * handle's PRIVATE (non-blocking) stream, not the default stream -- a caller
+ * whose work sits on the default stream names it with cudaStreamLegacy or
+ * cudaStreamPerThread (the Python layer does this for torch's default stream). */
 int tks_run_async(tks_handle *h, uint32_t k, void *cuda_stream);
 
 /* read_result(): sorted (score desc, tie-break).  Float mode: val_out is

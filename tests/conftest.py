@@ -67,3 +67,27 @@ def make_query(cols, seed):
 @pytest.fixture(scope="session")
 def query():
     return make_query
+
+
+def collect_from_workers(q, procs, n, timeout=300):
+    """n items from the queue of spawned rank processes; fails at once (instead of after the whole timeout) when a
+    worker has died -- its traceback is on stderr, which pytest shows with the failure."""
+    import queue as _queue
+    import time as _time
+    got, t0 = [], _time.time()
+    while len(got) < n:
+        try:
+            got.append(q.get(timeout=2))
+        except _queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead:
+                for p in procs:
+                    if p.is_alive():
+                        p.terminate()
+                raise AssertionError(f"a rank process died (exit codes {dead}); see captured stderr")
+            if _time.time() - t0 > timeout:
+                for p in procs:
+                    if p.is_alive():
+                        p.terminate()
+                raise AssertionError(f"only {len(got)} of {n} ranks reported within {timeout} s")
+    return got

@@ -69,7 +69,8 @@ def test_sharded_ranks_agree_with_global_topk(cuda_required, tks, orc, gen, batc
     procs = [ctx.Process(target=_worker, args=(r, world, port, batch, q, exchange, k)) for r in range(world)]
     for p in procs:
         p.start()
-    results = dict(q.get(timeout=300) for _ in range(world))
+    from conftest import collect_from_workers
+    results = dict(collect_from_workers(q, procs, world, 300))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -118,6 +119,20 @@ def _worker_fixed(rank, world, port, q):
         s()
         val, idx = s.read_result()
         out.append((val.copy(), idx.copy(), s.idx_words.copy(), s.val_words.copy()))
+    # pipelined form: six queries through submit / fetch with two in flight == the blocking verbs, words included
+    qs = [oracle.query_fx32_from_f32(make_query(cols, 1 + (i % 2))) for i in range(6)]
+    prev, got = None, []
+    for v32 in qs:
+        t = s.submit(v32)
+        if prev is not None:
+            val, idx = s.fetch(prev)
+            got.append((val.copy(), idx.copy(), s.idx_words.copy(), s.val_words.copy()))
+        prev = t
+    val, idx = s.fetch(prev)
+    got.append((val.copy(), idx.copy(), s.idx_words.copy(), s.val_words.copy()))
+    for i, g in enumerate(got):
+        ref = out[i % 2]
+        assert all(np.array_equal(a, b) for a, b in zip(g, ref)), f"pipelined step {i} differs from the blocking verbs"
     q.put((rank, out))
     dist.barrier()
     s.close()
@@ -137,7 +152,8 @@ def test_fixed_mode_partitions_over_ranks_equal_oracle(cuda_required, tks, orc, 
     procs = [ctx.Process(target=_worker_fixed, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = dict(q.get(timeout=300) for _ in range(world))
+    from conftest import collect_from_workers
+    results = dict(collect_from_workers(q, procs, world, 300))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0

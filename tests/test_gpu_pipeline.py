@@ -260,7 +260,8 @@ def test_pipelined_exchange_over_ranks_equals_global_topk(cuda_required, tks, or
     procs = [ctx.Process(target=_worker, args=(r, world, port, q, k, n)) for r in range(world)]
     for p in procs:
         p.start()
-    results = {r: (out, mode) for r, out, mode in (q.get(timeout=600) for _ in range(world))}
+    from conftest import collect_from_workers
+    results = {r: (out, mode) for r, out, mode in collect_from_workers(q, procs, world, 600)}
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0

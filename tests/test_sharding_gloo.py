@@ -181,6 +181,21 @@ def _worker_fixed(rank, world, port, rows, P, q):
     s.reset(oracle.query_fx32_from_f32(vec))
     s()
     val, idx = s.read_result()
+    # submit / fetch (without NCCL: the blocking verbs behind the same tickets): same lists, two queries kept
+    vec2 = rng.random(1024); vec2 = (vec2 / np.linalg.norm(vec2)).astype(np.float32)
+    t1 = s.submit(oracle.query_fx32_from_f32(vec))
+    t2 = s.submit(oracle.query_fx32_from_f32(vec2))
+    v1, i1 = s.fetch(t1)
+    assert np.array_equal(v1, val) and np.array_equal(i1, idx)
+    v2, i2 = s.fetch(t2)
+    s.reset(oracle.query_fx32_from_f32(vec2)); s()
+    vb, ib = s.read_result()
+    assert np.array_equal(v2, vb) and np.array_equal(i2, ib)
+    try:
+        s.fetch(t1)
+        raise AssertionError("a ticket can be fetched once")
+    except tks.capi.TksError:
+        pass
     q.put((rank, val.copy(), idx.copy(), s.first_row.copy(), (s.r0, s.r1)))
     dist.barrier()
     dist.destroy_process_group()
