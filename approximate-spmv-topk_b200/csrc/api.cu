@@ -347,12 +347,35 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
     if (h->cfg.chunk_nnz > 0) {
         h->chunk_nnz = (uint32_t)h->cfg.chunk_nnz;
     } else {
-        // handles made for batched queries keep 4096: the batched kernel runs eight streams per warp, which want twice as
-        // many units to balance (cfg5 main kernel 10.85 ms with 4096, 11.42 ms with 8192, r02ah)
+        // handles made for batched queries stay near 4096: the batched kernel runs eight streams per warp, which want twice
+        // as many units to balance (cfg5 main kernel 10.85 ms with 4096, 11.42 ms with 8192, r02ah)
         // 16-bit value modes reduce 512 non-zeros per warp iteration: the same 32 iterations per unit are 16384 non-zeros
         // (cfg2h step 0.170 / 0.155 / 0.1445 ms with 4096 / 8192 / 16384, r02al)
         uint32_t dflt = 4096u;
-        if (h->cfg.max_batch == 1 && nnz >= (32ull << 20)) dflt = (half_mode(h) && nnz >= (64ull << 20)) ? 16384u : 8192u;
+        if (h->cfg.max_batch == 1 && nnz >= (32ull << 20)) {
+            // The persistent warps run at the same speed, so the dynamic scheduler ends up handing every warp
+            // ceil(units / warps) units: the main kernel alone takes 0.1966 / 0.1925 / 0.2022 / 0.1923 / 0.2134 / 0.1968 ms
+            // with 8192 / 9216 / 11264 / 12288 / 16384 / 20480 non-zeros per unit on cfg2 -- exactly the order of
+            // ceil(units / 5328 warps) x unit (r02aq).  Hence: a whole number m of units per resident warp of the k <= 128
+            // main kernel, the largest m that keeps a unit at ~48 warp iterations or more (12 000 non-zeros; 24 000
+            // with 16-bit values, whose iterations are 512 non-zeros).
+            const uint64_t warps = (uint64_t)(h->main_grid[0] > 0 ? h->main_grid[0] : 2 * h->num_sms) *
+                                   (uint64_t)(cap_threads(0, value_type(h)) / 32);
+            const uint64_t per_warp = (nnz + warps - 1) / warps;
+            const uint64_t tmin = half_mode(h) ? 24000u : 12000u;
+            const uint64_t m = per_warp / tmin > 0 ? per_warp / tmin : 1u;
+            uint64_t unit = (per_warp + m - 1) / m;
+            if (unit < 4096u) unit = 4096u;
+            dflt = (uint32_t)unit;   // rounded up to whole warp iterations below
+        } else if (h->cfg.max_batch > 1 && nnz >= (32ull << 20)) {
+            // batched handles: the same rule over the batched kernel's streams (one CTA per SM, eight quads per warp, a
+            // warp takes eight units at a time and waits for the longest), at ~4096 non-zeros per unit
+            const uint64_t streams = (uint64_t)h->num_sms * (kBThreads / 32u) * kBStreams;
+            const uint64_t per_stream = (nnz + streams - 1) / streams;
+            const uint64_t m = per_stream / 4096u > 0 ? per_stream / 4096u : 1u;
+            const uint64_t unit = (per_stream + m - 1) / m;
+            dflt = (uint32_t)(unit < 2048u ? 2048u : unit);
+        }
         h->chunk_nnz = env_u32("TKS_CHUNK_NNZ", dflt);   // env: A/B switch
         if (nnz >= (32ull << 20) && env_u32("TKS_CHUNK_TAIL", 0u)) chunk_small = h->chunk_nnz / 4u;
     }
