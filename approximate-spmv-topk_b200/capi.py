@@ -37,7 +37,8 @@ class TksStats(C.Structure):
                 ("last_kernel_ms", C.c_float), ("last_total_ms", C.c_float),
                 ("last_candidates", C.c_uint32), ("launches_per_run", C.c_uint32),
                 ("last_main_kernel_ms", C.c_float), ("batched_fallbacks", C.c_uint32),
-                ("logged_candidates", C.c_uint32), ("reserved", C.c_uint32 * 5)]
+                ("logged_candidates", C.c_uint32), ("work_unit_nnz", C.c_uint32), ("work_units", C.c_uint32),
+                ("reserved", C.c_uint32 * 3)]
 
 
 class TksError(RuntimeError):

@@ -393,6 +393,8 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
     if (nch == 0) nch = 1;
     if (nch > 0xFFFFFFF0ull) return h->fail(TKS_EINVAL, "too many chunks (%llu)", (unsigned long long)nch);
     h->n_chunks = (uint32_t)nch;
+    h->stats.work_unit_nnz = h->chunk_nnz;
+    h->stats.work_units = h->n_chunks;
 
     if (half_mode(h)) {
         // the reference's half-precision mode (host_spmv_topk_csr_gpu.cu:133,152: float_to_half of every value)

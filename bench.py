@@ -615,6 +615,7 @@ def float_workload(tks, torch, dist, wl_key, args, world, rank, local, tstream, 
                                        "main kernels chained by programmatic dependent launch, select on its own stream); "
                                        "every query's three kernels complete inside the timed region") if pipelined else "none (stream order)",
                           "l2": "inputs larger than L2 (matrix %.2f GB per GPU vs 126 MB), no flush" % (nnz_local * (6 if half else 8) / 1e9),
+                          "work_unit_nnz": int(stats.work_unit_nnz), "work_units": int(stats.work_units),
                           "generator_s": round(gen_s, 2)},
                "per_step": per_step, "parity_n": parity["ok"], "parity": parity,
                "roofline": roof,

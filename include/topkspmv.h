@@ -94,7 +94,9 @@ typedef struct tks_stats {
     float last_main_kernel_ms;    /* dominant kernel alone (only with cfg.profile_kernels) */
     uint32_t batched_fallbacks;   /* batched queries re-run alone because their pool overflowed */
     uint32_t logged_candidates;   /* BS-CSR mode with profile_kernels: entries the stream kernel logged */
-    uint32_t reserved[5];
+    uint32_t work_unit_nnz;       /* float mode: non-zeros per work unit of the resident matrix */
+    uint32_t work_units;          /* float mode: number of work units                                       */
+    uint32_t reserved[3];
 } tks_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */

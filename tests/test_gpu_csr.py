@@ -408,3 +408,32 @@ def test_bf16_mode_batched_queries(cuda_required, tks, orc, cfg1):
             yref = orc.spmv_f32(x, y, orc.bf16_round(v), orc.bf16_round(vecs[q]), 10000)
             check_against_scores(idx, val, cnt, yref, 50)
             assert np.array_equal(val.view(np.uint32), yref[idx].view(np.uint32))
+
+
+@pytest.mark.parametrize("half,batch", [(False, 1), (True, 1), (False, 64)])
+def test_work_units_are_a_whole_number_per_resident_warp(cuda_required, tks, half, batch):
+    """Default work-unit sizing from 32M non-zeros on: at most m units per resident warp (stream) for a
+    whole number m, units of >= 12 000 non-zeros (24 000 with 16-bit values, ~4096 per stream of a batched handle),
+    so that no warp is handed one unit more than the others.  Smaller matrices keep 4096-non-zero units."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    rows = 2_500_000                              # gamma-20: ~4.9e7 non-zeros
+    with tks.SpMV(num_cols=1024, k=100, half=half, max_batch=batch) as s:
+        s.generate_synthetic(rows, 1024, 20, "gamma", seed=3)
+        st = s.stats()
+        nnz, unit, units = int(st.nnz), int(st.work_unit_nnz), int(st.work_units)
+        assert nnz >= 32 << 20 and units == -(-nnz // unit)
+        if batch > 1:
+            streams = sms * 24 * 8                # one 768-thread CTA per SM, eight quads per warp
+            m = max(1, (-(-nnz // streams)) // 4096)
+            assert units <= m * streams and 2048 <= unit <= 8192 + 256
+        else:
+            # resident warps of the k <= 128 main kernel: 2 x 18 per SM (fp32), 2 x 12 (16-bit values)
+            warps = sms * (24 if half else 36)
+            tmin = 24000 if half else 12000
+            m = max(1, (-(-nnz // warps)) // tmin)
+            assert units <= m * warps, (units, m, warps)
+            assert unit >= min(tmin, -(-nnz // warps)) and unit % 256 == 0
+    with tks.SpMV(num_cols=1024, k=100) as s:
+        s.generate_synthetic(200_000, 1024, 20, "gamma", seed=3)
+        assert int(s.stats().work_unit_nnz) == 4096
