@@ -500,7 +500,6 @@ void launch_sample(Handle *h, const CsrDevice &m, const float *x, RunState *st, 
     if (for_depth4 > want) want = for_depth4;
     if (want > h->n_sample_cap) want = h->n_sample_cap;
     uint32_t n_sample = h->n_chunks < want ? h->n_chunks : (uint32_t)want;
-    const uint32_t stride = h->n_chunks / n_sample;
     size_t sample_smem = ((size_t)h->cols + 1u) * 4u;
     if (sample_smem < (size_t)kHistScratchWords * 4u) sample_smem = (size_t)kHistScratchWords * 4u;
     const uint32_t sgrid = (n_sample * kWarp + threads - 1) / threads;
@@ -510,16 +509,16 @@ void launch_sample(Handle *h, const CsrDevice &m, const float *x, RunState *st, 
     const uint32_t sample_iters = (uint32_t)(si < 2 ? 2 : (si > max_si ? (max_si < 2 ? 2 : max_si) : si));
     if (use_col12(h, k)) {
         switch (value_type(h)) {
-            case TKS_VALUE_FP16: csr_sample_kernel<1, true><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
-            case TKS_VALUE_BF16: csr_sample_kernel<2, true><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
-            default: csr_sample_kernel<0, true><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
+            case TKS_VALUE_FP16: csr_sample_kernel<1, true><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, sample_iters, k, seq, stamp); break;
+            case TKS_VALUE_BF16: csr_sample_kernel<2, true><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, sample_iters, k, seq, stamp); break;
+            default: csr_sample_kernel<0, true><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, sample_iters, k, seq, stamp); break;
         }
         return;
     }
     switch (value_type(h)) {
-        case TKS_VALUE_FP16: csr_sample_kernel<1><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
-        case TKS_VALUE_BF16: csr_sample_kernel<2><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
-        default: csr_sample_kernel<0><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, stride, sample_iters, k, seq, stamp); break;
+        case TKS_VALUE_FP16: csr_sample_kernel<1><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, sample_iters, k, seq, stamp); break;
+        case TKS_VALUE_BF16: csr_sample_kernel<2><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, sample_iters, k, seq, stamp); break;
+        default: csr_sample_kernel<0><<<sgrid, threads, sample_smem, s>>>(m, x, st, sample_keys, n_sample, sample_iters, k, seq, stamp); break;
     }
 }
 

@@ -750,7 +750,7 @@ __device__ __forceinline__ uint32_t block_hist_threshold(LoadF load32, uint32_t 
 
 // --------------------------------------------------------------------------
 // Kernel 1: the sample.  Warp w reduces the first sample_iters iterations (256 non-zeros each; ~1 % of the
-// matrix in total) of chunk w*stride exactly as the main kernel will and publishes its best completed row.
+// matrix in total) of chunk w * n_chunks / n_sample exactly as the main kernel will and publishes its best completed row.
 // The k-th largest of these warp maxima is the score of k distinct real rows, hence a valid lower bound on
 // the k-th best score; the last CTA to finish derives it in one histogram pass (block_hist_threshold: the lower
 // edge of the bin that holds the k-th largest maximum -- still a lower bound) and publishes it in st->tau_key.
@@ -769,7 +769,7 @@ __device__ __forceinline__ float query_value(float x) {
 template <int VT, bool C12 = false>
 __global__ void __launch_bounds__(kSampleThreads, 4) csr_sample_kernel(CsrDevice m, const float *__restrict__ x,
                                                                      RunState *st, uint32_t *sample_keys,
-                                                                     uint32_t n_sample, uint32_t stride,
+                                                                     uint32_t n_sample,
                                                                      uint32_t sample_iters, uint32_t k, uint32_t seq,
                                                                      uint64_t *stamp) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -781,7 +781,8 @@ __global__ void __launch_bounds__(kSampleThreads, 4) csr_sample_kernel(CsrDevice
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
     if (gw < n_sample) {
         MaxSink sink{0.0f, false, neg_inf()};
-        const uint32_t c = gw * stride;
+        // sampled work units are spread evenly over the whole stream, also when units / samples is not a whole number
+        const uint32_t c = (uint32_t)(((uint64_t)gw * m.n_chunks) / n_sample);
         if (c < m.n_chunks) csr_process_chunk<VT, C12>(m, smem_raw, c, sample_iters, sink);
         uint32_t key = sink.any ? f32_to_ordered(sink.best) : 0u;
         key = __reduce_max_sync(kFull, key);
