@@ -223,3 +223,17 @@ def test_cpu_driver_runs_and_keeps_the_reference_csv_schema(gen, tmp_path):
     df = pd.read_csv(out)
     assert list(df.columns) == ["iter", "rows", "cols", "nnz", "K", "exec_time_ms"] and len(df) == 3
     assert int(df.rows[0]) == 2000 and int(df.cols[0]) == 1024 and int(df.nnz[0]) == x.size and int(df.K[0]) == 100
+
+
+def test_default_torch_stream_is_named_by_cuda_stream_legacy():
+    """The C ABI reads a NULL stream as "the handle's private stream"; torch's default stream is handle 0.  The Python
+    layer must hand it over as cudaStreamLegacy (1) so that collectives and copies on torch's stream are ordered behind
+    the engine's kernels; any other stream goes through unchanged."""
+    from types import SimpleNamespace
+    from _pkg import pkg
+    dist = pkg().distributed
+
+    def fake(handle):
+        return SimpleNamespace(cuda=SimpleNamespace(current_stream=lambda: SimpleNamespace(cuda_stream=handle)))
+    assert dist._current_stream_handle(fake(0)) == 1
+    assert dist._current_stream_handle(fake(0x7F00DEAD0000)) == 0x7F00DEAD0000
