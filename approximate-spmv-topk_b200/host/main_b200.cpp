@@ -120,6 +120,42 @@ static int run(const Options &options, coo_t<int_type, V> &coo, int_type rows, i
         std::cout << "----------------" << std::endl;
         std::cout.precision(old);
     }
+    if (options.throughput_queries > 0) {
+        // -F n: the loop above keeps ONE query in flight, like the reference's hosts.  Here n fresh queries go through
+        // the throughput verbs (submit / fetch, Engine::kInFlight queries behind); every result must equal what the
+        // blocking verbs return for the same query.  Reported on stderr so that the CSV on stdout keeps its schema.
+        const unsigned n = options.throughput_queries;
+        std::vector<std::vector<V>> qs(n, std::vector<V>(cols));
+        std::vector<std::vector<int_type>> want_idx(n);
+        std::vector<std::vector<V>> want_val(n);
+        for (unsigned i = 0; i < n; i++) {
+            create_sample_vector(qs[i].data(), (int)cols, true, false, true, options.seed ? options.seed + 1000 + (int)i : 0);
+            spmv.reset(qs[i].data(), 0);
+            spmv(0);
+            spmv.read_result(want_val[i], want_idx[i], 0);
+        }
+        std::vector<uint64_t> tickets(n);
+        std::vector<V> got_val;
+        std::vector<int_type> got_idx;
+        unsigned mismatches = 0;
+        const unsigned lag = (unsigned)Engine::kInFlight;
+        auto check = [&](unsigned i) {
+            spmv.fetch(tickets[i], got_val, got_idx);
+            bool same = got_idx.size() == want_idx[i].size();
+            for (size_t j = 0; j < got_idx.size() && same; j++) same = got_idx[j] == want_idx[i][j] && to_print(got_val[j]) == to_print(want_val[i][j]);
+            mismatches += same ? 0u : 1u;
+        };
+        auto t0 = clock_type::now();
+        for (unsigned i = 0; i < n; i++) {
+            tickets[i] = spmv.submit(qs[i].data());
+            if (i >= lag) check(i - lag);
+        }
+        for (unsigned i = (n > lag ? n - lag : 0); i < n; i++) check(i);
+        const double ms = (double)chrono::duration_cast<chrono::nanoseconds>(clock_type::now() - t0).count() / 1e6 / n;
+        std::cerr << "throughput: " << n << " queries through submit/fetch, " << ms << " ms per query, "
+                  << (double)nnz / (ms * 1e-3) / 1e9 << " Gnnz/s, results differing from the blocking verbs: " << mismatches << std::endl;
+        if (mismatches) return 2;
+    }
     (void)rows;
     return 0;
 }

@@ -67,6 +67,7 @@ struct Options {
     bool drift_free = false;
     bool device_pack = false;
     std::string cache_path;
+    unsigned throughput_queries = 0;   // -F n: after the tests, n more queries through submit / fetch (queries in flight)
 
     Options(int argc, char *argv[]) {
         static struct option long_options[] = {{"debug", no_argument, 0, 'd'},
@@ -94,9 +95,10 @@ struct Options {
                                                {"drift_free", no_argument, 0, 'D'},
                                                {"device_pack", no_argument, 0, 'P'},
                                                {"cache", required_argument, 0, 'C'},
+                                               {"in_flight", required_argument, 0, 'F'},
                                                {0, 0, 0, 0}};
         int option_index = 0, opt;
-        while ((opt = getopt_long(argc, argv, "dm:st:x:vk:rb:c:g:i:azfw:p:l:q:e:G:TDPC:", long_options, &option_index)) != EOF) {
+        while ((opt = getopt_long(argc, argv, "dm:st:x:vk:rb:c:g:i:azfw:p:l:q:e:G:TDPC:F:", long_options, &option_index)) != EOF) {
             switch (opt) {
                 case 'd': debug = true; break;
                 case 'r': reset = true; break;   // sic: the reference's -r also sets true (options.hpp:90-92)
@@ -135,6 +137,7 @@ struct Options {
                 case 'D': drift_free = true; break;
                 case 'C': cache_path = optarg; break;
                 case 'P': device_pack = true; break;
+                case 'F': throughput_queries = (unsigned)atoi(optarg); break;
                 default: break;
             }
         }

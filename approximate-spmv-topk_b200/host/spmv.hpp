@@ -71,6 +71,19 @@ struct SpMV {
         if (debug) printf("Reset took %f ms\n", ns / 1e6);
         return ns;
     }
+    // Throughput form (not in the reference, whose hosts keep one query in flight): reset + operator() without waiting,
+    // read_result by ticket.  Up to kInFlight queries are kept; fetch(t) before submit number t + kInFlight.
+    static constexpr int kInFlight = 3;
+    uint64_t submit(float *vec) {
+        uint64_t ticket = 0;
+        TKS_OR_DIE(h, tks_submit_host(h, vec, (uint32_t)k, 0, &ticket));
+        return ticket;
+    }
+    void fetch(uint64_t ticket, std::vector<float> &res, std::vector<int_type> &res_idx) {
+        res.resize(k); res_idx.resize(k);
+        uint32_t count = 0;
+        TKS_OR_DIE(h, tks_fetch(h, ticket, res_idx.data(), res.data(), &count));
+    }
 };
 
 // The same functor over SEVERAL GPUs driven by this one process (tks_group_*): rows sharded contiguously over the
@@ -127,6 +140,17 @@ struct SpMVGroup {
         long ns = (long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::high_resolution_clock::now() - t0).count();
         if (debug) printf("Reset took %f ms\n", ns / 1e6);
         return ns;
+    }
+    static constexpr int kInFlight = 3;
+    uint64_t submit(float *vec) {
+        uint64_t ticket = 0;
+        TKS_G_OR_DIE(tks_group_submit_host(g, vec, (uint32_t)k, &ticket));
+        return ticket;
+    }
+    void fetch(uint64_t ticket, std::vector<float> &res, std::vector<int_type> &res_idx) {
+        res.resize(k); res_idx.resize(k);
+        uint32_t count = 0;
+        TKS_G_OR_DIE(tks_group_fetch(g, ticket, res_idx.data(), res.data(), &count));
     }
 #undef TKS_G_OR_DIE
 };
@@ -203,5 +227,19 @@ struct SpMVFixed {
         long ns = (long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::high_resolution_clock::now() - t0).count();
         if (debug) printf("Reset took %f ms\n", ns / 1e6);
         return ns;
+    }
+    // Throughput form: two queries are kept in this mode (the merge of a query runs in fetch while the next one streams)
+    static constexpr int kInFlight = 1;
+    uint64_t submit(ufixed32 *vec) {
+        uint64_t ticket = 0;
+        TKS_OR_DIE(h, tks_submit_host(h, vec, (uint32_t)k, 0, &ticket));
+        return ticket;
+    }
+    void fetch(uint64_t ticket, std::vector<ufixed32> &res, std::vector<int_type> &res_idx) {
+        std::vector<uint32_t> idx(k), val(k);
+        uint32_t count = 0;
+        TKS_OR_DIE(h, tks_fetch(h, ticket, idx.data(), val.data(), &count));
+        res.clear(); res_idx.clear();
+        for (uint32_t i = 0; i < count; i++) { res_idx.push_back(idx[i]); res.push_back(ufixed32::from_raw(val[i])); }
     }
 };

@@ -105,3 +105,17 @@ def test_group_cli_over_several_devices_gives_the_one_device_rows(cuda_required,
         assert a["sw_res_idx"] == b["sw_res_idx"]
         assert int(b["error_val"]) == 0 and float(b["precision"]) >= 0.99
         np.testing.assert_allclose([float(v) for v in a["hw_res_val"].split(";")], [float(v) for v in b["hw_res_val"].split(";")], rtol=1e-5)
+
+
+@pytest.mark.parametrize("extra", [(), ("-a",), ("-f", "-w", 20), ("-G", "0,0")])
+def test_throughput_loop_equals_the_blocking_verbs(cuda_required, tks, mtx, extra):
+    """-F n: n more queries through the throughput verbs of the C++ functors (submit / fetch, queries in flight); the
+    executable itself compares every result with what reset + operator() + read_result return for the same query and
+    exits non-zero on a difference.  The CSV on stdout keeps its schema; the summary goes to stderr."""
+    assert EXE.exists(), "build/topk-spmv-b200 missing: run __graft_entry__.build()"
+    out = subprocess.run([str(EXE), "-m", str(mtx), "-k", "100", "-t", "2", "-e", "7", "-F", "12", *map(str, extra)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert len(list(csv.DictReader(io.StringIO(out.stdout)))) == 2
+    line = [l for l in out.stderr.splitlines() if l.startswith("throughput:")]
+    assert line and "12 queries" in line[0] and line[0].rstrip().endswith("blocking verbs: 0"), out.stderr
