@@ -339,18 +339,15 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
                           const uint32_t *d_idx, const float *d_val_src, float *d_val_adopt) {
     cudaStream_t s = h->stream;
     const size_t pad = 2048;   // over-read slack of the 256-bit streaming loads (zero filled)
-    // work units: cfg.chunk_nnz if given; else 8192 non-zeros for large streams, 4096 for small matrices.  Every chunk start
-    // costs a warp three dependent round trips (scheduler atomic, chunk table, first loads), ~2 us: cfg2 steps with 2048 /
-    // 4096 / 8192 / 16384 take 0.283 / 0.201 / 0.191 / 0.193 ms (r02af).  A tail of quarter-size chunks (TKS_CHUNK_TAIL=1),
-    // meant to let the persistent warps run dry together, costs more than it balances: 0.2041 vs 0.1915 ms (r02ag).
+    // work units: cfg.chunk_nnz if given; else sized below for large streams, 4096 non-zeros for small matrices.  Every
+    // unit start costs a warp three dependent round trips (scheduler atomic, chunk table, first loads), ~2 us: cfg2 steps
+    // with 2048 / 4096 / 8192 non-zeros per unit take 0.283 / 0.201 / 0.191 ms (r02af).  A tail of quarter-size units
+    // (TKS_CHUNK_TAIL=1), meant to let the persistent warps run dry together, costs more than it balances: 0.2041 vs
+    // 0.1915 ms (r02ag).
     uint32_t n_big = 0, chunk_small = 0;
     if (h->cfg.chunk_nnz > 0) {
         h->chunk_nnz = (uint32_t)h->cfg.chunk_nnz;
     } else {
-        // handles made for batched queries stay near 4096: the batched kernel runs eight streams per warp, which want twice
-        // as many units to balance (cfg5 main kernel 10.85 ms with 4096, 11.42 ms with 8192, r02ah)
-        // 16-bit value modes reduce 512 non-zeros per warp iteration: the same 32 iterations per unit are 16384 non-zeros
-        // (cfg2h step 0.170 / 0.155 / 0.1445 ms with 4096 / 8192 / 16384, r02al)
         uint32_t dflt = 4096u;
         if (h->cfg.max_batch == 1 && nnz >= (32ull << 20)) {
             // The persistent warps run at the same speed, so the dynamic scheduler ends up handing every warp
@@ -369,7 +366,9 @@ int build_from_device_csr(Handle *h, uint64_t rows, uint32_t cols, uint64_t nnz,
             dflt = (uint32_t)unit;   // rounded up to whole warp iterations below
         } else if (h->cfg.max_batch > 1 && nnz >= (32ull << 20)) {
             // batched handles: the same rule over the batched kernel's streams (one CTA per SM, eight quads per warp, a
-            // warp takes eight units at a time and waits for the longest), at ~4096 non-zeros per unit
+            // warp takes eight units at a time and waits for the longest), at ~4096 non-zeros per unit -- eight streams
+            // per warp want smaller units to balance (cfg5 main kernel 10.85 ms with 4096, 11.42 ms with 8192, r02ah; with
+            // the whole-number rule 10.56 ms, and 1.73 -> 1.39 ms on one rank's share of 8 GPUs, r02as)
             const uint64_t streams = (uint64_t)h->num_sms * (kBThreads / 32u) * kBStreams;
             const uint64_t per_stream = (nnz + streams - 1) / streams;
             const uint64_t m = per_stream / 4096u > 0 ? per_stream / 4096u : 1u;
